@@ -1,0 +1,183 @@
+/* methylasso_b200.h — C ABI of the B200-native MethyLasso segmentation engine.
+ *
+ * This is the drop-in boundary for the reference's Rcpp module "MethyLasso_cpp"
+ * (/root/reference/src/MethyLasso_cpp.cpp:9-31, loaded by R/zzz.R:1-3).  Each entry point
+ * below names the reference interface it replaces.  Plain pointers and sizes only; the engine
+ * owns the GPU, its streams and all device memory.  No entry point has a CPU fallback: without
+ * a CUDA device `ml_engine_create` fails and nothing else can be called.
+ *
+ * Conventions
+ *   - Every function returns 0 (ML_OK) or an error code; `ml_last_error()` gives the message of
+ *     the last failure on the calling thread.  No exception crosses the boundary.
+ *   - Batched calls take JOBS: one job = one chromosome of one data frame = one native call of the
+ *     reference (R/genome_wide.R:67-70).  A job that fails validation gets its own status code
+ *     and does not fail the batch (mirrors foreach(.errorhandling="remove"),
+ *     R/genome_wide.R:43).
+ *   - Inputs are the six int32 columns the R layer passes (signal_detection.cpp:13-15), rows of a
+ *     job sorted by (dataset, pos); `job_ptr[njobs+1]` holds CSR-style row offsets.
+ *   - Outputs are caller-allocated; sizes come from ml_result_job_sizes().
+ *   - One engine = one GPU = one host thread at a time.
+ */
+#ifndef METHYLASSO_B200_H
+#define METHYLASSO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ML_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ML_API __attribute__((visibility("default")))
+#else
+#define ML_API
+#endif
+
+/* error / status codes: one per reference error site */
+enum {
+  ML_OK = 0,
+  ML_ERR_TOO_FEW_ROWS = 1,      /* core/Observations.hpp:31  "Need at least 2 data points!" */
+  ML_ERR_SIZE_MISMATCH = 2,     /* core/Observations.hpp:33-34; src/weighted_1d_flsa.cpp:9 */
+  ML_ERR_FIRST_DATASET = 3,     /* core/Observations.hpp:40 */
+  ML_ERR_FIRST_CONDITION = 4,   /* core/Observations.hpp:41 */
+  ML_ERR_FIRST_REPLICATE = 5,   /* core/Observations.hpp:42 */
+  ML_ERR_NOT_SORTED = 6,        /* core/Observations.hpp:46 */
+  ML_ERR_DATASET_GAP = 7,       /* core/Observations.hpp:48 */
+  ML_ERR_REPLICATE_GAP = 8,     /* core/Observations.hpp:50 */
+  ML_ERR_CONDITION_GAP = 9,     /* core/Observations.hpp:52 */
+  ML_ERR_REPLICATE_START = 10,  /* core/Observations.hpp:54 */
+  ML_ERR_NEGATIVE_COUNT = 11,   /* src/MethData.hpp:18 */
+  ML_ERR_NMETH_GT_COV = 12,     /* src/MethData.hpp:19 */
+  ML_ERR_LAMBDA2 = 13,          /* core/fitter_lasso.ipp:4 */
+  ML_ERR_TWO_CONDITIONS = 14,   /* src/difference_detection.cpp:28 */
+  ML_ERR_BAD_REF = 15,          /* core/data_design_helpers.cpp:35 */
+  ML_ERR_NAN = 16,              /* core/Posterior.ipp:36 */
+  ML_ERR_TOO_FEW_PARAMS = 18,   /* reference: undefined behaviour (size()-2 underflow); refused */
+  ML_ERR_BAD_ARGUMENT = 19,
+  ML_ERR_CUDA = 100,            /* CUDA runtime failure (message has the details) */
+  ML_ERR_NO_DEVICE = 101
+};
+
+/* model = which instantiation of methylation_detection<> (src/methylation_detection.hpp:22-54) */
+enum {
+  ML_MODEL_FAST = 0,            /* Normal/Identity/UniquePositions: signal_detection_fast_R
+                                   (src/signal_detection.cpp:11-47) */
+  ML_MODEL_FULL_SIGNAL = 1,     /* BetaBinomialRate/Logit/BinnedGenome: signal_detection_R (:49-80) */
+  ML_MODEL_FULL_DIFFERENCE = 2  /* same with the difference design: difference_detection_R
+                                   (src/difference_detection.cpp:13-45) */
+};
+
+/* The arguments of the three Rcpp entry points (src/MethyLasso_cpp.cpp:13-26). */
+typedef struct {
+  double lambda2;      /* fusion penalty                                   (R default 25) */
+  double max_lambda2;  /* unused while optimize_lambda2 == 0; FAST sets lambda2 + 1 */
+  double lambda1;      /* always 0 in the reference (signal_detection.cpp:22,58) */
+  double tol_val;      /* convergence tolerance on max |delta mu|          (0.01) */
+  double bf_per_kb;    /* FULL: basis functions per kb                     (50) */
+  double hyper;        /* FULL: beta-binomial nu                           (100) */
+  uint32_t max_iter;   /* IRLS steps per iterate()          (FAST 1, FULL 30) */
+  uint32_t nouter;     /* outer iterations                  (FAST 1, FULL 20) */
+  uint32_t ref;        /* FULL_DIFFERENCE: reference condition, 1-based */
+  int32_t model;       /* ML_MODEL_* */
+  int32_t optimize_lambda2; /* must be 0 (FALSE at every reference call site) */
+  int32_t optimize_hyper;   /* must be 0 */
+} ml_params;
+
+typedef struct ml_engine ml_engine;
+typedef struct ml_batch ml_batch;    /* validated, indexed input resident in HBM */
+typedef struct ml_result ml_result;  /* outputs of one detect call, resident in HBM until copied */
+
+/* ---- engine ------------------------------------------------------------------------------ */
+ML_API int ml_abi_version(void);
+ML_API const char *ml_last_error(void);
+ML_API const char *ml_strerror(int code);
+/* device < 0: use the current CUDA device */
+ML_API int ml_engine_create(int device, ml_engine **out);
+ML_API void ml_engine_destroy(ml_engine *eng);
+/* engine knobs: "flsa_chunk", "flsa_warm", "flsa_sequential" (1 = start-to-end DP, one thread
+ * per series: the bit-faithful verification mode) */
+ML_API int ml_engine_set(ml_engine *eng, const char *key, long long value);
+/* number of kernel launches issued by this engine so far */
+ML_API long long ml_engine_launch_count(const ml_engine *eng);
+/* raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller */
+ML_API void *ml_engine_stream(ml_engine *eng);
+ML_API int ml_engine_synchronize(ml_engine *eng);
+
+/* ---- weighted_1d_flsa  (src/weighted_1d_flsa.cpp:7-21; Rcpp module line
+ *      src/MethyLasso_cpp.cpp:28) --------------------------------------------------------------
+ * beta = soft_threshold(clamp(FLSA(y, wt, lambda2), +-35), lambda1).  Host buffers. */
+ML_API int ml_weighted_1d_flsa(ml_engine *eng, int64_t n, const double *y, const double *wt,
+                        double lambda2, double lambda1, double *beta);
+/* many independent series in one call: ptr[nseries+1] element offsets, one lambda2 per series */
+ML_API int ml_weighted_1d_flsa_batch(ml_engine *eng, int nseries, const int64_t *ptr, const double *y,
+                              const double *wt, const double *lambda2, double lambda1,
+                              double *beta);
+/* same on device-resident buffers (y, wt, beta are device pointers; ptr/lambda2 host) */
+ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const int64_t *ptr,
+                                     const double *d_y, const double *d_wt, const double *lambda2,
+                                     double lambda1, double *d_beta);
+
+/* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
+ *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
+/* Copy the six columns to the GPU, validate every job (core/Observations.hpp:29-59,
+ * src/MethData.hpp:17-19) and keep them resident.  status[njobs] receives per-job codes. */
+ML_API int ml_batch_upload(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
+                    const int32_t *condition, const int32_t *replicate, const int32_t *pos,
+                    const int32_t *nmeth, const int32_t *coverage, ml_batch **out, int *status);
+ML_API void ml_batch_free(ml_batch *b);
+/* Run methylation_detection on every valid job of a resident batch.  `params` is one struct
+ * shared by all jobs.  status[njobs] (may be NULL) receives per-job codes. */
+ML_API int ml_batch_detect(ml_engine *eng, ml_batch *b, const ml_params *params, ml_result **out,
+                    int *status);
+/* upload + detect in one call (host buffers in, result handle out) */
+ML_API int ml_detect_batch(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
+                    const int32_t *condition, const int32_t *replicate, const int32_t *pos,
+                    const int32_t *nmeth, const int32_t *coverage, const ml_params *params,
+                    ml_result **out, int *status);
+
+ML_API int ml_result_njobs(const ml_result *r);
+/* sizes of job j: rows N, params per estimator P, estimators E, datasets D, status */
+ML_API int ml_result_job_sizes(const ml_result *r, int job, int64_t *n_rows, int64_t *n_params,
+                        int32_t *n_est, int32_t *n_dsets, int32_t *status);
+/* scalars of job j: converged, irls steps, dampings, outer iterations, hyper, last -log posterior */
+ML_API int ml_result_job_info(const ml_result *r, int job, int32_t *converged, int32_t *irls_steps,
+                       int32_t *dampings, int32_t *outer_iters, double *hyper, double *mlogp);
+/* The List the Rcpp entry points return (src/methylation_detection.hpp:47-53,
+ * src/methylation_helpers.hpp:25-49): mu[N], lambda2[E], offset[D] and the estimates table of E*P
+ * rows (estimate_id, start, beta, betahat, pseudoweight).  Any pointer may be NULL to skip it. */
+ML_API int ml_result_copy_job(ml_engine *eng, const ml_result *r, int job, double *mu, double *lambda2,
+                       double *offset, int32_t *estimate_id, double *start, double *beta,
+                       double *betahat, double *pseudoweight);
+/* All jobs at once, concatenated in job order (failed jobs contribute nothing): one D2H per column. */
+ML_API int ml_result_copy_all(ml_engine *eng, const ml_result *r, double *mu, double *offset,
+                       int32_t *estimate_id, double *start, double *beta, double *betahat,
+                       double *pseudoweight);
+ML_API void ml_result_free(ml_result *r);
+
+/* R/fast_diff.R:15-28 applied in place to a FAST result with >= 2 estimators: estimates of
+ * conditions 2.. become differences to condition 1 (beta - beta_ref, pooled betahat, summed
+ * pseudoweight). */
+ML_API int ml_result_fast_diff_combine(ml_engine *eng, ml_result *r);
+
+/* ---- segment_methylation_helper (src/methylation_helpers.cpp:6-72; Rcpp module line
+ *      src/MethyLasso_cpp.cpp:21) --------------------------------------------------------------
+ * Host table in (n rows sorted by estimate_id, start), caller-allocated outputs of capacity n;
+ * *n_segments receives the number of segments written. */
+ML_API int ml_segment_methylation_helper(ml_engine *eng, int64_t n, const int32_t *estimate_id,
+                                  const int32_t *start, const double *beta, const double *betahat,
+                                  const double *pseudoweight, double tol_val, int64_t *n_segments,
+                                  int32_t *seg_estimate_id, int32_t *seg_id, uint32_t *seg_start,
+                                  uint32_t *seg_end, double *seg_beta, double *seg_betahat,
+                                  double *seg_pseudoweight, double *seg_stdev);
+/* The same on the estimates of a resident result (no D2H/H2D of the per-CpG table): segments of
+ * all valid jobs concatenated, seg_job[] gives the job of each.  Query with outputs NULL to get
+ * *n_segments, then call again with buffers of that capacity. */
+ML_API int ml_result_segments(ml_engine *eng, ml_result *r, double tol_val, int64_t *n_segments,
+                       int32_t *seg_job, int32_t *seg_estimate_id, int32_t *seg_id,
+                       uint32_t *seg_start, uint32_t *seg_end, double *seg_beta,
+                       double *seg_betahat, double *seg_pseudoweight, double *seg_stdev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

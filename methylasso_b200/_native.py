@@ -1,0 +1,80 @@
+"""ctypes loader for libmethylasso_b200.so (the C ABI of include/methylasso_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present the import of
+the library / creation of an engine raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmethylasso_b200.so")
+
+ABI_VERSION = 1
+
+
+class MlParams(C.Structure):
+    """ml_params (include/methylasso_b200.h)."""
+    _fields_ = [("lambda2", C.c_double), ("max_lambda2", C.c_double), ("lambda1", C.c_double),
+                ("tol_val", C.c_double), ("bf_per_kb", C.c_double), ("hyper", C.c_double),
+                ("max_iter", C.c_uint32), ("nouter", C.c_uint32), ("ref", C.c_uint32),
+                ("model", C.c_int32), ("optimize_lambda2", C.c_int32), ("optimize_hyper", C.c_int32)]
+
+
+# every symbol the header declares, with (restype, argtypes)
+_P = C.c_void_p
+_I64P = C.POINTER(C.c_int64)
+SIGNATURES = {
+    "ml_abi_version": (C.c_int, []),
+    "ml_last_error": (C.c_char_p, []),
+    "ml_strerror": (C.c_char_p, [C.c_int]),
+    "ml_engine_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "ml_engine_destroy": (None, [_P]),
+    "ml_engine_set": (C.c_int, [_P, C.c_char_p, C.c_longlong]),
+    "ml_engine_launch_count": (C.c_longlong, [_P]),
+    "ml_engine_stream": (_P, [_P]),
+    "ml_engine_synchronize": (C.c_int, [_P]),
+    "ml_weighted_1d_flsa": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, C.c_double, _P]),
+    "ml_weighted_1d_flsa_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
+    "ml_weighted_1d_flsa_batch_device": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
+    "ml_batch_upload": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P), _P]),
+    "ml_batch_free": (None, [_P]),
+    "ml_batch_detect": (C.c_int, [_P, _P, C.POINTER(MlParams), C.POINTER(_P), _P]),
+    "ml_detect_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlParams),
+                                  C.POINTER(_P), _P]),
+    "ml_result_njobs": (C.c_int, [_P]),
+    "ml_result_job_sizes": (C.c_int, [_P, C.c_int, _I64P, _I64P, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "ml_result_job_info": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ml_result_copy_job": (C.c_int, [_P, _P, C.c_int] + [_P] * 8),
+    "ml_result_copy_all": (C.c_int, [_P, _P] + [_P] * 7),
+    "ml_result_free": (None, [_P]),
+    "ml_result_fast_diff_combine": (C.c_int, [_P, _P]),
+    "ml_segment_methylation_helper": (C.c_int, [_P, C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 8),
+    "ml_result_segments": (C.c_int, [_P, _P, C.c_double, _I64P] + [_P] * 9),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library and bind every declared symbol (raises if anything is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m methylasso_b200.build` "
+            "(nvcc, sm_100a). methylasso_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ml_abi_version() != ABI_VERSION:
+        raise ImportError("libmethylasso_b200.so ABI version mismatch")
+    _lib = lib
+    return lib

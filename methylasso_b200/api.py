@@ -1,0 +1,412 @@
+"""Host-side mirror of the reference's native interface, on top of the C ABI.
+
+Same names, argument meaning, defaults and error behaviour as the five functions of the Rcpp
+module `MethyLasso_cpp` (/root/reference/src/MethyLasso_cpp.cpp:13-28) and of the R wrappers that
+loop over chromosomes (/root/reference/R/genome_wide.R:38-135, R/fast_diff.R:12-30).  A "data
+frame" is a mapping of column name -> 1-D array (a pandas DataFrame works too); results are dicts
+with the reference's list element names.
+
+The genome-wide wrappers hand ALL chromosomes to the engine in one batched native call instead of
+forking one R worker per chromosome (fork + CUDA do not mix).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from ._native import MlParams
+
+MODEL_FAST, MODEL_FULL_SIGNAL, MODEL_FULL_DIFFERENCE = 0, 1, 2
+_COLUMNS = ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")
+
+
+class MethyLassoError(RuntimeError):
+    """An R-level error of the reference (Rcpp::stop / std::invalid_argument)."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = int(code)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    # R hands Nmeth / coverage as doubles sometimes (MethyLasso.R:266-277); Rcpp coerces to int
+    return np.ascontiguousarray(np.asarray(a), dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float64)
+
+
+class Engine:
+    """One GPU, one stream.  Creating it without a CUDA device raises (no CPU path)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = _native.load()
+        h = C.c_void_p()
+        rc = self.lib.ml_engine_create(int(device), C.byref(h))
+        if rc:
+            raise MethyLassoError(rc, self.lib.ml_last_error().decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ml_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise MethyLassoError(rc, self.lib.ml_last_error().decode())
+
+    def set(self, key: str, value: int):
+        self._check(self.lib.ml_engine_set(self.h, key.encode(), int(value)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ml_engine_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.ml_engine_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.ml_engine_synchronize(self.h))
+
+    # ---- weighted_1d_flsa ---------------------------------------------------------------------
+    def weighted_1d_flsa(self, y, wt, lambda2, lambda1=0.0):
+        y, wt = _f64(y), _f64(wt)
+        if y.size != wt.size:  # src/weighted_1d_flsa.cpp:9
+            raise MethyLassoError(2, "Input vectors must be of same size!")
+        beta = np.empty_like(y)
+        self._check(self.lib.ml_weighted_1d_flsa(self.h, y.size, _p(y), _p(wt), float(lambda2),
+                                                 float(lambda1), _p(beta)))
+        return beta
+
+    def weighted_1d_flsa_batch(self, ptr, y, wt, lambda2, lambda1=0.0):
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        y, wt = _f64(y), _f64(wt)
+        lam = _f64(np.broadcast_to(lambda2, (ptr.size - 1,)))
+        beta = np.empty_like(y)
+        self._check(self.lib.ml_weighted_1d_flsa_batch(self.h, ptr.size - 1, _p(ptr), _p(y), _p(wt), _p(lam),
+                                                       float(lambda1), _p(beta)))
+        return beta
+
+    # ---- detection ------------------------------------------------------------------------------
+    def upload(self, job_ptr, cols) -> "Batch":
+        job_ptr = np.ascontiguousarray(job_ptr, dtype=np.int64)
+        arrs = [_i32(cols[k]) for k in _COLUMNS]
+        h = C.c_void_p()
+        self._check(self.lib.ml_batch_upload(self.h, job_ptr.size - 1, _p(job_ptr), *[_p(a) for a in arrs],
+                                             C.byref(h), None))
+        return Batch(self, h, job_ptr.size - 1)
+
+    def detect(self, batch: "Batch", params: MlParams) -> "Result":
+        h = C.c_void_p()
+        status = np.zeros(max(batch.njobs, 1), np.int32)
+        self._check(self.lib.ml_batch_detect(self.h, batch.h, C.byref(params), C.byref(h), _p(status)))
+        return Result(self, h, status[:batch.njobs].copy())
+
+    def detect_batch(self, job_ptr, cols, params: MlParams) -> "Result":
+        """upload + detect through the single host-buffer entry point (ml_detect_batch)."""
+        job_ptr = np.ascontiguousarray(job_ptr, dtype=np.int64)
+        arrs = [_i32(cols[k]) for k in _COLUMNS]
+        nj = job_ptr.size - 1
+        h = C.c_void_p()
+        status = np.zeros(max(nj, 1), np.int32)
+        self._check(self.lib.ml_detect_batch(self.h, nj, _p(job_ptr), *[_p(a) for a in arrs],
+                                             C.byref(params), C.byref(h), _p(status)))
+        return Result(self, h, status[:nj].copy())
+
+    # ---- segment_methylation_helper -------------------------------------------------------------
+    def segment_methylation_helper(self, df, tol_val=0.01):
+        idx, start = _i32(df["estimate_id"]), _i32(df["start"])
+        beta, bh, pw = _f64(df["beta"]), _f64(df["betahat"]), _f64(df["pseudoweight"])
+        n = idx.size
+        out = _seg_buffers(n, with_job=False)
+        ns = C.c_int64(0)
+        self._check(self.lib.ml_segment_methylation_helper(
+            self.h, n, _p(idx), _p(start), _p(beta), _p(bh), _p(pw), float(tol_val), C.byref(ns),
+            *[_p(out[k]) for k in _SEG_COLS]))
+        return {k: v[:ns.value].copy() for k, v in out.items()}
+
+
+_SEG_COLS = ("estimate_id", "segment_id", "start", "end", "beta", "betahat", "pseudoweight", "stdev")
+
+
+def _seg_buffers(n, with_job):
+    out = dict(estimate_id=np.empty(n, np.int32), segment_id=np.empty(n, np.int32),
+               start=np.empty(n, np.uint32), end=np.empty(n, np.uint32), beta=np.empty(n),
+               betahat=np.empty(n), pseudoweight=np.empty(n), stdev=np.empty(n))
+    if with_job:
+        out = dict(job=np.empty(n, np.int32), **out)
+    return out
+
+
+class Batch:
+    def __init__(self, eng, h, njobs):
+        self.eng, self.h, self.njobs = eng, h, njobs
+
+    def free(self):
+        if self.h:
+            self.eng.lib.ml_batch_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    """Outputs of one detect call, resident on the GPU until copied."""
+
+    def __init__(self, eng, h, status):
+        self.eng, self.h, self.status = eng, h, status
+        self.njobs = status.size
+
+    def free(self):
+        if self.h:
+            self.eng.lib.ml_result_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def sizes(self, job):
+        n, p = C.c_int64(), C.c_int64()
+        e, d, s = C.c_int32(), C.c_int32(), C.c_int32()
+        self.eng._check(self.eng.lib.ml_result_job_sizes(self.h, job, C.byref(n), C.byref(p), C.byref(e),
+                                                         C.byref(d), C.byref(s)))
+        return n.value, p.value, e.value, d.value, s.value
+
+    def info(self, job):
+        v = [C.c_int32() for _ in range(4)]
+        hy, ml = C.c_double(), C.c_double()
+        self.eng._check(self.eng.lib.ml_result_job_info(self.h, job, *[C.byref(x) for x in v], C.byref(hy),
+                                                        C.byref(ml)))
+        return dict(converged=bool(v[0].value), irls_steps=v[1].value, dampings=v[2].value,
+                    outer_iters=v[3].value, hyper=hy.value, mlogp=ml.value)
+
+    def job(self, job, want_mu=True):
+        """The Rcpp List of one job (src/methylation_detection.hpp:47-53)."""
+        n, P, E, D, status = self.sizes(job)
+        if status:
+            raise MethyLassoError(status, self.eng.lib.ml_strerror(status).decode())
+        mu = np.empty(n) if want_mu else None
+        lam, off = np.empty(E), np.empty(D)
+        est = dict(estimate_id=np.empty(E * P, np.int32), start=np.empty(E * P), beta=np.empty(E * P),
+                   betahat=np.empty(E * P), pseudoweight=np.empty(E * P))
+        self.eng._check(self.eng.lib.ml_result_copy_job(
+            self.h_eng(), self.h, job, _p(mu), _p(lam), _p(off), _p(est["estimate_id"]), _p(est["start"]),
+            _p(est["beta"]), _p(est["betahat"]), _p(est["pseudoweight"])))
+        out = dict(mu=mu, lambda2=lam, offset=off, estimates=est, n_params=P, n_est=E, n_dsets=D)
+        out.update(self.info(job))
+        return out
+
+    def h_eng(self):
+        return self.eng.h
+
+    def fast_diff_combine(self):
+        self.eng._check(self.eng.lib.ml_result_fast_diff_combine(self.eng.h, self.h))
+
+    def segments(self, tol_val=0.01):
+        """segment_methylation_helper on the resident estimates of every valid job."""
+        ns = C.c_int64(0)
+        self.eng._check(self.eng.lib.ml_result_segments(self.eng.h, self.h, float(tol_val), C.byref(ns),
+                                                        *([None] * 9)))
+        out = _seg_buffers(max(ns.value, 1), with_job=True)
+        self.eng._check(self.eng.lib.ml_result_segments(
+            self.eng.h, self.h, float(tol_val), C.byref(ns), _p(out["job"]),
+            *[_p(out[k]) for k in _SEG_COLS]))
+        return {k: v[:ns.value].copy() for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# module-level mirror of the Rcpp module (one shared engine on the current device)
+# ---------------------------------------------------------------------------------------------
+_engine = None
+
+
+def default_engine() -> Engine:
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+    return _engine
+
+
+def _columns(data):
+    missing = [k for k in _COLUMNS if k not in data]
+    if missing:  # src/signal_detection.cpp:13-15
+        raise MethyLassoError(19, "data should contain columns dataset, condition, replicate, pos, "
+                                  "Nmeth and coverage!")
+    return {k: data[k] for k in _COLUMNS}
+
+
+def _single(data, params, engine=None):
+    eng = engine or default_engine()
+    cols = _columns(data)
+    n = len(cols["pos"])
+    res = eng.detect_batch(np.array([0, n], np.int64), cols, params)
+    try:
+        return res.job(0)
+    finally:
+        res.free()
+
+
+def signal_detection_fast_singlechr(data, lambda2=50, tol_val=0.01, max_iter=1, engine=None):
+    """src/signal_detection.cpp:11-47 (module defaults src/MethyLasso_cpp.cpp:18-19)."""
+    p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
+    r = _single(data, p, engine)
+    return {"mu": r["mu"], "lambda2": r["lambda2"], "converged": r["converged"], "offset": r["offset"],
+            "estimates": r["estimates"], "detection.type": "signal", "model": "normal",
+            "_info": {k: r[k] for k in ("irls_steps", "dampings", "outer_iters", "mlogp")}}
+
+
+def signal_detection_singlechr(data, optimize_lambda2=False, lambda2=50, max_lambda2=1000,
+                               optimize_hyper=False, hyper=100, nouter=20, bf_per_kb=50, tol_val=0.01,
+                               max_iter=30, engine=None):
+    """src/signal_detection.cpp:49-80 (module defaults src/MethyLasso_cpp.cpp:13-16)."""
+    p = MlParams(lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, 1,
+                 MODEL_FULL_SIGNAL, int(bool(optimize_lambda2)), int(bool(optimize_hyper)))
+    r = _single(data, p, engine)
+    return {"mu": r["mu"], "lambda2": r["lambda2"], "hyper": np.array([r["hyper"]]),
+            "converged": r["converged"], "offset": r["offset"], "estimates": r["estimates"],
+            "detection.type": "signal", "model": "beta-binomial",
+            "_info": {k: r[k] for k in ("irls_steps", "dampings", "outer_iters", "mlogp")}}
+
+
+def difference_detection_singlechr(data, ref, optimize_lambda2=False, lambda2=50, max_lambda2=1000,
+                                   optimize_hyper=False, hyper=100, nouter=20, bf_per_kb=50, tol_val=0.01,
+                                   max_iter=30, engine=None):
+    """src/difference_detection.cpp:13-45 (module defaults src/MethyLasso_cpp.cpp:23-26)."""
+    p = MlParams(lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, int(ref),
+                 MODEL_FULL_DIFFERENCE, int(bool(optimize_lambda2)), int(bool(optimize_hyper)))
+    r = _single(data, p, engine)
+    return {"mu": r["mu"], "lambda2": r["lambda2"], "hyper": np.array([r["hyper"]]),
+            "converged": r["converged"], "offset": r["offset"], "estimates": r["estimates"],
+            "ref.cond": int(ref), "detection.type": "difference", "model": "beta-binomial",
+            "_info": {k: r[k] for k in ("irls_steps", "dampings", "outer_iters", "mlogp")}}
+
+
+def segment_methylation_helper(df, tol_val=0.01, engine=None):
+    """src/methylation_helpers.cpp:6-72 (module line src/MethyLasso_cpp.cpp:21)."""
+    return (engine or default_engine()).segment_methylation_helper(df, tol_val)
+
+
+def weighted_1d_flsa(y, wt, lambda2, lambda1=0, engine=None):
+    """src/weighted_1d_flsa.cpp:7-21 (module line src/MethyLasso_cpp.cpp:28)."""
+    return (engine or default_engine()).weighted_1d_flsa(y, wt, lambda2, lambda1)
+
+
+def difference_detection_fast_singlechr(data, ref, lambda2=25, tol_val=0.01, max_iter=1, engine=None):
+    """R/fast_diff.R:12-30: FAST fit of all conditions, then differences to condition 1 on the GPU."""
+    eng = engine or default_engine()
+    cols = _columns(data)
+    p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
+    res = eng.detect_batch(np.array([0, len(cols["pos"])], np.int64), cols, p)
+    try:
+        res.sizes(0)
+        if res.status[0] == 0:
+            res.fast_diff_combine()
+        r = res.job(0)
+    finally:
+        res.free()
+    return {"mu": r["mu"], "lambda2": r["lambda2"], "converged": r["converged"], "offset": r["offset"],
+            "estimates": r["estimates"], "detection.type": "difference", "model": "normal",
+            "ref.cond": ref}
+
+
+# ---- genome-wide wrappers (R/genome_wide.R): one batched native call over all chromosomes -------
+def split_by_chr(data):
+    """Rows grouped by chromosome in order of first appearance (data[,unique(chr)])."""
+    chr_col = np.asarray(data["chr"])
+    _, first, inv = np.unique(chr_col, return_index=True, return_inverse=True)
+    order = np.argsort(first)                    # unique() keeps first-appearance order in R
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    job_of_row = rank[inv]
+    perm = np.argsort(job_of_row, kind="stable")
+    counts = np.bincount(job_of_row, minlength=order.size)
+    ptr = np.zeros(order.size + 1, np.int64)
+    np.cumsum(counts, out=ptr[1:])
+    cols = {k: np.asarray(data[k])[perm] for k in _COLUMNS}
+    names = chr_col[first[order]]
+    return names, ptr, cols, perm
+
+
+def _genome_wide(data, params, detection_type, model, engine=None, combine_diff=False, ref=None,
+                 verbose=False):
+    eng = engine or default_engine()
+    names, ptr, cols, perm = split_by_chr(data)
+    res = eng.detect_batch(ptr, cols, params)
+    try:
+        if combine_diff:
+            res.fast_diff_combine()
+        ok = [j for j in range(res.njobs) if res.status[j] == 0]
+        missing = [str(names[j]) for j in range(res.njobs) if res.status[j] != 0]
+        if missing and verbose:  # foreach(.errorhandling="remove") + warning (R/genome_wide.R:51-52)
+            print("Warning: the following chromosomes did not work:", " ".join(missing))
+        jobs = [res.job(j) for j in ok]
+    finally:
+        res.free()
+    # combine_ret (R/genome_wide.R:6-15)
+    est = {k: np.concatenate([r["estimates"][k] for r in jobs]) if jobs else np.empty(0)
+           for k in ("estimate_id", "start", "beta", "betahat", "pseudoweight")}
+    est["chr"] = np.concatenate([np.repeat(names[j], jobs[i]["estimates"]["beta"].size)
+                                 for i, j in enumerate(ok)]) if jobs else np.empty(0, dtype=object)
+    ret = {"mu": np.concatenate([r["mu"] for r in jobs]) if jobs else np.empty(0),
+           "lambda2": np.concatenate([r["lambda2"] for r in jobs]) if jobs else np.empty(0),
+           "converged": np.array([r["converged"] for r in jobs], bool),
+           "offset": np.concatenate([r["offset"] for r in jobs]) if jobs else np.empty(0),
+           "estimates": est, "chr": np.array([names[j] for j in ok]),
+           "detection.type": detection_type, "model": model}
+    if model == "beta-binomial":
+        ret["hyper"] = np.array([r["hyper"] for r in jobs])
+    if ref is not None:
+        ret["ref.cond"] = ref
+    return ret
+
+
+def signal_detection_fast(data, lambda2=25, tol_val=0.01, max_iter=1, ncores=1, verbose=True, engine=None):
+    """R/genome_wide.R:64-78.  `ncores` is accepted and ignored: chromosomes are batched on the GPU."""
+    p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
+    return _genome_wide(data, p, "signal", "normal", engine, verbose=verbose)
+
+
+def signal_detection(data, optimize_lambda2=False, lambda2=25, max_lambda2=1000, optimize_hyper=False,
+                     hyper=100, nouter=20, bf_per_kb=50, tol_val=0.01, max_iter=30, ncores=1, engine=None):
+    """R/genome_wide.R:38-54."""
+    p = MlParams(lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, 1,
+                 MODEL_FULL_SIGNAL, int(bool(optimize_lambda2)), int(bool(optimize_hyper)))
+    return _genome_wide(data, p, "signal", "beta-binomial", engine, verbose=True)
+
+
+def difference_detection(data, ref, optimize_lambda2=False, lambda2=25, max_lambda2=1000,
+                         optimize_hyper=False, hyper=100, nouter=20, bf_per_kb=50, tol_val=0.01,
+                         max_iter=30, ncores=1, engine=None):
+    """R/genome_wide.R:91-107."""
+    p = MlParams(lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, int(ref),
+                 MODEL_FULL_DIFFERENCE, int(bool(optimize_lambda2)), int(bool(optimize_hyper)))
+    return _genome_wide(data, p, "difference", "beta-binomial", engine, ref=int(ref), verbose=True)
+
+
+def difference_detection_fast(data, ref, lambda2=25, tol_val=0.01, max_iter=1, ncores=1, verbose=True,
+                              engine=None):
+    """R/genome_wide.R:121-135 + R/fast_diff.R:12-30."""
+    p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
+    return _genome_wide(data, p, "difference", "normal", engine, combine_diff=True, ref=ref, verbose=verbose)

@@ -1,0 +1,399 @@
+// capi.cu — the C ABI of include/methylasso_b200.h: argument checking, error translation and the
+// host<->device copies at the boundary.  All compute is in flsa.cu / detect.cu / segment.cu.
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/methylasso_b200.h"
+#include "detect.cuh"
+#include "segment.cuh"
+
+using namespace ml;
+
+struct ml_engine { Engine e; };
+struct ml_batch { std::unique_ptr<Batch> b; };
+struct ml_result { std::unique_ptr<Result> r; };
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define ML_TRY try {
+#define ML_CATCH                                                        \
+  }                                                                     \
+  catch (const MlError& e) { return fail(e.code, e.what()); }           \
+  catch (const std::bad_alloc&) { return fail(ML_ERR_CUDA, "host allocation failed"); } \
+  catch (const std::exception& e) { return fail(ML_ERR_BAD_ARGUMENT, e.what()); }
+
+static_assert(sizeof(ml_params) == sizeof(Params), "ml_params / Params layout mismatch");
+
+extern "C" {
+
+int ml_abi_version(void) { return ML_ABI_VERSION; }
+const char* ml_last_error(void) { return g_err.c_str(); }
+
+const char* ml_strerror(int code) {
+  switch (code) {
+    case ML_OK: return "ok";
+    case ML_ERR_TOO_FEW_ROWS: return "Need at least 2 data points!";
+    case ML_ERR_SIZE_MISMATCH: return "Input vectors must be of same size!";
+    case ML_ERR_FIRST_DATASET: return "First dataset ID must be 1";
+    case ML_ERR_FIRST_CONDITION: return "First condition ID must be 1";
+    case ML_ERR_FIRST_REPLICATE: return "First replicate ID must be 1";
+    case ML_ERR_NOT_SORTED: return "data is not sorted by dataset and position";
+    case ML_ERR_DATASET_GAP: return "dataset IDs must start at 1 and increase without gaps";
+    case ML_ERR_REPLICATE_GAP: return "replicate ID must increase without gaps within the same condition";
+    case ML_ERR_CONDITION_GAP: return "condition ID must start at 1 and increase without gaps";
+    case ML_ERR_REPLICATE_START: return "replicate ID must start at 1 within the same condition";
+    case ML_ERR_NEGATIVE_COUNT: return "Read counts should be >=0 !";
+    case ML_ERR_NMETH_GT_COV: return "Number of methylated reads cannot be larger than number of total reads!";
+    case ML_ERR_LAMBDA2: return "lambda2 should be >0";
+    case ML_ERR_TWO_CONDITIONS: return "Needs at least two conditions!";
+    case ML_ERR_BAD_REF: return "Invalid reference dataset!";
+    case ML_ERR_NAN: return "NaN found, aborting...";
+    case ML_ERR_TOO_FEW_PARAMS: return "fewer than 2 parameters (reference behaviour undefined)";
+    case ML_ERR_BAD_ARGUMENT: return "bad argument";
+    case ML_ERR_CUDA: return "CUDA failure";
+    case ML_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown error";
+  }
+}
+
+int ml_engine_create(int device, ml_engine** out) {
+  if (!out) return fail(ML_ERR_BAD_ARGUMENT, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(ML_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                      (ce != cudaSuccess ? cudaGetErrorString(ce) : "count = 0") +
+                                      "); this engine has no CPU path");
+  ML_TRY
+  auto* h = new ml_engine();
+  std::unique_ptr<ml_engine> guard(h);
+  if (device < 0) ML_CUDA(cudaGetDevice(&device));
+  if (device >= count) throw MlError(ML_ERR_BAD_ARGUMENT, "device ordinal out of range");
+  ML_CUDA(cudaSetDevice(device));
+  h->e.device = device;
+  cudaDeviceProp prop;
+  ML_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    throw MlError(ML_ERR_NO_DEVICE, "this library is built for sm_100a only; found sm_" +
+                                        std::to_string(prop.major) + std::to_string(prop.minor));
+  h->e.sm_count = prop.multiProcessorCount;
+  ML_CUDA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
+  // keep freed blocks in the pool: steady-state calls never reach the driver allocator
+  cudaMemPool_t pool;
+  ML_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = ~0ull;
+  ML_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  if (const char* s = getenv("ML_FLSA_CHUNK")) h->e.flsa_chunk = atoi(s);
+  if (const char* s = getenv("ML_FLSA_WARM")) h->e.flsa_warm = atoi(s);
+  if (const char* s = getenv("ML_FLSA_SEQUENTIAL")) h->e.flsa_sequential = atoi(s);
+  *out = guard.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+void ml_engine_destroy(ml_engine* eng) {
+  if (!eng) return;
+  cudaSetDevice(eng->e.device);
+  if (eng->e.stream) {
+    cudaStreamSynchronize(eng->e.stream);
+    cudaStreamDestroy(eng->e.stream);
+  }
+  delete eng;
+}
+
+int ml_engine_set(ml_engine* eng, const char* key, long long value) {
+  if (!eng || !key) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  const std::string k(key);
+  if (k == "flsa_chunk") eng->e.flsa_chunk = (int)value;
+  else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
+  else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
+  else return fail(ML_ERR_BAD_ARGUMENT, "unknown engine key: " + k);
+  return ML_OK;
+}
+
+long long ml_engine_launch_count(const ml_engine* eng) { return eng ? eng->e.launches : 0; }
+void* ml_engine_stream(ml_engine* eng) { return eng ? (void*)eng->e.stream : nullptr; }
+int ml_engine_synchronize(ml_engine* eng) {
+  if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  return ML_OK;
+  ML_CATCH
+}
+
+// ---- weighted_1d_flsa -----------------------------------------------------------------------------
+static void flsa_batch_device(Engine& e, int nseries, const int64_t* ptr, const double* d_y,
+                              const double* d_w, const double* lambda2, double lambda1, double* d_beta) {
+  std::vector<FlsaSeries> series(nseries);
+  for (int s = 0; s < nseries; ++s) {
+    const int64_t n = ptr[s + 1] - ptr[s];
+    if (n < 0 || n > 0x7fffffff) throw MlError(ML_ERR_BAD_ARGUMENT, "series length out of range");
+    series[s] = FlsaSeries{ptr[s], (int32_t)n, lambda2[s]};
+  }
+  FlsaPlan plan(e, series, ptr[nseries]);
+  plan.solve(d_y, d_w, d_beta, 1, lambda1, nullptr);
+  ML_CUDA(cudaStreamSynchronize(e.stream));
+}
+
+int ml_weighted_1d_flsa_batch_device(ml_engine* eng, int nseries, const int64_t* ptr, const double* d_y,
+                                     const double* d_wt, const double* lambda2, double lambda1,
+                                     double* d_beta) {
+  if (!eng || !ptr || !lambda2 || nseries < 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  if (nseries == 0 || ptr[nseries] == 0) return ML_OK;
+  flsa_batch_device(eng->e, nseries, ptr, d_y, d_wt, lambda2, lambda1, d_beta);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_weighted_1d_flsa_batch(ml_engine* eng, int nseries, const int64_t* ptr, const double* y,
+                              const double* wt, const double* lambda2, double lambda1, double* beta) {
+  if (!eng || !ptr || !lambda2 || nseries < 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  if (nseries == 0) return ML_OK;
+  const int64_t total = ptr[nseries];
+  if (total == 0) return ML_OK;
+  if (!y || !wt || !beta) throw MlError(ML_ERR_BAD_ARGUMENT, "NULL data pointer");
+  cudaStream_t st = eng->e.stream;
+  DevBuf<double> d_y(st, (size_t)total), d_w(st, (size_t)total), d_b(st, (size_t)total);
+  d_y.upload(y, (size_t)total);
+  d_w.upload(wt, (size_t)total);
+  flsa_batch_device(eng->e, nseries, ptr, d_y.p, d_w.p, lambda2, lambda1, d_b.p);
+  d_b.download(beta, (size_t)total);
+  ML_CUDA(cudaStreamSynchronize(st));
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_weighted_1d_flsa(ml_engine* eng, int64_t n, const double* y, const double* wt, double lambda2,
+                        double lambda1, double* beta) {
+  if (n < 0) return fail(ML_ERR_BAD_ARGUMENT, "n < 0");
+  const int64_t ptr[2] = {0, n};
+  return ml_weighted_1d_flsa_batch(eng, 1, ptr, y, wt, &lambda2, lambda1, beta);
+}
+
+// ---- detection ------------------------------------------------------------------------------------
+int ml_batch_upload(ml_engine* eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                    const int32_t* condition, const int32_t* replicate, const int32_t* pos,
+                    const int32_t* nmeth, const int32_t* coverage, ml_batch** out, int* status) {
+  if (!eng || !out || !job_ptr) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  if (njobs > 0 && job_ptr[njobs] > 0 && (!dataset || !condition || !replicate || !pos || !nmeth || !coverage))
+    throw MlError(ML_ERR_BAD_ARGUMENT, "NULL column (data should contain columns dataset, condition, "
+                                       "replicate, pos, Nmeth and coverage!)");
+  auto h = std::make_unique<ml_batch>();
+  h->b = batch_upload(eng->e, njobs, job_ptr, dataset, condition, replicate, pos, nmeth, coverage);
+  if (status)
+    for (int j = 0; j < njobs; ++j) status[j] = 0;  // validation runs on the device inside detect
+  *out = h.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+void ml_batch_free(ml_batch* b) {
+  if (!b) return;
+  if (b->b && b->b->eng) cudaSetDevice(b->b->eng->device);
+  delete b;
+}
+
+int ml_batch_detect(ml_engine* eng, ml_batch* b, const ml_params* params, ml_result** out, int* status) {
+  if (!eng || !b || !params || !out) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  Params p;
+  memcpy(&p, params, sizeof(p));
+  auto h = std::make_unique<ml_result>();
+  h->r = batch_detect(eng->e, *b->b, p);
+  if (status)
+    for (size_t j = 0; j < h->r->jobs.size(); ++j) status[j] = h->r->jobs[j].status;
+  *out = h.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_detect_batch(ml_engine* eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                    const int32_t* condition, const int32_t* replicate, const int32_t* pos,
+                    const int32_t* nmeth, const int32_t* coverage, const ml_params* params,
+                    ml_result** out, int* status) {
+  ml_batch* b = nullptr;
+  int rc = ml_batch_upload(eng, njobs, job_ptr, dataset, condition, replicate, pos, nmeth, coverage, &b, nullptr);
+  if (rc) return rc;
+  rc = ml_batch_detect(eng, b, params, out, status);
+  ml_batch_free(b);
+  return rc;
+}
+
+int ml_result_njobs(const ml_result* r) { return r ? (int)r->r->jobs.size() : 0; }
+
+int ml_result_job_sizes(const ml_result* r, int job, int64_t* n_rows, int64_t* n_params, int32_t* n_est,
+                        int32_t* n_dsets, int32_t* status) {
+  if (!r || job < 0 || job >= (int)r->r->jobs.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad job index");
+  const JobHost& j = r->r->jobs[job];
+  if (n_rows) *n_rows = j.nrows;
+  if (n_params) *n_params = j.status ? 0 : j.P;
+  if (n_est) *n_est = j.status ? 0 : j.E;
+  if (n_dsets) *n_dsets = j.status ? 0 : j.D;
+  if (status) *status = j.status;
+  return ML_OK;
+}
+
+int ml_result_job_info(const ml_result* r, int job, int32_t* converged, int32_t* irls_steps,
+                       int32_t* dampings, int32_t* outer_iters, double* hyper, double* mlogp) {
+  if (!r || job < 0 || job >= (int)r->r->jobs.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad job index");
+  const JobHost& j = r->r->jobs[job];
+  if (converged) *converged = j.converged;
+  if (irls_steps) *irls_steps = j.irls_steps;
+  if (dampings) *dampings = j.dampings;
+  if (outer_iters) *outer_iters = j.outer_iters;
+  if (hyper) *hyper = j.hyper;
+  if (mlogp) *mlogp = j.mlogp;
+  return ML_OK;
+}
+
+int ml_result_copy_job(ml_engine* eng, const ml_result* r, int job, double* mu, double* lambda2,
+                       double* offset, int32_t* estimate_id, double* start, double* beta,
+                       double* betahat, double* pseudoweight) {
+  if (!eng || !r || job < 0 || job >= (int)r->r->jobs.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  const Result& R = *r->r;
+  const JobHost& j = R.jobs[job];
+  if (j.status) return fail(j.status, ml_strerror(j.status));
+  cudaStream_t st = eng->e.stream;
+  const size_t EP = (size_t)j.E * (size_t)j.P;
+  if (mu) ML_CUDA(cudaMemcpyAsync(mu, R.mu.p + j.row0, sizeof(double) * (size_t)j.nrows, cudaMemcpyDeviceToHost, st));
+  if (offset) ML_CUDA(cudaMemcpyAsync(offset, R.offset.p + j.off0, sizeof(double) * (size_t)j.D, cudaMemcpyDeviceToHost, st));
+  if (beta) ML_CUDA(cudaMemcpyAsync(beta, R.beta.p + j.par0, sizeof(double) * EP, cudaMemcpyDeviceToHost, st));
+  if (betahat) ML_CUDA(cudaMemcpyAsync(betahat, R.betahat.p + j.par0, sizeof(double) * EP, cudaMemcpyDeviceToHost, st));
+  if (pseudoweight) ML_CUDA(cudaMemcpyAsync(pseudoweight, R.pw.p + j.par0, sizeof(double) * EP, cudaMemcpyDeviceToHost, st));
+  if (start)
+    for (int e = 0; e < j.E; ++e)
+      ML_CUDA(cudaMemcpyAsync(start + (size_t)e * j.P, R.start.p + R.start0[job], sizeof(double) * (size_t)j.P,
+                              cudaMemcpyDeviceToHost, st));
+  if (lambda2) for (int e = 0; e < j.E; ++e) lambda2[e] = j.lambda2;
+  if (estimate_id)
+    for (int e = 0; e < j.E; ++e)
+      for (int64_t k = 0; k < j.P; ++k) estimate_id[(size_t)e * j.P + k] = e + 1;
+  ML_CUDA(cudaStreamSynchronize(st));
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
+                       double* start, double* beta, double* betahat, double* pseudoweight) {
+  if (!eng || !r) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  const Result& R = *r->r;
+  cudaStream_t st = eng->e.stream;
+  // parameter arrays and offsets of the valid jobs are already contiguous in job order
+  if (beta && R.npar) ML_CUDA(cudaMemcpyAsync(beta, R.beta.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
+  if (betahat && R.npar) ML_CUDA(cudaMemcpyAsync(betahat, R.betahat.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
+  if (pseudoweight && R.npar) ML_CUDA(cudaMemcpyAsync(pseudoweight, R.pw.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
+  if (offset && R.noff) ML_CUDA(cudaMemcpyAsync(offset, R.offset.p, sizeof(double) * (size_t)R.noff, cudaMemcpyDeviceToHost, st));
+  size_t mu_at = 0, par_at = 0;
+  for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
+    const JobHost& j = R.jobs[jn];
+    if (j.status) continue;
+    if (mu) {
+      // rows of valid jobs are contiguous runs of the batch; copy run by run
+      ML_CUDA(cudaMemcpyAsync(mu + mu_at, R.mu.p + j.row0, sizeof(double) * (size_t)j.nrows, cudaMemcpyDeviceToHost, st));
+      mu_at += (size_t)j.nrows;
+    }
+    for (int e = 0; e < j.E; ++e) {
+      if (start)
+        ML_CUDA(cudaMemcpyAsync(start + par_at, R.start.p + R.start0[jn], sizeof(double) * (size_t)j.P,
+                                cudaMemcpyDeviceToHost, st));
+      if (estimate_id)
+        for (int64_t k = 0; k < j.P; ++k) estimate_id[par_at + k] = e + 1;
+      par_at += (size_t)j.P;
+    }
+  }
+  ML_CUDA(cudaStreamSynchronize(st));
+  return ML_OK;
+  ML_CATCH
+}
+
+void ml_result_free(ml_result* r) {
+  if (!r) return;
+  if (r->r && r->r->eng) cudaSetDevice(r->r->eng->device);
+  delete r;
+}
+
+int ml_result_fast_diff_combine(ml_engine* eng, ml_result* r) {
+  if (!eng || !r) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  result_fast_diff_combine(eng->e, *r->r);
+  return ML_OK;
+  ML_CATCH
+}
+
+// ---- segment_methylation_helper -------------------------------------------------------------------
+int ml_segment_methylation_helper(ml_engine* eng, int64_t n, const int32_t* estimate_id, const int32_t* start,
+                                  const double* beta, const double* betahat, const double* pseudoweight,
+                                  double tol_val, int64_t* n_segments, int32_t* seg_estimate_id,
+                                  int32_t* seg_id, uint32_t* seg_start, uint32_t* seg_end, double* seg_beta,
+                                  double* seg_betahat, double* seg_pseudoweight, double* seg_stdev) {
+  if (!eng || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  if (n <= 0 || !estimate_id || !start || !beta || !betahat || !pseudoweight)
+    return fail(ML_ERR_BAD_ARGUMENT, "segment_methylation_helper needs a non-empty table");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  SegHostOut ho;
+  ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
+  ho.beta = seg_beta; ho.betahat = seg_betahat; ho.pseudoweight = seg_pseudoweight; ho.stdev = seg_stdev;
+  *n_segments = segment_host_table(eng->e, n, estimate_id, start, beta, betahat, pseudoweight, tol_val, ho);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_result_segments(ml_engine* eng, ml_result* r, double tol_val, int64_t* n_segments, int32_t* seg_job,
+                       int32_t* seg_estimate_id, int32_t* seg_id, uint32_t* seg_start, uint32_t* seg_end,
+                       double* seg_beta, double* seg_betahat, double* seg_pseudoweight, double* seg_stdev) {
+  if (!eng || !r || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  Result& R = *r->r;
+  if (!R.seg_cache || R.seg_tol != tol_val) {
+    std::vector<SegGroup> groups;
+    for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
+      const JobHost& j = R.jobs[jn];
+      if (j.status) continue;
+      for (int e = 0; e < j.E; ++e)
+        groups.push_back(SegGroup{j.par0 + (int64_t)e * j.P, j.P, R.start0[jn], e + 1, (int32_t)jn});
+    }
+    auto ds_new = std::make_unique<SegDeviceOut>();
+    ds_new->n = segment_device(eng->e, groups, R.npar, R.start.p, 1, R.beta.p, R.betahat.p, R.pw.p, tol_val,
+                               *ds_new);
+    R.seg_cache = std::move(ds_new);
+    R.seg_tol = tol_val;
+  }
+  SegDeviceOut& ds = *R.seg_cache;
+  const int64_t S = ds.n;
+  *n_segments = S;
+  SegHostOut ho;
+  ho.job = seg_job; ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start;
+  ho.end = seg_end; ho.beta = seg_beta; ho.betahat = seg_betahat; ho.pseudoweight = seg_pseudoweight;
+  ho.stdev = seg_stdev;
+  if (S > 0) ds.download(eng->e.stream, S, ho);
+  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  return ML_OK;
+  ML_CATCH
+}
+
+}  // extern "C"

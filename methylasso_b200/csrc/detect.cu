@@ -1,0 +1,1172 @@
+// detect.cu — batched methylation_detection on sm_100a.
+//
+// One call processes many JOBS (chromosomes) at once.  All per-CpG data are struct-of-arrays in HBM:
+//   rows   : dataset, condition, replicate, pos, nmeth, cov (int32, as uploaded), pidx (int32 row ->
+//            parameter), mu / mu_res / mu_outer (f64)
+//   params : betahat, pw (pseudo-weight), beta, old_beta (f64), laid out [job][estimator][P]
+//   table  : rowstart[job][dataset][P] (int32) first row of dataset d that falls on parameter k
+// The reference's Binner / Design / Pseudodata objects (std::map, Eigen sparse) become these index
+// arrays; every kernel is a coalesced sweep over rows or parameters, with per-tile partial
+// reductions combined in a fixed order (deterministic, independent of job placement).
+//
+// Reference path restated here (file:line relative to /root/reference/src):
+//   MethData.hpp:13-21, core/Observations.hpp:29-59           -> k_validate
+//   unique_positions.cpp:16-31, core/binner_helpers.cpp:24-43,47-95 -> bitmap kernels + k_rank_unique
+//   binned_genome.cpp:16-31, core/binner_helpers.cpp:11-22    -> k_even_bins
+//   core/binned_residuals_helpers.cpp:9-17, core/pseudodata_helpers.hpp:27-39 -> k_pseudodata
+//   offset.cpp:14-32, core/fitter_mean.hpp:56-61              -> k_offset_partial / k_offset_finalize
+//   core/params_helpers.hpp:23-30                             -> k_center
+//   core/Posterior.ipp:63-82, NormalDistribution.hpp:46-51, BetaBinomialRateDistribution.hpp:69-90,
+//   GFLLibrary1D.hpp:62-67, predictor_helpers.cpp:10-12       -> k_eval_rows / k_tv_partial / k_job_finalize
+//   core/fitter_lasso.hpp:61-68, fitter_mean.hpp:63-70        -> k_damp
+//   core/Posterior.ipp:22-59, 99-110, 204-252                 -> host state machine in batch_detect
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "detect.cuh"
+
+namespace ml {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_ordered(double v, double* smem /*>= 8*/) {
+  // fixed tree: lanes by shuffle, warps left to right; result valid in thread 0
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int k = 0; k < nw; ++k) r += smem[k];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(double v, double* smem) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, d));
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    r = smem[0];
+    for (int k = 1; k < nw; ++k) r = fmax(r, smem[k]);
+  }
+  __syncthreads();
+  return r;
+}
+
+// first index in [0, n) with a[i] >= v (a sorted ascending)
+__device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, int n, int32_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: validation (core/Observations.hpp:29-59 then src/MethData.hpp:17-19).  The reference walks
+// the rows once and throws at the first offence; here every row evaluates its own predicate and the
+// smallest (stage, row) wins, which is the same row and the same message.
+// ------------------------------------------------------------------------------------------------
+struct VTile { int64_t r0; int32_t job; int32_t cnt; };
+constexpr int VTILE = 2048;
+
+__global__ void __launch_bounds__(256)
+k_validate(const VTile* __restrict__ tiles, const int64_t* __restrict__ job_ptr,
+           const int32_t* __restrict__ dataset, const int32_t* __restrict__ condition,
+           const int32_t* __restrict__ replicate, const int32_t* __restrict__ pos,
+           const int32_t* __restrict__ nmeth, const int32_t* __restrict__ cov,
+           unsigned long long* __restrict__ keys) {
+  const VTile t = tiles[blockIdx.x];
+  const int64_t j0 = job_ptr[t.job];
+  unsigned long long best = ~0ull;
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const int64_t r = t.r0 + i;
+    const unsigned long long li = (unsigned long long)(r - j0);
+    int code = 0;
+    if (li == 0) {
+      if ((uint32_t)dataset[r] != 1u) code = 3;
+      else if ((uint32_t)condition[r] != 1u) code = 4;
+      else if ((uint32_t)replicate[r] != 1u) code = 5;
+    } else {
+      const uint32_t dp = (uint32_t)dataset[r - 1], dc = (uint32_t)dataset[r];
+      if (dp == dc) {
+        if ((double)pos[r - 1] >= (double)pos[r]) code = 6;
+      } else if (dc != dp + 1u) {
+        code = 7;
+      } else {
+        // condition / replicate remembered by the reference are those of the first row of the
+        // previous dataset's run; with no earlier offence the prefix is sorted by dataset
+        const int rs = lower_bound_i32(dataset + j0, (int)li, (int32_t)dp);
+        const uint32_t lc = (uint32_t)condition[j0 + rs], lr = (uint32_t)replicate[j0 + rs];
+        if ((uint32_t)condition[r] == lc) {
+          if ((uint32_t)replicate[r] != lr + 1u) code = 8;
+        } else if ((uint32_t)condition[r] != lc + 1u) {
+          code = 9;
+        } else if ((uint32_t)replicate[r] != 1u) {
+          code = 10;
+        }
+      }
+    }
+    unsigned long long key = ~0ull;
+    if (code) key = (1ull << 60) | (li << 8) | (unsigned)code;
+    else if (nmeth[r] < 0 || cov[r] < 0) key = (2ull << 60) | (li << 8) | 11u;
+    else if (nmeth[r] > cov[r]) key = (3ull << 60) | (li << 8) | 12u;
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const unsigned long long o = __shfl_down_sync(0xffffffffu, best, d);
+    best = o < best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(&keys[t.job], best);
+}
+
+// dataset row ranges of every job: entry i = (job, d): first row with dataset >= d+1
+__global__ void k_dset_bounds(const int32_t* __restrict__ ent_job, const int32_t* __restrict__ ent_d,
+                              int n_ent, const int64_t* __restrict__ job_ptr,
+                              const int32_t* __restrict__ dataset, const int32_t* __restrict__ condition,
+                              const int32_t* __restrict__ pos, int32_t* __restrict__ dptr,
+                              int32_t* __restrict__ dcond, int32_t* __restrict__ dfirst,
+                              int32_t* __restrict__ dlast) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ent) return;
+  const int j = ent_job[i], d = ent_d[i];
+  const int64_t j0 = job_ptr[j];
+  const int n = (int)(job_ptr[j + 1] - j0);
+  const int lo = lower_bound_i32(dataset + j0, n, d + 1);
+  const int hi = lower_bound_i32(dataset + j0, n, d + 2);
+  dptr[i] = lo;
+  if (lo < hi) {
+    dcond[i] = condition[j0 + lo];
+    dfirst[i] = pos[j0 + lo];
+    dlast[i] = pos[j0 + hi - 1];
+  } else {
+    dcond[i] = 0; dfirst[i] = 0; dlast[i] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: unique-position index (FAST leg).  Positions of a job are marked in a bitmap over
+// [minpos, maxpos]; the rank of a position among the distinct ones is a prefix popcount.
+// Replaces make_unique_bins' sort+unique and the std::map upper_bound per row
+// (core/binner_helpers.cpp:24-43, 53-60).
+// ------------------------------------------------------------------------------------------------
+constexpr int WTILE = 2048;  // bitmap words per scan tile
+struct WTileDesc { int64_t w0; int32_t job; int32_t cnt; };
+
+__global__ void __launch_bounds__(256)
+k_bitmap_mark(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+              const int32_t* __restrict__ pos, const int64_t* __restrict__ bm0,
+              const int32_t* __restrict__ minpos, uint32_t* __restrict__ bitmap) {
+  const RowTile t = tiles[blockIdx.x];
+  const JobDev J = jobs[t.job];
+  const int32_t mp = minpos[t.job];
+  uint32_t* bm = bitmap + bm0[t.job];
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const uint32_t rel = (uint32_t)(pos[J.row0 + t.r0 + i] - mp);
+    atomicOr(&bm[rel >> 5], 1u << (rel & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bitmap_tile_count(const WTileDesc* __restrict__ tiles, const uint32_t* __restrict__ bitmap,
+                    uint32_t* __restrict__ tile_count) {
+  __shared__ uint32_t sm[8];
+  const WTileDesc t = tiles[blockIdx.x];
+  uint32_t c = 0;
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) c += __popc(bitmap[t.w0 + i]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) s += sm[k];
+    tile_count[blockIdx.x] = s;
+  }
+}
+
+// one warp per job: exclusive scan of its tile counts; total = number of distinct positions
+__global__ void k_bitmap_job_scan(const int32_t* __restrict__ job_wtile0, int njobs,
+                                  uint32_t* __restrict__ tile_count /*in: counts, out: bases*/,
+                                  int32_t* __restrict__ job_unique) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= njobs) return;
+  const int t0 = job_wtile0[j], t1 = job_wtile0[j + 1];
+  uint32_t run = 0;
+  for (int base = t0; base < t1; base += 32) {
+    const int t = base + lane;
+    const uint32_t c = t < t1 ? tile_count[t] : 0;
+    uint32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (t < t1) tile_count[t] = run + inc - c;
+    run += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  if (lane == 0) job_unique[j] = (int32_t)run;
+}
+
+// per word: number of set bits before it within its job
+__global__ void __launch_bounds__(256)
+k_bitmap_word_prefix(const WTileDesc* __restrict__ tiles, const uint32_t* __restrict__ bitmap,
+                     const uint32_t* __restrict__ tile_base, uint32_t* __restrict__ word_prefix) {
+  __shared__ uint32_t sm[8];
+  const WTileDesc t = tiles[blockIdx.x];
+  constexpr int V = WTILE / 256;
+  const int i0 = threadIdx.x * V;
+  uint32_t c[V];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    c[k] = (i0 + k < t.cnt) ? __popc(bitmap[t.w0 + i0 + k]) : 0;
+    mine += c[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) sm[wid] = inc;
+  __syncthreads();
+  uint32_t before = tile_base[blockIdx.x];
+  for (int k = 0; k < wid; ++k) before += sm[k];
+  uint32_t run = before + inc - mine;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (i0 + k < t.cnt) word_prefix[t.w0 + i0 + k] = run;
+    run += c[k];
+  }
+}
+
+// rows: parameter index = rank of the position; also the (dataset, param) -> row table and the
+// support (bin start = the position itself, BinDesign::starts)
+__global__ void __launch_bounds__(256)
+k_rank_unique(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+              const int32_t* __restrict__ pos, const int64_t* __restrict__ bm0,
+              const int32_t* __restrict__ minpos, const uint32_t* __restrict__ bitmap,
+              const uint32_t* __restrict__ word_prefix, const int64_t* __restrict__ start0,
+              const int32_t* __restrict__ alive, int32_t* __restrict__ pidx,
+              int32_t* __restrict__ rowstart, double* __restrict__ start) {
+  const RowTile t = tiles[blockIdx.x];
+  if (!alive[t.job]) return;
+  const JobDev J = jobs[t.job];
+  const int32_t mp = minpos[t.job];
+  const int64_t b0 = bm0[t.job];
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const int rl = t.r0 + i;
+    const int32_t p = pos[J.row0 + rl];
+    const uint32_t rel = (uint32_t)(p - mp);
+    const uint32_t w = bitmap[b0 + (rel >> 5)];
+    const int k = (int)(word_prefix[b0 + (rel >> 5)] + __popc(w & ((1u << (rel & 31)) - 1u)));
+    pidx[J.row0 + rl] = k;
+    rowstart[J.tab0 + (int64_t)t.d * J.P + k] = rl;
+    // BinDesign::starts holds the position as double(unsigned); the estimates table reports
+    // int(start) (methylation_helpers.hpp:20).  Every dataset writes the same value.
+    start[start0[t.job] + k] = (double)(int32_t)(double)(uint32_t)p;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: even-bin index (FULL leg): binned_genome.cpp:22-25 + binner_helpers.cpp:11-22, 53-60
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_even_bins(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+            const int32_t* __restrict__ pos, const int32_t* __restrict__ alive,
+            int32_t* __restrict__ pidx) {
+  const RowTile t = tiles[blockIdx.x];
+  if (!alive[t.job]) return;
+  const JobDev J = jobs[t.job];
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const int64_t r = J.row0 + t.r0 + i;
+    pidx[r] = (int32_t)even_bin((double)pos[r], J.lower, J.size, J.nbins);
+  }
+}
+// first row of every (dataset, bin) run; rows of a dataset are sorted so bins form runs
+__global__ void __launch_bounds__(256)
+k_rowstart_runs(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                const int32_t* __restrict__ dptr, const int32_t* __restrict__ pidx,
+                const int32_t* __restrict__ alive, int32_t* __restrict__ rowstart) {
+  const RowTile t = tiles[blockIdx.x];
+  if (!alive[t.job]) return;
+  const JobDev J = jobs[t.job];
+  const int dstart = dptr[J.dptr0 + t.d];
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const int rl = t.r0 + i;
+    const int k = pidx[J.row0 + rl];
+    if (rl == dstart || pidx[J.row0 + rl - 1] != k) rowstart[J.tab0 + (int64_t)t.d * J.P + k] = rl;
+  }
+}
+__global__ void __launch_bounds__(PAR_TILE)
+k_support_even(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+               const int64_t* __restrict__ start0, double* __restrict__ start) {
+  const ParTile t = tiles[blockIdx.x];   // parameter tiles exist only for jobs that are still alive
+  if (t.e != 0) return;
+  const JobDev J = jobs[t.job];
+  const int k = t.k0 + threadIdx.x;
+  if (threadIdx.x < t.cnt)
+    start[start0[t.job] + k] = (double)(int32_t)even_boundary(J.lower, J.size, (uint32_t)k, J.nbins);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4+K5: residuals -> binned residuals -> pseudodata, one thread per (estimator, parameter).
+//   What_d = sum_rows W            (Binner::bin, sequential in row order)
+//   zhat_d = sum_rows z W / What_d (0 where What_d == 0)
+//   pw     = sum_d (c What_d) c ;  betahat = sum_d (pw^+ c)(What_d zhat_d) + beta
+// Datasets are visited in increasing order, rows in row order: the reference's summation order.
+// ------------------------------------------------------------------------------------------------
+struct RowCols {
+  const int32_t* __restrict__ nmeth;
+  const int32_t* __restrict__ cov;
+  const int32_t* __restrict__ pidx;
+  const double* __restrict__ mu_res;
+};
+
+__device__ __forceinline__ void bin_residuals(const JobDev& J, const RowCols& rc, int first, int r0,
+                                              int rend, int k, double& What, double& Zs) {
+  What = 0.0;
+  Zs = 0.0;
+  for (int r = r0; r < rend; ++r) {
+    const int64_t g = J.row0 + r;
+    if (r != r0 && rc.pidx[g] != k) break;
+    const double nobs = (double)rc.cov[g];
+    const double y = (double)rc.nmeth[g] / nobs;
+    double z, W;
+    irls_residual(J.model, first, y, nobs, first ? 0.0 : rc.mu_res[g], J.nu, z, W);
+    What += W;
+    Zs += z * W;
+  }
+}
+
+__global__ void __launch_bounds__(PAR_TILE)
+k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+             const int32_t* __restrict__ ctl, RowCols rc, const int32_t* __restrict__ dptr,
+             const double* __restrict__ design, const int32_t* __restrict__ rowstart,
+             double* __restrict__ beta, double* __restrict__ old_beta, double* __restrict__ betahat,
+             double* __restrict__ pw) {
+  const ParTile t = tiles[blockIdx.x];
+  const int c = ctl[t.job];
+  if (!(c & CTL_UPDATE)) return;
+  if ((int)threadIdx.x >= t.cnt) return;
+  const JobDev J = jobs[t.job];
+  const int first = (c & CTL_FIRST) ? 1 : 0;
+  const int k = t.k0 + threadIdx.x;
+  const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
+  double wt = 0.0;
+  for (int d = 0; d < J.D; ++d) {
+    const double cf = design[J.des0 + d * J.E + t.e];
+    if (cf == 0) continue;
+    const int r0 = rowstart[J.tab0 + (int64_t)d * J.P + k];
+    if (r0 < 0) continue;
+    double What, Zs;
+    bin_residuals(J, rc, first, r0, dptr[J.dptr0 + d + 1], k, What, Zs);
+    wt += (cf * What) * cf;
+  }
+  double inv = 1 / wt;
+  if (!is_finite(inv)) inv = 0.0;     // pseudo-inverse (pseudodata_helpers.hpp:33-34)
+  double bh = 0.0;
+  for (int d = 0; d < J.D; ++d) {
+    const double cf = design[J.des0 + d * J.E + t.e];
+    if (cf == 0) continue;
+    const int r0 = rowstart[J.tab0 + (int64_t)d * J.P + k];
+    if (r0 < 0) continue;
+    double What, Zs;
+    bin_residuals(J, rc, first, r0, dptr[J.dptr0 + d + 1], k, What, Zs);
+    const double q = Zs / What;
+    const double zhat = (What == 0) ? What : q;
+    bh += (inv * cf) * (What * zhat);
+  }
+  const double b = beta[pi];
+  old_beta[pi] = b;                   // Estimator::update_params: set_old_params (Estimator.ipp:22)
+  betahat[pi] = bh + b;
+  pw[pi] = wt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: offset (one mean per dataset): per row-tile partial sums, then per dataset in tile order.
+// The reference adds the rows of a dataset left to right (Binner.cpp:34); here the association is
+// a fixed tree per tile followed by a left-to-right sum over tiles (documented deviation, ~1e-16).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_offset_partial(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+                 const int32_t* __restrict__ ctl, RowCols rc, double* __restrict__ part /*2 per tile*/) {
+  __shared__ double sm[8];
+  const RowTile t = tiles[blockIdx.x];
+  const int c = ctl[t.job];
+  if (!(c & CTL_UPDATE)) return;
+  const JobDev J = jobs[t.job];
+  const int first = (c & CTL_FIRST) ? 1 : 0;
+  double sw = 0.0, sz = 0.0;
+#pragma unroll
+  for (int q = 0; q < ROW_TILE / 256; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i < t.cnt) {
+      const int64_t g = J.row0 + t.r0 + i;
+      const double nobs = (double)rc.cov[g];
+      const double y = (double)rc.nmeth[g] / nobs;
+      double z, W;
+      irls_residual(J.model, first, y, nobs, first ? 0.0 : rc.mu_res[g], J.nu, z, W);
+      sw += W;
+      sz += z * W;
+    }
+  }
+  const double a = block_sum_ordered(sw, sm);
+  const double b = block_sum_ordered(sz, sm);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
+}
+
+__global__ void k_offset_finalize(const int32_t* __restrict__ ent_job, const int32_t* __restrict__ ent_d,
+                                  int n_ent, const JobDev* __restrict__ jobs,
+                                  const int32_t* __restrict__ ctl, const int32_t* __restrict__ dtile0,
+                                  const double* __restrict__ part, double* __restrict__ off,
+                                  double* __restrict__ old_off) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_ent) return;
+  const int j = ent_job[i], d = ent_d[i];
+  if (!(ctl[j] & CTL_UPDATE)) return;
+  const JobDev J = jobs[j];
+  if (d >= J.D) return;
+  double What = 0.0, Zs = 0.0;
+  for (int t = dtile0[i]; t < dtile0[i + 1]; ++t) { What += part[2 * t]; Zs += part[2 * t + 1]; }
+  const double q = Zs / What;
+  const double zhat = (What == 0) ? What : q;
+  const double pwd = (1. * What) * 1.;
+  double inv = 1 / pwd;
+  if (!is_finite(inv)) inv = 0.0;
+  const double o = off[J.off0 + d];
+  old_off[J.off0 + d] = o;
+  off[J.off0 + d] = (inv * 1.) * (What * zhat) + o;   // Fitter<Mean>: beta = betahat
+}
+
+// centring: beta -= sum(beta*pw)/sum(pw)   (params_helpers.hpp:23-30)
+__global__ void __launch_bounds__(PAR_TILE)
+k_center(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+         const int32_t* __restrict__ ctl, const double* __restrict__ sums, double* __restrict__ beta) {
+  const ParTile t = tiles[blockIdx.x];
+  if (!(ctl[t.job] & CTL_UPDATE)) return;
+  if ((int)threadIdx.x >= t.cnt) return;
+  const JobDev J = jobs[t.job];
+  const int s = J.ser0 + t.e;
+  const double mean = sums[2 * s] / sums[2 * s + 1];
+  const int64_t pi = J.par0 + (int64_t)t.e * J.P + t.k0 + threadIdx.x;
+  beta[pi] = beta[pi] - mean;
+}
+
+// damping: p <- w p + (1-w) p_old for every lasso estimator and the offset
+// (fitter_lasso.hpp:61-68, fitter_mean.hpp:63-70; weight 1-5/10, posterior_policies.hpp:67)
+__global__ void __launch_bounds__(PAR_TILE)
+k_damp(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+       const int32_t* __restrict__ ctl, double wnew, double* __restrict__ beta,
+       const double* __restrict__ old_beta, double* __restrict__ off, const double* __restrict__ old_off) {
+  const ParTile t = tiles[blockIdx.x];
+  if (!(ctl[t.job] & CTL_DAMP)) return;
+  const JobDev J = jobs[t.job];
+  if ((int)threadIdx.x < t.cnt) {
+    const int64_t pi = J.par0 + (int64_t)t.e * J.P + t.k0 + threadIdx.x;
+    beta[pi] = wnew * beta[pi] + (1 - wnew) * old_beta[pi];
+  }
+  if (t.e == 0 && t.k0 == 0 && (int)threadIdx.x < J.D) {
+    const int o = J.off0 + threadIdx.x;
+    off[o] = wnew * off[o] + (1 - wnew) * old_off[o];
+  }
+  // J.D > PAR_TILE datasets: remaining offsets
+  if (t.e == 0 && t.k0 == 0)
+    for (int d = PAR_TILE + threadIdx.x; d < J.D; d += PAR_TILE) {
+      const int o = J.off0 + d;
+      off[o] = wnew * off[o] + (1 - wnew) * old_off[o];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10/K11/K13: mu, -log pdf and max |delta mu| per row tile
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+            const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
+            const double* __restrict__ beta, const double* __restrict__ off, double log2pi,
+            double* __restrict__ mu, const double* __restrict__ mu_outer, int want_outer,
+            double* __restrict__ part /*3 per tile: lik, dres, douter*/) {
+  __shared__ double sm[8];
+  const RowTile t = tiles[blockIdx.x];
+  if (!(ctl[t.job] & CTL_EVAL)) return;
+  const JobDev J = jobs[t.job];
+  const double o = off[J.off0 + t.d];
+  double lik = 0.0, dres = 0.0, dout = 0.0;
+#pragma unroll
+  for (int q = 0; q < ROW_TILE / 256; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i < t.cnt) {
+      const int64_t g = J.row0 + t.r0 + i;
+      const int k = rc.pidx[g];
+      double eta = 0.0;
+      for (int e = 0; e < J.E; ++e) {
+        const double cf = design[J.des0 + t.d * J.E + e];
+        const double phi = (cf != 0) ? (0. + cf * beta[J.par0 + (int64_t)e * J.P + k]) : 0.;
+        eta += phi;
+      }
+      eta = eta + (0. + 1. * o);
+      const double m = irls_mu(J.model, eta);
+      const double nobs = (double)rc.cov[g];
+      const double y = (double)rc.nmeth[g] / nobs;
+      lik += irls_minus_log_pdf(J.model, y, nobs, m, J.nu, log2pi);
+      dres = fmax(dres, fabs(m - rc.mu_res[g]));
+      if (want_outer) dout = fmax(dout, fabs(m - mu_outer[g]));
+      mu[g] = m;
+    }
+  }
+  const double a = block_sum_ordered(lik, sm);
+  const double b = block_max(dres, sm);
+  const double c = block_max(dout, sm);
+  if (threadIdx.x == 0) {
+    part[3 * blockIdx.x] = a;
+    part[3 * blockIdx.x + 1] = b;
+    part[3 * blockIdx.x + 2] = c;
+  }
+}
+
+// total variation of one parameter tile: sum |beta_k - beta_{k-1}|   (GFLLibrary1D.hpp:64)
+__global__ void __launch_bounds__(PAR_TILE)
+k_tv_partial(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+             const int32_t* __restrict__ ctl, const double* __restrict__ beta, double* __restrict__ part) {
+  __shared__ double sm[8];
+  const ParTile t = tiles[blockIdx.x];
+  if (!(ctl[t.job] & CTL_EVAL)) return;
+  const JobDev J = jobs[t.job];
+  const int k = t.k0 + threadIdx.x;
+  double v = 0.0;
+  if ((int)threadIdx.x < t.cnt && k > 0) {
+    const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
+    v = fabs(beta[pi] - beta[pi - 1]);
+  }
+  const double a = block_sum_ordered(v, sm);
+  if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+// one thread per job: tile partials in tile order -> {mlogp, lik, prior, dres, douter}
+__global__ void k_job_finalize(const JobDev* __restrict__ jobs, int njobs, const int32_t* __restrict__ ctl,
+                               const double* __restrict__ row_part, const double* __restrict__ tv_part,
+                               double* __restrict__ scalars /*5 per job*/) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= njobs) return;
+  if (!(ctl[j] & CTL_EVAL)) return;
+  const JobDev J = jobs[j];
+  double lik = 0.0, dres = 0.0, dout = 0.0;
+  for (int t = J.rtile0; t < J.rtile0 + J.n_rtiles; ++t) {
+    lik += row_part[3 * t];
+    dres = fmax(dres, row_part[3 * t + 1]);
+    dout = fmax(dout, row_part[3 * t + 2]);
+  }
+  double pri = 0.0;
+  const int tiles_per_e = J.n_ptiles / J.E;
+  for (int e = 0; e < J.E; ++e) {
+    double tv = 0.0;
+    for (int t = 0; t < tiles_per_e; ++t) tv += tv_part[J.ptile0 + e * tiles_per_e + t];
+    const double lam = J.lambda2;
+    pri += lam * tv - (double)(uint64_t)(J.P - 2) * log(lam) + (double)(uint64_t)(J.P - 1) * log(2.0);
+  }
+  scalars[5 * j] = lik + pri;
+  scalars[5 * j + 1] = lik;
+  scalars[5 * j + 2] = pri;
+  scalars[5 * j + 3] = dres;
+  scalars[5 * j + 4] = dout;
+}
+
+__global__ void __launch_bounds__(256)
+k_copy_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+            const int32_t* __restrict__ ctl, const double* __restrict__ mu, double* __restrict__ mu_res,
+            double* __restrict__ mu_outer) {
+  const RowTile t = tiles[blockIdx.x];
+  const int c = ctl[t.job];
+  if (!(c & (CTL_COPY_RES | CTL_COPY_OUTER))) return;
+  const JobDev J = jobs[t.job];
+  for (int i = threadIdx.x; i < t.cnt; i += blockDim.x) {
+    const int64_t g = J.row0 + t.r0 + i;
+    const double m = mu[g];
+    if (c & CTL_COPY_RES) mu_res[g] = m;
+    if ((c & CTL_COPY_OUTER) && mu_outer) mu_outer[g] = m;
+  }
+}
+
+// R/fast_diff.R:15-28 on the parameter arrays (estimator 0 = reference condition)
+__global__ void __launch_bounds__(PAR_TILE)
+k_fast_diff(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs, double* __restrict__ beta,
+            double* __restrict__ betahat, double* __restrict__ pw) {
+  const ParTile t = tiles[blockIdx.x];
+  if (t.e == 0 || (int)threadIdx.x >= t.cnt) return;
+  const JobDev J = jobs[t.job];
+  const int k = t.k0 + threadIdx.x;
+  const int64_t pi = J.par0 + (int64_t)t.e * J.P + k, pr = J.par0 + k;
+  const double s = pw[pi] + pw[pr];
+  double bh = (betahat[pi] * pw[pi] - betahat[pr] * pw[pr]) / s;
+  if (s == 0) bh = 0.0;
+  beta[pi] = beta[pi] - beta[pr];
+  betahat[pi] = bh;
+  pw[pi] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                                    const int32_t* condition, const int32_t* replicate,
+                                    const int32_t* pos, const int32_t* nmeth, const int32_t* cov) {
+  if (njobs < 0) throw MlError(19, "njobs < 0");
+  auto b = std::make_unique<Batch>();
+  b->eng = &eng;
+  b->njobs = njobs;
+  b->job_ptr.assign(job_ptr, job_ptr + njobs + 1);
+  if (njobs && b->job_ptr[0] != 0) throw MlError(19, "job_ptr[0] must be 0");
+  for (int j = 0; j < njobs; ++j) {
+    if (b->job_ptr[j + 1] < b->job_ptr[j]) throw MlError(19, "job_ptr must be non-decreasing");
+    if (b->job_ptr[j + 1] - b->job_ptr[j] > 0x7fffffff) throw MlError(19, "a job has more than 2^31-1 rows");
+  }
+  b->nrows = njobs ? b->job_ptr[njobs] : 0;
+  const size_t n = (size_t)b->nrows;
+  cudaStream_t st = eng.stream;
+  b->hint_D.resize(njobs);
+  b->hint_C.resize(njobs);
+  for (int j = 0; j < njobs; ++j) {
+    const int64_t last = b->job_ptr[j + 1] - 1;
+    const bool any = b->job_ptr[j + 1] > b->job_ptr[j];
+    b->hint_D[j] = any ? dataset[last] : 0;     // dset.tail<1>() (data_design_helpers.cpp:23)
+    b->hint_C[j] = any ? condition[last] : 0;
+  }
+  b->dataset.alloc(st, n);   b->dataset.upload(dataset, n);
+  b->condition.alloc(st, n); b->condition.upload(condition, n);
+  b->replicate.alloc(st, n); b->replicate.upload(replicate, n);
+  b->pos.alloc(st, n);       b->pos.upload(pos, n);
+  b->nmeth.alloc(st, n);     b->nmeth.upload(nmeth, n);
+  b->cov.alloc(st, n);       b->cov.upload(cov, n);
+  b->d_job_ptr.alloc(st, njobs + 1);
+  b->d_job_ptr.upload(b->job_ptr);
+  ML_CUDA(cudaStreamSynchronize(st));  // the caller may reuse its buffers after return
+  return b;
+}
+
+namespace {
+
+struct Ctx {   // everything one detect call owns on the device besides the Result
+  DevBuf<JobDev> jobs;
+  DevBuf<RowTile> rtiles;
+  DevBuf<ParTile> ptiles;
+  DevBuf<int32_t> ctl;
+  DevBuf<int32_t> dptr, ent_job, ent_d, dtile0;
+  DevBuf<double> design;
+  DevBuf<int32_t> pidx, rowstart;
+  DevBuf<double> mu_res, mu_outer, old_beta, old_off;
+  DevBuf<double> off_part, row_part, tv_part, scalars, sums;
+  DevBuf<int64_t> start0;
+};
+
+int decode_status(unsigned long long key) { return key == ~0ull ? 0 : (int)(key & 0xff); }
+
+}  // namespace
+
+std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
+  if (p.optimize_lambda2 || p.optimize_hyper)
+    throw MlError(19, "optimize_lambda2 / optimize_hyper are not supported (FALSE at every reference call site)");
+  if (p.model < 0 || p.model > 2) throw MlError(19, "unknown model");
+  cudaStream_t st = eng.stream;
+  const int nj = b.njobs;
+  auto res = std::make_unique<Result>();
+  res->eng = &eng;
+  res->jobs.resize(nj);
+  res->nrows = b.nrows;
+  if (nj == 0) return res;
+
+  // ---- K1: validation --------------------------------------------------------------------------
+  std::vector<VTile> vt;
+  for (int j = 0; j < nj; ++j)
+    for (int64_t r = b.job_ptr[j]; r < b.job_ptr[j + 1]; r += VTILE)
+      vt.push_back(VTile{r, j, (int32_t)std::min<int64_t>(VTILE, b.job_ptr[j + 1] - r)});
+  DevBuf<VTile> d_vt(st, std::max<size_t>(1, vt.size()));
+  d_vt.upload(vt);
+  DevBuf<unsigned long long> d_keys(st, nj);
+  ML_CUDA(cudaMemsetAsync(d_keys.p, 0xff, sizeof(unsigned long long) * nj, st));
+  if (!vt.empty()) {
+    k_validate<<<(int)vt.size(), 256, 0, st>>>(d_vt.p, b.d_job_ptr.p, b.dataset.p, b.condition.p,
+                                               b.replicate.p, b.pos.p, b.nmeth.p, b.cov.p, d_keys.p);
+    ML_CHECK_LAUNCH();
+    eng.launches++;
+  }
+  // dataset ranges (for jobs whose last-row dataset id is plausible)
+  std::vector<int32_t> ent_job, ent_d, job_ent0(nj + 1, 0);
+  for (int j = 0; j < nj; ++j) {
+    job_ent0[j] = (int32_t)ent_job.size();
+    const int64_t n = b.job_ptr[j + 1] - b.job_ptr[j];
+    const int D = b.hint_D[j];
+    if (n >= 2 && D >= 1 && D <= n)
+      for (int d = 0; d <= D; ++d) { ent_job.push_back(j); ent_d.push_back(d); }
+  }
+  job_ent0[nj] = (int32_t)ent_job.size();
+  const int n_ent = (int)ent_job.size();
+  Ctx cx;
+  cx.ent_job.alloc(st, std::max(1, n_ent)); cx.ent_job.upload(ent_job);
+  cx.ent_d.alloc(st, std::max(1, n_ent));   cx.ent_d.upload(ent_d);
+  cx.dptr.alloc(st, std::max(1, n_ent));
+  DevBuf<int32_t> d_dcond(st, std::max(1, n_ent)), d_dfirst(st, std::max(1, n_ent)), d_dlast(st, std::max(1, n_ent));
+  if (n_ent) {
+    k_dset_bounds<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, b.d_job_ptr.p,
+                                                    b.dataset.p, b.condition.p, b.pos.p, cx.dptr.p,
+                                                    d_dcond.p, d_dfirst.p, d_dlast.p);
+    ML_CHECK_LAUNCH();
+    eng.launches++;
+  }
+  std::vector<unsigned long long> keys(nj);
+  std::vector<int32_t> h_dptr(n_ent), h_dcond(n_ent), h_dfirst(n_ent), h_dlast(n_ent);
+  d_keys.download(keys.data(), nj);
+  cx.dptr.download(h_dptr.data(), n_ent);
+  d_dcond.download(h_dcond.data(), n_ent);
+  d_dfirst.download(h_dfirst.data(), n_ent);
+  d_dlast.download(h_dlast.data(), n_ent);
+  ML_CUDA(cudaStreamSynchronize(st));
+
+  // ---- host: per-job status, design, geometry ----------------------------------------------------
+  const bool fast = p.model == MODEL_FAST;
+  std::vector<JobDev> hj(nj);
+  std::vector<double> h_design;
+  std::vector<int32_t> h_minpos(nj, 0);
+  std::vector<int64_t> h_bm0(nj + 1, 0);
+  int64_t rows_valid = 0;
+  int32_t noff = 0;
+  for (int j = 0; j < nj; ++j) {
+    JobHost& jh = res->jobs[j];
+    JobDev& J = hj[j];
+    memset(&J, 0, sizeof(J));
+    const int64_t n = b.job_ptr[j + 1] - b.job_ptr[j];
+    jh.nrows = n;
+    jh.row0 = b.job_ptr[j];
+    jh.lambda2 = p.lambda2;
+    if (n <= 1) { jh.status = 1; continue; }
+    jh.status = decode_status(keys[j]);
+    if (jh.status) continue;
+    const int D = b.hint_D[j], C = b.hint_C[j];
+    if (job_ent0[j + 1] - job_ent0[j] != D + 1 || C < 1) { jh.status = 19; continue; }  // cannot happen for validated data
+    jh.D = D;
+    jh.C = C;
+    if (p.model == MODEL_FULL_DIFFERENCE && C <= 1) { jh.status = 14; continue; }
+    const int E = C;
+    jh.E = E;
+    // build_signal_design / build_difference_design (core/data_design_helpers.cpp:10-28, 30-40)
+    const int e0 = job_ent0[j];
+    std::vector<double> X((size_t)D * E, 0.0);
+    for (int d = 0; d < D; ++d) X[(size_t)d * E + (h_dcond[e0 + d] - 1)] = 1.0;
+    if (p.model == MODEL_FULL_DIFFERENCE) {
+      const uint32_t ref = p.ref;
+      if ((uint32_t)D < ref || ref == 0 || ref > (uint32_t)C) { jh.status = 15; continue; }
+      for (int d = 0; d < D; ++d) {
+        double* row = &X[(size_t)d * E];
+        for (int c = (int)ref - 1; c >= 1; --c) row[c] = row[c - 1];
+        row[0] = 1.0;
+      }
+    }
+    int32_t mn = h_dfirst[e0], mx = h_dlast[e0];
+    for (int d = 1; d < D; ++d) { mn = std::min(mn, h_dfirst[e0 + d]); mx = std::max(mx, h_dlast[e0 + d]); }
+    h_minpos[j] = mn;
+    J.row0 = b.job_ptr[j];
+    J.nrows = (int32_t)n;
+    J.D = D;
+    J.E = E;
+    J.dptr0 = e0;
+    J.des0 = (int32_t)h_design.size();
+    h_design.insert(h_design.end(), X.begin(), X.end());
+    J.off0 = noff;
+    jh.off0 = noff;
+    noff += D;
+    J.model = p.model;
+    J.lambda2 = p.lambda2;
+    J.nu = p.hyper;
+    if (fast) {
+      h_bm0[j + 1] = ((int64_t)mx - (int64_t)mn) / 32 + 1;  // words of this job's bitmap
+    } else {
+      const double lo = (double)mn, hi = (double)mx;
+      const double genome_sz = (hi - lo + 1);
+      const uint32_t nbins = (uint32_t)(genome_sz * p.bf_per_kb / 1000.);  // binned_genome.cpp:22-23
+      if (nbins < 2) { jh.status = 18; noff -= D; h_design.resize(J.des0); continue; }
+      J.lower = lo;
+      J.size = hi - lo;
+      J.nbins = nbins;
+      J.P = (int32_t)nbins;
+      jh.P = nbins;
+    }
+    rows_valid += n;
+  }
+  // row tiles of valid jobs (per dataset)
+  std::vector<RowTile> rt;
+  std::vector<int32_t> h_dtile0(n_ent + 1, 0);
+  for (int j = 0; j < nj; ++j) {
+    JobDev& J = hj[j];
+    if (res->jobs[j].status) {
+      for (int i = job_ent0[j]; i < job_ent0[j + 1]; ++i) h_dtile0[i] = (int32_t)rt.size();
+      continue;
+    }
+    J.rtile0 = (int32_t)rt.size();
+    for (int d = 0; d < J.D; ++d) {
+      h_dtile0[J.dptr0 + d] = (int32_t)rt.size();
+      const int r0 = h_dptr[J.dptr0 + d], r1 = h_dptr[J.dptr0 + d + 1];
+      for (int r = r0; r < r1; r += ROW_TILE) rt.push_back(RowTile{j, d, r, std::min(ROW_TILE, r1 - r)});
+    }
+    h_dtile0[J.dptr0 + J.D] = (int32_t)rt.size();
+    J.n_rtiles = (int32_t)rt.size() - J.rtile0;
+  }
+  h_dtile0[n_ent] = (int32_t)rt.size();
+  const int n_rt = (int)rt.size();
+  cx.rtiles.alloc(st, std::max(1, n_rt));
+  cx.rtiles.upload(rt);
+  cx.dtile0.alloc(st, n_ent + 1);
+  cx.dtile0.upload(h_dtile0);
+  cx.pidx.alloc(st, (size_t)std::max<int64_t>(1, b.nrows));
+
+  // ---- K2 (FAST): bitmap rank ---------------------------------------------------------------------
+  DevBuf<uint32_t> d_bitmap, d_wprefix, d_wtile_count;
+  DevBuf<int64_t> d_bm0;
+  DevBuf<int32_t> d_minpos;
+  DevBuf<WTileDesc> d_wt;
+  DevBuf<int32_t> d_job_wtile0, d_job_unique;
+  cx.jobs.alloc(st, nj);
+  if (fast && n_rt) {
+    for (int j = 0; j < nj; ++j) h_bm0[j + 1] += h_bm0[j];
+    const int64_t nwords = h_bm0[nj];
+    std::vector<WTileDesc> wt;
+    std::vector<int32_t> job_wtile0(nj + 1, 0);
+    for (int j = 0; j < nj; ++j) {
+      job_wtile0[j] = (int32_t)wt.size();
+      for (int64_t w = h_bm0[j]; w < h_bm0[j + 1]; w += WTILE)
+        wt.push_back(WTileDesc{w, j, (int32_t)std::min<int64_t>(WTILE, h_bm0[j + 1] - w)});
+    }
+    job_wtile0[nj] = (int32_t)wt.size();
+    d_bitmap.alloc(st, (size_t)std::max<int64_t>(1, nwords));
+    d_bitmap.zero();
+    d_wprefix.alloc(st, (size_t)std::max<int64_t>(1, nwords));
+    d_bm0.alloc(st, nj + 1);  d_bm0.upload(h_bm0);
+    d_minpos.alloc(st, nj);   d_minpos.upload(h_minpos);
+    d_wt.alloc(st, std::max<size_t>(1, wt.size())); d_wt.upload(wt);
+    d_wtile_count.alloc(st, std::max<size_t>(1, wt.size()));
+    d_job_wtile0.alloc(st, nj + 1); d_job_wtile0.upload(job_wtile0);
+    d_job_unique.alloc(st, nj);
+    cx.jobs.upload(hj);  // row0 etc. are final; P / par0 / tab0 follow after the count
+    k_bitmap_mark<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p);
+    ML_CHECK_LAUNCH();
+    k_bitmap_tile_count<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p);
+    ML_CHECK_LAUNCH();
+    k_bitmap_job_scan<<<cdiv((long long)nj * 32, 128), 128, 0, st>>>(d_job_wtile0.p, nj, d_wtile_count.p,
+                                                                     d_job_unique.p);
+    ML_CHECK_LAUNCH();
+    k_bitmap_word_prefix<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p);
+    ML_CHECK_LAUNCH();
+    eng.launches += 4;
+    std::vector<int32_t> uniq(nj);
+    d_job_unique.download(uniq.data(), nj);
+    ML_CUDA(cudaStreamSynchronize(st));
+    for (int j = 0; j < nj; ++j) {
+      if (res->jobs[j].status) continue;
+      hj[j].P = uniq[j];
+      res->jobs[j].P = uniq[j];
+      if (uniq[j] < 2) res->jobs[j].status = 18;   // reference: size()-2 underflow
+    }
+  }
+  if (p.lambda2 <= 0)                               // fitter_lasso.ipp:4 (thrown at the first fit)
+    for (int j = 0; j < nj; ++j)
+      if (!res->jobs[j].status) res->jobs[j].status = 13;
+
+  // ---- layout of parameter arrays -------------------------------------------------------------------
+  std::vector<ParTile> pt;
+  std::vector<FlsaSeries> series;
+  std::vector<int64_t> h_start0(nj, 0);
+  int64_t npar = 0, ntab = 0, nstart = 0;
+  for (int j = 0; j < nj; ++j) {
+    JobDev& J = hj[j];
+    JobHost& jh = res->jobs[j];
+    if (jh.status) continue;
+    J.par0 = npar;
+    jh.par0 = npar;
+    J.tab0 = ntab;
+    J.ser0 = (int32_t)series.size();
+    J.ptile0 = (int32_t)pt.size();
+    h_start0[j] = nstart;
+    for (int e = 0; e < J.E; ++e) {
+      series.push_back(FlsaSeries{npar + (int64_t)e * J.P, J.P, p.lambda2});
+      for (int k = 0; k < J.P; k += PAR_TILE) pt.push_back(ParTile{j, e, k, std::min(PAR_TILE, J.P - k)});
+    }
+    J.n_ptiles = (int32_t)pt.size() - J.ptile0;
+    npar += (int64_t)J.E * J.P;
+    ntab += (int64_t)J.D * J.P;
+    nstart += J.P;
+  }
+  res->npar = npar;
+  res->noff = noff;
+  res->nstart = nstart;
+  res->start0 = h_start0;
+  const int n_pt = (int)pt.size();
+  cx.jobs.upload(hj);
+  cx.ptiles.alloc(st, std::max(1, n_pt));
+  cx.ptiles.upload(pt);
+  cx.design.alloc(st, std::max<size_t>(1, h_design.size()));
+  cx.design.upload(h_design);
+  cx.start0.alloc(st, nj);
+  cx.start0.upload(h_start0);
+  cx.rowstart.alloc(st, (size_t)std::max<int64_t>(1, ntab));
+  ML_CUDA(cudaMemsetAsync(cx.rowstart.p, 0xff, sizeof(int32_t) * (size_t)std::max<int64_t>(1, ntab), st));
+  res->mu.alloc(st, (size_t)std::max<int64_t>(1, b.nrows));
+  res->beta.alloc(st, (size_t)std::max<int64_t>(1, npar));    res->beta.zero();   // Params: zero (fitter_lasso.hpp:29)
+  res->betahat.alloc(st, (size_t)std::max<int64_t>(1, npar)); res->betahat.zero();
+  res->pw.alloc(st, (size_t)std::max<int64_t>(1, npar));      res->pw.zero();
+  res->start.alloc(st, (size_t)std::max<int64_t>(1, nstart));
+  res->offset.alloc(st, std::max(1, noff));                   res->offset.zero();
+  cx.old_beta.alloc(st, (size_t)std::max<int64_t>(1, npar));  cx.old_beta.zero();
+  cx.old_off.alloc(st, std::max(1, noff));                    cx.old_off.zero();
+  cx.mu_res.alloc(st, (size_t)std::max<int64_t>(1, b.nrows));
+  const bool want_outer = p.nouter > 1;
+  if (want_outer) cx.mu_outer.alloc(st, (size_t)std::max<int64_t>(1, b.nrows));
+  cx.ctl.alloc(st, nj);
+  cx.off_part.alloc(st, 2 * (size_t)std::max(1, n_rt));
+  cx.row_part.alloc(st, 3 * (size_t)std::max(1, n_rt));
+  cx.tv_part.alloc(st, std::max(1, n_pt));
+  cx.scalars.alloc(st, 5 * (size_t)nj);
+  cx.sums.alloc(st, 2 * std::max<size_t>(1, series.size()));
+
+  // Jobs that failed after their row tiles were built (P < 2, lambda2 <= 0) own no slice of the
+  // parameter arrays: the index kernels test alive[job], every later kernel tests ctl[job], which is
+  // only ever set for jobs with status 0.
+  std::vector<int32_t> h_alive(nj);
+  for (int j = 0; j < nj; ++j) h_alive[j] = res->jobs[j].status == 0;
+  cx.ctl.upload(h_alive);
+  if (n_rt) {
+    if (fast) {
+      k_rank_unique<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p,
+                                          d_wprefix.p, cx.start0.p, cx.ctl.p, cx.pidx.p, cx.rowstart.p,
+                                          res->start.p);
+      ML_CHECK_LAUNCH();
+      eng.launches++;
+    } else {
+      k_even_bins<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, cx.ctl.p, cx.pidx.p);
+      ML_CHECK_LAUNCH();
+      k_rowstart_runs<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.dptr.p, cx.pidx.p, cx.ctl.p,
+                                            cx.rowstart.p);
+      ML_CHECK_LAUNCH();
+      if (n_pt) {
+        k_support_even<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.start0.p, res->start.p);
+        ML_CHECK_LAUNCH();
+      }
+      eng.launches += 3;
+    }
+  }
+  std::unique_ptr<FlsaPlan> plan;
+  if (!series.empty()) plan = std::make_unique<FlsaPlan>(eng, series, npar);
+
+  // ---- IRLS state machine (core/Posterior.ipp:22-59, 99-110, 204-252) ----------------------------
+  enum { S_INIT_EVAL, S_UPDATE, S_DAMP, S_DONE };
+  struct St {
+    int state = S_DONE;
+    uint32_t it = 0, outer = 0, dstep = 0;
+    double old_mlogp = 0, m = 0, dres = 0, dout = 0;
+    bool converged = false, first = true, have_m = false;
+  };
+  std::vector<St> S(nj);
+  int alive = 0;
+  for (int j = 0; j < nj; ++j)
+    if (!res->jobs[j].status) { S[j].state = S_INIT_EVAL; ++alive; }
+  const double log2pi = std::log(2 * M_PI * 1.0 * 1.0);
+  const double wnew = 1 - 5 / 10.;
+  RowCols rc{b.nmeth.p, b.cov.p, cx.pidx.p, cx.mu_res.p};
+  std::vector<int32_t> ctl(nj), skip(series.size());
+  std::vector<double> sc(5 * (size_t)nj);
+  // mu_res must hold something finite for the first evaluation's max|mu - mu_res| (ignored at it = 0)
+  cx.mu_res.zero();
+  if (want_outer) cx.mu_outer.zero();
+
+  auto finish_iterate = [&](int j) {
+    St& s = S[j];
+    JobHost& jh = res->jobs[j];
+    if (p.max_iter == 1) s.converged = true;                       // Posterior.ipp:57
+    if (p.nouter <= 1) { s.state = S_DONE; jh.outer_iters = 1; return 0; }
+    int copy = 0;
+    const uint32_t i = s.outer;
+    jh.outer_iters = (int)i + 1;
+    if (i > 0) {
+      if (s.dout < p.tol_val) { s.state = S_DONE; return 0; }      // :213-217
+      s.converged = false;                                         // :219
+    }
+    copy |= CTL_COPY_OUTER;                                        // mu_old = mu (:222)
+    if (!(std::isfinite(p.lambda2) && std::isfinite(p.hyper))) { s.converged = false; s.state = S_DONE; return copy; }
+    s.outer = i + 1;
+    if (s.outer < p.nouter) {
+      // next iterate(): set_converged(false); old_mlogp = -log posterior at the current parameters,
+      // which is the value of the last evaluation (same parameters, deterministic kernels)
+      s.converged = false;
+      s.old_mlogp = s.m;
+      s.it = 0;
+      s.state = p.max_iter > 0 ? S_UPDATE : S_DONE;
+    } else {
+      s.state = S_DONE;
+    }
+    return copy;
+  };
+
+  while (alive > 0) {
+    bool any_update = false, any_damp = false, any_eval = false;
+    for (int j = 0; j < nj; ++j) {
+      int c = 0;
+      const St& s = S[j];
+      if (s.state == S_UPDATE) { c |= CTL_UPDATE | CTL_EVAL; any_update = true; }
+      if (s.state == S_DAMP) { c |= CTL_DAMP | CTL_EVAL; any_damp = true; }
+      if (s.state == S_INIT_EVAL) c |= CTL_EVAL;
+      if (s.first) c |= CTL_FIRST;
+      if (c & CTL_EVAL) any_eval = true;
+      ctl[j] = (s.state == S_DONE) ? 0 : c;
+    }
+    cx.ctl.upload(ctl);
+    if (any_update) {
+      k_pseudodata<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.dptr.p, cx.design.p,
+                                              cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
+                                              res->pw.p);
+      ML_CHECK_LAUNCH();
+      k_offset_partial<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p);
+      ML_CHECK_LAUNCH();
+      k_offset_finalize<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
+                                                          cx.dtile0.p, cx.off_part.p, res->offset.p,
+                                                          cx.old_off.p);
+      ML_CHECK_LAUNCH();
+      eng.launches += 3;
+      for (int j = 0; j < nj; ++j)
+        if (!res->jobs[j].status)
+          for (int e = 0; e < hj[j].E; ++e) skip[hj[j].ser0 + e] = (ctl[j] & CTL_UPDATE) ? 0 : 1;
+      plan->solve(res->betahat.p, res->pw.p, res->beta.p, 1, p.lambda1, cx.sums.p, &skip);
+      k_center<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, cx.sums.p, res->beta.p);
+      ML_CHECK_LAUNCH();
+      eng.launches++;
+      for (int j = 0; j < nj; ++j)
+        if (ctl[j] & CTL_UPDATE) res->jobs[j].irls_steps++;
+    }
+    if (any_damp) {
+      k_damp<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, wnew, res->beta.p, cx.old_beta.p,
+                                        res->offset.p, cx.old_off.p);
+      ML_CHECK_LAUNCH();
+      eng.launches++;
+      for (int j = 0; j < nj; ++j)
+        if (ctl[j] & CTL_DAMP) res->jobs[j].dampings++;
+    }
+    if (any_eval) {
+      k_eval_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p, res->beta.p,
+                                        res->offset.p, log2pi, res->mu.p, cx.mu_outer.p, want_outer ? 1 : 0,
+                                        cx.row_part.p);
+      ML_CHECK_LAUNCH();
+      k_tv_partial<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, res->beta.p, cx.tv_part.p);
+      ML_CHECK_LAUNCH();
+      k_job_finalize<<<cdiv(nj, 64), 64, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
+                                                  cx.scalars.p);
+      ML_CHECK_LAUNCH();
+      eng.launches += 3;
+      cx.scalars.download(sc.data(), sc.size());
+      ML_CUDA(cudaStreamSynchronize(st));
+    }
+    // ---- host decisions -------------------------------------------------------------------------
+    bool any_copy = false;
+    for (int j = 0; j < nj; ++j) {
+      St& s = S[j];
+      if (s.state == S_DONE || !(ctl[j] & CTL_EVAL)) { ctl[j] = 0; continue; }
+      JobHost& jh = res->jobs[j];
+      const double m = sc[5 * (size_t)j];
+      s.m = m;
+      s.dres = sc[5 * (size_t)j + 3];
+      s.dout = sc[5 * (size_t)j + 4];
+      jh.mlogp = m;
+      int copy = 0;
+      if (s.state == S_INIT_EVAL) {                                // Posterior.ipp:25
+        s.old_mlogp = m;
+        s.it = 0;
+        s.converged = false;
+        if (p.max_iter > 0) s.state = S_UPDATE;
+        else copy = finish_iterate(j);
+      } else {
+        if (s.state == S_UPDATE) s.dstep = 0;
+        // adapt_all_params (:99-110) with AdaptiveDampingPolicy<1,5,10> (posterior_policies.hpp:57-68)
+        const uint32_t ds = s.dstep++;
+        if (ds < 10 && m > s.old_mlogp) {
+          s.state = S_DAMP;
+        } else {
+          if (std::isnan(m)) { jh.status = 16; s.state = S_DONE; }   // :36
+          else {
+            bool conv = false;
+            if (s.it > 0 && s.dres < p.tol_val) conv = true;       // :37-45
+            if (conv) {
+              s.converged = true;
+              copy = finish_iterate(j);
+            } else {
+              // mu_old = mu; old_mlogp = mlogp; refresh residuals (:46-51)
+              s.old_mlogp = m;
+              s.first = false;
+              s.it++;
+              const bool more = s.it < p.max_iter;
+              // the refreshed residuals are only ever read by a later update: skip the copy when this
+              // job can never update again
+              if (more || p.nouter > 1) copy |= CTL_COPY_RES;
+              if (more) s.state = S_UPDATE;
+              else copy |= finish_iterate(j);
+            }
+          }
+        }
+      }
+      ctl[j] = copy;
+      if (copy) any_copy = true;
+      if (s.state == S_DONE) {
+        --alive;
+        jh.converged = s.converged ? 1 : 0;
+      }
+    }
+    if (any_copy) {
+      cx.ctl.upload(ctl);
+      k_copy_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, res->mu.p, cx.mu_res.p,
+                                        want_outer ? cx.mu_outer.p : nullptr);
+      ML_CHECK_LAUNCH();
+      eng.launches++;
+    }
+  }
+  for (int j = 0; j < nj; ++j) {
+    JobHost& jh = res->jobs[j];
+    jh.hyper = (p.model == MODEL_FAST) ? 1.0 : p.hyper;
+  }
+  ML_CUDA(cudaStreamSynchronize(st));
+  return res;
+}
+
+void result_fast_diff_combine(Engine& eng, Result& r) {
+  // rebuild the parameter tiles of the valid jobs (cheap) and run one elementwise kernel
+  cudaStream_t st = eng.stream;
+  std::vector<JobDev> hj(r.jobs.size());
+  std::vector<ParTile> pt;
+  for (size_t j = 0; j < r.jobs.size(); ++j) {
+    const JobHost& jh = r.jobs[j];
+    memset(&hj[j], 0, sizeof(JobDev));
+    if (jh.status) continue;
+    hj[j].par0 = jh.par0;
+    hj[j].P = (int32_t)jh.P;
+    hj[j].E = jh.E;
+    for (int e = 1; e < jh.E; ++e)
+      for (int k = 0; k < jh.P; k += PAR_TILE)
+        pt.push_back(ParTile{(int32_t)j, e, k, (int32_t)std::min<int64_t>(PAR_TILE, jh.P - k)});
+  }
+  if (pt.empty()) return;
+  DevBuf<JobDev> d_jobs(st, hj.size());
+  d_jobs.upload(hj);
+  DevBuf<ParTile> d_pt(st, pt.size());
+  d_pt.upload(pt);
+  k_fast_diff<<<(int)pt.size(), PAR_TILE, 0, st>>>(d_pt.p, d_jobs.p, r.beta.p, r.betahat.p, r.pw.p);
+  ML_CHECK_LAUNCH();
+  eng.launches++;
+  ML_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace ml

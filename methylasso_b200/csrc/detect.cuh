@@ -1,0 +1,101 @@
+// detect.cuh — host-side objects of the batched methylation_detection engine.
+#pragma once
+#include <memory>
+
+#include "common.h"
+#include "flsa.cuh"
+#include "irls_core.cuh"
+#include "segment.cuh"
+
+namespace ml {
+
+// mirror of ml_params (include/methylasso_b200.h)
+struct Params {
+  double lambda2, max_lambda2, lambda1, tol_val, bf_per_kb, hyper;
+  uint32_t max_iter, nouter, ref;
+  int32_t model;
+  int32_t optimize_lambda2, optimize_hyper;
+};
+
+// per-job record read by every IRLS kernel
+struct JobDev {
+  int64_t row0;     // first row of the job in the batch columns
+  int64_t par0;     // first parameter (estimator 0) in the parameter arrays; E*P contiguous
+  int64_t tab0;     // first entry of the (dataset x param) -> first-row table
+  int32_t nrows;
+  int32_t P, D, E;
+  int32_t dptr0;    // first of the D+1 dataset row offsets (job-relative) in the dptr array
+  int32_t des0;     // first of the D*E design coefficients
+  int32_t off0;     // first of the D offsets
+  int32_t ser0;     // first FLSA series (one per estimator)
+  int32_t rtile0;   // first row tile
+  int32_t ptile0;   // first parameter tile
+  int32_t n_rtiles, n_ptiles;
+  int32_t model;
+  int32_t pad;
+  double lambda2, nu;
+  // even-bin geometry (FULL)
+  double lower, size;
+  uint32_t nbins, pad2;
+};
+
+struct RowTile {   // never straddles a (job, dataset) boundary
+  int32_t job, d;
+  int32_t r0;      // job-relative first row
+  int32_t cnt;
+};
+struct ParTile {   // never straddles a (job, estimator) boundary
+  int32_t job, e;
+  int32_t k0, cnt;
+};
+
+constexpr int ROW_TILE = 1024;   // 256 threads x 4 rows
+constexpr int PAR_TILE = 256;
+
+enum : int32_t {  // per-job control bits, re-uploaded every global step of the IRLS loop
+  CTL_UPDATE = 1, CTL_DAMP = 2, CTL_EVAL = 4, CTL_COPY_RES = 8, CTL_COPY_OUTER = 16, CTL_FIRST = 32
+};
+
+struct Batch {
+  Engine* eng = nullptr;
+  int njobs = 0;
+  int64_t nrows = 0;
+  std::vector<int64_t> job_ptr;
+  std::vector<int32_t> hint_D, hint_C;  // dataset / condition of each job's last row (host copy)
+  DevBuf<int32_t> dataset, condition, replicate, pos, nmeth, cov;
+  DevBuf<int64_t> d_job_ptr;
+};
+
+struct JobHost {
+  int32_t status = 0;
+  int64_t nrows = 0, P = 0;
+  int32_t D = 0, E = 0, C = 0;
+  int64_t par0 = 0, row0 = 0;
+  int32_t off0 = 0;
+  int32_t converged = 0, irls_steps = 0, dampings = 0, outer_iters = 0;
+  double hyper = 0, mlogp = 0, lambda2 = 0;
+};
+
+struct Result {
+  Engine* eng = nullptr;
+  std::vector<JobHost> jobs;
+  int64_t nrows = 0, npar = 0;  // totals over the batch (npar = sum E*P over valid jobs)
+  int32_t noff = 0;
+  DevBuf<double> mu;                      // per row (rows of failed jobs are untouched)
+  DevBuf<double> beta, betahat, pw;       // per parameter
+  DevBuf<double> start;                   // per (job, param): bin start truncated to int, as double
+  DevBuf<double> offset;
+  std::vector<int64_t> start0;            // per job: offset into start (P entries)
+  int64_t nstart = 0;
+  // segments of the last ml_result_segments call (query-then-fetch without recomputing)
+  std::unique_ptr<SegDeviceOut> seg_cache;
+  double seg_tol = 0;
+};
+
+std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                                    const int32_t* condition, const int32_t* replicate,
+                                    const int32_t* pos, const int32_t* nmeth, const int32_t* cov);
+std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p);
+void result_fast_diff_combine(Engine& eng, Result& r);
+
+}  // namespace ml

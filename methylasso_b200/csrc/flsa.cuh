@@ -1,0 +1,74 @@
+// flsa.cuh — host interface of the batched weighted 1-D FLSA solver (kernels in flsa.cu).
+#pragma once
+#include "common.h"
+#include "flsa_core.cuh"
+
+namespace ml {
+
+struct FlsaSeries {
+  int64_t off;  // element offset of the series in the concatenated y / w / beta arrays
+  int32_t n;
+  double lam;
+};
+
+struct TileDesc {
+  int32_t series;
+  int32_t t0;    // first element of the tile within the series
+  int32_t cnt;   // elements in the tile
+  int32_t idx;   // tile index within the series
+};
+
+constexpr int FLSA_TILE_THREADS = 256;
+constexpr int FLSA_TILE_VEC = 8;
+constexpr int FLSA_TILE = FLSA_TILE_THREADS * FLSA_TILE_VEC;
+
+// A plan owns everything that depends only on the series lengths (chunk / tile tables, knot-state
+// and back-pointer scratch) so the IRLS loop can re-solve the same shapes without re-planning.
+class FlsaPlan {
+ public:
+  FlsaPlan(Engine& eng, const std::vector<FlsaSeries>& series, int64_t total_len);
+
+  // Solve every series: y, w, beta are device arrays of total_len doubles.
+  //   post = 0: beta = raw DP solution
+  //   post = 1: beta = soft_threshold(clamp(beta, +-35), lambda1)   (FusedLassoGaussianEstimator::get)
+  // If d_sums != nullptr (2 doubles per series) it receives, per series, sum(beta*w) and sum(w)
+  // over the post-processed beta (centring numerator / denominator, params_helpers.hpp:27),
+  // accumulated tile by tile in a fixed order.
+  // skip_series (optional, one int per series): non-zero entries are left untouched.
+  void solve(const double* d_y, const double* d_w, double* d_beta, int post, double lambda1,
+             double* d_sums, const std::vector<int32_t>* skip_series = nullptr);
+
+  int n_series() const { return (int)series_.size(); }
+  int n_chunks() const { return n_chunks_; }
+  int n_tiles() const { return n_tiles_; }
+  int chunk_len() const { return chunk_; }
+  int warm_len() const { return warm_; }
+  // counters of the last solve (read back with the overflow flags)
+  struct Stats { int chunks_unresolved_after_a = 0, series_fallback = 0; };
+  Stats last_stats() const { return stats_; }
+
+ private:
+  Engine& eng_;
+  std::vector<FlsaSeries> series_;
+  int64_t total_len_;
+  int chunk_ = 0, warm_ = 0, n_chunks_ = 0, n_tiles_ = 0, max_tiles_per_series_ = 0;
+  DevBuf<SeriesDesc> d_series_;
+  DevBuf<ChunkDesc> d_chunks_;
+  DevBuf<ChunkState> d_states_;
+  DevBuf<TileDesc> d_tiles_;
+  DevBuf<int32_t> d_series_tile0_;  // first tile of each series (+1 sentinel)
+  DevBuf<double> d_tm_, d_tp_;
+  DevBuf<double> d_beta_last_;
+  DevBuf<int32_t> d_flags_;         // per series: bit0 overflow, bit1 clamp-order violation
+  DevBuf<int32_t> d_counters_;      // [0] chunks not done after pass A
+  DevBuf<Clamp> d_tile_agg_;
+  DevBuf<double> d_tile_in_;
+  DevBuf<double> d_tile_sums_;      // 2 per tile
+  DevBuf<int32_t> d_skip_;
+  std::vector<SeriesDesc> h_series_;
+  std::vector<int32_t> h_series_tile0_;
+  Stats stats_;
+  void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);
+};
+
+}  // namespace ml

@@ -1,0 +1,326 @@
+// segment.cu — segment_methylation_helper on sm_100a (K15).
+//
+// Replaces src/methylation_helpers.cpp:6-72: a single sweep over the estimates table that opens a
+// new segment when |beta_i - beta_at_segment_start| > tol_val or the estimate changes, and emits
+// per-segment weighted statistics.  The dependence on the SEGMENT-START beta makes the sweep
+// sequential, but only over RUNS of equal beta (the FLSA output is exactly piecewise constant):
+//   1. run heads        : beta_i != beta_{i-1} or group start            (parallel, rows)
+//   2. compaction       : exclusive scan of the head flags               (3-phase scan)
+//   3. tolerance merge  : one thread per group walks its runs            (sequential over runs)
+//   4. compaction of segment heads, then one thread per segment adds its rows in row order — the
+//      reference's own summation order, so betahat / pseudoweight / stdev are bit-identical.
+// A group is one estimate of one job (one `estimate_id` block of one table).
+#include <algorithm>
+#include <cstring>
+
+#include "segment.cuh"
+
+namespace ml {
+
+namespace {
+
+constexpr int STILE = 2048;
+
+// ---- generic exclusive scan of int32 flags (3 phases, no inter-block waiting) -----------------
+__global__ void __launch_bounds__(256)
+k_scan_tile_sums(const int32_t* __restrict__ flags, int64_t n, int32_t* __restrict__ tile_sum) {
+  __shared__ int32_t sm[8];
+  const int64_t base = (int64_t)blockIdx.x * STILE;
+  int32_t c = 0;
+  for (int i = threadIdx.x; i < STILE; i += 256)
+    if (base + i < n) c += flags[base + i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int32_t s = 0;
+    for (int k = 0; k < 8; ++k) s += sm[k];
+    tile_sum[blockIdx.x] = s;
+  }
+}
+// single block: exclusive scan of the tile sums in place; total -> *total
+__global__ void __launch_bounds__(256)
+k_scan_block(int32_t* __restrict__ tile_sum, int ntiles, int32_t* __restrict__ total) {
+  __shared__ int32_t sm[8];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base = 0; base < ntiles; base += 256) {
+    const int t = base + threadIdx.x;
+    const int32_t c = t < ntiles ? tile_sum[t] : 0;
+    int32_t inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) sm[wid] = inc;
+    __syncthreads();
+    int32_t before = carry_s;
+    for (int k = 0; k < wid; ++k) before += sm[k];
+    if (t < ntiles) tile_sum[t] = before + inc - c;
+    __syncthreads();
+    if (threadIdx.x == 255) carry_s = before + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+// positions: pos[i] = exclusive prefix of flags; if compact != nullptr, compact[pos[i]] = i for heads
+__global__ void __launch_bounds__(256)
+k_scan_apply(const int32_t* __restrict__ flags, int64_t n, const int32_t* __restrict__ tile_base,
+             int32_t* __restrict__ pos, int32_t* __restrict__ compact) {
+  __shared__ int32_t sm[8];
+  constexpr int V = STILE / 256;
+  const int64_t base = (int64_t)blockIdx.x * STILE + (int64_t)threadIdx.x * V;
+  int32_t f[V];
+  int32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    f[k] = (base + k < n) ? flags[base + k] : 0;
+    mine += f[k];
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += o;
+  }
+  if (lane == 31) sm[wid] = inc;
+  __syncthreads();
+  int32_t run = tile_base[blockIdx.x] + inc - mine;
+  for (int k = 0; k < wid; ++k) run += sm[k];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    if (base + k < n) {
+      if (pos) pos[base + k] = run;
+      if (compact && f[k]) compact[run] = (int32_t)(base + k);
+    }
+    run += f[k];
+  }
+}
+
+struct Scan {
+  DevBuf<int32_t> tile_sum, total;
+  int32_t run(Engine& eng, const int32_t* flags, int64_t n, int32_t* pos, int32_t* compact) {
+    cudaStream_t st = eng.stream;
+    const int nt = cdiv(n, STILE);
+    tile_sum.alloc(st, std::max(1, nt));
+    total.alloc(st, 1);
+    k_scan_tile_sums<<<nt, 256, 0, st>>>(flags, n, tile_sum.p);
+    ML_CHECK_LAUNCH();
+    k_scan_block<<<1, 256, 0, st>>>(tile_sum.p, nt, total.p);
+    ML_CHECK_LAUNCH();
+    k_scan_apply<<<nt, 256, 0, st>>>(flags, n, tile_sum.p, pos, compact);
+    ML_CHECK_LAUNCH();
+    eng.launches += 3;
+    int32_t h = 0;
+    total.download(&h, 1);
+    ML_CUDA(cudaStreamSynchronize(st));
+    return h;
+  }
+};
+
+// ---- segmentation kernels ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_seg_run_heads(const SegGroup* __restrict__ groups, const int32_t* __restrict__ tile_group,
+                const int64_t* __restrict__ tile_r0, const double* __restrict__ beta,
+                int32_t* __restrict__ flags) {
+  const SegGroup G = groups[tile_group[blockIdx.x]];
+  const int64_t r0 = tile_r0[blockIdx.x];
+  const int64_t rend = min(r0 + (int64_t)STILE, G.row0 + G.nrows);
+  for (int64_t i = r0 + threadIdx.x; i < rend; i += 256)
+    flags[i] = (i == G.row0 || beta[i] != beta[i - 1]) ? 1 : 0;
+}
+
+// one thread per group: walk the runs, open a segment when |beta_run - beta_segment_start| > tol
+// (methylation_helpers.cpp:23; the estimate change of :42 is the group boundary)
+__global__ void k_seg_merge(const SegGroup* __restrict__ groups, int ngroups,
+                            const int32_t* __restrict__ run_pos /*row -> run index*/,
+                            const int32_t* __restrict__ run_row, int32_t n_runs,
+                            const double* __restrict__ beta, double tol, int32_t* __restrict__ seg_head) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ngroups) return;
+  const SegGroup G = groups[g];
+  if (G.nrows == 0) return;
+  const int r_first = run_pos[G.row0];
+  // empty groups were dropped by the host, so the next group's first run closes this one
+  const int rend = (g + 1 < ngroups) ? run_pos[groups[g + 1].row0] : n_runs;
+  double curr = beta[run_row[r_first]];
+  seg_head[r_first] = 1;
+  for (int r = r_first + 1; r < rend; ++r) {
+    const double b = beta[run_row[r]];
+    if (fabs(b - curr) > tol) { seg_head[r] = 1; curr = b; }
+    else seg_head[r] = 0;
+  }
+}
+
+__device__ __forceinline__ int32_t seg_start_at(const SegGroup& G, const void* start, int start_f64,
+                                                int64_t row) {
+  const int64_t k = G.start0 + (row - G.row0);
+  return start_f64 ? (int32_t)((const double*)start)[k] : ((const int32_t*)start)[k];
+}
+
+// one thread per segment: rows added in row order (methylation_helpers.cpp:14-18, 24-40, 60-67)
+__global__ void k_seg_emit(const SegGroup* __restrict__ groups, const int32_t* __restrict__ row_group,
+                           const int32_t* __restrict__ seg_run, int32_t n_segs,
+                           const int32_t* __restrict__ run_row, const int32_t* __restrict__ seg_of_run,
+                           const int32_t* __restrict__ run_pos, const void* __restrict__ start,
+                           int start_f64, const double* __restrict__ beta,
+                           const double* __restrict__ betahat, const double* __restrict__ pw, SegOut out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs) return;
+  const int r = seg_run[s];
+  const int64_t first = run_row[r];
+  const int g = row_group[r];   // group of the run (stored per run)
+  const SegGroup G = groups[g];
+  const int64_t gend = G.row0 + G.nrows;
+  int64_t last;       // one past the last row of the segment
+  bool next_same_group = false;
+  if (s + 1 < n_segs) {
+    const int64_t nf = run_row[seg_run[s + 1]];
+    if (nf < gend) { last = nf; next_same_group = true; }
+    else last = gend;
+  } else {
+    last = gend;
+  }
+  const double cb = beta[first];
+  double d0 = betahat[first] - cb;
+  double res = pw[first] * d0;
+  double var = res * d0;
+  double w = pw[first];
+  for (int64_t i = first + 1; i < last; ++i) {
+    const double d = betahat[i] - beta[i];
+    res += pw[i] * d;
+    var += pw[i] * d * d;
+    w += pw[i];
+  }
+  const int seg_in_group = s - seg_of_run[run_pos[G.row0]];
+  if (out.job) out.job[s] = G.job;
+  out.estimate_id[s] = G.estimate_id;
+  out.seg_id[s] = seg_in_group + 1;
+  out.start[s] = (uint32_t)seg_start_at(G, start, start_f64, first);
+  out.end[s] = next_same_group ? (uint32_t)(seg_start_at(G, start, start_f64, last) - 1)
+                               : (uint32_t)seg_start_at(G, start, start_f64, gend - 1);
+  out.beta[s] = cb;
+  out.pseudoweight[s] = w;
+  out.betahat[s] = res / w + cb;
+  out.stdev[s] = sqrt(var / w - res * res / (w * w));
+}
+
+__global__ void k_run_group(const int32_t* __restrict__ run_row, int32_t n_runs,
+                            const int64_t* __restrict__ group_row0, int ngroups,
+                            int32_t* __restrict__ run_group) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const int64_t row = run_row[r];
+  int lo = 0, hi = ngroups;   // last group with row0 <= row
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (group_row0[mid] <= row) lo = mid; else hi = mid;
+  }
+  run_group[r] = lo;
+}
+
+__global__ void k_group_heads(const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || idx[i] != idx[i - 1]) ? 1 : 0;
+}
+
+}  // namespace
+
+// Core: groups over device arrays -> segments in device buffers owned by `ds`.
+int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int64_t nrows,
+                       const void* d_start, int start_f64, const double* d_beta, const double* d_betahat,
+                       const double* d_pw, double tol_val, SegDeviceOut& ds) {
+  cudaStream_t st = eng.stream;
+  std::vector<SegGroup> groups;
+  for (const SegGroup& g : groups_in)
+    if (g.nrows > 0) groups.push_back(g);
+  const int ng = (int)groups.size();
+  if (ng == 0 || nrows == 0) return 0;
+  if (nrows >= 0x7fffffff) throw MlError(19, "segment table too large");
+  std::vector<int32_t> tile_group;
+  std::vector<int64_t> tile_r0, group_row0(ng);
+  for (int g = 0; g < ng; ++g) {
+    group_row0[g] = groups[g].row0;
+    for (int64_t r = groups[g].row0; r < groups[g].row0 + groups[g].nrows; r += STILE) {
+      tile_group.push_back(g);
+      tile_r0.push_back(r);
+    }
+  }
+  DevBuf<SegGroup> d_groups(st, ng);
+  d_groups.upload(groups);
+  DevBuf<int32_t> d_tile_group(st, tile_group.size());
+  d_tile_group.upload(tile_group);
+  DevBuf<int64_t> d_tile_r0(st, tile_r0.size());
+  d_tile_r0.upload(tile_r0);
+  DevBuf<int64_t> d_group_row0(st, ng);
+  d_group_row0.upload(group_row0);
+  DevBuf<int32_t> flags(st, (size_t)nrows), run_pos(st, (size_t)nrows);
+  flags.zero();   // rows outside every group (none in practice) are not heads
+  k_seg_run_heads<<<(int)tile_group.size(), 256, 0, st>>>(d_groups.p, d_tile_group.p, d_tile_r0.p, d_beta,
+                                                          flags.p);
+  ML_CHECK_LAUNCH();
+  eng.launches++;
+  Scan scan;
+  DevBuf<int32_t> run_row(st, (size_t)nrows);
+  const int32_t n_runs = scan.run(eng, flags.p, nrows, run_pos.p, run_row.p);
+  DevBuf<int32_t> seg_head(st, std::max(1, n_runs)), seg_of_run(st, std::max(1, n_runs)),
+      seg_run(st, std::max(1, n_runs)), run_group(st, std::max(1, n_runs));
+  k_seg_merge<<<cdiv(ng, 64), 64, 0, st>>>(d_groups.p, ng, run_pos.p, run_row.p, n_runs, d_beta, tol_val,
+                                           seg_head.p);
+  ML_CHECK_LAUNCH();
+  k_run_group<<<cdiv(n_runs, 256), 256, 0, st>>>(run_row.p, n_runs, d_group_row0.p, ng, run_group.p);
+  ML_CHECK_LAUNCH();
+  eng.launches += 2;
+  const int32_t n_segs = scan.run(eng, seg_head.p, n_runs, seg_of_run.p, seg_run.p);
+  ds.alloc(st, n_segs);
+  SegOut out = ds.view();
+  k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
+                                                seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
+                                                d_betahat, d_pw, out);
+  ML_CHECK_LAUNCH();
+  eng.launches++;
+  ML_CUDA(cudaStreamSynchronize(st));
+  return n_segs;
+}
+
+// Host table in, host segments out (the Rcpp signature).
+int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, const int32_t* start,
+                           const double* beta, const double* betahat, const double* pw, double tol_val,
+                           SegHostOut& ho) {
+  if (n <= 0) throw MlError(19, "segment_methylation_helper needs at least one row");
+  cudaStream_t st = eng.stream;
+  DevBuf<int32_t> d_idx(st, (size_t)n), d_start(st, (size_t)n);
+  DevBuf<double> d_beta(st, (size_t)n), d_bh(st, (size_t)n), d_pw(st, (size_t)n);
+  d_idx.upload(estimate_id, n);
+  d_start.upload(start, n);
+  d_beta.upload(beta, n);
+  d_bh.upload(betahat, n);
+  d_pw.upload(pw, n);
+  // groups = maximal blocks of equal estimate_id (the reference compares neighbours only)
+  DevBuf<int32_t> gflags(st, (size_t)n), ghead(st, (size_t)n);
+  k_group_heads<<<cdiv(n, 256), 256, 0, st>>>(d_idx.p, n, gflags.p);
+  ML_CHECK_LAUNCH();
+  eng.launches++;
+  Scan scan;
+  const int32_t ng = scan.run(eng, gflags.p, n, nullptr, ghead.p);
+  std::vector<int32_t> heads(ng);
+  ghead.download(heads.data(), ng);
+  ML_CUDA(cudaStreamSynchronize(st));
+  std::vector<SegGroup> groups(ng);
+  for (int g = 0; g < ng; ++g) {
+    const int64_t r0 = heads[g], r1 = g + 1 < ng ? heads[g + 1] : n;
+    groups[g] = SegGroup{r0, r1 - r0, r0, estimate_id[r0], 0};
+  }
+  SegDeviceOut ds;
+  const int64_t S = segment_device(eng, groups, n, d_start.p, 0, d_beta.p, d_bh.p, d_pw.p, tol_val, ds);
+  ds.download(st, S, ho);
+  ML_CUDA(cudaStreamSynchronize(st));
+  return S;
+}
+
+}  // namespace ml

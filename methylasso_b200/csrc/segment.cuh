@@ -1,0 +1,61 @@
+// segment.cuh — host interface of the segment_methylation_helper kernels (segment.cu).
+#pragma once
+#include <algorithm>
+#include "common.h"
+
+namespace ml {
+
+// one estimate of one table: rows [row0, row0+nrows) of the beta/betahat/pw arrays; its `start`
+// column lives at start[start0 + (row - row0)]
+struct SegGroup {
+  int64_t row0, nrows, start0;
+  int32_t estimate_id, job;
+};
+
+struct SegOut {   // device pointers
+  int32_t *job, *estimate_id, *seg_id;
+  uint32_t *start, *end;
+  double *beta, *betahat, *pseudoweight, *stdev;
+};
+
+struct SegHostOut {  // caller buffers (any may be null)
+  int32_t *job = nullptr, *estimate_id = nullptr, *seg_id = nullptr;
+  uint32_t *start = nullptr, *end = nullptr;
+  double *beta = nullptr, *betahat = nullptr, *pseudoweight = nullptr, *stdev = nullptr;
+};
+
+struct SegDeviceOut {
+  DevBuf<int32_t> job, estimate_id, seg_id;
+  DevBuf<uint32_t> start, end;
+  DevBuf<double> beta, betahat, pseudoweight, stdev;
+  int64_t n = 0;
+  void alloc(cudaStream_t st, int64_t count) {
+    n = count;
+    const size_t c = (size_t)std::max<int64_t>(1, count);
+    job.alloc(st, c); estimate_id.alloc(st, c); seg_id.alloc(st, c);
+    start.alloc(st, c); end.alloc(st, c);
+    beta.alloc(st, c); betahat.alloc(st, c); pseudoweight.alloc(st, c); stdev.alloc(st, c);
+  }
+  SegOut view() { return SegOut{job.p, estimate_id.p, seg_id.p, start.p, end.p, beta.p, betahat.p, pseudoweight.p, stdev.p}; }
+  void download(cudaStream_t, int64_t count, SegHostOut& h) const {
+    const size_t c = (size_t)count;
+    if (h.job) job.download(h.job, c);
+    if (h.estimate_id) estimate_id.download(h.estimate_id, c);
+    if (h.seg_id) seg_id.download(h.seg_id, c);
+    if (h.start) start.download(h.start, c);
+    if (h.end) end.download(h.end, c);
+    if (h.beta) beta.download(h.beta, c);
+    if (h.betahat) betahat.download(h.betahat, c);
+    if (h.pseudoweight) pseudoweight.download(h.pseudoweight, c);
+    if (h.stdev) stdev.download(h.stdev, c);
+  }
+};
+
+int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups, int64_t nrows, const void* d_start,
+                       int start_f64, const double* d_beta, const double* d_betahat, const double* d_pw,
+                       double tol_val, SegDeviceOut& out);
+int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, const int32_t* start,
+                           const double* beta, const double* betahat, const double* pw, double tol_val,
+                           SegHostOut& out);
+
+}  // namespace ml

@@ -1,0 +1,113 @@
+/* oracle/methylasso_oracle.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C CPU restatement of MethyLasso's segmentation hot path (the IRLS loop of
+ * `methylation_detection` wrapped around the weighted 1-D fused-lasso DP).  Only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library; the product (libmethylasso_b200.so) never does.
+ *
+ * Parity status: the reference ships no tests, fixtures or golden vectors
+ * (SURVEY.md §4), so this oracle is pinned by (a) the reference's own DP kernel
+ * compiled verbatim into oracle/_ref/libtfdp_ref.so (bit-exact comparison, see
+ * tests/test_oracle.py) and (b) the two known answers recorded in BASELINE.md §2.
+ * Everything above the DP (Rcpp/Eigen code) cannot be compiled here (no R, Rcpp,
+ * Eigen): for that part parity is UNPINNED by the reference — it is a literal,
+ * line-cited restatement only.
+ */
+#ifndef METHYLASSO_ORACLE_H
+#define METHYLASSO_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* same numeric values as include/methylasso_b200.h (kept in sync by tests/test_abi.py) */
+enum {
+  ORC_OK = 0,
+  ORC_ERR_TOO_FEW_ROWS = 1,        /* Observations.hpp:31 */
+  ORC_ERR_SIZE_MISMATCH = 2,       /* Observations.hpp:33-34 ; weighted_1d_flsa.cpp:9 */
+  ORC_ERR_FIRST_DATASET = 3,       /* Observations.hpp:40 */
+  ORC_ERR_FIRST_CONDITION = 4,     /* Observations.hpp:41 */
+  ORC_ERR_FIRST_REPLICATE = 5,     /* Observations.hpp:42 */
+  ORC_ERR_NOT_SORTED = 6,          /* Observations.hpp:46 */
+  ORC_ERR_DATASET_GAP = 7,         /* Observations.hpp:48 */
+  ORC_ERR_REPLICATE_GAP = 8,       /* Observations.hpp:50 */
+  ORC_ERR_CONDITION_GAP = 9,       /* Observations.hpp:52 */
+  ORC_ERR_REPLICATE_START = 10,    /* Observations.hpp:54 */
+  ORC_ERR_NEGATIVE_COUNT = 11,     /* MethData.hpp:18 */
+  ORC_ERR_NMETH_GT_COV = 12,       /* MethData.hpp:19 */
+  ORC_ERR_LAMBDA2 = 13,            /* fitter_lasso.ipp:4 */
+  ORC_ERR_TWO_CONDITIONS = 14,     /* difference_detection.cpp:28 */
+  ORC_ERR_BAD_REF = 15,            /* data_design_helpers.cpp:35 */
+  ORC_ERR_NAN = 16,                /* Posterior.ipp:36 */
+  ORC_ERR_TOO_FEW_PARAMS = 18,     /* reference: undefined behaviour; we refuse */
+  ORC_ERR_BAD_ARGUMENT = 19
+};
+
+enum { ORC_MODEL_FAST = 0, ORC_MODEL_FULL_SIGNAL = 1, ORC_MODEL_FULL_DIFFERENCE = 2 };
+
+typedef struct {
+  double lambda2, max_lambda2, lambda1, tol_val, bf_per_kb, hyper;
+  uint32_t max_iter, nouter, ref;
+  int32_t model;
+  int32_t optimize_lambda2, optimize_hyper; /* must be 0: out of scope */
+} orc_params;
+
+typedef struct {
+  int64_t n_rows;      /* N */
+  int64_t n_params;    /* P: unique positions (FAST) or Nbins (FULL) */
+  int32_t n_est;       /* E */
+  int32_t n_dsets;     /* D */
+  int32_t converged;
+  int32_t irls_steps;  /* total update_all_params calls */
+  int32_t dampings;    /* total damp_all_params calls */
+  int32_t outer_iters;
+  double hyper;
+  double last_mlogp;
+  double *mu;          /* N */
+  double *lambda2;     /* E */
+  double *offset;      /* D */
+  int32_t *estimate_id;/* E*P */
+  double *start, *beta, *betahat, *pseudoweight; /* E*P each */
+} orc_result;
+
+/* DP used inside orc_detect / orc_weighted_1d_flsa.  Default: the restatement
+ * orc_tf_dp_weight.  Tests and the CPU baseline may point it at the reference's own
+ * tf_dp_weight from oracle/_ref/libtfdp_ref.so. */
+typedef void (*orc_dp_fn)(int n, double *y, double *w, double lam, double *beta,
+                          double *x, double *a, double *b, double *tm, double *tp);
+void orc_set_dp(orc_dp_fn fn);
+
+void orc_tf_dp_weight(int n, double *y, double *w, double lam, double *beta,
+                      double *x, double *a, double *b, double *tm, double *tp);
+
+int orc_weighted_1d_flsa(int64_t n, const double *y, const double *wt, double lambda2,
+                         double lambda1, double *beta);
+
+int orc_check_observations(int64_t n, const int32_t *dataset, const int32_t *condition,
+                           const int32_t *replicate, const int32_t *pos, const int32_t *nmeth,
+                           const int32_t *coverage);
+
+int orc_detect(const orc_params *p, int64_t n, const int32_t *dataset, const int32_t *condition,
+               const int32_t *replicate, const int32_t *pos, const int32_t *nmeth,
+               const int32_t *coverage, orc_result *out);
+void orc_result_free(orc_result *r);
+
+/* segment_methylation_helper: returns number of segments written (<= n), or <0 on error.
+ * Outputs must be caller-allocated with capacity n. */
+int64_t orc_segment_helper(int64_t n, const int32_t *estimate_id, const int32_t *start,
+                           const double *beta, const double *betahat, const double *pseudoweight,
+                           double tol_val, int32_t *seg_estimate_id, int32_t *seg_id,
+                           uint32_t *seg_start, uint32_t *seg_end, double *seg_beta,
+                           double *seg_betahat, double *seg_pseudoweight, double *seg_stdev);
+
+/* R/fast_diff.R:15-28 combine, restated on the estimates table of one job. */
+int orc_fast_diff_combine(int64_t n_params, int32_t n_est, const double *beta, const double *betahat,
+                          const double *pseudoweight, double *out_beta, double *out_betahat,
+                          double *out_pseudoweight);
+
+const char *orc_strerror(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,189 @@
+"""ctypes binding of the TEST-ONLY CPU oracle (oracle/liboracle.so, oracle/_ref/libtfdp_ref.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  Nothing under methylasso_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_PATH = os.path.join(HERE, "_ref", "libtfdp_ref.so")
+
+MODEL_FAST, MODEL_FULL_SIGNAL, MODEL_FULL_DIFFERENCE = 0, 1, 2
+
+
+class OrcParams(C.Structure):
+    _fields_ = [("lambda2", C.c_double), ("max_lambda2", C.c_double), ("lambda1", C.c_double),
+                ("tol_val", C.c_double), ("bf_per_kb", C.c_double), ("hyper", C.c_double),
+                ("max_iter", C.c_uint32), ("nouter", C.c_uint32), ("ref", C.c_uint32),
+                ("model", C.c_int32), ("optimize_lambda2", C.c_int32), ("optimize_hyper", C.c_int32)]
+
+
+class OrcResult(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_params", C.c_int64), ("n_est", C.c_int32),
+                ("n_dsets", C.c_int32), ("converged", C.c_int32), ("irls_steps", C.c_int32),
+                ("dampings", C.c_int32), ("outer_iters", C.c_int32), ("hyper", C.c_double),
+                ("last_mlogp", C.c_double),
+                ("mu", C.POINTER(C.c_double)), ("lambda2", C.POINTER(C.c_double)),
+                ("offset", C.POINTER(C.c_double)), ("estimate_id", C.POINTER(C.c_int32)),
+                ("start", C.POINTER(C.c_double)), ("beta", C.POINTER(C.c_double)),
+                ("betahat", C.POINTER(C.c_double)), ("pseudoweight", C.POINTER(C.c_double))]
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def build(force=False):
+    """Compile liboracle.so (and oracle/_ref when /root/reference is present)."""
+    if force or not os.path.exists(LIB_PATH) or \
+            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(HERE, "methylasso_oracle.c")):
+        subprocess.check_call(["make", "-C", HERE, "-s", os.path.join(HERE, "liboracle.so")])
+    if (force or not os.path.exists(REF_PATH)) and os.path.exists("/root/reference/src/core/gfl/gfl_tf.c"):
+        subprocess.check_call(["make", "-C", HERE, "-s", "ref"])
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        dp = C.c_void_p
+        L.orc_set_dp.argtypes = [dp]
+        L.orc_weighted_1d_flsa.argtypes = [C.c_int64, dp, dp, C.c_double, C.c_double, dp]
+        L.orc_check_observations.argtypes = [C.c_int64] + [dp] * 6
+        L.orc_detect.argtypes = [C.POINTER(OrcParams), C.c_int64] + [dp] * 6 + [C.POINTER(OrcResult)]
+        L.orc_result_free.argtypes = [C.POINTER(OrcResult)]
+        L.orc_segment_helper.argtypes = [C.c_int64] + [dp] * 5 + [C.c_double] + [dp] * 8
+        L.orc_segment_helper.restype = C.c_int64
+        L.orc_fast_diff_combine.argtypes = [C.c_int64, C.c_int32] + [dp] * 6
+        L.orc_strerror.restype = C.c_char_p
+        L.orc_tf_dp_weight.argtypes = [C.c_int] + [dp, dp, C.c_double] + [dp] * 6
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own tf_dp_weight compiled verbatim (None if oracle/_ref is absent)."""
+    global _ref
+    if _ref is None and os.path.exists(REF_PATH):
+        R = C.CDLL(REF_PATH)
+        R.tf_dp_weight.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 6
+        _ref = R
+    return _ref
+
+
+def use_reference_dp(on=True):
+    """Route the oracle's DP calls through the reference's verbatim kernel (if available)."""
+    R = ref_lib()
+    if on and R is not None:
+        lib().orc_set_dp(C.cast(R.tf_dp_weight, C.c_void_p))
+        return True
+    lib().orc_set_dp(None)
+    return False
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _check(rc):
+    if rc != 0:
+        raise OracleError(rc, lib().orc_strerror(rc).decode())
+
+
+def tf_dp_weight(y, w, lam, which="port"):
+    """Raw DP (no clamp); which = 'port' (restatement) or 'reference' (verbatim gfl_tf.c)."""
+    y, w = _f64(y).copy(), _f64(w).copy()
+    n = y.size
+    beta = np.zeros(n)
+    x, a, b = np.zeros(2 * n + 2), np.zeros(2 * n + 2), np.zeros(2 * n + 2)
+    tm, tp = np.zeros(n + 1), np.zeros(n + 1)
+    fn = lib().orc_tf_dp_weight if which == "port" else ref_lib().tf_dp_weight
+    fn(n, _p(y), _p(w), float(lam), _p(beta), _p(x), _p(a), _p(b), _p(tm), _p(tp))
+    return beta, tm[:max(n - 1, 0)], tp[:max(n - 1, 0)]
+
+
+def weighted_1d_flsa(y, wt, lambda2, lambda1=0.0):
+    y, wt = _f64(y), _f64(wt)
+    if y.size != wt.size:
+        raise OracleError(2, "Input vectors must be of same size!")
+    beta = np.zeros(y.size)
+    _check(lib().orc_weighted_1d_flsa(y.size, _p(y), _p(wt), float(lambda2), float(lambda1), _p(beta)))
+    return beta
+
+
+def check_observations(t):
+    return lib().orc_check_observations(
+        t["pos"].size, _p(_i32(t["dataset"])), _p(_i32(t["condition"])), _p(_i32(t["replicate"])),
+        _p(_i32(t["pos"])), _p(_i32(t["Nmeth"])), _p(_i32(t["coverage"])))
+
+
+def detect(t, model=MODEL_FAST, lambda2=25.0, tol_val=0.01, max_iter=1, nouter=1, max_lambda2=None,
+           lambda1=0.0, bf_per_kb=50.0, hyper=100.0, ref=1):
+    """methylation_detection on one chromosome table (dict of int32 columns)."""
+    p = OrcParams(lambda2, lambda2 + 1 if max_lambda2 is None else max_lambda2, lambda1, tol_val,
+                  bf_per_kb, hyper, max_iter, nouter, ref, model, 0, 0)
+    cols = [_i32(t[k]) for k in ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")]
+    res = OrcResult()
+    rc = lib().orc_detect(C.byref(p), cols[0].size, *[_p(c) for c in cols], C.byref(res))
+    _check(rc)
+    try:
+        n, P, E, D = res.n_rows, res.n_params, res.n_est, res.n_dsets
+
+        def arr(ptr, k, dt=np.float64):
+            return np.ctypeslib.as_array(ptr, shape=(k,)).astype(dt, copy=True)
+        out = dict(mu=arr(res.mu, n), lambda2=arr(res.lambda2, E), offset=arr(res.offset, D),
+                   converged=bool(res.converged), hyper=res.hyper, irls_steps=res.irls_steps,
+                   dampings=res.dampings, outer_iters=res.outer_iters, last_mlogp=res.last_mlogp,
+                   n_params=P, n_est=E, n_dsets=D,
+                   estimates=dict(estimate_id=arr(res.estimate_id, E * P, np.int32),
+                                  start=arr(res.start, E * P), beta=arr(res.beta, E * P),
+                                  betahat=arr(res.betahat, E * P),
+                                  pseudoweight=arr(res.pseudoweight, E * P)))
+    finally:
+        lib().orc_result_free(C.byref(res))
+    return out
+
+
+def segment_methylation_helper(est, tol_val=0.01):
+    idx, start = _i32(est["estimate_id"]), _i32(est["start"])
+    beta, bh, pw = _f64(est["beta"]), _f64(est["betahat"]), _f64(est["pseudoweight"])
+    n = idx.size
+    o = dict(estimate_id=np.zeros(n, np.int32), segment_id=np.zeros(n, np.int32),
+             start=np.zeros(n, np.uint32), end=np.zeros(n, np.uint32), beta=np.zeros(n),
+             betahat=np.zeros(n), pseudoweight=np.zeros(n), stdev=np.zeros(n))
+    S = lib().orc_segment_helper(n, _p(idx), _p(start), _p(beta), _p(bh), _p(pw), float(tol_val),
+                                 *[_p(o[k]) for k in ("estimate_id", "segment_id", "start", "end",
+                                                      "beta", "betahat", "pseudoweight", "stdev")])
+    if S < 0:
+        _check(int(-S))
+    return {k: v[:S].copy() for k, v in o.items()}
+
+
+def fast_diff_combine(est, n_params, n_est):
+    beta, bh, pw = _f64(est["beta"]), _f64(est["betahat"]), _f64(est["pseudoweight"])
+    ob, obh, opw = np.zeros_like(beta), np.zeros_like(bh), np.zeros_like(pw)
+    _check(lib().orc_fast_diff_combine(n_params, n_est, _p(beta), _p(bh), _p(pw), _p(ob), _p(obh), _p(opw)))
+    return dict(estimate_id=est["estimate_id"].copy(), start=est["start"].copy(), beta=ob, betahat=obh,
+                pseudoweight=opw)

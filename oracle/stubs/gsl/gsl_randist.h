@@ -1,0 +1,1 @@
+/* stub: see gsl_rng.h */

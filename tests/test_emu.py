@@ -1,0 +1,134 @@
+"""CPU emulation of the device logic (tests/emu): the same inline functions the CUDA kernels call,
+compiled with g++ -ffp-contract=off, checked against the oracle.  Catches logic errors in the
+chunked / sandwiched DP before any GPU time is spent."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from methylasso_b200 import synth
+from conftest import pooled_series
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu_flsa.cpp")
+LIB = os.path.join(HERE, "emu", "libemu_flsa.so")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(HERE, "..", "methylasso_b200", "csrc", f)
+                    for f in ("flsa_core.cuh", "irls_core.cuh", "hd.h")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
+    L = C.CDLL(LIB)
+    L.emu_clamp35_soft.restype = C.c_double
+    L.emu_clamp35_soft.argtypes = [C.c_double, C.c_double]
+
+    def run(y, w, lam, chunk=512, warm=512, tile=2048):
+        y, w = np.ascontiguousarray(y, float), np.ascontiguousarray(w, float)
+        n = y.size
+        beta, tm, tp = np.zeros(n), np.zeros(n + 1), np.zeros(n + 1)
+        st = np.zeros(8, np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = L.emu_flsa(n, p(y), p(w), C.c_double(lam), chunk, warm, p(beta), p(tm), p(tp), tile, p(st))
+        assert rc == 0
+        return beta, st
+    run.lib = L
+    return run
+
+
+@pytest.mark.parametrize("reps", [(1,), (3,)])
+@pytest.mark.parametrize("lam", [10.0, 25.0, 1000.0])
+def test_chunked_dp_bit_exact_on_count_data(emu, oracle, reps, lam):
+    """On count-valued pseudodata (the FAST path) every partial sum is exact, so the chunked run
+    reproduces the sequential reference bit for bit whatever the chunking."""
+    t = synth.chromosome_table(120_000, 31, reps)
+    y, w = pooled_series(t)
+    ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+    for chunk, warm in ((512, 512), (256, 64), (4096, 2048)):
+        beta, st = emu(y, w, lam, chunk, warm)
+        assert np.array_equal(beta, ref), (chunk, warm, st.tolist())
+        assert st[4] == 0  # no ring overflow on WGBS-like data
+
+
+def test_chunked_dp_generic_inputs_within_rounding(emu, oracle):
+    """Real-valued weights: exact in exact arithmetic; association of a few sums may differ."""
+    rng = np.random.default_rng(0)
+    worst = 0.0
+    for trial in range(400):
+        n = int(rng.integers(2, 500))
+        kind = trial % 5
+        if kind == 0:
+            y, w = rng.random(n), rng.integers(0, 3, n).astype(float)
+        elif kind == 1:
+            y, w = np.sort(rng.random(n)), rng.random(n)
+        elif kind == 2:
+            y, w = np.repeat(rng.random(n // 7 + 1), 7)[:n], rng.integers(0, 50, n).astype(float)
+        elif kind == 3:
+            y = rng.integers(0, 2, n).astype(float)
+            w = np.where(rng.random(n) < 0.8, 0.0, rng.integers(1, 30, n)).astype(float)
+        else:
+            y, w = rng.normal(size=n), rng.exponential(size=n)
+        lam = float(rng.choice([1e-3, 0.1, 0.5, 5.0, 25.0, 1000.0]))
+        ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+        beta, st = emu(y, w, lam, int(rng.choice([1, 2, 4, 16, 64])), int(rng.choice([1, 2, 8, 32])),
+                       int(rng.choice([1, 3, 8, 64])))
+        scale = max(1.0, np.max(np.abs(ref[np.isfinite(ref)])) if np.isfinite(ref).any() else 1.0)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(beta), ok)
+        if ok.any():
+            worst = max(worst, np.max(np.abs(beta[ok] - ref[ok])) / scale)
+    assert worst < 1e-11, worst
+
+
+def test_chunked_dp_edge_sizes(emu, oracle):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 4, 5, 6):
+        y, w = rng.random(n), rng.integers(1, 9, n).astype(float)
+        for lam in (0.0, 0.5, 50.0):
+            ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+            beta, _ = emu(y, w, lam, 2, 1, 2)
+            assert np.array_equal(beta, ref)
+
+
+def test_knot_ring_overflow_falls_back(emu, oracle):
+    """Strictly convex data with a tiny penalty keeps every knot alive: the 64-knot ring overflows and
+    the series is redone start-to-end with the reference's 2n scratch layout."""
+    n = 400
+    y = (np.arange(n) / n) ** 2 * 50
+    w = np.ones(n)
+    ref, _, _ = oracle.tf_dp_weight(y, w, 200.0, "port")
+    beta, st = emu(y, w, 200.0, 64, 16)
+    assert st[4] > 0
+    assert np.array_equal(beta, ref)
+
+
+def test_even_bin_matches_oracle_rule(emu):
+    rng = np.random.default_rng(5)
+    for lower, upper, bf in ((10_000.0, 3_400_000.0, 50.0), (5.0, 6.0, 2000.0), (0.0, 1e9, 0.004), (7.0, 7.0, 5000.0)):
+        size = upper - lower
+        nb = int((size + 1) * bf / 1000.0)
+        if nb < 1:
+            continue
+        v = np.concatenate([rng.integers(int(lower), int(upper) + 1, 5000).astype(float),
+                            [lower, upper], lower + np.arange(min(nb, 3000)) * size / nb])
+        v = v[(v >= lower) & (v <= upper)]
+        out = np.zeros(v.size, np.uint32)
+        emu.lib.emu_even_bin(v.size, v.ctypes.data_as(C.c_void_p), C.c_double(lower), C.c_double(size),
+                             C.c_uint(nb), out.ctypes.data_as(C.c_void_p))
+        bounds = lower + np.arange(nb + 1) * size / float(nb)
+        want = np.searchsorted(bounds, v, side="right").astype(np.int64) - 1
+        want[np.searchsorted(bounds, v, side="right") > nb] = nb - 1
+        if size > 0:
+            assert np.array_equal(out.astype(np.int64), want)
+        else:
+            assert np.all(out == nb - 1)
+
+
+def test_clamp_soft_threshold_semantics(emu):
+    f = emu.lib.emu_clamp35_soft
+    assert f(40.0, 0.0) == 35.0 and f(-40.0, 0.0) == -35.0 and f(0.3, 0.0) == 0.3
+    assert f(0.3, 0.5) == 0.0 and f(-0.3, 0.5) == 0.0 and f(2.0, 0.5) == 1.5 and f(-2.0, 0.5) == -1.5
+    assert f(float("nan"), 0.0) == -35.0   # std::max(-35, NaN) keeps -35 (reference behaviour)

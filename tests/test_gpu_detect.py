@@ -1,0 +1,233 @@
+"""GPU parity of the batched methylation_detection engine (through the C ABI) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from methylasso_b200 import api, synth
+from methylasso_b200._native import MlParams
+from test_oracle import FIXTURES, VALIDATION_CASES, fixture_table, _tbl
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-6  # north_star: fitted betas within 1e-6 relative (measured deviations are ~1e-15)
+
+
+def params(model=0, lambda2=25.0, tol_val=0.01, max_iter=1, nouter=1, max_lambda2=None, lambda1=0.0,
+           bf_per_kb=50.0, hyper=100.0, ref=1):
+    return MlParams(lambda2, lambda2 + 1 if max_lambda2 is None else max_lambda2, lambda1, tol_val, bf_per_kb,
+                    hyper, max_iter, nouter, ref, model, 0, 0)
+
+
+def run_one(engine, t, **kw):
+    res = engine.detect_batch(np.array([0, t["pos"].size], np.int64), t, params(**kw))
+    try:
+        return res.job(0)
+    finally:
+        res.free()
+
+
+def close(a, b, rel=REL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
+    return a.shape == b.shape and (a.size == 0 or float(np.max(np.abs(a - b))) <= rel * scale)
+
+
+def assert_job_matches(r, o, exact_fast=True):
+    est, oest = r["estimates"], o["estimates"]
+    assert np.array_equal(est["estimate_id"], oest["estimate_id"])
+    assert np.array_equal(est["start"], oest["start"])
+    assert close(est["pseudoweight"], oest["pseudoweight"])
+    assert close(est["betahat"], oest["betahat"])
+    assert close(est["beta"], oest["beta"])
+    assert close(r["mu"], o["mu"]) and close(r["offset"], o["offset"])
+    assert r["converged"] == o["converged"]
+    assert (r["irls_steps"], r["dampings"], r["outer_iters"]) == (o["irls_steps"], o["dampings"], o["outer_iters"])
+
+
+@pytest.mark.parametrize("prefix", list(FIXTURES))
+def test_golden_path_fixtures(engine, oracle, prefix):
+    g = np.load(os.path.join(GOLD, "path_fixtures.npz"))
+    t = fixture_table(g, prefix)
+    r = run_one(engine, t, **FIXTURES[prefix])
+    o = dict(mu=g[f"{prefix}_mu"], offset=g[f"{prefix}_offset"],
+             estimates={c: g[f"{prefix}_est_{c}"] for c in ("estimate_id", "start", "beta", "betahat", "pseudoweight")})
+    meta = g[f"{prefix}_meta"].tolist()
+    o.update(converged=bool(meta[3]), irls_steps=meta[4], dampings=meta[5], outer_iters=meta[6])
+    assert_job_matches(r, o)
+    if prefix.startswith("fast"):
+        # count data: pseudodata and the FLSA fit before centring are exact; what remains is the
+        # association order of two long sums (centring mean, offset) -> a uniform shift ~1e-16
+        assert np.array_equal(r["estimates"]["pseudoweight"], o["estimates"]["pseudoweight"])
+        assert np.array_equal(r["estimates"]["betahat"], o["estimates"]["betahat"])
+        assert np.max(np.abs(r["estimates"]["beta"] - o["estimates"]["beta"])) < 1e-13
+    # segment boundaries identical
+    seg = engine.segment_methylation_helper(r["estimates"], 0.01)
+    for c in ("estimate_id", "segment_id", "start", "end"):
+        assert np.array_equal(seg[c], g[f"{prefix}_seg_{c}"]), c
+    assert close(seg["beta"], g[f"{prefix}_seg_beta"]) and close(seg["pseudoweight"], g[f"{prefix}_seg_pseudoweight"])
+
+
+@pytest.mark.parametrize("reps,kw", [((1,), {}), ((3,), {}), ((3, 3), {}), ((2,), dict(lambda2=1000.0)),
+                                     ((1,), dict(max_iter=4, lambda2=10.0))])
+def test_fast_against_oracle(engine, oracle, reps, kw):
+    t = synth.chromosome_table(60_000, 41 + len(reps), reps)
+    o = oracle.detect(t, 0, **kw)
+    r = run_one(engine, t, **kw)
+    assert_job_matches(r, o)
+    so = oracle.segment_methylation_helper(o["estimates"], 0.01)
+    sr = engine.segment_methylation_helper(r["estimates"], 0.01)
+    for c in ("estimate_id", "segment_id", "start", "end"):
+        assert np.array_equal(sr[c], so[c]), c
+
+
+@pytest.mark.parametrize("model,reps,kw", [(1, (1,), {}), (1, (3,), {}), (2, (2, 2), dict(ref=1)),
+                                           (2, (1, 2), dict(ref=2))])
+def test_full_against_oracle(engine, oracle, model, reps, kw):
+    t = synth.chromosome_table(6000, 51 + model, reps)
+    full = dict(max_iter=30, nouter=20, hyper=100.0, bf_per_kb=50.0, max_lambda2=1000.0)
+    o = oracle.detect(t, model, **full, **kw)
+    r = run_one(engine, t, model=model, **full, **kw)
+    # device exp/log/lgamma differ from glibc in the last ulp; a damping decision on a knife edge
+    # could in principle flip, so the control-flow counters are compared first and reported
+    assert (r["irls_steps"], r["dampings"], r["outer_iters"]) == (o["irls_steps"], o["dampings"], o["outer_iters"])
+    assert_job_matches(r, o)
+
+
+def test_batch_of_chromosomes_equals_single_calls(engine, oracle):
+    tables = [synth.chromosome_table(n, 70 + i, (2,)) for i, n in enumerate((30_000, 500, 12_345, 2, 80_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, params())
+    try:
+        assert res.status.tolist() == [0] * 5
+        for j, t in enumerate(tables):
+            assert_job_matches(res.job(j), oracle.detect(t, 0))
+        # resident segmentation of the whole batch == per-job segment helper
+        seg = res.segments(0.01)
+        for j, t in enumerate(tables):
+            so = oracle.segment_methylation_helper(oracle.detect(t, 0)["estimates"], 0.01)
+            m = seg["job"] == j
+            for c in ("estimate_id", "segment_id", "start", "end"):
+                assert np.array_equal(seg[c][m], so[c]), (j, c)
+            assert close(seg["betahat"][m], so["betahat"]) and close(seg["pseudoweight"][m], so["pseudoweight"])
+    finally:
+        res.free()
+
+
+def test_validation_codes_per_job_and_batch_survives(engine):
+    """One bad chromosome does not fail the batch (foreach .errorhandling='remove')."""
+    good = synth.chromosome_table(5000, 5, (1,))
+    tables = [good] + [t for t, _ in VALIDATION_CASES] + [good]
+    want = [0] + [c for _, c in VALIDATION_CASES] + [0]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, params())
+    try:
+        got = res.status.tolist()
+        # valid 3-row tables have 3 distinct positions -> fine
+        assert got == want
+        a, b = res.job(0), res.job(len(tables) - 1)
+        assert np.array_equal(a["estimates"]["beta"], b["estimates"]["beta"])
+        with pytest.raises(api.MethyLassoError) as e:
+            res.job(1)
+        assert e.value.code == 1
+    finally:
+        res.free()
+
+
+def test_error_sites(engine):
+    t = synth.chromosome_table(500, 1, (1,))
+    for kw, code in ((dict(lambda2=0.0), 13), (dict(model=2, ref=1), 14)):
+        with pytest.raises(api.MethyLassoError) as e:
+            run_one(engine, t, **kw)
+        assert e.value.code == code
+    t2 = synth.chromosome_table(500, 1, (1, 1))
+    with pytest.raises(api.MethyLassoError) as e:
+        run_one(engine, t2, model=2, ref=3)
+    assert e.value.code == 15
+    same = _tbl(dataset=[1, 2], condition=[1, 1], replicate=[1, 2], pos=[7, 7], Nmeth=[1, 1], coverage=[2, 2])
+    with pytest.raises(api.MethyLassoError) as e:
+        run_one(engine, same)
+    assert e.value.code == 18
+    with pytest.raises(api.MethyLassoError):
+        api.signal_detection_fast_singlechr({"pos": np.arange(3)}, engine=engine)
+
+
+def test_segment_helper_generic_tables(engine, oracle):
+    rng = np.random.default_rng(4)
+    for trial in range(30):
+        n = int(rng.integers(1, 4000))
+        ids = np.sort(rng.integers(1, 4, n)).astype(np.int32)
+        beta = np.cumsum(rng.normal(scale=0.004, size=n)) if trial % 2 else np.repeat(rng.random(n // 9 + 1), 9)[:n]
+        est = dict(estimate_id=ids, start=np.cumsum(rng.integers(1, 300, n)).astype(np.int32), beta=beta,
+                   betahat=beta + rng.normal(scale=0.1, size=n), pseudoweight=rng.integers(0, 60, n).astype(float))
+        so = oracle.segment_methylation_helper(est, 0.01)
+        sr = engine.segment_methylation_helper(est, 0.01)
+        for c in so:
+            assert np.array_equal(sr[c], so[c], equal_nan=True), (trial, c)   # rows added in row order: bit-equal
+
+
+def test_fast_diff_combine(engine, oracle):
+    t = synth.chromosome_table(30_000, 88, (3, 3))
+    o = oracle.detect(t, 0)
+    d = oracle.fast_diff_combine(o["estimates"], o["n_params"], o["n_est"])
+    r = api.difference_detection_fast_singlechr(t, ref=2, engine=engine)
+    assert r["detection.type"] == "difference" and r["ref.cond"] == 2
+    for c in ("beta", "betahat", "pseudoweight"):
+        assert close(r["estimates"][c], d[c])
+
+
+def test_genome_wide_wrapper_mirrors_r_layer(engine, oracle):
+    tables = [synth.chromosome_table(8000, 90 + i, (2,)) for i in range(3)]
+    names = ["chr2", "chr10", "chrX"]
+    data = {k: np.concatenate([t[k] for t in tables]) for k in tables[0]}
+    data["chr"] = np.concatenate([np.repeat(nm, t["pos"].size) for nm, t in zip(names, tables)])
+    ret = api.signal_detection_fast(data, lambda2=25, verbose=False, engine=engine)
+    assert ret["chr"].tolist() == names and ret["detection.type"] == "signal" and ret["model"] == "normal"
+    at = 0
+    for nm, t in zip(names, tables):
+        o = oracle.detect(t, 0)
+        n = o["estimates"]["beta"].size
+        assert close(ret["estimates"]["beta"][at:at + n], o["estimates"]["beta"])
+        assert (ret["estimates"]["chr"][at:at + n] == nm).all()
+        at += n
+
+
+def test_placement_independence(engine):
+    """The same chromosome gives bit-identical results alone or inside any batch (what makes
+    1-GPU and 8-GPU runs identical)."""
+    a = synth.chromosome_table(50_000, 7, (3,))
+    b = synth.chromosome_table(20_000, 8, (3,))
+    r1 = run_one(engine, a)
+    ptr, cols = synth.concat_jobs([b, a, b])
+    res = engine.detect_batch(ptr, cols, params())
+    try:
+        r2 = res.job(1)
+    finally:
+        res.free()
+    for c in ("beta", "betahat", "pseudoweight"):
+        assert np.array_equal(r1["estimates"][c], r2["estimates"][c])
+    assert np.array_equal(r1["mu"], r2["mu"]) and np.array_equal(r1["offset"], r2["offset"])
+
+
+def test_full_genome_shape_properties(engine):
+    """Config 2 at 1/4 scale per chromosome count (24 jobs, 3 replicates): size-independent checks."""
+    tables = synth.genome_tables(2, total_cpgs=7_000_000, reps_per_condition=(3,))
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, params())
+    try:
+        assert res.status.tolist() == [0] * 24
+        for j in (0, 11, 23):
+            r = res.job(j)
+            t = tables[j]
+            est = r["estimates"]
+            u, inv = np.unique(t["pos"], return_inverse=True)
+            assert np.array_equal(est["start"], u.astype(float))
+            assert np.array_equal(est["pseudoweight"], np.bincount(inv, t["coverage"], u.size))
+            assert abs(np.sum(est["beta"] * est["pseudoweight"]) / np.sum(est["pseudoweight"])) < 1e-12
+            assert np.allclose(r["mu"], est["beta"][inv] + r["offset"][t["dataset"] - 1], rtol=0, atol=1e-14)
+            # FLSA optimality of beta + mean against (betahat, pseudoweight)
+            from test_oracle import kkt_residual
+            shift = np.sum(est["betahat"] * est["pseudoweight"]) / np.sum(est["pseudoweight"])
+            assert kkt_residual(est["betahat"] - shift, est["pseudoweight"], est["beta"], 25.0) < 1e-8
+    finally:
+        res.free()

@@ -1,0 +1,115 @@
+"""GPU parity of the batched weighted 1-D FLSA (through the C ABI) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from methylasso_b200 import synth
+from conftest import pooled_series
+from test_oracle import kkt_residual
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_known_answers(engine):
+    assert np.allclose(engine.weighted_1d_flsa([0, 0, 1, 1], [1, 1, 1, 1], 0.5), [.25, .25, .75, .75], atol=1e-15)
+    assert np.allclose(engine.weighted_1d_flsa([0, 0, 1, 1], [1, 1, 1, 1], 10), [.5, .5, .5, .5], atol=1e-15)
+
+
+def test_golden_reference_vectors(engine):
+    """Vectors produced by the reference's verbatim tf_dp_weight (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, "dp_vectors.npz"))
+    for k in ("random", "zero_w", "monotone", "plateaus", "known"):
+        beta = engine.weighted_1d_flsa(g[f"{k}_y"], g[f"{k}_w"], float(g[f"{k}_lam"]))
+        want = np.clip(g[f"{k}_beta"], -35, 35)
+        assert np.array_equal(beta, want, equal_nan=True), k
+
+
+def test_trivial_and_error_cases(engine, oracle):
+    from methylasso_b200.api import MethyLassoError
+    assert engine.weighted_1d_flsa([], [], 5.0).size == 0
+    assert np.array_equal(engine.weighted_1d_flsa([0.3], [2.0], 5.0), [0.3])
+    y = np.array([1.0, 50.0, -70.0])
+    assert np.array_equal(engine.weighted_1d_flsa(y, np.ones(3), 0.0), [1.0, 35.0, -35.0])  # lam == 0: beta = y, clamped
+    assert np.array_equal(engine.weighted_1d_flsa(y, np.ones(3), 0.0, 2.0), [0.0, 33.0, -33.0])  # soft threshold
+    with pytest.raises(MethyLassoError) as e:
+        engine.weighted_1d_flsa([1.0, 2.0], [1.0], 1.0)
+    assert e.value.code == 2
+
+
+@pytest.mark.parametrize("reps", [(1,), (3,)])
+def test_count_data_bit_exact(engine, oracle, reps):
+    t = synth.chromosome_table(400_000, 20241, reps)
+    y, w = pooled_series(t)
+    for lam in (10.0, 25.0, 1000.0, 2000.0):
+        ref = oracle.weighted_1d_flsa(y, w, lam)
+        got = engine.weighted_1d_flsa(y, w, lam)
+        assert np.array_equal(got, ref), lam
+
+
+def test_generic_inputs_and_ragged_batch(engine, oracle):
+    rng = np.random.default_rng(0)
+    ys, ws, lams, ptr = [], [], [], [0]
+    for trial in range(300):
+        n = int(rng.integers(0, 3000)) if trial % 7 else int(rng.integers(0, 4))
+        kind = trial % 5
+        if kind == 0:
+            y, w = rng.random(n), rng.integers(0, 3, n).astype(float)
+        elif kind == 1:
+            y, w = np.sort(rng.random(n)), rng.random(n)
+        elif kind == 2:
+            y, w = np.repeat(rng.random(n // 7 + 1), 7)[:n], rng.integers(0, 50, n).astype(float)
+        elif kind == 3:
+            y = rng.integers(0, 2, n).astype(float)
+            w = np.where(rng.random(n) < 0.8, 0.0, rng.integers(1, 30, n)).astype(float)
+        else:
+            y, w = rng.normal(size=n), rng.exponential(size=n)
+        ys.append(y); ws.append(w); ptr.append(ptr[-1] + n)
+        lams.append(float(rng.choice([0.0, 1e-3, 0.1, 0.5, 5.0, 25.0, 1000.0])))
+    yy, ww = np.concatenate(ys), np.concatenate(ws)
+    got = engine.weighted_1d_flsa_batch(np.array(ptr), yy, ww, np.array(lams))
+    worst = 0.0
+    for s in range(len(ys)):
+        ref = oracle.weighted_1d_flsa(ys[s], ws[s], lams[s])
+        g = got[ptr[s]:ptr[s + 1]]
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(g), ok), s
+        if ok.any():
+            worst = max(worst, np.max(np.abs(g[ok] - ref[ok])) / max(1.0, np.max(np.abs(ref[ok]))))
+    assert worst < 1e-11, worst   # tolerance: rounding of re-associated sums; north_star allows 1e-6
+
+
+def test_ring_overflow_falls_back_to_global_scratch(engine, oracle):
+    n = 5000
+    y = (np.arange(n) / n) ** 2 * 500
+    w = np.ones(n)
+    assert np.array_equal(engine.weighted_1d_flsa(y, w, 200.0), oracle.weighted_1d_flsa(y, w, 200.0))
+
+
+def test_sequential_mode_is_bit_faithful_on_real_valued_data(engine, oracle):
+    """flsa_sequential = 1: one thread walks each series start to end -> the reference's operation
+    order exactly, for any input."""
+    rng = np.random.default_rng(9)
+    y, w = rng.normal(size=20_000), rng.exponential(size=20_000)
+    engine.set("flsa_sequential", 1)
+    try:
+        got = engine.weighted_1d_flsa(y, w, 3.0)
+    finally:
+        engine.set("flsa_sequential", 0)
+    assert np.array_equal(got, oracle.weighted_1d_flsa(y, w, 3.0))
+
+
+def test_full_size_chromosome_properties(engine):
+    """chr1-sized series (2.26 M): too long for the oracle in a unit test; check optimality (KKT)
+    and that chunked == sequential mode bit for bit (count data)."""
+    t = synth.chromosome_table(2_260_000, 99, (1,))
+    y, w = pooled_series(t)
+    beta = engine.weighted_1d_flsa(y, w, 25.0)
+    assert kkt_residual(y, w, beta, 25.0) < 1e-8
+    engine.set("flsa_sequential", 1)
+    try:
+        seq = engine.weighted_1d_flsa(y, w, 25.0)
+    finally:
+        engine.set("flsa_sequential", 0)
+    assert np.array_equal(beta, seq)
