@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — CpGs/s through IRLS + weighted 1-D FLSA (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cpgs M]
+
+Workload (config.workload): BASELINE.json configs[1] — a full human-genome-shaped synthetic WGBS
+sample set (~28 M CpGs over 24 chromosomes, one condition, 3 replicates, coverage ~ Poisson(20)
+filtered at >= 5), UMR/LMR segmentation at lambda2 = 25 followed by the PMD std fusion at
+lambda2 = 1000.  One STEP = the native calls the reference's R layer makes for that config:
+    signal_detection_fast (24 x signal_detection_fast_singlechr, MethyLasso.R:559)
+    segment_methylation_helper on the estimates            (R/call.R:53)
+    weighted_1d_flsa(std, width, 1000) per chromosome      (R/call.R:93)
+    segment_methylation_helper on the fused table          (R/call.R:95)
+`value` times the step with inputs already resident in HBM (validation, indexing, IRLS, FLSA,
+segmentation all inside); `e2e` times the same step through the host-buffer C ABI from pinned host
+memory, including the H2D of the six input columns and the D2H of mu, the estimates table and both
+segment tables.  With N > 1 every rank processes its own genome (independent units, no data-path
+collective; weak scaling) and the ranks all-gather their segment-table sizes over NCCL at the end.
+
+--impl reference times the reference's CPU path for the same workload on the host cores: the oracle's
+plain-C restatement of methylation_detection with the reference's own tf_dp_weight (oracle/_ref,
+compiled verbatim) as the DP, one chromosome per thread (mirrors foreach %dopar% / -t).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from methylasso_b200 import synth  # noqa: E402
+
+LAMBDA2, PMD_LAMBDA2, TOL = 25.0, 1000.0, 0.01
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(total_cpgs, seed_offset=0):
+    tables = synth.genome_tables(2, total_cpgs=total_cpgs, reps_per_condition=(3,),
+                                 seed=synth.BASE_SEED + 2 + 1000 * seed_offset)
+    ptr, cols = synth.concat_jobs(tables)
+    return tables, ptr, cols
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: oracle port + the reference's verbatim DP, all host threads
+# ------------------------------------------------------------------------------------------------
+def reference_step(tables, O, threads):
+    """One pass of the same native-call sequence on the CPU; returns unique CpGs processed."""
+    out = [None] * len(tables)
+
+    def work(ids):
+        for j in ids:
+            t = tables[j]
+            r = O.detect(t, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+            seg = O.segment_methylation_helper(r["estimates"], TOL)
+            y = np.where(np.isfinite(seg["stdev"]), seg["stdev"], 0.0)
+            w = seg["end"].astype(float) - seg["start"].astype(float) + 1.0
+            fused = O.weighted_1d_flsa(y, w, PMD_LAMBDA2)
+            pmd = O.segment_methylation_helper(dict(estimate_id=seg["estimate_id"], start=seg["start"].astype(np.int32),
+                                                    beta=fused, betahat=y, pseudoweight=seg["pseudoweight"]), TOL)
+            out[j] = (r["n_params"], seg["start"].size, pmd["start"].size)
+    order = sorted(range(len(tables)), key=lambda j: -tables[j]["pos"].size)  # longest first
+    buckets = [[] for _ in range(threads)]
+    load = [0] * threads
+    for j in order:
+        k = int(np.argmin(load))
+        buckets[k].append(j)
+        load[k] += tables[j]["pos"].size
+    ths = [threading.Thread(target=work, args=(b,)) for b in buckets if b]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return sum(o[0] for o in out)
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    kind_dp = "reference tf_dp_weight (oracle/_ref)" if O.use_reference_dp(True) else "oracle DP restatement"
+    threads = os.cpu_count() or 1
+    tables, ptr, cols = make_workload(args.cpgs)
+    U = None
+    for _ in range(args.warmup):
+        U = reference_step(tables, O, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        U = reference_step(tables, O, threads)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = U / dt
+    line = {
+        "impl": "reference", "metric": "CpGs/sec through IRLS+weighted 1D FLSA", "value": value, "unit": "CpG/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, tables, ptr, U),
+        "cpu_baseline": {"value": value, "unit": "CpG/s", "cores": threads, "kind": "port",
+                         "sample": f"whole workload per step; oracle C restatement of methylation_detection, DP = {kind_dp}, "
+                                   f"one chromosome per thread over {threads} threads"},
+        "e2e": {"value": value, "unit": "CpG/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
+
+
+def workload_config(args, tables, ptr, U=None):
+    return {"workload": "configs[1]: full human-genome synthetic, one condition, 3 replicates, UMR/LMR (lambda2=25) "
+                        "+ PMD std fusion (lambda2=1000)",
+            "cpgs_per_genome": int(U) if U is not None else int(args.cpgs),
+            "rows_per_genome": int(ptr[-1]), "chromosomes": len(tables), "replicates": 3, "lambda2": LAMBDA2,
+            "pmd_lambda2": PMD_LAMBDA2, "tol_val": TOL, "model": "FAST (normal/identity, max_iter=1)",
+            "l2_policy": "inputs (2.0 GB per genome) and parameter arrays are larger than the 126 MB L2",
+            "pmd_input": "segment helper stdev/width (the R-side per-segment sd of R/call.R:57-68 is not native yet)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic bytes per launch: N rows, EP = E*P parameters, D datasets
+# ------------------------------------------------------------------------------------------------
+def kernel_bytes(N, EP, D, words):
+    return {
+        "k_validate": 24 * N,
+        "k_dset_bounds": 0,
+        "k_bitmap_mark": 4 * N + 8 * words,
+        "k_bitmap_tile_count": 4 * words,
+        "k_bitmap_word_prefix": 8 * words,
+        "k_rank_unique": 16 * N + 4 * D * EP + 8 * EP,
+        "k_pseudodata": 4 * D * EP + 8 * N + 32 * EP,
+        "k_offset_partial": 8 * N,
+        "flsa_pass_a_kernel": 32 * EP,
+        "flsa_bwd_reduce_kernel": 16 * EP,
+        "flsa_bwd_apply_kernel": 32 * EP,
+        "k_center": 16 * EP,
+        "k_eval_rows": 36 * N,
+        "k_tv_partial": 8 * EP,
+        "k_seg_run_heads": 12 * EP,
+        "k_scan_tile_sums": 4 * EP,
+        "k_scan_apply": 12 * EP,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpgs", type=int, default=synth.GENOME_CPGS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--out", default=None, help="also append the JSON line to this file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from methylasso_b200 import api
+    from methylasso_b200._native import MlParams
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: methylasso_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    eng = api.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+
+    tables, ptr, cols = make_workload(args.cpgs, seed_offset=rank)
+    N = int(ptr[-1])
+    # pinned host copies of the inputs (e2e) and of the outputs
+    pin = {k: torch.from_numpy(v).pin_memory() for k, v in cols.items()}
+    pcols = {k: v.numpy() for k, v in pin.items()}
+    batch = eng.upload(ptr, pcols)
+
+    def step_resident():
+        res = eng.detect(batch, params)
+        nseg = res.segments_count(TOL)
+        npmd = res.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+        return res, nseg, npmd
+
+    # sizes (one untimed call)
+    res, nseg, npmd = step_resident()
+    sizes = [res.sizes(j) for j in range(res.njobs)]
+    assert all(s[4] == 0 for s in sizes), "a synthetic chromosome failed validation"
+    U = int(sum(s[1] for s in sizes))
+    EP = int(sum(s[1] * s[2] for s in sizes))
+    D = 3
+    words = int(sum((int(t["pos"].max()) - int(t["pos"].min())) // 32 + 1 for t in tables))
+    res.free()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: resident inputs ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        r, _, _ = step_resident()
+        r.free()
+    eng.set("profile", 1)
+    eng.profile_reset()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        r, nseg, npmd = step_resident()
+        r.free()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count - l0
+    ms = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.profile()
+    eng.set("profile", 0)
+    t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    u_all = torch.tensor([U], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(u_all, op=dist.ReduceOp.SUM)
+    value = float(u_all.item()) / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI -------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        mu = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+        est = {k: torch.empty(EP, dtype=torch.float64).pin_memory().numpy() for k in ("start", "beta", "betahat", "pseudoweight")}
+        est_id = torch.empty(EP, dtype=torch.int32).pin_memory().numpy()
+        off = np.empty(3 * len(tables))
+
+        def step_e2e():
+            rr = eng.detect_batch(ptr, pcols, params)
+            rr.copy_all(mu, off, est_id, est["start"], est["beta"], est["betahat"], est["pseudoweight"])
+            seg = rr.segments(TOL)
+            pmd = rr.pmd_segments(TOL, PMD_LAMBDA2)
+            rr.free()
+            return seg, pmd
+        for _ in range(max(1, args.warmup - 1)):
+            seg, pmd = step_e2e()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            seg, pmd = step_e2e()
+        e1.record(stream)
+        barrier()
+        ems = e0.elapsed_time(e1) / args.steps
+        t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        seg_bytes = sum(v.nbytes for v in seg.values()) + sum(v.nbytes for v in pmd.values())
+        e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
+               "ms_per_step": float(t2.item()), "h2d_bytes_per_step": 24 * N,
+               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes)}
+
+    # ---- K16: all-gather of per-shard segment summaries over NCCL ---------------------------------
+    gathered = None
+    if world > 1:
+        mine = torch.tensor([U, nseg, npmd], device="cuda", dtype=torch.int64)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        gathered = [v.tolist() for v in allv]
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    pk, pk_kind = peaks()
+    kb = kernel_bytes(N, EP, D, words)
+    table = []
+    for name, (tot_ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+        per = tot_ms / max(1, n)
+        b = kb.get(name)
+        gbs = (b / (per * 1e-3) / 1e9) if b and per > 0 else None
+        table.append({"kernel": name, "ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps,
+                      "avg_launch_ms": per, "alg_bytes_per_launch": b, "GBps": gbs,
+                      "frac_of_hbm": (gbs / pk["hbm_gbs"]) if gbs else None})
+    top = table[0] if table else None
+    roofline = None
+    if top:
+        roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": top["frac_of_hbm"], "traffic": None, "peak_source": pk_kind,
+                    "note": "flsa_pass_a_kernel is latency-bound (dependent fp64 compare/add/divide chain per element); "
+                            "its HBM fraction is reported for the record, see profiles/ and DESIGN.md"}
+
+    # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        dp = "reference tf_dp_weight (oracle/_ref)" if O.use_reference_dp(True) else "oracle DP restatement"
+        sample = [tables[j] for j in (18, 19, 20, 21)]  # chr19..chr22: ~7.9 % of the genome
+        t0 = time.perf_counter()
+        Us = reference_step(sample, O, 1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": Us / dt, "unit": "CpG/s", "cores": 1, "kind": "port",
+               "sample": f"chr19-chr22 of the same workload ({Us} CpGs, {dt:.1f} s), single thread; oracle C restatement, DP = {dp}"}
+
+    if rank == 0:
+        line = {
+            "metric": "CpGs/sec through IRLS+weighted 1D FLSA", "value": value, "unit": "CpG/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16],
+            "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
+        }
+        print(json.dumps(line), flush=True)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(json.dumps(line) + "\n")
+    batch.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,13 +95,22 @@ ML_API const char *ml_strerror(int code);
 ML_API int ml_engine_create(int device, ml_engine **out);
 ML_API void ml_engine_destroy(ml_engine *eng);
 /* engine knobs: "flsa_chunk", "flsa_warm", "flsa_sequential" (1 = start-to-end DP, one thread
- * per series: the bit-faithful verification mode) */
+ * per series: the bit-faithful verification mode), "profile" (1 = time every kernel) */
 ML_API int ml_engine_set(ml_engine *eng, const char *key, long long value);
 /* number of kernel launches issued by this engine so far */
 ML_API long long ml_engine_launch_count(const ml_engine *eng);
 /* raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller */
 ML_API void *ml_engine_stream(ml_engine *eng);
 ML_API int ml_engine_synchronize(ml_engine *eng);
+/* Launch on a caller-owned CUDA stream (cudaStream_t) instead of the engine's own, so the caller's
+ * CUDA events bracket the engine's work; NULL restores the engine's stream. */
+ML_API int ml_engine_set_stream(ml_engine *eng, void *cuda_stream);
+/* Per-kernel timing (CUDA events on the launching stream).  Enable with
+ * ml_engine_set(eng, "profile", 1); entries accumulate until ml_engine_profile_reset. */
+ML_API int ml_engine_profile_count(ml_engine *eng);
+ML_API int ml_engine_profile_get(ml_engine *eng, int i, char *name, int name_cap, double *total_ms,
+                                 long long *launches);
+ML_API int ml_engine_profile_reset(ml_engine *eng);
 
 /* ---- weighted_1d_flsa  (src/weighted_1d_flsa.cpp:7-21; Rcpp module line
  *      src/MethyLasso_cpp.cpp:28) --------------------------------------------------------------
@@ -119,8 +128,8 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
 
 /* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
  *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
-/* Copy the six columns to the GPU, validate every job (core/Observations.hpp:29-59,
- * src/MethData.hpp:17-19) and keep them resident.  status[njobs] receives per-job codes. */
+/* Copy the six columns to the GPU and keep them resident (validation and indexing run on the
+ * device inside ml_batch_detect).  status may be NULL; it is zero-filled. */
 ML_API int ml_batch_upload(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
                     const int32_t *condition, const int32_t *replicate, const int32_t *pos,
                     const int32_t *nmeth, const int32_t *coverage, ml_batch **out, int *status);
@@ -176,6 +185,20 @@ ML_API int ml_result_segments(ml_engine *eng, ml_result *r, double tol_val, int6
                        int32_t *seg_job, int32_t *seg_estimate_id, int32_t *seg_id,
                        uint32_t *seg_start, uint32_t *seg_end, double *seg_beta,
                        double *seg_betahat, double *seg_pseudoweight, double *seg_stdev);
+
+/* PMD std fusion of R/call.R:93-95 on the resident segments: per (job, estimate)
+ * fused = weighted_1d_flsa(std, width, pmd_lambda2) with std = segment stdev (NA -> 0) and
+ * width = end - start + 1, then segment_methylation_helper on (estimate_id, start, beta = fused,
+ * betahat = std, pseudoweight).  fused_std (may be NULL) has one entry per segment of
+ * ml_result_segments(tol_val); the seg_* outputs describe the fused-std segments.  Query with NULL
+ * outputs for *n_segments first.
+ * NOTE: the reference feeds this step the per-segment sd that its R layer computes from the raw data
+ * (R/call.R:57-68); here the helper's own weighted stdev stands in until that R step is native. */
+ML_API int ml_result_pmd_segments(ml_engine *eng, ml_result *r, double tol_val, double pmd_lambda2,
+                                  int64_t *n_segments, double *fused_std, int32_t *seg_job,
+                                  int32_t *seg_estimate_id, int32_t *seg_id, uint32_t *seg_start,
+                                  uint32_t *seg_end, double *seg_fused_std, double *seg_std,
+                                  double *seg_pseudoweight);
 
 #ifdef __cplusplus
 }

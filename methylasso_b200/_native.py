@@ -35,6 +35,11 @@ SIGNATURES = {
     "ml_engine_launch_count": (C.c_longlong, [_P]),
     "ml_engine_stream": (_P, [_P]),
     "ml_engine_synchronize": (C.c_int, [_P]),
+    "ml_engine_set_stream": (C.c_int, [_P, _P]),
+    "ml_engine_profile_count": (C.c_int, [_P]),
+    "ml_engine_profile_get": (C.c_int, [_P, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_double),
+                                        C.POINTER(C.c_longlong)]),
+    "ml_engine_profile_reset": (C.c_int, [_P]),
     "ml_weighted_1d_flsa": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch_device": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
@@ -55,6 +60,7 @@ SIGNATURES = {
     "ml_result_fast_diff_combine": (C.c_int, [_P, _P]),
     "ml_segment_methylation_helper": (C.c_int, [_P, C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 8),
     "ml_result_segments": (C.c_int, [_P, _P, C.c_double, _I64P] + [_P] * 9),
+    "ml_result_pmd_segments": (C.c_int, [_P, _P, C.c_double, C.c_double, _I64P] + [_P] * 9),
 }
 
 _lib = None

@@ -83,6 +83,23 @@ class Engine:
     def synchronize(self):
         self._check(self.lib.ml_engine_synchronize(self.h))
 
+    def set_stream(self, cuda_stream: int):
+        """Launch on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self.lib.ml_engine_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def profile(self):
+        """{kernel name: (total ms, launches)} accumulated since the last profile_reset()."""
+        out = {}
+        for i in range(self.lib.ml_engine_profile_count(self.h)):
+            name = C.create_string_buffer(128)
+            ms, n = C.c_double(), C.c_longlong()
+            self._check(self.lib.ml_engine_profile_get(self.h, i, name, 128, C.byref(ms), C.byref(n)))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
+
+    def profile_reset(self):
+        self._check(self.lib.ml_engine_profile_reset(self.h))
+
     # ---- weighted_1d_flsa ---------------------------------------------------------------------
     def weighted_1d_flsa(self, y, wt, lambda2, lambda1=0.0):
         y, wt = _f64(y), _f64(wt)
@@ -233,6 +250,37 @@ class Result:
         self.eng._check(self.eng.lib.ml_result_segments(
             self.eng.h, self.h, float(tol_val), C.byref(ns), _p(out["job"]),
             *[_p(out[k]) for k in _SEG_COLS]))
+        return {k: v[:ns.value].copy() for k, v in out.items()}
+
+
+    def segments_count(self, tol_val=0.01) -> int:
+        """Run the segmentation on the device and leave the table there (fetch later with segments())."""
+        ns = C.c_int64(0)
+        self.eng._check(self.eng.lib.ml_result_segments(self.eng.h, self.h, float(tol_val), C.byref(ns),
+                                                        *([None] * 9)))
+        return ns.value
+
+    def copy_all(self, mu=None, offset=None, estimate_id=None, start=None, beta=None, betahat=None,
+                 pseudoweight=None):
+        """All valid jobs concatenated in job order into caller buffers (one D2H per column)."""
+        self.eng._check(self.eng.lib.ml_result_copy_all(self.eng.h, self.h, _p(mu), _p(offset), _p(estimate_id),
+                                                        _p(start), _p(beta), _p(betahat), _p(pseudoweight)))
+
+    def pmd_segments(self, tol_val=0.01, pmd_lambda2=1000.0, fetch=True):
+        """R/call.R:93-95 on the resident segments (see ml_result_pmd_segments)."""
+        ns = C.c_int64(0)
+        self.eng._check(self.eng.lib.ml_result_pmd_segments(self.eng.h, self.h, float(tol_val), float(pmd_lambda2),
+                                                            C.byref(ns), *([None] * 9)))
+        if not fetch:
+            return ns.value
+        n = max(ns.value, 1)
+        out = dict(job=np.empty(n, np.int32), estimate_id=np.empty(n, np.int32), segment_id=np.empty(n, np.int32),
+                   start=np.empty(n, np.uint32), end=np.empty(n, np.uint32), fused_std=np.empty(n),
+                   std=np.empty(n), pseudoweight=np.empty(n))
+        self.eng._check(self.eng.lib.ml_result_pmd_segments(
+            self.eng.h, self.h, float(tol_val), float(pmd_lambda2), C.byref(ns), None,
+            *[_p(out[k]) for k in ("job", "estimate_id", "segment_id", "start", "end", "fused_std", "std",
+                                   "pseudoweight")]))
         return {k: v[:ns.value].copy() for k, v in out.items()}
 
 

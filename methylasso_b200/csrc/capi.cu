@@ -2,6 +2,7 @@
 // host<->device copies at the boundary.  All compute is in flsa.cu / detect.cu / segment.cu.
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <memory>
 #include <string>
 
@@ -11,7 +12,7 @@
 
 using namespace ml;
 
-struct ml_engine { Engine e; };
+struct ml_engine { Engine e; cudaStream_t own = nullptr; };
 struct ml_batch { std::unique_ptr<Batch> b; };
 struct ml_result { std::unique_ptr<Result> r; };
 
@@ -102,10 +103,9 @@ int ml_engine_create(int device, ml_engine** out) {
 void ml_engine_destroy(ml_engine* eng) {
   if (!eng) return;
   cudaSetDevice(eng->e.device);
-  if (eng->e.stream) {
-    cudaStreamSynchronize(eng->e.stream);
-    cudaStreamDestroy(eng->e.stream);
-  }
+  if (eng->e.stream) cudaStreamSynchronize(eng->e.stream);
+  cudaStream_t mine = eng->e.own_stream ? eng->e.stream : eng->own;
+  if (mine) cudaStreamDestroy(mine);
   delete eng;
 }
 
@@ -115,6 +115,7 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   if (k == "flsa_chunk") eng->e.flsa_chunk = (int)value;
   else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
   else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
+  else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }
   else return fail(ML_ERR_BAD_ARGUMENT, "unknown engine key: " + k);
   return ML_OK;
 }
@@ -126,6 +127,45 @@ int ml_engine_synchronize(ml_engine* eng) {
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
   ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_engine_set_stream(ml_engine* eng, void* cuda_stream) {
+  if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  if (cuda_stream) {
+    if (eng->e.own_stream) { eng->e.own_stream = false; eng->own = eng->e.stream; }
+    eng->e.stream = (cudaStream_t)cuda_stream;
+  } else if (!eng->e.own_stream) {
+    eng->e.stream = eng->own;
+    eng->e.own_stream = true;
+  }
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_engine_profile_count(ml_engine* eng) {
+  if (!eng) return 0;
+  try { eng->e.prof.collect(); } catch (...) { return 0; }
+  return (int)eng->e.prof.acc.size();
+}
+int ml_engine_profile_get(ml_engine* eng, int i, char* name, int name_cap, double* total_ms,
+                          long long* launches) {
+  if (!eng || i < 0 || i >= (int)eng->e.prof.acc.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad profile index");
+  auto it = eng->e.prof.acc.begin();
+  std::advance(it, i);
+  if (name && name_cap > 0) { strncpy(name, it->first.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (total_ms) *total_ms = it->second.first;
+  if (launches) *launches = it->second.second;
+  return ML_OK;
+}
+int ml_engine_profile_reset(ml_engine* eng) {
+  if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
+  ML_TRY
+  eng->e.prof.reset();
   return ML_OK;
   ML_CATCH
 }
@@ -392,6 +432,45 @@ int ml_result_segments(ml_engine* eng, ml_result* r, double tol_val, int64_t* n_
   ho.stdev = seg_stdev;
   if (S > 0) ds.download(eng->e.stream, S, ho);
   ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_result_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double pmd_lambda2,
+                           int64_t* n_segments, double* fused_std, int32_t* seg_job, int32_t* seg_estimate_id,
+                           int32_t* seg_id, uint32_t* seg_start, uint32_t* seg_end, double* seg_fused_std,
+                           double* seg_std, double* seg_pseudoweight) {
+  if (!eng || !r || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  Result& R = *r->r;
+  if (!R.seg_cache || R.seg_tol != tol_val) {
+    int64_t ns = 0;
+    const int rc = ml_result_segments(eng, r, tol_val, &ns, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr);
+    if (rc) return rc;
+  }
+  SegDeviceOut& seg = *R.seg_cache;
+  cudaStream_t st = eng->e.stream;
+  if (!R.pmd_cache || R.pmd_tol != tol_val || R.pmd_lambda2 != pmd_lambda2) {
+    std::vector<int32_t> job((size_t)seg.n), est((size_t)seg.n);
+    seg.job.download(job.data(), (size_t)seg.n);
+    seg.estimate_id.download(est.data(), (size_t)seg.n);
+    ML_CUDA(cudaStreamSynchronize(st));
+    auto out = std::make_unique<SegDeviceOut>();
+    out->n = pmd_segments_device(eng->e, seg, job, est, pmd_lambda2, tol_val, R.pmd_fused, *out);
+    R.pmd_cache = std::move(out);
+    R.pmd_tol = tol_val;
+    R.pmd_lambda2 = pmd_lambda2;
+  }
+  const SegDeviceOut& P = *R.pmd_cache;
+  *n_segments = P.n;
+  if (fused_std && seg.n) R.pmd_fused.download(fused_std, (size_t)seg.n);
+  SegHostOut ho;
+  ho.job = seg_job; ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
+  ho.beta = seg_fused_std; ho.betahat = seg_std; ho.pseudoweight = seg_pseudoweight;
+  if (P.n > 0) P.download(st, P.n, ho);
+  ML_CUDA(cudaStreamSynchronize(st));
   return ML_OK;
   ML_CATCH
 }

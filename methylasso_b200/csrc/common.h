@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -27,10 +28,52 @@ struct MlError : public std::runtime_error {
 
 #define ML_CHECK_LAUNCH() ML_CUDA(cudaGetLastError())
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+struct Profiler {
+  struct Rec { const char* name; cudaEvent_t a, b; };
+  bool on = false;
+  std::vector<Rec> pending;
+  std::vector<cudaEvent_t> pool;
+  std::map<std::string, std::pair<double, long long>> acc;  // name -> (total ms, launches)
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e;
+    ML_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void begin(const char* name, cudaStream_t st) {
+    if (!on) return;
+    Rec r{name, get(), get()};
+    ML_CUDA(cudaEventRecord(r.a, st));
+    pending.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    ML_CUDA(cudaEventRecord(pending.back().b, st));
+  }
+  void collect() {
+    for (Rec& r : pending) {
+      ML_CUDA(cudaEventSynchronize(r.b));
+      float ms = 0;
+      ML_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+      auto& a = acc[r.name];
+      a.first += ms;
+      a.second += 1;
+      pool.push_back(r.a);
+      pool.push_back(r.b);
+    }
+    pending.clear();
+  }
+  void reset() { collect(); acc.clear(); }
+  ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
+};
+
 struct Engine {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  Profiler prof;
   // tunables (env overridable, see engine.cu)
   int flsa_chunk = 0;       // 0 = choose from total work
   int flsa_warm = 0;        // 0 = choose from lambda
@@ -78,5 +121,15 @@ struct DevBuf {
 };
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// every kernel launch of the engine goes through this: error check, launch count, optional timing
+#define ML_LAUNCH(ENG, NAME, ...)            \
+  do {                                       \
+    (ENG).prof.begin(NAME, (ENG).stream);    \
+    __VA_ARGS__;                             \
+    ML_CHECK_LAUNCH();                       \
+    (ENG).prof.end((ENG).stream);            \
+    (ENG).launches++;                        \
+  } while (0)
 
 }  // namespace ml

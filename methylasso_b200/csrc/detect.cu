@@ -696,10 +696,8 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   DevBuf<unsigned long long> d_keys(st, nj);
   ML_CUDA(cudaMemsetAsync(d_keys.p, 0xff, sizeof(unsigned long long) * nj, st));
   if (!vt.empty()) {
-    k_validate<<<(int)vt.size(), 256, 0, st>>>(d_vt.p, b.d_job_ptr.p, b.dataset.p, b.condition.p,
-                                               b.replicate.p, b.pos.p, b.nmeth.p, b.cov.p, d_keys.p);
-    ML_CHECK_LAUNCH();
-    eng.launches++;
+    ML_LAUNCH(eng, "k_validate", k_validate<<<(int)vt.size(), 256, 0, st>>>(d_vt.p, b.d_job_ptr.p, b.dataset.p, b.condition.p,
+                                               b.replicate.p, b.pos.p, b.nmeth.p, b.cov.p, d_keys.p));
   }
   // dataset ranges (for jobs whose last-row dataset id is plausible)
   std::vector<int32_t> ent_job, ent_d, job_ent0(nj + 1, 0);
@@ -718,11 +716,9 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   cx.dptr.alloc(st, std::max(1, n_ent));
   DevBuf<int32_t> d_dcond(st, std::max(1, n_ent)), d_dfirst(st, std::max(1, n_ent)), d_dlast(st, std::max(1, n_ent));
   if (n_ent) {
-    k_dset_bounds<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, b.d_job_ptr.p,
+    ML_LAUNCH(eng, "k_dset_bounds", k_dset_bounds<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, b.d_job_ptr.p,
                                                     b.dataset.p, b.condition.p, b.pos.p, cx.dptr.p,
-                                                    d_dcond.p, d_dfirst.p, d_dlast.p);
-    ML_CHECK_LAUNCH();
-    eng.launches++;
+                                                    d_dcond.p, d_dfirst.p, d_dlast.p));
   }
   std::vector<unsigned long long> keys(nj);
   std::vector<int32_t> h_dptr(n_ent), h_dcond(n_ent), h_dfirst(n_ent), h_dlast(n_ent);
@@ -857,16 +853,11 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     d_job_wtile0.alloc(st, nj + 1); d_job_wtile0.upload(job_wtile0);
     d_job_unique.alloc(st, nj);
     cx.jobs.upload(hj);  // row0 etc. are final; P / par0 / tab0 follow after the count
-    k_bitmap_mark<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p);
-    ML_CHECK_LAUNCH();
-    k_bitmap_tile_count<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p);
-    ML_CHECK_LAUNCH();
-    k_bitmap_job_scan<<<cdiv((long long)nj * 32, 128), 128, 0, st>>>(d_job_wtile0.p, nj, d_wtile_count.p,
-                                                                     d_job_unique.p);
-    ML_CHECK_LAUNCH();
-    k_bitmap_word_prefix<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p);
-    ML_CHECK_LAUNCH();
-    eng.launches += 4;
+    ML_LAUNCH(eng, "k_bitmap_mark", k_bitmap_mark<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p));
+    ML_LAUNCH(eng, "k_bitmap_tile_count", k_bitmap_tile_count<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p));
+    ML_LAUNCH(eng, "k_bitmap_job_scan", k_bitmap_job_scan<<<cdiv((long long)nj * 32, 128), 128, 0, st>>>(d_job_wtile0.p, nj, d_wtile_count.p,
+                                                                     d_job_unique.p));
+    ML_LAUNCH(eng, "k_bitmap_word_prefix", k_bitmap_word_prefix<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p));
     std::vector<int32_t> uniq(nj);
     d_job_unique.download(uniq.data(), nj);
     ML_CUDA(cudaStreamSynchronize(st));
@@ -945,22 +936,16 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   cx.ctl.upload(h_alive);
   if (n_rt) {
     if (fast) {
-      k_rank_unique<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p,
+      ML_LAUNCH(eng, "k_rank_unique", k_rank_unique<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p,
                                           d_wprefix.p, cx.start0.p, cx.ctl.p, cx.pidx.p, cx.rowstart.p,
-                                          res->start.p);
-      ML_CHECK_LAUNCH();
-      eng.launches++;
+                                          res->start.p));
     } else {
-      k_even_bins<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, cx.ctl.p, cx.pidx.p);
-      ML_CHECK_LAUNCH();
-      k_rowstart_runs<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.dptr.p, cx.pidx.p, cx.ctl.p,
-                                            cx.rowstart.p);
-      ML_CHECK_LAUNCH();
+      ML_LAUNCH(eng, "k_even_bins", k_even_bins<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, cx.ctl.p, cx.pidx.p));
+      ML_LAUNCH(eng, "k_rowstart_runs", k_rowstart_runs<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.dptr.p, cx.pidx.p, cx.ctl.p,
+                                            cx.rowstart.p));
       if (n_pt) {
-        k_support_even<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.start0.p, res->start.p);
-        ML_CHECK_LAUNCH();
+        ML_LAUNCH(eng, "k_support_even", k_support_even<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.start0.p, res->start.p));
       }
-      eng.launches += 3;
     }
   }
   std::unique_ptr<FlsaPlan> plan;
@@ -1029,46 +1014,34 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     }
     cx.ctl.upload(ctl);
     if (any_update) {
-      k_pseudodata<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.dptr.p, cx.design.p,
+      ML_LAUNCH(eng, "k_pseudodata", k_pseudodata<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.dptr.p, cx.design.p,
                                               cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
-                                              res->pw.p);
-      ML_CHECK_LAUNCH();
-      k_offset_partial<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p);
-      ML_CHECK_LAUNCH();
-      k_offset_finalize<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
+                                              res->pw.p));
+      ML_LAUNCH(eng, "k_offset_partial", k_offset_partial<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p));
+      ML_LAUNCH(eng, "k_offset_finalize", k_offset_finalize<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
                                                           cx.dtile0.p, cx.off_part.p, res->offset.p,
-                                                          cx.old_off.p);
-      ML_CHECK_LAUNCH();
-      eng.launches += 3;
+                                                          cx.old_off.p));
       for (int j = 0; j < nj; ++j)
         if (!res->jobs[j].status)
           for (int e = 0; e < hj[j].E; ++e) skip[hj[j].ser0 + e] = (ctl[j] & CTL_UPDATE) ? 0 : 1;
       plan->solve(res->betahat.p, res->pw.p, res->beta.p, 1, p.lambda1, cx.sums.p, &skip);
-      k_center<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, cx.sums.p, res->beta.p);
-      ML_CHECK_LAUNCH();
-      eng.launches++;
+      ML_LAUNCH(eng, "k_center", k_center<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, cx.sums.p, res->beta.p));
       for (int j = 0; j < nj; ++j)
         if (ctl[j] & CTL_UPDATE) res->jobs[j].irls_steps++;
     }
     if (any_damp) {
-      k_damp<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, wnew, res->beta.p, cx.old_beta.p,
-                                        res->offset.p, cx.old_off.p);
-      ML_CHECK_LAUNCH();
-      eng.launches++;
+      ML_LAUNCH(eng, "k_damp", k_damp<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, wnew, res->beta.p, cx.old_beta.p,
+                                        res->offset.p, cx.old_off.p));
       for (int j = 0; j < nj; ++j)
         if (ctl[j] & CTL_DAMP) res->jobs[j].dampings++;
     }
     if (any_eval) {
-      k_eval_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p, res->beta.p,
+      ML_LAUNCH(eng, "k_eval_rows", k_eval_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p, res->beta.p,
                                         res->offset.p, log2pi, res->mu.p, cx.mu_outer.p, want_outer ? 1 : 0,
-                                        cx.row_part.p);
-      ML_CHECK_LAUNCH();
-      k_tv_partial<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, res->beta.p, cx.tv_part.p);
-      ML_CHECK_LAUNCH();
-      k_job_finalize<<<cdiv(nj, 64), 64, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
-                                                  cx.scalars.p);
-      ML_CHECK_LAUNCH();
-      eng.launches += 3;
+                                        cx.row_part.p));
+      ML_LAUNCH(eng, "k_tv_partial", k_tv_partial<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, res->beta.p, cx.tv_part.p));
+      ML_LAUNCH(eng, "k_job_finalize", k_job_finalize<<<cdiv(nj, 64), 64, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
+                                                  cx.scalars.p));
       cx.scalars.download(sc.data(), sc.size());
       ML_CUDA(cudaStreamSynchronize(st));
     }
@@ -1128,10 +1101,8 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     }
     if (any_copy) {
       cx.ctl.upload(ctl);
-      k_copy_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, res->mu.p, cx.mu_res.p,
-                                        want_outer ? cx.mu_outer.p : nullptr);
-      ML_CHECK_LAUNCH();
-      eng.launches++;
+      ML_LAUNCH(eng, "k_copy_rows", k_copy_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, res->mu.p, cx.mu_res.p,
+                                        want_outer ? cx.mu_outer.p : nullptr));
     }
   }
   for (int j = 0; j < nj; ++j) {
@@ -1163,9 +1134,7 @@ void result_fast_diff_combine(Engine& eng, Result& r) {
   d_jobs.upload(hj);
   DevBuf<ParTile> d_pt(st, pt.size());
   d_pt.upload(pt);
-  k_fast_diff<<<(int)pt.size(), PAR_TILE, 0, st>>>(d_pt.p, d_jobs.p, r.beta.p, r.betahat.p, r.pw.p);
-  ML_CHECK_LAUNCH();
-  eng.launches++;
+  ML_LAUNCH(eng, "k_fast_diff", k_fast_diff<<<(int)pt.size(), PAR_TILE, 0, st>>>(d_pt.p, d_jobs.p, r.beta.p, r.betahat.p, r.pw.p));
   ML_CUDA(cudaStreamSynchronize(st));
 }
 

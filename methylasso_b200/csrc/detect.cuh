@@ -90,6 +90,9 @@ struct Result {
   // segments of the last ml_result_segments call (query-then-fetch without recomputing)
   std::unique_ptr<SegDeviceOut> seg_cache;
   double seg_tol = 0;
+  std::unique_ptr<SegDeviceOut> pmd_cache;
+  DevBuf<double> pmd_fused;
+  double pmd_tol = 0, pmd_lambda2 = 0;
 };
 
 std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,

@@ -14,6 +14,8 @@
 #include <cstring>
 
 #include "segment.cuh"
+#include "flsa.cuh"
+#include "hd.h"
 
 namespace ml {
 
@@ -109,13 +111,9 @@ struct Scan {
     const int nt = cdiv(n, STILE);
     tile_sum.alloc(st, std::max(1, nt));
     total.alloc(st, 1);
-    k_scan_tile_sums<<<nt, 256, 0, st>>>(flags, n, tile_sum.p);
-    ML_CHECK_LAUNCH();
-    k_scan_block<<<1, 256, 0, st>>>(tile_sum.p, nt, total.p);
-    ML_CHECK_LAUNCH();
-    k_scan_apply<<<nt, 256, 0, st>>>(flags, n, tile_sum.p, pos, compact);
-    ML_CHECK_LAUNCH();
-    eng.launches += 3;
+    ML_LAUNCH(eng, "k_scan_tile_sums", k_scan_tile_sums<<<nt, 256, 0, st>>>(flags, n, tile_sum.p));
+    ML_LAUNCH(eng, "k_scan_block", k_scan_block<<<1, 256, 0, st>>>(tile_sum.p, nt, total.p));
+    ML_LAUNCH(eng, "k_scan_apply", k_scan_apply<<<nt, 256, 0, st>>>(flags, n, tile_sum.p, pos, compact));
     int32_t h = 0;
     total.download(&h, 1);
     ML_CUDA(cudaStreamSynchronize(st));
@@ -229,7 +227,49 @@ __global__ void k_group_heads(const int32_t* __restrict__ idx, int64_t n, int32_
   if (i < n) flags[i] = (i == 0 || idx[i] != idx[i - 1]) ? 1 : 0;
 }
 
+// PMD inputs from a segment table (R/call.R:57-93, native part): y = segment sd with NA -> 0
+// (R/call.R:68), weight = width in bp.
+__global__ void k_pmd_inputs(int64_t n, const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                             const double* __restrict__ stdev, double* __restrict__ y, double* __restrict__ w,
+                             int32_t* __restrict__ start_i32) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double sd = stdev[i];
+  y[i] = is_finite(sd) ? sd : 0.0;
+  w[i] = (double)end[i] - (double)start[i] + 1.0;
+  start_i32[i] = (int32_t)start[i];
+}
+
 }  // namespace
+
+// std fusion + re-segmentation of a segment table (R/call.R:93-95): fused = weighted_1d_flsa(std,
+// width, pmd_lambda2) per (job, estimate); then segment_methylation_helper on
+// (estimate_id, start, beta = fused, betahat = std, pseudoweight).
+int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, const std::vector<int32_t>& seg_job,
+                            const std::vector<int32_t>& seg_est, double pmd_lambda2, double tol_val,
+                            DevBuf<double>& fused, SegDeviceOut& out) {
+  cudaStream_t st = eng.stream;
+  const int64_t n = seg.n;
+  if (n == 0) return 0;
+  std::vector<FlsaSeries> series;
+  std::vector<SegGroup> groups;
+  for (int64_t i = 0; i < n;) {
+    int64_t j = i + 1;
+    while (j < n && seg_job[j] == seg_job[i] && seg_est[j] == seg_est[i]) ++j;
+    series.push_back(FlsaSeries{i, (int32_t)(j - i), pmd_lambda2});
+    groups.push_back(SegGroup{i, j - i, i, seg_est[i], seg_job[i]});
+    i = j;
+  }
+  DevBuf<double> y(st, (size_t)n), w(st, (size_t)n);
+  DevBuf<int32_t> start_i32(st, (size_t)n);
+  fused.alloc(st, (size_t)n);
+  ML_LAUNCH(eng, "k_pmd_inputs", k_pmd_inputs<<<cdiv(n, 256), 256, 0, st>>>(n, seg.start.p, seg.end.p, seg.stdev.p,
+                                                                          y.p, w.p, start_i32.p));
+  FlsaPlan plan(eng, series, n);
+  plan.solve(y.p, w.p, fused.p, 1, 0.0, nullptr);
+  const int64_t S = segment_device(eng, groups, n, start_i32.p, 0, fused.p, y.p, seg.pseudoweight.p, tol_val, out);
+  return S;
+}
 
 // Core: groups over device arrays -> segments in device buffers owned by `ds`.
 int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int64_t nrows,
@@ -261,29 +301,22 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   d_group_row0.upload(group_row0);
   DevBuf<int32_t> flags(st, (size_t)nrows), run_pos(st, (size_t)nrows);
   flags.zero();   // rows outside every group (none in practice) are not heads
-  k_seg_run_heads<<<(int)tile_group.size(), 256, 0, st>>>(d_groups.p, d_tile_group.p, d_tile_r0.p, d_beta,
-                                                          flags.p);
-  ML_CHECK_LAUNCH();
-  eng.launches++;
+  ML_LAUNCH(eng, "k_seg_run_heads", k_seg_run_heads<<<(int)tile_group.size(), 256, 0, st>>>(d_groups.p, d_tile_group.p, d_tile_r0.p, d_beta,
+                                                          flags.p));
   Scan scan;
   DevBuf<int32_t> run_row(st, (size_t)nrows);
   const int32_t n_runs = scan.run(eng, flags.p, nrows, run_pos.p, run_row.p);
   DevBuf<int32_t> seg_head(st, std::max(1, n_runs)), seg_of_run(st, std::max(1, n_runs)),
       seg_run(st, std::max(1, n_runs)), run_group(st, std::max(1, n_runs));
-  k_seg_merge<<<cdiv(ng, 64), 64, 0, st>>>(d_groups.p, ng, run_pos.p, run_row.p, n_runs, d_beta, tol_val,
-                                           seg_head.p);
-  ML_CHECK_LAUNCH();
-  k_run_group<<<cdiv(n_runs, 256), 256, 0, st>>>(run_row.p, n_runs, d_group_row0.p, ng, run_group.p);
-  ML_CHECK_LAUNCH();
-  eng.launches += 2;
+  ML_LAUNCH(eng, "k_seg_merge", k_seg_merge<<<cdiv(ng, 64), 64, 0, st>>>(d_groups.p, ng, run_pos.p, run_row.p, n_runs, d_beta, tol_val,
+                                           seg_head.p));
+  ML_LAUNCH(eng, "k_run_group", k_run_group<<<cdiv(n_runs, 256), 256, 0, st>>>(run_row.p, n_runs, d_group_row0.p, ng, run_group.p));
   const int32_t n_segs = scan.run(eng, seg_head.p, n_runs, seg_of_run.p, seg_run.p);
   ds.alloc(st, n_segs);
   SegOut out = ds.view();
-  k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
+  ML_LAUNCH(eng, "k_seg_emit", k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
                                                 seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
-                                                d_betahat, d_pw, out);
-  ML_CHECK_LAUNCH();
-  eng.launches++;
+                                                d_betahat, d_pw, out));
   ML_CUDA(cudaStreamSynchronize(st));
   return n_segs;
 }
@@ -303,9 +336,7 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
   d_pw.upload(pw, n);
   // groups = maximal blocks of equal estimate_id (the reference compares neighbours only)
   DevBuf<int32_t> gflags(st, (size_t)n), ghead(st, (size_t)n);
-  k_group_heads<<<cdiv(n, 256), 256, 0, st>>>(d_idx.p, n, gflags.p);
-  ML_CHECK_LAUNCH();
-  eng.launches++;
+  ML_LAUNCH(eng, "k_group_heads", k_group_heads<<<cdiv(n, 256), 256, 0, st>>>(d_idx.p, n, gflags.p));
   Scan scan;
   const int32_t ng = scan.run(eng, gflags.p, n, nullptr, ghead.p);
   std::vector<int32_t> heads(ng);
