@@ -427,19 +427,22 @@ k_offset_partial(const RowTile* __restrict__ tiles, const JobDev* __restrict__ j
   if (threadIdx.x == 0) { part[2 * blockIdx.x] = a; part[2 * blockIdx.x + 1] = b; }
 }
 
-__global__ void k_offset_finalize(const int32_t* __restrict__ ent_job, const int32_t* __restrict__ ent_d,
-                                  int n_ent, const JobDev* __restrict__ jobs,
-                                  const int32_t* __restrict__ ctl, const int32_t* __restrict__ dtile0,
-                                  const double* __restrict__ part, double* __restrict__ off,
-                                  double* __restrict__ old_off) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_ent) return;
+__global__ void __launch_bounds__(128)
+k_offset_finalize(const int32_t* __restrict__ ent_job, const int32_t* __restrict__ ent_d, int n_ent,
+                  const JobDev* __restrict__ jobs, const int32_t* __restrict__ ctl,
+                  const int32_t* __restrict__ dtile0, const double* __restrict__ part,
+                  double* __restrict__ off, double* __restrict__ old_off) {
+  __shared__ double sm[8];
+  const int i = blockIdx.x;   // one block per (job, dataset): fixed-order sum over that dataset's tiles
   const int j = ent_job[i], d = ent_d[i];
   if (!(ctl[j] & CTL_UPDATE)) return;
   const JobDev J = jobs[j];
   if (d >= J.D) return;
   double What = 0.0, Zs = 0.0;
-  for (int t = dtile0[i]; t < dtile0[i + 1]; ++t) { What += part[2 * t]; Zs += part[2 * t + 1]; }
+  for (int t = dtile0[i] + threadIdx.x; t < dtile0[i + 1]; t += 128) { What += part[2 * t]; Zs += part[2 * t + 1]; }
+  What = block_sum_ordered(What, sm);
+  Zs = block_sum_ordered(Zs, sm);
+  if (threadIdx.x != 0) return;
   const double q = Zs / What;
   const double zhat = (What == 0) ? What : q;
   const double pwd = (1. * What) * 1.;
@@ -554,33 +557,42 @@ k_tv_partial(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
   if (threadIdx.x == 0) part[blockIdx.x] = a;
 }
 
-// one thread per job: tile partials in tile order -> {mlogp, lik, prior, dres, douter}
-__global__ void k_job_finalize(const JobDev* __restrict__ jobs, int njobs, const int32_t* __restrict__ ctl,
-                               const double* __restrict__ row_part, const double* __restrict__ tv_part,
-                               double* __restrict__ scalars /*5 per job*/) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= njobs) return;
+// one block per job: tile partials combined in a fixed order (thread t takes tiles t, t+256, ...,
+// then a fixed tree) -> {mlogp, lik, prior, dres, douter}.  The order depends only on the job's own
+// tile count, so a job gives the same bits wherever it is placed.
+__global__ void __launch_bounds__(256)
+k_job_finalize(const JobDev* __restrict__ jobs, int njobs, const int32_t* __restrict__ ctl,
+               const double* __restrict__ row_part, const double* __restrict__ tv_part,
+               double* __restrict__ scalars /*5 per job*/) {
+  __shared__ double sm[8];
+  const int j = blockIdx.x;
   if (!(ctl[j] & CTL_EVAL)) return;
   const JobDev J = jobs[j];
   double lik = 0.0, dres = 0.0, dout = 0.0;
-  for (int t = J.rtile0; t < J.rtile0 + J.n_rtiles; ++t) {
+  for (int t = J.rtile0 + threadIdx.x; t < J.rtile0 + J.n_rtiles; t += 256) {
     lik += row_part[3 * t];
     dres = fmax(dres, row_part[3 * t + 1]);
     dout = fmax(dout, row_part[3 * t + 2]);
   }
+  lik = block_sum_ordered(lik, sm);
+  dres = block_max(dres, sm);
+  dout = block_max(dout, sm);
   double pri = 0.0;
   const int tiles_per_e = J.n_ptiles / J.E;
   for (int e = 0; e < J.E; ++e) {
     double tv = 0.0;
-    for (int t = 0; t < tiles_per_e; ++t) tv += tv_part[J.ptile0 + e * tiles_per_e + t];
+    for (int t = threadIdx.x; t < tiles_per_e; t += 256) tv += tv_part[J.ptile0 + e * tiles_per_e + t];
+    tv = block_sum_ordered(tv, sm);
     const double lam = J.lambda2;
     pri += lam * tv - (double)(uint64_t)(J.P - 2) * log(lam) + (double)(uint64_t)(J.P - 1) * log(2.0);
   }
-  scalars[5 * j] = lik + pri;
-  scalars[5 * j + 1] = lik;
-  scalars[5 * j + 2] = pri;
-  scalars[5 * j + 3] = dres;
-  scalars[5 * j + 4] = dout;
+  if (threadIdx.x == 0) {
+    scalars[5 * j] = lik + pri;
+    scalars[5 * j + 1] = lik;
+    scalars[5 * j + 2] = pri;
+    scalars[5 * j + 3] = dres;
+    scalars[5 * j + 4] = dout;
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1018,7 +1030,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
                                               cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                               res->pw.p));
       ML_LAUNCH(eng, "k_offset_partial", k_offset_partial<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p));
-      ML_LAUNCH(eng, "k_offset_finalize", k_offset_finalize<<<cdiv(n_ent, 128), 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
+      ML_LAUNCH(eng, "k_offset_finalize", k_offset_finalize<<<n_ent, 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
                                                           cx.dtile0.p, cx.off_part.p, res->offset.p,
                                                           cx.old_off.p));
       for (int j = 0; j < nj; ++j)
@@ -1040,7 +1052,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
                                         res->offset.p, log2pi, res->mu.p, cx.mu_outer.p, want_outer ? 1 : 0,
                                         cx.row_part.p));
       ML_LAUNCH(eng, "k_tv_partial", k_tv_partial<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, res->beta.p, cx.tv_part.p));
-      ML_LAUNCH(eng, "k_job_finalize", k_job_finalize<<<cdiv(nj, 64), 64, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
+      ML_LAUNCH(eng, "k_job_finalize", k_job_finalize<<<nj, 256, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
                                                   cx.scalars.p));
       cx.scalars.download(sc.data(), sc.size());
       ML_CUDA(cudaStreamSynchronize(st));

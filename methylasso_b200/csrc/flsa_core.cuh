@@ -27,7 +27,9 @@
 
 namespace ml {
 
-constexpr int KNOT_CAP = 64;  // ring capacity per knot window (power of two)
+constexpr int KNOT_CAP = 64;       // largest knot window a chunk may hold / save (power of two)
+constexpr int KNOT_CAP_FAST = 32;  // shared-memory ring of the fast path; a thread whose window
+                                   // outgrows it redoes its chunk with a KNOT_CAP ring in local memory
 static_assert((KNOT_CAP & (KNOT_CAP - 1)) == 0, "KNOT_CAP must be a power of two");
 
 enum : int32_t {
@@ -67,9 +69,43 @@ struct ChunkState {
 };
 
 // ---- knot window -------------------------------------------------------------------------
+// A ring of knots (x, a, b) addressed by logical index (masked by CAP-1).  Two storages:
+//   LocalRing   : arrays inside the thread (registers / local memory) — CPU emulation, and the
+//                 in-kernel fallback when a window outgrows the shared-memory ring
+//   StridedRing : a column of a shared-memory tile laid out [field][slot][thread]; lanes of a warp
+//                 touch distinct banks whatever slot each of them is at (no bank conflicts)
+template <int CAP_>
+struct LocalRing {
+  static constexpr int CAP = CAP_;
+  double xs[CAP_], as[CAP_], bs[CAP_];
+  ML_HD double x(int i) const { return xs[i & (CAP_ - 1)]; }
+  ML_HD double a(int i) const { return as[i & (CAP_ - 1)]; }
+  ML_HD double b(int i) const { return bs[i & (CAP_ - 1)]; }
+  ML_HD void set(int i, double x_, double a_, double b_) {
+    const int k = i & (CAP_ - 1);
+    xs[k] = x_; as[k] = a_; bs[k] = b_;
+  }
+};
+
+template <int CAP_, int STRIDE>
+struct StridedRing {
+  static constexpr int CAP = CAP_;
+  double* base;  // this thread's column
+  ML_HD double x(int i) const { return base[(i & (CAP_ - 1)) * STRIDE]; }
+  ML_HD double a(int i) const { return base[(CAP_ + (i & (CAP_ - 1))) * STRIDE]; }
+  ML_HD double b(int i) const { return base[(2 * CAP_ + (i & (CAP_ - 1))) * STRIDE]; }
+  ML_HD void set(int i, double x_, double a_, double b_) {
+    const int k = i & (CAP_ - 1);
+    base[k * STRIDE] = x_;
+    base[(CAP_ + k) * STRIDE] = a_;
+    base[(2 * CAP_ + k) * STRIDE] = b_;
+  }
+};
+
+template <class Ring>
 struct Knots {
-  double x[KNOT_CAP], a[KNOT_CAP], b[KNOT_CAP];
-  int l, r;      // logical indices of the leftmost / rightmost live knot (ring: & (CAP-1))
+  Ring ring;
+  int l, r;      // logical indices of the leftmost / rightmost live knot
   uint64_t h;    // xor of knot_hash over live knots: cheap inequality test between two windows
 };
 
@@ -84,52 +120,50 @@ ML_HD uint64_t knot_hash(double x, double a, double b) {
 }
 
 // first element of a series: gfl_tf.c:231-240
-ML_HD void knots_init_first(Knots& q, double y0, double w0, double lam) {
+template <class Ring>
+ML_HD void knots_init_first(Knots<Ring>& q, double y0, double w0, double lam, double& tm0, double& tp0) {
   q.l = 0;
   q.r = 1;
-  q.x[0] = -lam / w0 + y0;
-  q.a[0] = w0;
-  q.b[0] = -w0 * y0 + lam;
-  q.x[1] = lam / w0 + y0;
-  q.a[1] = -w0;
-  q.b[1] = w0 * y0 + lam;
-  q.h = knot_hash(q.x[0], q.a[0], q.b[0]) ^ knot_hash(q.x[1], q.a[1], q.b[1]);
+  tm0 = -lam / w0 + y0;
+  tp0 = lam / w0 + y0;
+  const double bl = -w0 * y0 + lam, br = w0 * y0 + lam;
+  q.ring.set(0, tm0, w0, bl);
+  q.ring.set(1, tp0, -w0, br);
+  q.h = knot_hash(tm0, w0, bl) ^ knot_hash(tp0, -w0, br);
 }
 
 // incoming message identically -lam (sign < 0) or +lam (sign > 0): one zero-slope knot at
 // +inf / -inf carrying the 2*lam offset between the left-scan and right-scan conventions.
-ML_HD void knots_init_bound(Knots& q, int sign, double lam) {
+template <class Ring>
+ML_HD void knots_init_bound(Knots<Ring>& q, int sign, double lam) {
   q.l = 0;
   q.r = 0;
-  q.x[0] = sign < 0 ? HUGE_VAL : -HUGE_VAL;
-  q.a[0] = 0.0;
-  q.b[0] = 2 * lam;
-  q.h = knot_hash(q.x[0], q.a[0], q.b[0]);
+  const double x0 = sign < 0 ? HUGE_VAL : -HUGE_VAL;
+  q.ring.set(0, x0, 0.0, 2 * lam);
+  q.h = knot_hash(x0, 0.0, 2 * lam);
 }
 
 // One DP step: fold element (y, w) into the message (gfl_tf.c:251-289).  Returns false when the
-// window would outgrow the ring.  tm/tp are the back-pointers of this step.
-ML_HD bool dp_step(Knots& q, double y, double w, double lam, double& tm, double& tp) {
-  constexpr int M = KNOT_CAP - 1;
+// window would outgrow the ring (the ring is then left untouched).  tm/tp are the back-pointers.
+template <class Ring>
+ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, double& tp) {
   double alo = w, blo = -w * y - lam;      // :286-287 (seeds of the incoming element)
   double ahi = -w, bhi = w * y - lam;      // :288-289
   int lo = q.l, hi = q.r;
   uint64_t h = q.h;
   while (lo <= hi) {                       // :253-258 (hi == q.r here)
-    const int i = lo & M;
-    const double xi = q.x[i];
+    const double xi = q.ring.x(lo);
     if (alo * xi + blo > -lam) break;
-    const double ai = q.a[i], bi = q.b[i];
+    const double ai = q.ring.a(lo), bi = q.ring.b(lo);
     alo += ai;
     blo += bi;
     h ^= knot_hash(xi, ai, bi);
     ++lo;
   }
   while (hi >= lo) {                       // :264-269
-    const int i = hi & M;
-    const double xi = q.x[i];
+    const double xi = q.ring.x(hi);
     if (-ahi * xi - bhi < lam) break;
-    const double ai = q.a[i], bi = q.b[i];
+    const double ai = q.ring.a(hi), bi = q.ring.b(hi);
     ahi += ai;
     bhi += bi;
     h ^= knot_hash(xi, ai, bi);
@@ -138,10 +172,10 @@ ML_HD bool dp_step(Knots& q, double y, double w, double lam, double& tm, double&
   tm = (-lam - blo) / alo;                 // :272
   tp = (lam + bhi) / (-ahi);               // :277
   const int nl = lo - 1, nr = hi + 1;
-  if (nr - nl + 1 > KNOT_CAP) return false;
+  if (nr - nl + 1 > Ring::CAP) return false;
   const double bl = blo + lam, br = bhi + lam;   // :283, :285
-  q.x[nl & M] = tm; q.a[nl & M] = alo; q.b[nl & M] = bl;
-  q.x[nr & M] = tp; q.a[nr & M] = ahi; q.b[nr & M] = br;
+  q.ring.set(nl, tm, alo, bl);
+  q.ring.set(nr, tp, ahi, br);
   q.l = nl;
   q.r = nr;
   q.h = h ^ knot_hash(tm, alo, bl) ^ knot_hash(tp, ahi, br);
@@ -149,55 +183,55 @@ ML_HD bool dp_step(Knots& q, double y, double w, double lam, double& tm, double&
 }
 
 // last coefficient: zero of the final message (gfl_tf.c:294-302)
-ML_HD double dp_last(const Knots& q, double y, double w, double lam) {
-  constexpr int M = KNOT_CAP - 1;
+template <class Ring>
+ML_HD double dp_last(const Knots<Ring>& q, double y, double w, double lam) {
   double alo = w, blo = -w * y - lam;
   for (int lo = q.l; lo <= q.r; ++lo) {
-    const int i = lo & M;
-    if (alo * q.x[i] + blo > 0) break;
-    alo += q.a[i];
-    blo += q.b[i];
+    if (alo * q.ring.x(lo) + blo > 0) break;
+    alo += q.ring.a(lo);
+    blo += q.ring.b(lo);
   }
   return -blo / alo;
 }
 
-ML_HD bool knots_same(const Knots& p, const Knots& q) {
-  constexpr int M = KNOT_CAP - 1;
+template <class Ring>
+ML_HD bool knots_same(const Knots<Ring>& p, const Knots<Ring>& q) {
   if (p.h != q.h || p.r - p.l != q.r - q.l) return false;
   const int cnt = p.r - p.l + 1;
   for (int k = 0; k < cnt; ++k) {
-    const int i = (p.l + k) & M, j = (q.l + k) & M;
-    if (f64_bits(p.x[i]) != f64_bits(q.x[j]) || f64_bits(p.a[i]) != f64_bits(q.a[j]) ||
-        f64_bits(p.b[i]) != f64_bits(q.b[j]))
+    if (f64_bits(p.ring.x(p.l + k)) != f64_bits(q.ring.x(q.l + k)) ||
+        f64_bits(p.ring.a(p.l + k)) != f64_bits(q.ring.a(q.l + k)) ||
+        f64_bits(p.ring.b(p.l + k)) != f64_bits(q.ring.b(q.l + k)))
       return false;
   }
   return true;
 }
 
-ML_HD void knots_save(const Knots& q, ChunkState& st) {
-  constexpr int M = KNOT_CAP - 1;
-  const int cnt = q.r - q.l + 1;
+template <class Ring>
+ML_HD void knots_save(const Knots<Ring>& q, ChunkState& st) {
+  const int cnt = q.r - q.l + 1;   // <= KNOT_CAP: callers only instantiate rings up to KNOT_CAP
   for (int k = 0; k < cnt; ++k) {
-    const int i = (q.l + k) & M;
-    st.x[k] = q.x[i];
-    st.a[k] = q.a[i];
-    st.b[k] = q.b[i];
+    st.x[k] = q.ring.x(q.l + k);
+    st.a[k] = q.ring.a(q.l + k);
+    st.b[k] = q.ring.b(q.l + k);
   }
   st.count = cnt;
 }
 
-ML_HD void knots_load(Knots& q, const ChunkState& st) {
+// false if the saved window does not fit this ring
+template <class Ring>
+ML_HD bool knots_load(Knots<Ring>& q, const ChunkState& st) {
   const int cnt = st.count;
+  if (cnt > Ring::CAP) return false;
   uint64_t h = 0;
   for (int k = 0; k < cnt; ++k) {
-    q.x[k] = st.x[k];
-    q.a[k] = st.a[k];
-    q.b[k] = st.b[k];
+    q.ring.set(k, st.x[k], st.a[k], st.b[k]);
     h ^= knot_hash(st.x[k], st.a[k], st.b[k]);
   }
   q.l = 0;
   q.r = cnt - 1;
   q.h = h;
+  return true;
 }
 
 // ---- pass A: every chunk independently -----------------------------------------------------
@@ -205,35 +239,44 @@ ML_HD void knots_load(Knots& q, const ChunkState& st) {
 // status = 0, resolved_from = ke before the first round.  Later rounds call this again with a
 // longer warm-up for chunks that are not CHUNK_DONE yet; only the still-missing head
 // [kb, resolved_from) of the chunk is then produced.
-ML_HD void flsa_pass_a(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
+// q and p are scratch windows provided by the caller (p is used by the warm-up only).
+// Returns false if a window outgrew Ring::CAP; `st` is then untouched and the caller may retry
+// with a larger ring.
+template <class Ring>
+ML_HD bool flsa_pass_a(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
                        const double* __restrict__ w, double* __restrict__ tm,
-                       double* __restrict__ tp, ChunkState& st, int warm) {
+                       double* __restrict__ tp, ChunkState& st, int warm, Knots<Ring>& q,
+                       Knots<Ring>& p) {
   const double lam = S.lam;
   const int kb = c.kb, ke = c.ke;
   const bool have_end = (st.status & CHUNK_END_VALID) != 0;
   const int stop = have_end ? st.resolved_from : ke;  // tm/tp of [stop, ke) already written
-  Knots q;
   double t1, t2;
-  bool ok = true;
+  double yn = 0.0, wn = 0.0;   // element k, loaded one step ahead of its use (k + 1 <= n - 1 always)
+  bool ok = true, irregular = false;
   int k, resolved;
   if (kb - warm <= 1) {
     // close enough to the head of the series: run from element 0, exact by construction
-    knots_init_first(q, y[0], w[0], lam);
+    knots_init_first(q, y[0], w[0], lam, t1, t2);
     if (kb == 1) {                                       // gfl_tf.c:231-232
-      tm[0] = q.x[0];
-      tp[0] = q.x[1];
-      if (q.x[0] > q.x[1]) st.status |= CHUNK_IRREGULAR;
+      tm[0] = t1;
+      tp[0] = t2;
+      irregular = t1 > t2;
     }
     for (k = 1; k < kb && ok; ++k) ok = dp_step(q, y[k], w[k], lam, t1, t2);
     resolved = kb;
+    if (k < stop) { yn = y[k]; wn = w[k]; }
   } else {
-    Knots p;
     knots_init_bound(q, -1, lam);
     knots_init_bound(p, +1, lam);
     bool merged = false;
     bool pristine = true;  // both windows still hold only their +-inf sentinel
-    for (k = kb - warm; k < stop && ok; ++k) {
-      const double yk = y[k], wk = w[k];
+    k = kb - warm;
+    if (k < stop) { yn = y[k]; wn = w[k]; }
+    for (; k < stop && ok; ++k) {
+      const double yk = yn, wk = wn;
+      yn = y[k + 1];
+      wn = w[k + 1];
       double u1, u2;
       if (pristine) {
         // A zero-weight element leaves a constant message unchanged (clip(+-lam + 0)); the generic
@@ -245,52 +288,67 @@ ML_HD void flsa_pass_a(const SeriesDesc& S, const ChunkDesc& c, const double* __
       ok = dp_step(p, yk, wk, lam, u1, u2) && ok;
       if (ok && knots_same(p, q)) { merged = true; ++k; break; }
     }
-    if (!ok) { st.status |= CHUNK_OVERFLOW; return; }
-    if (!merged) return;                       // nothing learnt this round
-    for (; k < kb && ok; ++k) ok = dp_step(q, y[k], w[k], lam, t1, t2);
+    if (!ok) return false;
+    if (!merged) return true;                  // nothing learnt this round
+    for (; k < kb && ok; ++k) {
+      const double yk = yn, wk = wn;
+      yn = y[k + 1];
+      wn = w[k + 1];
+      ok = dp_step(q, yk, wk, lam, t1, t2);
+    }
     resolved = k;  // >= kb: first step whose back-pointers are exact
   }
-  bool irregular = false;
   for (; k < stop && ok; ++k) {
-    ok = dp_step(q, y[k], w[k], lam, t1, t2);
+    const double yk = yn, wk = wn;
+    yn = y[k + 1];
+    wn = w[k + 1];
+    ok = dp_step(q, yk, wk, lam, t1, t2);
     tm[k] = t1;
     tp[k] = t2;
     irregular |= (t1 > t2);
   }
+  if (!ok) return false;
   if (irregular) st.status |= CHUNK_IRREGULAR;
-  if (!ok) { st.status |= CHUNK_OVERFLOW; return; }
   if (!have_end) { knots_save(q, st); st.status |= CHUNK_END_VALID; }
   st.resolved_from = resolved;
   if (resolved == kb) st.status |= CHUNK_DONE;
+  return true;
 }
 
 // ---- pass B / C: finish the unresolved head of a chunk from its left neighbour's end state ---
-// `left` must be CHUNK_END_VALID and stable (written by an earlier launch).
-ML_HD void flsa_finish_chunk(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
+// `left` must be CHUNK_END_VALID and stable (written by an earlier launch).  Returns false on
+// ring overflow (st untouched).
+template <class Ring>
+ML_HD bool flsa_finish_chunk(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
                              const double* __restrict__ w, double* __restrict__ tm,
-                             double* __restrict__ tp, const ChunkState& left, ChunkState& st) {
-  Knots q;
-  knots_load(q, left);
+                             double* __restrict__ tp, const ChunkState& left, ChunkState& st,
+                             Knots<Ring>& q) {
+  if (!knots_load(q, left)) return false;
   const double lam = S.lam;
   const bool have_end = (st.status & CHUNK_END_VALID) != 0;
   const int stop = have_end ? st.resolved_from : c.ke;
   double t1, t2;
-  bool ok = true;
-  bool irregular = false;
+  bool ok = true, irregular = false;
+  double yn = 0.0, wn = 0.0;
+  if (c.kb < stop) { yn = y[c.kb]; wn = w[c.kb]; }
   for (int k = c.kb; k < stop && ok; ++k) {
-    ok = dp_step(q, y[k], w[k], lam, t1, t2);
+    const double yk = yn, wk = wn;
+    yn = y[k + 1];
+    wn = w[k + 1];
+    ok = dp_step(q, yk, wk, lam, t1, t2);
     tm[k] = t1;
     tp[k] = t2;
     irregular |= (t1 > t2);
   }
+  if (!ok) return false;
   if (irregular) st.status |= CHUNK_IRREGULAR;
-  if (!ok) { st.status |= CHUNK_OVERFLOW; return; }
   if (!have_end) {  // the whole chunk was unresolved: its end state is ours
     knots_save(q, st);
     st.status |= CHUNK_END_VALID;
   }
   st.resolved_from = c.kb;
   st.status |= CHUNK_DONE;
+  return true;
 }
 
 // ---- start-to-end DP with the knot window in caller-provided scratch of 2n doubles x 3 -------

@@ -133,23 +133,36 @@ k_seg_run_heads(const SegGroup* __restrict__ groups, const int32_t* __restrict__
     flags[i] = (i == G.row0 || beta[i] != beta[i - 1]) ? 1 : 0;
 }
 
-// one thread per group: walk the runs, open a segment when |beta_run - beta_segment_start| > tol
-// (methylation_helpers.cpp:23; the estimate change of :42 is the group boundary)
-__global__ void k_seg_merge(const SegGroup* __restrict__ groups, int ngroups,
-                            const int32_t* __restrict__ run_pos /*row -> run index*/,
-                            const int32_t* __restrict__ run_row, int32_t n_runs,
-                            const double* __restrict__ beta, double tol, int32_t* __restrict__ seg_head) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= ngroups) return;
-  const SegGroup G = groups[g];
-  if (G.nrows == 0) return;
-  const int r_first = run_pos[G.row0];
-  // empty groups were dropped by the host, so the next group's first run closes this one
-  const int rend = (g + 1 < ngroups) ? run_pos[groups[g + 1].row0] : n_runs;
-  double curr = beta[run_row[r_first]];
-  seg_head[r_first] = 1;
-  for (int r = r_first + 1; r < rend; ++r) {
-    const double b = beta[run_row[r]];
+// Tolerance merge over runs.  A segment opens at run r when |beta_r - beta_at_segment_start| > tol
+// (methylation_helpers.cpp:23; the estimate change of :42 is the group boundary).  The dependence
+// on the segment start is sequential, but a run whose jump from its predecessor exceeds 2*tol opens
+// a segment whatever the current start is (the predecessor is within tol of that start, triangle
+// inequality; the 2.001 factor absorbs rounding), so such CERTAIN heads cut the walk into
+// independent pieces: one thread per piece.
+__global__ void k_seg_certain(const SegGroup* __restrict__ groups, const int32_t* __restrict__ run_group,
+                              const int32_t* __restrict__ run_row, int32_t n_runs,
+                              const double* __restrict__ beta, double tol, double* __restrict__ run_beta,
+                              int32_t* __restrict__ certain) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_runs) return;
+  const int64_t row = run_row[r];
+  const double b = beta[row];
+  run_beta[r] = b;
+  bool c = row == groups[run_group[r]].row0;
+  if (!c) c = fabs(b - beta[run_row[r - 1]]) > 2.001 * tol;
+  certain[r] = c ? 1 : 0;
+}
+
+__global__ void k_seg_merge(const int32_t* __restrict__ piece_run, int32_t n_pieces, int32_t n_runs,
+                            const double* __restrict__ run_beta, double tol, int32_t* __restrict__ seg_head) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pieces) return;
+  const int r0 = piece_run[p];
+  const int r1 = p + 1 < n_pieces ? piece_run[p + 1] : n_runs;
+  double curr = run_beta[r0];
+  seg_head[r0] = 1;
+  for (int r = r0 + 1; r < r1; ++r) {
+    const double b = run_beta[r];
     if (fabs(b - curr) > tol) { seg_head[r] = 1; curr = b; }
     else seg_head[r] = 0;
   }
@@ -307,10 +320,15 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   DevBuf<int32_t> run_row(st, (size_t)nrows);
   const int32_t n_runs = scan.run(eng, flags.p, nrows, run_pos.p, run_row.p);
   DevBuf<int32_t> seg_head(st, std::max(1, n_runs)), seg_of_run(st, std::max(1, n_runs)),
-      seg_run(st, std::max(1, n_runs)), run_group(st, std::max(1, n_runs));
-  ML_LAUNCH(eng, "k_seg_merge", k_seg_merge<<<cdiv(ng, 64), 64, 0, st>>>(d_groups.p, ng, run_pos.p, run_row.p, n_runs, d_beta, tol_val,
-                                           seg_head.p));
+      seg_run(st, std::max(1, n_runs)), run_group(st, std::max(1, n_runs)), certain(st, std::max(1, n_runs)),
+      piece_run(st, std::max(1, n_runs));
+  DevBuf<double> run_beta(st, std::max(1, n_runs));
   ML_LAUNCH(eng, "k_run_group", k_run_group<<<cdiv(n_runs, 256), 256, 0, st>>>(run_row.p, n_runs, d_group_row0.p, ng, run_group.p));
+  ML_LAUNCH(eng, "k_seg_certain", k_seg_certain<<<cdiv(n_runs, 256), 256, 0, st>>>(d_groups.p, run_group.p, run_row.p, n_runs, d_beta,
+                                                                               tol_val, run_beta.p, certain.p));
+  const int32_t n_pieces = scan.run(eng, certain.p, n_runs, nullptr, piece_run.p);
+  ML_LAUNCH(eng, "k_seg_merge", k_seg_merge<<<cdiv(n_pieces, 128), 128, 0, st>>>(piece_run.p, n_pieces, n_runs, run_beta.p, tol_val,
+                                                                            seg_head.p));
   const int32_t n_segs = scan.run(eng, seg_head.p, n_runs, seg_of_run.p, seg_run.p);
   ds.alloc(st, n_segs);
   SegOut out = ds.view();

@@ -10,7 +10,7 @@ using namespace ml;
 extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int chunk, int warm,
                         double* beta, double* tm, double* tp, int tile, long long* stats) {
   // stats: [0] chunks, [1] resolved in A, [2] finished in B, [3] finished in C, [4] overflow,
-  //        [5] max steps of B prefix, [6] total DP steps executed, [7] clamp order violations
+  //        [5] max steps of B prefix, [6] chunks that outgrew the fast ring, [7] clamp order violations
   for (int i = 0; i < 8; ++i) stats[i] = 0;
   if (n == 0) return 0;
   if (n == 1 || lam == 0) { for (int i = 0; i < n; ++i) beta[i] = y[i]; return 0; }
@@ -27,9 +27,16 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   S.n_chunks = (int)cd.size();
   std::vector<ChunkState> st(cd.size());
   stats[0] = (long long)cd.size();
+  typedef LocalRing<KNOT_CAP_FAST> FastRing;   // same two-tier policy as the kernels
+  typedef LocalRing<KNOT_CAP> BigRing;
   for (size_t c = 0; c < cd.size(); ++c) {
-    flsa_pass_a(S, cd[c], y, w, tm, tp, st[c], warm);
-    if (cd[c].kb == 1) { Knots q; knots_init_first(q, y[0], w[0], lam); tm[0] = q.x[0]; tp[0] = q.x[1]; }
+    st[c].status = 0; st[c].count = 0; st[c].resolved_from = cd[c].ke;
+    Knots<FastRing> q, p;
+    if (!flsa_pass_a(S, cd[c], y, w, tm, tp, st[c], warm, q, p)) {
+      stats[6]++;
+      Knots<BigRing> Q, P;
+      if (!flsa_pass_a(S, cd[c], y, w, tm, tp, st[c], warm, Q, P)) st[c].status |= CHUNK_OVERFLOW;
+    }
     if (st[c].status & CHUNK_DONE) stats[1]++;
     if (st[c].status & CHUNK_OVERFLOW) stats[4]++;
   }
@@ -40,7 +47,11 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
     if (a_status[c] & (CHUNK_DONE | CHUNK_OVERFLOW)) continue;
     if (!(a_status[c - 1] & CHUNK_END_VALID)) continue;
     stats[5] = std::max<long long>(stats[5], st[c].resolved_from - cd[c].kb);
-    flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c]);
+    { Knots<FastRing> q;
+      if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], q)) {
+        Knots<BigRing> Q;
+        if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW;
+      } }
     stats[2]++;
   }
   // pass C: chains, in order
@@ -49,7 +60,8 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
     if (st[c].status & CHUNK_OVERFLOW) { ovf = true; break; }
     if (st[c].status & CHUNK_DONE) continue;
     if (c == 0 || !(st[c - 1].status & CHUNK_END_VALID)) return -1;
-    flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c]);
+    { Knots<BigRing> Q;
+      if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW; }
     if (st[c].status & CHUNK_OVERFLOW) { ovf = true; break; }
     stats[3]++;
   }
@@ -59,7 +71,7 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
     std::vector<double> x(2 * (size_t)n), a(2 * (size_t)n), b(2 * (size_t)n);
     flsa_sequential_forward(n, y, w, lam, x.data(), a.data(), b.data(), tm, tp, &blast);
   } else {
-    Knots q; knots_load(q, st.back());
+    Knots<BigRing> q; knots_load(q, st.back());
     blast = dp_last(q, y[n - 1], w[n - 1], lam);
   }
   // backward: 3-phase reverse clamp scan over tiles of `tile` back-pointers (k = 0..n-2)
