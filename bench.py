@@ -186,7 +186,8 @@ def kernel_bytes(N, EP, D, words):
         "k_rank_unique": 16 * N + 4 * D * EP + 8 * EP,
         "k_pseudodata": 4 * D * EP + 8 * N + 32 * EP,
         "k_offset_partial": 8 * N,
-        "flsa_pass_a_kernel": 32 * EP,
+        "flsa_warm_kernel": 16 * EP,   # y, w of the warm-up stretch (warm == chunk: one extra read of each)
+        "flsa_main_kernel": 32 * EP,   # y, w read; tm, tp written
         "flsa_bwd_reduce_kernel": 16 * EP,
         "flsa_bwd_apply_kernel": 32 * EP,
         "k_center": 16 * EP,
@@ -351,7 +352,7 @@ def main():
     if top:
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": top["frac_of_hbm"], "traffic": None, "peak_source": pk_kind,
-                    "note": "flsa_pass_a_kernel is latency-bound (dependent fp64 compare/add/divide chain per element); "
+                    "note": "the FLSA chunk kernels are latency-bound (dependent fp64 compare/add/divide chain per element); "
                             "its HBM fraction is reported for the record, see profiles/ and DESIGN.md"}
 
     # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------

@@ -18,8 +18,9 @@
 //    thread continues with one copy, now exact.  (Measured on WGBS-like series: the windows
 //    coalesce after a few hundred steps at lam=25 and the coalesced window was bit-identical to
 //    the sequential run's window in every case — scripts/experiments/coalesce.py.)
-//  * Chunks whose warm-up did not coalesce before their first step are finished by pass B from
-//    the (exact) end state their left neighbour saved, chains of such chunks by pass C.
+//  * A chunk whose warm-up did not coalesce takes its start state from the (exact) end state its
+//    left neighbour saved, or retries with a warm-up eight times longer in the next round; what
+//    is still open after the last round is finished in order by one lane per series.
 //  * The back-substitution beta_k = clamp(beta_{k+1}; tm_k, tp_k) is a composition of clamps,
 //    which is again a clamp: a reverse parallel scan with min/max only (exact).
 #pragma once
@@ -41,6 +42,7 @@ enum : int32_t {
   CHUNK_END_VALID = 1,   // end-of-chunk knot window saved and exact
   CHUNK_DONE = 2,        // every tm/tp of the chunk written
   CHUNK_OVERFLOW = 4,    // knot window outgrew KNOT_CAP: series goes to the global-scratch kernel
+  CHUNK_START_VALID = 16, // the saved window is the exact state just BEFORE the chunk's first step
   CHUNK_IRREGULAR = 8,   // some tm_k > tp_k (rounding on absurd inputs): clamps do not compose, the
                          // series' back-substitution is redone element by element
 };
@@ -63,8 +65,8 @@ struct ChunkDesc {
 struct ChunkState {
   int32_t status;
   int32_t count;          // knots saved
-  int32_t resolved_from;  // first step of the chunk whose tm/tp pass A wrote (== ke: none)
-  int32_t pad;
+  int32_t reserved;
+  int32_t pad;            // snapshot of status taken at the start of a launch (neighbour reads)
   double x[KNOT_CAP], a[KNOT_CAP], b[KNOT_CAP];
 };
 
@@ -106,18 +108,7 @@ template <class Ring>
 struct Knots {
   Ring ring;
   int l, r;      // logical indices of the leftmost / rightmost live knot
-  uint64_t h;    // xor of knot_hash over live knots: cheap inequality test between two windows
 };
-
-ML_HD uint64_t knot_hash(double x, double a, double b) {
-  uint64_t m = f64_bits(x) * 0x9E3779B97F4A7C15ull;
-  m ^= m >> 29;
-  m += f64_bits(a) * 0xBF58476D1CE4E5B9ull;
-  m ^= m >> 32;
-  m += f64_bits(b) * 0x94D049BB133111EBull;
-  m ^= m >> 31;
-  return m;
-}
 
 // first element of a series: gfl_tf.c:231-240
 template <class Ring>
@@ -129,7 +120,6 @@ ML_HD void knots_init_first(Knots<Ring>& q, double y0, double w0, double lam, do
   const double bl = -w0 * y0 + lam, br = w0 * y0 + lam;
   q.ring.set(0, tm0, w0, bl);
   q.ring.set(1, tp0, -w0, br);
-  q.h = knot_hash(tm0, w0, bl) ^ knot_hash(tp0, -w0, br);
 }
 
 // incoming message identically -lam (sign < 0) or +lam (sign > 0): one zero-slope knot at
@@ -140,34 +130,44 @@ ML_HD void knots_init_bound(Knots<Ring>& q, int sign, double lam) {
   q.r = 0;
   const double x0 = sign < 0 ? HUGE_VAL : -HUGE_VAL;
   q.ring.set(0, x0, 0.0, 2 * lam);
-  q.h = knot_hash(x0, 0.0, 2 * lam);
 }
 
 // One DP step: fold element (y, w) into the message (gfl_tf.c:251-289).  Returns false when the
 // window would outgrow the ring (the ring is then left untouched).  tm/tp are the back-pointers.
+// The outermost knot of each side is examined on every step, so both are loaded up front (one
+// shared-memory latency instead of two); the arithmetic and its order are the reference's.
 template <class Ring>
 ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, double& tp) {
   double alo = w, blo = -w * y - lam;      // :286-287 (seeds of the incoming element)
   double ahi = -w, bhi = w * y - lam;      // :288-289
-  int lo = q.l, hi = q.r;
-  uint64_t h = q.h;
-  while (lo <= hi) {                       // :253-258 (hi == q.r here)
-    const double xi = q.ring.x(lo);
-    if (alo * xi + blo > -lam) break;
-    const double ai = q.ring.a(lo), bi = q.ring.b(lo);
-    alo += ai;
-    blo += bi;
-    h ^= knot_hash(xi, ai, bi);
+  int lo = q.l, hi = q.r;                  // the window always holds at least one knot
+  const double xl = q.ring.x(lo), al = q.ring.a(lo), bl0 = q.ring.b(lo);
+  const double xr = q.ring.x(hi), ar = q.ring.a(hi), br0 = q.ring.b(hi);
+  if (!(alo * xl + blo > -lam)) {          // :253-258, first iteration peeled (lo <= r holds)
+    alo += al;
+    blo += bl0;
     ++lo;
+    while (lo <= hi) {
+      const double xi = q.ring.x(lo);
+      if (alo * xi + blo > -lam) break;
+      const double ai = q.ring.a(lo), bi = q.ring.b(lo);
+      alo += ai;
+      blo += bi;
+      ++lo;
+    }
   }
-  while (hi >= lo) {                       // :264-269
-    const double xi = q.ring.x(hi);
-    if (-ahi * xi - bhi < lam) break;
-    const double ai = q.ring.a(hi), bi = q.ring.b(hi);
-    ahi += ai;
-    bhi += bi;
-    h ^= knot_hash(xi, ai, bi);
+  if (hi >= lo && !(-ahi * xr - bhi < lam)) {   // :264-269, first iteration peeled
+    ahi += ar;
+    bhi += br0;
     --hi;
+    while (hi >= lo) {
+      const double xi = q.ring.x(hi);
+      if (-ahi * xi - bhi < lam) break;
+      const double ai = q.ring.a(hi), bi = q.ring.b(hi);
+      ahi += ai;
+      bhi += bi;
+      --hi;
+    }
   }
   tm = (-lam - blo) / alo;                 // :272
   tp = (lam + bhi) / (-ahi);               // :277
@@ -178,7 +178,66 @@ ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, d
   q.ring.set(nr, tp, ahi, br);
   q.l = nl;
   q.r = nr;
-  q.h = h ^ knot_hash(tm, alo, bl) ^ knot_hash(tp, ahi, br);
+  return true;
+}
+
+// The same step applied to the two sandwich copies at once.  Written as one function so that the
+// two independent dependency chains (loads, compares, divisions) interleave in the instruction
+// stream: a lone thread is latency-bound, and the warm-up is where most DP steps are spent.
+template <class Ring>
+ML_HD bool dp_step_dual(Knots<Ring>& q, Knots<Ring>& p, double y, double w, double lam) {
+  const double b_lo0 = -w * y - lam, b_hi0 = w * y - lam;
+  double aloq = w, bloq = b_lo0, ahiq = -w, bhiq = b_hi0;
+  double alop = w, blop = b_lo0, ahip = -w, bhip = b_hi0;
+  int loq = q.l, hiq = q.r, lop = p.l, hip = p.r;
+  const double xlq = q.ring.x(loq), alq = q.ring.a(loq), blq = q.ring.b(loq);
+  const double xlp = p.ring.x(lop), alp = p.ring.a(lop), blp = p.ring.b(lop);
+  const double xrq = q.ring.x(hiq), arq = q.ring.a(hiq), brq = q.ring.b(hiq);
+  const double xrp = p.ring.x(hip), arp = p.ring.a(hip), brp = p.ring.b(hip);
+  const bool popq = !(aloq * xlq + bloq > -lam);
+  const bool popp = !(alop * xlp + blop > -lam);
+  if (popq) {
+    aloq += alq; bloq += blq; ++loq;
+    while (loq <= hiq) {
+      const double xi = q.ring.x(loq);
+      if (aloq * xi + bloq > -lam) break;
+      aloq += q.ring.a(loq); bloq += q.ring.b(loq); ++loq;
+    }
+  }
+  if (popp) {
+    alop += alp; blop += blp; ++lop;
+    while (lop <= hip) {
+      const double xi = p.ring.x(lop);
+      if (alop * xi + blop > -lam) break;
+      alop += p.ring.a(lop); blop += p.ring.b(lop); ++lop;
+    }
+  }
+  if (hiq >= loq && !(-ahiq * xrq - bhiq < lam)) {
+    ahiq += arq; bhiq += brq; --hiq;
+    while (hiq >= loq) {
+      const double xi = q.ring.x(hiq);
+      if (-ahiq * xi - bhiq < lam) break;
+      ahiq += q.ring.a(hiq); bhiq += q.ring.b(hiq); --hiq;
+    }
+  }
+  if (hip >= lop && !(-ahip * xrp - bhip < lam)) {
+    ahip += arp; bhip += brp; --hip;
+    while (hip >= lop) {
+      const double xi = p.ring.x(hip);
+      if (-ahip * xi - bhip < lam) break;
+      ahip += p.ring.a(hip); bhip += p.ring.b(hip); --hip;
+    }
+  }
+  const double tmq = (-lam - bloq) / aloq, tpq = (lam + bhiq) / (-ahiq);
+  const double tmp_ = (-lam - blop) / alop, tpp = (lam + bhip) / (-ahip);
+  const int nlq = loq - 1, nrq = hiq + 1, nlp = lop - 1, nrp = hip + 1;
+  if (nrq - nlq + 1 > Ring::CAP || nrp - nlp + 1 > Ring::CAP) return false;
+  q.ring.set(nlq, tmq, aloq, bloq + lam);
+  q.ring.set(nrq, tpq, ahiq, bhiq + lam);
+  p.ring.set(nlp, tmp_, alop, blop + lam);
+  p.ring.set(nrp, tpp, ahip, bhip + lam);
+  q.l = nlq; q.r = nrq;
+  p.l = nlp; p.r = nrp;
   return true;
 }
 
@@ -196,7 +255,7 @@ ML_HD double dp_last(const Knots<Ring>& q, double y, double w, double lam) {
 
 template <class Ring>
 ML_HD bool knots_same(const Knots<Ring>& p, const Knots<Ring>& q) {
-  if (p.h != q.h || p.r - p.l != q.r - q.l) return false;
+  if (p.r - p.l != q.r - q.l) return false;
   const int cnt = p.r - p.l + 1;
   for (int k = 0; k < cnt; ++k) {
     if (f64_bits(p.ring.x(p.l + k)) != f64_bits(q.ring.x(q.l + k)) ||
@@ -223,115 +282,88 @@ template <class Ring>
 ML_HD bool knots_load(Knots<Ring>& q, const ChunkState& st) {
   const int cnt = st.count;
   if (cnt > Ring::CAP) return false;
-  uint64_t h = 0;
-  for (int k = 0; k < cnt; ++k) {
-    q.ring.set(k, st.x[k], st.a[k], st.b[k]);
-    h ^= knot_hash(st.x[k], st.a[k], st.b[k]);
-  }
+  for (int k = 0; k < cnt; ++k) q.ring.set(k, st.x[k], st.a[k], st.b[k]);
   q.l = 0;
   q.r = cnt - 1;
-  q.h = h;
   return true;
 }
 
-// ---- pass A: every chunk independently -----------------------------------------------------
-// y, w, tm, tp point at element 0 of the series.  `st` must have been initialised with
-// status = 0, resolved_from = ke before the first round.  Later rounds call this again with a
-// longer warm-up for chunks that are not CHUNK_DONE yet; only the still-missing head
-// [kb, resolved_from) of the chunk is then produced.
-// q and p are scratch windows provided by the caller (p is used by the warm-up only).
-// Returns false if a window outgrew Ring::CAP; `st` is then untouched and the caller may retry
-// with a larger ring.
+// ---- warm-up: pin the state at the start of a chunk ------------------------------------------
+// Runs the two sandwich copies over [kb - warm, kb) (or the exact DP from element 0 when the chunk
+// is that close to the head of its series).  If the two windows become bit-identical the window
+// is carried to kb and saved in `st` with CHUNK_START_VALID.  The loop has the same trip count
+// for every thread of a warp (divergence-free apart from the data-dependent knot pops).
+// y, w, tm, tp point at element 0 of the series.  Returns false on ring overflow (st untouched).
 template <class Ring>
-ML_HD bool flsa_pass_a(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
-                       const double* __restrict__ w, double* __restrict__ tm,
-                       double* __restrict__ tp, ChunkState& st, int warm, Knots<Ring>& q,
-                       Knots<Ring>& p) {
+ML_HD bool flsa_warm(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
+                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
+                     ChunkState& st, int warm, Knots<Ring>& q, Knots<Ring>& p) {
   const double lam = S.lam;
-  const int kb = c.kb, ke = c.ke;
-  const bool have_end = (st.status & CHUNK_END_VALID) != 0;
-  const int stop = have_end ? st.resolved_from : ke;  // tm/tp of [stop, ke) already written
+  const int kb = c.kb;
   double t1, t2;
-  double yn = 0.0, wn = 0.0;   // element k, loaded one step ahead of its use (k + 1 <= n - 1 always)
-  bool ok = true, irregular = false;
-  int k, resolved;
+  bool ok = true, dual, pristine;
+  int k;
   if (kb - warm <= 1) {
-    // close enough to the head of the series: run from element 0, exact by construction
+    // exact by construction: first element (gfl_tf.c:231-240), then steps 1 .. kb-1
     knots_init_first(q, y[0], w[0], lam, t1, t2);
-    if (kb == 1) {                                       // gfl_tf.c:231-232
+    if (kb == 1) {
       tm[0] = t1;
       tp[0] = t2;
-      irregular = t1 > t2;
+      if (t1 > t2) st.status |= CHUNK_IRREGULAR;
     }
-    for (k = 1; k < kb && ok; ++k) ok = dp_step(q, y[k], w[k], lam, t1, t2);
-    resolved = kb;
-    if (k < stop) { yn = y[k]; wn = w[k]; }
+    dual = false;
+    pristine = false;
+    k = 1;
   } else {
     knots_init_bound(q, -1, lam);
     knots_init_bound(p, +1, lam);
-    bool merged = false;
-    bool pristine = true;  // both windows still hold only their +-inf sentinel
+    dual = true;
+    pristine = true;   // both windows still hold only their +-inf sentinel
     k = kb - warm;
-    if (k < stop) { yn = y[k]; wn = w[k]; }
-    for (; k < stop && ok; ++k) {
-      const double yk = yn, wk = wn;
-      yn = y[k + 1];
-      wn = w[k + 1];
-      double u1, u2;
-      if (pristine) {
-        // A zero-weight element leaves a constant message unchanged (clip(+-lam + 0)); the generic
-        // step cannot express that on a sentinel-only window (0 * inf), so skip it exactly.
-        if (!(wk > 0)) continue;
-        pristine = false;
-      }
-      ok = dp_step(q, yk, wk, lam, t1, t2);
-      ok = dp_step(p, yk, wk, lam, u1, u2) && ok;
-      if (ok && knots_same(p, q)) { merged = true; ++k; break; }
-    }
-    if (!ok) return false;
-    if (!merged) return true;                  // nothing learnt this round
-    for (; k < kb && ok; ++k) {
-      const double yk = yn, wk = wn;
-      yn = y[k + 1];
-      wn = w[k + 1];
-      ok = dp_step(q, yk, wk, lam, t1, t2);
-    }
-    resolved = k;  // >= kb: first step whose back-pointers are exact
   }
-  for (; k < stop && ok; ++k) {
+  double yn = 0.0, wn = 0.0;   // element k, loaded one step ahead of its use (k + 1 <= n - 1 always)
+  if (k < kb) { yn = y[k]; wn = w[k]; }
+  for (; k < kb && ok; ++k) {
     const double yk = yn, wk = wn;
     yn = y[k + 1];
     wn = w[k + 1];
-    ok = dp_step(q, yk, wk, lam, t1, t2);
-    tm[k] = t1;
-    tp[k] = t2;
-    irregular |= (t1 > t2);
+    if (pristine) {
+      // A zero-weight element leaves a constant message unchanged (clip(+-lam + 0)); the generic
+      // step cannot express that on a sentinel-only window (0 * inf), so skip it exactly.
+      if (!(wk > 0)) continue;
+      pristine = false;
+    }
+    if (dual) {
+      ok = dp_step_dual(q, p, yk, wk, lam);
+      // the windows are compared knot by knot every 8th step (and at the last one): pinning is
+      // noticed at most 7 steps late, which costs nothing but those 7 duplicated steps
+      if (ok && ((k & 7) == 7 || k == kb - 1) && knots_same(p, q)) dual = false;
+    } else {
+      ok = dp_step(q, yk, wk, lam, t1, t2);
+    }
   }
   if (!ok) return false;
-  if (irregular) st.status |= CHUNK_IRREGULAR;
-  if (!have_end) { knots_save(q, st); st.status |= CHUNK_END_VALID; }
-  st.resolved_from = resolved;
-  if (resolved == kb) st.status |= CHUNK_DONE;
+  if (dual) return true;   // not pinned within this warm-up: a later round looks further back
+  knots_save(q, st);
+  st.status |= CHUNK_START_VALID;
   return true;
 }
 
-// ---- pass B / C: finish the unresolved head of a chunk from its left neighbour's end state ---
-// `left` must be CHUNK_END_VALID and stable (written by an earlier launch).  Returns false on
-// ring overflow (st untouched).
+// ---- main: the chunk's own steps from a pinned start state ------------------------------------
+// `start` is the chunk's own CHUNK_START_VALID window or its left neighbour's CHUNK_END_VALID
+// window (the same state by definition).  Writes tm/tp of [kb, ke), saves the end state.
+// Returns false on ring overflow (st untouched).
 template <class Ring>
-ML_HD bool flsa_finish_chunk(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
-                             const double* __restrict__ w, double* __restrict__ tm,
-                             double* __restrict__ tp, const ChunkState& left, ChunkState& st,
-                             Knots<Ring>& q) {
-  if (!knots_load(q, left)) return false;
+ML_HD bool flsa_main(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
+                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
+                     const ChunkState& start, ChunkState& st, Knots<Ring>& q) {
+  if (!knots_load(q, start)) return false;
   const double lam = S.lam;
-  const bool have_end = (st.status & CHUNK_END_VALID) != 0;
-  const int stop = have_end ? st.resolved_from : c.ke;
   double t1, t2;
   bool ok = true, irregular = false;
   double yn = 0.0, wn = 0.0;
-  if (c.kb < stop) { yn = y[c.kb]; wn = w[c.kb]; }
-  for (int k = c.kb; k < stop && ok; ++k) {
+  if (c.kb < c.ke) { yn = y[c.kb]; wn = w[c.kb]; }
+  for (int k = c.kb; k < c.ke && ok; ++k) {
     const double yk = yn, wk = wn;
     yn = y[k + 1];
     wn = w[k + 1];
@@ -342,12 +374,8 @@ ML_HD bool flsa_finish_chunk(const SeriesDesc& S, const ChunkDesc& c, const doub
   }
   if (!ok) return false;
   if (irregular) st.status |= CHUNK_IRREGULAR;
-  if (!have_end) {  // the whole chunk was unresolved: its end state is ours
-    knots_save(q, st);
-    st.status |= CHUNK_END_VALID;
-  }
-  st.resolved_from = c.kb;
-  st.status |= CHUNK_DONE;
+  knots_save(q, st);
+  st.status = (st.status & ~CHUNK_START_VALID) | CHUNK_END_VALID | CHUNK_DONE;
   return true;
 }
 

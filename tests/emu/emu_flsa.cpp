@@ -9,7 +9,7 @@ using namespace ml;
 
 extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int chunk, int warm,
                         double* beta, double* tm, double* tp, int tile, long long* stats) {
-  // stats: [0] chunks, [1] resolved in A, [2] finished in B, [3] finished in C, [4] overflow,
+  // stats: [0] chunks, [1] pinned by the first warm-up, [2] started from the left neighbour, [3] finished in C, [4] overflow,
   //        [5] max steps of B prefix, [6] chunks that outgrew the fast ring, [7] clamp order violations
   for (int i = 0; i < 8; ++i) stats[i] = 0;
   if (n == 0) return 0;
@@ -29,30 +29,41 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   stats[0] = (long long)cd.size();
   typedef LocalRing<KNOT_CAP_FAST> FastRing;   // same two-tier policy as the kernels
   typedef LocalRing<KNOT_CAP> BigRing;
-  for (size_t c = 0; c < cd.size(); ++c) {
-    st[c].status = 0; st[c].count = 0; st[c].resolved_from = cd[c].ke;
-    Knots<FastRing> q, p;
-    if (!flsa_pass_a(S, cd[c], y, w, tm, tp, st[c], warm, q, p)) {
-      stats[6]++;
-      Knots<BigRing> Q, P;
-      if (!flsa_pass_a(S, cd[c], y, w, tm, tp, st[c], warm, Q, P)) st[c].status |= CHUNK_OVERFLOW;
-    }
-    if (st[c].status & CHUNK_DONE) stats[1]++;
-    if (st[c].status & CHUNK_OVERFLOW) stats[4]++;
-  }
-  // pass B: only from neighbours whose end state pass A validated (snapshot of A's flags)
-  std::vector<int> a_status(cd.size());
-  for (size_t c = 0; c < cd.size(); ++c) a_status[c] = st[c].status;
-  for (size_t c = 1; c < cd.size(); ++c) {
-    if (a_status[c] & (CHUNK_DONE | CHUNK_OVERFLOW)) continue;
-    if (!(a_status[c - 1] & CHUNK_END_VALID)) continue;
-    stats[5] = std::max<long long>(stats[5], st[c].resolved_from - cd[c].kb);
-    { Knots<FastRing> q;
-      if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], q)) {
+  for (size_t c = 0; c < cd.size(); ++c) { st[c].status = 0; st[c].count = 0; st[c].pad = 0; }
+  auto run_main = [&](bool count_b) {
+    std::vector<int> snap(cd.size());
+    for (size_t c = 0; c < cd.size(); ++c) snap[c] = st[c].status;   // pad: statuses before this launch
+    for (size_t c = 0; c < cd.size(); ++c) {
+      if (snap[c] & (CHUNK_DONE | CHUNK_OVERFLOW)) continue;
+      const ChunkState* start = nullptr;
+      if (snap[c] & CHUNK_START_VALID) start = &st[c];
+      else if (cd[c].kb > 1 && (snap[c - 1] & CHUNK_END_VALID) && !(snap[c - 1] & CHUNK_OVERFLOW)) start = &st[c - 1];
+      if (!start) continue;
+      if (!(snap[c] & CHUNK_START_VALID)) stats[2]++;
+      Knots<FastRing> q;
+      if (!flsa_main(S, cd[c], y, w, tm, tp, *start, st[c], q)) {
+        stats[6]++;
         Knots<BigRing> Q;
-        if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW;
-      } }
-    stats[2]++;
+        if (!flsa_main(S, cd[c], y, w, tm, tp, *start, st[c], Q)) st[c].status |= CHUNK_OVERFLOW;
+      }
+    }
+  };
+  int wlen = warm;
+  for (int round = 0; round < 3; ++round) {
+    for (size_t c = 0; c < cd.size(); ++c) {
+      if (st[c].status & (CHUNK_DONE | CHUNK_OVERFLOW | CHUNK_START_VALID)) continue;
+      Knots<FastRing> q, p;
+      if (!flsa_warm(S, cd[c], y, w, tm, tp, st[c], wlen, q, p)) {
+        stats[6]++;
+        Knots<BigRing> Q, P;
+        if (!flsa_warm(S, cd[c], y, w, tm, tp, st[c], wlen, Q, P)) st[c].status |= CHUNK_OVERFLOW;
+      }
+      if (round == 0 && (st[c].status & CHUNK_START_VALID)) stats[1]++;
+    }
+    run_main(false);
+    if (S.mode == SERIES_SEQUENTIAL) break;
+    run_main(true);
+    wlen = wlen > (1 << 27) ? wlen : wlen * 8;
   }
   // pass C: chains, in order
   bool ovf = false;
@@ -61,7 +72,7 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
     if (st[c].status & CHUNK_DONE) continue;
     if (c == 0 || !(st[c - 1].status & CHUNK_END_VALID)) return -1;
     { Knots<BigRing> Q;
-      if (!flsa_finish_chunk(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW; }
+      if (!flsa_main(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW; }
     if (st[c].status & CHUNK_OVERFLOW) { ovf = true; break; }
     stats[3]++;
   }
