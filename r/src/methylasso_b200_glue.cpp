@@ -1,0 +1,163 @@
+// methylasso_b200_glue.cpp — drop-in replacement for the reference's Rcpp module
+// (/root/reference/src/MethyLasso_cpp.cpp:9-31): the same five exported functions with the same
+// argument names and defaults, forwarding to the C ABI of include/methylasso_b200.h, plus one batched
+// entry that takes all chromosomes at once.
+//
+// NOT COMPILED IN THIS REPOSITORY'S IMAGE (no R / Rcpp here).  Build inside the R package with
+//   PKG_CPPFLAGS = -I<repo>/include      PKG_LIBS = -L<repo>/methylasso_b200 -lmethylasso_b200
+// (see INTEGRATION.md).  Everything below is thin marshalling: Rcpp vectors -> int32 / double
+// pointers, error codes -> Rcpp::stop with the reference's messages.
+#include <Rcpp.h>
+#include <vector>
+
+#include "methylasso_b200.h"
+
+using namespace Rcpp;
+
+namespace {
+
+ml_engine* engine() {                       // one engine per R process, created on first use
+  static ml_engine* eng = nullptr;
+  if (!eng) {
+    if (ml_engine_create(-1, &eng) != ML_OK) stop(ml_last_error());
+  }
+  return eng;
+}
+
+void check(int rc) { if (rc != ML_OK) stop(ml_last_error()); }
+
+void need_columns(const DataFrame& data) {   // src/signal_detection.cpp:13-15
+  if (!(data.containsElementNamed("dataset") && data.containsElementNamed("condition") &&
+        data.containsElementNamed("replicate") && data.containsElementNamed("pos") &&
+        data.containsElementNamed("Nmeth") && data.containsElementNamed("coverage")))
+    stop("data should contain columns dataset, condition, replicate, pos, Nmeth and coverage!");
+}
+
+// one job (job_ptr = {0, n}) or many (job_ptr given): returns the reference's List per job
+List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml_params& p, bool diff_fast) {
+  need_columns(data);
+  IntegerVector dset = data["dataset"], cond = data["condition"], rep = data["replicate"], pos = data["pos"],
+                nmeth = data["Nmeth"], cov = data["coverage"];   // Rcpp coerces doubles to int
+  const int nj = (int)job_ptr.size() - 1;
+  ml_result* res = nullptr;
+  std::vector<int> status(nj);
+  check(ml_detect_batch(engine(), nj, job_ptr.data(), dset.begin(), cond.begin(), rep.begin(), pos.begin(),
+                        nmeth.begin(), cov.begin(), &p, &res, status.data()));
+  if (diff_fast) check(ml_result_fast_diff_combine(engine(), res));
+  List out(nj);
+  for (int j = 0; j < nj; ++j) {
+    int64_t n, P; int32_t E, D, st;
+    ml_result_job_sizes(res, j, &n, &P, &E, &D, &st);
+    if (st != ML_OK) {                       // R wrapper drops the chromosome (.errorhandling = "remove")
+      if (nj == 1) { ml_result_free(res); stop(ml_strerror(st)); }
+      out[j] = R_NilValue;
+      continue;
+    }
+    NumericVector mu(n), lambda2(E), offset(D), start(E * P), beta(E * P), betahat(E * P), pw(E * P);
+    IntegerVector id(E * P);
+    check(ml_result_copy_job(engine(), res, j, mu.begin(), lambda2.begin(), offset.begin(), id.begin(),
+                             start.begin(), beta.begin(), betahat.begin(), pw.begin()));
+    int32_t conv; double hyper;
+    ml_result_job_info(res, j, &conv, nullptr, nullptr, nullptr, &hyper, nullptr);
+    DataFrame est = DataFrame::create(_["estimate_id"] = id, _["start"] = start, _["beta"] = beta,
+                                      _["betahat"] = betahat, _["pseudoweight"] = pw);
+    out[j] = List::create(_["mu"] = mu, _["lambda2"] = lambda2, _["hyper"] = hyper,
+                          _["converged"] = (bool)conv, _["offset"] = offset, _["estimates"] = est);
+  }
+  ml_result_free(res);
+  return out;
+}
+
+ml_params fast_params(double lambda2, double tol_val, unsigned max_iter) {
+  ml_params p = {lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1u, 1u, ML_MODEL_FAST, 0, 0};
+  return p;
+}
+
+}  // namespace
+
+// src/signal_detection.cpp:11-47
+List signal_detection_fast_R(const DataFrame& data, double lambda2, double tol_val, unsigned max_iter) {
+  List r = detect(data, {0, (int64_t)data.nrows()}, fast_params(lambda2, tol_val, max_iter), false)[0];
+  return List::create(_["mu"] = r["mu"], _["lambda2"] = r["lambda2"], _["converged"] = r["converged"],
+                      _["offset"] = r["offset"], _["estimates"] = r["estimates"],
+                      _["detection.type"] = "signal", _["model"] = "normal");
+}
+
+// src/signal_detection.cpp:49-80
+List signal_detection_R(const DataFrame& data, bool optimize_lambda2, double lambda2, double max_lambda2,
+                        bool optimize_hyper, double hyper, unsigned nouter, double bf_per_kb, double tol_val,
+                        unsigned max_iter) {
+  ml_params p = {lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, 1u,
+                 ML_MODEL_FULL_SIGNAL, optimize_lambda2, optimize_hyper};
+  List r = detect(data, {0, (int64_t)data.nrows()}, p, false)[0];
+  return List::create(_["mu"] = r["mu"], _["lambda2"] = r["lambda2"], _["hyper"] = r["hyper"],
+                      _["converged"] = r["converged"], _["offset"] = r["offset"], _["estimates"] = r["estimates"],
+                      _["detection.type"] = "signal", _["model"] = "beta-binomial");
+}
+
+// src/difference_detection.cpp:13-45
+List difference_detection_R(const DataFrame& data, unsigned ref, bool optimize_lambda2, double lambda2,
+                            double max_lambda2, bool optimize_hyper, double hyper, unsigned nouter,
+                            double bf_per_kb, double tol_val, unsigned max_iter) {
+  ml_params p = {lambda2, max_lambda2, 0.0, tol_val, bf_per_kb, hyper, max_iter, nouter, ref,
+                 ML_MODEL_FULL_DIFFERENCE, optimize_lambda2, optimize_hyper};
+  List r = detect(data, {0, (int64_t)data.nrows()}, p, false)[0];
+  return List::create(_["mu"] = r["mu"], _["lambda2"] = r["lambda2"], _["hyper"] = r["hyper"],
+                      _["converged"] = r["converged"], _["offset"] = r["offset"], _["estimates"] = r["estimates"],
+                      _["ref.cond"] = ref, _["detection.type"] = "difference", _["model"] = "beta-binomial");
+}
+
+// src/methylation_helpers.cpp:6-72
+DataFrame segment_methylation_helper(const DataFrame& df, double tol_val = 0.01) {
+  IntegerVector idx = df["estimate_id"], start = df["start"];
+  NumericVector beta = df["beta"], betahat = df["betahat"], pw = df["pseudoweight"];
+  const int64_t n = idx.size();
+  std::vector<int32_t> sid(n), sno(n);
+  std::vector<uint32_t> smin(n), smax(n);
+  std::vector<double> sb(n), sbh(n), spw(n), ssd(n);
+  int64_t S = 0;
+  check(ml_segment_methylation_helper(engine(), n, idx.begin(), start.begin(), beta.begin(), betahat.begin(),
+                                      pw.begin(), tol_val, &S, sid.data(), sno.data(), smin.data(), smax.data(),
+                                      sb.data(), sbh.data(), spw.data(), ssd.data()));
+  return DataFrame::create(_["estimate_id"] = IntegerVector(sid.begin(), sid.begin() + S),
+                           _["segment_id"] = IntegerVector(sno.begin(), sno.begin() + S),
+                           _["start"] = NumericVector(smin.begin(), smin.begin() + S),
+                           _["end"] = NumericVector(smax.begin(), smax.begin() + S),
+                           _["beta"] = NumericVector(sb.begin(), sb.begin() + S),
+                           _["betahat"] = NumericVector(sbh.begin(), sbh.begin() + S),
+                           _["pseudoweight"] = NumericVector(spw.begin(), spw.begin() + S),
+                           _["stdev"] = NumericVector(ssd.begin(), ssd.begin() + S));
+}
+
+// src/weighted_1d_flsa.cpp:7-21
+NumericVector weighted_1d_flsa(const NumericVector& y, const NumericVector& wt, double lambda2, double lambda1 = 0) {
+  if (wt.size() != y.size()) stop("Input vectors must be of same size!");
+  NumericVector beta(y.size());
+  check(ml_weighted_1d_flsa(engine(), y.size(), y.begin(), wt.begin(), lambda2, lambda1, beta.begin()));
+  return beta;
+}
+
+// NEW: every chromosome of `data` in one native call.  job_ptr = row offsets of the chromosomes
+// (data sorted by chr, dataset, pos).  Returns a list with one element per chromosome (NULL for a
+// chromosome that failed, mirroring foreach's .errorhandling = "remove").
+List signal_detection_fast_batch(const DataFrame& data, const NumericVector& job_ptr, double lambda2,
+                                 double tol_val, unsigned max_iter, bool difference) {
+  std::vector<int64_t> ptr(job_ptr.begin(), job_ptr.end());
+  return detect(data, ptr, fast_params(lambda2, tol_val, max_iter), difference);
+}
+
+RCPP_MODULE(MethyLasso_cpp) {
+  function("signal_detection_singlechr", &signal_detection_R,
+           List::create(_["data"], _["optimize_lambda2"] = false, _["lambda2"] = 50, _["max_lambda2"] = 1000,
+                        _["optimize_hyper"] = false, _["hyper"] = 100, _["nouter"] = 20, _["bf_per_kb"] = 50,
+                        _["tol_val"] = 0.01, _["max_iter"] = 30));
+  function("signal_detection_fast_singlechr", &signal_detection_fast_R,
+           List::create(_["data"], _["lambda2"] = 50, _["tol_val"] = 0.01, _["max_iter"] = 1));
+  function("segment_methylation_helper", &segment_methylation_helper, List::create(_["data"], _["tol_val"] = 0.01));
+  function("difference_detection_singlechr", &difference_detection_R,
+           List::create(_["data"], _["ref"], _["optimize_lambda2"] = false, _["lambda2"] = 50,
+                        _["max_lambda2"] = 1000, _["optimize_hyper"] = false, _["hyper"] = 100, _["nouter"] = 20,
+                        _["bf_per_kb"] = 50, _["tol_val"] = 0.01, _["max_iter"] = 30));
+  function("weighted_1d_flsa", &weighted_1d_flsa, List::create(_["y"], _["wt"], _["lambda2"], _["lambda1"] = 0));
+  function("signal_detection_fast_batch", &signal_detection_fast_batch);
+}
