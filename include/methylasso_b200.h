@@ -126,6 +126,11 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
                                      const double *d_y, const double *d_wt, const double *lambda2,
                                      double lambda1, double *d_beta);
 
+/* debugging aid, not part of the drop-in surface: raw DP solution (no clamp) of one series and its
+ * back-pointers tm[k], tp[k] (k = 0..n-2) */
+ML_API int ml_debug_flsa_backpointers(ml_engine *eng, int64_t n, const double *y, const double *wt,
+                                      double lambda2, double *beta, double *tm, double *tp);
+
 /* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
  *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
 /* Copy the six columns to the GPU and keep them resident (validation and indexing run on the

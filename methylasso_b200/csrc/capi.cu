@@ -184,6 +184,31 @@ static void flsa_batch_device(Engine& e, int nseries, const int64_t* ptr, const 
   ML_CUDA(cudaStreamSynchronize(e.stream));
 }
 
+// debugging aid (not part of the drop-in surface): one series, also returns the DP back-pointers
+int ml_debug_flsa_backpointers(ml_engine* eng, int64_t n, const double* y, const double* wt, double lambda2,
+                               double* beta, double* tm, double* tp) {
+  if (!eng || n <= 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  cudaStream_t st = eng->e.stream;
+  DevBuf<double> d_y(st, (size_t)n), d_w(st, (size_t)n), d_b(st, (size_t)n);
+  d_y.upload(y, (size_t)n);
+  d_w.upload(wt, (size_t)n);
+  std::vector<FlsaSeries> series{FlsaSeries{0, (int32_t)n, lambda2}};
+  FlsaPlan plan(eng->e, series, n);
+  plan.solve(d_y.p, d_w.p, d_b.p, 0, 0.0, nullptr);
+  d_b.download(beta, (size_t)n);
+  plan.debug_backpointers(tm, tp);
+  if (getenv("ML_DEBUG_CHUNKS")) {
+    std::vector<ChunkState> cs;
+    plan.debug_chunk_states(cs);
+    for (size_t c = 0; c < cs.size(); ++c)
+      fprintf(stderr, "chunk %zu status %d count %d pad %d\n", c, cs[c].status, cs[c].count, cs[c].pad);
+  }
+  return ML_OK;
+  ML_CATCH
+}
+
 int ml_weighted_1d_flsa_batch_device(ml_engine* eng, int nseries, const int64_t* ptr, const double* d_y,
                                      const double* d_wt, const double* lambda2, double lambda1,
                                      double* d_beta) {

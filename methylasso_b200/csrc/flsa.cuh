@@ -38,6 +38,17 @@ class FlsaPlan {
   void solve(const double* d_y, const double* d_w, double* d_beta, int post, double lambda1,
              double* d_sums, const std::vector<int32_t>* skip_series = nullptr);
 
+  // debugging aid: copy the back-pointers of the last solve to the host (total_len doubles each)
+  void debug_backpointers(double* h_tm, double* h_tp) const {
+    d_tm_.download(h_tm, (size_t)total_len_);
+    d_tp_.download(h_tp, (size_t)total_len_);
+    ML_CUDA(cudaStreamSynchronize(eng_.stream));
+  }
+  void debug_chunk_states(std::vector<ChunkState>& out) const {
+    out.resize((size_t)n_chunks_);
+    d_states_.download(out.data(), (size_t)n_chunks_);
+    ML_CUDA(cudaStreamSynchronize(eng_.stream));
+  }
   int n_series() const { return (int)series_.size(); }
   int n_chunks() const { return n_chunks_; }
   int n_tiles() const { return n_tiles_; }

@@ -132,112 +132,53 @@ ML_HD void knots_init_bound(Knots<Ring>& q, int sign, double lam) {
   q.ring.set(0, x0, 0.0, 2 * lam);
 }
 
-// One DP step: fold element (y, w) into the message (gfl_tf.c:251-289).  Returns false when the
-// window would outgrow the ring (the ring is then left untouched).  tm/tp are the back-pointers.
-// The outermost knot of each side is examined on every step, so both are loaded up front (one
-// shared-memory latency instead of two); the arithmetic and its order are the reference's.
+// ---- one DP step, side-symmetric ------------------------------------------------------------
+// The reference scans the window from the left (gfl_tf.c:251-258) and from the right (:262-269)
+// with mirrored formulas.  Because IEEE rounding is sign-symmetric the right scan is the SAME
+// computation as the left one on negated accumulators:
+//     -ahi*x - bhi <  lam   <=>   ahi*x + bhi > -lam        (fl(-p - q) = -fl(p + q))
+//     (lam + bhi) / (-ahi)   ==   (-lam - bhi) / ahi         (bit for bit)
+// so both sides are:  seeds (a, b);  while knot in range and !(a*x + b > -lam): a += a_k, b += b_k;
+// new knot x = (-lam - b) / a, stored as (x, a, b + lam).  Sides differ only in their seeds
+// ((w, -w*y - lam) left, (-w, w*y - lam) right) and in the direction they walk.  That is what lets
+// two lanes of a warp take one side each without diverging (flsa.cu).
+//
+// The right scan of the reference is bounded by where the left scan stopped (hi >= lo).  Run
+// independently it is bounded by the window only; the results coincide unless it walked past
+// lo - 1 (the window was exhausted from both sides), in which case it is redone with the bound.
 template <class Ring>
-ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, double& tp) {
-  double alo = w, blo = -w * y - lam;      // :286-287 (seeds of the incoming element)
-  double ahi = -w, bhi = w * y - lam;      // :288-289
-  int lo = q.l, hi = q.r;                  // the window always holds at least one knot
-  const double xl = q.ring.x(lo), al = q.ring.a(lo), bl0 = q.ring.b(lo);
-  const double xr = q.ring.x(hi), ar = q.ring.a(hi), br0 = q.ring.b(hi);
-  if (!(alo * xl + blo > -lam)) {          // :253-258, first iteration peeled (lo <= r holds)
-    alo += al;
-    blo += bl0;
-    ++lo;
-    while (lo <= hi) {
-      const double xi = q.ring.x(lo);
-      if (alo * xi + blo > -lam) break;
-      const double ai = q.ring.a(lo), bi = q.ring.b(lo);
-      alo += ai;
-      blo += bi;
-      ++lo;
-    }
+ML_HD int side_scan(const Ring& ring, int idx, int dir, int last, double& a, double& b, double lam) {
+  while ((last - idx) * dir >= 0) {            // idx still inside [.., last] in walking direction
+    const double x = ring.x(idx);
+    if (a * x + b > -lam) break;
+    a += ring.a(idx);
+    b += ring.b(idx);
+    idx += dir;
   }
-  if (hi >= lo && !(-ahi * xr - bhi < lam)) {   // :264-269, first iteration peeled
-    ahi += ar;
-    bhi += br0;
-    --hi;
-    while (hi >= lo) {
-      const double xi = q.ring.x(hi);
-      if (-ahi * xi - bhi < lam) break;
-      const double ai = q.ring.a(hi), bi = q.ring.b(hi);
-      ahi += ai;
-      bhi += bi;
-      --hi;
-    }
-  }
-  tm = (-lam - blo) / alo;                 // :272
-  tp = (lam + bhi) / (-ahi);               // :277
-  const int nl = lo - 1, nr = hi + 1;
-  if (nr - nl + 1 > Ring::CAP) return false;
-  const double bl = blo + lam, br = bhi + lam;   // :283, :285
-  q.ring.set(nl, tm, alo, bl);
-  q.ring.set(nr, tp, ahi, br);
-  q.l = nl;
-  q.r = nr;
-  return true;
+  return idx;
 }
 
-// The same step applied to the two sandwich copies at once.  Written as one function so that the
-// two independent dependency chains (loads, compares, divisions) interleave in the instruction
-// stream: a lone thread is latency-bound, and the warm-up is where most DP steps are spent.
+// One DP step: fold element (y, w) into the message (gfl_tf.c:251-289).  Returns false when the
+// window would outgrow the ring (the ring is then left untouched).  tm/tp are the back-pointers.
 template <class Ring>
-ML_HD bool dp_step_dual(Knots<Ring>& q, Knots<Ring>& p, double y, double w, double lam) {
-  const double b_lo0 = -w * y - lam, b_hi0 = w * y - lam;
-  double aloq = w, bloq = b_lo0, ahiq = -w, bhiq = b_hi0;
-  double alop = w, blop = b_lo0, ahip = -w, bhip = b_hi0;
-  int loq = q.l, hiq = q.r, lop = p.l, hip = p.r;
-  const double xlq = q.ring.x(loq), alq = q.ring.a(loq), blq = q.ring.b(loq);
-  const double xlp = p.ring.x(lop), alp = p.ring.a(lop), blp = p.ring.b(lop);
-  const double xrq = q.ring.x(hiq), arq = q.ring.a(hiq), brq = q.ring.b(hiq);
-  const double xrp = p.ring.x(hip), arp = p.ring.a(hip), brp = p.ring.b(hip);
-  const bool popq = !(aloq * xlq + bloq > -lam);
-  const bool popp = !(alop * xlp + blop > -lam);
-  if (popq) {
-    aloq += alq; bloq += blq; ++loq;
-    while (loq <= hiq) {
-      const double xi = q.ring.x(loq);
-      if (aloq * xi + bloq > -lam) break;
-      aloq += q.ring.a(loq); bloq += q.ring.b(loq); ++loq;
-    }
+ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, double& tp) {
+  double al = w, bl = -w * y - lam;        // :286-287 (seeds of the incoming element)
+  double ar = -w, br = w * y - lam;        // :288-289
+  const int lo = side_scan(q.ring, q.l, +1, q.r, al, bl, lam);
+  int hi = side_scan(q.ring, q.r, -1, q.l, ar, br, lam);
+  if (hi < lo - 1) {                       // both scans crossed: redo the right one with :264's bound
+    ar = -w;
+    br = w * y - lam;
+    hi = side_scan(q.ring, q.r, -1, lo, ar, br, lam);
   }
-  if (popp) {
-    alop += alp; blop += blp; ++lop;
-    while (lop <= hip) {
-      const double xi = p.ring.x(lop);
-      if (alop * xi + blop > -lam) break;
-      alop += p.ring.a(lop); blop += p.ring.b(lop); ++lop;
-    }
-  }
-  if (hiq >= loq && !(-ahiq * xrq - bhiq < lam)) {
-    ahiq += arq; bhiq += brq; --hiq;
-    while (hiq >= loq) {
-      const double xi = q.ring.x(hiq);
-      if (-ahiq * xi - bhiq < lam) break;
-      ahiq += q.ring.a(hiq); bhiq += q.ring.b(hiq); --hiq;
-    }
-  }
-  if (hip >= lop && !(-ahip * xrp - bhip < lam)) {
-    ahip += arp; bhip += brp; --hip;
-    while (hip >= lop) {
-      const double xi = p.ring.x(hip);
-      if (-ahip * xi - bhip < lam) break;
-      ahip += p.ring.a(hip); bhip += p.ring.b(hip); --hip;
-    }
-  }
-  const double tmq = (-lam - bloq) / aloq, tpq = (lam + bhiq) / (-ahiq);
-  const double tmp_ = (-lam - blop) / alop, tpp = (lam + bhip) / (-ahip);
-  const int nlq = loq - 1, nrq = hiq + 1, nlp = lop - 1, nrp = hip + 1;
-  if (nrq - nlq + 1 > Ring::CAP || nrp - nlp + 1 > Ring::CAP) return false;
-  q.ring.set(nlq, tmq, aloq, bloq + lam);
-  q.ring.set(nrq, tpq, ahiq, bhiq + lam);
-  p.ring.set(nlp, tmp_, alop, blop + lam);
-  p.ring.set(nrp, tpp, ahip, bhip + lam);
-  q.l = nlq; q.r = nrq;
-  p.l = nlp; p.r = nrp;
+  tm = (-lam - bl) / al;                   // :272
+  tp = (-lam - br) / ar;                   // :277, (lam + bhi) / (-ahi) bit for bit
+  const int nl = lo - 1, nr = hi + 1;
+  if (nr - nl + 1 > Ring::CAP) return false;
+  q.ring.set(nl, tm, al, bl + lam);        // :282-285
+  q.ring.set(nr, tp, ar, br + lam);
+  q.l = nl;
+  q.r = nr;
   return true;
 }
 
@@ -334,7 +275,8 @@ ML_HD bool flsa_warm(const SeriesDesc& S, const ChunkDesc& c, const double* __re
       pristine = false;
     }
     if (dual) {
-      ok = dp_step_dual(q, p, yk, wk, lam);
+      ok = dp_step(q, yk, wk, lam, t1, t2);
+      ok = dp_step(p, yk, wk, lam, t1, t2) && ok;
       // the windows are compared knot by knot every 8th step (and at the last one): pinning is
       // noticed at most 7 steps late, which costs nothing but those 7 duplicated steps
       if (ok && ((k & 7) == 7 || k == kb - 1) && knots_same(p, q)) dual = false;

@@ -83,6 +83,20 @@ def test_chunked_dp_generic_inputs_within_rounding(emu, oracle):
     assert worst < 1e-11, worst
 
 
+def test_side_symmetric_step_is_bit_exact_on_any_input(emu, oracle):
+    """One chunk = the whole series: the side-symmetric step (both scans as `a*x + b > -lam`, knot
+    (-lam - b)/a, crossing redo) must reproduce the reference's mirrored formulas bit for bit."""
+    rng = np.random.default_rng(11)
+    for trial in range(300):
+        n = int(rng.integers(2, 400))
+        y = rng.normal(size=n) * float(rng.choice([1e-3, 1.0, 1e3]))
+        w = np.where(rng.random(n) < 0.25, 0.0, rng.exponential(size=n))
+        lam = float(rng.choice([1e-6, 1e-2, 0.7, 30.0, 1e4]))
+        ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+        beta, st = emu(y, w, lam, 1 << 30, 1)
+        assert np.array_equal(beta, ref, equal_nan=True), (trial, n, lam)
+
+
 def test_chunked_dp_edge_sizes(emu, oracle):
     rng = np.random.default_rng(3)
     for n in (1, 2, 3, 4, 5, 6):
