@@ -350,7 +350,7 @@ __device__ __forceinline__ void bin_residuals(const JobDev& J, const RowCols& rc
   }
 }
 
-__global__ void __launch_bounds__(PAR_TILE)
+__global__ void __launch_bounds__(PAR_TILE, 4)
 k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
              const int32_t* __restrict__ ctl, RowCols rc, const int32_t* __restrict__ dptr,
              const double* __restrict__ design, const int32_t* __restrict__ rowstart,
@@ -364,8 +364,26 @@ k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
   const int first = (c & CTL_FIRST) ? 1 : 0;
   const int k = t.k0 + threadIdx.x;
   const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
+  constexpr int DC = 4;                // datasets whose binned residuals are kept in registers
+  double Wd[DC], Zd[DC], Cd[DC];
   double wt = 0.0;
-  for (int d = 0; d < J.D; ++d) {
+  // the first-row lookups of all datasets are independent: issue them together
+  int r0s[DC];
+#pragma unroll
+  for (int d = 0; d < DC; ++d) {
+    Cd[d] = d < J.D ? design[J.des0 + d * J.E + t.e] : 0.0;
+    r0s[d] = (d < J.D && Cd[d] != 0) ? rowstart[J.tab0 + (int64_t)d * J.P + k] : -1;
+  }
+#pragma unroll
+  for (int d = 0; d < DC; ++d) {
+    Wd[d] = 0.0;
+    Zd[d] = 0.0;
+    if (r0s[d] >= 0) {
+      bin_residuals(J, rc, first, r0s[d], dptr[J.dptr0 + d + 1], k, Wd[d], Zd[d]);
+      wt += (Cd[d] * Wd[d]) * Cd[d];
+    }
+  }
+  for (int d = DC; d < J.D; ++d) {     // more than DC datasets: no caching
     const double cf = design[J.des0 + d * J.E + t.e];
     if (cf == 0) continue;
     const int r0 = rowstart[J.tab0 + (int64_t)d * J.P + k];
@@ -377,7 +395,15 @@ k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
   double inv = 1 / wt;
   if (!is_finite(inv)) inv = 0.0;     // pseudo-inverse (pseudodata_helpers.hpp:33-34)
   double bh = 0.0;
-  for (int d = 0; d < J.D; ++d) {
+#pragma unroll
+  for (int d = 0; d < DC; ++d) {
+    if (r0s[d] >= 0) {
+      const double q = Zd[d] / Wd[d];
+      const double zhat = (Wd[d] == 0) ? Wd[d] : q;
+      bh += (inv * Cd[d]) * (Wd[d] * zhat);
+    }
+  }
+  for (int d = DC; d < J.D; ++d) {
     const double cf = design[J.des0 + d * J.E + t.e];
     if (cf == 0) continue;
     const int r0 = rowstart[J.tab0 + (int64_t)d * J.P + k];
@@ -501,41 +527,70 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
             const double* __restrict__ beta, const double* __restrict__ off, double log2pi,
             double* __restrict__ mu, const double* __restrict__ mu_outer, int want_outer,
             double* __restrict__ part /*3 per tile: lik, dres, douter*/) {
-  __shared__ double sm[8];
+  __shared__ double sm[3][8];
   const RowTile t = tiles[blockIdx.x];
-  if (!(ctl[t.job] & CTL_EVAL)) return;
+  const int c = ctl[t.job];
+  if (!(c & CTL_EVAL)) return;
   const JobDev J = jobs[t.job];
   const double o = off[J.off0 + t.d];
-  double lik = 0.0, dres = 0.0, dout = 0.0;
+  const bool write_mu = !(c & CTL_NO_MU);      // the initial evaluation's mu is never read
+  const bool need_dres = (c & CTL_DRES) != 0;  // max|mu - mu_res| is only consulted from the 2nd step on
+  constexpr int V = ROW_TILE / 256;
+  const int64_t g0 = J.row0 + t.r0;
+  int cv[V], nm[V], kx[V];
 #pragma unroll
-  for (int q = 0; q < ROW_TILE / 256; ++q) {
+  for (int q = 0; q < V; ++q) {                // independent loads first
     const int i = threadIdx.x + q * 256;
-    if (i < t.cnt) {
-      const int64_t g = J.row0 + t.r0 + i;
-      const int k = rc.pidx[g];
-      double eta = 0.0;
-      for (int e = 0; e < J.E; ++e) {
-        const double cf = design[J.des0 + t.d * J.E + e];
-        const double phi = (cf != 0) ? (0. + cf * beta[J.par0 + (int64_t)e * J.P + k]) : 0.;
-        eta += phi;
-      }
-      eta = eta + (0. + 1. * o);
-      const double m = irls_mu(J.model, eta);
-      const double nobs = (double)rc.cov[g];
-      const double y = (double)rc.nmeth[g] / nobs;
-      lik += irls_minus_log_pdf(J.model, y, nobs, m, J.nu, log2pi);
-      dres = fmax(dres, fabs(m - rc.mu_res[g]));
-      if (want_outer) dout = fmax(dout, fabs(m - mu_outer[g]));
-      mu[g] = m;
+    const bool in = i < t.cnt;
+    cv[q] = in ? rc.cov[g0 + i] : 1;
+    nm[q] = in ? rc.nmeth[g0 + i] : 0;
+    kx[q] = in ? rc.pidx[g0 + i] : 0;
+  }
+  double eta[V];
+#pragma unroll
+  for (int q = 0; q < V; ++q) eta[q] = 0.0;
+  for (int e = 0; e < J.E; ++e) {
+    const double cf = design[J.des0 + t.d * J.E + e];
+    if (cf != 0) {
+      const double* be = beta + J.par0 + (int64_t)e * J.P;
+#pragma unroll
+      for (int q = 0; q < V; ++q) eta[q] += (0. + cf * be[kx[q]]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < V; ++q) eta[q] += 0.;
     }
   }
-  const double a = block_sum_ordered(lik, sm);
-  const double b = block_max(dres, sm);
-  const double c = block_max(dout, sm);
+  double lik = 0.0, dres = 0.0, dout = 0.0;
+#pragma unroll
+  for (int q = 0; q < V; ++q) {
+    const int i = threadIdx.x + q * 256;
+    if (i < t.cnt) {
+      const int64_t g = g0 + i;
+      const double m = irls_mu(J.model, eta[q] + (0. + 1. * o));
+      const double nobs = (double)cv[q];
+      const double y = (double)nm[q] / nobs;
+      lik += irls_minus_log_pdf(J.model, y, nobs, m, J.nu, log2pi);
+      if (need_dres) dres = fmax(dres, fabs(m - rc.mu_res[g]));
+      if (want_outer) dout = fmax(dout, fabs(m - mu_outer[g]));
+      if (write_mu) mu[g] = m;
+    }
+  }
+  // one pass for the three reductions: lanes by shuffle, warps in order (fixed association)
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    lik += __shfl_down_sync(0xffffffffu, lik, d);
+    dres = fmax(dres, __shfl_down_sync(0xffffffffu, dres, d));
+    dout = fmax(dout, __shfl_down_sync(0xffffffffu, dout, d));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][wid] = lik; sm[1][wid] = dres; sm[2][wid] = dout; }
+  __syncthreads();
   if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0, cc = 0.0;
+    for (int k = 0; k < 8; ++k) { a += sm[0][k]; b = fmax(b, sm[1][k]); cc = fmax(cc, sm[2][k]); }
     part[3 * blockIdx.x] = a;
     part[3 * blockIdx.x + 1] = b;
-    part[3 * blockIdx.x + 2] = c;
+    part[3 * blockIdx.x + 2] = cc;
   }
 }
 
@@ -1019,7 +1074,8 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       const St& s = S[j];
       if (s.state == S_UPDATE) { c |= CTL_UPDATE | CTL_EVAL; any_update = true; }
       if (s.state == S_DAMP) { c |= CTL_DAMP | CTL_EVAL; any_damp = true; }
-      if (s.state == S_INIT_EVAL) c |= CTL_EVAL;
+      if (s.state == S_INIT_EVAL) c |= CTL_EVAL | CTL_NO_MU;
+      if (s.state != S_INIT_EVAL && s.it > 0) c |= CTL_DRES;
       if (s.first) c |= CTL_FIRST;
       if (c & CTL_EVAL) any_eval = true;
       ctl[j] = (s.state == S_DONE) ? 0 : c;
