@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -275,11 +277,16 @@ def main():
     sampler.start()
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     ev0.record(stream)
     for _ in range(args.steps):
         r, nseg, npmd = step_resident()
         r.free()
     ev1.record(stream)
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     clocks = sampler.stop()
     launches = eng.launch_count - l0
@@ -303,16 +310,28 @@ def main():
         est_id = torch.empty(EP, dtype=torch.int32).pin_memory().numpy()
         off = np.empty(3 * len(tables))
 
+        e2e_parts = {"upload+detect": 0.0, "copy_all": 0.0, "segments": 0.0, "pmd_segments": 0.0, "free": 0.0}
+
         def step_e2e():
+            t0 = time.perf_counter()
             rr = eng.detect_batch(ptr, pcols, params)
+            t1 = time.perf_counter()
             rr.copy_all(mu, off, est_id, est["start"], est["beta"], est["betahat"], est["pseudoweight"])
+            t2 = time.perf_counter()
             seg = rr.segments(TOL)
+            t3 = time.perf_counter()
             pmd = rr.pmd_segments(TOL, PMD_LAMBDA2)
+            t4 = time.perf_counter()
             rr.free()
+            t5 = time.perf_counter()
+            for k, v in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                e2e_parts[k] += v * 1e3
             return seg, pmd
         for _ in range(max(1, args.warmup - 1)):
             seg, pmd = step_e2e()
         barrier()
+        for k in e2e_parts:
+            e2e_parts[k] = 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(args.steps):
@@ -326,7 +345,8 @@ def main():
         seg_bytes = sum(v.nbytes for v in seg.values()) + sum(v.nbytes for v in pmd.values())
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "h2d_bytes_per_step": 24 * N,
-               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes)}
+               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes),
+               "host_ms_per_step": {k: v / args.steps for k, v in e2e_parts.items()}}
 
     # ---- K16: all-gather of per-shard segment summaries over NCCL ---------------------------------
     gathered = None
@@ -375,6 +395,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16],
+            "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
         }
         print(json.dumps(line), flush=True)
