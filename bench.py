@@ -208,6 +208,8 @@ def main():
     ap.add_argument("--cpgs", type=int, default=synth.GENOME_CPGS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-groups", type=int, default=1,
+                    help="engines (streams + host threads) the e2e step spreads the chromosomes over; 1 = single call")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
@@ -305,48 +307,77 @@ def main():
     # ---- e2e: host buffers through the C ABI -------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        mu = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
-        est = {k: torch.empty(EP, dtype=torch.float64).pin_memory().numpy() for k in ("start", "beta", "betahat", "pseudoweight")}
-        est_id = torch.empty(EP, dtype=torch.int32).pin_memory().numpy()
-        off = np.empty(3 * len(tables))
+        # The user-level call: chromosomes split into groups, one engine (stream) + host thread per group,
+        # so H2D of one group, kernels of another and D2H of a third overlap.  Inputs and outputs are
+        # pinned host buffers; sizes are known from the untimed call above.
+        G = max(1, args.e2e_groups)
+        pool = api.EnginePool(G, local)
+        groups = []
+        for jobs, gptr, gcols in api.split_jobs(ptr, cols, G):
+            pin_in = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in gcols.items()}
+            n_g = int(gptr[-1])
+            ep_g = int(sum(sizes[j][1] * sizes[j][2] for j in jobs))
+            outb = dict(mu=torch.empty(n_g, dtype=torch.float64).pin_memory().numpy(),
+                        off=np.empty(3 * len(jobs)),
+                        est_id=torch.empty(ep_g, dtype=torch.int32).pin_memory().numpy(),
+                        **{k: torch.empty(ep_g, dtype=torch.float64).pin_memory().numpy()
+                           for k in ("start", "beta", "betahat", "pseudoweight")})
+            groups.append((jobs, gptr, pin_in, outb))
 
-        e2e_parts = {"upload+detect": 0.0, "copy_all": 0.0, "segments": 0.0, "pmd_segments": 0.0, "free": 0.0}
+        def run_group(eng_g, grp):
+            jobs, gptr, pin_in, o = grp
+            ts = [time.perf_counter()]
+            with pool.h2d_turn:
+                ts.append(time.perf_counter())
+                bt = eng_g.upload(gptr, pin_in)
+            ts.append(time.perf_counter())
+            rr = eng_g.detect(bt, params)
+            bt.free()
+            ts.append(time.perf_counter())
+            # D2H of mu / estimates is enqueued on the copy stream and overlaps the segmentation kernels
+            rr.copy_all_async(o["mu"], o["off"], o["est_id"], o["start"], o["beta"], o["betahat"], o["pseudoweight"])
+            ts.append(time.perf_counter())
+            rr.segments_count(TOL)                      # resident; the tables are fetched after the big copies
+            rr.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+            ts.append(time.perf_counter())
+            eng_g.synchronize()
+            seg = rr.segments(TOL)
+            pmd = rr.pmd_segments(TOL, PMD_LAMBDA2)
+            rr.free()
+            ts.append(time.perf_counter())
+            timeline.append((len(jobs), [round((x - t_step0[0]) * 1e3, 1) for x in ts]))
+            return seg, pmd
+
+        timeline, t_step0 = [], [0.0]
 
         def step_e2e():
-            t0 = time.perf_counter()
-            rr = eng.detect_batch(ptr, pcols, params)
-            t1 = time.perf_counter()
-            rr.copy_all(mu, off, est_id, est["start"], est["beta"], est["betahat"], est["pseudoweight"])
-            t2 = time.perf_counter()
-            seg = rr.segments(TOL)
-            t3 = time.perf_counter()
-            pmd = rr.pmd_segments(TOL, PMD_LAMBDA2)
-            t4 = time.perf_counter()
-            rr.free()
-            t5 = time.perf_counter()
-            for k, v in zip(e2e_parts, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
-                e2e_parts[k] += v * 1e3
-            return seg, pmd
+            timeline.clear()
+            t_step0[0] = time.perf_counter()
+            return pool.map(run_group, groups)
         for _ in range(max(1, args.warmup - 1)):
-            seg, pmd = step_e2e()
+            outs = step_e2e()
         barrier()
-        for k in e2e_parts:
-            e2e_parts[k] = 0.0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(args.steps):
-            seg, pmd = step_e2e()
+            outs = step_e2e()
+        torch.cuda.synchronize()
         e1.record(stream)
         barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         ems = e0.elapsed_time(e1) / args.steps
         t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        seg_bytes = sum(v.nbytes for v in seg.values()) + sum(v.nbytes for v in pmd.values())
+        seg_bytes = sum(v.nbytes for sg, pm in outs for v in list(sg.values()) + list(pm.values()))
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
-               "ms_per_step": float(t2.item()), "h2d_bytes_per_step": 24 * N,
-               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes),
-               "host_ms_per_step": {k: v / args.steps for k, v in e2e_parts.items()}}
+               "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
+               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
+               "timeline_ms_last_step": sorted(timeline, key=lambda t: t[1][0]),  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
+               "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "
+                      "ml_result_segments + ml_result_pmd_segments per group, transfers taking turns per direction"}
+        pool.close()
 
     # ---- K16: all-gather of per-shard segment summaries over NCCL ---------------------------------
     gathered = None

@@ -166,6 +166,13 @@ ML_API int ml_result_copy_job(ml_engine *eng, const ml_result *r, int job, doubl
 ML_API int ml_result_copy_all(ml_engine *eng, const ml_result *r, double *mu, double *offset,
                        int32_t *estimate_id, double *start, double *beta, double *betahat,
                        double *pseudoweight);
+/* Same, but the copies are only ENQUEUED (on the engine's copy stream): the buffers must be pinned
+ * host memory and must not be read before ml_engine_synchronize(eng) returns.  Later calls on the
+ * same engine (ml_result_segments, ...) overlap with the transfer.  The result must stay alive until
+ * the synchronisation. */
+ML_API int ml_result_copy_all_async(ml_engine *eng, const ml_result *r, double *mu, double *offset,
+                                    int32_t *estimate_id, double *start, double *beta, double *betahat,
+                                    double *pseudoweight);
 ML_API void ml_result_free(ml_result *r);
 
 /* R/fast_diff.R:15-28 applied in place to a FAST result with >= 2 estimators: estimates of

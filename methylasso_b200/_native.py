@@ -57,6 +57,7 @@ SIGNATURES = {
                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ml_result_copy_job": (C.c_int, [_P, _P, C.c_int] + [_P] * 8),
     "ml_result_copy_all": (C.c_int, [_P, _P] + [_P] * 7),
+    "ml_result_copy_all_async": (C.c_int, [_P, _P] + [_P] * 7),
     "ml_result_free": (None, [_P]),
     "ml_result_fast_diff_combine": (C.c_int, [_P, _P]),
     "ml_segment_methylation_helper": (C.c_int, [_P, C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 8),

@@ -266,6 +266,13 @@ class Result:
         self.eng._check(self.eng.lib.ml_result_copy_all(self.eng.h, self.h, _p(mu), _p(offset), _p(estimate_id),
                                                         _p(start), _p(beta), _p(betahat), _p(pseudoweight)))
 
+    def copy_all_async(self, mu=None, offset=None, estimate_id=None, start=None, beta=None, betahat=None,
+                       pseudoweight=None):
+        """copy_all that only enqueues the transfers (pinned buffers!); engine.synchronize() completes them."""
+        self.eng._check(self.eng.lib.ml_result_copy_all_async(self.eng.h, self.h, _p(mu), _p(offset),
+                                                              _p(estimate_id), _p(start), _p(beta), _p(betahat),
+                                                              _p(pseudoweight)))
+
     def pmd_segments(self, tol_val=0.01, pmd_lambda2=1000.0, fetch=True):
         """R/call.R:93-95 on the resident segments (see ml_result_pmd_segments)."""
         ns = C.c_int64(0)
@@ -282,6 +289,71 @@ class Result:
             *[_p(out[k]) for k in ("job", "estimate_id", "segment_id", "start", "end", "fused_std", "std",
                                    "pseudoweight")]))
         return {k: v[:ns.value].copy() for k, v in out.items()}
+
+
+class EnginePool:
+    """Several engines (= CUDA streams) on ONE GPU, each driven by its own host thread.
+
+    The C ABI calls are synchronous, so one engine alternates between PCIe transfers and kernels.
+    Splitting the chromosomes of a call into groups and running the groups on different engines lets
+    the H2D copy of one group, the kernels of another and the D2H copy of a third overlap (PCIe is
+    full duplex and the copy engines are independent of the SMs).  ctypes releases the GIL during the
+    native calls, so plain Python threads are enough.  Jobs never interact, so results do not depend
+    on the grouping (see tests/test_gpu_detect.py::test_placement_independence)."""
+
+    def __init__(self, n_engines=3, device=-1):
+        import threading
+        self.engines = [Engine(device) for _ in range(n_engines)]
+        # One transfer at a time per direction: if every group queued its H2D copies at once the copy
+        # engine would interleave them and all groups would finish uploading together (no overlap
+        # with compute); taking turns lets group 1 compute while group 2 uploads.
+        self.h2d_turn = threading.Lock()
+        self.d2h_turn = threading.Lock()
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def map(self, fn, items):
+        """Run fn(engine, item) for every item, items[i] on engine i % n, one thread per engine."""
+        import threading
+        n = len(self.engines)
+        out = [None] * len(items)
+        err = []
+
+        def work(k):
+            try:
+                for i in range(k, len(items), n):
+                    out[i] = fn(self.engines[k], items[i])
+            except Exception as e:  # surfaced to the caller below
+                err.append(e)
+        ths = [threading.Thread(target=work, args=(k,)) for k in range(min(n, len(items)))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        if err:
+            raise err[0]
+        return out
+
+
+def split_jobs(job_ptr, cols, n_groups):
+    """Split a batch into n_groups contiguous-in-memory sub-batches, balanced longest-first by rows.
+    Returns [(job_indices, sub_ptr, sub_cols)], with sub_cols freshly concatenated arrays."""
+    from .shard import lpt_assign
+    job_ptr = np.asarray(job_ptr, dtype=np.int64)
+    sizes = np.diff(job_ptr)
+    group_of = lpt_assign(sizes, n_groups)
+    out = []
+    for g in range(n_groups):
+        jobs = [int(j) for j in np.nonzero(group_of == g)[0]]
+        if not jobs:
+            continue
+        ptr = np.zeros(len(jobs) + 1, np.int64)
+        ptr[1:] = np.cumsum(sizes[jobs])
+        sub = {k: np.concatenate([np.asarray(cols[k])[job_ptr[j]:job_ptr[j + 1]] for j in jobs]) for k in _COLUMNS}
+        out.append((jobs, ptr, sub))
+    return out
 
 
 # ---------------------------------------------------------------------------------------------

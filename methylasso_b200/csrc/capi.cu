@@ -1,6 +1,7 @@
 // capi.cu — the C ABI of include/methylasso_b200.h: argument checking, error translation and the
 // host<->device copies at the boundary.  All compute is in flsa.cu / detect.cu / segment.cu.
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <iterator>
 #include <memory>
@@ -17,6 +18,37 @@ struct ml_batch { std::unique_ptr<Batch> b; };
 struct ml_result { std::unique_ptr<Result> r; };
 
 static thread_local std::string g_err;
+
+namespace ml {
+
+__global__ void k_mailbox_copy(char* __restrict__ dst, const char* __restrict__ src, size_t bytes) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+bool mailbox_fetch(cudaStream_t st, void* host_dst, const void* dev_src, size_t bytes) {
+  Mailbox* m = tls_mailbox();
+  if (!m || !m->host) return false;
+  const size_t off = (m->used + 15) & ~(size_t)15;
+  if (off + bytes > m->cap) return false;
+  k_mailbox_copy<<<(unsigned)std::min<size_t>(32, (bytes + 255) / 256), 256, 0, st>>>(m->dev + off, (const char*)dev_src, bytes);
+  ML_CHECK_LAUNCH();
+  m->pending.push_back(Mailbox::Pending{host_dst, off, bytes});
+  m->used = off + bytes;
+  return true;
+}
+
+void stream_sync(cudaStream_t st) {
+  ML_CUDA(cudaStreamSynchronize(st));
+  Mailbox* m = tls_mailbox();
+  if (m && !m->pending.empty()) {
+    for (const Mailbox::Pending& p : m->pending) memcpy(p.dst, m->host + p.off, p.bytes);
+    m->pending.clear();
+    m->used = 0;
+  }
+}
+
+}  // namespace ml
 
 static int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -87,11 +119,19 @@ int ml_engine_create(int device, ml_engine** out) {
                                         std::to_string(prop.major) + std::to_string(prop.minor));
   h->e.sm_count = prop.multiProcessorCount;
   ML_CUDA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
-  // keep freed blocks in the pool: steady-state calls never reach the driver allocator
-  cudaMemPool_t pool;
-  ML_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  ML_CUDA(cudaStreamCreateWithFlags(&h->e.copy_stream, cudaStreamNonBlocking));
+  // the engine's own pool; freed blocks stay in it, so steady-state calls never reach the driver
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  ML_CUDA(cudaMemPoolCreate(&h->e.pool, &props));
   uint64_t thr = ~0ull;
-  ML_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  ML_CUDA(cudaMemPoolSetAttribute(h->e.pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  h->e.mailbox.cap = 1 << 20;
+  ML_CUDA(cudaHostAlloc((void**)&h->e.mailbox.host, h->e.mailbox.cap, cudaHostAllocMapped));
+  ML_CUDA(cudaHostGetDevicePointer((void**)&h->e.mailbox.dev, h->e.mailbox.host, 0));
   if (const char* s = getenv("ML_FLSA_CHUNK")) h->e.flsa_chunk = atoi(s);
   if (const char* s = getenv("ML_FLSA_WARM")) h->e.flsa_warm = atoi(s);
   if (const char* s = getenv("ML_FLSA_SEQUENTIAL")) h->e.flsa_sequential = atoi(s);
@@ -106,6 +146,9 @@ void ml_engine_destroy(ml_engine* eng) {
   if (eng->e.stream) cudaStreamSynchronize(eng->e.stream);
   cudaStream_t mine = eng->e.own_stream ? eng->e.stream : eng->own;
   if (mine) cudaStreamDestroy(mine);
+  if (eng->e.copy_stream) { cudaStreamSynchronize(eng->e.copy_stream); cudaStreamDestroy(eng->e.copy_stream); }
+  if (eng->e.pool) cudaMemPoolDestroy(eng->e.pool);
+  if (eng->e.mailbox.host) cudaFreeHost(eng->e.mailbox.host);
   delete eng;
 }
 
@@ -126,7 +169,10 @@ int ml_engine_synchronize(ml_engine* eng) {
   if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
-  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  stream_sync(eng->e.stream);
+  ML_CUDA(cudaStreamSynchronize(eng->e.copy_stream));
   return ML_OK;
   ML_CATCH
 }
@@ -135,7 +181,9 @@ int ml_engine_set_stream(ml_engine* eng, void* cuda_stream) {
   if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
-  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  stream_sync(eng->e.stream);
   if (cuda_stream) {
     if (eng->e.own_stream) { eng->e.own_stream = false; eng->own = eng->e.stream; }
     eng->e.stream = (cudaStream_t)cuda_stream;
@@ -181,7 +229,7 @@ static void flsa_batch_device(Engine& e, int nseries, const int64_t* ptr, const 
   }
   FlsaPlan plan(e, series, ptr[nseries]);
   plan.solve(d_y, d_w, d_beta, 1, lambda1, nullptr);
-  ML_CUDA(cudaStreamSynchronize(e.stream));
+  stream_sync(e.stream);
 }
 
 // debugging aid (not part of the drop-in surface): one series, also returns the DP back-pointers
@@ -190,6 +238,8 @@ int ml_debug_flsa_backpointers(ml_engine* eng, int64_t n, const double* y, const
   if (!eng || n <= 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   cudaStream_t st = eng->e.stream;
   DevBuf<double> d_y(st, (size_t)n), d_w(st, (size_t)n), d_b(st, (size_t)n);
   d_y.upload(y, (size_t)n);
@@ -215,6 +265,8 @@ int ml_weighted_1d_flsa_batch_device(ml_engine* eng, int nseries, const int64_t*
   if (!eng || !ptr || !lambda2 || nseries < 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   if (nseries == 0 || ptr[nseries] == 0) return ML_OK;
   flsa_batch_device(eng->e, nseries, ptr, d_y, d_wt, lambda2, lambda1, d_beta);
   return ML_OK;
@@ -226,6 +278,8 @@ int ml_weighted_1d_flsa_batch(ml_engine* eng, int nseries, const int64_t* ptr, c
   if (!eng || !ptr || !lambda2 || nseries < 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   if (nseries == 0) return ML_OK;
   const int64_t total = ptr[nseries];
   if (total == 0) return ML_OK;
@@ -236,7 +290,7 @@ int ml_weighted_1d_flsa_batch(ml_engine* eng, int nseries, const int64_t* ptr, c
   d_w.upload(wt, (size_t)total);
   flsa_batch_device(eng->e, nseries, ptr, d_y.p, d_w.p, lambda2, lambda1, d_b.p);
   d_b.download(beta, (size_t)total);
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   return ML_OK;
   ML_CATCH
 }
@@ -256,6 +310,8 @@ int ml_batch_upload(ml_engine* eng, int njobs, const int64_t* job_ptr, const int
   *out = nullptr;
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   if (njobs > 0 && job_ptr[njobs] > 0 && (!dataset || !condition || !replicate || !pos || !nmeth || !coverage))
     throw MlError(ML_ERR_BAD_ARGUMENT, "NULL column (data should contain columns dataset, condition, "
                                        "replicate, pos, Nmeth and coverage!)");
@@ -279,6 +335,8 @@ int ml_batch_detect(ml_engine* eng, ml_batch* b, const ml_params* params, ml_res
   *out = nullptr;
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   Params p;
   memcpy(&p, params, sizeof(p));
   auto h = std::make_unique<ml_result>();
@@ -335,6 +393,8 @@ int ml_result_copy_job(ml_engine* eng, const ml_result* r, int job, double* mu, 
   if (!eng || !r || job < 0 || job >= (int)r->r->jobs.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   const Result& R = *r->r;
   const JobHost& j = R.jobs[job];
   if (j.status) return fail(j.status, ml_strerror(j.status));
@@ -353,23 +413,29 @@ int ml_result_copy_job(ml_engine* eng, const ml_result* r, int job, double* mu, 
   if (estimate_id)
     for (int e = 0; e < j.E; ++e)
       for (int64_t k = 0; k < j.P; ++k) estimate_id[(size_t)e * j.P + k] = e + 1;
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   return ML_OK;
   ML_CATCH
 }
 
-int ml_result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
-                       double* start, double* beta, double* betahat, double* pseudoweight) {
+static int result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
+                           double* start, double* beta, double* betahat, double* pseudoweight, bool async) {
   if (!eng || !r) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   const Result& R = *r->r;
-  cudaStream_t st = eng->e.stream;
-  // parameter arrays and offsets of the valid jobs are already contiguous in job order
+  // the result is complete (detect synchronised); the asynchronous variant copies on the engine's
+  // copy stream so that later compute calls on the main stream overlap with the transfer
+  cudaStream_t st = async ? eng->e.copy_stream : eng->e.stream;
+  // parameter arrays and offsets of the valid jobs are already contiguous in job order.  The tiny
+  // offset copy goes first: if its destination is pageable the call blocks until everything queued
+  // before it on this stream has completed.
+  if (offset && R.noff) ML_CUDA(cudaMemcpyAsync(offset, R.offset.p, sizeof(double) * (size_t)R.noff, cudaMemcpyDeviceToHost, st));
   if (beta && R.npar) ML_CUDA(cudaMemcpyAsync(beta, R.beta.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
   if (betahat && R.npar) ML_CUDA(cudaMemcpyAsync(betahat, R.betahat.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
   if (pseudoweight && R.npar) ML_CUDA(cudaMemcpyAsync(pseudoweight, R.pw.p, sizeof(double) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
-  if (offset && R.noff) ML_CUDA(cudaMemcpyAsync(offset, R.offset.p, sizeof(double) * (size_t)R.noff, cudaMemcpyDeviceToHost, st));
   size_t mu_at = 0, par_at = 0;
   for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
     const JobHost& j = R.jobs[jn];
@@ -383,14 +449,24 @@ int ml_result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* o
       if (start)
         ML_CUDA(cudaMemcpyAsync(start + par_at, R.start.p + R.start0[jn], sizeof(double) * (size_t)j.P,
                                 cudaMemcpyDeviceToHost, st));
-      if (estimate_id)
-        for (int64_t k = 0; k < j.P; ++k) estimate_id[par_at + k] = e + 1;
       par_at += (size_t)j.P;
     }
   }
-  ML_CUDA(cudaStreamSynchronize(st));
+  if (estimate_id && R.npar)
+    ML_CUDA(cudaMemcpyAsync(estimate_id, R.est_id.p, sizeof(int32_t) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
+  if (!async) stream_sync(st);
   return ML_OK;
   ML_CATCH
+}
+
+int ml_result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
+                       double* start, double* beta, double* betahat, double* pseudoweight) {
+  return result_copy_all(eng, r, mu, offset, estimate_id, start, beta, betahat, pseudoweight, false);
+}
+
+int ml_result_copy_all_async(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
+                             double* start, double* beta, double* betahat, double* pseudoweight) {
+  return result_copy_all(eng, r, mu, offset, estimate_id, start, beta, betahat, pseudoweight, true);
 }
 
 void ml_result_free(ml_result* r) {
@@ -403,6 +479,8 @@ int ml_result_fast_diff_combine(ml_engine* eng, ml_result* r) {
   if (!eng || !r) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   result_fast_diff_combine(eng->e, *r->r);
   return ML_OK;
   ML_CATCH
@@ -419,6 +497,8 @@ int ml_segment_methylation_helper(ml_engine* eng, int64_t n, const int32_t* esti
     return fail(ML_ERR_BAD_ARGUMENT, "segment_methylation_helper needs a non-empty table");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   SegHostOut ho;
   ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
   ho.beta = seg_beta; ho.betahat = seg_betahat; ho.pseudoweight = seg_pseudoweight; ho.stdev = seg_stdev;
@@ -433,6 +513,8 @@ int ml_result_segments(ml_engine* eng, ml_result* r, double tol_val, int64_t* n_
   if (!eng || !r || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   Result& R = *r->r;
   if (!R.seg_cache || R.seg_tol != tol_val) {
     std::vector<SegGroup> groups;
@@ -456,7 +538,7 @@ int ml_result_segments(ml_engine* eng, ml_result* r, double tol_val, int64_t* n_
   ho.end = seg_end; ho.beta = seg_beta; ho.betahat = seg_betahat; ho.pseudoweight = seg_pseudoweight;
   ho.stdev = seg_stdev;
   if (S > 0) ds.download(eng->e.stream, S, ho);
-  ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+  stream_sync(eng->e.stream);
   return ML_OK;
   ML_CATCH
 }
@@ -468,6 +550,8 @@ int ml_result_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double 
   if (!eng || !r || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
   Result& R = *r->r;
   if (!R.seg_cache || R.seg_tol != tol_val) {
     int64_t ns = 0;
@@ -478,12 +562,8 @@ int ml_result_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double 
   SegDeviceOut& seg = *R.seg_cache;
   cudaStream_t st = eng->e.stream;
   if (!R.pmd_cache || R.pmd_tol != tol_val || R.pmd_lambda2 != pmd_lambda2) {
-    std::vector<int32_t> job((size_t)seg.n), est((size_t)seg.n);
-    seg.job.download(job.data(), (size_t)seg.n);
-    seg.estimate_id.download(est.data(), (size_t)seg.n);
-    ML_CUDA(cudaStreamSynchronize(st));
     auto out = std::make_unique<SegDeviceOut>();
-    out->n = pmd_segments_device(eng->e, seg, job, est, pmd_lambda2, tol_val, R.pmd_fused, *out);
+    out->n = pmd_segments_device(eng->e, seg, pmd_lambda2, tol_val, R.pmd_fused, *out);
     R.pmd_cache = std::move(out);
     R.pmd_tol = tol_val;
     R.pmd_lambda2 = pmd_lambda2;
@@ -495,7 +575,7 @@ int ml_result_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double 
   ho.job = seg_job; ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
   ho.beta = seg_fused_std; ho.betahat = seg_std; ho.pseudoweight = seg_pseudoweight;
   if (P.n > 0) P.download(st, P.n, ho);
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   return ML_OK;
   ML_CATCH
 }

@@ -683,6 +683,22 @@ k_fast_diff(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs, 
   pw[pi] = s;
 }
 
+__global__ void k_scatter_cond_rep(const int64_t* __restrict__ rows, const int32_t* __restrict__ vc,
+                                   const int32_t* __restrict__ vr, int n, int32_t* __restrict__ condition,
+                                   int32_t* __restrict__ replicate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { condition[rows[i]] = vc[i]; replicate[rows[i]] = vr[i]; }
+}
+
+// estimate_id column of the estimates table (methylation_helpers.hpp:39): e + 1 per parameter
+__global__ void __launch_bounds__(PAR_TILE)
+k_fill_estimate_id(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs, int32_t* __restrict__ id) {
+  const ParTile t = tiles[blockIdx.x];
+  if ((int)threadIdx.x >= t.cnt) return;
+  const JobDev J = jobs[t.job];
+  id[J.par0 + (int64_t)t.e * J.P + t.k0 + threadIdx.x] = t.e + 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -711,14 +727,50 @@ std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_p
     b->hint_C[j] = any ? condition[last] : 0;
   }
   b->dataset.alloc(st, n);   b->dataset.upload(dataset, n);
-  b->condition.alloc(st, n); b->condition.upload(condition, n);
-  b->replicate.alloc(st, n); b->replicate.upload(replicate, n);
   b->pos.alloc(st, n);       b->pos.upload(pos, n);
   b->nmeth.alloc(st, n);     b->nmeth.upload(nmeth, n);
   b->cov.alloc(st, n);       b->cov.upload(cov, n);
+  // condition / replicate: the reference reads them only at the first row of each dataset
+  // (Observations.hpp:47-56; data_design_helpers.cpp:17-20), so only those rows cross PCIe.  The rows
+  // are found by the same lower_bound the kernels use; a job whose dataset column does not split
+  // cleanly into runs 1..D (invalid input) gets its two columns uploaded whole instead, so that the
+  // device reports the reference's error for it.
+  b->condition.alloc(st, n); b->condition.zero();
+  b->replicate.alloc(st, n); b->replicate.zero();
+  std::vector<int64_t> rows;
+  std::vector<int32_t> vc, vr;
+  for (int j = 0; j < njobs; ++j) {
+    const int64_t j0 = b->job_ptr[j], nj = b->job_ptr[j + 1] - j0;
+    if (nj <= 0) continue;
+    const int32_t* dj = dataset + j0;
+    const int D = b->hint_D[j];
+    bool clean = D >= 1 && D <= nj && dj[0] == 1;
+    std::vector<int64_t> mine{0};
+    for (int d = 2; clean && d <= D; ++d) {
+      const int64_t lb = std::lower_bound(dj, dj + nj, d) - dj;
+      if (lb <= 0 || lb >= nj || dj[lb] != d || dj[lb - 1] != d - 1) clean = false;
+      else mine.push_back(lb);
+    }
+    if (clean) {
+      for (int64_t r : mine) { rows.push_back(j0 + r); vc.push_back(condition[j0 + r]); vr.push_back(replicate[j0 + r]); }
+    } else {
+      ML_CUDA(cudaMemcpyAsync(b->condition.p + j0, condition + j0, sizeof(int32_t) * (size_t)nj, cudaMemcpyHostToDevice, st));
+      ML_CUDA(cudaMemcpyAsync(b->replicate.p + j0, replicate + j0, sizeof(int32_t) * (size_t)nj, cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (!rows.empty()) {
+    DevBuf<int64_t> d_rows(st, rows.size());
+    DevBuf<int32_t> d_vc(st, vc.size()), d_vr(st, vr.size());
+    d_rows.upload(rows);
+    d_vc.upload(vc);
+    d_vr.upload(vr);
+    ML_LAUNCH(eng, "k_scatter_cond_rep", k_scatter_cond_rep<<<cdiv((long long)rows.size(), 128), 128, 0, st>>>(
+        d_rows.p, d_vc.p, d_vr.p, (int)rows.size(), b->condition.p, b->replicate.p));
+    stream_sync(st);
+  }
   b->d_job_ptr.alloc(st, njobs + 1);
   b->d_job_ptr.upload(b->job_ptr);
-  ML_CUDA(cudaStreamSynchronize(st));  // the caller may reuse its buffers after return
+  stream_sync(st);  // the caller may reuse its buffers after return
   return b;
 }
 
@@ -794,7 +846,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   d_dcond.download(h_dcond.data(), n_ent);
   d_dfirst.download(h_dfirst.data(), n_ent);
   d_dlast.download(h_dlast.data(), n_ent);
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
 
   // ---- host: per-job status, design, geometry ----------------------------------------------------
   const bool fast = p.model == MODEL_FAST;
@@ -927,7 +979,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     ML_LAUNCH(eng, "k_bitmap_word_prefix", k_bitmap_word_prefix<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p));
     std::vector<int32_t> uniq(nj);
     d_job_unique.download(uniq.data(), nj);
-    ML_CUDA(cudaStreamSynchronize(st));
+    stream_sync(st);
     for (int j = 0; j < nj; ++j) {
       if (res->jobs[j].status) continue;
       hj[j].P = uniq[j];
@@ -1111,7 +1163,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       ML_LAUNCH(eng, "k_job_finalize", k_job_finalize<<<nj, 256, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
                                                   cx.scalars.p));
       cx.scalars.download(sc.data(), sc.size());
-      ML_CUDA(cudaStreamSynchronize(st));
+      stream_sync(st);
     }
     // ---- host decisions -------------------------------------------------------------------------
     bool any_copy = false;
@@ -1177,7 +1229,9 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     JobHost& jh = res->jobs[j];
     jh.hyper = (p.model == MODEL_FAST) ? 1.0 : p.hyper;
   }
-  ML_CUDA(cudaStreamSynchronize(st));
+  res->est_id.alloc(st, (size_t)std::max<int64_t>(1, npar));
+  if (n_pt) ML_LAUNCH(eng, "k_fill_estimate_id", k_fill_estimate_id<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, res->est_id.p));
+  stream_sync(st);
   return res;
 }
 
@@ -1203,7 +1257,7 @@ void result_fast_diff_combine(Engine& eng, Result& r) {
   DevBuf<ParTile> d_pt(st, pt.size());
   d_pt.upload(pt);
   ML_LAUNCH(eng, "k_fast_diff", k_fast_diff<<<(int)pt.size(), PAR_TILE, 0, st>>>(d_pt.p, d_jobs.p, r.beta.p, r.betahat.p, r.pw.p));
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
 }
 
 }  // namespace ml

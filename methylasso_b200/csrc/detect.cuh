@@ -86,6 +86,7 @@ struct Result {
   DevBuf<double> beta, betahat, pw;       // per parameter
   DevBuf<double> start;                   // per (job, param): bin start truncated to int, as double
   DevBuf<double> offset;
+  DevBuf<int32_t> est_id;                 // per parameter: estimator index + 1
   std::vector<int64_t> start0;            // per job: offset into start (P entries)
   int64_t nstart = 0;
   // segments of the last ml_result_segments call (query-then-fetch without recomputing)

@@ -42,12 +42,12 @@ class FlsaPlan {
   void debug_backpointers(double* h_tm, double* h_tp) const {
     d_tm_.download(h_tm, (size_t)total_len_);
     d_tp_.download(h_tp, (size_t)total_len_);
-    ML_CUDA(cudaStreamSynchronize(eng_.stream));
+    stream_sync(eng_.stream);
   }
   void debug_chunk_states(std::vector<ChunkState>& out) const {
     out.resize((size_t)n_chunks_);
     d_states_.download(out.data(), (size_t)n_chunks_);
-    ML_CUDA(cudaStreamSynchronize(eng_.stream));
+    stream_sync(eng_.stream);
   }
   int n_series() const { return (int)series_.size(); }
   int n_chunks() const { return n_chunks_; }

@@ -116,7 +116,7 @@ struct Scan {
     ML_LAUNCH(eng, "k_scan_apply", k_scan_apply<<<nt, 256, 0, st>>>(flags, n, tile_sum.p, pos, compact));
     int32_t h = 0;
     total.download(&h, 1);
-    ML_CUDA(cudaStreamSynchronize(st));
+    stream_sync(st);
     return h;
   }
 };
@@ -235,6 +235,14 @@ __global__ void k_run_group(const int32_t* __restrict__ run_row, int32_t n_runs,
   run_group[r] = lo;
 }
 
+// first segment of every group (and the total as a sentinel)
+__global__ void k_group_seg0(const SegGroup* __restrict__ groups, int ngroups, const int32_t* __restrict__ run_pos,
+                             const int32_t* __restrict__ seg_of_run, int32_t n_segs, int32_t* __restrict__ out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < ngroups) out[g] = seg_of_run[run_pos[groups[g].row0]];
+  if (g == ngroups) out[g] = n_segs;
+}
+
 __global__ void k_group_heads(const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = (i == 0 || idx[i] != idx[i - 1]) ? 1 : 0;
@@ -258,20 +266,18 @@ __global__ void k_pmd_inputs(int64_t n, const uint32_t* __restrict__ start, cons
 // std fusion + re-segmentation of a segment table (R/call.R:93-95): fused = weighted_1d_flsa(std,
 // width, pmd_lambda2) per (job, estimate); then segment_methylation_helper on
 // (estimate_id, start, beta = fused, betahat = std, pseudoweight).
-int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, const std::vector<int32_t>& seg_job,
-                            const std::vector<int32_t>& seg_est, double pmd_lambda2, double tol_val,
+int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, double pmd_lambda2, double tol_val,
                             DevBuf<double>& fused, SegDeviceOut& out) {
   cudaStream_t st = eng.stream;
   const int64_t n = seg.n;
   if (n == 0) return 0;
   std::vector<FlsaSeries> series;
   std::vector<SegGroup> groups;
-  for (int64_t i = 0; i < n;) {
-    int64_t j = i + 1;
-    while (j < n && seg_job[j] == seg_job[i] && seg_est[j] == seg_est[i]) ++j;
+  for (size_t g = 0; g + 1 < seg.group_seg0.size(); ++g) {
+    const int64_t i = seg.group_seg0[g], j = seg.group_seg0[g + 1];
+    if (j <= i) continue;
     series.push_back(FlsaSeries{i, (int32_t)(j - i), pmd_lambda2});
-    groups.push_back(SegGroup{i, j - i, i, seg_est[i], seg_job[i]});
-    i = j;
+    groups.push_back(SegGroup{i, j - i, i, seg.group_est[g], seg.group_job[g]});
   }
   DevBuf<double> y(st, (size_t)n), w(st, (size_t)n);
   DevBuf<int32_t> start_i32(st, (size_t)n);
@@ -332,10 +338,22 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   const int32_t n_segs = scan.run(eng, seg_head.p, n_runs, seg_of_run.p, seg_run.p);
   ds.alloc(st, n_segs);
   SegOut out = ds.view();
+  {   // per-group segment ranges for callers that go on working on the table (PMD fusion)
+    DevBuf<int32_t> d_g0(st, ng + 1);
+    ML_LAUNCH(eng, "k_group_seg0", k_group_seg0<<<cdiv(ng + 1, 128), 128, 0, st>>>(d_groups.p, ng, run_pos.p, seg_of_run.p,
+                                                                               n_segs, d_g0.p));
+    std::vector<int32_t> g0(ng + 1);
+    d_g0.download(g0.data(), ng + 1);
+    stream_sync(st);
+    ds.group_seg0.assign(g0.begin(), g0.end());
+    ds.group_job.resize(ng);
+    ds.group_est.resize(ng);
+    for (int g = 0; g < ng; ++g) { ds.group_job[g] = groups[g].job; ds.group_est[g] = groups[g].estimate_id; }
+  }
   ML_LAUNCH(eng, "k_seg_emit", k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
                                                 seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
                                                 d_betahat, d_pw, out));
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   return n_segs;
 }
 
@@ -359,7 +377,7 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
   const int32_t ng = scan.run(eng, gflags.p, n, nullptr, ghead.p);
   std::vector<int32_t> heads(ng);
   ghead.download(heads.data(), ng);
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   std::vector<SegGroup> groups(ng);
   for (int g = 0; g < ng; ++g) {
     const int64_t r0 = heads[g], r1 = g + 1 < ng ? heads[g + 1] : n;
@@ -368,7 +386,7 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
   SegDeviceOut ds;
   const int64_t S = segment_device(eng, groups, n, d_start.p, 0, d_beta.p, d_bh.p, d_pw.p, tol_val, ds);
   ds.download(st, S, ho);
-  ML_CUDA(cudaStreamSynchronize(st));
+  stream_sync(st);
   return S;
 }
 

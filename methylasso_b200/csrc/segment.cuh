@@ -29,6 +29,8 @@ struct SegDeviceOut {
   DevBuf<uint32_t> start, end;
   DevBuf<double> beta, betahat, pseudoweight, stdev;
   int64_t n = 0;
+  // host copy of the group structure: segments [group_seg0[g], group_seg0[g+1]) belong to group g
+  std::vector<int32_t> group_seg0, group_job, group_est;
   void alloc(cudaStream_t st, int64_t count) {
     n = count;
     const size_t c = (size_t)std::max<int64_t>(1, count);
@@ -54,8 +56,7 @@ struct SegDeviceOut {
 int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups, int64_t nrows, const void* d_start,
                        int start_f64, const double* d_beta, const double* d_betahat, const double* d_pw,
                        double tol_val, SegDeviceOut& out);
-int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, const std::vector<int32_t>& seg_job,
-                            const std::vector<int32_t>& seg_est, double pmd_lambda2, double tol_val,
+int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, double pmd_lambda2, double tol_val,
                             DevBuf<double>& fused, SegDeviceOut& out);
 int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, const int32_t* start,
                            const double* beta, const double* betahat, const double* pw, double tol_val,
