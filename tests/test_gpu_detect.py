@@ -248,3 +248,45 @@ def test_full_genome_shape_properties(engine):
             assert kkt_residual(est["betahat"] - shift, est["pseudoweight"], est["beta"], 25.0) < 1e-8
     finally:
         res.free()
+
+
+def test_cohort_batch_config4(engine, oracle):
+    """BASELINE config 4 at reduced size: many independent samples x chromosomes in one batched call
+    (on 8 GPUs the same job list is sharded by methylasso_b200.shard.lpt_assign)."""
+    tables = [synth.chromosome_table(n, 1000 * s + c, (1,)) for s in range(8) for c, n in enumerate((9000, 4000, 1500))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, params())
+    try:
+        assert res.status.tolist() == [0] * len(tables)
+        for j in (0, 5, 13, 23):
+            assert_job_matches(res.job(j), oracle.detect(tables[j], 0))
+        seg = res.segments(0.01)
+        so = oracle.segment_methylation_helper(oracle.detect(tables[13], 0)["estimates"], 0.01)
+        m = seg["job"] == 13
+        assert np.array_equal(seg["start"][m], so["start"]) and np.array_equal(seg["end"][m], so["end"])
+    finally:
+        res.free()
+
+
+def test_engine_pool_grouping_is_result_neutral(engine):
+    """EnginePool / split_jobs: any grouping of the chromosomes gives the same bits."""
+    tables = [synth.chromosome_table(n, 400 + i, (2,)) for i, n in enumerate((20_000, 3000, 12_000, 700, 9000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, params())
+    whole = [res.job(j) for j in range(5)]
+    res.free()
+    pool = api.EnginePool(2)
+    try:
+        def run(eng, grp):
+            jobs, gptr, gcols = grp
+            r = eng.detect_batch(gptr, gcols, params())
+            out = [(j, r.job(i)) for i, j in enumerate(jobs)]
+            r.free()
+            return out
+        got = dict(sum(pool.map(run, api.split_jobs(ptr, cols, 2)), []))
+    finally:
+        pool.close()
+    for j in range(5):
+        for c in ("beta", "betahat", "pseudoweight"):
+            assert np.array_equal(got[j]["estimates"][c], whole[j]["estimates"][c])
+        assert np.array_equal(got[j]["mu"], whole[j]["mu"])

@@ -113,3 +113,41 @@ def test_full_size_chromosome_properties(engine):
     finally:
         engine.set("flsa_sequential", 0)
     assert np.array_equal(beta, seq)
+
+
+def test_lambda_sweep_config5(engine, oracle):
+    """BASELINE config 5: 16 lambda2 values in [10, 2000] on the same series, one batched call."""
+    t = synth.chromosome_table(150_000, 5, (3,))
+    y, w = pooled_series(t)
+    lams = np.geomspace(10, 2000, 16)
+    n = y.size
+    ptr = np.arange(17) * n
+    got = engine.weighted_1d_flsa_batch(ptr, np.tile(y, 16), np.tile(w, 16), lams)
+    for i, lam in enumerate(lams):
+        ref = oracle.weighted_1d_flsa(y, w, float(lam))
+        assert np.array_equal(got[i * n:(i + 1) * n], ref), lam   # count data: bit-exact at every lambda
+        assert kkt_residual(y, w, ref, float(lam)) < 1e-8
+
+
+def test_hypothesis_kkt_and_oracle(engine, oracle):
+    """Property test on arbitrary inputs: optimality conditions + agreement with the oracle."""
+    from hypothesis import given, settings, strategies as st
+    import hypothesis.extra.numpy as hnp
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(2, 300).flatmap(lambda n: st.tuples(
+        hnp.arrays(np.float64, n, elements=st.floats(-5, 5, allow_nan=False, width=32)),
+        hnp.arrays(np.float64, n, elements=st.floats(0.0, 50.0, allow_nan=False, width=32)),
+        st.sampled_from([0.01, 0.5, 7.0, 300.0]))))
+    def check(args):
+        y, w, lam = args
+        if not (w > 0).any():
+            return
+        got = engine.weighted_1d_flsa(y, w, lam)
+        ref = oracle.weighted_1d_flsa(y, w, lam)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(got), ok)
+        assert np.allclose(got[ok], ref[ok], rtol=1e-9, atol=1e-9)
+        if ok.all() and np.all(np.abs(ref) < 35):
+            assert kkt_residual(y, w, got, lam) < 1e-6 * max(1.0, float(np.max(w)) * float(np.max(np.abs(y))) / lam)
+    check()

@@ -1,0 +1,39 @@
+"""CPU tests of the Python host layer that need no GPU: chromosome splitting, job grouping."""
+import numpy as np
+
+from methylasso_b200 import api, synth
+
+
+def test_split_by_chr_keeps_first_appearance_order_and_rows():
+    tables = [synth.chromosome_table(n, 10 + i, (2,)) for i, n in enumerate((300, 120, 500))]
+    names = ["chr9", "chr1", "chrX"]   # data[, unique(chr)] keeps first-appearance order, not sorted order
+    data = {k: np.concatenate([t[k] for t in tables]) for k in tables[0]}
+    data["chr"] = np.concatenate([np.repeat(nm, t["pos"].size) for nm, t in zip(names, tables)])
+    # interleave rows of different chromosomes to make the split do real work
+    perm = np.random.default_rng(0).permutation(data["pos"].size)
+    order = np.argsort(perm, kind="stable")
+    shuffled = {k: v[perm] for k, v in data.items()}
+    # restore (dataset, pos) order inside each chromosome as the R layer does (data is keyed that way)
+    key = np.lexsort((shuffled["pos"], shuffled["dataset"]))
+    shuffled = {k: v[key] for k, v in shuffled.items()}
+    got_names, ptr, cols, _ = api.split_by_chr(shuffled)
+    assert sorted(got_names.tolist()) == sorted(names)
+    for nm, j in zip(got_names, range(3)):
+        t = tables[names.index(nm)]
+        sl = slice(ptr[j], ptr[j + 1])
+        for k in ("dataset", "pos", "Nmeth", "coverage"):
+            assert np.array_equal(cols[k][sl], t[k]), (nm, k)
+    del order
+
+
+def test_split_jobs_partitions_and_balances():
+    tables = [synth.chromosome_table(n, 50 + i, (1,)) for i, n in enumerate((900, 100, 400, 350, 800, 50))]
+    ptr, cols = synth.concat_jobs(tables)
+    groups = api.split_jobs(ptr, cols, 3)
+    seen = sorted(j for jobs, _, _ in groups for j in jobs)
+    assert seen == list(range(6))
+    sizes = [int(g[1][-1]) for g in groups]
+    assert max(sizes) < 1.5 * (sum(sizes) / 3)
+    for jobs, gptr, gcols in groups:
+        for i, j in enumerate(jobs):
+            assert np.array_equal(gcols["pos"][gptr[i]:gptr[i + 1]], tables[j]["pos"])
