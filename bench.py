@@ -147,6 +147,23 @@ def run_reference(args, rank, world):
         U = reference_step(tables, O, threads)
     dt = (time.perf_counter() - t0) / max(1, args.steps)
     value = U / dt
+    # For information: the reference's OWN C++ path (unmodified sources compiled against the stand-in Rcpp/Eigen
+    # headers, oracle/_ref/libmethylasso_ref.so) on a bounded sample, one thread.  It is much slower than the
+    # restatement (std::map binner, eager stand-in Eigen), so the restatement stays the conservative baseline.
+    ref_cxx = None
+    if O.ref_full_lib() is not None:
+        small = synth.chromosome_table(100_000, 4242, (3,))
+        t1 = time.perf_counter()
+        rr = O.reference_detect(small, model=0, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+        O.reference_segment_helper(rr["estimates"], TOL)
+        d1 = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        O.detect(small, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+        d2 = time.perf_counter() - t1
+        u = int(np.unique(small["pos"]).size)
+        ref_cxx = {"value": u / d1, "unit": "CpG/s", "cores": 1, "port_same_sample": u / d2,
+                   "sample": "one 100k-CpG x 3-replicate chromosome, FAST detect + segment helper, 1 thread; "
+                             "reference sources + stand-in Rcpp/Eigen headers (oracle/stubs)"}
     line = {
         "impl": "reference", "metric": "CpGs/sec through IRLS+weighted 1D FLSA", "value": value, "unit": "CpG/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -156,6 +173,7 @@ def run_reference(args, rank, world):
                          "sample": f"whole workload per step; oracle C restatement of methylation_detection, DP = {kind_dp}, "
                                    f"one chromosome per thread over {threads} threads"},
         "e2e": {"value": value, "unit": "CpG/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ref_cxx": ref_cxx,
     }
     print(json.dumps(line), flush=True)
     if args.out:

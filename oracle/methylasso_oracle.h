@@ -5,13 +5,26 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load this library; the product (libmethylasso_b200.so) never does.
  *
- * Parity status: the reference ships no tests, fixtures or golden vectors
- * (SURVEY.md §4), so this oracle is pinned by (a) the reference's own DP kernel
- * compiled verbatim into oracle/_ref/libtfdp_ref.so (bit-exact comparison, see
- * tests/test_oracle.py) and (b) the two known answers recorded in BASELINE.md §2.
- * Everything above the DP (Rcpp/Eigen code) cannot be compiled here (no R, Rcpp,
- * Eigen): for that part parity is UNPINNED by the reference — it is a literal,
- * line-cited restatement only.
+ * Parity status: PINNED against the reference itself.  The reference ships no tests,
+ * fixtures or golden vectors, and R / Rcpp / Eigen / GSL / Boost are not in
+ * this image, so the pin is built from the reference's own sources compiled in place
+ * (oracle/Makefile, nothing is copied into this repository):
+ *   (a) oracle/_ref/libtfdp_ref.so: the DP kernel src/core/gfl/gfl_tf.c compiled verbatim;
+ *       the DP restatement is bit-identical to it (tests/test_oracle.py);
+ *   (b) oracle/_ref/libmethylasso_ref.so: the reference's unmodified C++ path above the DP
+ *       (signal_detection*.cpp, difference_detection.cpp, methylation_helpers.cpp,
+ *       weighted_1d_flsa.cpp, core/Posterior.ipp, Estimator.ipp, Binner.cpp, ... 19 translation
+ *       units) compiled against small stand-in headers for Rcpp / Eigen / Boost
+ *       (oracle/stubs: NOT those libraries, see each header) behind C entry points
+ *       (oracle/ref_driver.cpp).  tests/test_oracle_pin.py runs it live against this
+ *       restatement and against tests/golden/reference_fixtures.npz (generated from it by
+ *       tests/golden/make_golden.py): integer outputs, convergence flags, refusal messages and
+ *       the segment helper identical; FAST pseudodata bit-identical; every float within 1.3e-12
+ *       (Eigen's two-lane vectorised sums vs left-to-right sums here);
+ *   (c) the two known answers recorded in BASELINE.md §2.
+ * What the stand-in headers cannot vouch for is real Eigen's association order inside .sum()
+ * and sparse products (reproduced from Eigen's documented default traversal; effect ~1e-16
+ * relative) and Boost's brent_find_minima (optimize_hyper = TRUE, outside the hot path: refused).
  */
 #ifndef METHYLASSO_ORACLE_H
 #define METHYLASSO_ORACLE_H

@@ -49,6 +49,9 @@ def build(force=False):
         subprocess.check_call(["make", "-C", HERE, "-s", os.path.join(HERE, "liboracle.so")])
     if (force or not os.path.exists(REF_PATH)) and os.path.exists("/root/reference/src/core/gfl/gfl_tf.c"):
         subprocess.check_call(["make", "-C", HERE, "-s", "ref"])
+    full = os.path.join(HERE, "_ref", "libmethylasso_ref.so")
+    if (force or not os.path.exists(full)) and os.path.exists("/root/reference/src/signal_detection.cpp"):
+        subprocess.check_call(["make", "-C", HERE, "-s", "ref_full"])
 
 
 _lib = None
@@ -187,3 +190,84 @@ def fast_diff_combine(est, n_params, n_est):
     _check(lib().orc_fast_diff_combine(n_params, n_est, _p(beta), _p(bh), _p(pw), _p(ob), _p(obh), _p(opw)))
     return dict(estimate_id=est["estimate_id"].copy(), start=est["start"].copy(), beta=ob, betahat=obh,
                 pseudoweight=opw)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference's OWN hot path (unmodified sources compiled against stub headers: oracle/Makefile,
+# target ref_full; C entry points in oracle/ref_driver.cpp).  Used only to pin the restatement above.
+REF_FULL_PATH = os.path.join(HERE, "_ref", "libmethylasso_ref.so")
+_ref_full = None
+
+
+class ReferenceError_(RuntimeError):
+    pass
+
+
+def ref_full_lib():
+    """oracle/_ref/libmethylasso_ref.so (None if absent and the reference tree is not there to build it)."""
+    global _ref_full
+    if _ref_full is None:
+        if not os.path.exists(REF_FULL_PATH) and os.path.exists("/root/reference/src/signal_detection.cpp"):
+            subprocess.check_call(["make", "-C", HERE, "-s", "ref_full"])
+        if not os.path.exists(REF_FULL_PATH):
+            return None
+        R = C.CDLL(REF_FULL_PATH)
+        vp = C.c_void_p
+        R.ref_last_error.restype = C.c_char_p
+        R.ref_detect.argtypes = [C.c_int, C.c_long] + [vp] * 6 + [C.c_double, C.c_double, C.c_double, C.c_uint,
+                                                                 C.c_double, C.c_double, C.c_uint, C.c_uint,
+                                                                 C.c_int, C.c_int]
+        R.ref_result_sizes.argtypes = [C.POINTER(C.c_long)] * 4
+        R.ref_result_copy.argtypes = [vp] * 9
+        R.ref_segment_helper.argtypes = [C.c_long] + [vp] * 5 + [C.c_double, C.POINTER(C.c_long)]
+        R.ref_segments_copy.argtypes = [vp] * 8
+        R.ref_weighted_1d_flsa.argtypes = [C.c_long, vp, vp, C.c_double, C.c_double, vp]
+        _ref_full = R
+    return _ref_full
+
+
+def _ref_check(rc):
+    if rc != 0:
+        raise ReferenceError_(ref_full_lib().ref_last_error().decode())
+
+
+def reference_detect(t, model=MODEL_FAST, lambda2=25.0, tol_val=0.01, max_iter=1, nouter=20, max_lambda2=1000.0,
+                     bf_per_kb=50.0, hyper=100.0, ref=1):
+    """The reference's signal_detection_fast_R / signal_detection_R / difference_detection_R
+    (src/signal_detection.cpp:11,51; src/difference_detection.cpp:13) on one chromosome table."""
+    R = ref_full_lib()
+    cols = [_i32(t[k]) for k in ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")]
+    _ref_check(R.ref_detect(int(model), cols[0].size, *[_p(c) for c in cols], float(lambda2), float(max_lambda2),
+                            float(hyper), int(nouter), float(bf_per_kb), float(tol_val), int(max_iter), int(ref), 0, 0))
+    sz = [C.c_long() for _ in range(4)]
+    _ref_check(R.ref_result_sizes(*[C.byref(s) for s in sz]))
+    n, ne, nl, no = [s.value for s in sz]
+    mu, lam, off = np.zeros(n), np.zeros(nl), np.zeros(no)
+    conv = C.c_int()
+    est = {k: np.zeros(ne) for k in ("estimate_id", "start", "beta", "betahat", "pseudoweight")}
+    _ref_check(R.ref_result_copy(_p(mu), _p(lam), _p(off), C.cast(C.byref(conv), C.c_void_p),
+                                 *[_p(est[k]) for k in ("estimate_id", "start", "beta", "betahat", "pseudoweight")]))
+    est["estimate_id"] = est["estimate_id"].astype(np.int32)
+    return dict(mu=mu, lambda2=lam, offset=off, converged=bool(conv.value), estimates=est)
+
+
+def reference_segment_helper(est, tol_val=0.01):
+    """The reference's segment_methylation_helper (src/methylation_helpers.cpp:6)."""
+    R = ref_full_lib()
+    idx, start = _i32(est["estimate_id"]), _i32(est["start"])
+    beta, bh, pw = _f64(est["beta"]), _f64(est["betahat"]), _f64(est["pseudoweight"])
+    S = C.c_long()
+    _ref_check(R.ref_segment_helper(idx.size, _p(idx), _p(start), _p(beta), _p(bh), _p(pw), float(tol_val), C.byref(S)))
+    keys = ("estimate_id", "segment_id", "start", "end", "beta", "betahat", "pseudoweight", "stdev")
+    o = {k: np.zeros(S.value) for k in keys}
+    _ref_check(R.ref_segments_copy(*[_p(o[k]) for k in keys]))
+    return o
+
+
+def reference_weighted_1d_flsa(y, wt, lambda2, lambda1=0.0):
+    """The reference's weighted_1d_flsa (src/weighted_1d_flsa.cpp:7)."""
+    R = ref_full_lib()
+    y, wt = _f64(y), _f64(wt)
+    out = np.zeros(y.size)
+    _ref_check(R.ref_weighted_1d_flsa(y.size, _p(y), _p(wt), float(lambda2), float(lambda1), _p(out)))
+    return out

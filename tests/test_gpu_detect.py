@@ -71,6 +71,40 @@ def test_golden_path_fixtures(engine, oracle, prefix):
     assert close(seg["beta"], g[f"{prefix}_seg_beta"]) and close(seg["pseudoweight"], g[f"{prefix}_seg_pseudoweight"])
 
 
+REFERENCE_FIXTURES = ("fast_1x1", "fast_1x3", "fast_2x2", "fast_iter3", "fast_lam1000", "full_sig", "full_sig_3c",
+                      "full_diff", "full_diff_ref2")
+
+
+@pytest.mark.parametrize("name", REFERENCE_FIXTURES)
+def test_reference_generated_fixtures(engine, name):
+    """tests/golden/reference_fixtures.npz holds outputs of the reference's OWN C++ path (unmodified sources
+    compiled against stand-in Rcpp/Eigen headers, tests/golden/make_golden.py): no restatement in between."""
+    g = np.load(os.path.join(GOLD, "reference_fixtures.npz"))
+    t = {c: g[f"{name}_in_{c}"] for c in ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")}
+    model, lambda2, max_iter, nouter, ref = g[f"{name}_kw"].tolist()
+    kw = dict(model=int(model), lambda2=lambda2, max_iter=int(max_iter), ref=int(ref))
+    if model != 0:
+        kw.update(nouter=int(nouter), max_lambda2=1000.0, hyper=100.0, bf_per_kb=50.0)
+    r = run_one(engine, t, **kw)
+    est = r["estimates"]
+    assert r["converged"] == bool(g[f"{name}_converged"])
+    assert np.array_equal(est["estimate_id"], g[f"{name}_est_estimate_id"])
+    assert np.array_equal(est["start"], g[f"{name}_est_start"])
+    for c in ("beta", "betahat", "pseudoweight"):
+        assert close(est[c], g[f"{name}_est_{c}"]), c
+    assert close(r["mu"], g[f"{name}_mu"]) and close(r["offset"], g[f"{name}_offset"])
+    if model == 0 and max_iter == 1:        # count data: bit-identical pseudodata, beta to the rounding of one mean
+        assert np.array_equal(est["betahat"], g[f"{name}_est_betahat"])
+        assert np.array_equal(est["pseudoweight"], g[f"{name}_est_pseudoweight"])
+        assert np.max(np.abs(est["beta"] - g[f"{name}_est_beta"])) < 1e-13
+    seg = engine.segment_methylation_helper({c: g[f"{name}_est_{c}"] for c in ("estimate_id", "start", "beta", "betahat",
+                                                                               "pseudoweight")}, 0.01)
+    for c in ("estimate_id", "segment_id", "start", "end"):
+        assert np.array_equal(np.asarray(seg[c], np.int64), g[f"{name}_seg_{c}"].astype(np.int64)), c
+    for c in ("beta", "betahat", "pseudoweight", "stdev"):     # same additions in the same order: bit-identical
+        assert np.array_equal(seg[c], g[f"{name}_seg_{c}"], equal_nan=True), c
+
+
 @pytest.mark.parametrize("reps,kw", [((1,), {}), ((3,), {}), ((3, 3), {}), ((2,), dict(lambda2=1000.0)),
                                      ((1,), dict(max_iter=4, lambda2=10.0))])
 def test_fast_against_oracle(engine, oracle, reps, kw):

@@ -26,6 +26,15 @@ def test_golden_reference_vectors(engine):
         assert np.array_equal(beta, want, equal_nan=True), k
 
 
+def test_reference_flsa_fixture(engine):
+    """weighted_1d_flsa outputs of the reference's own C++ entry point (src/weighted_1d_flsa.cpp:7),
+    tests/golden/reference_fixtures.npz: integer weights with zeros, with and without lambda1."""
+    g = np.load(os.path.join(GOLD, "reference_fixtures.npz"))
+    for lam2, lam1 in ((25.0, 0.0), (3.0, 0.05)):
+        got = engine.weighted_1d_flsa(g["flsa_y"], g["flsa_w"], lam2, lam1)
+        assert np.array_equal(got, g[f"flsa_{lam2:g}_{lam1:g}"])
+
+
 def test_trivial_and_error_cases(engine, oracle):
     from methylasso_b200.api import MethyLassoError
     assert engine.weighted_1d_flsa([], [], 5.0).size == 0
