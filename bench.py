@@ -226,7 +226,7 @@ def main():
     ap.add_argument("--cpgs", type=int, default=synth.GENOME_CPGS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=1,
+    ap.add_argument("--e2e-groups", type=int, default=6,
                     help="engines (streams + host threads) the e2e step spreads the chromosomes over; 1 = single call")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     ap.add_argument("--profiler-range", action="store_true",
@@ -372,14 +372,21 @@ def main():
             timeline.clear()
             t_step0[0] = time.perf_counter()
             return pool.map(run_group, groups)
-        for _ in range(max(1, args.warmup - 1)):
+        for _ in range(max(3, args.warmup)):
             outs = step_e2e()
+        for e_g in pool.engines:          # pre-grow each engine's pool a little: no cuMemMap inside a timed step
+            e_g.set("pool_headroom_percent", 10)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
+        step_wall = []
         for _ in range(args.steps):
+            ts0 = time.perf_counter()
             outs = step_e2e()
+            step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
+            if os.environ.get("ML_BENCH_MEMINFO"):
+                step_wall.append(("free_gb", round(torch.cuda.mem_get_info()[0] / 2**30, 3)))
         torch.cuda.synchronize()
         e1.record(stream)
         barrier()
@@ -392,6 +399,7 @@ def main():
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
                "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
+               "host_wall_ms_each_step": step_wall,
                "timeline_ms_last_step": sorted(timeline, key=lambda t: t[1][0]),  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
                "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "
                       "ml_result_segments + ml_result_pmd_segments per group, transfers taking turns per direction"}

@@ -73,12 +73,20 @@ struct Profiler {
 // picks them up after the stream synchronisation.  A 4-byte cudaMemcpy would otherwise queue behind
 // any large result download in flight on the same copy engine and stall the compute stream for the
 // whole transfer (measured: segmentation 10 ms -> 28 ms while 1.7 GB of results were downloading).
+//
+// The same holds in the other direction: the descriptor tables a call uploads (tiles, job structs,
+// control words; a few KB to a few MB) would queue behind another engine's 300 MB input upload on the
+// host-to-device copy engine.  They are memcpy'd into the mapped "inbox" instead and moved to device
+// memory by a small kernel on the compute stream.  Both areas are recycled at every stream_sync.
 struct Mailbox {
   char* host = nullptr;   // cudaHostAlloc(mapped)
   char* dev = nullptr;    // device alias of the same memory
   size_t cap = 0, used = 0;
   struct Pending { void* dst; size_t off, bytes; };
   std::vector<Pending> pending;
+  char* in_host = nullptr;   // inbox (host -> device staging), cudaHostAlloc(mapped | write-combined)
+  char* in_dev = nullptr;
+  size_t in_cap = 0, in_used = 0;
 };
 inline Mailbox*& tls_mailbox() {
   static thread_local Mailbox* m = nullptr;
@@ -86,6 +94,7 @@ inline Mailbox*& tls_mailbox() {
 }
 // defined in capi.cu
 bool mailbox_fetch(cudaStream_t st, void* host_dst, const void* dev_src, size_t bytes);
+bool inbox_push(cudaStream_t st, void* dev_dst, const void* host_src, size_t bytes);
 void stream_sync(cudaStream_t st);   // cudaStreamSynchronize + delivery of pending mailbox readbacks
 
 struct Engine {
@@ -147,7 +156,9 @@ struct DevBuf {
   }
   void zero() { if (n) ML_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
   void upload(const T* h, size_t count) {
-    if (count) ML_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    if (!count) return;
+    if (count * sizeof(T) <= (size_t)(8 << 20) && inbox_push(s, p, h, count * sizeof(T))) return;
+    ML_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
   }
   void upload(const std::vector<T>& h) { upload(h.data(), h.size()); }
   void download(T* h, size_t count) const {
