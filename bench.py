@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=6,
                     help="engines (streams + host threads) the e2e step spreads the chromosomes over; 1 = single call")
+    ap.add_argument("--e2e-edge", type=float, default=0.0,
+                    help="share of the rows given to the first and to the last group of the e2e pipeline (0 = balanced)")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
@@ -312,6 +314,7 @@ def main():
     launches = eng.launch_count - l0
     ms = ev0.elapsed_time(ev1) / args.steps
     prof = eng.profile()
+    prof_work = eng.profile_work()
     eng.set("profile", 0)
     t_ms = torch.tensor([ms], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -331,7 +334,7 @@ def main():
         G = max(1, args.e2e_groups)
         pool = api.EnginePool(G, local)
         groups = []
-        for jobs, gptr, gcols in api.split_jobs(ptr, cols, G):
+        for jobs, gptr, gcols in api.split_jobs(ptr, cols, G, edge_share=(args.e2e_edge or None)):
             pin_in = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in gcols.items()}
             n_g = int(gptr[-1])
             ep_g = int(sum(sizes[j][1] * sizes[j][2] for j in jobs))
@@ -416,21 +419,32 @@ def main():
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     pk, pk_kind = peaks()
     kb = kernel_bytes(N, EP, D, words)
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    # capture of this same command (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch", {})
     table = []
     for name, (tot_ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per = tot_ms / max(1, n)
-        b = kb.get(name)
+        # data-dependent kernels (FLSA chunk kernels) report the bytes of the DP steps they completed
+        b = (prof_work[name] / max(1, n)) if name in prof_work else kb.get(name)
         gbs = (b / (per * 1e-3) / 1e9) if b and per > 0 else None
         table.append({"kernel": name, "ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps,
                       "avg_launch_ms": per, "alg_bytes_per_launch": b, "GBps": gbs,
-                      "frac_of_hbm": (gbs / pk["hbm_gbs"]) if gbs else None})
+                      "frac_of_hbm": (gbs / pk["hbm_gbs"]) if gbs else None,
+                      "ncu_dram_bytes_per_launch": traffic.get(name)})
     top = table[0] if table else None
     roofline = None
     if top:
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": top["frac_of_hbm"], "traffic": None, "peak_source": pk_kind,
-                    "note": "the FLSA chunk kernels are latency-bound (dependent fp64 compare/add/divide chain per element); "
-                            "its HBM fraction is reported for the record, see profiles/ and DESIGN.md"}
+                    "frac": top["frac_of_hbm"], "traffic": top["ncu_dram_bytes_per_launch"], "peak_source": pk_kind,
+                    "alg_bytes_per_launch": top["alg_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
+                    "note": "FLSA chunk kernels run a dependent fp64 compare/add/divide chain per element (latency-bound, "
+                            "not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped kernels "
+                            "of the step are listed in `kernels` with their own fractions"}
 
     # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------
     cpu = None

@@ -110,6 +110,9 @@ ML_API int ml_engine_set_stream(ml_engine *eng, void *cuda_stream);
 ML_API int ml_engine_profile_count(ml_engine *eng);
 ML_API int ml_engine_profile_get(ml_engine *eng, int i, char *name, int name_cap, double *total_ms,
                                  long long *launches);
+/* Algorithmic bytes accumulated by entry i when its work is data-dependent (the FLSA chunk kernels: DP steps
+ * completed x 32 B, warm-up steps x 16 B); -1 when the kernel's traffic follows from the batch shape alone. */
+ML_API int ml_engine_profile_work(ml_engine *eng, int i, double *bytes);
 ML_API int ml_engine_profile_reset(ml_engine *eng);
 
 /* ---- weighted_1d_flsa  (src/weighted_1d_flsa.cpp:7-21; Rcpp module line

@@ -97,6 +97,18 @@ class Engine:
             out[name.value.decode()] = (ms.value, n.value)
         return out
 
+    def profile_work(self):
+        """{kernel name: algorithmic bytes} for the kernels whose work is data-dependent (FLSA chunk kernels)."""
+        out = {}
+        for i in range(self.lib.ml_engine_profile_count(self.h)):
+            name = C.create_string_buffer(128)
+            ms, n, b = C.c_double(), C.c_longlong(), C.c_double()
+            self._check(self.lib.ml_engine_profile_get(self.h, i, name, 128, C.byref(ms), C.byref(n)))
+            self._check(self.lib.ml_engine_profile_work(self.h, i, C.byref(b)))
+            if b.value >= 0:
+                out[name.value.decode()] = b.value
+        return out
+
     def profile_reset(self):
         self._check(self.lib.ml_engine_profile_reset(self.h))
 
@@ -337,13 +349,30 @@ class EnginePool:
         return out
 
 
-def split_jobs(job_ptr, cols, n_groups):
+def split_jobs(job_ptr, cols, n_groups, edge_share=None):
     """Split a batch into n_groups contiguous-in-memory sub-batches, balanced longest-first by rows.
+    edge_share=s (0 < s < 0.5, n_groups >= 3): the FIRST and the LAST group only get the smallest jobs, about a
+    fraction s of the rows each, and the groups in between are balanced.  In an upload | compute | download
+    pipeline (EnginePool) the first results are then ready to download early and little is left to compute and
+    download after the last upload.
     Returns [(job_indices, sub_ptr, sub_cols)], with sub_cols freshly concatenated arrays."""
     from .shard import lpt_assign
     job_ptr = np.asarray(job_ptr, dtype=np.int64)
     sizes = np.diff(job_ptr)
-    group_of = lpt_assign(sizes, n_groups)
+    if not edge_share or n_groups < 3 or sizes.size < n_groups:
+        group_of = lpt_assign(sizes, n_groups)
+    else:
+        order = [int(j) for j in np.argsort(sizes, kind="stable")]
+        budget = float(edge_share) * float(sizes.sum())
+        group_of = np.full(sizes.size, -1, np.int64)
+        for edge in (0, n_groups - 1):
+            got = 0.0
+            while order and (got == 0.0 or got + sizes[order[0]] <= budget):
+                j = order.pop(0)
+                group_of[j] = edge
+                got += float(sizes[j])
+        rest = np.array(order, np.int64)
+        group_of[rest] = 1 + lpt_assign(sizes[rest], n_groups - 2)
     out = []
     for g in range(n_groups):
         jobs = [int(j) for j in np.nonzero(group_of == g)[0]]

@@ -257,6 +257,14 @@ int ml_engine_profile_get(ml_engine* eng, int i, char* name, int name_cap, doubl
   if (launches) *launches = it->second.second;
   return ML_OK;
 }
+int ml_engine_profile_work(ml_engine* eng, int i, double* bytes) {
+  if (!eng || !bytes || i < 0 || i >= (int)eng->e.prof.acc.size()) return fail(ML_ERR_BAD_ARGUMENT, "bad profile index");
+  auto it = eng->e.prof.acc.begin();
+  std::advance(it, i);
+  auto w = eng->e.prof.work.find(it->first);
+  *bytes = w == eng->e.prof.work.end() ? -1.0 : w->second;
+  return ML_OK;
+}
 int ml_engine_profile_reset(ml_engine* eng) {
   if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
   ML_TRY

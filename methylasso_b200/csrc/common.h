@@ -35,6 +35,8 @@ struct Profiler {
   std::vector<Rec> pending;
   std::vector<cudaEvent_t> pool;
   std::map<std::string, std::pair<double, long long>> acc;  // name -> (total ms, launches)
+  std::map<std::string, double> work;   // name -> algorithmic bytes moved, for kernels whose work is data-dependent
+  void add_work(const char* name, double bytes) { if (on) work[name] += bytes; }
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
     cudaEvent_t e;
@@ -64,7 +66,7 @@ struct Profiler {
     }
     pending.clear();
   }
-  void reset() { collect(); acc.clear(); }
+  void reset() { collect(); acc.clear(); work.clear(); }
   ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
 
