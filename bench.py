@@ -228,6 +228,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-groups", type=int, default=6,
                     help="engines (streams + host threads) the e2e step spreads the chromosomes over; 1 = single call")
+    ap.add_argument("--resident-groups", type=int, default=0,
+                    help="> 1: also time the resident step with the chromosomes spread over this many engines")
     ap.add_argument("--e2e-edge", type=float, default=0.0,
                     help="share of the rows given to the first and to the last group of the e2e pipeline (0 = balanced)")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
@@ -324,6 +326,49 @@ def main():
     if world > 1:
         dist.all_reduce(u_all, op=dist.ReduceOp.SUM)
     value = float(u_all.item()) / (ms_max * 1e-3)
+
+    # ---- resident inputs, chromosomes spread over several engines (streams + host threads) ---------
+    # The latency-bound phases of one group (FLSA left-neighbour rounds, PMD chains, host round trips) overlap
+    # with the bandwidth-bound kernels of the others.
+    resident_pool = None
+    if args.resident_groups > 1:
+        Gr = args.resident_groups
+        rpool = api.EnginePool(Gr, local)
+        rgroups = []
+        for k, (jobs, gptr, gcols) in enumerate(api.split_jobs(ptr, cols, Gr)):
+            rgroups.append((rpool.engines[k % Gr].upload(gptr, gcols), jobs))
+
+        def run_group_resident(eng_g, grp):
+            bt, jobs = grp
+            rr = eng_g.detect(bt, params)
+            ns = rr.segments_count(TOL)
+            npm = rr.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+            rr.free()
+            eng_g.synchronize()
+            return ns, npm
+        for _ in range(max(3, args.warmup)):
+            outs_r = rpool.map(run_group_resident, rgroups)
+        for e_g in rpool.engines:
+            e_g.set("pool_headroom_percent", 10)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lr0 = sum(e_g.launch_count for e_g in rpool.engines)
+        r0.record(stream)
+        for _ in range(args.steps):
+            outs_r = rpool.map(run_group_resident, rgroups)
+        torch.cuda.synchronize()
+        r1.record(stream)
+        barrier()
+        rms = r0.elapsed_time(r1) / args.steps
+        t3 = torch.tensor([rms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        resident_pool = {"engines": Gr, "ms_per_step": float(t3.item()), "value": float(u_all.item()) / (float(t3.item()) * 1e-3),
+                         "unit": "CpG/s", "gpu_launches": int(sum(e_g.launch_count for e_g in rpool.engines) - lr0),
+                         "segments": [int(sum(o[0] for o in outs_r)), int(sum(o[1] for o in outs_r))]}
+        for bt, _ in rgroups:
+            bt.free()
+        rpool.close()
 
     # ---- e2e: host buffers through the C ABI -------------------------------------------------------
     e2e = None
@@ -465,7 +510,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16],
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16], "resident_pipelined": resident_pool,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
         }

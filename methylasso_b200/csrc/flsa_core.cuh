@@ -132,6 +132,18 @@ ML_HD void knots_init_bound(Knots<Ring>& q, int sign, double lam) {
   q.ring.set(0, x0, 0.0, 2 * lam);
 }
 
+// The knot quotient num / a.  A zero numerator is common on methylation data (an unmethylated position has
+// y == 0, so b == -lam exactly and num == -lam - b == +0) and sends the device's IEEE division down its slow
+// path (a ~150-instruction subroutine, taken by a fifth of all warp-steps of the first main pass).  The quotient
+// of a zero by a non-zero, non-NaN divisor is a zero whose sign is the product of the signs: same bits, no call.
+ML_HD double knot_div(double num, double a) {
+#ifdef __CUDA_ARCH__
+  if (num == 0.0 && a != 0.0 && a == a)
+    return __longlong_as_double((__double_as_longlong(num) ^ __double_as_longlong(a)) & (long long)0x8000000000000000ull);
+#endif
+  return num / a;
+}
+
 // ---- one DP step, side-symmetric ------------------------------------------------------------
 // The reference scans the window from the left (gfl_tf.c:251-258) and from the right (:262-269)
 // with mirrored formulas.  Because IEEE rounding is sign-symmetric the right scan is the SAME
@@ -171,8 +183,8 @@ ML_HD bool dp_step(Knots<Ring>& q, double y, double w, double lam, double& tm, d
     br = w * y - lam;
     hi = side_scan(q.ring, q.r, -1, lo, ar, br, lam);
   }
-  tm = (-lam - bl) / al;                   // :272
-  tp = (-lam - br) / ar;                   // :277, (lam + bhi) / (-ahi) bit for bit
+  tm = knot_div(-lam - bl, al);            // :272
+  tp = knot_div(-lam - br, ar);            // :277, (lam + bhi) / (-ahi) bit for bit
   const int nl = lo - 1, nr = hi + 1;
   if (nr - nl + 1 > Ring::CAP) return false;
   q.ring.set(nl, tm, al, bl + lam);        // :282-285
