@@ -215,6 +215,40 @@ ML_API int ml_result_pmd_segments(ml_engine *eng, ml_result *r, double tol_val, 
                                   uint32_t *seg_end, double *seg_fused_std, double *seg_std,
                                   double *seg_pseudoweight);
 
+/* The per-segment call table of R/call.R:43-68 (segment_methylation_singlechr, before the rule engine), resident:
+ * the helper's segments (tol_val) are matched with the pooled per-position data of their condition as
+ * foverlaps does (CpG p belongs to segment [start, end] iff start - 1 <= p <= end), split at gaps larger than
+ * max_distance (:59-61, segment ids shift by the number of gaps so far in the condition), shrunk to
+ * start = min(pos), end = max(pos) + 2, width = end - start + 1 (:64-65), and summarised: beta = mean(Nmeth/coverage),
+ * coverage = sum, pseudoweight = the segment's, num_cpgs, std = sd(Nmeth/coverage) with NA -> 0 (:68-72; R's
+ * two-pass long-double mean / sd reproduced with double-double sums).  Needs a FAST result with max_iter = 1
+ * (there betahat * pseudoweight are the pooled methylated counts exactly).  Every output may be NULL; query
+ * *n_rows first.  Rows are ordered by (job, estimate, start). */
+ML_API int ml_result_call_table(ml_engine *eng, ml_result *r, double tol_val, double max_distance, int64_t *n_rows,
+                                int32_t *job, int32_t *estimate_id, int32_t *segment_id, uint32_t *start,
+                                uint32_t *end, double *width, double *beta, double *coverage,
+                                double *pseudoweight, int32_t *num_cpgs, double *std);
+
+/* R/call.R:93-95 on that call table, i.e. with the reference's own inputs: fused = weighted_1d_flsa(std, width,
+ * pmd_lambda2) per (job, condition), then segment_methylation_helper on (estimate_id, start, beta = fused,
+ * betahat = std, pseudoweight).  fused_std (may be NULL) has one entry per call-table row. */
+ML_API int ml_result_call_pmd_segments(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                       double pmd_lambda2, int64_t *n_segments, double *fused_std,
+                                       int32_t *seg_job, int32_t *seg_estimate_id, int32_t *seg_id,
+                                       uint32_t *seg_start, uint32_t *seg_end, double *seg_fused_std,
+                                       double *seg_std, double *seg_pseudoweight);
+
+/* The same call table from host tables (any model): pooled rows (estimate_id, pos, Nmeth, coverage) sorted by
+ * (estimate_id, pos) as R/call.R:43-46 builds them, and the segment table of segment_methylation_helper.  Outputs
+ * need capacity n. */
+ML_API int ml_segment_call_table(ml_engine *eng, int64_t n, const int32_t *estimate_id, const int32_t *pos,
+                                 const int32_t *nmeth, const int32_t *coverage, int64_t n_seg,
+                                 const int32_t *seg_estimate_id, const int32_t *seg_id, const uint32_t *seg_start,
+                                 const uint32_t *seg_end, const double *seg_pseudoweight, double max_distance,
+                                 int64_t *n_rows, int32_t *o_estimate_id, int32_t *o_segment_id, uint32_t *o_start,
+                                 uint32_t *o_end, double *o_width, double *o_beta, double *o_coverage,
+                                 double *o_pseudoweight, int32_t *o_num_cpgs, double *o_std);
+
 #ifdef __cplusplus
 }
 #endif

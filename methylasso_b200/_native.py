@@ -64,6 +64,9 @@ SIGNATURES = {
     "ml_segment_methylation_helper": (C.c_int, [_P, C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 8),
     "ml_result_segments": (C.c_int, [_P, _P, C.c_double, _I64P] + [_P] * 9),
     "ml_result_pmd_segments": (C.c_int, [_P, _P, C.c_double, C.c_double, _I64P] + [_P] * 9),
+    "ml_result_call_table": (C.c_int, [_P, _P, C.c_double, C.c_double, _I64P] + [_P] * 11),
+    "ml_result_call_pmd_segments": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, _I64P] + [_P] * 9),
+    "ml_segment_call_table": (C.c_int, [_P, C.c_int64] + [_P] * 4 + [C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 10),
 }
 
 _lib = None

@@ -112,6 +112,23 @@ class Engine:
     def profile_reset(self):
         self._check(self.lib.ml_engine_profile_reset(self.h))
 
+    def segment_call_table(self, pooled, seg, max_distance=500.0):
+        """R/call.R:43-68 from host tables: pooled = dict(estimate_id, pos, Nmeth, coverage) per position and
+        condition sorted by (estimate_id, pos); seg = the table of segment_methylation_helper."""
+        e, p, m, c = (np.ascontiguousarray(pooled[k], np.int32) for k in ("estimate_id", "pos", "Nmeth", "coverage"))
+        se = np.ascontiguousarray(seg["estimate_id"], np.int32)
+        si = np.ascontiguousarray(seg["segment_id"], np.int32)
+        ss = np.ascontiguousarray(seg["start"], np.uint32)
+        sn = np.ascontiguousarray(seg["end"], np.uint32)
+        sp = _f64(seg["pseudoweight"])
+        cols = [(k, dt) for k, dt in Result.CALL_COLUMNS if k != "job"]
+        out = {k: np.empty(max(e.size, 1), dt) for k, dt in cols}
+        n = C.c_int64(0)
+        self._check(self.lib.ml_segment_call_table(self.h, e.size, _p(e), _p(p), _p(m), _p(c), se.size, _p(se), _p(si),
+                                                   _p(ss), _p(sn), _p(sp), float(max_distance), C.byref(n),
+                                                   *[_p(out[k]) for k, _ in cols]))
+        return {k: v[:n.value].copy() for k, v in out.items()}
+
     # ---- weighted_1d_flsa ---------------------------------------------------------------------
     def weighted_1d_flsa(self, y, wt, lambda2, lambda1=0.0):
         y, wt = _f64(y), _f64(wt)
@@ -301,6 +318,43 @@ class Result:
             *[_p(out[k]) for k in ("job", "estimate_id", "segment_id", "start", "end", "fused_std", "std",
                                    "pseudoweight")]))
         return {k: v[:ns.value].copy() for k, v in out.items()}
+
+    CALL_COLUMNS = (("job", np.int32), ("estimate_id", np.int32), ("segment_id", np.int32), ("start", np.uint32),
+                    ("end", np.uint32), ("width", np.float64), ("beta", np.float64), ("coverage", np.float64),
+                    ("pseudoweight", np.float64), ("num_cpgs", np.int32), ("std", np.float64))
+
+    def call_table(self, tol_val=0.01, max_distance=500.0, fetch=True):
+        """R/call.R:43-68 on the resident result (see ml_result_call_table): one row per gap-split segment."""
+        n = C.c_int64(0)
+        self.eng._check(self.eng.lib.ml_result_call_table(self.eng.h, self.h, float(tol_val), float(max_distance),
+                                                          C.byref(n), *([None] * 11)))
+        if not fetch:
+            return n.value
+        out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.CALL_COLUMNS}
+        self.eng._check(self.eng.lib.ml_result_call_table(self.eng.h, self.h, float(tol_val), float(max_distance),
+                                                          C.byref(n), *[_p(out[k]) for k, _ in self.CALL_COLUMNS]))
+        return {k: v[:n.value].copy() for k, v in out.items()}
+
+    def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
+        """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
+        ns = C.c_int64(0)
+        args = (self.eng.h, self.h, float(tol_val), float(max_distance), float(pmd_lambda2))
+        self.eng._check(self.eng.lib.ml_result_call_pmd_segments(*args, C.byref(ns), *([None] * 9)))
+        if not fetch:
+            return ns.value
+        n = max(ns.value, 1)
+        out = dict(job=np.empty(n, np.int32), estimate_id=np.empty(n, np.int32), segment_id=np.empty(n, np.int32),
+                   start=np.empty(n, np.uint32), end=np.empty(n, np.uint32), fused_std=np.empty(n),
+                   std=np.empty(n), pseudoweight=np.empty(n))
+        fused = np.empty(max(self.call_table(tol_val, max_distance, fetch=False), 1)) if want_fused else None
+        self.eng._check(self.eng.lib.ml_result_call_pmd_segments(
+            *args, C.byref(ns), _p(fused) if want_fused else None,
+            *[_p(out[k]) for k in ("job", "estimate_id", "segment_id", "start", "end", "fused_std", "std",
+                                   "pseudoweight")]))
+        res = {k: v[:ns.value].copy() for k, v in out.items()}
+        if want_fused:
+            res["row_fused_std"] = fused[:self.call_table(tol_val, max_distance, fetch=False)]
+        return res
 
 
 class EnginePool:

@@ -481,9 +481,17 @@ static int result_copy_all(ml_engine* eng, const ml_result* r, double* mu, doubl
   tls_pool() = eng->e.pool;
   tls_mailbox() = &eng->e.mailbox;
   const Result& R = *r->r;
-  // the result is complete (detect synchronised); the asynchronous variant copies on the engine's
-  // copy stream so that later compute calls on the main stream overlap with the transfer
+  // The asynchronous variant copies on the engine's copy stream, so that later compute calls on the main
+  // stream overlap with the transfer; the copy stream first waits for whatever the main stream still has
+  // in flight for this result (ml_batch_detect does not synchronise at its end).
   cudaStream_t st = async ? eng->e.copy_stream : eng->e.stream;
+  if (async) {
+    cudaEvent_t ready;
+    ML_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    ML_CUDA(cudaEventRecord(ready, eng->e.stream));
+    ML_CUDA(cudaStreamWaitEvent(st, ready, 0));
+    ML_CUDA(cudaEventDestroy(ready));
+  }
   // parameter arrays and offsets of the valid jobs are already contiguous in job order.  The tiny
   // offset copy goes first: if its destination is pageable the call blocks until everything queued
   // before it on this stream has completed.
@@ -630,6 +638,172 @@ int ml_result_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double 
   ho.job = seg_job; ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
   ho.beta = seg_fused_std; ho.betahat = seg_std; ho.pseudoweight = seg_pseudoweight;
   if (P.n > 0) P.download(st, P.n, ho);
+  stream_sync(st);
+  return ML_OK;
+  ML_CATCH
+}
+
+// ---- call table (R/call.R:43-68) --------------------------------------------------------------------
+namespace {
+struct CallHostOut {
+  int32_t *job, *estimate_id, *seg_id;
+  uint32_t *start, *end;
+  double *width, *beta, *coverage, *pseudoweight;
+  int32_t* num_cpgs;
+  double* std_;
+};
+void call_download(const CallTable& c, const CallHostOut& h) {
+  const size_t n = (size_t)c.t.n;
+  if (!n) return;
+  if (h.job) c.t.job.download(h.job, n);
+  if (h.estimate_id) c.t.estimate_id.download(h.estimate_id, n);
+  if (h.seg_id) c.t.seg_id.download(h.seg_id, n);
+  if (h.start) c.t.start.download(h.start, n);
+  if (h.end) c.t.end.download(h.end, n);
+  if (h.width) c.width.download(h.width, n);
+  if (h.beta) c.t.beta.download(h.beta, n);
+  if (h.coverage) c.coverage.download(h.coverage, n);
+  if (h.pseudoweight) c.t.pseudoweight.download(h.pseudoweight, n);
+  if (h.num_cpgs) c.num_cpgs.download(h.num_cpgs, n);
+  if (h.std_) c.t.stdev.download(h.std_, n);
+}
+std::vector<SegGroup> result_groups(const Result& R) {
+  std::vector<SegGroup> groups;
+  for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
+    const JobHost& j = R.jobs[jn];
+    if (j.status) continue;
+    for (int e = 0; e < j.E; ++e)
+      groups.push_back(SegGroup{j.par0 + (int64_t)e * j.P, j.P, R.start0[jn], e + 1, (int32_t)jn});
+  }
+  return groups;
+}
+int ensure_call_table(ml_engine* eng, ml_result* r, double tol_val, double max_distance) {
+  Result& R = *r->r;
+  if (!R.counts_exact)
+    return fail(ML_ERR_BAD_ARGUMENT, "the resident call table needs a FAST result with max_iter = 1 (pooled counts are "
+                                     "recovered from betahat * pseudoweight); use ml_segment_call_table otherwise");
+  if (!R.seg_cache || R.seg_tol != tol_val) {
+    int64_t ns = 0;
+    const int rc = ml_result_segments(eng, r, tol_val, &ns, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                      nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    R.call_cache.reset();
+  }
+  if (!R.call_cache || R.call_tol != tol_val || R.call_max_distance != max_distance) {
+    auto c = std::make_unique<CallTable>();
+    call_table_from_estimates(eng->e, result_groups(R), *R.seg_cache, R.start.p, 1, R.betahat.p, R.pw.p, max_distance, *c);
+    R.call_cache = std::move(c);
+    R.call_tol = tol_val;
+    R.call_max_distance = max_distance;
+    R.call_pmd_cache.reset();
+  }
+  return ML_OK;
+}
+}  // namespace
+
+int ml_result_call_table(ml_engine* eng, ml_result* r, double tol_val, double max_distance, int64_t* n_rows,
+                         int32_t* job, int32_t* estimate_id, int32_t* segment_id, uint32_t* start, uint32_t* end,
+                         double* width, double* beta, double* coverage, double* pseudoweight, int32_t* num_cpgs,
+                         double* std_) {
+  if (!eng || !r || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  const int rc = ensure_call_table(eng, r, tol_val, max_distance);
+  if (rc) return rc;
+  const CallTable& c = *r->r->call_cache;
+  *n_rows = c.t.n;
+  call_download(c, CallHostOut{job, estimate_id, segment_id, start, end, width, beta, coverage, pseudoweight, num_cpgs, std_});
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_result_call_pmd_segments(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
+                                int64_t* n_segments, double* fused_std, int32_t* seg_job, int32_t* seg_estimate_id,
+                                int32_t* seg_id, uint32_t* seg_start, uint32_t* seg_end, double* seg_fused_std,
+                                double* seg_std, double* seg_pseudoweight) {
+  if (!eng || !r || !n_segments) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  const int rc = ensure_call_table(eng, r, tol_val, max_distance);
+  if (rc) return rc;
+  Result& R = *r->r;
+  const CallTable& c = *R.call_cache;
+  cudaStream_t st = eng->e.stream;
+  if (!R.call_pmd_cache || R.call_pmd_lambda2 != pmd_lambda2) {
+    auto out = std::make_unique<SegDeviceOut>();
+    out->n = pmd_segments_device(eng->e, c.t, pmd_lambda2, tol_val, R.call_pmd_fused, *out);
+    R.call_pmd_cache = std::move(out);
+    R.call_pmd_lambda2 = pmd_lambda2;
+  }
+  const SegDeviceOut& P = *R.call_pmd_cache;
+  *n_segments = P.n;
+  if (fused_std && c.t.n) R.call_pmd_fused.download(fused_std, (size_t)c.t.n);
+  SegHostOut ho;
+  ho.job = seg_job; ho.estimate_id = seg_estimate_id; ho.seg_id = seg_id; ho.start = seg_start; ho.end = seg_end;
+  ho.beta = seg_fused_std; ho.betahat = seg_std; ho.pseudoweight = seg_pseudoweight;
+  if (P.n > 0) P.download(st, P.n, ho);
+  stream_sync(st);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_segment_call_table(ml_engine* eng, int64_t n, const int32_t* estimate_id, const int32_t* pos, const int32_t* nmeth,
+                          const int32_t* coverage, int64_t n_seg, const int32_t* seg_estimate_id, const int32_t* seg_id,
+                          const uint32_t* seg_start, const uint32_t* seg_end, const double* seg_pseudoweight,
+                          double max_distance, int64_t* n_rows, int32_t* o_estimate_id, int32_t* o_segment_id,
+                          uint32_t* o_start, uint32_t* o_end, double* o_width, double* o_beta, double* o_coverage,
+                          double* o_pseudoweight, int32_t* o_num_cpgs, double* o_std) {
+  if (!eng || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  if (n <= 0 || n_seg <= 0 || !estimate_id || !pos || !nmeth || !coverage || !seg_estimate_id || !seg_id || !seg_start ||
+      !seg_end || !seg_pseudoweight)
+    return fail(ML_ERR_BAD_ARGUMENT, "the call table needs non-empty pooled rows and segments");
+  if (n >= 0x7fffffff || n_seg >= 0x7fffffff) return fail(ML_ERR_BAD_ARGUMENT, "table too large");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  Engine& e = eng->e;
+  cudaStream_t st = e.stream;
+  // groups = blocks of equal estimate id, which must appear in the same order in both tables
+  std::vector<SegGroup> groups;
+  SegDeviceOut seg;
+  seg.group_seg0.clear();
+  int64_t r0 = 0, s0 = 0;
+  while (s0 < n_seg) {
+    const int32_t est = seg_estimate_id[s0];
+    int64_t s1 = s0;
+    while (s1 < n_seg && seg_estimate_id[s1] == est) ++s1;
+    while (r0 < n && estimate_id[r0] != est) ++r0;
+    int64_t r1 = r0;
+    while (r1 < n && estimate_id[r1] == est) ++r1;
+    if (r1 == r0) throw MlError(ML_ERR_BAD_ARGUMENT, "a segment's estimate_id has no rows (tables must be sorted by estimate_id)");
+    groups.push_back(SegGroup{r0, r1 - r0, r0, est, 0});
+    seg.group_seg0.push_back((int32_t)s0);
+    seg.group_job.push_back(0);
+    seg.group_est.push_back(est);
+    r0 = r1;
+    s0 = s1;
+  }
+  seg.group_seg0.push_back((int32_t)n_seg);
+  seg.alloc(st, n_seg);
+  seg.seg_id.upload(seg_id, (size_t)n_seg);
+  seg.start.upload(seg_start, (size_t)n_seg);
+  seg.end.upload(seg_end, (size_t)n_seg);
+  seg.pseudoweight.upload(seg_pseudoweight, (size_t)n_seg);
+  DevBuf<int32_t> d_pos(st, (size_t)n), d_nm(st, (size_t)n), d_cov(st, (size_t)n);
+  d_pos.upload(pos, (size_t)n);
+  d_nm.upload(nmeth, (size_t)n);
+  d_cov.upload(coverage, (size_t)n);
+  CallTable c;
+  call_table_from_counts(e, groups, seg, d_pos.p, d_nm.p, d_cov.p, max_distance, c);
+  *n_rows = c.t.n;
+  call_download(c, CallHostOut{nullptr, o_estimate_id, o_segment_id, o_start, o_end, o_width, o_beta, o_coverage,
+                               o_pseudoweight, o_num_cpgs, o_std});
   stream_sync(st);
   return ML_OK;
   ML_CATCH

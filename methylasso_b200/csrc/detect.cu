@@ -1231,7 +1231,9 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   }
   res->est_id.alloc(st, (size_t)std::max<int64_t>(1, npar));
   if (n_pt) ML_LAUNCH(eng, "k_fill_estimate_id", k_fill_estimate_id<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, res->est_id.p));
-  stream_sync(st);
+  res->counts_exact = fast && p.max_iter == 1;
+  // no synchronisation here: every host decision has been taken, the scratch buffers are freed in stream
+  // order, and whatever reads the result next (copy, segmentation) is enqueued on the same stream
   return res;
 }
 

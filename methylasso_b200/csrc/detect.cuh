@@ -95,6 +95,13 @@ struct Result {
   std::unique_ptr<SegDeviceOut> pmd_cache;
   DevBuf<double> pmd_fused;
   double pmd_tol = 0, pmd_lambda2 = 0;
+  // call table of R/call.R:43-68 (and the PMD re-segmentation computed from it)
+  std::unique_ptr<CallTable> call_cache;
+  double call_tol = 0, call_max_distance = 0;
+  std::unique_ptr<SegDeviceOut> call_pmd_cache;
+  DevBuf<double> call_pmd_fused;
+  double call_pmd_lambda2 = 0;
+  bool counts_exact = false;   // FAST model, one IRLS step: betahat * pw are the pooled methylated counts
 };
 
 std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,

@@ -261,6 +261,159 @@ __global__ void k_pmd_inputs(int64_t n, const uint32_t* __restrict__ start, cons
   start_i32[i] = (int32_t)start[i];
 }
 
+
+// ---- call table (R/call.R:43-68) ----------------------------------------------------------------
+// Where the per-position methylation value and coverage of a row come from.
+struct RowsFromEstimates {   // FAST result: betahat = pooled Nmeth / pooled coverage, pw = pooled coverage (exact
+  const double* betahat;     // integers in double): Nmeth = rint(betahat * pw) recovers the pooled count exactly,
+  const double* pw;          // and Nmeth / pw is then R's own `Nmeth/coverage`.  Parameters without data in this
+  __device__ bool valid(int64_t i) const { return pw[i] > 0; }         // condition (pw == 0) are not rows of mdata.
+  __device__ double cov(int64_t i) const { return pw[i]; }
+  __device__ double x(int64_t i) const { return rint(betahat[i] * pw[i]) / pw[i]; }
+};
+struct RowsFromCounts {      // host table: pooled Nmeth, coverage per position as given
+  const int32_t* nmeth;
+  const int32_t* coverage;
+  __device__ bool valid(int64_t) const { return true; }
+  __device__ double cov(int64_t i) const { return (double)coverage[i]; }
+  __device__ double x(int64_t i) const { return (double)nmeth[i] / (double)coverage[i]; }
+};
+
+// double-double accumulator standing in for R's long double sums (summary.c real_mean, cov.c)
+struct DD { double hi, lo; };
+__device__ __forceinline__ void dd_add(DD& a, double x) {
+  const double s = a.hi + x;
+  const double bb = s - a.hi;
+  a.lo += (a.hi - (s - bb)) + (x - bb);
+  a.hi = s;
+}
+
+__device__ __forceinline__ int group_of_segment(const int32_t* __restrict__ group_seg0, int ng, int s) {
+  int lo = 0, hi = ng;       // last group with group_seg0[g] <= s
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (group_seg0[mid] <= s) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// rows of segment s: start_s - 1 <= pos <= end_s within its group (foverlaps of [pos, pos+1] with [start, end])
+__device__ __forceinline__ void segment_rows(const SegGroup& G, const void* pos, int pos_f64, uint32_t s0, uint32_t s1,
+                                             int64_t& lo, int64_t& hi) {
+  const int64_t want_lo = (int64_t)s0 - 1, want_hi = (int64_t)s1;
+  int64_t a = G.row0, b = G.row0 + G.nrows;
+  while (a < b) { const int64_t m = (a + b) >> 1; if ((int64_t)seg_start_at(G, pos, pos_f64, m) < want_lo) a = m + 1; else b = m; }
+  lo = a;
+  b = G.row0 + G.nrows;
+  while (a < b) { const int64_t m = (a + b) >> 1; if ((int64_t)seg_start_at(G, pos, pos_f64, m) <= want_hi) a = m + 1; else b = m; }
+  hi = a;
+}
+
+// pass 1: number of parts (maximal runs without a gap > max_distance) and of oversize gaps per segment
+template <class Rows>
+__global__ void k_call_count(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0, int ng,
+                             int n_segs, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_end,
+                             const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+                             int32_t* __restrict__ parts, int32_t* __restrict__ gaps) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs) return;
+  int np = 0;
+  if (seg_start[s] <= seg_end[s]) {                          // sg <- segmentation[start <= end]
+    const SegGroup G = groups[group_of_segment(group_seg0, ng, s)];
+    int64_t lo, hi;
+    segment_rows(G, pos, pos_f64, seg_start[s], seg_end[s], lo, hi);
+    double prev = 0;
+    for (int64_t i = lo; i < hi; ++i) {
+      if (!rows.valid(i)) continue;
+      const double p = (double)seg_start_at(G, pos, pos_f64, i);
+      if (np == 0 || p - prev > max_distance) ++np;
+      prev = p;
+    }
+  }
+  parts[s] = np;
+  gaps[s] = np > 0 ? np - 1 : 0;
+}
+
+struct CallOut {
+  SegOut t;
+  double *coverage, *width;
+  int32_t* num_cpgs;
+};
+
+// pass 2: one thread per segment emits its parts; sums run in row order (mean refined by a second pass and
+// the squares taken about that mean, as R's mean() and sd() do)
+template <class Rows>
+__global__ void k_call_emit(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0, int ng,
+                            int n_segs, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_end,
+                            const int32_t* __restrict__ seg_id, const double* __restrict__ seg_pw,
+                            const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+                            const int32_t* __restrict__ part_off, const int32_t* __restrict__ gap_off, CallOut out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_segs || seg_start[s] > seg_end[s]) return;
+  const int g = group_of_segment(group_seg0, ng, s);
+  const SegGroup G = groups[g];
+  int64_t lo, hi;
+  segment_rows(G, pos, pos_f64, seg_start[s], seg_end[s], lo, hi);
+  int o = part_off[s];
+  int shift = gap_off[s] - gap_off[group_seg0[g]];
+  int64_t a = lo;
+  while (a < hi && !rows.valid(a)) ++a;
+  bool first_part = true;
+  while (a < hi) {
+    // part [a, b): valid rows until the first oversize gap
+    DD sum{0.0, 0.0};
+    double csum = 0.0, prev = (double)seg_start_at(G, pos, pos_f64, a);
+    const double p0 = prev;
+    int m = 0;
+    int64_t b = a;
+    for (; b < hi; ++b) {
+      if (!rows.valid(b)) continue;
+      const double p = (double)seg_start_at(G, pos, pos_f64, b);
+      if (m > 0 && p - prev > max_distance) break;
+      dd_add(sum, rows.x(b));
+      csum += rows.cov(b);
+      prev = p;
+      ++m;
+    }
+    if (!first_part) ++shift;
+    first_part = false;
+    double mean = (sum.hi + sum.lo) / m;
+    if (is_finite(mean)) {
+      DD t{0.0, 0.0};
+      for (int64_t i = a; i < b; ++i) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+      mean += (t.hi + t.lo) / m;
+    }
+    double sd = 0.0;
+    if (m >= 2) {
+      DD ss{0.0, 0.0};
+      for (int64_t i = a; i < b; ++i) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
+      sd = sqrt((ss.hi + ss.lo) / (m - 1));
+    }
+    if (out.t.job) out.t.job[o] = G.job;
+    out.t.estimate_id[o] = G.estimate_id;
+    out.t.seg_id[o] = seg_id[s] + shift;
+    out.t.start[o] = (uint32_t)p0;
+    out.t.end[o] = (uint32_t)prev + 2u;
+    out.width[o] = ((double)prev + 2.0) - p0 + 1.0;
+    out.t.beta[o] = mean;
+    out.t.betahat[o] = mean;
+    out.t.pseudoweight[o] = seg_pw[s];
+    out.t.stdev[o] = sd;
+    out.coverage[o] = csum;
+    out.num_cpgs[o] = m;
+    ++o;
+    a = b;
+  }
+}
+
+// first row of the call table of every group (and the total as a sentinel)
+__global__ void k_call_group0(const int32_t* __restrict__ group_seg0, int ng, int n_segs, const int32_t* __restrict__ part_off,
+                              int32_t total, int32_t* __restrict__ g0) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g > ng) return;
+  const int s = g < ng ? group_seg0[g] : n_segs;
+  g0[g] = s < n_segs ? part_off[s] : total;
+}
 }  // namespace
 
 // std fusion + re-segmentation of a segment table (R/call.R:93-95): fused = weighted_1d_flsa(std,
@@ -288,6 +441,60 @@ int64_t pmd_segments_device(Engine& eng, const SegDeviceOut& seg, double pmd_lam
   plan.solve(y.p, w.p, fused.p, 1, 0.0, nullptr);
   const int64_t S = segment_device(eng, groups, n, start_i32.p, 0, fused.p, y.p, seg.pseudoweight.p, tol_val, out);
   return S;
+}
+
+// Per-segment call table (R/call.R:43-68) from the helper's segments `seg` and the per-position rows they were
+// computed on.  `groups` are the row groups the segmentation ran on, in the same order as seg.group_*.
+template <class Rows>
+static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_in, const SegDeviceOut& seg,
+                               const void* d_pos, int pos_f64, Rows rows, double max_distance, CallTable& out) {
+  cudaStream_t st = eng.stream;
+  std::vector<SegGroup> groups;
+  for (const SegGroup& g : groups_in)
+    if (g.nrows > 0) groups.push_back(g);
+  const int ng = (int)groups.size();
+  const int n_segs = (int)seg.n;
+  if (ng == 0 || n_segs == 0) { out.t.alloc(st, 0); out.t.group_seg0.assign(1, 0); return 0; }
+  if ((int)seg.group_seg0.size() != ng + 1) throw MlError(19, "call table: segments and row groups do not match");
+  DevBuf<SegGroup> d_groups(st, ng);
+  d_groups.upload(groups);
+  DevBuf<int32_t> d_g0(st, ng + 1);
+  d_g0.upload(seg.group_seg0);
+  DevBuf<int32_t> parts(st, n_segs), gaps(st, n_segs), part_off(st, n_segs), gap_off(st, n_segs);
+  ML_LAUNCH(eng, "k_call_count", k_call_count<Rows><<<cdiv(n_segs, 128), 128, 0, st>>>(
+      d_groups.p, d_g0.p, ng, n_segs, seg.start.p, seg.end.p, d_pos, pos_f64, rows, max_distance, parts.p, gaps.p));
+  Scan scan;
+  scan.run(eng, gaps.p, n_segs, gap_off.p, nullptr);
+  const int32_t total = scan.run(eng, parts.p, n_segs, part_off.p, nullptr);
+  out.t.alloc(st, total);
+  out.coverage.alloc(st, (size_t)std::max(1, total));
+  out.width.alloc(st, (size_t)std::max(1, total));
+  out.num_cpgs.alloc(st, (size_t)std::max(1, total));
+  CallOut co{out.t.view(), out.coverage.p, out.width.p, out.num_cpgs.p};
+  ML_LAUNCH(eng, "k_call_emit", k_call_emit<Rows><<<cdiv(n_segs, 128), 128, 0, st>>>(
+      d_groups.p, d_g0.p, ng, n_segs, seg.start.p, seg.end.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
+      max_distance, part_off.p, gap_off.p, co));
+  DevBuf<int32_t> d_c0(st, ng + 1);
+  ML_LAUNCH(eng, "k_call_group0", k_call_group0<<<cdiv(ng + 1, 128), 128, 0, st>>>(d_g0.p, ng, n_segs, part_off.p, total, d_c0.p));
+  std::vector<int32_t> c0(ng + 1);
+  d_c0.download(c0.data(), ng + 1);
+  stream_sync(st);
+  out.t.group_seg0.assign(c0.begin(), c0.end());
+  out.t.group_job = seg.group_job;
+  out.t.group_est = seg.group_est;
+  return total;
+}
+
+int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
+                                  const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,
+                                  double max_distance, CallTable& out) {
+  return call_table_impl(eng, groups, seg, d_pos, pos_f64, RowsFromEstimates{d_betahat, d_pw}, max_distance, out);
+}
+
+int64_t call_table_from_counts(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
+                               const int32_t* d_pos, const int32_t* d_nmeth, const int32_t* d_cov,
+                               double max_distance, CallTable& out) {
+  return call_table_impl(eng, groups, seg, d_pos, 0, RowsFromCounts{d_nmeth, d_cov}, max_distance, out);
 }
 
 // Core: groups over device arrays -> segments in device buffers owned by `ds`.

@@ -53,6 +53,20 @@ struct SegDeviceOut {
   }
 };
 
+// Call table of R/call.R:43-68: `t` holds estimate_id, seg_id, start, end, beta (mean methylation), pseudoweight and
+// stdev (sample sd, 0 for single-CpG rows) per gap-split segment; coverage / width / num_cpgs complete the row.
+struct CallTable {
+  SegDeviceOut t;
+  DevBuf<double> coverage, width;
+  DevBuf<int32_t> num_cpgs;
+};
+int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
+                                  const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,
+                                  double max_distance, CallTable& out);
+int64_t call_table_from_counts(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
+                               const int32_t* d_pos, const int32_t* d_nmeth, const int32_t* d_cov,
+                               double max_distance, CallTable& out);
+
 int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups, int64_t nrows, const void* d_start,
                        int start_f64, const double* d_beta, const double* d_betahat, const double* d_pw,
                        double tol_val, SegDeviceOut& out);

@@ -755,3 +755,73 @@ int orc_fast_diff_combine(int64_t P, int32_t E, const double *beta, const double
     }
   return ORC_OK;
 }
+
+/* R/call.R:43-68 (segment_methylation_singlechr), the per-segment call table:
+ *   ov = foverlaps(mdata[pos, pos+1], segmentation[start, end])   -> CpG p belongs to segment s of its estimate
+ *                                                                    iff start_s - 1 <= p <= end_s (type "any")
+ *   is.oversize = pos - shift(pos) > max_distance within a segment (:59-60)
+ *   segment_id += cumsum(is.oversize) over the estimate (:61)
+ *   start = min(pos), end = max(pos) + 2, width = end - start + 1 by (estimate, segment_id) (:64-65)
+ *   beta = mean(Nmeth/coverage), coverage = sum(coverage), pseudoweight = pseudoweight[1],
+ *   num.cpgs = length(unique(pos)), std = sd(Nmeth/coverage), NA -> 0 (:68-72)
+ * Rows are the per-position data pooled per condition (:43-46), sorted by (estimate, pos); segments are the
+ * helper's table sorted by (estimate, start).  mean() and sd() follow R's own algorithms (summary.c real_mean,
+ * cov.c: long double accumulation, mean refined by a second pass, sum of squares about that mean / (n-1)).
+ * R itself is not in this image: this function is a restatement of the R lines, NOT pinned against R. */
+int64_t orc_call_table(int64_t n, const int32_t *est_id, const int32_t *pos, const int32_t *nmeth,
+                       const int32_t *cov, int64_t S, const int32_t *seg_est, const int32_t *seg_id,
+                       const uint32_t *seg_start, const uint32_t *seg_end, const double *seg_pw,
+                       double max_distance, int32_t *o_est, int32_t *o_seg_id, uint32_t *o_start,
+                       uint32_t *o_end, double *o_width, double *o_beta, double *o_cov, double *o_pw,
+                       int32_t *o_ncpg, double *o_std) {
+  if (n <= 0 || S <= 0) return -ORC_ERR_BAD_ARGUMENT;
+  int64_t out = 0, r0 = 0;
+  int32_t cur_est = seg_est[0] - 1;
+  int64_t shift = 0;                      /* cumsum(is.oversize) within the current estimate */
+  for (int64_t s = 0; s < S; ++s) {
+    if (seg_est[s] != cur_est) { cur_est = seg_est[s]; shift = 0; r0 = 0; }
+    if (seg_start[s] > seg_end[s]) continue;                        /* sg <- segmentation[start <= end] */
+    /* rows of this estimate with start-1 <= pos <= end (rows are sorted: advance a cursor, then scan) */
+    while (r0 < n && (est_id[r0] < cur_est || (est_id[r0] == cur_est && (int64_t)pos[r0] < (int64_t)seg_start[s] - 1))) ++r0;
+    int64_t lo = r0, hi = lo;
+    while (hi < n && est_id[hi] == cur_est && (int64_t)pos[hi] <= (int64_t)seg_end[s]) ++hi;
+    int64_t a = lo;
+    while (a < hi) {
+      int64_t b = a + 1;                                             /* part [a, b): no oversize gap inside */
+      while (b < hi && !((double)pos[b] - (double)pos[b - 1] > max_distance)) ++b;
+      if (a > lo) ++shift;                                           /* this part starts at an oversize gap */
+      const int64_t m = b - a;
+      long double sum = 0;
+      double csum = 0;
+      for (int64_t i = a; i < b; ++i) { sum += (long double)((double)nmeth[i] / (double)cov[i]); csum += (double)cov[i]; }
+      long double mean = sum / m;
+      if (isfinite((double)mean)) {
+        long double t = 0;
+        for (int64_t i = a; i < b; ++i) t += ((long double)((double)nmeth[i] / (double)cov[i]) - mean);
+        mean += t / m;
+      }
+      double sd = 0;
+      if (m >= 2) {
+        long double ss = 0;
+        for (int64_t i = a; i < b; ++i) {
+          const long double d = (long double)((double)nmeth[i] / (double)cov[i]) - mean;
+          ss += d * d;
+        }
+        sd = sqrt((double)(ss / (m - 1)));
+      }
+      o_est[out] = cur_est;
+      o_seg_id[out] = (int32_t)(seg_id[s] + shift);
+      o_start[out] = (uint32_t)pos[a];
+      o_end[out] = (uint32_t)pos[b - 1] + 2u;
+      o_width[out] = (double)o_end[out] - (double)o_start[out] + 1.0;
+      o_beta[out] = (double)mean;
+      o_cov[out] = csum;
+      o_pw[out] = seg_pw[s];
+      o_ncpg[out] = (int32_t)m;
+      o_std[out] = sd;
+      ++out;
+      a = b;
+    }
+  }
+  return out;
+}

@@ -113,6 +113,16 @@ int64_t orc_segment_helper(int64_t n, const int32_t *estimate_id, const int32_t 
                            uint32_t *seg_start, uint32_t *seg_end, double *seg_beta,
                            double *seg_betahat, double *seg_pseudoweight, double *seg_stdev);
 
+/* R/call.R:43-68: per-segment call table (gap split, shrunk boundaries, mean / sd of the pooled per-position
+ * methylation) from pooled rows sorted by (estimate, pos) and the helper's segments.  Outputs need capacity n.
+ * Returns the number of rows, <0 on error.  Restates R code; R is not in this image (not pinned against R). */
+int64_t orc_call_table(int64_t n, const int32_t *est_id, const int32_t *pos, const int32_t *nmeth,
+                       const int32_t *cov, int64_t S, const int32_t *seg_est, const int32_t *seg_id,
+                       const uint32_t *seg_start, const uint32_t *seg_end, const double *seg_pw,
+                       double max_distance, int32_t *o_est, int32_t *o_seg_id, uint32_t *o_start,
+                       uint32_t *o_end, double *o_width, double *o_beta, double *o_cov, double *o_pw,
+                       int32_t *o_ncpg, double *o_std);
+
 /* R/fast_diff.R:15-28 combine, restated on the estimates table of one job. */
 int orc_fast_diff_combine(int64_t n_params, int32_t n_est, const double *beta, const double *betahat,
                           const double *pseudoweight, double *out_beta, double *out_betahat,

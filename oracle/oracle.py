@@ -71,6 +71,8 @@ def lib():
         L.orc_result_free.argtypes = [C.POINTER(OrcResult)]
         L.orc_segment_helper.argtypes = [C.c_int64] + [dp] * 5 + [C.c_double] + [dp] * 8
         L.orc_segment_helper.restype = C.c_int64
+        L.orc_call_table.argtypes = [C.c_int64] + [dp] * 4 + [C.c_int64] + [dp] * 5 + [C.c_double] + [dp] * 10
+        L.orc_call_table.restype = C.c_int64
         L.orc_fast_diff_combine.argtypes = [C.c_int64, C.c_int32] + [dp] * 6
         L.orc_strerror.restype = C.c_char_p
         L.orc_tf_dp_weight.argtypes = [C.c_int] + [dp, dp, C.c_double] + [dp] * 6
@@ -182,6 +184,26 @@ def segment_methylation_helper(est, tol_val=0.01):
     if S < 0:
         _check(int(-S))
     return {k: v[:S].copy() for k, v in o.items()}
+
+
+CALL_COLUMNS = (("estimate_id", np.int32), ("segment_id", np.int32), ("start", np.uint32), ("end", np.uint32),
+                ("width", np.float64), ("beta", np.float64), ("coverage", np.float64), ("pseudoweight", np.float64),
+                ("num_cpgs", np.int32), ("std", np.float64))
+
+
+def call_table(pooled, seg, max_distance=500.0):
+    """R/call.R:43-68.  pooled: dict(estimate_id, pos, Nmeth, coverage) per position and condition, sorted by
+    (estimate_id, pos); seg: the helper's table (estimate_id, segment_id, start, end, pseudoweight)."""
+    e, p, m, c = (_i32(pooled[k]) for k in ("estimate_id", "pos", "Nmeth", "coverage"))
+    se, si = _i32(seg["estimate_id"]), _i32(seg["segment_id"])
+    ss, sn = np.ascontiguousarray(seg["start"], np.uint32), np.ascontiguousarray(seg["end"], np.uint32)
+    sp = _f64(seg["pseudoweight"])
+    o = {k: np.zeros(e.size, dt) for k, dt in CALL_COLUMNS}
+    n = lib().orc_call_table(e.size, _p(e), _p(p), _p(m), _p(c), se.size, _p(se), _p(si), _p(ss), _p(sn), _p(sp),
+                             float(max_distance), *[_p(o[k]) for k, _ in CALL_COLUMNS])
+    if n < 0:
+        _check(int(-n))
+    return {k: v[:n].copy() for k, v in o.items()}
 
 
 def fast_diff_combine(est, n_params, n_est):
