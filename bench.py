@@ -9,6 +9,8 @@ filtered at >= 5), UMR/LMR segmentation at lambda2 = 25 followed by the PMD std 
 lambda2 = 1000.  One STEP = the native calls the reference's R layer makes for that config:
     signal_detection_fast (24 x signal_detection_fast_singlechr, MethyLasso.R:559)
     segment_methylation_helper on the estimates            (R/call.R:53)
+    the per-segment call table: gap split, shrink, mean/sd (R/call.R:55-72; data.table code in the reference,
+                                                            native here so that the chain stays on the device)
     weighted_1d_flsa(std, width, 1000) per chromosome      (R/call.R:93)
     segment_methylation_helper on the fused table          (R/call.R:95)
 `value` times the step with inputs already resident in HBM (validation, indexing, IRLS, FLSA,
@@ -38,7 +40,7 @@ sys.path.insert(0, ROOT)
 
 from methylasso_b200 import synth  # noqa: E402
 
-LAMBDA2, PMD_LAMBDA2, TOL = 25.0, 1000.0, 0.01
+LAMBDA2, PMD_LAMBDA2, TOL, MAX_DISTANCE = 25.0, 1000.0, 0.01, 500.0
 
 
 def peaks():
@@ -109,12 +111,18 @@ def reference_step(tables, O, threads):
         for j in ids:
             t = tables[j]
             r = O.detect(t, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
-            seg = O.segment_methylation_helper(r["estimates"], TOL)
-            y = np.where(np.isfinite(seg["stdev"]), seg["stdev"], 0.0)
-            w = seg["end"].astype(float) - seg["start"].astype(float) + 1.0
-            fused = O.weighted_1d_flsa(y, w, PMD_LAMBDA2)
-            pmd = O.segment_methylation_helper(dict(estimate_id=seg["estimate_id"], start=seg["start"].astype(np.int32),
-                                                    beta=fused, betahat=y, pseudoweight=seg["pseudoweight"]), TOL)
+            est = r["estimates"]
+            seg = O.segment_methylation_helper(est, TOL)
+            # R/call.R:43-72: call table from the pooled per-position data (one condition: the estimates table
+            # holds exactly that: pooled coverage = pseudoweight, pooled Nmeth = betahat * pseudoweight)
+            pooled = dict(estimate_id=est["estimate_id"], pos=est["start"].astype(np.int32),
+                          Nmeth=np.rint(est["betahat"] * est["pseudoweight"]).astype(np.int32),
+                          coverage=est["pseudoweight"].astype(np.int32))
+            call = O.call_table(pooled, seg, MAX_DISTANCE)
+            fused = O.weighted_1d_flsa(call["std"], call["width"], PMD_LAMBDA2)              # R/call.R:93
+            pmd = O.segment_methylation_helper(dict(estimate_id=call["estimate_id"], start=call["start"].astype(np.int32),
+                                                    beta=fused, betahat=call["std"],
+                                                    pseudoweight=call["pseudoweight"]), TOL)  # R/call.R:95
             out[j] = (r["n_params"], seg["start"].size, pmd["start"].size)
     order = sorted(range(len(tables)), key=lambda j: -tables[j]["pos"].size)  # longest first
     buckets = [[] for _ in range(threads)]
@@ -188,7 +196,7 @@ def workload_config(args, tables, ptr, U=None):
             "rows_per_genome": int(ptr[-1]), "chromosomes": len(tables), "replicates": 3, "lambda2": LAMBDA2,
             "pmd_lambda2": PMD_LAMBDA2, "tol_val": TOL, "model": "FAST (normal/identity, max_iter=1)",
             "l2_policy": "inputs (2.0 GB per genome) and parameter arrays are larger than the 126 MB L2",
-            "pmd_input": "segment helper stdev/width (the R-side per-segment sd of R/call.R:57-68 is not native yet)"}
+            "pmd_input": "std and width of the native call table (R/call.R:55-72), max_distance = 500"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -272,7 +280,8 @@ def main():
     def step_resident():
         res = eng.detect(batch, params)
         nseg = res.segments_count(TOL)
-        npmd = res.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+        res.call_table(TOL, MAX_DISTANCE, fetch=False)
+        npmd = res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
         return res, nseg, npmd
 
     # sizes (one untimed call)
@@ -294,6 +303,7 @@ def main():
     for _ in range(args.warmup):
         r, _, _ = step_resident()
         r.free()
+    eng.set("pool_headroom_percent", 10)     # no cuMemMap inside a timed step
     eng.set("profile", 1)
     eng.profile_reset()
     sampler = ClockSampler(local)
@@ -304,9 +314,12 @@ def main():
     if args.profiler_range:
         torch.cuda.cudart().cudaProfilerStart()
     ev0.record(stream)
+    step_wall_res = []
     for _ in range(args.steps):
+        tw0 = time.perf_counter()
         r, nseg, npmd = step_resident()
         r.free()
+        step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
     ev1.record(stream)
     if args.profiler_range:
         torch.cuda.synchronize()
@@ -342,7 +355,8 @@ def main():
             bt, jobs = grp
             rr = eng_g.detect(bt, params)
             ns = rr.segments_count(TOL)
-            npm = rr.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+            rr.call_table(TOL, MAX_DISTANCE, fetch=False)
+            npm = rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
             rr.free()
             eng_g.synchronize()
             return ns, npm
@@ -404,11 +418,14 @@ def main():
             rr.copy_all_async(o["mu"], o["off"], o["est_id"], o["start"], o["beta"], o["betahat"], o["pseudoweight"])
             ts.append(time.perf_counter())
             rr.segments_count(TOL)                      # resident; the tables are fetched after the big copies
-            rr.pmd_segments(TOL, PMD_LAMBDA2, fetch=False)
+            rr.call_table(TOL, MAX_DISTANCE, fetch=False)
+            rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
             ts.append(time.perf_counter())
             eng_g.synchronize()
             seg = rr.segments(TOL)
-            pmd = rr.pmd_segments(TOL, PMD_LAMBDA2)
+            call = rr.call_table(TOL, MAX_DISTANCE)
+            pmd = rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
+            pmd["call_table"] = call
             rr.free()
             ts.append(time.perf_counter())
             timeline.append((len(jobs), [round((x - t_step0[0]) * 1e3, 1) for x in ts]))
@@ -443,7 +460,8 @@ def main():
         t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        seg_bytes = sum(v.nbytes for sg, pm in outs for v in list(sg.values()) + list(pm.values()))
+        seg_bytes = sum(v.nbytes for sg, pm in outs for v in list(sg.values()) + [x for x in pm.values() if not isinstance(x, dict)]
+                        + list(pm["call_table"].values()))
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
                "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
@@ -512,6 +530,7 @@ def main():
             "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16], "resident_pipelined": resident_pool,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
+            "host_wall_ms_each_step": step_wall_res,
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
         }
         print(json.dumps(line), flush=True)

@@ -210,6 +210,7 @@ __global__ void k_seg_emit(const SegGroup* __restrict__ groups, const int32_t* _
   }
   const int seg_in_group = s - seg_of_run[run_pos[G.row0]];
   if (out.job) out.job[s] = G.job;
+  out.first_row[s] = (int32_t)first;
   out.estimate_id[s] = G.estimate_id;
   out.seg_id[s] = seg_in_group + 1;
   out.start[s] = (uint32_t)seg_start_at(G, start, start_f64, first);
@@ -309,29 +310,62 @@ __device__ __forceinline__ void segment_rows(const SegGroup& G, const void* pos,
   hi = a;
 }
 
-// pass 1: number of parts (maximal runs without a gap > max_distance) and of oversize gaps per segment
-template <class Rows>
-__global__ void k_call_count(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0, int ng,
-                             int n_segs, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_end,
-                             const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
-                             int32_t* __restrict__ parts, int32_t* __restrict__ gaps) {
+// Row range [lo, hi) and group of every segment.  From the helper's own bookkeeping when the segments were
+// computed on these very rows (no search: the rows of segment s run from its first row to the next segment's,
+// plus the row before if it sits at start - 1), by binary search otherwise.
+__global__ void k_call_ranges(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0, int ng, int n_segs,
+                              const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_end,
+                              const int32_t* __restrict__ first_row, const void* __restrict__ pos, int pos_f64,
+                              int32_t* __restrict__ seg_group, int32_t* __restrict__ row_lo, int32_t* __restrict__ row_hi) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_segs) return;
-  int np = 0;
-  if (seg_start[s] <= seg_end[s]) {                          // sg <- segmentation[start <= end]
-    const SegGroup G = groups[group_of_segment(group_seg0, ng, s)];
-    int64_t lo, hi;
+  const int g = group_of_segment(group_seg0, ng, s);
+  const SegGroup G = groups[g];
+  seg_group[s] = g;
+  int64_t lo, hi;
+  if (first_row) {
+    lo = first_row[s];
+    hi = s + 1 < group_seg0[g + 1] ? (int64_t)first_row[s + 1] : G.row0 + G.nrows;
+    if (lo > G.row0 && (int64_t)seg_start_at(G, pos, pos_f64, lo - 1) == (int64_t)seg_start[s] - 1) --lo;
+  } else {
     segment_rows(G, pos, pos_f64, seg_start[s], seg_end[s], lo, hi);
-    double prev = 0;
-    for (int64_t i = lo; i < hi; ++i) {
+  }
+  if (seg_start[s] > seg_end[s]) hi = lo;                    // sg <- segmentation[start <= end]
+  row_lo[s] = (int32_t)lo;
+  row_hi[s] = (int32_t)hi;
+}
+
+// pass 1, one warp per segment: number of parts (maximal runs without a gap > max_distance) and of oversize gaps
+template <class Rows>
+__global__ void __launch_bounds__(256)
+k_call_count(const SegGroup* __restrict__ groups, const int32_t* __restrict__ seg_group, int n_segs,
+             const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
+             const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+             int32_t* __restrict__ parts, int32_t* __restrict__ gaps) {
+  const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= n_segs) return;
+  int nvalid = 0, ngap = 0;
+  {
+    const SegGroup G = groups[seg_group[s]];
+    const int64_t lo = row_lo[s], hi = row_hi[s];
+    for (int64_t i = lo + lane; i < hi; i += 32) {
       if (!rows.valid(i)) continue;
-      const double p = (double)seg_start_at(G, pos, pos_f64, i);
-      if (np == 0 || p - prev > max_distance) ++np;
-      prev = p;
+      ++nvalid;
+      int64_t j = i - 1;                                     // previous valid row of the segment, if any
+      while (j >= lo && !rows.valid(j)) --j;
+      if (j >= lo && (double)seg_start_at(G, pos, pos_f64, i) - (double)seg_start_at(G, pos, pos_f64, j) > max_distance) ++ngap;
     }
   }
-  parts[s] = np;
-  gaps[s] = np > 0 ? np - 1 : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
+    ngap += __shfl_xor_sync(0xffffffffu, ngap, d);
+  }
+  if (lane == 0) {
+    parts[s] = nvalid > 0 ? ngap + 1 : 0;
+    gaps[s] = nvalid > 0 ? ngap : 0;
+  }
 }
 
 struct CallOut {
@@ -340,67 +374,115 @@ struct CallOut {
   int32_t* num_cpgs;
 };
 
-// pass 2: one thread per segment emits its parts; sums run in row order (mean refined by a second pass and
-// the squares taken about that mean, as R's mean() and sd() do)
+__device__ __forceinline__ DD dd_merge(const DD& a, const DD& b) {
+  const double s = a.hi + b.hi;
+  const double bb = s - a.hi;
+  double e = (a.hi - (s - bb)) + (b.hi - bb);
+  e += a.lo + b.lo;
+  const double hi = s + e;
+  return DD{hi, e - (hi - s)};
+}
+__device__ __forceinline__ DD dd_warp_sum(DD v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    DD o{__shfl_xor_sync(0xffffffffu, v.hi, d), __shfl_xor_sync(0xffffffffu, v.lo, d)};
+    v = dd_merge(v, o);
+  }
+  return v;
+}
+
+// pass 2, one WARP per segment (coalesced row sweeps).  The parts of a segment (runs without an oversize gap) are
+// found with a ballot over the gap flags and summarised one after the other; within a part the three sums of R's
+// mean() / sd() (sum, correction about the first mean, squares about the refined mean) are reduced across the lanes in
+// double-double, whose error (~1e-32 relative) is far below the final rounding to double, so the order of the
+// additions does not show.
 template <class Rows>
-__global__ void k_call_emit(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0, int ng,
-                            int n_segs, const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ seg_end,
-                            const int32_t* __restrict__ seg_id, const double* __restrict__ seg_pw,
-                            const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
-                            const int32_t* __restrict__ part_off, const int32_t* __restrict__ gap_off, CallOut out) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n_segs || seg_start[s] > seg_end[s]) return;
-  const int g = group_of_segment(group_seg0, ng, s);
+__global__ void __launch_bounds__(256)
+k_call_emit_warp(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0,
+                 const int32_t* __restrict__ seg_group, int n_segs,
+                 const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
+                 const int32_t* __restrict__ seg_id, const double* __restrict__ seg_pw,
+                 const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+                 const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
+                 const int32_t* __restrict__ gap_off, CallOut out) {
+  const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= n_segs) return;
+  const int np = parts[s];
+  if (np == 0) return;
+  const int g = seg_group[s];
   const SegGroup G = groups[g];
-  int64_t lo, hi;
-  segment_rows(G, pos, pos_f64, seg_start[s], seg_end[s], lo, hi);
-  int o = part_off[s];
+  const int64_t lo = row_lo[s], hi = row_hi[s];
   int shift = gap_off[s] - gap_off[group_seg0[g]];
+  int o = part_off[s];
   int64_t a = lo;
-  while (a < hi && !rows.valid(a)) ++a;
-  bool first_part = true;
-  while (a < hi) {
-    // part [a, b): valid rows until the first oversize gap
-    DD sum{0.0, 0.0};
-    double csum = 0.0, prev = (double)seg_start_at(G, pos, pos_f64, a);
-    const double p0 = prev;
-    int m = 0;
-    int64_t b = a;
-    for (; b < hi; ++b) {
-      if (!rows.valid(b)) continue;
-      const double p = (double)seg_start_at(G, pos, pos_f64, b);
-      if (m > 0 && p - prev > max_distance) break;
-      dd_add(sum, rows.x(b));
-      csum += rows.cov(b);
-      prev = p;
-      ++m;
+  for (int part = 0; part < np; ++part) {
+    // end of the part: the first valid row whose distance to the previous valid row of the part is oversize
+    int64_t b = hi;
+    if (part + 1 < np) {
+      for (int64_t base = a + 1; base < hi && b == hi; base += 32) {
+        const int64_t i = base + lane;
+        bool gap = false;
+        if (i < hi && rows.valid(i)) {
+          int64_t j = i - 1;
+          while (j >= a && !rows.valid(j)) --j;
+          gap = j >= a && (double)seg_start_at(G, pos, pos_f64, i) - (double)seg_start_at(G, pos, pos_f64, j) > max_distance;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, gap);
+        if (bal) b = base + __ffs(bal) - 1;
+      }
     }
-    if (!first_part) ++shift;
-    first_part = false;
+    DD sum{0.0, 0.0};
+    double csum = 0.0;
+    int m = 0;
+    int64_t first = b, last = a - 1;
+    for (int64_t i = a + lane; i < b; i += 32) {
+      if (!rows.valid(i)) continue;
+      dd_add(sum, rows.x(i));
+      csum += rows.cov(i);
+      ++m;
+      if (i < first) first = i;
+      last = i;
+    }
+    sum = dd_warp_sum(sum);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      csum += __shfl_xor_sync(0xffffffffu, csum, d);
+      m += __shfl_xor_sync(0xffffffffu, m, d);
+      first = min(first, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)first, d));
+      last = max(last, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)last, d));
+    }
     double mean = (sum.hi + sum.lo) / m;
     if (is_finite(mean)) {
       DD t{0.0, 0.0};
-      for (int64_t i = a; i < b; ++i) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+      for (int64_t i = a + lane; i < b; i += 32) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+      t = dd_warp_sum(t);
       mean += (t.hi + t.lo) / m;
     }
     double sd = 0.0;
     if (m >= 2) {
       DD ss{0.0, 0.0};
-      for (int64_t i = a; i < b; ++i) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
+      for (int64_t i = a + lane; i < b; i += 32) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
+      ss = dd_warp_sum(ss);
       sd = sqrt((ss.hi + ss.lo) / (m - 1));
     }
-    if (out.t.job) out.t.job[o] = G.job;
-    out.t.estimate_id[o] = G.estimate_id;
-    out.t.seg_id[o] = seg_id[s] + shift;
-    out.t.start[o] = (uint32_t)p0;
-    out.t.end[o] = (uint32_t)prev + 2u;
-    out.width[o] = ((double)prev + 2.0) - p0 + 1.0;
-    out.t.beta[o] = mean;
-    out.t.betahat[o] = mean;
-    out.t.pseudoweight[o] = seg_pw[s];
-    out.t.stdev[o] = sd;
-    out.coverage[o] = csum;
-    out.num_cpgs[o] = m;
+    if (part > 0) ++shift;
+    if (lane == 0) {
+      const double p0 = (double)seg_start_at(G, pos, pos_f64, first), p1 = (double)seg_start_at(G, pos, pos_f64, last);
+      if (out.t.job) out.t.job[o] = G.job;
+      out.t.first_row[o] = (int32_t)first;
+      out.t.estimate_id[o] = G.estimate_id;
+      out.t.seg_id[o] = seg_id[s] + shift;
+      out.t.start[o] = (uint32_t)p0;
+      out.t.end[o] = (uint32_t)p1 + 2u;
+      out.width[o] = (p1 + 2.0) - p0 + 1.0;
+      out.t.beta[o] = mean;
+      out.t.betahat[o] = mean;
+      out.t.pseudoweight[o] = seg_pw[s];
+      out.t.stdev[o] = sd;
+      out.coverage[o] = csum;
+      out.num_cpgs[o] = m;
+    }
     ++o;
     a = b;
   }
@@ -461,8 +543,12 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
   DevBuf<int32_t> d_g0(st, ng + 1);
   d_g0.upload(seg.group_seg0);
   DevBuf<int32_t> parts(st, n_segs), gaps(st, n_segs), part_off(st, n_segs), gap_off(st, n_segs);
-  ML_LAUNCH(eng, "k_call_count", k_call_count<Rows><<<cdiv(n_segs, 128), 128, 0, st>>>(
-      d_groups.p, d_g0.p, ng, n_segs, seg.start.p, seg.end.p, d_pos, pos_f64, rows, max_distance, parts.p, gaps.p));
+  DevBuf<int32_t> seg_group(st, n_segs), row_lo(st, n_segs), row_hi(st, n_segs);
+  ML_LAUNCH(eng, "k_call_ranges", k_call_ranges<<<cdiv(n_segs, 128), 128, 0, st>>>(
+      d_groups.p, d_g0.p, ng, n_segs, seg.start.p, seg.end.p, seg.has_first_row ? seg.first_row.p : nullptr, d_pos, pos_f64,
+      seg_group.p, row_lo.p, row_hi.p));
+  ML_LAUNCH(eng, "k_call_count", k_call_count<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
+      d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, gaps.p));
   Scan scan;
   scan.run(eng, gaps.p, n_segs, gap_off.p, nullptr);
   const int32_t total = scan.run(eng, parts.p, n_segs, part_off.p, nullptr);
@@ -471,9 +557,9 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
   out.width.alloc(st, (size_t)std::max(1, total));
   out.num_cpgs.alloc(st, (size_t)std::max(1, total));
   CallOut co{out.t.view(), out.coverage.p, out.width.p, out.num_cpgs.p};
-  ML_LAUNCH(eng, "k_call_emit", k_call_emit<Rows><<<cdiv(n_segs, 128), 128, 0, st>>>(
-      d_groups.p, d_g0.p, ng, n_segs, seg.start.p, seg.end.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
-      max_distance, part_off.p, gap_off.p, co));
+  ML_LAUNCH(eng, "k_call_emit_warp", k_call_emit_warp<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
+      d_groups.p, d_g0.p, seg_group.p, n_segs, row_lo.p, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
+      max_distance, parts.p, part_off.p, gap_off.p, co));
   DevBuf<int32_t> d_c0(st, ng + 1);
   ML_LAUNCH(eng, "k_call_group0", k_call_group0<<<cdiv(ng + 1, 128), 128, 0, st>>>(d_g0.p, ng, n_segs, part_off.p, total, d_c0.p));
   std::vector<int32_t> c0(ng + 1);
@@ -560,6 +646,7 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   ML_LAUNCH(eng, "k_seg_emit", k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
                                                 seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
                                                 d_betahat, d_pw, out));
+  ds.has_first_row = true;
   stream_sync(st);
   return n_segs;
 }

@@ -13,6 +13,7 @@ struct SegGroup {
 };
 
 struct SegOut {   // device pointers
+  int32_t* first_row;   // first row of the segment in the arrays it was computed on
   int32_t *job, *estimate_id, *seg_id;
   uint32_t *start, *end;
   double *beta, *betahat, *pseudoweight, *stdev;
@@ -25,20 +26,21 @@ struct SegHostOut {  // caller buffers (any may be null)
 };
 
 struct SegDeviceOut {
-  DevBuf<int32_t> job, estimate_id, seg_id;
+  DevBuf<int32_t> job, estimate_id, seg_id, first_row;
   DevBuf<uint32_t> start, end;
   DevBuf<double> beta, betahat, pseudoweight, stdev;
   int64_t n = 0;
+  bool has_first_row = false;   // set by segment_device: first_row holds row indices of its input arrays
   // host copy of the group structure: segments [group_seg0[g], group_seg0[g+1]) belong to group g
   std::vector<int32_t> group_seg0, group_job, group_est;
   void alloc(cudaStream_t st, int64_t count) {
     n = count;
     const size_t c = (size_t)std::max<int64_t>(1, count);
-    job.alloc(st, c); estimate_id.alloc(st, c); seg_id.alloc(st, c);
+    job.alloc(st, c); estimate_id.alloc(st, c); seg_id.alloc(st, c); first_row.alloc(st, c);
     start.alloc(st, c); end.alloc(st, c);
     beta.alloc(st, c); betahat.alloc(st, c); pseudoweight.alloc(st, c); stdev.alloc(st, c);
   }
-  SegOut view() { return SegOut{job.p, estimate_id.p, seg_id.p, start.p, end.p, beta.p, betahat.p, pseudoweight.p, stdev.p}; }
+  SegOut view() { return SegOut{first_row.p, job.p, estimate_id.p, seg_id.p, start.p, end.p, beta.p, betahat.p, pseudoweight.p, stdev.p}; }
   void download(cudaStream_t, int64_t count, SegHostOut& h) const {
     const size_t c = (size_t)count;
     if (h.job) job.download(h.job, c);
