@@ -220,6 +220,9 @@ def kernel_bytes(N, EP, D, words):
         "k_eval_rows": 36 * N,
         "k_tv_partial": 8 * EP,
         "k_seg_run_heads": 12 * EP,
+        "k_seg_emit": 28 * EP,          # beta, betahat, pw, start once (two launches: the second one is on the call table)
+        "k_call_count": 16 * EP,        # pos, pw
+        "k_call_emit_warp": 24 * EP,    # pos, betahat, pw once (the second and third sweeps hit L1 / L2)
         "k_scan_tile_sums": 4 * EP,
         "k_scan_apply": 12 * EP,
     }
@@ -320,6 +323,7 @@ def main():
         r, nseg, npmd = step_resident()
         r.free()
         step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
+        eng.lib.ml_engine_profile_count(eng.h)   # folds this step's timing events into the totals (bounded event pool)
     ev1.record(stream)
     if args.profiler_range:
         torch.cuda.synchronize()

@@ -43,6 +43,7 @@ enum : int32_t {
   CHUNK_DONE = 2,        // every tm/tp of the chunk written
   CHUNK_OVERFLOW = 4,    // knot window outgrew KNOT_CAP: series goes to the global-scratch kernel
   CHUNK_START_VALID = 16, // the saved window is the exact state just BEFORE the chunk's first step
+  CHUNK_CLAIMED = 32,    // a chain walker (flsa_chain_kernel) has taken the chunk in this launch
   CHUNK_IRREGULAR = 8,   // some tm_k > tp_k (rounding on absurd inputs): clamps do not compose, the
                          // series' back-substitution is redone element by element
 };
