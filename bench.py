@@ -26,6 +26,7 @@ compiled verbatim) as the DP, one chromosome per thread (mirrors foreach %dopar%
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -444,7 +445,9 @@ def main():
         for _ in range(max(3, args.warmup)):
             outs = step_e2e()
         for e_g in pool.engines:          # pre-grow each engine's pool a little: no cuMemMap inside a timed step
-            e_g.set("pool_headroom_percent", 10)
+            e_g.set("pool_headroom_percent", 25)
+        gc.collect()
+        gc.disable()                      # no collector pause inside a 50 ms step
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -459,6 +462,7 @@ def main():
         torch.cuda.synchronize()
         e1.record(stream)
         barrier()
+        gc.enable()
         wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         ems = e0.elapsed_time(e1) / args.steps
         t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)

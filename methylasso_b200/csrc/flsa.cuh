@@ -62,6 +62,7 @@ class FlsaPlan {
   Engine& eng_;
   std::vector<FlsaSeries> series_;
   int64_t total_len_;
+  int stats_open_after_main_ = 0;
   int chunk_ = 0, warm_ = 0, n_chunks_ = 0, n_tiles_ = 0, max_tiles_per_series_ = 0;
   DevBuf<SeriesDesc> d_series_;
   DevBuf<ChunkDesc> d_chunks_;

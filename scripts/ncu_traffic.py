@@ -52,6 +52,7 @@ def main(src, dst):
         else:
             k = re.sub(r"^void ", "", full.strip())
             k = re.sub(r"^ml::", "", k)
+            k = re.sub(r"^(<?unnamed>|\(anonymous namespace\))::", "", k)
             k = re.sub(r"[<(].*", "", k)
         acc[k]["dram"].append((scaled(r, "dram__bytes_read.sum") or 0) + (scaled(r, "dram__bytes_write.sum") or 0))
         acc[k]["ms"].append(scaled(r, "gpu__time_duration.sum"))
