@@ -59,10 +59,18 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.idx = gpu_index
         self.proc = None
+        self.t_mark = None
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported.  The process itself is
+        started earlier, because nvidia-smi's own start-up (NVML initialisation) stalls CUDA calls of every process
+        on the box for 50-350 ms (measured: a 365 ms step right after the launch)."""
+        import datetime
+        self.t_mark = datetime.datetime.now()
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.QUERY}", "--format=csv,noheader,nounits",
                                           "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
@@ -79,9 +87,17 @@ class ClockSampler:
             out = ""
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                ts = None
+            f = f[1:]
+            if self.t_mark is not None and ts is not None and ts < self.t_mark:
                 continue
             try:
                 sm.append(float(f[1])); mx.append(float(f[2]))
@@ -304,15 +320,22 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: resident inputs ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()                          # before the warm-up: its start-up stall must not land in a timed step
+    eng.set("profile", 1)                    # the warm-up also fills the pool of timing events
+    lw0 = eng.launch_count
     for _ in range(args.warmup):
         r, _, _ = step_resident()
         r.free()
+        eng.lib.ml_engine_profile_count(eng.h)
+    per_step = (eng.launch_count - lw0) // max(1, args.warmup)
+    eng.set("profile_reserve_events", int(2.2 * per_step * (args.steps + 1)))   # no cudaEventCreate while timing
     eng.set("pool_headroom_percent", 10)     # no cuMemMap inside a timed step
-    eng.set("profile", 1)
     eng.profile_reset()
-    sampler = ClockSampler(local)
+    gc.collect()
+    gc.disable()
     barrier()
-    sampler.start()
+    sampler.mark()
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if args.profiler_range:
@@ -324,12 +347,12 @@ def main():
         r, nseg, npmd = step_resident()
         r.free()
         step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
-        eng.lib.ml_engine_profile_count(eng.h)   # folds this step's timing events into the totals (bounded event pool)
     ev1.record(stream)
     if args.profiler_range:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
     barrier()
+    gc.enable()
     clocks = sampler.stop()
     launches = eng.launch_count - l0
     ms = ev0.elapsed_time(ev1) / args.steps

@@ -95,7 +95,9 @@ ML_API const char *ml_strerror(int code);
 ML_API int ml_engine_create(int device, ml_engine **out);
 ML_API void ml_engine_destroy(ml_engine *eng);
 /* engine knobs: "flsa_chunk", "flsa_warm", "flsa_sequential" (1 = start-to-end DP, one thread
- * per series: the bit-faithful verification mode), "profile" (1 = time every kernel) */
+ * per series: the bit-faithful verification mode), "profile" (1 = time every kernel),
+ * "profile_reserve_events" (pre-create that many timing events), "pool_headroom_percent" (grow the engine's
+ * memory pool now by that share of what it holds, so that steady-state calls never map memory) */
 ML_API int ml_engine_set(ml_engine *eng, const char *key, long long value);
 /* number of kernel launches issued by this engine so far */
 ML_API long long ml_engine_launch_count(const ml_engine *eng);

@@ -189,6 +189,17 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
   else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
   else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }
+  else if (k == "profile_reserve_events") {
+    // pre-create timing events so that a profiled region does not call cudaEventCreate
+    ML_TRY
+    ML_CUDA(cudaSetDevice(eng->e.device));
+    for (long long i = (long long)eng->e.prof.pool.size(); i < value; ++i) {
+      cudaEvent_t ev;
+      ML_CUDA(cudaEventCreate(&ev));
+      eng->e.prof.pool.push_back(ev);
+    }
+    ML_CATCH
+  }
   else if (k == "pool_headroom_percent") {
     // Grow the engine's memory pool NOW by value % of what it has reserved so far (one block, allocated and
     // freed): a later call whose allocation order fragments the pool slightly differently then finds the
