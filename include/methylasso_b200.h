@@ -251,6 +251,18 @@ ML_API int ml_segment_call_table(ml_engine *eng, int64_t n, const int32_t *estim
                                  uint32_t *o_end, double *o_width, double *o_beta, double *o_coverage,
                                  double *o_pseudoweight, int32_t *o_num_cpgs, double *o_std);
 
+/* ---- region statistics applied by R/call.R to the path's segments ------------------------------------------------
+ * wilcox.test(x, y, conf.int = F)$p.value of R/call.R:315-317 for many groups at once: group g compares
+ * x[x_ptr[g] .. x_ptr[g+1]) with y[y_ptr[g] .. y_ptr[g+1]) (host buffers).  Two-sided rank-sum test as R's
+ * wilcox.test.default runs it: NaN values dropped; exact distribution when both samples have fewer than 50 values and
+ * there are no ties, normal approximation with continuity and tie correction otherwise.  pval[g] is NaN where R
+ * fails or returns NaN (an empty sample; all values equal), which R/call.R:317 turns into 1.  stat (may be NULL)
+ * receives W. */
+ML_API int ml_wilcoxon_groups(ml_engine *eng, int64_t n_groups, const int64_t *x_ptr, const double *x,
+                              const int64_t *y_ptr, const double *y, double *pval, double *stat);
+/* p.adjust(p, method = 'fdr') of R/call.R:360 (Benjamini-Hochberg); NaN entries stay NaN and are not counted. */
+ML_API int ml_p_adjust_fdr(ml_engine *eng, int64_t n, const double *p, double *q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,6 +129,31 @@ class Engine:
                                                    *[_p(out[k]) for k, _ in cols]))
         return {k: v[:n.value].copy() for k, v in out.items()}
 
+    # ---- region statistics (R/call.R:315-317, :360) -----------------------------------------------
+    def wilcoxon_groups(self, x_ptr, x, y_ptr, y, want_stat=False):
+        """wilcox.test(x_g, y_g, conf.int = F)$p.value for every group g (CSR offsets x_ptr / y_ptr); NaN where R
+        gives NaN or fails (R/call.R:317 maps those to 1)."""
+        x_ptr = np.ascontiguousarray(x_ptr, dtype=np.int64)
+        y_ptr = np.ascontiguousarray(y_ptr, dtype=np.int64)
+        if x_ptr.size != y_ptr.size or x_ptr.size < 1:
+            raise MethyLassoError(2, "x_ptr and y_ptr must have n_groups + 1 entries")
+        x, y = _f64(x), _f64(y)
+        if x_ptr[-1] > x.size or y_ptr[-1] > y.size or x_ptr[0] < 0 or y_ptr[0] < 0:
+            raise MethyLassoError(19, "offsets point outside the samples")
+        ng = x_ptr.size - 1
+        p = np.empty(ng)
+        w = np.empty(ng) if want_stat else None
+        self._check(self.lib.ml_wilcoxon_groups(self.h, ng, _p(x_ptr), _p(x), _p(y_ptr), _p(y), _p(p),
+                                                _p(w) if want_stat else None))
+        return (p, w) if want_stat else p
+
+    def p_adjust_fdr(self, p):
+        """p.adjust(p, method = 'fdr')."""
+        p = _f64(p)
+        q = np.empty_like(p)
+        self._check(self.lib.ml_p_adjust_fdr(self.h, p.size, _p(p), _p(q)))
+        return q
+
     # ---- weighted_1d_flsa ---------------------------------------------------------------------
     def weighted_1d_flsa(self, y, wt, lambda2, lambda1=0.0):
         y, wt = _f64(y), _f64(wt)

@@ -10,6 +10,7 @@
 #include "../../include/methylasso_b200.h"
 #include "detect.cuh"
 #include "segment.cuh"
+#include "stats.cuh"
 
 using namespace ml;
 
@@ -816,6 +817,36 @@ int ml_segment_call_table(ml_engine* eng, int64_t n, const int32_t* estimate_id,
   call_download(c, CallHostOut{nullptr, o_estimate_id, o_segment_id, o_start, o_end, o_width, o_beta, o_coverage,
                                o_pseudoweight, o_num_cpgs, o_std});
   stream_sync(st);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_wilcoxon_groups(ml_engine* eng, int64_t n_groups, const int64_t* x_ptr, const double* x, const int64_t* y_ptr,
+                       const double* y, double* pval, double* stat) {
+  if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
+  if (n_groups < 0) return fail(ML_ERR_BAD_ARGUMENT, "negative number of groups");
+  if (n_groups == 0) return ML_OK;
+  if (!x_ptr || !y_ptr || !pval) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  if ((x_ptr[n_groups] > x_ptr[0] && !x) || (y_ptr[n_groups] > y_ptr[0] && !y)) return fail(ML_ERR_BAD_ARGUMENT, "NULL sample");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  wilcoxon_groups(eng->e, n_groups, x_ptr, x, y_ptr, y, pval, stat);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_p_adjust_fdr(ml_engine* eng, int64_t n, const double* p, double* q) {
+  if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");
+  if (n < 0) return fail(ML_ERR_BAD_ARGUMENT, "negative length");
+  if (n == 0) return ML_OK;
+  if (!p || !q) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  p_adjust_fdr(eng->e, n, p, q);
   return ML_OK;
   ML_CATCH
 }

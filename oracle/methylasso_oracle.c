@@ -825,3 +825,132 @@ int64_t orc_call_table(int64_t n, const int32_t *est_id, const int32_t *pos, con
   }
   return out;
 }
+
+/* ---- R/call.R:315-317 and :360: wilcox.test(x, y, conf.int = F)$p.value and p.adjust(p, 'fdr') ----------------
+ * Restated from the published algorithms of R's stats package (wilcox.test.default, two-sided, mu = 0,
+ * exact = NULL, correct = TRUE; pwilcox / cwilcox of nmath/wilcox.c; p.adjust method "BH").  R is not in this
+ * image; tests/test_wilcoxon.py pins this restatement against scipy.stats.mannwhitneyu (exact and asymptotic with
+ * continuity) and scipy.stats.false_discovery_control, which implement the same tests independently. */
+static int orc_cmp_double(const void *a, const void *b) {
+  const double x = *(const double *)a, y = *(const double *)b;
+  return x < y ? -1 : x > y;
+}
+
+/* counts[k] = number of ways the rank-sum statistic of m-vs-n takes the value k (k = 0..m*n), by the recurrence
+ * w(k; i, j) = w(k - j; i - 1, j) + w(k; i, j - 1) that nmath/wilcox.c memoises */
+static double *orc_cwilcox_table(int m, int n) {
+  const int K = m * n + 1;
+  double *A = (double *)calloc((size_t)(n + 1) * K, sizeof(double));
+  if (!A) return NULL;
+  for (int j = 0; j <= n; ++j) A[(size_t)j * K] = 1.0;                 /* w(0; 0, j) = 1 */
+  for (int i = 1; i <= m; ++i)
+    for (int j = 1; j <= n; ++j) {
+      double *row = A + (size_t)j * K, *left = A + (size_t)(j - 1) * K;
+      for (int k = i * j; k >= 0; --k) row[k] = (k >= j ? row[k - j] : 0.0) + left[k];
+    }
+  double *out = (double *)malloc(sizeof(double) * K);
+  if (out) memcpy(out, A + (size_t)n * K, sizeof(double) * K);
+  free(A);
+  return out;
+}
+
+static double orc_choose(int n, int k) {        /* exact in double for the sizes used (n < 100) up to rounding */
+  double c = 1.0;
+  if (k > n - k) k = n - k;
+  for (int i = 1; i <= k; ++i) c = c * (double)(n - k + i) / (double)i;
+  return floor(c + 0.5);
+}
+
+/* pwilcox(q, m, n, lower_tail) of nmath/wilcox.c */
+static double orc_pwilcox(double q, int m, int n, int lower_tail, const double *w) {
+  q = floor(q + 1e-7);
+  if (q < 0.0) return lower_tail ? 0.0 : 1.0;
+  if (q >= (double)m * n) return lower_tail ? 1.0 : 0.0;
+  const double c = orc_choose(m + n, n);
+  double p = 0.0;
+  if (q <= (double)m * n / 2) {
+    for (int i = 0; i <= (int)q; ++i) p += w[i] / c;
+    return lower_tail ? p : 1.0 - p;
+  }
+  q = (double)m * n - q;
+  for (int i = 0; i < (int)q; ++i) p += w[i] / c;
+  return lower_tail ? 1.0 - p : p;
+}
+
+/* returns 0 and sets *pval (NaN when undefined, e.g. all values equal) and *stat = W; 1 if a sample is empty */
+int orc_wilcox_test(int64_t nx, const double *x, int64_t ny, const double *y, double *stat, double *pval) {
+  /* x <- x[!is.na(x)], y <- y[!is.na(y)] */
+  double *v = (double *)malloc(sizeof(double) * (size_t)(nx + ny + 1));
+  int64_t mx = 0, my = 0;
+  for (int64_t i = 0; i < nx; ++i) if (!isnan(x[i])) v[mx++] = x[i];
+  for (int64_t i = 0; i < ny; ++i) if (!isnan(y[i])) v[mx + my++] = y[i];
+  if (mx < 1 || my < 1) { free(v); *pval = NAN; *stat = NAN; return 1; }
+  const int64_t N = mx + my;
+  double *s = (double *)malloc(sizeof(double) * (size_t)N);
+  memcpy(s, v, sizeof(double) * (size_t)N);
+  qsort(s, (size_t)N, sizeof(double), orc_cmp_double);
+  /* W = sum of the (average) ranks of x - nx (nx + 1) / 2; tie term sum(t^3 - t) */
+  double W = 0.0, tie_term = 0.0;
+  int ties = 0;
+  for (int64_t i = 0; i < N;) {
+    int64_t j = i;
+    while (j < N && s[j] == s[i]) ++j;
+    const double t = (double)(j - i);
+    if (j - i > 1) ties = 1;
+    tie_term += t * t * t - t;
+    i = j;
+  }
+  for (int64_t i = 0; i < mx; ++i) {
+    /* rank = (#less) + (#equal + 1) / 2, by binary search in the sorted pool */
+    int64_t lo = 0, hi = N;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (s[mid] < v[i]) lo = mid + 1; else hi = mid; }
+    int64_t first = lo;
+    hi = N;
+    while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (s[mid] <= v[i]) lo = mid + 1; else hi = mid; }
+    W += (double)first + ((double)(lo - first) + 1.0) / 2.0;
+  }
+  W -= (double)mx * ((double)mx + 1.0) / 2.0;
+  *stat = W;
+  const double dx = (double)mx, dy = (double)my;
+  if (mx < 50 && my < 50 && !ties) {
+    double *w = orc_cwilcox_table((int)mx, (int)my);
+    double p = W > dx * dy / 2 ? orc_pwilcox(W - 1, (int)mx, (int)my, 0, w) : orc_pwilcox(W, (int)mx, (int)my, 1, w);
+    free(w);
+    *pval = fmin(2 * p, 1.0);
+  } else {
+    double z = W - dx * dy / 2;
+    const double sigma = sqrt((dx * dy / 12) * ((dx + dy + 1) - tie_term / ((dx + dy) * (dx + dy - 1))));
+    const double corr = (z > 0) ? 0.5 : (z < 0 ? -0.5 : 0.0);
+    z = (z - corr) / sigma;
+    const double pl = 0.5 * erfc(-z / sqrt(2.0)), pu = 0.5 * erfc(z / sqrt(2.0));
+    *pval = 2 * fmin(pl, pu);
+  }
+  free(s);
+  free(v);
+  return 0;
+}
+
+/* p.adjust(p, method = "fdr"): NaN entries are left out of n and of the ranking, as R leaves NA out */
+void orc_p_adjust_fdr(int64_t n, const double *p, double *q) {
+  int64_t *o = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+  int64_t lp = 0;
+  for (int64_t i = 0; i < n; ++i) { q[i] = NAN; if (!isnan(p[i])) o[lp++] = i; }
+  /* order(p, decreasing = TRUE), stable: insertion into a sorted index by merge sort */
+  int64_t *tmp = (int64_t *)malloc(sizeof(int64_t) * (size_t)(lp + 1));
+  for (int64_t w = 1; w < lp; w *= 2)
+    for (int64_t a = 0; a < lp; a += 2 * w) {
+      int64_t i = a, mid = a + w < lp ? a + w : lp, j = mid, end = a + 2 * w < lp ? a + 2 * w : lp, k = a;
+      while (i < mid && j < end) tmp[k++] = (p[o[j]] > p[o[i]]) ? o[j++] : o[i++];
+      while (i < mid) tmp[k++] = o[i++];
+      while (j < end) tmp[k++] = o[j++];
+      memcpy(o + a, tmp + a, sizeof(int64_t) * (size_t)(end - a));
+    }
+  double run = INFINITY;
+  for (int64_t r = 0; r < lp; ++r) {                /* i = lp - r; cummin(n / i * p[o]) */
+    const double val = (double)lp / (double)(lp - r) * p[o[r]];
+    if (val < run) run = val;
+    q[o[r]] = run < 1.0 ? run : 1.0;
+  }
+  free(tmp);
+  free(o);
+}

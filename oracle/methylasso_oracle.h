@@ -123,6 +123,12 @@ int64_t orc_call_table(int64_t n, const int32_t *est_id, const int32_t *pos, con
                        uint32_t *o_end, double *o_width, double *o_beta, double *o_cov, double *o_pw,
                        int32_t *o_ncpg, double *o_std);
 
+/* R/call.R:315-317: wilcox.test(x, y, conf.int = F)$p.value (two-sided; exact when both samples have fewer than 50
+ * values and there are no ties, normal approximation with continuity and tie correction otherwise); R/call.R:360:
+ * p.adjust(p, 'fdr').  Restated from R's published algorithms and pinned against scipy in tests/test_wilcoxon.py. */
+int orc_wilcox_test(int64_t nx, const double *x, int64_t ny, const double *y, double *stat, double *pval);
+void orc_p_adjust_fdr(int64_t n, const double *p, double *q);
+
 /* R/fast_diff.R:15-28 combine, restated on the estimates table of one job. */
 int orc_fast_diff_combine(int64_t n_params, int32_t n_est, const double *beta, const double *betahat,
                           const double *pseudoweight, double *out_beta, double *out_betahat,

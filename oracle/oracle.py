@@ -73,6 +73,9 @@ def lib():
         L.orc_segment_helper.restype = C.c_int64
         L.orc_call_table.argtypes = [C.c_int64] + [dp] * 4 + [C.c_int64] + [dp] * 5 + [C.c_double] + [dp] * 10
         L.orc_call_table.restype = C.c_int64
+        L.orc_wilcox_test.argtypes = [C.c_int64, dp, C.c_int64, dp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_p_adjust_fdr.argtypes = [C.c_int64, dp, dp]
+        L.orc_p_adjust_fdr.restype = None
         L.orc_fast_diff_combine.argtypes = [C.c_int64, C.c_int32] + [dp] * 6
         L.orc_strerror.restype = C.c_char_p
         L.orc_tf_dp_weight.argtypes = [C.c_int] + [dp, dp, C.c_double] + [dp] * 6
@@ -204,6 +207,22 @@ def call_table(pooled, seg, max_distance=500.0):
     if n < 0:
         _check(int(-n))
     return {k: v[:n].copy() for k, v in o.items()}
+
+
+def wilcox_test(x, y):
+    """(W, p) of R's wilcox.test(x, y, conf.int = F) (R/call.R:315); p is nan when undefined."""
+    x, y = _f64(x), _f64(y)
+    w, p = C.c_double(), C.c_double()
+    lib().orc_wilcox_test(x.size, _p(x), y.size, _p(y), C.byref(w), C.byref(p))
+    return w.value, p.value
+
+
+def p_adjust_fdr(p):
+    """R's p.adjust(p, method = 'fdr') (R/call.R:360)."""
+    p = _f64(p)
+    q = np.empty_like(p)
+    lib().orc_p_adjust_fdr(p.size, _p(p), _p(q))
+    return q
 
 
 def fast_diff_combine(est, n_params, n_est):
