@@ -239,7 +239,8 @@ def kernel_bytes(N, EP, D, words):
         "k_seg_run_heads": 12 * EP,
         "k_seg_emit": 28 * EP,          # beta, betahat, pw, start once (two launches: the second one is on the call table)
         "k_call_count": 16 * EP,        # pos, pw
-        "k_call_emit_warp": 24 * EP,    # pos, betahat, pw once (the second and third sweeps hit L1 / L2)
+        "k_call_parts": 16 * EP,        # pos, pw
+        "k_call_emit_part": 24 * EP,    # pos, betahat, pw once (the second and third sweeps hit L1 / L2)
         "k_scan_tile_sums": 4 * EP,
         "k_scan_apply": 12 * EP,
     }

@@ -342,7 +342,7 @@ __device__ __forceinline__ void bin_residuals(const JobDev& J, const RowCols& rc
     const int64_t g = J.row0 + r;
     if (r != r0 && rc.pidx[g] != k) break;
     const double nobs = (double)rc.cov[g];
-    const double y = (double)rc.nmeth[g] / nobs;
+    const double y = div_nz((double)rc.nmeth[g], nobs);
     double z, W;
     irls_residual(J.model, first, y, nobs, first ? 0.0 : rc.mu_res[g], J.nu, z, W);
     What += W;
@@ -441,7 +441,7 @@ k_offset_partial(const RowTile* __restrict__ tiles, const JobDev* __restrict__ j
     if (i < t.cnt) {
       const int64_t g = J.row0 + t.r0 + i;
       const double nobs = (double)rc.cov[g];
-      const double y = (double)rc.nmeth[g] / nobs;
+      const double y = div_nz((double)rc.nmeth[g], nobs);
       double z, W;
       irls_residual(J.model, first, y, nobs, first ? 0.0 : rc.mu_res[g], J.nu, z, W);
       sw += W;
@@ -568,7 +568,7 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
       const int64_t g = g0 + i;
       const double m = irls_mu(J.model, eta[q] + (0. + 1. * o));
       const double nobs = (double)cv[q];
-      const double y = (double)nm[q] / nobs;
+      const double y = div_nz((double)nm[q], nobs);
       lik += irls_minus_log_pdf(J.model, y, nobs, m, J.nu, log2pi);
       if (need_dres) dres = fmax(dres, fabs(m - rc.mu_res[g]));
       if (want_outer) dout = fmax(dout, fabs(m - mu_outer[g]));

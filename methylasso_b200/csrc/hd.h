@@ -34,4 +34,15 @@ ML_HD bool is_finite(double v) {
   return ((f64_bits(v) >> 52) & 0x7ffull) != 0x7ffull;
 }
 
+// num / den.  A zero numerator (an unmethylated position: Nmeth == 0) sends the device's IEEE division down its slow
+// path (a ~150-instruction subroutine; one such lane is enough for the whole warp to take it).  The quotient of a
+// zero by a non-zero, non-NaN divisor is a zero whose sign is the product of the signs: same bits, no call.
+ML_HD double div_nz(double num, double den) {
+#ifdef __CUDA_ARCH__
+  if (num == 0.0 && den != 0.0 && den == den)
+    return __longlong_as_double((__double_as_longlong(num) ^ __double_as_longlong(den)) & (long long)0x8000000000000000ull);
+#endif
+  return num / den;
+}
+
 }  // namespace ml

@@ -22,6 +22,7 @@ namespace ml {
 namespace {
 
 constexpr int STILE = 2048;
+constexpr int SEG_LONG = 256;   // rows; longer segments are summed by a block (k_seg_emit_long)
 
 // ---- generic exclusive scan of int32 flags (3 phases, no inter-block waiting) -----------------
 __global__ void __launch_bounds__(256)
@@ -180,7 +181,8 @@ __global__ void k_seg_emit(const SegGroup* __restrict__ groups, const int32_t* _
                            const int32_t* __restrict__ run_row, const int32_t* __restrict__ seg_of_run,
                            const int32_t* __restrict__ run_pos, const void* __restrict__ start,
                            int start_f64, const double* __restrict__ beta,
-                           const double* __restrict__ betahat, const double* __restrict__ pw, SegOut out) {
+                           const double* __restrict__ betahat, const double* __restrict__ pw, SegOut out,
+                           int32_t* __restrict__ long_list, int32_t* __restrict__ n_long) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_segs) return;
   const int r = seg_run[s];
@@ -198,15 +200,22 @@ __global__ void k_seg_emit(const SegGroup* __restrict__ groups, const int32_t* _
     last = gend;
   }
   const double cb = beta[first];
+  const bool is_long = last - first > SEG_LONG;   // summed by a whole block in k_seg_emit_long
   double d0 = betahat[first] - cb;
   double res = pw[first] * d0;
   double var = res * d0;
   double w = pw[first];
-  for (int64_t i = first + 1; i < last; ++i) {
-    const double d = betahat[i] - beta[i];
-    res += pw[i] * d;
-    var += pw[i] * d * d;
-    w += pw[i];
+  if (is_long) {
+    const int q = atomicAdd(n_long, 1);
+    long_list[2 * q] = s;
+    long_list[2 * q + 1] = (int32_t)(last - first);
+  } else {
+    for (int64_t i = first + 1; i < last; ++i) {
+      const double d = betahat[i] - beta[i];
+      res += pw[i] * d;
+      var += pw[i] * d * d;
+      w += pw[i];
+    }
   }
   const int seg_in_group = s - seg_of_run[run_pos[G.row0]];
   if (out.job) out.job[s] = G.job;
@@ -217,9 +226,51 @@ __global__ void k_seg_emit(const SegGroup* __restrict__ groups, const int32_t* _
   out.end[s] = next_same_group ? (uint32_t)(seg_start_at(G, start, start_f64, last) - 1)
                                : (uint32_t)seg_start_at(G, start, start_f64, gend - 1);
   out.beta[s] = cb;
+  if (is_long) return;
   out.pseudoweight[s] = w;
   out.betahat[s] = res / w + cb;
   out.stdev[s] = sqrt(var / w - res * res / (w * w));
+}
+
+// Segments of more than SEG_LONG rows (background stretches, fused PMD blocks: up to 10^5 rows) would make one
+// thread the tail of the whole launch: one block each instead.  Every thread adds its rows (stride 256) in row
+// order and the partial sums are combined by a fixed tree, so the result depends on the segment alone; it differs
+// from the reference's left-to-right sums in the last bits only (betahat and stdev of such segments; their
+// boundaries, beta and - integer coverage sums being exact in any order - pseudoweight are unaffected).
+__global__ void __launch_bounds__(256)
+k_seg_emit_long(const int32_t* __restrict__ long_list, const int32_t* __restrict__ n_long,
+                const double* __restrict__ beta, const double* __restrict__ betahat, const double* __restrict__ pw,
+                SegOut out) {
+  __shared__ double sm[3][8];
+  const int n = *n_long;
+  for (int q = blockIdx.x; q < n; q += gridDim.x) {
+    const int s = long_list[2 * q];
+    const int64_t first = out.first_row[s], last = first + long_list[2 * q + 1];
+    double res = 0.0, var = 0.0, w = 0.0;
+    for (int64_t i = first + threadIdx.x; i < last; i += 256) {
+      const double d = betahat[i] - beta[i], t = pw[i] * d;
+      res += t;
+      var += t * d;
+      w += pw[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      res += __shfl_xor_sync(0xffffffffu, res, d);
+      var += __shfl_xor_sync(0xffffffffu, var, d);
+      w += __shfl_xor_sync(0xffffffffu, w, d);
+    }
+    __syncthreads();                                   // sm free again (previous segment of this block)
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = res; sm[1][threadIdx.x >> 5] = var; sm[2][threadIdx.x >> 5] = w; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      res = sm[0][0]; var = sm[1][0]; w = sm[2][0];
+      for (int k = 1; k < 8; ++k) { res += sm[0][k]; var += sm[1][k]; w += sm[2][k]; }
+      const double cb = out.beta[s];
+      out.pseudoweight[s] = w;
+      out.betahat[s] = res / w + cb;
+      out.stdev[s] = sqrt(var / w - res * res / (w * w));
+    }
+  }
 }
 
 __global__ void k_run_group(const int32_t* __restrict__ run_row, int32_t n_runs,
@@ -270,14 +321,14 @@ struct RowsFromEstimates {   // FAST result: betahat = pooled Nmeth / pooled cov
   const double* pw;          // and Nmeth / pw is then R's own `Nmeth/coverage`.  Parameters without data in this
   __device__ bool valid(int64_t i) const { return pw[i] > 0; }         // condition (pw == 0) are not rows of mdata.
   __device__ double cov(int64_t i) const { return pw[i]; }
-  __device__ double x(int64_t i) const { return rint(betahat[i] * pw[i]) / pw[i]; }
+  __device__ double x(int64_t i) const { return div_nz(rint(betahat[i] * pw[i]), pw[i]); }
 };
 struct RowsFromCounts {      // host table: pooled Nmeth, coverage per position as given
   const int32_t* nmeth;
   const int32_t* coverage;
   __device__ bool valid(int64_t) const { return true; }
   __device__ double cov(int64_t i) const { return (double)coverage[i]; }
-  __device__ double x(int64_t i) const { return (double)nmeth[i] / (double)coverage[i]; }
+  __device__ double x(int64_t i) const { return div_nz((double)nmeth[i], (double)coverage[i]); }
 };
 
 // double-double accumulator standing in for R's long double sums (summary.c real_mean, cov.c)
@@ -391,100 +442,125 @@ __device__ __forceinline__ DD dd_warp_sum(DD v) {
   return v;
 }
 
-// pass 2, one WARP per segment (coalesced row sweeps).  The parts of a segment (runs without an oversize gap) are
-// found with a ballot over the gap flags and summarised one after the other; within a part the three sums of R's
-// mean() / sd() (sum, correction about the first mean, squares about the refined mean) are reduced across the lanes in
+// pass 2, one warp per segment: first row of each of its parts (a valid row without a valid predecessor in the
+// segment, or further than max_distance from it) -> part_first[part_off[s] + k], part_seg[...] = s
+template <class Rows>
+__global__ void __launch_bounds__(256)
+k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ seg_group, int n_segs,
+             const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
+             const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+             const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
+             int32_t* __restrict__ part_first, int32_t* __restrict__ part_seg) {
+  const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= n_segs) return;
+  if (parts[s] == 0) return;
+  const SegGroup G = groups[seg_group[s]];
+  const int64_t lo = row_lo[s], hi = row_hi[s];
+  int o = part_off[s];
+  for (int64_t base = lo; base < hi; base += 32) {
+    const int64_t i = base + lane;
+    bool head = false;
+    if (i < hi && rows.valid(i)) {
+      int64_t j = i - 1;
+      while (j >= lo && !rows.valid(j)) --j;
+      head = j < lo || (double)seg_start_at(G, pos, pos_f64, i) - (double)seg_start_at(G, pos, pos_f64, j) > max_distance;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int k = o + __popc(bal & ((1u << lane) - 1u));
+      part_first[k] = (int32_t)i;
+      part_seg[k] = s;
+    }
+    o += __popc(bal);
+  }
+}
+
+// pass 3, one WARP per part (row o of the call table; coalesced row sweeps).  The three sums of R's mean() / sd()
+// (sum, correction about the first mean, squares about the refined mean) are reduced across the lanes in
 // double-double, whose error (~1e-32 relative) is far below the final rounding to double, so the order of the
 // additions does not show.
 template <class Rows>
 __global__ void __launch_bounds__(256)
-k_call_emit_warp(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0,
-                 const int32_t* __restrict__ seg_group, int n_segs,
-                 const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
+k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0,
+                 const int32_t* __restrict__ seg_group, int n_parts, const int32_t* __restrict__ row_hi,
                  const int32_t* __restrict__ seg_id, const double* __restrict__ seg_pw,
-                 const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
+                 const void* __restrict__ pos, int pos_f64, Rows rows,
                  const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
-                 const int32_t* __restrict__ gap_off, CallOut out) {
-  const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+                 const int32_t* __restrict__ gap_off, const int32_t* __restrict__ part_first,
+                 const int32_t* __restrict__ part_seg, CallOut out) {
+  const int o = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (s >= n_segs) return;
-  const int np = parts[s];
-  if (np == 0) return;
+  if (o >= n_parts) return;
+  const int s = part_seg[o];
   const int g = seg_group[s];
   const SegGroup G = groups[g];
-  const int64_t lo = row_lo[s], hi = row_hi[s];
-  int shift = gap_off[s] - gap_off[group_seg0[g]];
-  int o = part_off[s];
-  int64_t a = lo;
-  for (int part = 0; part < np; ++part) {
-    // end of the part: the first valid row whose distance to the previous valid row of the part is oversize
-    int64_t b = hi;
-    if (part + 1 < np) {
-      for (int64_t base = a + 1; base < hi && b == hi; base += 32) {
-        const int64_t i = base + lane;
-        bool gap = false;
-        if (i < hi && rows.valid(i)) {
-          int64_t j = i - 1;
-          while (j >= a && !rows.valid(j)) --j;
-          gap = j >= a && (double)seg_start_at(G, pos, pos_f64, i) - (double)seg_start_at(G, pos, pos_f64, j) > max_distance;
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, gap);
-        if (bal) b = base + __ffs(bal) - 1;
-      }
-    }
-    DD sum{0.0, 0.0};
-    double csum = 0.0;
-    int m = 0;
-    int64_t first = b, last = a - 1;
-    for (int64_t i = a + lane; i < b; i += 32) {
-      if (!rows.valid(i)) continue;
-      dd_add(sum, rows.x(i));
-      csum += rows.cov(i);
-      ++m;
-      if (i < first) first = i;
-      last = i;
-    }
-    sum = dd_warp_sum(sum);
+  const int part = o - part_off[s];
+  const int64_t a = part_first[o], b = part + 1 < parts[s] ? (int64_t)part_first[o + 1] : (int64_t)row_hi[s];
+  const int shift = gap_off[s] - gap_off[group_seg0[g]] + part;     // oversize gaps so far in the condition
+  // the methylation values of the first CACHE sweeps of the warp stay in registers for the second and third pass
+  // (a part holds ~50 positions on WGBS data: two sweeps cover most of them)
+  constexpr int CACHE = 2;
+  double xc[CACHE];
+  unsigned have = 0;                                 // bit c: sweep c holds a row in this lane
+  DD sum{0.0, 0.0};
+  double csum = 0.0;
+  int m = 0;
+  int64_t last = a;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      csum += __shfl_xor_sync(0xffffffffu, csum, d);
-      m += __shfl_xor_sync(0xffffffffu, m, d);
-      first = min(first, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)first, d));
-      last = max(last, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)last, d));
-    }
-    double mean = (sum.hi + sum.lo) / m;
-    if (is_finite(mean)) {
-      DD t{0.0, 0.0};
-      for (int64_t i = a + lane; i < b; i += 32) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
-      t = dd_warp_sum(t);
-      mean += (t.hi + t.lo) / m;
-    }
-    double sd = 0.0;
-    if (m >= 2) {
-      DD ss{0.0, 0.0};
-      for (int64_t i = a + lane; i < b; i += 32) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
-      ss = dd_warp_sum(ss);
-      sd = sqrt((ss.hi + ss.lo) / (m - 1));
-    }
-    if (part > 0) ++shift;
-    if (lane == 0) {
-      const double p0 = (double)seg_start_at(G, pos, pos_f64, first), p1 = (double)seg_start_at(G, pos, pos_f64, last);
-      if (out.t.job) out.t.job[o] = G.job;
-      out.t.first_row[o] = (int32_t)first;
-      out.t.estimate_id[o] = G.estimate_id;
-      out.t.seg_id[o] = seg_id[s] + shift;
-      out.t.start[o] = (uint32_t)p0;
-      out.t.end[o] = (uint32_t)p1 + 2u;
-      out.width[o] = (p1 + 2.0) - p0 + 1.0;
-      out.t.beta[o] = mean;
-      out.t.betahat[o] = mean;
-      out.t.pseudoweight[o] = seg_pw[s];
-      out.t.stdev[o] = sd;
-      out.coverage[o] = csum;
-      out.num_cpgs[o] = m;
-    }
-    ++o;
-    a = b;
+  for (int c = 0; c < CACHE; ++c) {
+    const int64_t i = a + lane + 32 * c;
+    const bool ok = i < b && rows.valid(i);
+    xc[c] = ok ? rows.x(i) : 0.0;
+    if (ok) { have |= 1u << c; dd_add(sum, xc[c]); csum += rows.cov(i); ++m; last = i; }
+  }
+  for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) {
+    if (!rows.valid(i)) continue;
+    dd_add(sum, rows.x(i));
+    csum += rows.cov(i);
+    ++m;
+    last = i;
+  }
+  sum = dd_warp_sum(sum);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    csum += __shfl_xor_sync(0xffffffffu, csum, d);
+    m += __shfl_xor_sync(0xffffffffu, m, d);
+    last = max(last, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)last, d));
+  }
+  double mean = (sum.hi + sum.lo) / m;
+  if (is_finite(mean)) {
+    DD t{0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < CACHE; ++c) if (have >> c & 1u) dd_add(t, xc[c] - mean);
+    for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+    t = dd_warp_sum(t);
+    mean += (t.hi + t.lo) / m;
+  }
+  double sd = 0.0;
+  if (m >= 2) {
+    DD ss{0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < CACHE; ++c) if (have >> c & 1u) { const double d = xc[c] - mean; dd_add(ss, d * d); }
+    for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
+    ss = dd_warp_sum(ss);
+    sd = sqrt((ss.hi + ss.lo) / (m - 1));
+  }
+  if (lane == 0) {
+    const double p0 = (double)seg_start_at(G, pos, pos_f64, a), p1 = (double)seg_start_at(G, pos, pos_f64, last);
+    if (out.t.job) out.t.job[o] = G.job;
+    out.t.first_row[o] = (int32_t)a;
+    out.t.estimate_id[o] = G.estimate_id;
+    out.t.seg_id[o] = seg_id[s] + shift;
+    out.t.start[o] = (uint32_t)p0;
+    out.t.end[o] = (uint32_t)p1 + 2u;
+    out.width[o] = (p1 + 2.0) - p0 + 1.0;
+    out.t.beta[o] = mean;
+    out.t.betahat[o] = mean;
+    out.t.pseudoweight[o] = seg_pw[s];
+    out.t.stdev[o] = sd;
+    out.coverage[o] = csum;
+    out.num_cpgs[o] = m;
   }
 }
 
@@ -557,9 +633,14 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
   out.width.alloc(st, (size_t)std::max(1, total));
   out.num_cpgs.alloc(st, (size_t)std::max(1, total));
   CallOut co{out.t.view(), out.coverage.p, out.width.p, out.num_cpgs.p};
-  ML_LAUNCH(eng, "k_call_emit_warp", k_call_emit_warp<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
-      d_groups.p, d_g0.p, seg_group.p, n_segs, row_lo.p, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
-      max_distance, parts.p, part_off.p, gap_off.p, co));
+  DevBuf<int32_t> part_first(st, (size_t)std::max(1, total)), part_seg(st, (size_t)std::max(1, total));
+  ML_LAUNCH(eng, "k_call_parts", k_call_parts<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
+      d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, part_off.p,
+      part_first.p, part_seg.p));
+  if (total > 0)
+    ML_LAUNCH(eng, "k_call_emit_part", k_call_emit_part<Rows><<<cdiv((long long)total * 32, 256), 256, 0, st>>>(
+        d_groups.p, d_g0.p, seg_group.p, total, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
+        parts.p, part_off.p, gap_off.p, part_first.p, part_seg.p, co));
   DevBuf<int32_t> d_c0(st, ng + 1);
   ML_LAUNCH(eng, "k_call_group0", k_call_group0<<<cdiv(ng + 1, 128), 128, 0, st>>>(d_g0.p, ng, n_segs, part_off.p, total, d_c0.p));
   std::vector<int32_t> c0(ng + 1);
@@ -643,9 +724,16 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
     ds.group_est.resize(ng);
     for (int g = 0; g < ng; ++g) { ds.group_job[g] = groups[g].job; ds.group_est[g] = groups[g].estimate_id; }
   }
+  // at most nrows / SEG_LONG segments can be long
+  const int64_t max_long = nrows / SEG_LONG + 1;
+  DevBuf<int32_t> long_list(st, (size_t)(2 * max_long)), n_long(st, 1);
+  n_long.zero();
   ML_LAUNCH(eng, "k_seg_emit", k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
                                                 seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
-                                                d_betahat, d_pw, out));
+                                                d_betahat, d_pw, out, long_list.p, n_long.p));
+  ML_LAUNCH(eng, "k_seg_emit_long",
+            k_seg_emit_long<<<(int)std::min<int64_t>(max_long, (int64_t)eng.sm_count * 8), 256, 0, st>>>(
+                long_list.p, n_long.p, d_beta, d_betahat, d_pw, out));
   ds.has_first_row = true;
   stream_sync(st);
   return n_segs;

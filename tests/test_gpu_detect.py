@@ -33,6 +33,19 @@ def close(a, b, rel=REL):
     return a.shape == b.shape and (a.size == 0 or float(np.max(np.abs(a - b))) <= rel * scale)
 
 
+def seg_row_counts(est_id, est_start, seg):
+    """rows of the estimates table inside each segment (start <= row start <= end within the estimate)."""
+    est_id, est_start = np.asarray(est_id, np.int64), np.asarray(est_start, np.float64)
+    n = np.zeros(len(seg["start"]), np.int64)
+    for e in np.unique(est_id):
+        st = est_start[est_id == e]
+        m = np.nonzero(np.asarray(seg["estimate_id"]) == e)[0]
+        lo = np.searchsorted(st, np.asarray(seg["start"], np.float64)[m], "left")
+        hi = np.searchsorted(st, np.asarray(seg["end"], np.float64)[m], "right")
+        n[m] = hi - lo
+    return n
+
+
 def assert_job_matches(r, o, exact_fast=True):
     est, oest = r["estimates"], o["estimates"]
     assert np.array_equal(est["estimate_id"], oest["estimate_id"])
@@ -101,8 +114,23 @@ def test_reference_generated_fixtures(engine, name):
                                                                                "pseudoweight")}, 0.01)
     for c in ("estimate_id", "segment_id", "start", "end"):
         assert np.array_equal(np.asarray(seg[c], np.int64), g[f"{name}_seg_{c}"].astype(np.int64)), c
-    for c in ("beta", "betahat", "pseudoweight", "stdev"):     # same additions in the same order: bit-identical
-        assert np.array_equal(seg[c], g[f"{name}_seg_{c}"], equal_nan=True), c
+    # segments of up to SEG_LONG = 256 rows: same additions in the same order, bit-identical.  Longer ones are summed
+    # by a block in a fixed tree (k_seg_emit_long): beta (a copy) stays bit-identical, the sums agree to rounding.
+    rows = seg_row_counts(g[f"{name}_est_estimate_id"], g[f"{name}_est_start"], seg)
+    short = rows <= 256
+    assert np.array_equal(seg["beta"], g[f"{name}_seg_beta"], equal_nan=True)
+    for c in ("betahat", "pseudoweight", "stdev"):
+        ref = g[f"{name}_seg_{c}"]
+        assert np.array_equal(seg[c][short], ref[short], equal_nan=True), c
+        if c == "stdev":
+            # sqrt(var / w - (res / w)^2) is NaN or tiny when the true variance is 0 up to rounding (the reference
+            # itself returns NaN there): compare the variances, NaN standing for 0
+            a, b = np.nan_to_num(seg[c][~short]) ** 2, np.nan_to_num(ref[~short]) ** 2
+            assert np.all(np.abs(a - b) <= 1e-10 * np.maximum(1.0, b)), c
+        else:
+            assert np.array_equal(np.isnan(seg[c]), np.isnan(ref)), c
+            ok = ~short & ~np.isnan(ref)
+            assert np.all(np.abs(seg[c][ok] - ref[ok]) <= 1e-12 * np.maximum(1.0, np.abs(ref[ok]))), c
 
 
 @pytest.mark.parametrize("reps,kw", [((1,), {}), ((3,), {}), ((3, 3), {}), ((2,), dict(lambda2=1000.0)),
@@ -215,6 +243,30 @@ def test_segment_helper_generic_tables(engine, oracle):
         sr = engine.segment_methylation_helper(est, 0.01)
         for c in so:
             assert np.array_equal(sr[c], so[c], equal_nan=True), (trial, c)   # rows added in row order: bit-equal
+
+
+def test_segment_helper_long_segments(engine, oracle):
+    """Segments of more than 256 rows are summed by a block (k_seg_emit_long): boundaries, ids, beta and integer
+    pseudo-weights bit-equal, betahat / stdev equal to rounding."""
+    rng = np.random.default_rng(14)
+    sizes = [3, 257, 5000, 1, 100_000, 256, 40_000]
+    levels = np.arange(len(sizes)) * 0.05
+    beta = np.concatenate([np.full(n, v) for n, v in zip(sizes, levels)])
+    n = beta.size
+    ids = np.ones(n, np.int32)
+    ids[sum(sizes[:5]):] = 2
+    est = dict(estimate_id=ids, start=np.cumsum(rng.integers(1, 40, n)).astype(np.int32), beta=beta,
+               betahat=beta + rng.normal(scale=0.1, size=n), pseudoweight=rng.integers(0, 60, n).astype(float))
+    so = oracle.segment_methylation_helper(est, 0.01)
+    sr = engine.segment_methylation_helper(est, 0.01)
+    assert so["start"].size == len(sizes)
+    for c in ("estimate_id", "segment_id", "start", "end", "beta", "pseudoweight"):
+        assert np.array_equal(sr[c], so[c]), c
+    for c in ("betahat", "stdev"):
+        assert np.all(np.abs(sr[c] - so[c]) <= 1e-12 * np.maximum(1.0, np.abs(so[c]))), c
+    short = np.array(sizes) <= 256
+    for c in ("betahat", "stdev"):
+        assert np.array_equal(sr[c][short], so[c][short]), c
 
 
 def test_fast_diff_combine(engine, oracle):
