@@ -263,6 +263,26 @@ ML_API int ml_wilcoxon_groups(ml_engine *eng, int64_t n_groups, const int64_t *x
 /* p.adjust(p, method = 'fdr') of R/call.R:360 (Benjamini-Hochberg); NaN entries stay NaN and are not counted. */
 ML_API int ml_p_adjust_fdr(ml_engine *eng, int64_t n, const double *p, double *q);
 
+/* ---- call_differences (R/call.R:254-333 per chromosome; :348-365 adds the FDR and the threshold filter) ------------
+ * On a resident FAST result of >= 2 conditions to which ml_result_fast_diff_combine has been applied
+ * (= difference_detection_fast), and the batch it was computed from (the raw rows must still be resident): per job
+ * and non-reference condition, the difference estimates are segmented (tol_val), matched with the pooled per-position
+ * data of the condition and of the reference condition (coverage summed, beta = mean of the replicates'
+ * Nmeth / coverage), split at gaps larger than max_distance, grouped while neighbouring differences agree within
+ * min_delta_diff and both exceed min_diff, and every group is summarised: mean / sd of the per-position values on
+ * each side, Cohen's d, the Wilcoxon rank-sum p-value (NA -> 1) and the coverage score.  ref_condition is the
+ * 1-based condition code R/call.R:267 compares `condition` with.  Rows are ordered by (job, estimate_id,
+ * segment_id) (the reference sorts by (start, end) within a chromosome, :331).  Query with NULL outputs for
+ * *n_rows first; any output may be NULL.  The FDR of :360 is ml_p_adjust_fdr over the pval column of all jobs. */
+ML_API int ml_result_call_differences(ml_engine *eng, const ml_batch *b, ml_result *r, int ref_condition,
+                                      double min_diff, double min_delta_diff, double tol_val, double max_distance,
+                                      int64_t *n_rows, int32_t *job, int32_t *condition, int32_t *estimate_id,
+                                      int32_t *segment_id, uint32_t *start, uint32_t *end, double *width,
+                                      double *beta, double *std, double *coverage, int32_t *num_cpgs,
+                                      double *beta_ref, double *std_ref, double *coverage_ref,
+                                      int32_t *num_cpgs_ref, double *pseudoweight, double *diff, double *cohen_d,
+                                      double *pval, double *coverage_score);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,7 @@ SIGNATURES = {
     "ml_result_call_pmd_segments": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, _I64P] + [_P] * 9),
     "ml_wilcoxon_groups": (C.c_int, [_P, C.c_int64] + [_P] * 6),
     "ml_p_adjust_fdr": (C.c_int, [_P, C.c_int64, _P, _P]),
+    "ml_result_call_differences": (C.c_int, [_P, _P, _P, C.c_int] + [C.c_double] * 4 + [_I64P] + [_P] * 20),
     "ml_segment_call_table": (C.c_int, [_P, C.c_int64] + [_P] * 4 + [C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 10),
 }
 

@@ -348,6 +348,27 @@ class Result:
                     ("end", np.uint32), ("width", np.float64), ("beta", np.float64), ("coverage", np.float64),
                     ("pseudoweight", np.float64), ("num_cpgs", np.int32), ("std", np.float64))
 
+    DIFF_COLUMNS = (("job", np.int32), ("condition", np.int32), ("estimate_id", np.int32), ("segment_id", np.int32),
+                    ("start", np.uint32), ("end", np.uint32), ("width", np.float64), ("beta", np.float64),
+                    ("std", np.float64), ("coverage", np.float64), ("num_cpgs", np.int32), ("beta_ref", np.float64),
+                    ("std_ref", np.float64), ("coverage_ref", np.float64), ("num_cpgs_ref", np.int32),
+                    ("pseudoweight", np.float64), ("diff", np.float64), ("cohen_d", np.float64), ("pval", np.float64),
+                    ("coverage_score", np.float64))
+
+    def call_differences(self, batch, ref_condition, min_diff=0.1, min_delta_diff=0.1, tol_val=0.01,
+                         max_distance=500.0, fetch=True):
+        """R/call.R:254-333 (call_differences_singlechr) for every job of a difference_detection_fast result
+        (fast_diff_combine applied); `batch` is the resident input the result was computed from."""
+        n = C.c_int64(0)
+        args = (self.h_eng(), batch.h, self.h, int(ref_condition), float(min_diff), float(min_delta_diff),
+                float(tol_val), float(max_distance))
+        self.eng._check(self.eng.lib.ml_result_call_differences(*args, C.byref(n), *([None] * 20)))
+        if not fetch:
+            return n.value
+        out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.DIFF_COLUMNS}
+        self.eng._check(self.eng.lib.ml_result_call_differences(*args, C.byref(n), *[_p(out[k]) for k, _ in self.DIFF_COLUMNS]))
+        return {k: v[:n.value] for k, v in out.items()}
+
     def call_table(self, tol_val=0.01, max_distance=500.0, fetch=True):
         """R/call.R:43-68 on the resident result (see ml_result_call_table): one row per gap-split segment."""
         n = C.c_int64(0)
@@ -594,11 +615,29 @@ def split_by_chr(data):
     return names, ptr, cols, perm
 
 
+class ResidentFit:
+    """Input batch and result of a genome-wide fit kept in HBM for the calls that follow it (call_differences)."""
+
+    def __init__(self, eng, batch, res, names):
+        self.eng, self.batch, self.res, self.names = eng, batch, res, names
+
+    def free(self):
+        if self.res is not None:
+            self.res.free()
+            self.batch.free()
+            self.res = self.batch = None
+
+
 def _genome_wide(data, params, detection_type, model, engine=None, combine_diff=False, ref=None,
-                 verbose=False):
+                 verbose=False, keep_resident=False):
     eng = engine or default_engine()
     names, ptr, cols, perm = split_by_chr(data)
-    res = eng.detect_batch(ptr, cols, params)
+    batch = None
+    if keep_resident:
+        batch = eng.upload(ptr, cols)
+        res = eng.detect(batch, params)
+    else:
+        res = eng.detect_batch(ptr, cols, params)
     try:
         if combine_diff:
             res.fast_diff_combine()
@@ -608,7 +647,8 @@ def _genome_wide(data, params, detection_type, model, engine=None, combine_diff=
             print("Warning: the following chromosomes did not work:", " ".join(missing))
         jobs = [res.job(j) for j in ok]
     finally:
-        res.free()
+        if not keep_resident:
+            res.free()
     # combine_ret (R/genome_wide.R:6-15)
     est = {k: np.concatenate([r["estimates"][k] for r in jobs]) if jobs else np.empty(0)
            for k in ("estimate_id", "start", "beta", "betahat", "pseudoweight")}
@@ -624,6 +664,8 @@ def _genome_wide(data, params, detection_type, model, engine=None, combine_diff=
         ret["hyper"] = np.array([r["hyper"] for r in jobs])
     if ref is not None:
         ret["ref.cond"] = ref
+    if keep_resident:
+        ret["_resident"] = ResidentFit(eng, batch, res, names)
     return ret
 
 
@@ -651,7 +693,37 @@ def difference_detection(data, ref, optimize_lambda2=False, lambda2=25, max_lamb
 
 
 def difference_detection_fast(data, ref, lambda2=25, tol_val=0.01, max_iter=1, ncores=1, verbose=True,
-                              engine=None):
-    """R/genome_wide.R:121-135 + R/fast_diff.R:12-30."""
+                              engine=None, keep_resident=False):
+    """R/genome_wide.R:121-135 + R/fast_diff.R:12-30.  keep_resident=True leaves the input and the fit in HBM
+    (ret["_resident"]) for call_differences; release them with ret["_resident"].free()."""
     p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
-    return _genome_wide(data, p, "difference", "normal", engine, combine_diff=True, ref=ref, verbose=verbose)
+    return _genome_wide(data, p, "difference", "normal", engine, combine_diff=True, ref=ref, verbose=verbose,
+                        keep_resident=keep_resident)
+
+
+def call_differences(data, ret, min_diff=0.1, pval_cutoff=0.05, fdr_cutoff=1, cov_score=70, min_num_cpgs=4,
+                     tol_val=0.01, ncores=1, verbose=True, min_delta_diff=0.1, max_distance=500.0, return_all=False):
+    """R/call.R:348-365: DMR calls from the result of difference_detection_fast(..., keep_resident=True).
+    Per chromosome call_differences_singlechr (:254-333) runs on the GPU for all chromosomes at once; then the FDR
+    over the genome (:360, on the GPU) and the threshold filter (:363).  `ret["ref.cond"]` is the 1-based code of the
+    reference condition.  Returns the table of :361-363 as a dict of arrays (all rows with return_all=True, plus
+    the boolean column `called`)."""
+    if ret.get("detection.type") != "difference":           # R/call.R:256
+        raise MethyLassoError(19, "Please call call_differences on the result of difference_detection")
+    fit = ret.get("_resident")
+    if fit is None or fit.res is None:
+        raise MethyLassoError(19, "call_differences needs difference_detection_fast(..., keep_resident=True): the "
+                                  "DMR caller works on the fit and the input rows resident in HBM")
+    t = fit.res.call_differences(fit.batch, int(ret["ref.cond"]), min_diff, min_delta_diff, tol_val, max_distance)
+    t = dict(t)
+    t["chr"] = np.asarray(fit.names)[t["job"]] if t["job"].size else np.empty(0, dtype=object)
+    t["ref"] = np.full(t["job"].size, ret["ref.cond"])
+    t["fdr"] = fit.eng.p_adjust_fdr(t["pval"]) if t["pval"].size else np.empty(0)
+    with np.errstate(invalid="ignore"):
+        called = (~np.isnan(t["diff"]) & (np.abs(t["diff"]) >= min_diff) & (t["coverage_score"] >= cov_score)
+                  & (t["pval"] <= pval_cutoff) & (t["fdr"] <= fdr_cutoff)
+                  & (np.minimum(t["num_cpgs"], t["num_cpgs_ref"]) >= min_num_cpgs))
+    if return_all:
+        t["called"] = called
+        return t
+    return {k: v[called] for k, v in t.items()}

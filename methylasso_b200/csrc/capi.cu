@@ -851,4 +851,59 @@ int ml_p_adjust_fdr(ml_engine* eng, int64_t n, const double* p, double* q) {
   ML_CATCH
 }
 
+int ml_result_call_differences(ml_engine* eng, const ml_batch* b, ml_result* r, int ref_condition, double min_diff,
+                               double min_delta_diff, double tol_val, double max_distance, int64_t* n_rows,
+                               int32_t* job, int32_t* condition, int32_t* estimate_id, int32_t* segment_id,
+                               uint32_t* start, uint32_t* end, double* width, double* beta, double* std_,
+                               double* coverage, int32_t* num_cpgs, double* beta_ref, double* std_ref,
+                               double* coverage_ref, int32_t* num_cpgs_ref, double* pseudoweight, double* diff,
+                               double* cohen_d, double* pval, double* coverage_score) {
+  if (!eng || !b || !r || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  Result& R = *r->r;
+  const Batch& B = *b->b;
+  if (!R.diff_combined)
+    return fail(ML_ERR_BAD_ARGUMENT, "Please call call_differences on the result of difference_detection");   // R/call.R:256
+  if (B.njobs != (int)R.jobs.size() || B.nrows != R.nrows)
+    return fail(ML_ERR_BAD_ARGUMENT, "the batch is not the one this result was computed from");
+  const double key[5] = {(double)ref_condition, min_diff, min_delta_diff, tol_val, max_distance};
+  if (!R.diff_cache || memcmp(key, R.diff_key, sizeof key) != 0) {
+    auto t = std::make_shared<DiffCallTable>();
+    call_differences_device(eng->e, B, R, ref_condition, min_diff, min_delta_diff, tol_val, max_distance, *t);
+    R.diff_cache = std::move(t);
+    memcpy(R.diff_key, key, sizeof key);
+  }
+  const DiffCallTable& T = *R.diff_cache;
+  *n_rows = T.n;
+  const size_t n = (size_t)T.n;
+  if (n) {
+    if (job) T.job.download(job, n);
+    if (condition) T.condition.download(condition, n);
+    if (estimate_id) T.estimate_id.download(estimate_id, n);
+    if (segment_id) T.segment_id.download(segment_id, n);
+    if (start) T.start.download(start, n);
+    if (end) T.end.download(end, n);
+    if (width) T.width.download(width, n);
+    if (beta) T.beta.download(beta, n);
+    if (std_) T.std_.download(std_, n);
+    if (coverage) T.coverage.download(coverage, n);
+    if (num_cpgs) T.num_cpgs.download(num_cpgs, n);
+    if (beta_ref) T.beta_ref.download(beta_ref, n);
+    if (std_ref) T.std_ref.download(std_ref, n);
+    if (coverage_ref) T.coverage_ref.download(coverage_ref, n);
+    if (num_cpgs_ref) T.num_cpgs_ref.download(num_cpgs_ref, n);
+    if (pseudoweight) T.pseudoweight.download(pseudoweight, n);
+    if (diff) T.diff.download(diff, n);
+    if (cohen_d) T.cohen_d.download(cohen_d, n);
+    if (pval) T.pval.download(pval, n);
+    if (coverage_score) T.coverage_score.download(coverage_score, n);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
 }  // extern "C"

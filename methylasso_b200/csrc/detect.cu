@@ -1260,6 +1260,11 @@ void result_fast_diff_combine(Engine& eng, Result& r) {
   d_pt.upload(pt);
   ML_LAUNCH(eng, "k_fast_diff", k_fast_diff<<<(int)pt.size(), PAR_TILE, 0, st>>>(d_pt.p, d_jobs.p, r.beta.p, r.betahat.p, r.pw.p));
   stream_sync(st);
+  r.diff_combined = true;
+  r.seg_cache.reset();        // tables computed from the estimates before the combine are stale
+  r.pmd_cache.reset();
+  r.call_cache.reset();
+  r.call_pmd_cache.reset();
 }
 
 }  // namespace ml

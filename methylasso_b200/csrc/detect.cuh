@@ -102,7 +102,25 @@ struct Result {
   DevBuf<double> call_pmd_fused;
   double call_pmd_lambda2 = 0;
   bool counts_exact = false;   // FAST model, one IRLS step: betahat * pw are the pooled methylated counts
+  bool diff_combined = false;  // result_fast_diff_combine has been applied
+  // group_call of the last ml_result_call_differences call and the arguments it was computed with
+  std::shared_ptr<struct DiffCallTable> diff_cache;
+  double diff_key[5] = {0, 0, 0, 0, 0};
 };
+
+// group_call of R/call.R:305-332 (call_differences_singlechr), device arrays; rows ordered by (job, estimate, segment)
+struct DiffCallTable {
+  int64_t n = 0;
+  DevBuf<int32_t> job, condition, estimate_id, segment_id, num_cpgs, num_cpgs_ref;
+  DevBuf<uint32_t> start, end;
+  DevBuf<double> width, beta, std_, coverage, beta_ref, std_ref, coverage_ref, pseudoweight, diff, cohen_d, pval,
+      coverage_score;
+  void alloc(cudaStream_t st, int64_t count);
+};
+// The DMR caller on a resident FAST result after result_fast_diff_combine (segment.cu / diffcall.inc.cuh); the raw
+// rows of the batch the result was computed from must still be resident.  Returns the number of rows.
+int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, int ref_condition, double min_diff,
+                                double min_delta_diff, double tol_val, double max_distance, DiffCallTable& out);
 
 std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
                                     const int32_t* condition, const int32_t* replicate,

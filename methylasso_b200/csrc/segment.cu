@@ -14,8 +14,11 @@
 #include <cstring>
 
 #include "segment.cuh"
+#include "detect.cuh"
 #include "flsa.cuh"
 #include "hd.h"
+#include "stats.cuh"
+#include "x87.cuh"
 
 namespace ml {
 
@@ -771,5 +774,7 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
   stream_sync(st);
   return S;
 }
+
+#include "diffcall.inc.cuh"
 
 }  // namespace ml

@@ -221,19 +221,25 @@ void wilcoxon_groups(Engine& eng, int64_t n_groups, const int64_t* x_ptr, const 
   d_yp.upload(yp);
   d_x.upload(x + x0, (size_t)nx);
   d_y.upload(y + y0, (size_t)ny);
-  DevBuf<WilcoxGroup> grp(st, (size_t)n_groups);
-  grp.zero();
   DevBuf<double> d_p(st, (size_t)n_groups), d_w(st, (size_t)n_groups);
-  const int64_t n_pooled = nx + ny;
-  if (n_pooled > 0)
-    ML_LAUNCH(eng, "k_wilcox_rank",
-              k_wilcox_rank<<<cdiv(n_pooled, 256), 256, 0, st>>>(n_groups, n_pooled, d_xp.p, d_x.p, d_yp.p, d_y.p, grp.p));
-  const int blocks = (int)std::min<int64_t>((n_groups + kPvalWarps - 1) / kPvalWarps, (int64_t)eng.sm_count * 8);
-  ML_LAUNCH(eng, "k_wilcox_pvalue",
-            k_wilcox_pvalue<<<blocks, kPvalWarps * 32, 0, st>>>(n_groups, grp.p, d_p.p, stat ? d_w.p : nullptr));
+  wilcoxon_groups_device(eng, n_groups, d_xp.p, d_x.p, d_yp.p, d_y.p, nx + ny, d_p.p, stat ? d_w.p : nullptr);
   d_p.download(pval, (size_t)n_groups);
   if (stat) d_w.download(stat, (size_t)n_groups);
   stream_sync(st);
+}
+
+// the same on device-resident samples: offsets relative to d_x / d_y, n_pooled = total number of values
+void wilcoxon_groups_device(Engine& eng, int64_t n_groups, const int64_t* d_xptr, const double* d_x, const int64_t* d_yptr,
+                            const double* d_y, int64_t n_pooled, double* d_pval, double* d_stat) {
+  if (n_groups <= 0) return;
+  cudaStream_t st = eng.stream;
+  DevBuf<WilcoxGroup> grp(st, (size_t)n_groups);
+  grp.zero();
+  if (n_pooled > 0)
+    ML_LAUNCH(eng, "k_wilcox_rank",
+              k_wilcox_rank<<<cdiv(n_pooled, 256), 256, 0, st>>>(n_groups, n_pooled, d_xptr, d_x, d_yptr, d_y, grp.p));
+  const int blocks = (int)std::min<int64_t>((n_groups + kPvalWarps - 1) / kPvalWarps, (int64_t)eng.sm_count * 8);
+  ML_LAUNCH(eng, "k_wilcox_pvalue", k_wilcox_pvalue<<<blocks, kPvalWarps * 32, 0, st>>>(n_groups, grp.p, d_pval, d_stat));
 }
 
 void p_adjust_fdr(Engine& eng, int64_t n, const double* p, double* q) {

@@ -146,3 +146,27 @@ def test_clamp_soft_threshold_semantics(emu):
     assert f(40.0, 0.0) == 35.0 and f(-40.0, 0.0) == -35.0 and f(0.3, 0.0) == 0.3
     assert f(0.3, 0.5) == 0.0 and f(-0.3, 0.5) == 0.0 and f(2.0, 0.5) == 1.5 and f(-2.0, 0.5) == -1.5
     assert f(float("nan"), 0.0) == -35.0   # std::max(-35, NaN) keeps -35 (reference behaviour)
+
+
+def test_x87_mean_matches_host_long_double():
+    """methylasso_b200/csrc/x87.cuh (R's mean() with its 80-bit roundings, used for the per-position means of the DMR
+    caller) against the host's long double on methylation-like ratios and on random doubles."""
+    src = os.path.join(HERE, "emu", "emu_x87.cpp")
+    lib = os.path.join(HERE, "emu", "libemu_x87.so")
+    dep = os.path.join(HERE, "..", "methylasso_b200", "csrc", "x87.cuh")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(dep)):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", lib, src])
+    L = C.CDLL(lib)
+    if L.ref_long_double_digits() != 64:
+        pytest.skip("the host's long double is not the x87 80-bit format")
+    L.emu_x87_compare.restype = C.c_longlong
+    L.emu_x87_compare.argtypes = [C.c_longlong, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]
+    rng = np.random.default_rng(1)
+    for n in range(1, 9):
+        m = 100_000
+        cov = rng.integers(1, 60, (m, n))
+        x = np.ascontiguousarray(rng.binomial(cov, rng.random((m, n))) / cov)
+        first = C.c_longlong()
+        assert L.emu_x87_compare(m, n, x.ctypes.data, C.byref(first)) == 0, (n, x[first.value])
+        x = np.ascontiguousarray(rng.random((m, n)) * rng.choice([1e-3, 1.0, 1e3], (m, 1)))
+        assert L.emu_x87_compare(m, n, x.ctypes.data, C.byref(first)) == 0, (n, x[first.value])
