@@ -246,8 +246,87 @@ def kernel_bytes(N, EP, D, words):
     }
 
 
+# ------------------------------------------------------------------------------------------------
+# auxiliary line: configs[2], two-condition DMR calling (3 vs 3 replicates) - not the contract line
+# ------------------------------------------------------------------------------------------------
+def run_dmr(args, local):
+    """difference_detection_fast (MethyLasso.R:453) + call_differences (:463) on a 3-vs-3 synthetic genome: resident
+    step (detect, fast-diff combine, DMR caller, FDR) timed with CUDA events, per-kernel times, and the CPU oracle
+    (C restatement + Python restatement of the R lines) on one small chromosome beside it."""
+    import torch
+    from methylasso_b200 import api
+    from methylasso_b200._native import MlParams
+    torch.cuda.set_device(local)
+    eng = api.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    tables = synth.genome_tables(3, total_cpgs=args.cpgs, reps_per_condition=(3, 3))
+    ptr, cols = synth.concat_jobs(tables)
+    N = int(ptr[-1])
+    params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+    batch = eng.upload(ptr, cols)
+
+    def step():
+        res = eng.detect(batch, params)
+        res.fast_diff_combine()
+        t = res.call_differences(batch, 2, 0.1, 0.1, TOL, MAX_DISTANCE)
+        fdr = eng.p_adjust_fdr(t["pval"])
+        return res, t, fdr
+
+    res, t, fdr = step()
+    U = int(sum(res.sizes(j)[1] for j in range(res.njobs)))
+    res.free()
+    eng.set("profile", 1)
+    for _ in range(max(3, args.warmup)):
+        r, t, fdr = step()
+        r.free()
+    eng.profile_reset()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        r, t, fdr = step()
+        r.free()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    prof = eng.profile()
+    kern = sorted(((k, v[0] / args.steps, v[1] / args.steps) for k, v in prof.items()), key=lambda x: -x[1])
+    called = (~np.isnan(t["diff"]) & (np.abs(t["diff"]) >= 0.1) & (t["coverage_score"] >= 70) & (t["pval"] <= 0.05)
+              & (np.minimum(t["num_cpgs"], t["num_cpgs_ref"]) >= 4))
+    line = {"metric": "CpGs/sec through difference_detection_fast + call_differences (aux, configs[2])",
+            "value": U / (ms * 1e-3), "unit": "CpG/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms,
+            "config": {"workload": "configs[2]: two-condition DMR calling, 3 vs 3 replicates genome-wide",
+                       "cpgs_per_genome": U, "rows_per_genome": N, "chromosomes": len(tables)},
+            "regions": int(t["start"].size), "dmrs_called": int(called.sum()),
+            "gpu_launches": int(eng.launch_count - l0),
+            "kernels": [{"kernel": k, "ms_per_step": round(a, 4), "launches_per_step": b} for k, a, b in kern[:24]]}
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O, diffcall as DC
+        O.build()
+        small = synth.chromosome_table(100_000, 77, (3, 3))
+        t0 = time.perf_counter()
+        o = O.detect(small, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+        est = O.fast_diff_combine(o["estimates"], o["n_params"], o["n_est"])
+        t1 = time.perf_counter()
+        DC.call_differences_singlechr(small, est, 2)
+        t2 = time.perf_counter()
+        line["cpu_baseline"] = {"value": o["n_params"] / (t2 - t0), "unit": "CpG/s", "cores": 1, "kind": "port",
+                                "sample": "one 100 k-CpG chromosome, 3 vs 3; detect %.2f s (C port), call_differences "
+                                          "%.2f s (Python restatement of the R lines: not a timing baseline)" % (t1 - t0, t2 - t1)}
+    print(json.dumps(line), flush=True)
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
+    batch.free()
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--dmr", action="store_true",
+                    help="auxiliary measurement: configs[2] (3 vs 3 DMR calling) instead of the contract line")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -273,6 +352,10 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.dmr:
+        if rank == 0:
+            run_dmr(args, local)
         return
 
     import torch

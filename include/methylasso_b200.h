@@ -136,6 +136,11 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
 ML_API int ml_debug_flsa_backpointers(ml_engine *eng, int64_t n, const double *y, const double *wt,
                                       double lambda2, double *beta, double *tm, double *tp);
 
+/* debugging aid: num[i] / den[i] computed by the chain walker's split division (reciprocal prepared in advance, then the
+ * quotient part of the compiler's own division sequence) and by the plain division; the two must agree bit for bit */
+ML_API int ml_debug_divide(ml_engine *eng, int64_t n, const double *num, const double *den, double *out_split,
+                           double *out_plain);
+
 /* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
  *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
 /* Copy the six columns to the GPU and keep them resident (validation and indexing run on the

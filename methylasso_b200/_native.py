@@ -45,6 +45,7 @@ SIGNATURES = {
     "ml_weighted_1d_flsa_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch_device": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_debug_flsa_backpointers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, _P, _P, _P]),
+    "ml_debug_divide": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "ml_batch_upload": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P), _P]),
     "ml_batch_free": (None, [_P]),
     "ml_batch_detect": (C.c_int, [_P, _P, C.POINTER(MlParams), C.POINTER(_P), _P]),

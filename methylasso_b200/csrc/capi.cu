@@ -147,6 +147,7 @@ int ml_engine_create(int device, ml_engine** out) {
   h->e.sm_count = prop.multiProcessorCount;
   ML_CUDA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
   ML_CUDA(cudaStreamCreateWithFlags(&h->e.copy_stream, cudaStreamNonBlocking));
+  detect_init_device_tables(h->e.stream);
   // the engine's own pool; freed blocks stay in it, so steady-state calls never reach the driver
   cudaMemPoolProps props = {};
   props.allocType = cudaMemAllocationTypePinned;
@@ -902,6 +903,17 @@ int ml_result_call_differences(ml_engine* eng, const ml_batch* b, ml_result* r, 
     if (coverage_score) T.coverage_score.download(coverage_score, n);
   }
   stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_debug_divide(ml_engine* eng, int64_t n, const double* num, const double* den, double* out_split, double* out_plain) {
+  if (!eng || n <= 0 || !num || !den || !out_split || !out_plain) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  debug_divide(eng->e, n, num, den, out_split, out_plain);
   return ML_OK;
   ML_CATCH
 }

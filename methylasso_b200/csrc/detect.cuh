@@ -127,5 +127,7 @@ std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_p
                                     const int32_t* pos, const int32_t* nmeth, const int32_t* cov);
 std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p);
 void result_fast_diff_combine(Engine& eng, Result& r);
+// per-device constant tables of the IRLS kernels (idempotent; called when an engine is created)
+void detect_init_device_tables(cudaStream_t st);
 
 }  // namespace ml

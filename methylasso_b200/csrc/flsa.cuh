@@ -83,4 +83,7 @@ class FlsaPlan {
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);
 };
 
+// debugging aid: num / den through the chain walker's split division (reciprocal prepared first) and plainly
+void debug_divide(Engine& eng, int64_t n, const double* num, const double* den, double* out_split, double* out_plain);
+
 }  // namespace ml
