@@ -414,7 +414,7 @@ def main():
         eng.lib.ml_engine_profile_count(eng.h)
     per_step = (eng.launch_count - lw0) // max(1, args.warmup)
     eng.set("profile_reserve_events", int(2.2 * per_step * (args.steps + 1)))   # no cudaEventCreate while timing
-    eng.set("pool_headroom_percent", 10)     # no cuMemMap inside a timed step
+    eng.set("pool_headroom_percent", 25)     # no cuMemMap inside a timed step
     eng.profile_reset()
     gc.collect()
     gc.disable()

@@ -55,6 +55,8 @@ struct SeriesDesc {
   int32_t n_chunks;     // >= 1 for SERIES_NORMAL
   int32_t mode;
   double lam;
+  int32_t warm;         // warm-up steps in front of each chunk of this series (0: the launch's default)
+  int32_t pad;
 };
 
 struct ChunkDesc {

@@ -479,10 +479,19 @@ k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ se
   }
 }
 
-// pass 3, one WARP per part (row o of the call table; coalesced row sweeps).  The three sums of R's mean() / sd()
+// pass 3, PART_LANES lanes per part (row o of the call table; coalesced row sweeps).  The three sums of R's mean() / sd()
 // (sum, correction about the first mean, squares about the refined mean) are reduced across the lanes in
 // double-double, whose error (~1e-32 relative) is far below the final rounding to double, so the order of the
 // additions does not show.
+constexpr int PART_LANES = 8;     // lanes per part: a part holds ~25-50 positions on WGBS data, four parts share a warp
+__device__ __forceinline__ DD dd_group_sum(DD v) {
+#pragma unroll
+  for (int d = PART_LANES / 2; d > 0; d >>= 1) {
+    DD o{__shfl_xor_sync(0xffffffffu, v.hi, d), __shfl_xor_sync(0xffffffffu, v.lo, d)};
+    v = dd_merge(v, o);
+  }
+  return v;
+}
 template <class Rows>
 __global__ void __launch_bounds__(256)
 k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0,
@@ -492,18 +501,18 @@ k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict_
                  const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
                  const int32_t* __restrict__ gap_off, const int32_t* __restrict__ part_first,
                  const int32_t* __restrict__ part_seg, CallOut out) {
-  const int o = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (o >= n_parts) return;
+  const int o_raw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / PART_LANES);
+  const int lane = threadIdx.x & (PART_LANES - 1);
+  const bool live = o_raw < n_parts;        // the groups of a warp shuffle together: nobody leaves early
+  const int o = live ? o_raw : n_parts - 1;
   const int s = part_seg[o];
   const int g = seg_group[s];
   const SegGroup G = groups[g];
   const int part = o - part_off[s];
   const int64_t a = part_first[o], b = part + 1 < parts[s] ? (int64_t)part_first[o + 1] : (int64_t)row_hi[s];
   const int shift = gap_off[s] - gap_off[group_seg0[g]] + part;     // oversize gaps so far in the condition
-  // the methylation values of the first CACHE sweeps of the warp stay in registers for the second and third pass
-  // (a part holds ~50 positions on WGBS data: two sweeps cover most of them)
-  constexpr int CACHE = 2;
+  // the methylation values of the first CACHE sweeps of the group stay in registers for the second and third pass
+  constexpr int CACHE = 4;
   double xc[CACHE];
   unsigned have = 0;                                 // bit c: sweep c holds a row in this lane
   DD sum{0.0, 0.0};
@@ -512,44 +521,43 @@ k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict_
   int64_t last = a;
 #pragma unroll
   for (int c = 0; c < CACHE; ++c) {
-    const int64_t i = a + lane + 32 * c;
+    const int64_t i = a + lane + PART_LANES * c;
     const bool ok = i < b && rows.valid(i);
     xc[c] = ok ? rows.x(i) : 0.0;
     if (ok) { have |= 1u << c; dd_add(sum, xc[c]); csum += rows.cov(i); ++m; last = i; }
   }
-  for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) {
+  for (int64_t i = a + lane + PART_LANES * CACHE; i < b; i += PART_LANES) {
     if (!rows.valid(i)) continue;
     dd_add(sum, rows.x(i));
     csum += rows.cov(i);
     ++m;
     last = i;
   }
-  sum = dd_warp_sum(sum);
+  sum = dd_group_sum(sum);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) {
+  for (int d = PART_LANES / 2; d > 0; d >>= 1) {
     csum += __shfl_xor_sync(0xffffffffu, csum, d);
     m += __shfl_xor_sync(0xffffffffu, m, d);
     last = max(last, (int64_t)__shfl_xor_sync(0xffffffffu, (long long)last, d));
   }
   double mean = (sum.hi + sum.lo) / m;
+  DD t{0.0, 0.0};
   if (is_finite(mean)) {
-    DD t{0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < CACHE; ++c) if (have >> c & 1u) dd_add(t, xc[c] - mean);
-    for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
-    t = dd_warp_sum(t);
-    mean += (t.hi + t.lo) / m;
+    for (int64_t i = a + lane + PART_LANES * CACHE; i < b; i += PART_LANES) if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
   }
-  double sd = 0.0;
+  t = dd_group_sum(t);                               // every lane of the warp takes part in every shuffle
+  if (is_finite(mean)) mean += (t.hi + t.lo) / m;
+  DD ss{0.0, 0.0};
   if (m >= 2) {
-    DD ss{0.0, 0.0};
 #pragma unroll
     for (int c = 0; c < CACHE; ++c) if (have >> c & 1u) { const double d = xc[c] - mean; dd_add(ss, d * d); }
-    for (int64_t i = a + lane + 32 * CACHE; i < b; i += 32) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
-    ss = dd_warp_sum(ss);
-    sd = sqrt((ss.hi + ss.lo) / (m - 1));
+    for (int64_t i = a + lane + PART_LANES * CACHE; i < b; i += PART_LANES) if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
   }
-  if (lane == 0) {
+  ss = dd_group_sum(ss);
+  const double sd = m >= 2 ? sqrt((ss.hi + ss.lo) / (m - 1)) : 0.0;
+  if (lane == 0 && live) {
     const double p0 = (double)seg_start_at(G, pos, pos_f64, a), p1 = (double)seg_start_at(G, pos, pos_f64, last);
     if (out.t.job) out.t.job[o] = G.job;
     out.t.first_row[o] = (int32_t)a;
@@ -641,7 +649,7 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
       d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, part_off.p,
       part_first.p, part_seg.p));
   if (total > 0)
-    ML_LAUNCH(eng, "k_call_emit_part", k_call_emit_part<Rows><<<cdiv((long long)total * 32, 256), 256, 0, st>>>(
+    ML_LAUNCH(eng, "k_call_emit_part", k_call_emit_part<Rows><<<cdiv((long long)total * PART_LANES, 256), 256, 0, st>>>(
         d_groups.p, d_g0.p, seg_group.p, total, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
         parts.p, part_off.p, gap_off.p, part_first.p, part_seg.p, co));
   DevBuf<int32_t> d_c0(st, ng + 1);
