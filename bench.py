@@ -52,62 +52,62 @@ def peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, read through NVML (pynvml: nvmlDeviceGetClockInfo,
+    nvmlDeviceGetCurrentClocksEventReasons - the fields of the recipe's nvidia-smi clocks line) by the bench's own
+    thread BETWEEN steps of the timed loop (the GPU has been busy for the whole step a few microseconds earlier).
+    Anything that queries the driver concurrently with the CUDA calls of a step stalls them now and then: a separate
+    `nvidia-smi -lms 100` process gave steps of 338 and 452 ms among 15.3 ms ones, an NVML thread polling every
+    10 ms steps of 34 ms; without a concurrent sampler 36 steps in a row stayed within 15.2-15.9 ms.  The time the
+    queries take is inside the timed region and is reported (`query_ms_total`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.t_mark = None
-
-    def mark(self):
-        """Start of the timed region: only samples taken from here on are reported.  The process itself is
-        started earlier, because nvidia-smi's own start-up (NVML initialisation) stalls CUDA calls of every process
-        on the box for 50-350 ms (measured: a 365 ms step right after the launch)."""
-        import datetime
-        self.t_mark = datetime.datetime.now()
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.query_s = 0.0
+        self.max_mhz = None
+        self.nv = self.h = self.get_reasons = None
 
     def start(self):
+        if os.environ.get("ML_BENCH_NO_SAMPLER"):      # debugging aid
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.idx
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv = nv
         except Exception:
-            self.proc = None
+            self.nv = None
+
+    def mark(self):
+        """Start of the timed region: samples taken before are dropped."""
+        self.samples.clear()
+        self.query_s = 0.0
+
+    def sample(self):
+        if self.nv is None:
+            return
+        t0 = time.perf_counter()
+        try:
+            self.samples.append((float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)), int(self.get_reasons(self.h))))
+        except Exception:
+            pass
+        self.query_s += time.perf_counter() - t0
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        import datetime
-        for line in out.strip().splitlines():
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 10:
-                continue
-            try:
-                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
-            except ValueError:
-                ts = None
-            f = f[1:]
-            if self.t_mark is not None and ts is not None and ts < self.t_mark:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
+        mask = 0
+        for _, r in self.samples:
+            mask |= r
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(n for b, n in self.REASONS.items() if mask & b),
+                "samples": len(self.samples), "query_ms_total": round(self.query_s * 1e3, 3),
+                "how": "NVML queried by the bench thread between the steps of the timed loops"}
 
 
 def make_workload(total_cpgs, seed_offset=0):
@@ -374,6 +374,10 @@ def main():
     eng.set_stream(stream.cuda_stream)
     params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
 
+    # started seconds before anything is timed (NVML initialisation, or nvidia-smi's start-up in the fall-back, can
+    # stall CUDA calls for 50-350 ms)
+    sampler = ClockSampler(local)
+    sampler.start()
     tables, ptr, cols = make_workload(args.cpgs, seed_offset=rank)
     N = int(ptr[-1])
     # pinned host copies of the inputs (e2e) and of the outputs
@@ -404,18 +408,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: resident inputs ------------------------------------------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()                          # before the warm-up: its start-up stall must not land in a timed step
-    eng.set("profile", 1)                    # the warm-up also fills the pool of timing events
     lw0 = eng.launch_count
     for _ in range(args.warmup):
         r, _, _ = step_resident()
         r.free()
-        eng.lib.ml_engine_profile_count(eng.h)
     per_step = (eng.launch_count - lw0) // max(1, args.warmup)
-    eng.set("profile_reserve_events", int(2.2 * per_step * (args.steps + 1)))   # no cudaEventCreate while timing
     eng.set("pool_headroom_percent", 25)     # no cuMemMap inside a timed step
-    eng.profile_reset()
     gc.collect()
     gc.disable()
     barrier()
@@ -430,16 +428,33 @@ def main():
         tw0 = time.perf_counter()
         r, nseg, npmd = step_resident()
         r.free()
+        sampler.sample()
         step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
     ev1.record(stream)
     if args.profiler_range:
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
     barrier()
-    gc.enable()
-    clocks = sampler.stop()
     launches = eng.launch_count - l0
     ms = ev0.elapsed_time(ev1) / args.steps
+    clocks = sampler.stop()
+    # the same K steps once more with a pair of CUDA events around every kernel (the per-kernel durations of the
+    # roofline and of `kernels`); kept out of `value`: ~800 event records cost a step about 0.4 ms
+    eng.set("profile", 1)
+    r, _, _ = step_resident()                # fills the engine's pool of timing events
+    r.free()
+    eng.set("profile_reserve_events", int(2.2 * per_step * (args.steps + 1)))   # no cudaEventCreate while timing
+    eng.profile_reset()
+    barrier()
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record(stream)
+    for _ in range(args.steps):
+        r, _, _ = step_resident()
+        r.free()
+    pv1.record(stream)
+    barrier()
+    gc.enable()
+    ms_profiled = pv0.elapsed_time(pv1) / args.steps
     prof = eng.profile()
     prof_work = eng.profile_work()
     eng.set("profile", 0)
@@ -557,12 +572,15 @@ def main():
         gc.disable()                      # no collector pause inside a 50 ms step
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_sampler = sampler
+        e2e_sampler.mark()
         t0 = time.perf_counter()
         e0.record(stream)
         step_wall = []
         for _ in range(args.steps):
             ts0 = time.perf_counter()
             outs = step_e2e()
+            e2e_sampler.sample()
             step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
             if os.environ.get("ML_BENCH_MEMINFO"):
                 step_wall.append(("free_gb", round(torch.cuda.mem_get_info()[0] / 2**30, 3)))
@@ -580,7 +598,7 @@ def main():
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
                "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
-               "host_wall_ms_each_step": step_wall,
+               "host_wall_ms_each_step": step_wall, "clocks": e2e_sampler.stop(),
                "timeline_ms_last_step": sorted(timeline, key=lambda t: t[1][0]),  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
                "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "
                       "ml_result_segments + ml_result_pmd_segments per group, transfers taking turns per direction"}
@@ -624,6 +642,16 @@ def main():
                             "not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped kernels "
                             "of the step are listed in `kernels` with their own fractions"}
 
+    # the largest kernel of the step that IS bandwidth-shaped (elementwise / gather / reduction sweeps of the IRLS loop)
+    latency_bound = ("flsa_warm_kernel", "flsa_main_kernel", "flsa_chain_kernel", "flsa_pass_c_kernel")
+    top_bw = next((t for t in table if t["kernel"] not in latency_bound and t["GBps"]), None)
+    roofline_bw = None
+    if top_bw:
+        roofline_bw = {"kernel": top_bw["kernel"], "bound": "hbm", "achieved": top_bw["GBps"], "peak": pk["hbm_gbs"],
+                       "unit": "GB/s", "frac": top_bw["frac_of_hbm"], "traffic": top_bw["ncu_dram_bytes_per_launch"],
+                       "peak_source": pk_kind, "alg_bytes_per_launch": top_bw["alg_bytes_per_launch"],
+                       "avg_launch_ms": top_bw["avg_launch_ms"]}
+
     # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -643,7 +671,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": table[:16], "resident_pipelined": resident_pool,
+            "roofline": roofline, "roofline_largest_bandwidth_kernel": roofline_bw, "cpu_baseline": cpu,
+            "kernels": table[:16], "resident_pipelined": resident_pool, "ms_per_step_with_kernel_events": ms_profiled,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
             "host_wall_ms_each_step": step_wall_res,
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
