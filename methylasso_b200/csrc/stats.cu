@@ -7,17 +7,20 @@
 //                    group sizes) and adds rank, tie term and sample sizes into the group's accumulators.  Every
 //                    addend is a multiple of 1/2 far below 2^53, so the sums are exact and independent of the order
 //                    of the atomics;
-//   k_wilcox_pvalue  one warp per group: exact two-sided p-value from the rank-sum distribution when both samples
+//   k_wilcox_pvalue  one thread per group: exact two-sided p-value from the rank-sum distribution when both samples
 //                    have fewer than 50 values and there are no ties, normal approximation with continuity and tie
-//                    correction otherwise (wilcox.test.default of R's stats package).  The exact distribution
-//                    (cwilcox of nmath/wilcox.c, a memoised 3-index recurrence there) is built as the power series
-//                    of the Gaussian binomial  prod_{i=1..a} (1 - q^(b+i)) / (1 - q^i)  truncated at degree a*b/2
-//                    (pwilcox only ever sums the lower half), in shared memory: <= 1201 doubles per warp.
+//                    correction otherwise (wilcox.test.default of R's stats package).  The exact distributions
+//                    (cwilcox of nmath/wilcox.c, a memoised 3-index recurrence there) are tabulated once per device
+//                    by k_wilcox_tables: the power series of the Gaussian binomial
+//                    prod_{i=1..a} (1 - q^(b+i)) / (1 - q^i)  truncated at degree a*b/2 (pwilcox only ever sums the
+//                    lower half), built by one warp per pair of sizes in shared memory (<= 1201 doubles).
 // The FDR adjustment is a descending sort (cub radix sort: library plumbing), a scaled running minimum and a scatter.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <cmath>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "common.h"
@@ -107,67 +110,92 @@ __device__ double choose_d(int n, int k) {
   return floor(c + 0.5);
 }
 
+// Exact null distribution of the rank sum for sample sizes a <= b < 50 (cwilcox of nmath/wilcox.c, a memoised 3-index
+// recurrence there): the coefficients of the Gaussian binomial  prod_{i=1..a} (1 - q^(b+i)) / (1 - q^i)  as a power
+// series truncated at degree T = a*b/2 (pwilcox only ever sums the lower half), built by one warp in shared memory.
+__device__ __forceinline__ void wilcox_series(double* P, int a, int b, int T, int lane) {
+  for (int k = lane; k <= T; k += 32) P[k] = k == 0 ? 1.0 : 0.0;
+  __syncwarp();
+  for (int i = 1; i <= a; ++i) {
+    // times (1 - q^s), s = b + i: P[k] -= P[k - s] for k = T .. s, old values on the right-hand side
+    const int s = b + i;
+    for (int base = (T / 32) * 32; base + 31 >= s; base -= 32) {
+      const int k = base + lane;
+      const bool on = k >= s && k <= T;
+      const double v = on ? P[k] - P[k - s] : 0.0;
+      __syncwarp();
+      if (on) P[k] = v;
+      __syncwarp();
+    }
+    // divided by (1 - q^i): P[k] += P[k - i] ascending; the residue classes mod i are independent chains
+    for (int r = lane; r < i && r <= T; r += 32) {
+      double acc = P[r];
+      for (int k = r + i; k <= T; k += i) { acc += P[k]; P[k] = acc; }
+    }
+    __syncwarp();
+  }
+}
+
+// The distributions depend on (a, b) alone and a genome holds 10^5-10^6 regions: they are tabulated once per device,
+// as the running sums pwilcox forms (p += cwilcox(i, m, n) / choose(m + n, n), i = 0, 1, ... in that order), for all
+// 1225 pairs a <= b < 50 (3 MB).  k_wilcox_pvalue then reads one or two entries per region.
+__device__ int32_t g_wil_off[kExactLimit * kExactLimit];
 __global__ void __launch_bounds__(kPvalWarps * 32)
-k_wilcox_pvalue(int64_t n_groups, const WilcoxGroup* __restrict__ grp, double* __restrict__ pval,
-                double* __restrict__ stat) {
+k_wilcox_tables(double* __restrict__ table) {
   __shared__ double series[kPvalWarps][kSeriesLen];
   const int lane = threadIdx.x & 31;
   double* P = series[threadIdx.x >> 5];
-  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
-    const WilcoxGroup G = grp[g];
-    const bool empty = G.mx < 1 || G.my < 1;
-    const double dx = G.mx, dy = G.my;
-    const double W = G.rank_sum - dx * (dx + 1.0) / 2.0;
-    if (stat && lane == 0) stat[g] = empty ? NAN : W;
-    if (empty) { if (lane == 0) pval[g] = NAN; continue; }
-    if (G.mx < kExactLimit && G.my < kExactLimit && !G.ties) {
-      const int a = min(G.mx, G.my), b = max(G.mx, G.my), T = (a * b) / 2;
-      for (int k = lane; k <= T; k += 32) P[k] = k == 0 ? 1.0 : 0.0;
-      __syncwarp();
-      for (int i = 1; i <= a; ++i) {
-        // times (1 - q^s), s = b + i: P[k] -= P[k - s] for k = T .. s, old values on the right-hand side
-        const int s = b + i;
-        for (int base = (T / 32) * 32; base + 31 >= s; base -= 32) {
-          const int k = base + lane;
-          const bool on = k >= s && k <= T;
-          const double v = on ? P[k] - P[k - s] : 0.0;
-          __syncwarp();
-          if (on) P[k] = v;
-          __syncwarp();
-        }
-        // divided by (1 - q^i): P[k] += P[k - i] ascending; the residue classes mod i are independent chains
-        for (int r = lane; r < i && r <= T; r += 32) {
-          double acc = P[r];
-          for (int k = r + i; k <= T; k += i) { acc += P[k]; P[k] = acc; }
-        }
-        __syncwarp();
-      }
-      // pwilcox (nmath/wilcox.c): lower tail sums counts 0 .. q, the upper tail is mirrored into the lower half
-      const double mn = dx * dy, c = choose_d(G.mx + G.my, G.my);
-      const bool upper = W > mn / 2;                    // p <- pwilcox(W - 1, lower.tail = FALSE) else pwilcox(W)
-      double q = floor((upper ? W - 1.0 : W) + 1e-7), p;
-      if (q < 0.0) p = upper ? 1.0 : 0.0;
-      else if (q >= mn) p = upper ? 0.0 : 1.0;
-      else {
-        const bool low_half = q <= mn / 2;
-        const int last = low_half ? (int)q : (int)(mn - q) - 1;      // sum of counts[0 .. last] / c
-        double sum = 0.0;
-        for (int k = lane; k <= last; k += 32) sum += P[k] / c;
-        sum = warp_sum(sum);
-        // lower tail asked for: sum (low half) or 1 - sum; upper tail: 1 - sum (low half) or sum
-        p = (low_half != upper) ? sum : 1.0 - sum;
-      }
-      if (lane == 0) pval[g] = fmin(2 * p, 1.0);
-      __syncwarp();
-    } else if (lane == 0) {
-      double z = W - dx * dy / 2;
-      const double sigma = sqrt((dx * dy / 12) * ((dx + dy + 1) - G.tie_term / ((dx + dy) * (dx + dy - 1))));
-      const double corr = z > 0 ? 0.5 : (z < 0 ? -0.5 : 0.0);
-      z = (z - corr) / sigma;
-      const double pl = 0.5 * erfc(-z / sqrt(2.0)), pu = 0.5 * erfc(z / sqrt(2.0));
-      pval[g] = 2 * fmin(pl, pu);
-    }
+  const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;          // a = pair / 50, b = pair % 50
+  const int a = pair / kExactLimit, b = pair % kExactLimit;
+  if (pair >= kExactLimit * kExactLimit || a < 1 || b < a) return;
+  const int T = (a * b) / 2;
+  wilcox_series(P, a, b, T, lane);
+  if (lane == 0) {
+    const double c = choose_d(a + b, b);
+    double* out = table + g_wil_off[pair];
+    double p = 0.0;
+    for (int k = 0; k <= T; ++k) { p += P[k] / c; out[k] = p; }
+  }
+}
+
+// pwilcox(q, m, n, lower_tail) of nmath/wilcox.c on the tabulated running sums of the pair (min, max)
+__device__ __forceinline__ double pwilcox_tab(double q, int m, int n, bool lower_tail, const double* __restrict__ table) {
+  q = floor(q + 1e-7);
+  const double mn = (double)m * n;
+  if (q < 0.0) return lower_tail ? 0.0 : 1.0;
+  if (q >= mn) return lower_tail ? 1.0 : 0.0;
+  const double* cdf = table + g_wil_off[min(m, n) * kExactLimit + max(m, n)];
+  if (q <= mn / 2) {
+    const double p = cdf[(int)q];
+    return lower_tail ? p : 1.0 - p;
+  }
+  const int last = (int)(mn - q) - 1;                       // p = sum of the first mn - q terms
+  const double p = last >= 0 ? cdf[last] : 0.0;
+  return lower_tail ? 1.0 - p : p;
+}
+
+// wilcox.test.default of R's stats package, two-sided, mu = 0, exact = NULL, correct = TRUE; one thread per group
+__global__ void __launch_bounds__(256)
+k_wilcox_pvalue(int64_t n_groups, const WilcoxGroup* __restrict__ grp, const double* __restrict__ table,
+                double* __restrict__ pval, double* __restrict__ stat) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const WilcoxGroup G = grp[g];
+  const bool empty = G.mx < 1 || G.my < 1;
+  const double dx = G.mx, dy = G.my;
+  const double W = G.rank_sum - dx * (dx + 1.0) / 2.0;
+  if (stat) stat[g] = empty ? NAN : W;
+  if (empty) { pval[g] = NAN; return; }
+  if (G.mx < kExactLimit && G.my < kExactLimit && !G.ties) {
+    const double p = W > dx * dy / 2 ? pwilcox_tab(W - 1, G.mx, G.my, false, table) : pwilcox_tab(W, G.mx, G.my, true, table);
+    pval[g] = fmin(2 * p, 1.0);
+  } else {
+    double z = W - dx * dy / 2;
+    const double sigma = sqrt((dx * dy / 12) * ((dx + dy + 1) - G.tie_term / ((dx + dy) * (dx + dy - 1))));
+    const double corr = z > 0 ? 0.5 : (z < 0 ? -0.5 : 0.0);
+    z = (z - corr) / sigma;
+    const double pl = 0.5 * erfc(-z / sqrt(2.0)), pu = 0.5 * erfc(z / sqrt(2.0));
+    pval[g] = 2 * fmin(pl, pu);
   }
 }
 
@@ -201,6 +229,29 @@ __global__ void k_bh_scatter(int64_t lp, const double* __restrict__ run, const i
 struct MinOp { __device__ __forceinline__ double operator()(double a, double b) const { return fmin(a, b); } };
 
 }  // namespace
+
+// per-device table of the exact distributions, built on first use and kept for the life of the process (3 MB)
+static const double* wilcoxon_table(Engine& eng) {
+  static std::mutex mu;
+  static std::map<int, double*> tables;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = tables.find(eng.device);
+  if (it != tables.end()) return it->second;
+  std::vector<int32_t> off(kExactLimit * kExactLimit, 0);
+  int64_t total = 0;
+  for (int a = 1; a < kExactLimit; ++a)
+    for (int b = a; b < kExactLimit; ++b) { off[a * kExactLimit + b] = (int32_t)total; total += (a * b) / 2 + 1; }
+  double* t = nullptr;
+  ML_CUDA(cudaMalloc(&t, sizeof(double) * (size_t)total));
+  ML_CUDA(cudaMemcpyToSymbol(g_wil_off, off.data(), sizeof(int32_t) * off.size()));
+  const int warps = kExactLimit * kExactLimit;
+  k_wilcox_tables<<<cdiv(warps, kPvalWarps), kPvalWarps * 32, 0, eng.stream>>>(t);
+  ML_CHECK_LAUNCH();
+  ML_CUDA(cudaStreamSynchronize(eng.stream));
+  eng.launches++;
+  tables[eng.device] = t;
+  return t;
+}
 
 void wilcoxon_groups(Engine& eng, int64_t n_groups, const int64_t* x_ptr, const double* x, const int64_t* y_ptr,
                      const double* y, double* pval, double* stat) {
@@ -238,8 +289,8 @@ void wilcoxon_groups_device(Engine& eng, int64_t n_groups, const int64_t* d_xptr
   if (n_pooled > 0)
     ML_LAUNCH(eng, "k_wilcox_rank",
               k_wilcox_rank<<<cdiv(n_pooled, 256), 256, 0, st>>>(n_groups, n_pooled, d_xptr, d_x, d_yptr, d_y, grp.p));
-  const int blocks = (int)std::min<int64_t>((n_groups + kPvalWarps - 1) / kPvalWarps, (int64_t)eng.sm_count * 8);
-  ML_LAUNCH(eng, "k_wilcox_pvalue", k_wilcox_pvalue<<<blocks, kPvalWarps * 32, 0, st>>>(n_groups, grp.p, d_pval, d_stat));
+  const double* table = wilcoxon_table(eng);
+  ML_LAUNCH(eng, "k_wilcox_pvalue", k_wilcox_pvalue<<<cdiv(n_groups, 256), 256, 0, st>>>(n_groups, grp.p, table, d_pval, d_stat));
 }
 
 void p_adjust_fdr(Engine& eng, int64_t n, const double* p, double* q) {

@@ -146,6 +146,67 @@ List signal_detection_fast_batch(const DataFrame& data, const NumericVector& job
   return detect(data, ptr, fast_params(lambda2, tol_val, max_iter), difference);
 }
 
+// NEW: the DMR caller of R/call.R:254-365 in one native call: difference_detection_fast of every chromosome, the
+// per-chromosome call_differences_singlechr tables (segments of the differences, pooled data of both conditions,
+// gap split, grouping, group statistics, Wilcoxon p-value, coverage score) and the FDR over the genome (:360).
+// `ref` is the 1-based code of the reference condition (R/call.R:267 compares as.integer(condition) with it).
+// The threshold filter of :363 stays in R (dmr_calling_gpu in r/R/genome_wide_gpu.R).
+DataFrame call_differences_batch(const DataFrame& data, const NumericVector& job_ptr, int ref, double lambda2,
+                                 double tol_val, double min_diff, double min_delta_diff, double max_distance) {
+  need_columns(data);
+  IntegerVector dset = data["dataset"], cond = data["condition"], rep = data["replicate"], pos = data["pos"],
+                nmeth = data["Nmeth"], cov = data["coverage"];
+  std::vector<int64_t> ptr(job_ptr.begin(), job_ptr.end());
+  const int nj = (int)ptr.size() - 1;
+  ml_batch* batch = nullptr;
+  ml_result* res = nullptr;
+  std::vector<int> status(nj);
+  check(ml_batch_upload(engine(), nj, ptr.data(), dset.begin(), cond.begin(), rep.begin(), pos.begin(), nmeth.begin(),
+                        cov.begin(), &batch, nullptr));
+  const ml_params p = fast_params(lambda2, tol_val, 1);
+  int rc = ml_batch_detect(engine(), batch, &p, &res, status.data());
+  if (rc == ML_OK) rc = ml_result_fast_diff_combine(engine(), res);
+  int64_t n = 0;
+  if (rc == ML_OK)
+    rc = ml_result_call_differences(engine(), batch, res, ref, min_diff, min_delta_diff, tol_val, max_distance, &n,
+                                    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0);
+  if (rc != ML_OK) { ml_result_free(res); ml_batch_free(batch); stop(ml_last_error()); }
+  IntegerVector job(n), condition(n), estimate_id(n), segment_id(n), num(n), num_ref(n);
+  std::vector<uint32_t> start(n), end(n);
+  NumericVector width(n), beta(n), sd(n), coverage(n), beta_ref(n), sd_ref(n), coverage_ref(n), pw(n), diff(n), cohen(n),
+      pval(n), score(n), fdr(n);
+  rc = ml_result_call_differences(engine(), batch, res, ref, min_diff, min_delta_diff, tol_val, max_distance, &n,
+                                  job.begin(), condition.begin(), estimate_id.begin(), segment_id.begin(), start.data(),
+                                  end.data(), width.begin(), beta.begin(), sd.begin(), coverage.begin(), num.begin(),
+                                  beta_ref.begin(), sd_ref.begin(), coverage_ref.begin(), num_ref.begin(), pw.begin(),
+                                  diff.begin(), cohen.begin(), pval.begin(), score.begin());
+  if (rc == ML_OK && n > 0) rc = ml_p_adjust_fdr(engine(), n, pval.begin(), fdr.begin());     // R/call.R:360
+  ml_result_free(res);
+  ml_batch_free(batch);
+  check(rc);
+  NumericVector s(start.begin(), start.end()), e(end.begin(), end.end());
+  return DataFrame::create(_["job"] = job + 1, _["condition"] = condition, _["estimate_id"] = estimate_id,
+                           _["segment_id"] = segment_id, _["start"] = s, _["end"] = e, _["width"] = width, _["beta"] = beta,
+                           _["std"] = sd, _["coverage"] = coverage, _["num.cpgs"] = num, _["beta.ref"] = beta_ref,
+                           _["std.ref"] = sd_ref, _["coverage.ref"] = coverage_ref, _["num.cpgs.ref"] = num_ref,
+                           _["pseudoweight"] = pw, _["diff"] = diff, _["cohen.d"] = cohen, _["pval"] = pval, _["fdr"] = fdr,
+                           _["coverage.score"] = score);
+}
+
+// NEW: wilcox.test(x_g, y_g, conf.int = F)$p.value for many groups (CSR offsets) and p.adjust(p, 'fdr')
+NumericVector wilcoxon_groups(const NumericVector& x_ptr, const NumericVector& x, const NumericVector& y_ptr,
+                              const NumericVector& y) {
+  std::vector<int64_t> xp(x_ptr.begin(), x_ptr.end()), yp(y_ptr.begin(), y_ptr.end());
+  NumericVector p(xp.size() - 1);
+  check(ml_wilcoxon_groups(engine(), (int64_t)xp.size() - 1, xp.data(), x.begin(), yp.data(), y.begin(), p.begin(), nullptr));
+  return p;
+}
+NumericVector p_adjust_fdr(const NumericVector& p) {
+  NumericVector q(p.size());
+  check(ml_p_adjust_fdr(engine(), p.size(), p.begin(), q.begin()));
+  return q;
+}
+
 RCPP_MODULE(MethyLasso_cpp) {
   function("signal_detection_singlechr", &signal_detection_R,
            List::create(_["data"], _["optimize_lambda2"] = false, _["lambda2"] = 50, _["max_lambda2"] = 1000,
@@ -160,4 +221,7 @@ RCPP_MODULE(MethyLasso_cpp) {
                         _["bf_per_kb"] = 50, _["tol_val"] = 0.01, _["max_iter"] = 30));
   function("weighted_1d_flsa", &weighted_1d_flsa, List::create(_["y"], _["wt"], _["lambda2"], _["lambda1"] = 0));
   function("signal_detection_fast_batch", &signal_detection_fast_batch);
+  function("call_differences_batch", &call_differences_batch);
+  function("wilcoxon_groups", &wilcoxon_groups);
+  function("p_adjust_fdr", &p_adjust_fdr);
 }
