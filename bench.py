@@ -19,6 +19,13 @@ memory, including the H2D of the six input columns and the D2H of mu, the estima
 segment tables.  With N > 1 every rank processes its own genome (independent units, no data-path
 collective; weak scaling) and the ranks all-gather their segment-table sizes over NCCL at the end.
 
+Timing hygiene: `value` is one contiguous loop of K steps between two CUDA events, no per-kernel instrumentation
+(the `kernels` table comes from a second pass over the same K steps).  Clocks / throttle reasons are read through NVML
+right before and right after that loop and, polled every 5 ms, during one more untimed repetition of the step: any
+driver query issued while the steps run can stall them (measured).  The boxes are shared and an outside stall of
+0.1-1.5 s hits about one step in a hundred; a loop in which one step took more than 1.3 x the loop's median step
+(undisturbed loops stay within 1.15 x) is listed under `disturbed_attempts` and the loop is timed again (at most twice).
+
 --impl reference times the reference's CPU path for the same workload on the host cores: the oracle's
 plain-C restatement of methylation_detection with the reference's own tf_dp_weight (oracle/_ref,
 compiled verbatim) as the DP, one chromosome per thread (mirrors foreach %dopar% / -t).
@@ -42,6 +49,7 @@ sys.path.insert(0, ROOT)
 from methylasso_b200 import synth  # noqa: E402
 
 LAMBDA2, PMD_LAMBDA2, TOL, MAX_DISTANCE = 25.0, 1000.0, 0.01, 500.0
+DISTURBED = 1.3     # a step slower than this multiple of its loop's median step marks the loop as disturbed from outside
 
 
 def peaks():
@@ -52,13 +60,15 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons during the timed region, read through NVML (pynvml: nvmlDeviceGetClockInfo,
-    nvmlDeviceGetCurrentClocksEventReasons - the fields of the recipe's nvidia-smi clocks line) by the bench's own
-    thread BETWEEN steps of the timed loop (the GPU has been busy for the whole step a few microseconds earlier).
-    Anything that queries the driver concurrently with the CUDA calls of a step stalls them now and then: a separate
-    `nvidia-smi -lms 100` process gave steps of 338 and 452 ms among 15.3 ms ones, an NVML thread polling every
-    10 ms steps of 34 ms; without a concurrent sampler 36 steps in a row stayed within 15.2-15.9 ms.  The time the
-    queries take is inside the timed region and is reported (`query_ms_total`)."""
+    """SM clock and throttle reasons, read through NVML (pynvml: nvmlDeviceGetClockInfo,
+    nvmlDeviceGetCurrentClocksEventReasons - the fields of the recipe's nvidia-smi clocks line).
+    Anything that queries the driver while the steps run disturbs them on these boxes: a separate `nvidia-smi -lms 100`
+    process gave steps of 338 and 452 ms among 15.3 ms ones, an NVML thread polling every 10 ms steps of 34 ms, and
+    even one query between two steps was now and then followed by a step of 82 or 661 ms; without any query 60 steps
+    in a row stayed within 15.2-15.9 ms (one of 19.6).  So the timed loop is bracketed, not interleaved: one sample
+    right before its first step and one right after its last kernel has been enqueued and timed (the GPU has been
+    busy for the whole loop microseconds earlier), and then ONE MORE, UNTIMED repetition of the same step runs with
+    a thread polling NVML every 5 ms - the clocks under exactly this load."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
@@ -98,6 +108,25 @@ class ClockSampler:
             pass
         self.query_s += time.perf_counter() - t0
 
+    def sample_during(self, fn, period_s=0.005):
+        """run fn() once (untimed) while a thread polls NVML"""
+        if self.nv is None:
+            fn()
+            return
+        stop = threading.Event()
+
+        def poll():
+            while not stop.is_set():
+                self.sample()
+                time.sleep(period_s)
+        th = threading.Thread(target=poll, daemon=True)
+        th.start()
+        try:
+            fn()
+        finally:
+            stop.set()
+            th.join(timeout=2)
+
     def stop(self):
         if self.nv is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"], "samples": 0}
@@ -107,7 +136,8 @@ class ClockSampler:
         return {"sm_mhz": float(np.median([s[0] for s in self.samples])) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(n for b, n in self.REASONS.items() if mask & b),
                 "samples": len(self.samples), "query_ms_total": round(self.query_s * 1e3, 3),
-                "how": "NVML queried by the bench thread between the steps of the timed loops"}
+                "how": "NVML: one sample right before and one right after the timed loop, then polled every 5 ms "
+                       "during one more, untimed repetition of the same step"}
 
 
 def make_workload(total_cpgs, seed_offset=0):
@@ -421,26 +451,45 @@ def main():
     gc.collect()
     gc.disable()
     barrier()
-    sampler.mark()
-    l0 = eng.launch_count
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if args.profiler_range:
-        torch.cuda.cudart().cudaProfilerStart()
-    ev0.record(stream)
-    step_wall_res = []
-    for _ in range(args.steps):
-        tw0 = time.perf_counter()
-        r, nseg, npmd = step_resident()
-        r.free()
+    # The GPU boxes are shared: now and then something outside this process (another tenant's driver queries take a
+    # node-wide lock) stalls one step for 0.1-1.5 s (seen with no sampler of our own running: steps of 969 and 1535 ms
+    # among 15 ms ones).  A K-step loop in which a step took more than DISTURBED x the loop's median step is recorded under
+    # `disturbed_attempts` and the whole loop is timed again, at most twice; the reported numbers are those of ONE
+    # contiguous K-step loop.
+    disturbed = []
+    for attempt in range(3):
+        sampler.mark()
         sampler.sample()
-        step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
-    ev1.record(stream)
-    if args.profiler_range:
-        torch.cuda.synchronize()
-        torch.cuda.cudart().cudaProfilerStop()
-    barrier()
-    launches = eng.launch_count - l0
-    ms = ev0.elapsed_time(ev1) / args.steps
+        l0 = eng.launch_count
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profiler_range and attempt == 0:
+            torch.cuda.cudart().cudaProfilerStart()
+        ev0.record(stream)
+        step_wall_res = []
+        for _ in range(args.steps):
+            tw0 = time.perf_counter()
+            r, nseg, npmd = step_resident()
+            r.free()
+            step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
+        ev1.record(stream)
+        sampler.sample()
+        if args.profiler_range and attempt == 0:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
+        barrier()
+        launches = eng.launch_count - l0
+        ms = ev0.elapsed_time(ev1) / args.steps
+        bad = torch.tensor([1.0 if max(step_wall_res) > DISTURBED * float(np.median(step_wall_res)) else 0.0], device="cuda")
+        if world > 1:
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX)       # every rank repeats or none does
+        if bad.item() == 0.0 or attempt == 2 or args.profiler_range:
+            break
+        disturbed.append({"ms_per_step": ms, "host_wall_ms_each_step": step_wall_res})
+
+    def one_more():
+        r_, _, _ = step_resident()
+        r_.free()
+    sampler.sample_during(one_more)
     clocks = sampler.stop()
     # the same K steps once more with a pair of CUDA events around every kernel (the per-kernel durations of the
     # roofline and of `kernels`); kept out of `value`: ~800 event records cost a step about 0.4 ms
@@ -575,24 +624,34 @@ def main():
         gc.collect()
         gc.disable()                      # no collector pause inside a 50 ms step
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2e_sampler = sampler
-        e2e_sampler.mark()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        step_wall = []
-        for _ in range(args.steps):
-            ts0 = time.perf_counter()
-            outs = step_e2e()
+        e2e_disturbed = []
+        for attempt in range(3):             # same policy as for the resident loop
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2e_sampler.mark()
             e2e_sampler.sample()
-            step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
-            if os.environ.get("ML_BENCH_MEMINFO"):
-                step_wall.append(("free_gb", round(torch.cuda.mem_get_info()[0] / 2**30, 3)))
-        torch.cuda.synchronize()
-        e1.record(stream)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            step_wall = []
+            for _ in range(args.steps):
+                ts0 = time.perf_counter()
+                outs = step_e2e()
+                step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
+            torch.cuda.synchronize()
+            e1.record(stream)
+            wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+            barrier()
+            bad = torch.tensor([1.0 if max(step_wall) > DISTURBED * float(np.median(step_wall)) else 0.0], device="cuda")
+            if world > 1:
+                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+            if bad.item() == 0.0 or attempt == 2:
+                break
+            e2e_disturbed.append({"ms_per_step": e0.elapsed_time(e1) / args.steps, "host_wall_ms_each_step": step_wall})
+        timeline_timed = sorted(timeline, key=lambda t: t[1][0])
+        e2e_sampler.sample()
+        e2e_sampler.sample_during(step_e2e)
         barrier()
         gc.enable()
-        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         ems = e0.elapsed_time(e1) / args.steps
         t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -602,8 +661,8 @@ def main():
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
                "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
-               "host_wall_ms_each_step": step_wall, "clocks": e2e_sampler.stop(),
-               "timeline_ms_last_step": sorted(timeline, key=lambda t: t[1][0]),  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
+               "host_wall_ms_each_step": step_wall, "disturbed_attempts": e2e_disturbed, "clocks": e2e_sampler.stop(),
+               "timeline_ms_last_step": timeline_timed,  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
                "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "
                       "ml_result_segments + ml_result_pmd_segments per group, transfers taking turns per direction"}
         pool.close()
@@ -678,7 +737,7 @@ def main():
             "roofline": roofline, "roofline_largest_bandwidth_kernel": roofline_bw, "cpu_baseline": cpu,
             "kernels": table[:16], "resident_pipelined": resident_pool, "ms_per_step_with_kernel_events": ms_profiled,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
-            "host_wall_ms_each_step": step_wall_res,
+            "host_wall_ms_each_step": step_wall_res, "disturbed_attempts": disturbed,
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
         }
         print(json.dumps(line), flush=True)

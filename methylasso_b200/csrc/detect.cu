@@ -627,6 +627,9 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
   const double o = off[J.off0 + t.d];
   const bool write_mu = !(c & CTL_NO_MU);      // the initial evaluation's mu is never read
   const bool need_dres = (c & CTL_DRES) != 0;  // max|mu - mu_res| is only consulted from the 2nd step on
+  // initial evaluation: every parameter is still +0, so the linear response below is +0 whatever the index
+  // (0. + cf * (+0.) summed over the estimators) - the row -> parameter index and the gather are not needed
+  const bool zero_params = (c & CTL_ZERO_PARAMS) != 0;
   constexpr int V = ROW_TILE / 256;
   const int64_t g0 = J.row0 + t.r0;
   int cv[V], nm[V], kx[V];
@@ -636,12 +639,12 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
     const bool in = i < t.cnt;
     cv[q] = in ? rc.cov[g0 + i] : 1;
     nm[q] = in ? rc.nmeth[g0 + i] : 0;
-    kx[q] = in ? rc.pidx[g0 + i] : 0;
+    kx[q] = (in && !zero_params) ? rc.pidx[g0 + i] : 0;
   }
   double eta[V];
 #pragma unroll
   for (int q = 0; q < V; ++q) eta[q] = 0.0;
-  for (int e = 0; e < J.E; ++e) {
+  for (int e = 0; e < J.E && !zero_params; ++e) {
     const double cf = design[J.des0 + t.d * J.E + e];
     if (cf != 0) {
       const double* be = beta + J.par0 + (int64_t)e * J.P;
@@ -692,7 +695,12 @@ k_tv_partial(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
              const int32_t* __restrict__ ctl, const double* __restrict__ beta, double* __restrict__ part) {
   __shared__ double sm[8];
   const ParTile t = tiles[blockIdx.x];
-  if (!(ctl[t.job] & CTL_EVAL)) return;
+  const int c = ctl[t.job];
+  if (!(c & CTL_EVAL)) return;
+  if (c & CTL_ZERO_PARAMS) {                  // initial evaluation: all parameters +0, every |difference| is +0
+    if (threadIdx.x == 0) part[blockIdx.x] = 0.0;
+    return;
+  }
   const JobDev J = jobs[t.job];
   const int k = t.k0 + threadIdx.x;
   double v = 0.0;
@@ -1221,7 +1229,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       const St& s = S[j];
       if (s.state == S_UPDATE) { c |= CTL_UPDATE | CTL_EVAL; any_update = true; }
       if (s.state == S_DAMP) { c |= CTL_DAMP | CTL_EVAL; any_damp = true; }
-      if (s.state == S_INIT_EVAL) c |= CTL_EVAL | CTL_NO_MU;
+      if (s.state == S_INIT_EVAL) c |= CTL_EVAL | CTL_NO_MU | CTL_ZERO_PARAMS;   // parameters are still all zero here
       if (s.state != S_INIT_EVAL && s.it > 0) c |= CTL_DRES;
       if (s.first) c |= CTL_FIRST;
       if (c & CTL_EVAL) any_eval = true;

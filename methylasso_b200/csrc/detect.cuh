@@ -54,7 +54,7 @@ constexpr int PAR_TILE = 256;
 
 enum : int32_t {  // per-job control bits, re-uploaded every global step of the IRLS loop
   CTL_UPDATE = 1, CTL_DAMP = 2, CTL_EVAL = 4, CTL_COPY_RES = 8, CTL_COPY_OUTER = 16, CTL_FIRST = 32,
-  CTL_NO_MU = 64, CTL_DRES = 128
+  CTL_NO_MU = 64, CTL_DRES = 128, CTL_ZERO_PARAMS = 256
 };
 
 struct Batch {
