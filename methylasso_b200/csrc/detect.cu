@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "detect.cuh"
+#include "tiles.cuh"
 
 namespace ml {
 
@@ -76,6 +77,10 @@ __device__ __forceinline__ int lower_bound_i32(const int32_t* __restrict__ a, in
 // ------------------------------------------------------------------------------------------------
 struct VTile { int64_t r0; int32_t job; int32_t cnt; };
 constexpr int VTILE = 2048;
+// tile tables are expanded on the device from per-span descriptions (tiles.cuh)
+struct MakeVTile { __device__ VTile operator()(const TileSpan& s, int, int64_t off, int32_t cnt) const { return VTile{s.i0 + off, s.a, cnt}; } };
+struct MakeRowTile { __device__ RowTile operator()(const TileSpan& s, int, int64_t off, int32_t cnt) const { return RowTile{s.a, s.b, (int32_t)(s.i0 + off), cnt}; } };
+struct MakeParTile { __device__ ParTile operator()(const TileSpan& s, int, int64_t off, int32_t cnt) const { return ParTile{s.a, s.b, (int32_t)(s.i0 + off), cnt}; } };
 
 __global__ void __launch_bounds__(256)
 k_validate(const VTile* __restrict__ tiles, const int64_t* __restrict__ job_ptr,
@@ -160,6 +165,7 @@ __global__ void k_dset_bounds(const int32_t* __restrict__ ent_job, const int32_t
 // ------------------------------------------------------------------------------------------------
 constexpr int WTILE = 2048;  // bitmap words per scan tile
 struct WTileDesc { int64_t w0; int32_t job; int32_t cnt; };
+struct MakeWTile { __device__ WTileDesc operator()(const TileSpan& s, int, int64_t off, int32_t cnt) const { return WTileDesc{s.i0 + off, s.a, cnt}; } };
 
 __global__ void __launch_bounds__(256)
 k_bitmap_mark(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
@@ -906,16 +912,22 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   if (nj == 0) return res;
 
   // ---- K1: validation --------------------------------------------------------------------------
-  std::vector<VTile> vt;
-  for (int j = 0; j < nj; ++j)
-    for (int64_t r = b.job_ptr[j]; r < b.job_ptr[j + 1]; r += VTILE)
-      vt.push_back(VTile{r, j, (int32_t)std::min<int64_t>(VTILE, b.job_ptr[j + 1] - r)});
-  DevBuf<VTile> d_vt(st, std::max<size_t>(1, vt.size()));
-  d_vt.upload(vt);
+  DevBuf<VTile> d_vt;
+  int n_vt = 0;
+  {
+    std::vector<TileSpan> spans;
+    std::vector<int32_t> nt;
+    for (int j = 0; j < nj; ++j) {
+      const int64_t n = b.job_ptr[j + 1] - b.job_ptr[j];
+      spans.push_back(TileSpan{b.job_ptr[j], n, j, 0, VTILE, 0});
+      nt.push_back(span_tiles(n, VTILE));
+    }
+    n_vt = fill_tiles(eng, spans, nt, d_vt, MakeVTile(), "k_fill_tiles");
+  }
   DevBuf<unsigned long long> d_keys(st, nj);
   ML_CUDA(cudaMemsetAsync(d_keys.p, 0xff, sizeof(unsigned long long) * nj, st));
-  if (!vt.empty()) {
-    ML_LAUNCH(eng, "k_validate", k_validate<<<(int)vt.size(), 256, 0, st>>>(d_vt.p, b.d_job_ptr.p, b.dataset.p, b.condition.p,
+  if (n_vt > 0) {
+    ML_LAUNCH(eng, "k_validate", k_validate<<<n_vt, 256, 0, st>>>(d_vt.p, b.d_job_ptr.p, b.dataset.p, b.condition.p,
                                                b.replicate.p, b.pos.p, b.nmeth.p, b.cov.p, d_keys.p));
   }
   // dataset ranges (for jobs whose last-row dataset id is plausible)
@@ -1019,27 +1031,32 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     rows_valid += n;
   }
   // row tiles of valid jobs (per dataset)
-  std::vector<RowTile> rt;
   std::vector<int32_t> h_dtile0(n_ent + 1, 0);
-  for (int j = 0; j < nj; ++j) {
-    JobDev& J = hj[j];
-    if (res->jobs[j].status) {
-      for (int i = job_ent0[j]; i < job_ent0[j + 1]; ++i) h_dtile0[i] = (int32_t)rt.size();
-      continue;
+  int n_rt = 0;
+  {
+    std::vector<TileSpan> spans;
+    std::vector<int32_t> nt;
+    int32_t at = 0;                          // running tile index
+    for (int j = 0; j < nj; ++j) {
+      JobDev& J = hj[j];
+      if (res->jobs[j].status) {
+        for (int i = job_ent0[j]; i < job_ent0[j + 1]; ++i) h_dtile0[i] = at;
+        continue;
+      }
+      J.rtile0 = at;
+      for (int d = 0; d < J.D; ++d) {
+        h_dtile0[J.dptr0 + d] = at;
+        const int r0 = h_dptr[J.dptr0 + d], r1 = h_dptr[J.dptr0 + d + 1];
+        spans.push_back(TileSpan{r0, (int64_t)r1 - r0, j, d, ROW_TILE, 0});
+        nt.push_back(span_tiles((int64_t)r1 - r0, ROW_TILE));
+        at += nt.back();
+      }
+      h_dtile0[J.dptr0 + J.D] = at;
+      J.n_rtiles = at - J.rtile0;
     }
-    J.rtile0 = (int32_t)rt.size();
-    for (int d = 0; d < J.D; ++d) {
-      h_dtile0[J.dptr0 + d] = (int32_t)rt.size();
-      const int r0 = h_dptr[J.dptr0 + d], r1 = h_dptr[J.dptr0 + d + 1];
-      for (int r = r0; r < r1; r += ROW_TILE) rt.push_back(RowTile{j, d, r, std::min(ROW_TILE, r1 - r)});
-    }
-    h_dtile0[J.dptr0 + J.D] = (int32_t)rt.size();
-    J.n_rtiles = (int32_t)rt.size() - J.rtile0;
+    h_dtile0[n_ent] = at;
+    n_rt = fill_tiles(eng, spans, nt, cx.rtiles, MakeRowTile(), "k_fill_tiles");
   }
-  h_dtile0[n_ent] = (int32_t)rt.size();
-  const int n_rt = (int)rt.size();
-  cx.rtiles.alloc(st, std::max(1, n_rt));
-  cx.rtiles.upload(rt);
   cx.dtile0.alloc(st, n_ent + 1);
   cx.dtile0.upload(h_dtile0);
   cx.pidx.alloc(st, (size_t)std::max<int64_t>(1, b.nrows));
@@ -1054,29 +1071,35 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   if (fast && n_rt) {
     for (int j = 0; j < nj; ++j) h_bm0[j + 1] += h_bm0[j];
     const int64_t nwords = h_bm0[nj];
-    std::vector<WTileDesc> wt;
     std::vector<int32_t> job_wtile0(nj + 1, 0);
-    for (int j = 0; j < nj; ++j) {
-      job_wtile0[j] = (int32_t)wt.size();
-      for (int64_t w = h_bm0[j]; w < h_bm0[j + 1]; w += WTILE)
-        wt.push_back(WTileDesc{w, j, (int32_t)std::min<int64_t>(WTILE, h_bm0[j + 1] - w)});
+    int n_wt = 0;
+    {
+      std::vector<TileSpan> spans;
+      std::vector<int32_t> nt;
+      for (int j = 0; j < nj; ++j) {
+        job_wtile0[j] = n_wt;
+        const int64_t n = h_bm0[j + 1] - h_bm0[j];
+        spans.push_back(TileSpan{h_bm0[j], n, j, 0, WTILE, 0});
+        nt.push_back(span_tiles(n, WTILE));
+        n_wt += nt.back();
+      }
+      job_wtile0[nj] = n_wt;
+      fill_tiles(eng, spans, nt, d_wt, MakeWTile(), "k_fill_tiles");
     }
-    job_wtile0[nj] = (int32_t)wt.size();
     d_bitmap.alloc(st, (size_t)std::max<int64_t>(1, nwords));
     d_bitmap.zero();
     d_wprefix.alloc(st, (size_t)std::max<int64_t>(1, nwords));
     d_bm0.alloc(st, nj + 1);  d_bm0.upload(h_bm0);
     d_minpos.alloc(st, nj);   d_minpos.upload(h_minpos);
-    d_wt.alloc(st, std::max<size_t>(1, wt.size())); d_wt.upload(wt);
-    d_wtile_count.alloc(st, std::max<size_t>(1, wt.size()));
+    d_wtile_count.alloc(st, (size_t)std::max(1, n_wt));
     d_job_wtile0.alloc(st, nj + 1); d_job_wtile0.upload(job_wtile0);
     d_job_unique.alloc(st, nj);
     cx.jobs.upload(hj);  // row0 etc. are final; P / par0 / tab0 follow after the count
     ML_LAUNCH(eng, "k_bitmap_mark", k_bitmap_mark<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p));
-    ML_LAUNCH(eng, "k_bitmap_tile_count", k_bitmap_tile_count<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p));
+    ML_LAUNCH(eng, "k_bitmap_tile_count", k_bitmap_tile_count<<<n_wt, 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p));
     ML_LAUNCH(eng, "k_bitmap_job_scan", k_bitmap_job_scan<<<cdiv((long long)nj * 32, 128), 128, 0, st>>>(d_job_wtile0.p, nj, d_wtile_count.p,
                                                                      d_job_unique.p));
-    ML_LAUNCH(eng, "k_bitmap_word_prefix", k_bitmap_word_prefix<<<(int)wt.size(), 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p));
+    ML_LAUNCH(eng, "k_bitmap_word_prefix", k_bitmap_word_prefix<<<n_wt, 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_wprefix.p));
     std::vector<int32_t> uniq(nj);
     d_job_unique.download(uniq.data(), nj);
     stream_sync(st);
@@ -1092,7 +1115,9 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       if (!res->jobs[j].status) res->jobs[j].status = 13;
 
   // ---- layout of parameter arrays -------------------------------------------------------------------
-  std::vector<ParTile> pt;
+  std::vector<TileSpan> pt_spans;
+  std::vector<int32_t> pt_nt;
+  int32_t pt_at = 0;
   std::vector<FlsaSeries> series;
   std::vector<int64_t> h_start0(nj, 0);
   int64_t npar = 0, ntab = 0, nstart = 0;
@@ -1104,13 +1129,15 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     jh.par0 = npar;
     J.tab0 = ntab;
     J.ser0 = (int32_t)series.size();
-    J.ptile0 = (int32_t)pt.size();
+    J.ptile0 = pt_at;
     h_start0[j] = nstart;
     for (int e = 0; e < J.E; ++e) {
       series.push_back(FlsaSeries{npar + (int64_t)e * J.P, J.P, p.lambda2});
-      for (int k = 0; k < J.P; k += PAR_TILE) pt.push_back(ParTile{j, e, k, std::min(PAR_TILE, J.P - k)});
+      pt_spans.push_back(TileSpan{0, (int64_t)J.P, j, e, PAR_TILE, 0});
+      pt_nt.push_back(span_tiles(J.P, PAR_TILE));
+      pt_at += pt_nt.back();
     }
-    J.n_ptiles = (int32_t)pt.size() - J.ptile0;
+    J.n_ptiles = pt_at - J.ptile0;
     npar += (int64_t)J.E * J.P;
     ntab += (int64_t)J.D * J.P;
     nstart += J.P;
@@ -1119,10 +1146,8 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   res->noff = noff;
   res->nstart = nstart;
   res->start0 = h_start0;
-  const int n_pt = (int)pt.size();
   cx.jobs.upload(hj);
-  cx.ptiles.alloc(st, std::max(1, n_pt));
-  cx.ptiles.upload(pt);
+  const int n_pt = fill_tiles(eng, pt_spans, pt_nt, cx.ptiles, MakeParTile(), "k_fill_tiles");
   cx.design.alloc(st, std::max<size_t>(1, h_design.size()));
   cx.design.upload(h_design);
   cx.start0.alloc(st, nj);
