@@ -497,7 +497,7 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
   DevBuf<int32_t> part_first(st, n_parts), part_seg(st, n_parts);
   ML_LAUNCH(eng, "k_call_parts", k_call_parts<RowsDiff><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
       d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, R.start.p, 1, rows, max_distance, parts.p, part_off.p,
-      part_first.p, part_seg.p));
+      part_first.p, part_seg.p, nullptr));
   // ---- seg_call (:291-298) ---------------------------------------------------------------------------------
   DevBuf<int32_t> p_seg(st, n_parts), p_a(st, n_parts), p_b(st, n_parts), p_num(st, n_parts), p_numr(st, n_parts);
   DevBuf<uint32_t> p_start(st, n_parts), p_end(st, n_parts);

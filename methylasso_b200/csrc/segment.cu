@@ -325,6 +325,10 @@ struct RowsFromEstimates {   // FAST result: betahat = pooled Nmeth / pooled cov
   __device__ bool valid(int64_t i) const { return pw[i] > 0; }         // condition (pw == 0) are not rows of mdata.
   __device__ double cov(int64_t i) const { return pw[i]; }
   __device__ double x(int64_t i) const { return div_nz(rint(betahat[i] * pw[i]), pw[i]); }
+  // the same in two steps: plain loads first (raw, cov), arithmetic later
+  __device__ double raw(int64_t i) const { return betahat[i]; }
+  __device__ bool valid_cov(double c) const { return c > 0; }
+  __device__ double x_from(double r, double c) const { return div_nz(rint(r * c), c); }
 };
 struct RowsFromCounts {      // host table: pooled Nmeth, coverage per position as given
   const int32_t* nmeth;
@@ -332,6 +336,9 @@ struct RowsFromCounts {      // host table: pooled Nmeth, coverage per position 
   __device__ bool valid(int64_t) const { return true; }
   __device__ double cov(int64_t i) const { return (double)coverage[i]; }
   __device__ double x(int64_t i) const { return div_nz((double)nmeth[i], (double)coverage[i]); }
+  __device__ double raw(int64_t i) const { return (double)nmeth[i]; }
+  __device__ bool valid_cov(double) const { return true; }
+  __device__ double x_from(double r, double c) const { return div_nz(r, c); }
 };
 
 // double-double accumulator standing in for R's long double sums (summary.c real_mean, cov.c)
@@ -453,14 +460,15 @@ k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ se
              const int32_t* __restrict__ row_lo, const int32_t* __restrict__ row_hi,
              const void* __restrict__ pos, int pos_f64, Rows rows, double max_distance,
              const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
-             int32_t* __restrict__ part_first, int32_t* __restrict__ part_seg) {
+             int32_t* __restrict__ part_first, int32_t* __restrict__ part_seg, int32_t* __restrict__ part_end) {
   const int s = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (s >= n_segs) return;
   if (parts[s] == 0) return;
   const SegGroup G = groups[seg_group[s]];
   const int64_t lo = row_lo[s], hi = row_hi[s];
-  int o = part_off[s];
+  const int o0 = part_off[s];
+  int o = o0;
   for (int64_t base = lo; base < hi; base += 32) {
     const int64_t i = base + lane;
     bool head = false;
@@ -474,9 +482,11 @@ k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ se
       const int k = o + __popc(bal & ((1u << lane) - 1u));
       part_first[k] = (int32_t)i;
       part_seg[k] = s;
+      if (part_end && k > o0) part_end[k - 1] = (int32_t)i;   // a part ends where the next one of the segment begins
     }
     o += __popc(bal);
   }
+  if (part_end && lane == 0 && o > o0) part_end[o - 1] = (int32_t)hi;
 }
 
 // pass 3, PART_LANES lanes per part (row o of the call table; coalesced row sweeps).  The three sums of R's mean() / sd()
@@ -493,23 +503,25 @@ __device__ __forceinline__ DD dd_group_sum(DD v) {
   return v;
 }
 template <class Rows>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict__ group_seg0,
                  const int32_t* __restrict__ seg_group, int n_parts, const int32_t* __restrict__ row_hi,
                  const int32_t* __restrict__ seg_id, const double* __restrict__ seg_pw,
                  const void* __restrict__ pos, int pos_f64, Rows rows,
                  const int32_t* __restrict__ parts, const int32_t* __restrict__ part_off,
                  const int32_t* __restrict__ gap_off, const int32_t* __restrict__ part_first,
-                 const int32_t* __restrict__ part_seg, CallOut out) {
+                 const int32_t* __restrict__ part_seg, const int32_t* __restrict__ part_end, CallOut out) {
   const int o_raw = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / PART_LANES);
   const int lane = threadIdx.x & (PART_LANES - 1);
   const bool live = o_raw < n_parts;        // the groups of a warp shuffle together: nobody leaves early
   const int o = live ? o_raw : n_parts - 1;
+  // the row range comes straight from the part tables, so that the row sweeps start one load after the kernel does;
+  // the chain part -> segment -> group is only needed for the labels written at the end
+  const int64_t a = part_first[o], b = part_end[o];
   const int s = part_seg[o];
   const int g = seg_group[s];
   const SegGroup G = groups[g];
   const int part = o - part_off[s];
-  const int64_t a = part_first[o], b = part + 1 < parts[s] ? (int64_t)part_first[o + 1] : (int64_t)row_hi[s];
   const int shift = gap_off[s] - gap_off[group_seg0[g]] + part;     // oversize gaps so far in the condition
   // the methylation values of the first CACHE sweeps of the group stay in registers for the second and third pass
   constexpr int CACHE = 4;
@@ -519,12 +531,22 @@ k_call_emit_part(const SegGroup* __restrict__ groups, const int32_t* __restrict_
   double csum = 0.0;
   int m = 0;
   int64_t last = a;
+  // the loads of all CACHE sweeps are issued before anything is done with them (the kernel waits for memory: ncu
+  // shows stall_long_sb on the first use of every value loaded here)
+  double cvc[CACHE];
 #pragma unroll
   for (int c = 0; c < CACHE; ++c) {
     const int64_t i = a + lane + PART_LANES * c;
-    const bool ok = i < b && rows.valid(i);
-    xc[c] = ok ? rows.x(i) : 0.0;
-    if (ok) { have |= 1u << c; dd_add(sum, xc[c]); csum += rows.cov(i); ++m; last = i; }
+    const bool in = i < b;
+    cvc[c] = in ? rows.cov(i) : 0.0;
+    xc[c] = in ? rows.raw(i) : 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < CACHE; ++c) {
+    const int64_t i = a + lane + PART_LANES * c;
+    const bool ok = i < b && rows.valid_cov(cvc[c]);
+    xc[c] = ok ? rows.x_from(xc[c], cvc[c]) : 0.0;
+    if (ok) { have |= 1u << c; dd_add(sum, xc[c]); csum += cvc[c]; ++m; last = i; }
   }
   for (int64_t i = a + lane + PART_LANES * CACHE; i < b; i += PART_LANES) {
     if (!rows.valid(i)) continue;
@@ -644,14 +666,15 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
   out.width.alloc(st, (size_t)std::max(1, total));
   out.num_cpgs.alloc(st, (size_t)std::max(1, total));
   CallOut co{out.t.view(), out.coverage.p, out.width.p, out.num_cpgs.p};
-  DevBuf<int32_t> part_first(st, (size_t)std::max(1, total)), part_seg(st, (size_t)std::max(1, total));
+  DevBuf<int32_t> part_first(st, (size_t)std::max(1, total)), part_seg(st, (size_t)std::max(1, total)),
+      part_end(st, (size_t)std::max(1, total));
   ML_LAUNCH(eng, "k_call_parts", k_call_parts<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
       d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, part_off.p,
-      part_first.p, part_seg.p));
+      part_first.p, part_seg.p, part_end.p));
   if (total > 0)
     ML_LAUNCH(eng, "k_call_emit_part", k_call_emit_part<Rows><<<cdiv((long long)total * PART_LANES, 256), 256, 0, st>>>(
         d_groups.p, d_g0.p, seg_group.p, total, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
-        parts.p, part_off.p, gap_off.p, part_first.p, part_seg.p, co));
+        parts.p, part_off.p, gap_off.p, part_first.p, part_seg.p, part_end.p, co));
   DevBuf<int32_t> d_c0(st, ng + 1);
   ML_LAUNCH(eng, "k_call_group0", k_call_group0<<<cdiv(ng + 1, 128), 128, 0, st>>>(d_g0.p, ng, n_segs, part_off.p, total, d_c0.p));
   std::vector<int32_t> c0(ng + 1);
