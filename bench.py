@@ -264,8 +264,9 @@ def kernel_bytes(N, EP, D, words):
         "flsa_bwd_reduce_kernel": 16 * EP,
         "flsa_bwd_apply_kernel": 32 * EP,
         "k_center": 16 * EP,
-        "k_eval_rows": 36 * N,
-        "k_tv_partial": 8 * EP,
+        "k_eval_rows": 22 * N,          # two launches per step: the initial evaluation reads nmeth, cov (8 N: every parameter is
+                                        # still zero, no index, no gather, no mu), the one after the update 36 N; average
+        "k_tv_partial": 4 * EP,         # likewise: the initial launch writes zeros, the second reads beta (8 EP)
         "k_seg_run_heads": 12 * EP,
         "k_seg_emit": 28 * EP,          # beta, betahat, pw, start once (two launches: the second one is on the call table)
         "k_call_count": 16 * EP,        # pos, pw
