@@ -455,7 +455,8 @@ k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
 // issued together (the kernel is bound by the latency of these dependent loads), and W comes from the table.
 // Operations and their order are those of k_pseudodata (What = 0 + W, Zs = 0 + z W, ...): same bits.
 constexpr int PD_FAST_D = 8;
-__global__ void __launch_bounds__(PAR_TILE, 4)
+template <int PD_D>                      // datasets held in registers: 4 (more resident warps) or PD_FAST_D
+__global__ void __launch_bounds__(PAR_TILE, PD_D <= 4 ? 6 : 4)
 k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
                   const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
                   const int32_t* __restrict__ rowstart, double* __restrict__ beta, double* __restrict__ old_beta,
@@ -470,26 +471,26 @@ k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ 
   const int first = (c & CTL_FIRST) ? 1 : 0;
   const int k = t.k0 + threadIdx.x;
   const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
-  double Cd[PD_FAST_D];
-  int r0s[PD_FAST_D], cv[PD_FAST_D], nm[PD_FAST_D];
-  double mp[PD_FAST_D];
+  double Cd[PD_D];
+  int r0s[PD_D], cv[PD_D], nm[PD_D];
+  double mp[PD_D];
 #pragma unroll
-  for (int d = 0; d < PD_FAST_D; ++d) {
+  for (int d = 0; d < PD_D; ++d) {
     Cd[d] = d < J.D ? design[J.des0 + d * J.E + t.e] : 0.0;
     r0s[d] = (d < J.D && Cd[d] != 0) ? rowstart[J.tab0 + (int64_t)d * J.P + k] : -1;
   }
 #pragma unroll
-  for (int d = 0; d < PD_FAST_D; ++d) {
+  for (int d = 0; d < PD_D; ++d) {
     const int64_t g = J.row0 + (r0s[d] >= 0 ? r0s[d] : 0);
     cv[d] = r0s[d] >= 0 ? rc.cov[g] : 1;
     nm[d] = r0s[d] >= 0 ? rc.nmeth[g] : 0;
     mp[d] = (r0s[d] >= 0 && !first) ? rc.mu_res[g] : 0.0;
   }
   const double b = beta[pi];
-  double Wd[PD_FAST_D], Zd[PD_FAST_D];
+  double Wd[PD_D], Zd[PD_D];
   double wt = 0.0;
 #pragma unroll
-  for (int d = 0; d < PD_FAST_D; ++d) {
+  for (int d = 0; d < PD_D; ++d) {
     Wd[d] = 0.0;
     Zd[d] = 0.0;
     if (r0s[d] >= 0) {
@@ -504,7 +505,7 @@ k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ 
   if (!is_finite(inv)) inv = 0.0;        // pseudo-inverse (pseudodata_helpers.hpp:33-34)
   double bh = 0.0;
 #pragma unroll
-  for (int d = 0; d < PD_FAST_D; ++d) {
+  for (int d = 0; d < PD_D; ++d) {
     if (r0s[d] >= 0) {
       const double q = Zd[d] / Wd[d];
       const double zhat = (Wd[d] == 0) ? Wd[d] : q;
@@ -1262,10 +1263,14 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     }
     cx.ctl.upload(ctl);
     if (any_update) {
-      if (p.model == MODEL_FAST && max_D <= PD_FAST_D)
-        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
-                                                     cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
-                                                     res->pw.p));
+      if (p.model == MODEL_FAST && max_D <= 4)
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<4><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+                                                        cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
+                                                        res->pw.p));
+      else if (p.model == MODEL_FAST && max_D <= PD_FAST_D)
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<PD_FAST_D><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+                                                                cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
+                                                                res->pw.p));
       else
         ML_LAUNCH(eng, "k_pseudodata", k_pseudodata<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.dptr.p, cx.design.p,
                                                 cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
