@@ -359,9 +359,77 @@ def run_dmr(args, local):
             "regions": int(t["start"].size), "dmrs_called": int(called.sum()), "host_wall_ms_each_step": step_wall,
             "gpu_launches": int(eng.launch_count - l0),
             "kernels": [{"kernel": k, "ms_per_step": round(a, 4), "launches_per_step": b} for k, a, b in kern[:24]]}
+    # ---- e2e: host buffers in, region table out (what r/R/genome_wide_gpu.R::dmr_calling_gpu does) ------------------
+    # chromosomes in G groups, one engine + host thread per group: pinned H2D of the six... four moved input columns,
+    # detect, fast-diff combine, call_differences with its table downloaded; then one FDR over all regions.
+    if not args.no_e2e:
+        G = max(1, args.e2e_groups)
+        pool = api.EnginePool(G, local)
+        groups = []
+        for jobs, gptr, gcols in api.split_jobs(ptr, cols, G):
+            pin_in = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in gcols.items()}
+            groups.append((jobs, gptr, pin_in))
+
+        def run_group(eng_g, grp):
+            jobs, gptr, pin_in = grp
+            with pool.h2d_turn:
+                bt = eng_g.upload(gptr, pin_in)
+            rr = eng_g.detect(bt, params)
+            rr.fast_diff_combine()
+            tt = rr.call_differences(bt, 2, 0.1, 0.1, TOL, MAX_DISTANCE)
+            rr.free()
+            bt.free()
+            return tt
+
+        def step_e2e():
+            outs = pool.map(run_group, groups)
+            pv = np.concatenate([o["pval"] for o in outs])
+            return outs, pool.engines[0].p_adjust_fdr(pv)
+        for _ in range(3):
+            outs, q = step_e2e()
+        for e_g in pool.engines:
+            e_g.set("pool_headroom_percent", 25)
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        x0.record(stream)
+        e_wall = []
+        for _ in range(args.steps):
+            tw0 = time.perf_counter()
+            outs, q = step_e2e()
+            e_wall.append(round((time.perf_counter() - tw0) * 1e3, 1))
+        torch.cuda.synchronize()
+        x1.record(stream)
+        torch.cuda.synchronize()
+        ems = x0.elapsed_time(x1) / args.steps
+        d2h = int(sum(v.nbytes for o in outs for v in o.values()) + q.nbytes)
+        line["e2e"] = {"value": U / (ems * 1e-3), "unit": "CpG/s", "ms_per_step": ems, "engines": G,
+                       "h2d_bytes_per_step": 24 * N, "d2h_bytes_per_step": d2h, "host_wall_ms_each_step": e_wall,
+                       "regions": int(sum(o["start"].size for o in outs)),
+                       "api": "per chromosome group: ml_batch_upload + ml_batch_detect + ml_result_fast_diff_combine + "
+                              "ml_result_call_differences (table downloaded); then ml_p_adjust_fdr over all regions"}
+        pool.close()
     if not args.no_cpu_baseline:
         from oracle import oracle as O, diffcall as DC
         O.build()
+        # conservative CPU arm for this config: the FIT ALONE (oracle C port + the reference's verbatim DP) of four
+        # chromosomes, one per host thread - without any of the region calling the GPU line includes
+        samp = tables[:4]
+        Us = [0] * len(samp)
+
+        def fit(i):
+            o_ = O.detect(samp[i], O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+            O.fast_diff_combine(o_["estimates"], o_["n_params"], o_["n_est"])
+            Us[i] = int(o_["n_params"])
+        tc0 = time.perf_counter()
+        ths = [threading.Thread(target=fit, args=(i,)) for i in range(len(samp))]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        tc1 = time.perf_counter()
+        line["cpu_fit_only"] = {"value": sum(Us) / (tc1 - tc0), "unit": "CpG/s", "cores": len(samp), "kind": "port",
+                                "sample": "difference_detection_fast of the 4 largest chromosomes (%d CpGs, 3 vs 3), one per "
+                                          "thread, %.1f s; no region calling" % (sum(Us), tc1 - tc0)}
         small = synth.chromosome_table(100_000, 77, (3, 3))
         t0 = time.perf_counter()
         o = O.detect(small, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
