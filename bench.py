@@ -448,8 +448,121 @@ def run_dmr(args, local):
     eng.close()
 
 
+# ------------------------------------------------------------------------------------------------
+# auxiliary line: ONE genome sharded over the ranks, longest chromosome first (north star, point 3)
+# ------------------------------------------------------------------------------------------------
+def run_strong(args, rank, world, local):
+    """Strong scaling of configs[1]: the 24 chromosomes of one genome are assigned to the ranks longest-first
+    (methylasso_b200.shard.lpt_assign), every rank runs its shard resident (detect, segments, call table, PMD fusion)
+    with no data-path collective, and the per-shard segment and PMD tables are all-gathered over NCCL at the end
+    (shard.all_gather_tables) - inside the timed region.  Rank 0 checks the gathered tables against its own
+    single-GPU run of the whole genome (bit-equal: a job gives the same bits wherever it is placed)."""
+    import torch
+    import torch.distributed as dist
+    from methylasso_b200 import api, shard
+    from methylasso_b200._native import MlParams
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng = api.Engine(local)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+    tables, ptr, cols = make_workload(args.cpgs, seed_offset=0)          # the SAME genome on every rank
+    sizes = np.diff(ptr)
+    rank_of = shard.lpt_assign([shard.job_cost(n) for n in sizes], world)
+    mine = shard.my_jobs(rank_of, rank)
+    mptr = np.zeros(len(mine) + 1, np.int64)
+    mptr[1:] = np.cumsum(sizes[mine])
+    mcols = {k: np.ascontiguousarray(np.concatenate([cols[k][ptr[j]:ptr[j + 1]] for j in mine])) for k in cols}
+    batch = eng.upload(mptr, mcols)
+    job_ids = np.asarray(mine, np.int32)
+
+    t_parts = [0.0, 0.0]           # host wall of the shard's own work / of the exchange, accumulated over the timed steps
+
+    def step():
+        t0 = time.perf_counter()
+        res = eng.detect(batch, params)
+        seg = res.segments(TOL)
+        pmd = res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
+        res.free()
+        for t in (seg, pmd):
+            t["job"] = job_ids[t["job"]]                                  # shard-local job index -> chromosome
+        t1 = time.perf_counter()
+        # the exchange: every rank ends up with every shard's tables in its HBM; rank 0 also copies them to its host
+        gs = shard.all_gather_packed(seg, dist, device=f"cuda:{local}") if world > 1 else None
+        gp = shard.all_gather_packed(pmd, dist, device=f"cuda:{local}") if world > 1 else None
+        if world > 1 and rank == 0:
+            gs = ([p.cpu() for p in gs[0]],) + gs[1:]
+            gp = ([p.cpu() for p in gp[0]],) + gp[1:]
+        t_parts[0] += t1 - t0
+        t_parts[1] += time.perf_counter() - t1
+        return seg, pmd, gs, gp
+
+    def tables_of(seg, pmd, gs, gp):      # untimed: the gathered matrices as tables in chromosome order
+        if world > 1:
+            seg, pmd = shard.unpack_gathered(*gs), shard.unpack_gathered(*gp)
+        return shard.reorder_by_job(seg), shard.reorder_by_job(pmd)
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    t_parts[0] = t_parts[1] = 0.0
+    eng.set("pool_headroom_percent", 25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    wall = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        out = step()
+        wall.append(round((time.perf_counter() - t0) * 1e3, 2))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        seg, pmd = tables_of(*out)
+        same = None
+        if world > 1:                      # the whole genome on this GPU alone must give the same tables
+            full = eng.upload(ptr, cols)
+            res = eng.detect(full, params)
+            s1, p1 = res.segments(TOL), res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
+            res.free()
+            full.free()
+            same = all(np.array_equal(seg[k], s1[k], equal_nan=True) for k in s1) and \
+                all(np.array_equal(pmd[k], p1[k], equal_nan=True) for k in p1)
+        U = int(sum(np.unique(t["pos"]).size for t in tables))
+        line = {"metric": "CpGs/sec through IRLS+weighted 1D FLSA, ONE genome sharded over the ranks (aux)",
+                "value": U / (float(ms.item()) * 1e-3), "unit": "CpG/s", "n_gpus": world, "steps": args.steps,
+                "ms_per_step": float(ms.item()), "scaling": "strong", "host_wall_ms_each_step_rank0": wall,
+                "jobs_per_rank": np.bincount(rank_of, minlength=world).tolist(),
+                "rows_per_rank": np.bincount(rank_of, weights=sizes, minlength=world).astype(np.int64).tolist(),
+                "segments": int(seg["start"].size), "pmd_segments": int(pmd["start"].size),
+                "gathered_tables_equal_single_gpu": same,
+                "rank0_ms_per_step_shard_work": t_parts[0] * 1e3 / args.steps,
+                "rank0_ms_per_step_exchange_and_merge": t_parts[1] * 1e3 / args.steps,
+                "timed": "detect + segments + call table + PMD fusion of the rank's chromosomes, fetch of its segment and "
+                         "PMD tables, NCCL all-gather of both (one packed matrix per table: every rank holds all shards "
+                         "in HBM afterwards), copy of the gathered matrices to rank 0's host; max over ranks"}
+        print(json.dumps(line), flush=True)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(json.dumps(line) + "\n")
+    batch.free()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--strong", action="store_true",
+                    help="auxiliary measurement: one genome sharded over the ranks (strong scaling) instead of the contract line")
     ap.add_argument("--dmr", action="store_true",
                     help="auxiliary measurement: configs[2] (3 vs 3 DMR calling) instead of the contract line")
     ap.add_argument("--gpus", type=int, default=1)
@@ -481,6 +594,9 @@ def main():
     if args.dmr:
         if rank == 0:
             run_dmr(args, local)
+        return
+    if args.strong:
+        run_strong(args, rank, world, local)
         return
 
     import torch

@@ -61,6 +61,45 @@ def all_gather_tables(local, dist, device=None):
     return out, lens
 
 
+def all_gather_packed(local, dist, device=None):
+    """The exchange itself, for tables whose columns are float64 or 32-bit integers: ONE payload collective per table,
+    the columns travelling as the rows of one float64 matrix (32-bit integers are exact in it).  Returns
+    (parts, lens, keys, dtypes): parts[r] is rank r's matrix as a tensor on `device` (every rank ends up with all of
+    them), lens[r] its number of rows.  unpack_gathered() turns that into the concatenated table on the host."""
+    import torch
+    world = dist.get_world_size()
+    keys = sorted(local)
+    n = int(len(local[keys[0]])) if keys else 0
+    dev = device or "cpu"
+    dtypes = [np.asarray(local[k]).dtype for k in keys]
+    for k, dt in zip(keys, dtypes):
+        if not (dt == np.float64 or (np.issubdtype(dt, np.integer) and dt.itemsize <= 4)):
+            raise TypeError(f"column {k}: {dt} does not travel exactly in a float64 matrix")
+    lens = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(lens, torch.tensor([n], dtype=torch.int64, device=dev))
+    lens = [int(x.item()) for x in lens]
+    cap = max(lens + [1])
+    mat = np.zeros((len(keys), cap), np.float64)
+    for i, k in enumerate(keys):
+        mat[i, :n] = local[k]
+    buf = torch.from_numpy(mat).to(dev)
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return parts, lens, keys, dtypes
+
+
+def unpack_gathered(parts, lens, keys, dtypes):
+    host = [p.cpu().numpy() if hasattr(p, "cpu") else np.asarray(p) for p in parts]
+    return {k: np.concatenate([h[i, :m] for h, m in zip(host, lens)]).astype(dt)
+            for i, (k, dt) in enumerate(zip(keys, dtypes))}
+
+
+def all_gather_tables_packed(local, dist, device=None):
+    """all_gather_packed + unpack_gathered: same result as all_gather_tables with one collective per table."""
+    parts, lens, keys, dtypes = all_gather_packed(local, dist, device)
+    return unpack_gathered(parts, lens, keys, dtypes), lens
+
+
 def reorder_by_job(table, job_key="job"):
     """Stable sort of a gathered table by global job index (chromosome order of the input)."""
     order = np.argsort(table[job_key], kind="stable")

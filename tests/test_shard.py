@@ -46,6 +46,9 @@ def _worker(rank, world, port, q):
     local = {k: (np.concatenate(v) if v else np.empty(0, np.float64 if k == "beta" else np.int32))
              for k, v in segs.items()}
     gathered, lens = shard.all_gather_tables(local, dist)
+    packed, lens2 = shard.all_gather_tables_packed(local, dist)      # one collective per table: same result
+    assert lens2 == lens and all(np.array_equal(packed[k], gathered[k]) and packed[k].dtype == gathered[k].dtype
+                                 for k in gathered)
     gathered = shard.reorder_by_job(gathered)
     if rank == 0:
         q.put((gathered, lens, rank_of.tolist()))
