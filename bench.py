@@ -322,7 +322,7 @@ def run_dmr(args, local):
     def step():
         res = eng.detect(batch, params)
         res.fast_diff_combine()
-        t = res.call_differences(batch, 2, 0.1, 0.1, TOL, MAX_DISTANCE)
+        t = res.call_differences(batch, 2, 0.1, 0.1, TOL, MAX_DISTANCE, reuse_pinned=True)
         fdr = eng.p_adjust_fdr(t["pval"])
         return res, t, fdr
 
@@ -376,7 +376,7 @@ def run_dmr(args, local):
                 bt = eng_g.upload(gptr, pin_in)
             rr = eng_g.detect(bt, params)
             rr.fast_diff_combine()
-            tt = rr.call_differences(bt, 2, 0.1, 0.1, TOL, MAX_DISTANCE)
+            tt = rr.call_differences(bt, 2, 0.1, 0.1, TOL, MAX_DISTANCE, reuse_pinned=True)   # engine-owned buffers
             rr.free()
             bt.free()
             return tt

@@ -117,6 +117,12 @@ ML_API int ml_engine_profile_get(ml_engine *eng, int i, char *name, int name_cap
 ML_API int ml_engine_profile_work(ml_engine *eng, int i, double *bytes);
 ML_API int ml_engine_profile_reset(ml_engine *eng);
 
+/* Page-locked host memory for large outputs that a caller fills again and again: a download into pageable memory goes
+ * through the driver's bounce buffers at a fraction of the PCIe rate.  Allocate ONCE and reuse - page-locking costs
+ * milliseconds per 100 MB and ml_host_free synchronises the device.  Plain memory for the caller. */
+ML_API int ml_host_alloc(uint64_t bytes, void **out);
+ML_API void ml_host_free(void *p);
+
 /* ---- weighted_1d_flsa  (src/weighted_1d_flsa.cpp:7-21; Rcpp module line
  *      src/MethyLasso_cpp.cpp:28) --------------------------------------------------------------
  * beta = soft_threshold(clamp(FLSA(y, wt, lambda2), +-35), lambda1).  Host buffers. */

@@ -43,6 +43,33 @@ def _f64(a):
     return np.ascontiguousarray(np.asarray(a), dtype=np.float64)
 
 
+class _Pinned:
+    """Owner of one page-locked allocation; numpy arrays made from it keep it alive through their `base`."""
+
+    def __init__(self, lib, nbytes):
+        self.lib, self.ptr = lib, C.c_void_p()
+        rc = lib.ml_host_alloc(int(max(nbytes, 1)), C.byref(self.ptr))
+        if rc:
+            raise MethyLassoError(rc, lib.ml_last_error().decode())
+        self.nbytes = int(max(nbytes, 1))
+        self.__array_interface__ = {"data": (self.ptr.value, False), "shape": (self.nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.lib.ml_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(n, dtype, lib=None):
+    """numpy array of n elements in page-locked host memory (downloads into it run at the PCIe rate)."""
+    lib = lib or _native.load()
+    dt = np.dtype(dtype)
+    own = _Pinned(lib, int(n) * dt.itemsize)
+    return np.asarray(own)[:int(n) * dt.itemsize].view(dt)
+
+
 class Engine:
     """One GPU, one stream.  Creating it without a CUDA device raises (no CPU path)."""
 
@@ -54,8 +81,21 @@ class Engine:
             raise MethyLassoError(rc, self.lib.ml_last_error().decode())
         self.h = h
 
+    def pinned_buffer(self, name, n, dtype):
+        """View of n elements of an engine-owned page-locked buffer called `name` (allocated on first use, grown
+        by half when too small, released with the engine).  A later request for the same name reuses the memory."""
+        dt = np.dtype(dtype)
+        cache = self.__dict__.setdefault("_pinned", {})
+        cur = cache.get(name)
+        need = int(n) * dt.itemsize
+        if cur is None or cur.nbytes < need:
+            cur = np.asarray(_Pinned(self.lib, need + need // 2))
+            cache[name] = cur
+        return cur[:need].view(dt)
+
     def close(self):
         if getattr(self, "h", None):
+            self.__dict__.pop("_pinned", None)
             self.lib.ml_engine_destroy(self.h)
             self.h = None
 
@@ -356,7 +396,7 @@ class Result:
                     ("coverage_score", np.float64))
 
     def call_differences(self, batch, ref_condition, min_diff=0.1, min_delta_diff=0.1, tol_val=0.01,
-                         max_distance=500.0, fetch=True):
+                         max_distance=500.0, fetch=True, reuse_pinned=False):
         """R/call.R:254-333 (call_differences_singlechr) for every job of a difference_detection_fast result
         (fast_diff_combine applied); `batch` is the resident input the result was computed from."""
         n = C.c_int64(0)
@@ -365,7 +405,12 @@ class Result:
         self.eng._check(self.eng.lib.ml_result_call_differences(*args, C.byref(n), *([None] * 20)))
         if not fetch:
             return n.value
-        out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.DIFF_COLUMNS}
+        if reuse_pinned:
+            # engine-owned page-locked buffers, grown as needed and REUSED by the next call with reuse_pinned=True
+            # (page-locking costs far more than it saves when done per call): the returned arrays are views of them
+            out = {k: self.eng.pinned_buffer("diff_" + k, max(n.value, 1), dt) for k, dt in self.DIFF_COLUMNS}
+        else:
+            out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.DIFF_COLUMNS}
         self.eng._check(self.eng.lib.ml_result_call_differences(*args, C.byref(n), *[_p(out[k]) for k, _ in self.DIFF_COLUMNS]))
         return {k: v[:n.value] for k, v in out.items()}
 

@@ -918,4 +918,16 @@ int ml_debug_divide(ml_engine* eng, int64_t n, const double* num, const double* 
   ML_CATCH
 }
 
+int ml_host_alloc(uint64_t bytes, void** out) {
+  if (!out) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaHostAlloc(out, bytes ? (size_t)bytes : 1, cudaHostAllocPortable));
+  return ML_OK;
+  ML_CATCH
+}
+void ml_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 }  // extern "C"
