@@ -786,7 +786,8 @@ def main():
             n_g = int(gptr[-1])
             ep_g = int(sum(sizes[j][1] * sizes[j][2] for j in jobs))
             outb = dict(mu=torch.empty(n_g, dtype=torch.float64).pin_memory().numpy(),
-                        off=np.empty(3 * len(jobs)),
+                        off=torch.empty(3 * len(jobs), dtype=torch.float64).pin_memory().numpy(),   # pageable would make the
+                        # asynchronous copy call block until the detect kernels are done
                         est_id=torch.empty(ep_g, dtype=torch.int32).pin_memory().numpy(),
                         **{k: torch.empty(ep_g, dtype=torch.float64).pin_memory().numpy()
                            for k in ("start", "beta", "betahat", "pseudoweight")})
@@ -810,8 +811,8 @@ def main():
             rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
             ts.append(time.perf_counter())
             eng_g.synchronize()
-            seg = rr.segments(TOL)
-            call = rr.call_table(TOL, MAX_DISTANCE)
+            seg = rr.segments(TOL, reuse_pinned=True)               # the engine's own page-locked buffers
+            call = rr.call_table(TOL, MAX_DISTANCE, reuse_pinned=True)
             pmd = rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
             pmd["call_table"] = call
             rr.free()

@@ -335,16 +335,19 @@ class Result:
     def fast_diff_combine(self):
         self.eng._check(self.eng.lib.ml_result_fast_diff_combine(self.eng.h, self.h))
 
-    def segments(self, tol_val=0.01):
-        """segment_methylation_helper on the resident estimates of every valid job."""
+    def segments(self, tol_val=0.01, reuse_pinned=False):
+        """segment_methylation_helper on the resident estimates of every valid job.  reuse_pinned=True downloads
+        into engine-owned page-locked buffers and returns views of them (valid until the next such call)."""
         ns = C.c_int64(0)
         self.eng._check(self.eng.lib.ml_result_segments(self.eng.h, self.h, float(tol_val), C.byref(ns),
                                                         *([None] * 9)))
         out = _seg_buffers(max(ns.value, 1), with_job=True)
+        if reuse_pinned:
+            out = {k: self.eng.pinned_buffer("seg_" + k, v.size, v.dtype) for k, v in out.items()}
         self.eng._check(self.eng.lib.ml_result_segments(
             self.eng.h, self.h, float(tol_val), C.byref(ns), _p(out["job"]),
             *[_p(out[k]) for k in _SEG_COLS]))
-        return {k: v[:ns.value].copy() for k, v in out.items()}
+        return {k: (v[:ns.value] if reuse_pinned else v[:ns.value].copy()) for k, v in out.items()}
 
 
     def segments_count(self, tol_val=0.01) -> int:
@@ -414,17 +417,20 @@ class Result:
         self.eng._check(self.eng.lib.ml_result_call_differences(*args, C.byref(n), *[_p(out[k]) for k, _ in self.DIFF_COLUMNS]))
         return {k: v[:n.value] for k, v in out.items()}
 
-    def call_table(self, tol_val=0.01, max_distance=500.0, fetch=True):
+    def call_table(self, tol_val=0.01, max_distance=500.0, fetch=True, reuse_pinned=False):
         """R/call.R:43-68 on the resident result (see ml_result_call_table): one row per gap-split segment."""
         n = C.c_int64(0)
         self.eng._check(self.eng.lib.ml_result_call_table(self.eng.h, self.h, float(tol_val), float(max_distance),
                                                           C.byref(n), *([None] * 11)))
         if not fetch:
             return n.value
-        out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.CALL_COLUMNS}
+        if reuse_pinned:
+            out = {k: self.eng.pinned_buffer("call_" + k, max(n.value, 1), dt) for k, dt in self.CALL_COLUMNS}
+        else:
+            out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.CALL_COLUMNS}
         self.eng._check(self.eng.lib.ml_result_call_table(self.eng.h, self.h, float(tol_val), float(max_distance),
                                                           C.byref(n), *[_p(out[k]) for k, _ in self.CALL_COLUMNS]))
-        return {k: v[:n.value].copy() for k, v in out.items()}
+        return {k: (v[:n.value] if reuse_pinned else v[:n.value].copy()) for k, v in out.items()}
 
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
