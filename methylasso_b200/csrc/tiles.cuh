@@ -9,7 +9,10 @@
 #include <algorithm>
 #include <vector>
 
+#include "hd.h"
+#ifdef __CUDACC__
 #include "common.h"
+#endif
 
 namespace ml {
 
@@ -27,22 +30,47 @@ inline int32_t span_tiles(int64_t n, int32_t tile, bool at_least_one = false) {
   return (int32_t)std::max<int64_t>(t, at_least_one ? 1 : 0);
 }
 
+// tile t of the table: which span it belongs to (spans sorted by t0, every span owning at least one tile), its index
+// inside the span, its first item relative to the span and its item count.  Shared with the CPU emulation
+// (tests/emu/emu_tiles.cpp checks it against the host loops it replaced).
+ML_HD void tile_of_table(const TileSpan* spans, int n_spans, int t, int& span, int& i, int64_t& off, int32_t& cnt) {
+  int lo = 0, hi = n_spans - 1;              // last span with t0 <= t
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (spans[mid].t0 <= t) lo = mid; else hi = mid - 1;
+  }
+  const TileSpan& s = spans[lo];
+  span = lo;
+  i = t - s.t0;
+  off = (int64_t)i * s.tile;
+  const int64_t left = s.n - off;
+  cnt = (int32_t)(left < 0 ? 0 : (left < s.tile ? left : s.tile));
+}
+
+#ifdef __CUDACC__
 template <class Out, class Make>
 __global__ void __launch_bounds__(256)
 k_fill_tiles(const TileSpan* __restrict__ spans, int n_spans, int n_tiles, Out* __restrict__ out, Make make) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tiles) return;
-  int lo = 0, hi = n_spans - 1;              // last span with t0 <= t (spans without tiles share a t0: take the last)
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (spans[mid].t0 <= t) lo = mid; else hi = mid - 1;
+  int span, i;
+  int64_t off;
+  int32_t cnt;
+  tile_of_table(spans, n_spans, t, span, i, off, cnt);
+  out[t] = make(spans[span], i, off, cnt);
+}
+
+// first tile of every span (written into the spans) and the spans that own tiles, in order; returns the tile count
+inline int32_t place_spans(std::vector<TileSpan>& spans, const std::vector<int32_t>& ntiles, std::vector<TileSpan>& live) {
+  int32_t total = 0;
+  live.clear();
+  live.reserve(spans.size());
+  for (size_t i = 0; i < spans.size(); ++i) {
+    spans[i].t0 = total;
+    if (ntiles[i] > 0) live.push_back(spans[i]);     // spans without tiles are left out: their t0 would be ambiguous
+    total += ntiles[i];
   }
-  const TileSpan s = spans[lo];
-  const int i = t - s.t0;
-  const int64_t off = (int64_t)i * s.tile;
-  const int64_t left = s.n - off;
-  const int32_t cnt = (int32_t)(left < 0 ? 0 : (left < s.tile ? left : s.tile));
-  out[t] = make(s, i, off, cnt);
+  return total;
 }
 
 // expand `spans` (t0 filled in here) into `out`; returns the number of tiles
@@ -50,14 +78,8 @@ template <class Out, class Make>
 int fill_tiles(Engine& eng, std::vector<TileSpan>& spans, const std::vector<int32_t>& ntiles, DevBuf<Out>& out, Make make,
                const char* name) {
   cudaStream_t st = eng.stream;
-  int32_t total = 0;
-  std::vector<TileSpan> live;                // spans without tiles are left out (their t0 would be ambiguous)
-  live.reserve(spans.size());
-  for (size_t i = 0; i < spans.size(); ++i) {
-    spans[i].t0 = total;
-    if (ntiles[i] > 0) live.push_back(spans[i]);
-    total += ntiles[i];
-  }
+  std::vector<TileSpan> live;
+  const int32_t total = place_spans(spans, ntiles, live);
   out.alloc(st, (size_t)std::max(1, total));
   if (total == 0) return 0;
   DevBuf<TileSpan> d_spans(st, live.size());
@@ -65,5 +87,6 @@ int fill_tiles(Engine& eng, std::vector<TileSpan>& spans, const std::vector<int3
   ML_LAUNCH(eng, name, k_fill_tiles<Out, Make><<<cdiv(total, 256), 256, 0, st>>>(d_spans.p, (int)live.size(), total, out.p, make));
   return total;
 }
+#endif  // __CUDACC__
 
 }  // namespace ml

@@ -170,3 +170,27 @@ def test_x87_mean_matches_host_long_double():
         assert L.emu_x87_compare(m, n, x.ctypes.data, C.byref(first)) == 0, (n, x[first.value])
         x = np.ascontiguousarray(rng.random((m, n)) * rng.choice([1e-3, 1.0, 1e3], (m, 1)))
         assert L.emu_x87_compare(m, n, x.ctypes.data, C.byref(first)) == 0, (n, x[first.value])
+
+
+def test_device_tile_tables_match_host_loops():
+    """methylasso_b200/csrc/tiles.cuh: the span -> tile arithmetic of k_fill_tiles against the host loops it replaced."""
+    src = os.path.join(HERE, "emu", "emu_tiles.cpp")
+    lib = os.path.join(HERE, "emu", "libemu_tiles.so")
+    deps = [src] + [os.path.join(HERE, "..", "methylasso_b200", "csrc", f) for f in ("tiles.cuh", "hd.h")]
+    if not os.path.exists(lib) or os.path.getmtime(lib) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", lib, src])
+    L = C.CDLL(lib)
+    L.emu_tiles_check.restype = C.c_longlong
+    L.emu_tiles_check.argtypes = [C.c_int, C.c_void_p]
+    rng = np.random.default_rng(5)
+    cases = [np.array([[0, 0, 256, 0]]), np.array([[1, 0, 448, 1]]),                        # nothing / one empty chunk
+             np.array([[1, 7, 2**31 - 1, 1]]),                                           # sequential mode: one chunk
+             np.array([[5, 1024, 1024, 0], [0, 0, 1024, 0], [9, 1025, 1024, 0]])]         # exact fit, empty, one over
+    for _ in range(200):
+        k = int(rng.integers(1, 40))
+        d = np.stack([rng.integers(0, 10**9, k), rng.choice([0, 1, 2, 255, 256, 257, 5000, 123457], k),
+                      rng.choice([1, 64, 256, 448, 1024, 2048], k), rng.integers(0, 2, k)], axis=1)
+        cases.append(d)
+    for d in cases:
+        d = np.ascontiguousarray(d, np.int64)
+        assert L.emu_tiles_check(d.shape[0], d.ctypes.data) == 0, d.tolist()
