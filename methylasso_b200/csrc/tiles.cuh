@@ -60,6 +60,8 @@ k_fill_tiles(const TileSpan* __restrict__ spans, int n_spans, int n_tiles, Out* 
   out[t] = make(spans[span], i, off, cnt);
 }
 
+#endif  // __CUDACC__
+
 // first tile of every span (written into the spans) and the spans that own tiles, in order; returns the tile count
 inline int32_t place_spans(std::vector<TileSpan>& spans, const std::vector<int32_t>& ntiles, std::vector<TileSpan>& live) {
   int32_t total = 0;
@@ -73,6 +75,7 @@ inline int32_t place_spans(std::vector<TileSpan>& spans, const std::vector<int32
   return total;
 }
 
+#ifdef __CUDACC__
 // expand `spans` (t0 filled in here) into `out`; returns the number of tiles
 template <class Out, class Make>
 int fill_tiles(Engine& eng, std::vector<TileSpan>& spans, const std::vector<int32_t>& ntiles, DevBuf<Out>& out, Make make,
