@@ -578,6 +578,9 @@ def main():
                     help="> 1: also time the resident step with the chromosomes spread over this many engines")
     ap.add_argument("--e2e-edge", type=float, default=0.0,
                     help="share of the rows given to the first and to the last group of the e2e pipeline (0 = balanced)")
+    ap.add_argument("--e2e-no-mu", action="store_true",
+                    help="auxiliary: the e2e step does not download mu (the reference returns it, but neither MethyLasso.R "
+                         "nor R/call.R ever reads ret$mu); 39 %% fewer bytes come back")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
@@ -804,7 +807,8 @@ def main():
             bt.free()
             ts.append(time.perf_counter())
             # D2H of mu / estimates is enqueued on the copy stream and overlaps the segmentation kernels
-            rr.copy_all_async(o["mu"], o["off"], o["est_id"], o["start"], o["beta"], o["betahat"], o["pseudoweight"])
+            rr.copy_all_async(None if args.e2e_no_mu else o["mu"], o["off"], o["est_id"], o["start"], o["beta"],
+                              o["betahat"], o["pseudoweight"])
             ts.append(time.perf_counter())
             rr.segments_count(TOL)                      # resident; the tables are fetched after the big copies
             rr.call_table(TOL, MAX_DISTANCE, fetch=False)
@@ -869,7 +873,8 @@ def main():
                         + list(pm["call_table"].values()))
         e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
                "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
-               "d2h_bytes_per_step": int(8 * N + 36 * EP + seg_bytes), "engines": G,
+               "d2h_bytes_per_step": int((0 if args.e2e_no_mu else 8 * N) + 36 * EP + seg_bytes), "engines": G,
+               "mu_downloaded": not args.e2e_no_mu,
                "host_wall_ms_each_step": step_wall, "disturbed_attempts": e2e_disturbed, "clocks": e2e_sampler.stop(),
                "timeline_ms_last_step": timeline_timed,  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
                "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "

@@ -34,7 +34,8 @@ void need_columns(const DataFrame& data) {   // src/signal_detection.cpp:13-15
 }
 
 // one job (job_ptr = {0, n}) or many (job_ptr given): returns the reference's List per job
-List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml_params& p, bool diff_fast) {
+List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml_params& p, bool diff_fast,
+            bool want_mu = true) {
   need_columns(data);
   IntegerVector dset = data["dataset"], cond = data["condition"], rep = data["replicate"], pos = data["pos"],
                 nmeth = data["Nmeth"], cov = data["coverage"];   // Rcpp coerces doubles to int
@@ -53,9 +54,11 @@ List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml
       out[j] = R_NilValue;
       continue;
     }
-    NumericVector mu(n), lambda2(E), offset(D), start(E * P), beta(E * P), betahat(E * P), pw(E * P);
+    // mu is 8 bytes per data row, 39 % of everything that comes back for a genome, and neither MethyLasso.R nor R/call.R
+    // ever reads ret$mu (R/genome_wide.R:9 only concatenates it): want_mu = FALSE leaves it on the device
+    NumericVector mu(want_mu ? n : 0), lambda2(E), offset(D), start(E * P), beta(E * P), betahat(E * P), pw(E * P);
     IntegerVector id(E * P);
-    check(ml_result_copy_job(engine(), res, j, mu.begin(), lambda2.begin(), offset.begin(), id.begin(),
+    check(ml_result_copy_job(engine(), res, j, want_mu ? mu.begin() : nullptr, lambda2.begin(), offset.begin(), id.begin(),
                              start.begin(), beta.begin(), betahat.begin(), pw.begin()));
     int32_t conv; double hyper;
     ml_result_job_info(res, j, &conv, nullptr, nullptr, nullptr, &hyper, nullptr);
@@ -141,9 +144,9 @@ NumericVector weighted_1d_flsa(const NumericVector& y, const NumericVector& wt, 
 // (data sorted by chr, dataset, pos).  Returns a list with one element per chromosome (NULL for a
 // chromosome that failed, mirroring foreach's .errorhandling = "remove").
 List signal_detection_fast_batch(const DataFrame& data, const NumericVector& job_ptr, double lambda2,
-                                 double tol_val, unsigned max_iter, bool difference) {
+                                 double tol_val, unsigned max_iter, bool difference, bool want_mu) {
   std::vector<int64_t> ptr(job_ptr.begin(), job_ptr.end());
-  return detect(data, ptr, fast_params(lambda2, tol_val, max_iter), difference);
+  return detect(data, ptr, fast_params(lambda2, tol_val, max_iter), difference, want_mu);
 }
 
 // NEW: the DMR caller of R/call.R:254-365 in one native call: difference_detection_fast of every chromosome, the
