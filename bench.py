@@ -894,11 +894,12 @@ def main():
     kb = kernel_bytes(N, EP, D, words)
     # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
     # capture of this same command (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
-    traffic = {}
+    traffic, ncu_detail = {}, {}
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch", {})
+            tj = json.load(f)
+        traffic, ncu_detail = tj.get("dram_bytes_per_launch", {}), tj.get("detail", {})
     table = []
     for name, (tot_ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per = tot_ms / max(1, n)
@@ -915,6 +916,14 @@ def main():
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": top["frac_of_hbm"], "traffic": top["ncu_dram_bytes_per_launch"], "peak_source": pk_kind,
                     "alg_bytes_per_launch": top["alg_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
+                    # what bounds a latency-bound kernel: DP steps per second from this run, issue
+                    # and occupancy figures from the committed ncu capture
+                    "latency_bound": ({"dp_steps_per_s": (top["alg_bytes_per_launch"] / (16.0 if top["kernel"] == "flsa_warm_kernel" else 32.0))
+                                                         / (top["avg_launch_ms"] * 1e-3),
+                                       "ncu_issue_active_pct": ncu_detail.get(top["kernel"], {}).get("mean_issue_active_pct"),
+                                       "ncu_warps_active_pct": ncu_detail.get(top["kernel"], {}).get("mean_warps_active_pct"),
+                                       "ncu_fp64_pipe_pct": ncu_detail.get(top["kernel"], {}).get("mean_fp64_pipe_pct")}
+                                      if top["kernel"].startswith("flsa_") and top["alg_bytes_per_launch"] else None),
                     "note": "FLSA chunk kernels run a dependent fp64 compare/add/divide chain per element (latency-bound, "
                             "not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped kernels "
                             "of the step are listed in `kernels` with their own fractions"}

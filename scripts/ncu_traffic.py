@@ -58,7 +58,7 @@ def main(src, dst):
         acc[k]["ms"].append(scaled(r, "gpu__time_duration.sum"))
         for key, short in (("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
                            ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64_pipe_pct"),
-                           ("smsp__issue_active.avg.pct", "issue_active_pct"),
+                           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_active_pct"),
                            ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_throughput_pct"),
                            ("launch__registers_per_thread", "registers")):
             if key in col:
