@@ -294,6 +294,24 @@ ML_API int ml_result_call_differences(ml_engine *eng, const ml_batch *b, ml_resu
                                       int32_t *num_cpgs_ref, double *pseudoweight, double *diff, double *cohen_d,
                                       double *pval, double *coverage_score);
 
+/* ---- LMR / UMR annotation (R/call.R:75-91, inside segment_methylation_singlechr) ------------------------------------
+ * On the resident call table of ml_result_call_table(tol_val, max_distance), one entry per call-table row, in its
+ * order: is.admissible (:77), is.V among the admissible segments of a condition (:78), is.flank (:79), flank.dist,
+ * flank.beta and is.sep among the V-shaped and flanking segments (:80-82), and the category after :83-86.  Logical
+ * columns are three-valued as in R: 1 TRUE, 0 FALSE, -1 NA; numeric NA is NaN; category 0 = NA, 1 = "LMR", 2 = "UMR".
+ * shift() in those statements walks the rows the statement selects (of one condition of one chromosome; of one
+ * chromosome for :79), as data.table evaluates them.  The later steps of the function (valleys :97-131, PMD calls
+ * :133-221) still run in R on this table.  params == NULL: the reference's defaults.  Any output may be NULL. */
+typedef struct {
+  double min_width, max_distance, flank_width, flank_dist_max, lmr_max_beta, flank_beta_min, umr_max_beta,
+      umr_std_threshold, umr_large_width, umr_large_density;    /* 30, 500, 300, 5000, 0.5, 0.5, 0.1, 0.1, 500, 0.03 */
+  int32_t min_num_cpgs, flank_num_cpgs;                         /* 4, 10 */
+} ml_lmr_params;
+ML_API int ml_result_call_lmr_umr(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                  const ml_lmr_params *params, int64_t *n_rows, int8_t *is_admissible, int8_t *is_v,
+                                  int8_t *is_flank, double *flank_dist, double *flank_beta, int8_t *is_sep,
+                                  int8_t *category);
+
 #ifdef __cplusplus
 }
 #endif

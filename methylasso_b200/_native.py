@@ -22,6 +22,20 @@ class MlParams(C.Structure):
                 ("model", C.c_int32), ("optimize_lambda2", C.c_int32), ("optimize_hyper", C.c_int32)]
 
 
+class MlLmrParams(C.Structure):
+    """ml_lmr_params (include/methylasso_b200.h): thresholds of R/call.R:75-91 with the reference's defaults."""
+    _fields_ = [(k, C.c_double) for k in ("min_width", "max_distance", "flank_width", "flank_dist_max", "lmr_max_beta",
+                                          "flank_beta_min", "umr_max_beta", "umr_std_threshold", "umr_large_width",
+                                          "umr_large_density")] + [("min_num_cpgs", C.c_int32), ("flank_num_cpgs", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(min_width=30.0, max_distance=500.0, flank_width=300.0, flank_dist_max=5000.0, lmr_max_beta=0.5,
+                 flank_beta_min=0.5, umr_max_beta=0.1, umr_std_threshold=0.1, umr_large_width=500.0,
+                 umr_large_density=0.03, min_num_cpgs=4, flank_num_cpgs=10)
+        d.update(kw)
+        super().__init__(**d)
+
+
 # every symbol the header declares, with (restype, argtypes)
 _P = C.c_void_p
 _I64P = C.POINTER(C.c_int64)
@@ -72,6 +86,7 @@ SIGNATURES = {
     "ml_wilcoxon_groups": (C.c_int, [_P, C.c_int64] + [_P] * 6),
     "ml_p_adjust_fdr": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ml_result_call_differences": (C.c_int, [_P, _P, _P, C.c_int] + [C.c_double] * 4 + [_I64P] + [_P] * 20),
+    "ml_result_call_lmr_umr": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), _I64P] + [_P] * 7),
     "ml_segment_call_table": (C.c_int, [_P, C.c_int64] + [_P] * 4 + [C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 10),
 }
 

@@ -432,6 +432,21 @@ class Result:
                                                           C.byref(n), *[_p(out[k]) for k, _ in self.CALL_COLUMNS]))
         return {k: (v[:n.value] if reuse_pinned else v[:n.value].copy()) for k, v in out.items()}
 
+    def call_lmr_umr(self, tol_val=0.01, max_distance=500.0, **thresholds):
+        """R/call.R:75-91 on the resident call table: is_admissible, is_V, is_flank, is_sep (1 TRUE, 0 FALSE, -1 NA),
+        flank_dist, flank_beta (NaN = NA) and category (0 NA, 1 LMR, 2 UMR), one entry per row of call_table()."""
+        from ._native import MlLmrParams
+        p = MlLmrParams(max_distance=float(max_distance), **thresholds)
+        n = self.call_table(tol_val, max_distance, fetch=False)
+        i8 = lambda: np.empty(max(n, 1), np.int8)
+        out = dict(is_admissible=i8(), is_V=i8(), is_flank=i8(), flank_dist=np.empty(max(n, 1)),
+                   flank_beta=np.empty(max(n, 1)), is_sep=i8(), category=i8())
+        nn = C.c_int64(0)
+        self.eng._check(self.eng.lib.ml_result_call_lmr_umr(
+            self.eng.h, self.h, float(tol_val), float(max_distance), C.byref(p), C.byref(nn),
+            *[_p(out[k]) for k in ("is_admissible", "is_V", "is_flank", "flank_dist", "flank_beta", "is_sep", "category")]))
+        return {k: v[:nn.value] for k, v in out.items()}
+
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
         ns = C.c_int64(0)

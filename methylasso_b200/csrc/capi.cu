@@ -930,4 +930,36 @@ void ml_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
+static_assert(sizeof(ml_lmr_params) == sizeof(LmrParams), "ml_lmr_params / LmrParams layout mismatch");
+
+int ml_result_call_lmr_umr(ml_engine* eng, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* params,
+                           int64_t* n_rows, int8_t* is_admissible, int8_t* is_v, int8_t* is_flank, double* flank_dist,
+                           double* flank_beta, int8_t* is_sep, int8_t* category) {
+  if (!eng || !r || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  const int rc = ensure_call_table(eng, r, tol_val, max_distance);
+  if (rc) return rc;
+  LmrParams p;
+  if (params) memcpy(&p, params, sizeof p);
+  LmrUmrColumns out;
+  call_lmr_umr_device(eng->e, *r->r->call_cache, p, out);
+  *n_rows = out.n;
+  const size_t n = (size_t)out.n;
+  if (n) {
+    if (is_admissible) out.is_admissible.download(is_admissible, n);
+    if (is_v) out.is_v.download(is_v, n);
+    if (is_flank) out.is_flank.download(is_flank, n);
+    if (flank_dist) out.flank_dist.download(flank_dist, n);
+    if (flank_beta) out.flank_beta.download(flank_beta, n);
+    if (is_sep) out.is_sep.download(is_sep, n);
+    if (category) out.category.download(category, n);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
 }  // extern "C"

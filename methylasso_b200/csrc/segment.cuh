@@ -62,6 +62,22 @@ struct CallTable {
   DevBuf<double> coverage, width;
   DevBuf<int32_t> num_cpgs;
 };
+// Thresholds of the LMR / UMR annotation (arguments of segment_methylation_singlechr, R/call.R:31-35, with its defaults)
+struct LmrParams {
+  double min_width = 30, max_distance = 500, flank_width = 300, flank_dist_max = 5000, lmr_max_beta = 0.5,
+         flank_beta_min = 0.5, umr_max_beta = 0.1, umr_std_threshold = 0.1, umr_large_width = 500, umr_large_density = 0.03;
+  int32_t min_num_cpgs = 4, flank_num_cpgs = 10;
+};
+// R/call.R:75-91 on a call table: one entry per call-table row.  Logical columns: 1 TRUE, 0 FALSE, -1 NA;
+// flank_dist / flank_beta NaN = NA; category 0 NA, 1 LMR, 2 UMR.
+struct LmrUmrColumns {
+  int64_t n = 0;
+  DevBuf<int8_t> is_admissible, is_v, is_flank, is_sep, category;
+  DevBuf<double> flank_dist, flank_beta;
+  void alloc(cudaStream_t st, int64_t count);
+};
+void call_lmr_umr_device(Engine& eng, const CallTable& t, const LmrParams& p, LmrUmrColumns& out);
+
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,
                                   double max_distance, CallTable& out);
