@@ -18,6 +18,7 @@ calls = [("detect", lambda st: st.__setitem__("res", eng.detect(batch, params)))
          ("segments", lambda st: st["res"].segments_count(0.01)),
          ("call_table", lambda st: st["res"].call_table(0.01, 500.0, fetch=False)),
          ("call_pmd_segments", lambda st: st["res"].call_pmd_segments(0.01, 500.0, 1000.0, fetch=False)),
+         ("call_lmr_umr (not in the bench step)", lambda st: st["res"].call_lmr_umr(0.01, 500.0)),
          ("free", lambda st: st["res"].free())]
 
 def step(record=None, prof=False):
@@ -46,11 +47,11 @@ step(); step()
 recp = {}
 for _ in range(10):
     step(recp, prof=True)
-print(f"{'call':20s} {'host wall ms':>12s} {'(with events)':>14s} {'kernel ms':>10s} {'launches':>9s} {'gap ms':>8s}")
+print(f"{'call':38s} {'host wall ms':>12s} {'(with events)':>14s} {'kernel ms':>10s} {'launches':>9s} {'gap ms':>8s}")
 tot = [0, 0, 0]
 for name, _ in calls:
     w = np.median([x[0] for x in rec[name]]); wp = np.median([x[0] for x in recp[name]])
     k = np.median([x[1] for x in recp[name]]); n = np.median([x[2] for x in recp[name]])
-    print(f"{name:20s} {w:12.2f} {wp:14.2f} {k:10.2f} {n:9.0f} {w - k:8.2f}")
+    print(f"{name[:38]:38s} {w:12.2f} {wp:14.2f} {k:10.2f} {n:9.0f} {w - k:8.2f}")
     tot[0] += w; tot[1] += k; tot[2] += n
-print(f"{'step':20s} {tot[0]:12.2f} {'':14s} {tot[1]:10.2f} {tot[2]:9.0f} {tot[0] - tot[1]:8.2f}")
+print(f"{'step':38s} {tot[0]:12.2f} {'':14s} {tot[1]:10.2f} {tot[2]:9.0f} {tot[0] - tot[1]:8.2f}")
