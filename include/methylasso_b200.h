@@ -312,6 +312,23 @@ ML_API int ml_result_call_lmr_umr(ml_engine *eng, ml_result *r, double tol_val, 
                                   int8_t *is_flank, double *flank_dist, double *flank_beta, int8_t *is_sep,
                                   int8_t *category);
 
+/* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
+ * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =
+ * the two numeric columns the CLI selects.  sep = 0: tabs or blanks (runs of blanks count once), else the separator.
+ * The first skip_lines lines are not data (header).  Numbers are converted exactly as strtod / fread do when one
+ * correctly rounded operation suffices (<= 15 significant digits, |decimal exponent| <= 22); otherwise the line gets
+ * status 1 and the host parses that field itself - nothing is approximated.  status: 0 ok, 1 a number the host must
+ * parse, 2 malformed (missing column, not a number, position not an integer in [0, 2^31)), 3 blank line.
+ * ml_text_parse keeps the result resident; ml_text_fetch copies what is asked for (any pointer may be NULL):
+ * per data line pos, a, b, status and line_start (byte offset of the line in the text), per run of equal chromosome
+ * fields its first data line and the offset / length of the field inside that line. */
+typedef struct ml_text ml_text;
+ML_API int ml_text_parse(ml_engine *eng, const char *text, int64_t nbytes, int64_t skip_lines, int col_a, int col_b,
+                         char sep, ml_text **out, int64_t *n_lines, int64_t *n_chr_runs);
+ML_API int ml_text_fetch(ml_engine *eng, const ml_text *t, int32_t *pos, double *a, double *b, int8_t *status,
+                         int64_t *line_start, int64_t *run_first_line, int32_t *run_chr_off, int32_t *run_chr_len);
+ML_API void ml_text_free(ml_text *t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,9 @@ SIGNATURES = {
     "ml_p_adjust_fdr": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ml_result_call_differences": (C.c_int, [_P, _P, _P, C.c_int] + [C.c_double] * 4 + [_I64P] + [_P] * 20),
     "ml_result_call_lmr_umr": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), _I64P] + [_P] * 7),
+    "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
+    "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
+    "ml_text_free": (None, [_P]),
     "ml_segment_call_table": (C.c_int, [_P, C.c_int64] + [_P] * 4 + [C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 10),
 }
 

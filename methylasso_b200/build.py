@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libmethylasso_b200.so")
-SOURCES = ["flsa.cu", "detect.cu", "segment.cu", "stats.cu", "capi.cu"]
+SOURCES = ["flsa.cu", "detect.cu", "segment.cu", "stats.cu", "codec.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -11,12 +11,14 @@
 #include "detect.cuh"
 #include "segment.cuh"
 #include "stats.cuh"
+#include "codec.cuh"
 
 using namespace ml;
 
 struct ml_engine { Engine e; cudaStream_t own = nullptr; };
 struct ml_batch { std::unique_ptr<Batch> b; };
 struct ml_result { std::unique_ptr<Result> r; };
+struct ml_text { TextTable t; int device = 0; };
 
 static thread_local std::string g_err;
 
@@ -960,6 +962,86 @@ int ml_result_call_lmr_umr(ml_engine* eng, ml_result* r, double tol_val, double 
   stream_sync(eng->e.stream);
   return ML_OK;
   ML_CATCH
+}
+}  // extern "C"
+
+namespace ml {
+__global__ void k_txt_gather_runs(int64_t n_runs, const int64_t* __restrict__ run_first, const int32_t* __restrict__ chr_off,
+                                  const int32_t* __restrict__ chr_len, int32_t* __restrict__ off, int32_t* __restrict__ len) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_runs) return;
+  off[k] = chr_off[run_first[k]];
+  len[k] = chr_len[run_first[k]];
+}
+__global__ void k_txt_data_line_starts(int64_t n, int64_t skip, const int64_t* __restrict__ line_start, int64_t* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) out[r] = line_start[r + skip];
+}
+}  // namespace ml
+
+extern "C" {
+
+int ml_text_parse(ml_engine* eng, const char* text, int64_t nbytes, int64_t skip_lines, int col_a, int col_b, char sep,
+                  ml_text** out, int64_t* n_lines, int64_t* n_chr_runs) {
+  if (!eng || !out || !n_lines || (nbytes > 0 && !text) || nbytes < 0) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  auto t = std::make_unique<ml_text>();
+  t->device = eng->e.device;
+  text_parse(eng->e, text, nbytes, skip_lines, col_a, col_b, sep, t->t);
+  *n_lines = t->t.n;
+  if (n_chr_runs) *n_chr_runs = t->t.n_runs;
+  *out = t.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_text_fetch(ml_engine* eng, const ml_text* t, int32_t* pos, double* a, double* b, int8_t* status, int64_t* line_start,
+                  int64_t* run_first_line, int32_t* run_chr_off, int32_t* run_chr_len) {
+  if (!eng || !t) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  const TextTable& T = t->t;
+  cudaStream_t st = eng->e.stream;
+  const size_t n = (size_t)T.n, nr = (size_t)T.n_runs;
+  if (n) {
+    if (pos) T.pos.download(pos, n);
+    if (a) T.a.download(a, n);
+    if (b) T.b.download(b, n);
+    if (status) T.status.download(status, n);
+    DevBuf<int64_t> ls;
+    if (line_start) {
+      ls.alloc(st, n);
+      k_txt_data_line_starts<<<cdiv((long long)n, 256), 256, 0, st>>>((int64_t)n, T.skip, T.line_start.p, ls.p);
+      ML_CHECK_LAUNCH();
+      ls.download(line_start, n);
+    }
+    DevBuf<int32_t> ro, rl;
+    if (nr) {
+      if (run_first_line) T.run_first.download(run_first_line, nr);
+      if (run_chr_off || run_chr_len) {
+        ro.alloc(st, nr); rl.alloc(st, nr);
+        k_txt_gather_runs<<<cdiv((long long)nr, 256), 256, 0, st>>>((int64_t)nr, T.run_first.p, T.chr_off.p, T.chr_len.p, ro.p, rl.p);
+        ML_CHECK_LAUNCH();
+        if (run_chr_off) ro.download(run_chr_off, nr);
+        if (run_chr_len) rl.download(run_chr_len, nr);
+      }
+    }
+    stream_sync(st);
+  }
+  return ML_OK;
+  ML_CATCH
+}
+
+void ml_text_free(ml_text* t) {
+  if (!t) return;
+  cudaSetDevice(t->device);
+  delete t;
 }
 
 }  // extern "C"
