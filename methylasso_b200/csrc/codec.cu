@@ -3,6 +3,9 @@
 // tile, scan, scatter), parse the four selected fields of every line (codec_core.cuh: exact decimal -> double or a
 // flag for the host, never an approximation) and mark where the chromosome field changes, so that the host only has
 // to look at one name per run.  HBM-bound byte work: the text is read three times, ~40 bytes per line are written.
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+
 #include <algorithm>
 #include <vector>
 
@@ -133,13 +136,6 @@ k_txt_chr_heads(const char* __restrict__ text, const int64_t* __restrict__ line_
   flag[r] = head ? 1 : 0;
 }
 
-// compaction of the head flags: run_first[k] = line of the k-th head (flags scanned by k_txt_scan_tiles)
-__global__ void k_txt_compact(const int32_t* __restrict__ flag, const int64_t* __restrict__ before, int64_t n,
-                              int64_t* __restrict__ run_first) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < n && flag[r]) run_first[before[r]] = r;
-}
-
 }  // namespace
 
 void text_parse(Engine& eng, const char* text, int64_t nbytes, int64_t skip_lines, int col_a, int col_b, char sep,
@@ -174,17 +170,21 @@ void text_parse(Engine& eng, const char* text, int64_t nbytes, int64_t skip_line
       out.text.p, nbytes, out.line_start.p, n_total, out.skip, col_a, col_b, sep, out.pos.p, out.a.p, out.b.p,
       out.status.p, out.chr_off.p, out.chr_len.p));
   DevBuf<int32_t> flag(st, c);
-  DevBuf<int64_t> before(st, c);
   ML_LAUNCH(eng, "k_txt_chr_heads", k_txt_chr_heads<<<cdiv(n, 256), 256, 0, st>>>(
       out.text.p, out.line_start.p, out.skip, n, out.chr_off.p, out.chr_len.p, flag.p));
-  ML_LAUNCH(eng, "k_txt_scan_tiles", k_txt_scan_tiles<<<1, 1024, 0, st>>>(flag.p, n, before.p, total.p));
+  // run_first = the data lines whose flag is set, in order (cub stream compaction: library plumbing)
+  out.run_first.alloc(st, c);
+  size_t tmp_bytes = 0;
+  cub::CountingInputIterator<int64_t> line_index(0);
+  if (n >= 0x7fffffff) throw MlError(19, "too many lines");
+  ML_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, line_index, flag.p, out.run_first.p, total.p, (int)n, st));
+  DevBuf<char> tmp(st, tmp_bytes + 16);
+  ML_CUDA(cub::DeviceSelect::Flagged(tmp.p, tmp_bytes, line_index, flag.p, out.run_first.p, total.p, (int)n, st));
+  eng.launches++;
   int64_t runs = 0;
   total.download(&runs, 1);
   stream_sync(st);
   out.n_runs = runs;
-  out.run_first.alloc(st, (size_t)std::max<int64_t>(1, runs));
-  ML_LAUNCH(eng, "k_txt_compact", k_txt_compact<<<cdiv(n, 256), 256, 0, st>>>(flag.p, before.p, n, out.run_first.p));
-  stream_sync(st);
 }
 
 }  // namespace ml
