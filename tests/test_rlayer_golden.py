@@ -1,0 +1,88 @@
+"""tests/golden/rlayer_fixtures.npz (made by tests/golden/make_golden_rlayer.py): the restatements of the R-layer steps
+reproduce their committed outputs (CPU), and the CUDA path reproduces them too (GPU), without running the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rlayer_fixtures.npz")
+COLS = ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")
+INT_COLS = ("condition", "estimate_id", "segment_id", "start", "end", "num_cpgs", "num_cpgs_ref")
+FLOAT_COLS = ("width", "coverage", "coverage_ref", "pseudoweight", "beta", "std", "beta_ref", "std_ref", "diff", "cohen_d",
+              "pval", "coverage_score", "fdr")
+
+
+def close(a, b, tol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    ok = ~np.isnan(b)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.all(np.abs(a[ok] - b[ok]) <= tol * np.maximum(1.0, np.abs(b[ok])))
+
+
+def test_oracle_reproduces_fixtures(oracle):
+    from oracle import codec as OC, diffcall as DC, lmr_umr as LU
+    from test_calltable import pooled_from_table
+    g = np.load(GOLD)
+    t = {k: g["dmr_in_" + k] for k in COLS}
+    o = oracle.detect(t, 0, lambda2=25.0)
+    tab, called = DC.call_differences([DC.call_differences_singlechr(t, oracle.fast_diff_combine(o["estimates"], o["n_params"], o["n_est"]), 2)])
+    for k in INT_COLS:
+        assert np.array_equal(tab[k], g["dmr_out_" + k]), k
+    for k in FLOAT_COLS:
+        assert close(tab[k], g["dmr_out_" + k], 1e-13), k
+    assert np.array_equal(called, g["dmr_out_called"]) and called.sum() >= 1
+    t = {k: g["lu_in_" + k] for k in COLS}
+    o = oracle.detect(t, 0, lambda2=25.0)
+    call = oracle.call_table(pooled_from_table(t), oracle.segment_methylation_helper(o["estimates"], 0.01), 500.0)
+    for k, v in LU.annotate(call).items():
+        assert np.array_equal(v, g["lu_out_" + k], equal_nan=True), k
+    text = g["codec_text"].tobytes()
+    for mode, kw in (("counts", dict(mC=5, uC=6)), ("level", dict(cov=5, meth=4))):
+        r = OC.read_replicate(text, min_coverage=5, **kw)
+        assert np.array_equal(r["chr"].astype("U"), g[f"codec_{mode}_chr"])
+        for k in ("pos", "coverage", "Nmeth", "beta"):
+            assert np.array_equal(r[k], g[f"codec_{mode}_{k}"]), k
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_fixtures(engine):
+    from methylasso_b200 import codec
+    from methylasso_b200._native import MlParams
+    g = np.load(GOLD)
+    p = MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+    # DMR caller + FDR + threshold mask
+    t = {k: g["dmr_in_" + k] for k in COLS}
+    batch = engine.upload(np.array([0, t["pos"].size], np.int64), t)
+    res = engine.detect(batch, p)
+    try:
+        res.fast_diff_combine()
+        tab = dict(res.call_differences(batch, 2))
+        tab["fdr"] = engine.p_adjust_fdr(tab["pval"])
+        for k in INT_COLS:
+            assert np.array_equal(np.asarray(tab[k], np.int64), g["dmr_out_" + k]), k
+        for k in FLOAT_COLS:
+            assert close(tab[k], g["dmr_out_" + k], 1e-9 if k == "cohen_d" else 1e-12), k
+        with np.errstate(invalid="ignore"):
+            called = (~np.isnan(tab["diff"]) & (np.abs(tab["diff"]) >= 0.1) & (tab["coverage_score"] >= 70)
+                      & (tab["pval"] <= 0.05) & (tab["fdr"] <= 1) & (np.minimum(tab["num_cpgs"], tab["num_cpgs_ref"]) >= 4))
+        assert np.array_equal(called, g["dmr_out_called"])
+    finally:
+        res.free()
+        batch.free()
+    # LMR / UMR annotation
+    t = {k: g["lu_in_" + k] for k in COLS}
+    res = engine.detect_batch(np.array([0, t["pos"].size], np.int64), t, p)
+    try:
+        for k, v in res.call_lmr_umr(0.01, 500.0).items():
+            if k == "flank_beta":      # a neighbour's mean methylation: the call table's double-double mean against the
+                assert close(v, g["lu_out_" + k], 1e-13), k       # oracle's long double one, equal to the last bit or so
+            else:
+                assert np.array_equal(v, g["lu_out_" + k], equal_nan=True), k
+    finally:
+        res.free()
+    # codec
+    text = g["codec_text"].tobytes()
+    for mode, kw in (("counts", dict(mC=5, uC=6)), ("level", dict(cov=5, meth=4))):
+        r = codec.read_replicate(engine, text, min_coverage=5, **kw)
+        assert np.array_equal(r["chr"].astype("U"), g[f"codec_{mode}_chr"])
+        for k in ("pos", "coverage", "Nmeth", "beta"):
+            assert np.array_equal(r[k], g[f"codec_{mode}_{k}"]), k
