@@ -300,8 +300,8 @@ ML_API int ml_result_call_differences(ml_engine *eng, const ml_batch *b, ml_resu
  * flank.beta and is.sep among the V-shaped and flanking segments (:80-82), and the category after :83-86.  Logical
  * columns are three-valued as in R: 1 TRUE, 0 FALSE, -1 NA; numeric NA is NaN; category 0 = NA, 1 = "LMR", 2 = "UMR".
  * shift() in those statements walks the rows the statement selects (of one condition of one chromosome; of one
- * chromosome for :79), as data.table evaluates them.  The later steps of the function (valleys :97-131, PMD calls
- * :133-221) still run in R on this table.  params == NULL: the reference's defaults.  Any output may be NULL. */
+ * chromosome for :79), as data.table evaluates them.  The valleys (:100-133) are ml_result_call_valleys; the PMD calls
+ * (:143-221) still run in R on this table.  params == NULL: the reference's defaults.  Any output may be NULL. */
 typedef struct {
   double min_width, max_distance, flank_width, flank_dist_max, lmr_max_beta, flank_beta_min, umr_max_beta,
       umr_std_threshold, umr_large_width, umr_large_density;    /* 30, 500, 300, 5000, 0.5, 0.5, 0.1, 0.1, 500, 0.03 */
@@ -311,6 +311,28 @@ ML_API int ml_result_call_lmr_umr(ml_engine *eng, ml_result *r, double tol_val, 
                                   const ml_lmr_params *params, int64_t *n_rows, int8_t *is_admissible, int8_t *is_v,
                                   int8_t *is_flank, double *flank_dist, double *flank_beta, int8_t *is_sep,
                                   int8_t *category);
+
+/* ---- valleys / DMV (R/call.R:100-133, inside segment_methylation_singlechr) -----------------------------------------
+ * On the resident call table and its LMR / UMR categories (computed here with `lmr`, NULL = defaults): the "UMR-DMV"
+ * table `new_valleys` as it stands after :129 - runs of consecutive segments with beta <= valley_max_beta that are
+ * not separated by more than pmd_valley_min_width (:102-110; low.id.width / low.id.beta per run, the mean and the sums
+ * of doubles with R's long double accumulation), plus the UMRs that overlap none of them (:113-116), merged while
+ * their distance stays within pmd_valley_min_width (:119-124), kept when the merged region contains a run wider than
+ * pmd_valley_min_width ("DMV") and is itself admissible (:125-126).  Rows are ordered by (job, condition, start).
+ * beta is NaN where R has NA (a merged region that holds a UMR above valley_max_beta, :114-115).
+ * Per call-table row (n_rows of them, the order of ml_result_call_table): row_in_valley = 1 when the row overlaps a
+ * valley and :132-133 replaces it; low_id_width / low_id_beta = the columns of :106 (NaN = NA on high rows).
+ * The rest of the function (PMD split and calls, :143-221) still runs in R.  params == NULL: the reference's
+ * defaults with max_distance as passed.  Query with NULL outputs for the counts first; any output may be NULL. */
+typedef struct {
+  double valley_max_beta, pmd_valley_min_width, max_distance;   /* 0.1, 5000, 500 */
+  int32_t min_num_cpgs, reserved;                               /* 4, 0 */
+} ml_valley_params;
+ML_API int ml_result_call_valleys(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                  const ml_lmr_params *lmr, const ml_valley_params *params, int64_t *n_valleys,
+                                  int32_t *job, int32_t *condition, uint32_t *start, uint32_t *end, double *width,
+                                  double *beta, double *coverage, double *pseudoweight, int32_t *num_cpgs,
+                                  int64_t *n_rows, int8_t *row_in_valley, double *low_id_width, double *low_id_beta);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

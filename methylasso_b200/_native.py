@@ -36,6 +36,17 @@ class MlLmrParams(C.Structure):
         super().__init__(**d)
 
 
+class MlValleyParams(C.Structure):
+    """ml_valley_params (include/methylasso_b200.h): thresholds of R/call.R:100-133 with the reference's defaults."""
+    _fields_ = [("valley_max_beta", C.c_double), ("pmd_valley_min_width", C.c_double), ("max_distance", C.c_double),
+                ("min_num_cpgs", C.c_int32), ("reserved", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(valley_max_beta=0.1, pmd_valley_min_width=5000.0, max_distance=500.0, min_num_cpgs=4, reserved=0)
+        d.update(kw)
+        super().__init__(**d)
+
+
 # every symbol the header declares, with (restype, argtypes)
 _P = C.c_void_p
 _I64P = C.POINTER(C.c_int64)
@@ -87,6 +98,8 @@ SIGNATURES = {
     "ml_p_adjust_fdr": (C.c_int, [_P, C.c_int64, _P, _P]),
     "ml_result_call_differences": (C.c_int, [_P, _P, _P, C.c_int] + [C.c_double] * 4 + [_I64P] + [_P] * 20),
     "ml_result_call_lmr_umr": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), _I64P] + [_P] * 7),
+    "ml_result_call_valleys": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
+                                         _I64P] + [_P] * 9 + [_I64P] + [_P] * 3),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),

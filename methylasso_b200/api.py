@@ -447,6 +447,32 @@ class Result:
             *[_p(out[k]) for k in ("is_admissible", "is_V", "is_flank", "flank_dist", "flank_beta", "is_sep", "category")]))
         return {k: v[:nn.value] for k, v in out.items()}
 
+    VALLEY_COLUMNS = (("job", np.int32), ("condition", np.int32), ("start", np.uint32), ("end", np.uint32),
+                      ("width", np.float64), ("beta", np.float64), ("coverage", np.float64),
+                      ("pseudoweight", np.float64), ("num_cpgs", np.int32))
+
+    def call_valleys(self, tol_val=0.01, max_distance=500.0, valley_max_beta=0.1, pmd_valley_min_width=5000.0,
+                     min_num_cpgs=4, **lmr_thresholds):
+        """R/call.R:100-133 on the resident call table: the "UMR-DMV" valleys (one row each, ordered by job,
+        condition, start; category is "UMR-DMV" for every row) and, per row of call_table(), row_in_valley (the row
+        overlaps a valley and is replaced by it, :132-133) and the low.id.width / low.id.beta columns of :106."""
+        from ._native import MlLmrParams, MlValleyParams
+        lp = MlLmrParams(max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs), **lmr_thresholds)
+        vp = MlValleyParams(valley_max_beta=float(valley_max_beta), pmd_valley_min_width=float(pmd_valley_min_width),
+                            max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs))
+        nv, nr = C.c_int64(0), C.c_int64(0)
+        args = (self.eng.h, self.h, float(tol_val), float(max_distance), C.byref(lp), C.byref(vp))
+        self.eng._check(self.eng.lib.ml_result_call_valleys(*args, C.byref(nv), *([None] * 9), C.byref(nr), *([None] * 3)))
+        out = {k: np.empty(max(nv.value, 1), dt) for k, dt in self.VALLEY_COLUMNS}
+        rows = dict(row_in_valley=np.empty(max(nr.value, 1), np.int8), low_id_width=np.empty(max(nr.value, 1)),
+                    low_id_beta=np.empty(max(nr.value, 1)))
+        self.eng._check(self.eng.lib.ml_result_call_valleys(
+            *args, C.byref(nv), *[_p(out[k]) for k, _ in self.VALLEY_COLUMNS], C.byref(nr),
+            *[_p(rows[k]) for k in ("row_in_valley", "low_id_width", "low_id_beta")]))
+        res = {k: v[:nv.value] for k, v in out.items()}
+        res.update({k: v[:nr.value] for k, v in rows.items()})
+        return res
+
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
         ns = C.c_int64(0)

@@ -963,6 +963,56 @@ int ml_result_call_lmr_umr(ml_engine* eng, ml_result* r, double tol_val, double 
   return ML_OK;
   ML_CATCH
 }
+
+static_assert(sizeof(ml_valley_params) == sizeof(ValleyParams), "ml_valley_params / ValleyParams layout mismatch");
+
+int ml_result_call_valleys(ml_engine* eng, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* lmr,
+                           const ml_valley_params* params, int64_t* n_valleys, int32_t* job, int32_t* condition,
+                           uint32_t* start, uint32_t* end, double* width, double* beta, double* coverage,
+                           double* pseudoweight, int32_t* num_cpgs, int64_t* n_rows, int8_t* row_in_valley,
+                           double* low_id_width, double* low_id_beta) {
+  if (!eng || !r || !n_valleys) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  const int rc = ensure_call_table(eng, r, tol_val, max_distance);
+  if (rc) return rc;
+  LmrParams lp;
+  if (lmr) memcpy(&lp, lmr, sizeof lp);
+  ValleyParams vp;
+  if (params) memcpy(&vp, params, sizeof vp);
+  else vp.max_distance = max_distance;
+  const CallTable& ct = *r->r->call_cache;
+  LmrUmrColumns lu;
+  call_lmr_umr_device(eng->e, ct, lp, lu);
+  ValleyTable v;
+  DevBuf<int8_t> row_in;
+  DevBuf<double> low_w, low_b;
+  call_valleys_device(eng->e, ct, lu.category.p, vp, v, row_in, low_w, low_b);
+  *n_valleys = v.n;
+  if (n_rows) *n_rows = ct.t.n;
+  const size_t nv = (size_t)v.n, n = (size_t)ct.t.n;
+  if (nv) {
+    if (job) v.job.download(job, nv);
+    if (condition) v.condition.download(condition, nv);
+    if (start) v.start.download(start, nv);
+    if (end) v.end.download(end, nv);
+    if (width) v.width.download(width, nv);
+    if (beta) v.beta.download(beta, nv);
+    if (coverage) v.coverage.download(coverage, nv);
+    if (pseudoweight) v.pseudoweight.download(pseudoweight, nv);
+    if (num_cpgs) v.num_cpgs.download(num_cpgs, nv);
+  }
+  if (n) {
+    if (row_in_valley) row_in.download(row_in_valley, n);
+    if (low_id_width) low_w.download(low_id_width, n);
+    if (low_id_beta) low_b.download(low_id_beta, n);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
 }  // extern "C"
 
 namespace ml {

@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include "common.h"
+#include "valley_core.cuh"
 
 namespace ml {
 
@@ -77,6 +78,19 @@ struct LmrUmrColumns {
   void alloc(cudaStream_t st, int64_t count);
 };
 void call_lmr_umr_device(Engine& eng, const CallTable& t, const LmrParams& p, LmrUmrColumns& out);
+// R/call.R:100-129: the "UMR-DMV" valleys of a call table (ordered by job, condition, start), and per call-table row
+// whether a valley replaces it (:132-133); low_w / low_b are the low.id.width / low.id.beta columns of :106 (NaN = NA).
+struct ValleyTable {
+  int64_t n = 0;
+  DevBuf<int32_t> job, condition, num_cpgs;
+  DevBuf<uint32_t> start, end;
+  DevBuf<double> width, beta, coverage, pseudoweight;
+  DevBuf<int8_t> keep;
+  void alloc(cudaStream_t st, int64_t count);
+  ValleyOut view();
+};
+void call_valleys_device(Engine& eng, const CallTable& t, const int8_t* d_category, const ValleyParams& p,
+                         ValleyTable& out, DevBuf<int8_t>& row_in_valley, DevBuf<double>& low_w, DevBuf<double>& low_b);
 
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,

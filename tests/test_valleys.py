@@ -1,0 +1,204 @@
+"""Valleys / DMV of R/call.R:100-133: the numpy restatement (oracle/valleys.py) on hand-made tables, the device logic
+(csrc/valley_core.cuh) run on the CPU by tests/emu/emu_valleys.cpp against it, and the CUDA path against it on resident
+call tables (GPU)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from methylasso_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu_valleys.cpp")
+LIB = os.path.join(HERE, "emu", "libemu_valleys.so")
+VCOLS = (("job", np.int32), ("condition", np.int32), ("start", np.uint32), ("end", np.uint32), ("width", np.float64),
+         ("beta", np.float64), ("coverage", np.float64), ("pseudoweight", np.float64), ("num_cpgs", np.int32))
+
+
+def table(beta, width=None, gap=None, ncpg=None, cond=None, job=None, pw=None, cov=None):
+    n = len(beta)
+    width = np.full(n, 3000.0) if width is None else np.asarray(width, float)
+    gap = np.full(n, 100.0) if gap is None else np.asarray(gap, float)        # gap[i]: distance from row i-1's end
+    start = np.zeros(n)
+    end = np.zeros(n)
+    cond = np.ones(n, np.int32) if cond is None else np.asarray(cond, np.int32)
+    job = np.zeros(n, np.int32) if job is None else np.asarray(job, np.int32)
+    for i in range(n):
+        new = i == 0 or cond[i] != cond[i - 1] or job[i] != job[i - 1]
+        start[i] = 1000 if new else end[i - 1] + gap[i]
+        end[i] = start[i] + width[i] - 1
+    return dict(job=job, estimate_id=cond, start=start.astype(np.uint32), end=end.astype(np.uint32), width=width,
+                beta=np.asarray(beta, float), num_cpgs=np.full(n, 12, np.int32) if ncpg is None else np.asarray(ncpg, np.int32),
+                coverage=np.full(n, 240.0) if cov is None else np.asarray(cov, float),
+                pseudoweight=np.full(n, 100.0) if pw is None else np.asarray(pw, float))
+
+
+def test_oracle_hand_examples(oracle):
+    from oracle import valleys as V
+    # high | low low (6099 wide: a DMV) | high | low (3000 wide: "low") | high; everything within 5000 of its neighbour
+    t = table([0.9, 0.02, 0.04, 0.9, 0.05, 0.9])
+    r = V.valleys(t, np.zeros(6, np.int8))
+    low = r["low"]
+    assert low["is_high"].tolist() == [True, False, False, True, False, True]
+    assert low["low_id"].tolist() == [1, 1, 1, 2, 2, 3]
+    assert low["low_id_width"][1:3].tolist() == [6099.0, 6099.0] and low["low_id_width"][4] == 3000.0
+    assert np.isnan(low["low_id_width"][[0, 3, 5]]).all()
+    assert low["low_id_beta"][1] == (0.02 + 0.04) / 2 and low["low_id_beta"][4] == 0.05
+    v = r["valleys"]
+    # the DMV and the "low" region lie 3199 apart: one valley from row 1 to row 4; the high row between them is inside
+    # its span but contributes nothing to the sums
+    assert v["start"].tolist() == [float(t["start"][1])] and v["end"].tolist() == [float(t["end"][4])]
+    assert v["width"].tolist() == [4 * 3000.0 + 3 * 99.0] and v["num_cpgs"].tolist() == [36]
+    assert v["beta"][0] == np.mean([0.03, 0.05]) and v["coverage"].tolist() == [720.0] and v["pseudoweight"].tolist() == [300.0]
+    assert r["row_in_valley"].tolist() == [False, True, True, True, True, False]
+    # a gap wider than pmd_valley_min_width splits the run (follows.large.gap): two "low" regions, no DMV, no valley
+    r = V.valleys(table([0.9, 0.02, 0.04, 0.9], gap=[0, 100, 6000, 100]), np.zeros(4, np.int8))
+    assert r["low"]["low_id"].tolist() == [1, 1, 2, 3] and r["valleys"]["start"].size == 0 and not r["row_in_valley"].any()
+    # a DMV whose CpGs are too sparse is dropped (:125): 6099 / (4 - 1) > 500
+    r = V.valleys(table([0.9, 0.02, 0.04, 0.9], ncpg=[12, 2, 2, 12]), np.zeros(4, np.int8))
+    assert r["valleys"]["start"].size == 0
+    # conditions do not see each other: the second condition's first row opens a run of its own
+    t = table([0.9, 0.02, 0.04, 0.03, 0.02, 0.9], cond=[1, 1, 1, 2, 2, 2])
+    r = V.valleys(t, np.zeros(6, np.int8))
+    assert r["valleys"]["condition"].tolist() == [1, 2] and r["valleys"]["start"].tolist() == [float(t["start"][1]), 1000.0]
+    # an UMR above valley_max_beta (possible when valley_max_beta < umr_max_beta) overlaps no low region: it joins
+    # new_valleys with NA width / beta (:114-115) and the merged valley's mean(beta) becomes NA
+    t = table([0.9, 0.02, 0.03, 0.9, 0.08, 0.9])
+    r = V.valleys(t, np.array([0, 0, 0, 0, 2, 0], np.int8), valley_max_beta=0.05)
+    assert r["valleys"]["start"].tolist() == [float(t["start"][1])] and r["valleys"]["end"].tolist() == [float(t["end"][4])]
+    assert np.isnan(r["valleys"]["beta"][0]) and r["valleys"]["num_cpgs"].tolist() == [36]
+    # the same UMR lying inside a low region adds nothing
+    r2 = V.valleys(t, np.array([0, 0, 2, 0, 0, 0], np.int8), valley_max_beta=0.05)
+    assert r2["valleys"]["end"].tolist() == [float(t["end"][2])] and r2["valleys"]["beta"][0] == 0.025
+    # closed intervals: a row that only touches the valley's last base is replaced, one base further it is not
+    t = table([0.02, 0.04, 0.9], gap=[0, 100, 0])          # gap 0: the high row starts on the valley's end
+    assert t["start"][2] == t["end"][1]
+    assert V.valleys(t, np.zeros(3, np.int8))["row_in_valley"].tolist() == [True, True, True]
+    t = table([0.02, 0.04, 0.9], gap=[0, 100, 1])
+    assert V.valleys(t, np.zeros(3, np.int8))["row_in_valley"].tolist() == [True, True, False]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(HERE, "..", "methylasso_b200", "csrc", f) for f in ("valley_core.cuh", "x87.cuh", "hd.h")]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
+    L = C.CDLL(LIB)
+    L.emu_valleys.restype = C.c_int64
+    L.emu_x87_sum.restype = C.c_double
+    L.ref_x87_sum.restype = C.c_double
+
+    def run(t, category, valley_max_beta=0.1, pmd_valley_min_width=5000.0, max_distance=500.0, min_num_cpgs=4):
+        n = t["start"].size
+        cols = [np.ascontiguousarray(t[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("num_cpgs", np.int32),
+                                                              ("start", np.uint32), ("end", np.uint32), ("beta", np.float64),
+                                                              ("coverage", np.float64), ("pseudoweight", np.float64))]
+        cols.append(np.ascontiguousarray(category, np.int8))
+        m = max(n, 1)
+        out = {k: np.empty(m, dt) for k, dt in VCOLS}
+        rows = dict(row_in_valley=np.empty(m, np.int8), low_id_width=np.empty(m), low_id_beta=np.empty(m))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        k = L.emu_valleys(C.c_int64(n), *[p(a) for a in cols], C.c_double(valley_max_beta), C.c_double(pmd_valley_min_width),
+                          C.c_double(max_distance), C.c_int32(min_num_cpgs), *[p(out[c]) for c, _ in VCOLS],
+                          *[p(rows[c]) for c in ("row_in_valley", "low_id_width", "low_id_beta")])
+        res = {c: a[:k] for c, a in out.items()}
+        res.update({c: a[:n] for c, a in rows.items()})
+        return res
+    run.lib = L
+    return run
+
+
+def check_against_oracle(got, t, category, **kw):
+    """got: columns over all jobs (emulation or CUDA); the oracle works per chromosome."""
+    from oracle import valleys as V
+    n_valleys = 0
+    for j in np.unique(t["job"]):
+        m = t["job"] == j
+        want = V.valleys({k: v[m] for k, v in t.items()}, np.asarray(category)[m], **kw)
+        g = got["job"] == j
+        w = want["valleys"]
+        assert g.sum() == w["start"].size, (j, int(g.sum()), w["start"].size)
+        assert np.array_equal(got["condition"][g], w["condition"])
+        for k in ("start", "end", "width", "beta", "coverage", "pseudoweight", "num_cpgs"):
+            assert np.array_equal(got[k][g].astype(np.float64), w[k].astype(np.float64), equal_nan=True), (j, k)
+        assert np.array_equal(got["row_in_valley"][m] != 0, want["row_in_valley"]), j
+        assert np.array_equal(got["low_id_width"][m], want["low"]["low_id_width"], equal_nan=True), j
+        assert np.array_equal(got["low_id_beta"][m], want["low"]["low_id_beta"], equal_nan=True), j
+        n_valleys += w["start"].size
+    return n_valleys
+
+
+def random_table(rng, n_jobs=3, adjacent=False):
+    beta, width, gap, ncpg, cond, job, pw, cov = [], [], [], [], [], [], [], []
+    for j in range(n_jobs):
+        for c in range(1, int(rng.integers(1, 4))):
+            n = int(rng.integers(1, 120))
+            low = rng.random(n) < 0.55
+            beta += list(np.where(low, rng.random(n) * 0.12, 0.2 + rng.random(n) * 0.8))
+            width += list(rng.integers(1, 4000, n).astype(float) if not adjacent else rng.integers(1, 6, n).astype(float))
+            # gap 0 / 1: closed intervals that touch (positions one base apart) or just miss each other
+            gap += list(np.where(rng.random(n) < 0.1, rng.integers(4000, 9000, n), rng.integers(0, 3, n) if adjacent
+                                 else rng.integers(0, 1500, n)).astype(float))
+            ncpg += list(rng.integers(1, 60, n))
+            cond += [c] * n
+            job += [j] * n
+            pw += list(rng.random(n) * 1e4)
+            cov += list(rng.integers(5, 3000, n).astype(float))
+    return table(beta, width, gap, ncpg, cond, job, pw, cov)
+
+
+def test_emulated_device_logic_matches_oracle(emu, oracle):
+    from oracle import lmr_umr as LU
+    rng = np.random.default_rng(7)
+    total = nan_beta = 0
+    for trial in range(120):
+        t = random_table(rng, adjacent=trial % 4 == 3)
+        n = t["start"].size
+        if trial % 3 == 0:      # random UMR flags, also on high rows (valley_max_beta < umr_max_beta)
+            category = np.where(rng.random(n) < 0.2, 2, 0).astype(np.int8)
+        else:
+            category = np.zeros(n, np.int8)
+            category[(t["beta"] < 0.1) & (rng.random(n) < 0.5)] = 2
+        kw = [{}, dict(valley_max_beta=0.05, pmd_valley_min_width=2500.0), dict(pmd_valley_min_width=800.0, max_distance=200.0,
+                                                                                   min_num_cpgs=20)][trial % 3]
+        got = emu(t, category, **kw)
+        total += check_against_oracle(got, t, category, **kw)
+        nan_beta += int(np.isnan(got["beta"]).sum())
+    assert total > 300 and nan_beta > 5
+    # no rows at all; a table without any low row
+    assert emu(table([]), np.zeros(0, np.int8))["start"].size == 0
+    assert emu(table([0.9, 0.8]), np.zeros(2, np.int8))["start"].size == 0
+
+
+def test_emulated_long_double_sum(emu):
+    """sum() of doubles in R accumulates in long double (summary.c rsum): x87.cuh's accumulator against the host's."""
+    rng = np.random.default_rng(3)
+    L = emu.lib
+    for trial in range(4000):
+        n = int(rng.integers(1, 40))
+        x = np.ascontiguousarray(rng.random(n) * 10.0 ** rng.integers(-3, 7, n))
+        p = x.ctypes.data_as(C.c_void_p)
+        assert L.emu_x87_sum(n, p) == L.ref_x87_sum(n, p), trial
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps", [(2,), (2, 2)])
+def test_gpu_valleys_match_oracle(engine, oracle, reps):
+    from methylasso_b200._native import MlParams
+    tables = [synth.chromosome_table(n, 700 + i, reps) for i, n in enumerate((60_000, 9_000, 25_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        call = res.call_table(0.01, 500.0)
+        counts = []
+        for kw, lmr in (({}, {}), (dict(pmd_valley_min_width=1200.0), {}),
+                        (dict(valley_max_beta=0.04, pmd_valley_min_width=800.0, min_num_cpgs=3), dict(umr_large_density=0.01))):
+            category = res.call_lmr_umr(0.01, 500.0, **dict(lmr, **({"min_num_cpgs": kw["min_num_cpgs"]} if "min_num_cpgs" in kw else {})))["category"]
+            got = res.call_valleys(0.01, 500.0, **kw, **lmr)
+            assert got["row_in_valley"].size == call["start"].size
+            counts.append(check_against_oracle(got, call, category, max_distance=500.0, **kw))
+        assert counts[1] > 10 and counts[2] > 10, counts
+    finally:
+        res.free()
