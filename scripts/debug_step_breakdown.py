@@ -19,6 +19,7 @@ calls = [("detect", lambda st: st.__setitem__("res", eng.detect(batch, params)))
          ("call_table", lambda st: st["res"].call_table(0.01, 500.0, fetch=False)),
          ("call_pmd_segments", lambda st: st["res"].call_pmd_segments(0.01, 500.0, 1000.0, fetch=False)),
          ("call_lmr_umr (not in the bench step)", lambda st: st["res"].call_lmr_umr(0.01, 500.0)),
+         ("call_valleys (not in the bench step)", lambda st: st["res"].call_valleys(0.01, 500.0)),
          ("free", lambda st: st["res"].free())]
 
 def step(record=None, prof=False):

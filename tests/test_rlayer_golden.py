@@ -86,3 +86,42 @@ def test_gpu_reproduces_fixtures(engine):
         assert np.array_equal(r["chr"].astype("U"), g[f"codec_{mode}_chr"])
         for k in ("pos", "coverage", "Nmeth", "beta"):
             assert np.array_equal(r[k], g[f"codec_{mode}_{k}"]), k
+
+
+VGOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "valley_fixtures.npz")
+VALLEY_CASES = (("default", {}), ("narrow", dict(pmd_valley_min_width=1200.0)))
+
+
+def test_oracle_reproduces_valley_fixtures(oracle):
+    """tests/golden/valley_fixtures.npz (made by tests/golden/make_golden_valleys.py): R/call.R:100-133 restated."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_valleys as MG
+    v = np.load(VGOLD)
+    got = MG.compute(np.load(GOLD))
+    assert set(got) == set(v.files)
+    for k in v.files:
+        assert np.array_equal(got[k], v[k], equal_nan=True), k
+    assert v["narrow_start"].size >= 10
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_valley_fixtures(engine):
+    from methylasso_b200._native import MlParams
+    g, v = np.load(GOLD), np.load(VGOLD)
+    t = {k: g["lu_in_" + k] for k in COLS}
+    res = engine.detect_batch(np.array([0, t["pos"].size], np.int64), t, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        for name, kw in VALLEY_CASES:
+            got = res.call_valleys(0.01, 500.0, **kw)
+            for k in ("condition", "start", "end", "width", "coverage", "num_cpgs"):
+                assert np.array_equal(np.asarray(got[k], np.float64), np.asarray(v[f"{name}_{k}"], np.float64)), (name, k)
+            # means of the call table's per-segment means: the call table's double-double mean against the oracle's long
+            # double one can differ in the last bit, and these inherit it
+            for k in ("beta", "pseudoweight"):
+                assert close(got[k], v[f"{name}_{k}"], 1e-13), (name, k)
+            assert np.array_equal(got["row_in_valley"] != 0, v[f"{name}_row_in_valley"]), name
+            assert np.array_equal(got["low_id_width"], v[f"{name}_low_id_width"], equal_nan=True), name
+            assert close(got["low_id_beta"], v[f"{name}_low_id_beta"], 1e-13), name
+    finally:
+        res.free()
