@@ -322,7 +322,7 @@ ML_API int ml_result_call_lmr_umr(ml_engine *eng, ml_result *r, double tol_val, 
  * beta is NaN where R has NA (a merged region that holds a UMR above valley_max_beta, :114-115).
  * Per call-table row (n_rows of them, the order of ml_result_call_table): row_in_valley = 1 when the row overlaps a
  * valley and :132-133 replaces it; low_id_width / low_id_beta = the columns of :106 (NaN = NA on high rows).
- * The rest of the function (PMD split and calls, :143-221) still runs in R.  params == NULL: the reference's
+ * :134-164 continue in ml_result_call_pmd_split.  params == NULL: the reference's
  * defaults with max_distance as passed.  Query with NULL outputs for the counts first; any output may be NULL. */
 typedef struct {
   double valley_max_beta, pmd_valley_min_width, max_distance;   /* 0.1, 5000, 500 */
@@ -333,6 +333,25 @@ ML_API int ml_result_call_valleys(ml_engine *eng, ml_result *r, double tol_val, 
                                   int32_t *job, int32_t *condition, uint32_t *start, uint32_t *end, double *width,
                                   double *beta, double *coverage, double *pseudoweight, int32_t *num_cpgs,
                                   int64_t *n_rows, int8_t *row_in_valley, double *low_id_width, double *low_id_beta);
+
+/* ---- valleys into the call table, PMD candidate regions (R/call.R:131-164) --------------------------------------------
+ * Continues ml_result_call_valleys on the same resident tables.  Merged table = seg_call after :140: the call-table
+ * rows that overlap no valley plus the valleys, ordered by (job, condition, start); m_category 0 NA, 1 "LMR", 2 "UMR",
+ * 3 "UMR-DMV"; m_src_row = the row of ml_result_call_table / ml_result_call_lmr_umr it came from (-1 for a valley),
+ * m_src_valley = the row of ml_result_call_valleys (-1 for a call-table row) - the remaining columns of seg_call are
+ * gathered through these; m_segment_id = seq_len(.N) per condition (:137); m_follows_large_gap as recomputed at
+ * :139-140.  Pieces = split_call after :168: the PMD candidate segments of ml_result_call_pmd_segments(pmd_lambda2)
+ * (std_call, :93-95) intersected with the "isolate" / "complement" regions of :143-156 (split_pmds != 0: UMRs and
+ * valleys isolate, :145; else valleys only, :148), fused_std set to 0 outside "complement" (:161), ordered by (job,
+ * estimate_id, start) with p_segment_id = seq_len(.N) per estimate_id (:164).  The per-position gather and the PMD
+ * calls (:169-221) still run in R.  Query with NULL outputs for the counts first; any output may be NULL. */
+ML_API int ml_result_call_pmd_split(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                    double pmd_lambda2, const ml_lmr_params *lmr, const ml_valley_params *params,
+                                    int split_pmds, int64_t *n_merged, int32_t *m_job, int32_t *m_condition,
+                                    int32_t *m_segment_id, uint32_t *m_start, uint32_t *m_end, int8_t *m_category,
+                                    int32_t *m_src_row, int32_t *m_src_valley, int8_t *m_follows_large_gap,
+                                    int64_t *n_pieces, int32_t *p_job, int32_t *p_estimate_id, int32_t *p_segment_id,
+                                    uint32_t *p_start, uint32_t *p_end, double *p_fused_std, double *p_pseudoweight);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

@@ -100,6 +100,8 @@ SIGNATURES = {
     "ml_result_call_lmr_umr": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), _I64P] + [_P] * 7),
     "ml_result_call_valleys": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
                                          _I64P] + [_P] * 9 + [_I64P] + [_P] * 3),
+    "ml_result_call_pmd_split": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.POINTER(MlLmrParams),
+                                           C.POINTER(MlValleyParams), C.c_int, _I64P] + [_P] * 9 + [_I64P] + [_P] * 7),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),

@@ -473,6 +473,31 @@ class Result:
         res.update({k: v[:nr.value] for k, v in rows.items()})
         return res
 
+    MERGED_COLUMNS = (("job", np.int32), ("condition", np.int32), ("segment_id", np.int32), ("start", np.uint32),
+                      ("end", np.uint32), ("category", np.int8), ("src_row", np.int32), ("src_valley", np.int32),
+                      ("follows_large_gap", np.int8))
+    PIECE_COLUMNS = (("job", np.int32), ("estimate_id", np.int32), ("segment_id", np.int32), ("start", np.uint32),
+                     ("end", np.uint32), ("fused_std", np.float64), ("pseudoweight", np.float64))
+
+    def call_pmd_split(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, split_pmds=True, valley_max_beta=0.1,
+                       pmd_valley_min_width=5000.0, min_num_cpgs=4, **lmr_thresholds):
+        """R/call.R:131-164 on the resident tables: (seg_call after :140, split_call after :168) as two dicts of
+        columns (see ml_result_call_pmd_split)."""
+        from ._native import MlLmrParams, MlValleyParams
+        lp = MlLmrParams(max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs), **lmr_thresholds)
+        vp = MlValleyParams(valley_max_beta=float(valley_max_beta), pmd_valley_min_width=float(pmd_valley_min_width),
+                            max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs))
+        nm, npc = C.c_int64(0), C.c_int64(0)
+        args = (self.eng.h, self.h, float(tol_val), float(max_distance), float(pmd_lambda2), C.byref(lp), C.byref(vp),
+                1 if split_pmds else 0)
+        self.eng._check(self.eng.lib.ml_result_call_pmd_split(*args, C.byref(nm), *([None] * 9), C.byref(npc), *([None] * 7)))
+        merged = {k: np.empty(max(nm.value, 1), dt) for k, dt in self.MERGED_COLUMNS}
+        pieces = {k: np.empty(max(npc.value, 1), dt) for k, dt in self.PIECE_COLUMNS}
+        self.eng._check(self.eng.lib.ml_result_call_pmd_split(
+            *args, C.byref(nm), *[_p(merged[k]) for k, _ in self.MERGED_COLUMNS], C.byref(npc),
+            *[_p(pieces[k]) for k, _ in self.PIECE_COLUMNS]))
+        return ({k: v[:nm.value] for k, v in merged.items()}, {k: v[:npc.value] for k, v in pieces.items()})
+
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
         ns = C.c_int64(0)

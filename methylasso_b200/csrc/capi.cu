@@ -1013,6 +1013,66 @@ int ml_result_call_valleys(ml_engine* eng, ml_result* r, double tol_val, double 
   return ML_OK;
   ML_CATCH
 }
+
+int ml_result_call_pmd_split(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
+                             const ml_lmr_params* lmr, const ml_valley_params* params, int split_pmds,
+                             int64_t* n_merged, int32_t* m_job, int32_t* m_condition, int32_t* m_segment_id,
+                             uint32_t* m_start, uint32_t* m_end, int8_t* m_category, int32_t* m_src_row,
+                             int32_t* m_src_valley, int8_t* m_follows_large_gap, int64_t* n_pieces, int32_t* p_job,
+                             int32_t* p_estimate_id, int32_t* p_segment_id, uint32_t* p_start, uint32_t* p_end,
+                             double* p_fused_std, double* p_pseudoweight) {
+  if (!eng || !r || !n_merged || !n_pieces) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  int64_t ns = 0;   // call table + PMD candidate segments (std_call, R/call.R:93-95) resident
+  const int rc = ml_result_call_pmd_segments(eng, r, tol_val, max_distance, pmd_lambda2, &ns, nullptr, nullptr, nullptr,
+                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  LmrParams lp;
+  if (lmr) memcpy(&lp, lmr, sizeof lp);
+  ValleyParams vp;
+  if (params) memcpy(&vp, params, sizeof vp);
+  else vp.max_distance = max_distance;
+  Result& R = *r->r;
+  const CallTable& ct = *R.call_cache;
+  LmrUmrColumns lu;
+  call_lmr_umr_device(eng->e, ct, lp, lu);
+  ValleyTable v;
+  DevBuf<int8_t> row_in;
+  DevBuf<double> low_w, low_b;
+  call_valleys_device(eng->e, ct, lu.category.p, vp, v, row_in, low_w, low_b);
+  MergedDev M;
+  PiecesDev P;
+  call_pmd_split_device(eng->e, ct, lu.category.p, v, row_in.p, *R.call_pmd_cache, vp.pmd_valley_min_width, split_pmds, M, P);
+  *n_merged = M.n;
+  *n_pieces = P.n;
+  const size_t nm = (size_t)M.n, np = (size_t)P.n;
+  if (nm) {
+    if (m_job) M.job.download(m_job, nm);
+    if (m_condition) M.est.download(m_condition, nm);
+    if (m_segment_id) M.segment_id.download(m_segment_id, nm);
+    if (m_start) M.start.download(m_start, nm);
+    if (m_end) M.end.download(m_end, nm);
+    if (m_category) M.category.download(m_category, nm);
+    if (m_src_row) M.src_row.download(m_src_row, nm);
+    if (m_src_valley) M.src_valley.download(m_src_valley, nm);
+    if (m_follows_large_gap) M.follows_large_gap.download(m_follows_large_gap, nm);
+  }
+  if (np) {
+    if (p_job) P.job.download(p_job, np);
+    if (p_estimate_id) P.est.download(p_estimate_id, np);
+    if (p_segment_id) P.segment_id.download(p_segment_id, np);
+    if (p_start) P.start.download(p_start, np);
+    if (p_end) P.end.download(p_end, np);
+    if (p_fused_std) P.fused_std.download(p_fused_std, np);
+    if (p_pseudoweight) P.pw.download(p_pseudoweight, np);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
 }  // extern "C"
 
 namespace ml {

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include "common.h"
 #include "valley_core.cuh"
+#include "pmdsplit_core.cuh"
 
 namespace ml {
 
@@ -86,11 +87,33 @@ struct ValleyTable {
   DevBuf<uint32_t> start, end;
   DevBuf<double> width, beta, coverage, pseudoweight;
   DevBuf<int8_t> keep;
+  DevBuf<int32_t> row0;
   void alloc(cudaStream_t st, int64_t count);
   ValleyOut view();
 };
 void call_valleys_device(Engine& eng, const CallTable& t, const int8_t* d_category, const ValleyParams& p,
                          ValleyTable& out, DevBuf<int8_t>& row_in_valley, DevBuf<double>& low_w, DevBuf<double>& low_b);
+
+// R/call.R:131-164: seg_call with the valleys in place of the rows they overlap (MergedDev), and split_call, the PMD
+// candidate segments cut along the isolate / complement regions (PiecesDev).
+struct MergedDev {
+  int64_t n = 0;
+  DevBuf<int32_t> job, est, src_row, src_valley, segment_id;
+  DevBuf<uint32_t> start, end;
+  DevBuf<int8_t> category, follows_large_gap;
+  void alloc(cudaStream_t st, int64_t count);
+  MergedTable view();
+};
+struct PiecesDev {
+  int64_t n = 0;
+  DevBuf<int32_t> job, est, segment_id;
+  DevBuf<uint32_t> start, end;
+  DevBuf<double> fused_std, pw;
+  void alloc(cudaStream_t st, int64_t count);
+};
+void call_pmd_split_device(Engine& eng, const CallTable& t, const int8_t* d_category, ValleyTable& val,
+                           const int8_t* d_row_in_valley, const SegDeviceOut& pmd, double pmd_valley_min_width,
+                           int split_pmds, MergedDev& M, PiecesDev& P);
 
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,

@@ -125,6 +125,7 @@ struct ValleyOut {        // merged valleys (:122-124); `keep` = contains.valley
   uint32_t *start, *end;
   double *width, *beta, *cov, *pw;
   int8_t* keep;
+  int32_t* row0;                   // call-table row of the valley's first item (its start is the valley's start)
 };
 // :122-125  merged valley v = items [I.row index heads[v], heads[v + 1])
 ML_HD void vl_merge(const ValleyRows& c, const ValleyParams& p, const ValleyRuns& R, const ValleyItems& I,
@@ -149,6 +150,7 @@ ML_HD void vl_merge(const ValleyRows& c, const ValleyParams& p, const ValleyRuns
   const double b = x87_mean(r1 - r0, [&](int q) { return c.low_b[I.row[r0 + q]]; });
   const double w = hi - lo + 1, m = (double)ncpg;
   const int32_t row0 = I.row[r0];
+  o.row0[v] = row0;
   o.job[v] = c.job[row0];
   o.est[v] = c.est[row0];
   o.start[v] = (uint32_t)lo;

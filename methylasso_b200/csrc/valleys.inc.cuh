@@ -41,6 +41,7 @@ __global__ void k_dv_emit(int32_t n, const int32_t* __restrict__ list, ValleyOut
   out.start[k] = in.start[v]; out.end[k] = in.end[v];
   out.width[k] = in.width[v]; out.beta[k] = in.beta[v]; out.cov[k] = in.cov[v]; out.pw[k] = in.pw[v];
   out.keep[k] = 1;
+  out.row0[k] = in.row0[v];
 }
 __global__ void k_dv_row_in_valley(ValleyRows c, int32_t n_v, ValleyOut v, int8_t* __restrict__ row_in) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,10 +54,10 @@ void ValleyTable::alloc(cudaStream_t st, int64_t count) {
   n = count;
   const size_t c = (size_t)std::max<int64_t>(1, count);
   job.alloc(st, c); condition.alloc(st, c); num_cpgs.alloc(st, c); start.alloc(st, c); end.alloc(st, c);
-  width.alloc(st, c); beta.alloc(st, c); coverage.alloc(st, c); pseudoweight.alloc(st, c); keep.alloc(st, c);
+  width.alloc(st, c); beta.alloc(st, c); coverage.alloc(st, c); pseudoweight.alloc(st, c); keep.alloc(st, c); row0.alloc(st, c);
 }
 ValleyOut ValleyTable::view() {
-  return ValleyOut{job.p, condition.p, num_cpgs.p, start.p, end.p, width.p, beta.p, coverage.p, pseudoweight.p, keep.p};
+  return ValleyOut{job.p, condition.p, num_cpgs.p, start.p, end.p, width.p, beta.p, coverage.p, pseudoweight.p, keep.p, row0.p};
 }
 
 void call_valleys_device(Engine& eng, const CallTable& t, const int8_t* d_category, const ValleyParams& p,

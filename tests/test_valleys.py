@@ -87,6 +87,7 @@ def emu():
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
     L = C.CDLL(LIB)
     L.emu_valleys.restype = C.c_int64
+    L.emu_pmd_split.restype = C.c_int64
     L.emu_x87_sum.restype = C.c_double
     L.ref_x87_sum.restype = C.c_double
 
@@ -99,11 +100,13 @@ def emu():
         m = max(n, 1)
         out = {k: np.empty(m, dt) for k, dt in VCOLS}
         rows = dict(row_in_valley=np.empty(m, np.int8), low_id_width=np.empty(m), low_id_beta=np.empty(m))
+        row0 = np.empty(m, np.int32)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         k = L.emu_valleys(C.c_int64(n), *[p(a) for a in cols], C.c_double(valley_max_beta), C.c_double(pmd_valley_min_width),
                           C.c_double(max_distance), C.c_int32(min_num_cpgs), *[p(out[c]) for c, _ in VCOLS],
-                          *[p(rows[c]) for c in ("row_in_valley", "low_id_width", "low_id_beta")])
+                          *[p(rows[c]) for c in ("row_in_valley", "low_id_width", "low_id_beta")], p(row0))
         res = {c: a[:k] for c, a in out.items()}
+        res["row0"] = row0[:k]
         res.update({c: a[:n] for c, a in rows.items()})
         return res
     run.lib = L
@@ -200,5 +203,156 @@ def test_gpu_valleys_match_oracle(engine, oracle, reps):
             assert got["row_in_valley"].size == call["start"].size
             counts.append(check_against_oracle(got, call, category, max_distance=500.0, **kw))
         assert counts[1] > 10 and counts[2] > 10, counts
+    finally:
+        res.free()
+
+
+# ---- R/call.R:131-164: valleys into the call table, regions, pieces of the PMD candidate segments ------------------------
+MCOLS = (("job", np.int32), ("condition", np.int32), ("segment_id", np.int32), ("start", np.uint32), ("end", np.uint32),
+         ("category", np.int8), ("src_row", np.int32), ("src_valley", np.int32), ("follows_large_gap", np.int8))
+PCOLS = (("job", np.int32), ("estimate_id", np.int32), ("segment_id", np.int32), ("start", np.uint32), ("end", np.uint32),
+         ("fused_std", np.float64), ("pseudoweight", np.float64))
+
+
+def test_pmd_split_oracle_hand_example(oracle):
+    from oracle import pmd_split as PS, valleys as V
+    # rows: high | UMR (low, narrow) | high | low low (a DMV, 6099 wide) | high high; one PMD candidate segment over
+    # rows 0-2, a second one from row 3 on
+    t = table([0.9, 0.03, 0.9, 0.02, 0.04, 0.9, 0.8], gap=[0, 100, 100, 6000, 100, 100, 100])
+    category = np.array([0, 2, 0, 0, 0, 0, 1], np.int8)
+    val = V.valleys(t, category)
+    assert val["valleys"]["start"].tolist() == [float(t["start"][3])] and val["row_in_valley"].tolist() == [0, 0, 0, 1, 1, 0, 0]
+    M = PS.merged_table(t, category, val)
+    assert M["src_row"].tolist() == [0, 1, 2, -1, 5, 6] and M["src_valley"].tolist() == [-1, -1, -1, 0, -1, -1]
+    assert M["category"].tolist() == [0, 2, 0, 3, 0, 1] and M["segment_id"].tolist() == [1, 2, 3, 4, 5, 6]
+    assert M["follows_large_gap"].tolist() == [False, False, False, True, False, False]
+    reg = PS.regions(M)
+    # complement | isolate (the UMR) | complement | isolate (the valley, also behind a large gap) | complement
+    assert reg["isolate"].tolist() == [False, True, False, True, False]
+    assert reg["start"].tolist() == [float(t["start"][i]) for i in (0, 1, 2, 3, 5)]
+    assert reg["end"].tolist() == [float(t["end"][i]) for i in (0, 1, 2, 4, 6)]
+    std_call = dict(estimate_id=np.array([1, 1]), start=np.array([t["start"][0], t["start"][3]], float),
+                    end=np.array([t["start"][3] - 1.0, float(t["start"][6])]), fused_std=np.array([0.2, 0.3]),
+                    pseudoweight=np.array([7.0, 9.0]))
+    sp = PS.split_call(reg, std_call)
+    assert sp["start"].tolist() == [float(t["start"][i]) for i in (0, 1, 2, 3, 5)]
+    assert sp["end"].tolist() == [float(t["end"][0]), float(t["end"][1]), float(t["end"][2]), float(t["end"][4]), float(t["start"][6])]
+    assert sp["fused_std"].tolist() == [0.2, 0.0, 0.2, 0.0, 0.3] and sp["pseudoweight"].tolist() == [7.0, 7.0, 7.0, 9.0, 9.0]
+    assert sp["segment_id"].tolist() == [1, 2, 3, 4, 5]
+    # split.pmds = F: only the valley isolates
+    reg = PS.regions(M, split_pmds=False)
+    assert reg["isolate"].tolist() == [False, True, False]
+    assert PS.split_call(reg, std_call)["fused_std"].tolist() == [0.2, 0.0, 0.3]
+
+
+def random_std_call(rng, t):
+    """PMD candidate segments as the helper forms them: a segment starts on a call-table row's start and ends one base
+    before the next segment's start (the last one: on the last row's start)."""
+    out = dict(job=[], estimate_id=[], start=[], end=[], fused_std=[], pseudoweight=[])
+    key = t["job"].astype(np.int64) * 100 + t["estimate_id"]
+    for k in np.unique(key):
+        rows = np.nonzero(key == k)[0]
+        starts = t["start"][rows].astype(np.int64)
+        pick = np.unique(np.concatenate([[0], np.nonzero(rng.random(rows.size) < 0.25)[0]]))
+        pick = pick[np.concatenate([[True], np.diff(starts[pick]) > 0])]       # distinct starts
+        for a, b in zip(pick, np.append(pick[1:], -1)):
+            out["job"].append(int(t["job"][rows[0]]))
+            out["estimate_id"].append(int(t["estimate_id"][rows[0]]))
+            out["start"].append(starts[a])
+            out["end"].append(starts[b] - 1 if b >= 0 else starts[-1])
+            out["fused_std"].append(float(rng.random()))
+            out["pseudoweight"].append(float(rng.random() * 100))
+    return {k: np.asarray(v) for k, v in out.items()}
+
+
+def check_split_against_oracle(merged, pieces, t, category, val, std_call, split_pmds=True, pmd_valley_min_width=5000.0):
+    """merged / pieces: device (or emulated) tables over all jobs; val: the valley columns they were built from."""
+    from oracle import pmd_split as PS
+    n_pieces = 0
+    for j in np.unique(t["job"]):
+        m = t["job"] == j
+        rows = np.nonzero(m)[0]
+        g = val["job"] == j
+        v0 = int(np.nonzero(g)[0][0]) if g.any() else 0
+        vj = dict(valleys={k: np.asarray(val[k][g], np.float64 if k not in ("condition", "num_cpgs") else np.int64)
+                           for k in ("condition", "start", "end")}, row_in_valley=val["row_in_valley"][m] != 0)
+        M = PS.merged_table({k: v[m] for k, v in t.items()}, np.asarray(category)[m], vj, pmd_valley_min_width)
+        mm = merged["job"] == j
+        assert mm.sum() == M["condition"].size, j
+        for k in ("condition", "start", "end", "category", "segment_id"):
+            assert np.array_equal(np.asarray(merged[k][mm], np.float64), np.asarray(M[k], np.float64)), (j, k)
+        assert np.array_equal(merged["follows_large_gap"][mm] != 0, M["follows_large_gap"]), j
+        assert np.array_equal(merged["src_row"][mm], np.where(M["src_row"] >= 0, M["src_row"] + rows[0], -1)), j
+        assert np.array_equal(merged["src_valley"][mm], np.where(M["src_valley"] >= 0, M["src_valley"] + v0, -1)), j
+        x = std_call["job"] == j
+        want = PS.split_call(PS.regions(M, split_pmds), {k: v[x] for k, v in std_call.items()})
+        pp = pieces["job"] == j
+        assert pp.sum() == want["start"].size, (j, int(pp.sum()), want["start"].size)
+        for k in ("estimate_id", "segment_id", "start", "end", "fused_std", "pseudoweight"):
+            assert np.array_equal(np.asarray(pieces[k][pp], np.float64), np.asarray(want[k], np.float64)), (j, k)
+        n_pieces += want["start"].size
+    return n_pieces
+
+
+def test_emulated_pmd_split_matches_oracle(emu, oracle):
+    rng = np.random.default_rng(11)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    total = n_valley_rows = 0
+    for trial in range(90):
+        t = random_table(rng, adjacent=trial % 5 == 4)
+        n = t["start"].size
+        category = np.zeros(n, np.int8)
+        category[(t["beta"] < 0.1) & (rng.random(n) < 0.4)] = 2
+        category[(t["beta"] >= 0.1) & (rng.random(n) < 0.1)] = 1
+        kw = [{}, dict(pmd_valley_min_width=2500.0), dict(valley_max_beta=0.05, pmd_valley_min_width=1500.0)][trial % 3]
+        pvw = kw.get("pmd_valley_min_width", 5000.0)
+        val = emu(t, category, **kw)
+        x = random_std_call(rng, t)
+        cols = [np.ascontiguousarray(t[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32), ("end", np.uint32))]
+        cols += [np.ascontiguousarray(category, np.int8), np.ascontiguousarray(val["row_in_valley"], np.int8)]
+        nv = val["start"].size
+        vcols = [np.ascontiguousarray(val[k], dt) for k, dt in (("job", np.int32), ("condition", np.int32), ("start", np.uint32),
+                                                                 ("end", np.uint32), ("row0", np.int32))]
+        nx = x["start"].size
+        xcols = [np.ascontiguousarray(x[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32),
+                                                               ("end", np.uint32), ("fused_std", np.float64), ("pseudoweight", np.float64))]
+        split_pmds = trial % 4 != 1
+        merged = {k: np.empty(n + nv + 1, dt) for k, dt in MCOLS}
+        cap = nx + 2 * (n + nv) + 8
+        pieces = {k: np.empty(cap, dt) for k, dt in PCOLS}
+        npc = C.c_int64(0)
+        nm = emu.lib.emu_pmd_split(C.c_int64(n), *[p(a) for a in cols], C.c_int32(nv), *[p(a) for a in vcols], C.c_int32(nx),
+                                   *[p(a) for a in xcols], C.c_double(pvw), C.c_int(1 if split_pmds else 0),
+                                   *[p(merged[k]) for k in ("job", "condition", "segment_id", "start", "end", "category", "src_row",
+                                                            "src_valley", "follows_large_gap")],
+                                   C.c_int64(cap), C.byref(npc), *[p(pieces[k]) for k, _ in PCOLS])
+        assert npc.value >= 0
+        merged = {k: v[:nm] for k, v in merged.items()}
+        pieces = {k: v[:npc.value] for k, v in pieces.items()}
+        total += check_split_against_oracle(merged, pieces, t, category, val, x, split_pmds, pvw)
+        n_valley_rows += int((merged["src_valley"] >= 0).sum())
+    assert total > 2000 and n_valley_rows > 100
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps", [(2,), (2, 2)])
+def test_gpu_pmd_split_matches_oracle(engine, oracle, reps):
+    from methylasso_b200._native import MlParams
+    tables = [synth.chromosome_table(n, 800 + i, reps) for i, n in enumerate((60_000, 9_000, 25_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        call = res.call_table(0.01, 500.0)
+        category = res.call_lmr_umr(0.01, 500.0)["category"]
+        counts = []
+        for kw, split_pmds, lam in (({}, True, 1000.0), (dict(pmd_valley_min_width=1200.0), True, 100.0),
+                                    (dict(pmd_valley_min_width=1200.0), False, 100.0)):
+            val = res.call_valleys(0.01, 500.0, **kw)
+            x = res.call_pmd_segments(0.01, 500.0, lam)
+            merged, pieces = res.call_pmd_split(0.01, 500.0, lam, split_pmds, **kw)
+            counts.append(check_split_against_oracle(merged, pieces, call, category, val, x, split_pmds,
+                                                     kw.get("pmd_valley_min_width", 5000.0)))
+            assert (merged["src_valley"] >= 0).sum() == val["start"].size
+        assert min(counts) > 50, counts
     finally:
         res.free()
