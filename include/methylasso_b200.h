@@ -344,7 +344,7 @@ ML_API int ml_result_call_valleys(ml_engine *eng, ml_result *r, double tol_val, 
  * (std_call, :93-95) intersected with the "isolate" / "complement" regions of :143-156 (split_pmds != 0: UMRs and
  * valleys isolate, :145; else valleys only, :148), fused_std set to 0 outside "complement" (:161), ordered by (job,
  * estimate_id, start) with p_segment_id = seq_len(.N) per estimate_id (:164).  The per-position gather and the PMD
- * calls (:169-221) still run in R.  Query with NULL outputs for the counts first; any output may be NULL. */
+ * calls (:169-199) are ml_result_call_pmds.  Query with NULL outputs for the counts first; any output may be NULL. */
 ML_API int ml_result_call_pmd_split(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
                                     double pmd_lambda2, const ml_lmr_params *lmr, const ml_valley_params *params,
                                     int split_pmds, int64_t *n_merged, int32_t *m_job, int32_t *m_condition,
@@ -352,6 +352,29 @@ ML_API int ml_result_call_pmd_split(ml_engine *eng, ml_result *r, double tol_val
                                     int32_t *m_src_row, int32_t *m_src_valley, int8_t *m_follows_large_gap,
                                     int64_t *n_pieces, int32_t *p_job, int32_t *p_estimate_id, int32_t *p_segment_id,
                                     uint32_t *p_start, uint32_t *p_end, double *p_fused_std, double *p_pseudoweight);
+
+/* ---- PMD calls (R/call.R:169-199) ---------------------------------------------------------------------------------------
+ * Continues ml_result_call_pmd_split on the same resident tables and the pooled per-position data of the FAST result:
+ * every piece of split_call collects the positions with start - 1 <= pos <= end (foverlaps of [pos, pos + 1], :170),
+ * shrinks to them (:171) and gets the mean of Nmeth / coverage, the position count and its fused_std (:172-175); a
+ * piece is called "PMD" when it is wider than pmd_valley_min_width, dense enough (width / (num.cpgs - 1) <
+ * max_distance), fused_std >= pmd_std_threshold and beta < pmd_max_beta (:177-179); consecutive pieces with the same
+ * call and no gap wider than pmd_valley_min_width are merged (merge_pmds != 0, :182-187); each merged region reports
+ * start, end, width, num.cpgs, mean(fused_std) and the mean / sd of the methylation values of all its positions
+ * (:190-198; sd of a single value -> 0).  Rows = pmd_call after :198, ordered by (job, condition, start);
+ * category 1 = "PMD", 0 = "other" (drop = T keeps the PMD rows, :217); segment_id numbers the regions per condition.
+ * The means / sd use double-double sums where R accumulates in long double (equal to the last bit or so, as in the
+ * call table).  The final annotation of seg_call with PMD.status (:201-215) still runs in R.
+ * pmd == NULL: the reference's defaults.  Query with NULL outputs for *n_rows first; any output may be NULL. */
+typedef struct {
+  double pmd_lambda2, pmd_std_threshold, pmd_max_beta;          /* 1000, 0.15, 0.75 */
+  int32_t split_pmds, merge_pmds;                               /* 1, 1 */
+} ml_pmd_params;
+ML_API int ml_result_call_pmds(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                               const ml_lmr_params *lmr, const ml_valley_params *valley, const ml_pmd_params *pmd,
+                               int64_t *n_rows, int32_t *job, int32_t *condition, int8_t *category,
+                               int32_t *segment_id, uint32_t *start, uint32_t *end, double *width, int32_t *num_cpgs,
+                               double *fused_std, double *beta, double *std);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

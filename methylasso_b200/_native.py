@@ -47,6 +47,17 @@ class MlValleyParams(C.Structure):
         super().__init__(**d)
 
 
+class MlPmdParams(C.Structure):
+    """ml_pmd_params (include/methylasso_b200.h): R/call.R:31-35 defaults for the PMD calls."""
+    _fields_ = [("pmd_lambda2", C.c_double), ("pmd_std_threshold", C.c_double), ("pmd_max_beta", C.c_double),
+                ("split_pmds", C.c_int32), ("merge_pmds", C.c_int32)]
+
+    def __init__(self, **kw):
+        d = dict(pmd_lambda2=1000.0, pmd_std_threshold=0.15, pmd_max_beta=0.75, split_pmds=1, merge_pmds=1)
+        d.update(kw)
+        super().__init__(**d)
+
+
 # every symbol the header declares, with (restype, argtypes)
 _P = C.c_void_p
 _I64P = C.POINTER(C.c_int64)
@@ -102,6 +113,8 @@ SIGNATURES = {
                                          _I64P] + [_P] * 9 + [_I64P] + [_P] * 3),
     "ml_result_call_pmd_split": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.POINTER(MlLmrParams),
                                            C.POINTER(MlValleyParams), C.c_int, _I64P] + [_P] * 9 + [_I64P] + [_P] * 7),
+    "ml_result_call_pmds": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
+                                      C.POINTER(MlPmdParams), _I64P] + [_P] * 11),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),

@@ -1014,6 +1014,40 @@ int ml_result_call_valleys(ml_engine* eng, ml_result* r, double tol_val, double 
   ML_CATCH
 }
 
+namespace {
+// R/call.R:75-168 on the resident tables: categories, valleys, merged table, pieces (shared by the two entries below)
+struct PmdSplitState {
+  LmrUmrColumns lu;
+  ValleyTable v;
+  DevBuf<int8_t> row_in;
+  DevBuf<double> low_w, low_b;
+  MergedDev M;
+  PiecesDev P;
+  ValleyParams vp;
+};
+int run_pmd_split(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
+                  const ml_lmr_params* lmr, const ml_valley_params* params, int split_pmds, PmdSplitState& S) {
+  int64_t ns = 0;   // call table + PMD candidate segments (std_call, R/call.R:93-95) resident
+  const int rc = ml_result_call_pmd_segments(eng, r, tol_val, max_distance, pmd_lambda2, &ns, nullptr, nullptr, nullptr,
+                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  LmrParams lp;
+  if (lmr) memcpy(&lp, lmr, sizeof lp);
+  if (params) memcpy(&S.vp, params, sizeof S.vp);
+  else S.vp.max_distance = max_distance;
+  Result& R = *r->r;
+  const CallTable& ct = *R.call_cache;
+  call_lmr_umr_device(eng->e, ct, lp, S.lu);
+  call_valleys_device(eng->e, ct, S.lu.category.p, S.vp, S.v, S.row_in, S.low_w, S.low_b);
+  call_pmd_split_device(eng->e, ct, S.lu.category.p, S.v, S.row_in.p, *R.call_pmd_cache, S.vp.pmd_valley_min_width, split_pmds,
+                        S.M, S.P);
+  return ML_OK;
+}
+}  // namespace
+
 int ml_result_call_pmd_split(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
                              const ml_lmr_params* lmr, const ml_valley_params* params, int split_pmds,
                              int64_t* n_merged, int32_t* m_job, int32_t* m_condition, int32_t* m_segment_id,
@@ -1023,29 +1057,11 @@ int ml_result_call_pmd_split(ml_engine* eng, ml_result* r, double tol_val, doubl
                              double* p_fused_std, double* p_pseudoweight) {
   if (!eng || !r || !n_merged || !n_pieces) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
-  ML_CUDA(cudaSetDevice(eng->e.device));
-  tls_pool() = eng->e.pool;
-  tls_mailbox() = &eng->e.mailbox;
-  int64_t ns = 0;   // call table + PMD candidate segments (std_call, R/call.R:93-95) resident
-  const int rc = ml_result_call_pmd_segments(eng, r, tol_val, max_distance, pmd_lambda2, &ns, nullptr, nullptr, nullptr,
-                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  PmdSplitState S;
+  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pmd_lambda2, lmr, params, split_pmds, S);
   if (rc) return rc;
-  LmrParams lp;
-  if (lmr) memcpy(&lp, lmr, sizeof lp);
-  ValleyParams vp;
-  if (params) memcpy(&vp, params, sizeof vp);
-  else vp.max_distance = max_distance;
-  Result& R = *r->r;
-  const CallTable& ct = *R.call_cache;
-  LmrUmrColumns lu;
-  call_lmr_umr_device(eng->e, ct, lp, lu);
-  ValleyTable v;
-  DevBuf<int8_t> row_in;
-  DevBuf<double> low_w, low_b;
-  call_valleys_device(eng->e, ct, lu.category.p, vp, v, row_in, low_w, low_b);
-  MergedDev M;
-  PiecesDev P;
-  call_pmd_split_device(eng->e, ct, lu.category.p, v, row_in.p, *R.call_pmd_cache, vp.pmd_valley_min_width, split_pmds, M, P);
+  MergedDev& M = S.M;
+  PiecesDev& P = S.P;
   *n_merged = M.n;
   *n_pieces = P.n;
   const size_t nm = (size_t)M.n, np = (size_t)P.n;
@@ -1068,6 +1084,46 @@ int ml_result_call_pmd_split(ml_engine* eng, ml_result* r, double tol_val, doubl
     if (p_end) P.end.download(p_end, np);
     if (p_fused_std) P.fused_std.download(p_fused_std, np);
     if (p_pseudoweight) P.pw.download(p_pseudoweight, np);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_result_call_pmds(ml_engine* eng, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* lmr,
+                        const ml_valley_params* valley, const ml_pmd_params* pmd, int64_t* n_rows, int32_t* job,
+                        int32_t* condition, int8_t* category, int32_t* segment_id, uint32_t* start, uint32_t* end,
+                        double* width, int32_t* num_cpgs, double* fused_std, double* beta, double* std_) {
+  if (!eng || !r || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
+  if (pmd) pp = *pmd;
+  PmdSplitState S;
+  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, S);
+  if (rc) return rc;
+  Result& R = *r->r;
+  PmdCallParams cp;
+  cp.pmd_std_threshold = pp.pmd_std_threshold;
+  cp.pmd_max_beta = pp.pmd_max_beta;
+  cp.pmd_valley_min_width = S.vp.pmd_valley_min_width;
+  cp.max_distance = S.vp.max_distance;
+  cp.merge_pmds = pp.merge_pmds;
+  PmdCallDev out;
+  call_pmds_device(eng->e, result_groups(R), R.start.p, 1, R.betahat.p, R.pw.p, S.P, cp, out);
+  *n_rows = out.n;
+  const size_t n = (size_t)out.n;
+  if (n) {
+    if (job) out.job.download(job, n);
+    if (condition) out.est.download(condition, n);
+    if (category) out.category.download(category, n);
+    if (segment_id) out.segment_id.download(segment_id, n);
+    if (start) out.start.download(start, n);
+    if (end) out.end.download(end, n);
+    if (width) out.width.download(width, n);
+    if (num_cpgs) out.num_cpgs.download(num_cpgs, n);
+    if (fused_std) out.fused_std.download(fused_std, n);
+    if (beta) out.beta.download(beta, n);
+    if (std_) out.std_.download(std_, n);
   }
   stream_sync(eng->e.stream);
   return ML_OK;

@@ -1,0 +1,254 @@
+// pmdcall.inc.cuh — R/call.R:169-199 (segment_methylation_singlechr): the pooled per-position data gathered along
+// split_call (:169-175), the PMD calls (:177-180), their merge (:182-190) and the statistics of the merged regions
+// (:193-198).  Included at the end of segment.cu: it reuses the call table's row accessors (RowsFromEstimates: the
+// pooled Nmeth / coverage of a FAST result), its foverlaps row search (segment_rows) and its double-double sums, which
+// stand in for R's long double accumulators as they do for the call table (results equal to the last bit or so).
+namespace {
+
+constexpr int PC_THREADS = 128;
+
+// sum over the block; every thread receives the total (fixed combination order: lanes by shuffle, warps in order)
+__device__ __forceinline__ DD pc_block_sum(DD v, DD* sm) {
+  v = dd_warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  DD t = sm[0];
+  for (int k = 1; k < PC_THREADS / 32; ++k) t = dd_merge(t, sm[k]);
+  return t;
+}
+__device__ __forceinline__ double pc_block_sum(double v, double* sm) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  double t = sm[0];
+  for (int k = 1; k < PC_THREADS / 32; ++k) t += sm[k];
+  return t;
+}
+__device__ __forceinline__ int pc_find_group(const SegGroup* __restrict__ groups, int ng, int32_t job, int32_t est) {
+  int lo = 0, hi = ng;               // groups are ordered by (job, estimate_id)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const bool less = groups[mid].job < job || (groups[mid].job == job && groups[mid].estimate_id < est);
+    if (less) lo = mid + 1; else hi = mid;
+  }
+  return (lo < ng && groups[lo].job == job && groups[lo].estimate_id == est) ? lo : -1;
+}
+
+struct PcPieces {         // per piece of split_call: inputs, then what :169-175 compute
+  int32_t n;
+  const int32_t *job, *est;
+  const uint32_t *start, *end;
+  const double* fused_std;
+  int32_t *group, *ncpg;           // ncpg == 0: no position falls on the piece, it has no row in pmd_call
+  int64_t *row_lo, *row_hi;
+  uint32_t *pstart, *pend;         // min(pos), max(pos) + 2 (:171)
+  double *beta, *cov;
+};
+
+// :169-175  one block per piece: positions with start - 1 <= pos <= end (foverlaps of [pos, pos + 1]), mean of
+// Nmeth / coverage (two-pass, as R's mean), coverage sum, position count, first and last position
+template <class Rows>
+__global__ void __launch_bounds__(PC_THREADS)
+k_pc_piece_stats(const SegGroup* __restrict__ groups, int ng, const void* __restrict__ pos, int pos_f64, Rows rows, PcPieces P) {
+  __shared__ DD smd[PC_THREADS / 32];
+  __shared__ double sms[PC_THREADS / 32];
+  const int k = blockIdx.x;
+  const int g = pc_find_group(groups, ng, P.job[k], P.est[k]);
+  if (g < 0) {
+    if (threadIdx.x == 0) { P.group[k] = -1; P.ncpg[k] = 0; P.row_lo[k] = P.row_hi[k] = 0; }
+    return;
+  }
+  const SegGroup G = groups[g];
+  int64_t lo, hi;
+  segment_rows(G, pos, pos_f64, P.start[k], P.end[k], lo, hi);
+  DD sum{0.0, 0.0};
+  double csum = 0.0, m = 0.0, first = 4294967296.0, last = -1.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += PC_THREADS) {
+    if (!rows.valid(i)) continue;
+    dd_add(sum, rows.x(i));
+    csum += rows.cov(i);
+    m += 1.0;
+    const double p = (double)seg_start_at(G, pos, pos_f64, i);
+    first = fmin(first, p);
+    last = fmax(last, p);
+  }
+  sum = pc_block_sum(sum, smd);
+  csum = pc_block_sum(csum, sms);
+  m = pc_block_sum(m, sms);
+  // the positions are sorted: first / last valid one by a min / max over the block
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    first = fmin(first, __shfl_xor_sync(0xffffffffu, first, d));
+    last = fmax(last, __shfl_xor_sync(0xffffffffu, last, d));
+  }
+  __shared__ double smf[PC_THREADS / 32], sml[PC_THREADS / 32];
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { smf[threadIdx.x >> 5] = first; sml[threadIdx.x >> 5] = last; }
+  __syncthreads();
+  for (int w = 0; w < PC_THREADS / 32; ++w) { first = fmin(first, smf[w]); last = fmax(last, sml[w]); }
+  double mean = (sum.hi + sum.lo) / m;
+  DD t{0.0, 0.0};
+  if (m > 0 && is_finite(mean))
+    for (int64_t i = lo + threadIdx.x; i < hi; i += PC_THREADS)
+      if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+  t = pc_block_sum(t, smd);
+  if (m > 0 && is_finite(mean)) mean += (t.hi + t.lo) / m;
+  if (threadIdx.x == 0) {
+    P.group[k] = g;
+    P.ncpg[k] = (int32_t)m;
+    P.row_lo[k] = lo;
+    P.row_hi[k] = hi;
+    P.pstart[k] = m > 0 ? (uint32_t)first : 0u;
+    P.pend[k] = m > 0 ? (uint32_t)last + 2u : 0u;
+    P.beta[k] = mean;
+    P.cov[k] = csum;
+  }
+}
+__global__ void k_pc_live(PcPieces P, int32_t* __restrict__ flag) {
+  const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < P.n) flag[k] = P.ncpg[k] > 0 ? 1 : 0;
+}
+// :177-180  is.admissible and the PMD call of a pmd_call row (1 "PMD", 0 "other")
+__device__ __forceinline__ int8_t pc_category(const PcPieces& P, const PmdCallParams& p, int32_t k) {
+  const double w = (double)P.pend[k] - (double)P.pstart[k] + 1, m = (double)P.ncpg[k];
+  const bool adm = w > p.pmd_valley_min_width && w / (m - 1) < p.max_distance;
+  return (adm && P.fused_std[k] >= p.pmd_std_threshold && P.beta[k] < p.pmd_max_beta) ? 1 : 0;
+}
+// :182-190  a merged region starts where the condition starts, the call changes or a large gap precedes (merge.pmds);
+// without merging every row is its own region
+__global__ void k_pc_heads(PcPieces P, PmdCallParams p, int32_t n_live, const int32_t* __restrict__ live,
+                           int8_t* __restrict__ cat, int32_t* __restrict__ flag) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_live) return;
+  const int32_t k = live[r];
+  const int8_t c = pc_category(P, p, k);
+  cat[r] = c;
+  int32_t head = 1;
+  if (r > 0 && p.merge_pmds) {
+    const int32_t q = live[r - 1];
+    if (P.job[q] == P.job[k] && P.est[q] == P.est[k])
+      head = (pc_category(P, p, q) != c || (double)P.pstart[k] - (double)P.pend[q] > p.pmd_valley_min_width) ? 1 : 0;
+  }
+  flag[r] = head;
+}
+struct PcOut {
+  int32_t *job, *est, *segment_id, *ncpg;
+  int8_t* category;
+  uint32_t *start, *end;
+  double *width, *fused_std, *beta, *std_;
+};
+// :193-198  one block per merged region: min start, max end, num.cpgs, mean(fused_std) over its rows (R's mean),
+// mean / sd of the methylation values of all its positions (rows matched by two touching pieces count twice, as the
+// concatenated betavals lists do)
+template <class Rows>
+__global__ void __launch_bounds__(PC_THREADS)
+k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const int8_t* __restrict__ cat,
+           const int32_t* __restrict__ heads, int32_t n_heads, Rows rows, PcOut o) {
+  __shared__ DD smd[PC_THREADS / 32];
+  __shared__ double sms[PC_THREADS / 32];
+  const int v = blockIdx.x;
+  const int32_t r0 = heads[v], r1 = v + 1 < n_heads ? heads[v + 1] : n_live;
+  DD sum{0.0, 0.0};
+  double m = 0.0;
+  for (int32_t r = r0; r < r1; ++r) {
+    const int32_t k = live[r];
+    for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
+      if (rows.valid(i)) { dd_add(sum, rows.x(i)); m += 1.0; }
+  }
+  sum = pc_block_sum(sum, smd);
+  m = pc_block_sum(m, sms);
+  double mean = (sum.hi + sum.lo) / m;
+  DD t{0.0, 0.0};
+  if (is_finite(mean))
+    for (int32_t r = r0; r < r1; ++r) {
+      const int32_t k = live[r];
+      for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
+        if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+    }
+  t = pc_block_sum(t, smd);
+  if (is_finite(mean)) mean += (t.hi + t.lo) / m;
+  DD ss{0.0, 0.0};
+  if (m >= 2)
+    for (int32_t r = r0; r < r1; ++r) {
+      const int32_t k = live[r];
+      for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
+        if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
+    }
+  ss = pc_block_sum(ss, smd);
+  if (threadIdx.x != 0) return;
+  uint32_t lo = P.pstart[live[r0]], hi = P.pend[live[r0]];
+  int64_t ncpg = 0;
+  for (int32_t r = r0; r < r1; ++r) {
+    const int32_t k = live[r];
+    lo = P.pstart[k] < lo ? P.pstart[k] : lo;
+    hi = P.pend[k] > hi ? P.pend[k] : hi;
+    ncpg += P.ncpg[k];
+  }
+  const int32_t k0 = live[r0];
+  o.job[v] = P.job[k0];
+  o.est[v] = P.est[k0];
+  o.category[v] = cat[r0];
+  o.start[v] = lo;
+  o.end[v] = hi;
+  o.ncpg[v] = (int32_t)ncpg;
+  o.fused_std[v] = x87_mean(r1 - r0, [&](int q) { return P.fused_std[live[r0 + q]]; });
+  o.width[v] = (double)hi - (double)lo + 1;
+  o.beta[v] = mean;
+  o.std_[v] = m >= 2 ? sqrt((ss.hi + ss.lo) / (m - 1)) : 0.0;      // sd of one value is NA -> 0 (:197)
+}
+// segment_id of :186 / :189 is only a grouping key in the reference; the regions are numbered 1.. per condition here
+__global__ void k_pc_group_heads(int32_t n, PcOut o, int32_t* __restrict__ flag) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) flag[v] = (v == 0 || o.job[v] != o.job[v - 1] || o.est[v] != o.est[v - 1]) ? 1 : 0;
+}
+
+}  // namespace
+
+void PmdCallDev::alloc(cudaStream_t st, int64_t count) {
+  n = count;
+  const size_t c = (size_t)std::max<int64_t>(1, count);
+  job.alloc(st, c); est.alloc(st, c); segment_id.alloc(st, c); num_cpgs.alloc(st, c); category.alloc(st, c);
+  start.alloc(st, c); end.alloc(st, c); width.alloc(st, c); fused_std.alloc(st, c); beta.alloc(st, c); std_.alloc(st, c);
+}
+
+void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const void* d_pos, int pos_f64,
+                      const double* d_betahat, const double* d_pw, const PiecesDev& pieces, const PmdCallParams& p,
+                      PmdCallDev& out) {
+  cudaStream_t st = eng.stream;
+  out.alloc(st, 0);
+  const int32_t np = (int32_t)pieces.n;
+  const int ng = (int)groups.size();
+  if (np == 0 || ng == 0) return;
+  const RowsFromEstimates rows{d_betahat, d_pw};
+  DevBuf<SegGroup> d_groups(st, (size_t)ng);
+  d_groups.upload(groups);
+  DevBuf<int32_t> p_group(st, (size_t)np), p_ncpg(st, (size_t)np);
+  DevBuf<int64_t> p_lo(st, (size_t)np), p_hi(st, (size_t)np);
+  DevBuf<uint32_t> p_start(st, (size_t)np), p_end(st, (size_t)np);
+  DevBuf<double> p_beta(st, (size_t)np), p_cov(st, (size_t)np);
+  const PcPieces P{np, pieces.job.p, pieces.est.p, pieces.start.p, pieces.end.p, pieces.fused_std.p, p_group.p, p_ncpg.p,
+                   p_lo.p, p_hi.p, p_start.p, p_end.p, p_beta.p, p_cov.p};
+  ML_LAUNCH(eng, "k_pc_piece_stats", k_pc_piece_stats<RowsFromEstimates><<<np, PC_THREADS, 0, st>>>(d_groups.p, ng, d_pos, pos_f64, rows, P));
+  DevBuf<int32_t> flag(st, (size_t)np), live(st, (size_t)np), heads(st, (size_t)np);
+  ML_LAUNCH(eng, "k_pc_live", k_pc_live<<<cdiv(np, 256), 256, 0, st>>>(P, flag.p));
+  Scan scan;
+  const int32_t n_live = scan.run(eng, flag.p, np, nullptr, live.p);
+  if (n_live == 0) { stream_sync(st); return; }
+  DevBuf<int8_t> cat(st, (size_t)n_live);
+  ML_LAUNCH(eng, "k_pc_heads", k_pc_heads<<<cdiv(n_live, 256), 256, 0, st>>>(P, p, n_live, live.p, cat.p, flag.p));
+  const int32_t n_out = scan.run(eng, flag.p, n_live, nullptr, heads.p);
+  out.alloc(st, n_out);
+  const PcOut o{out.job.p, out.est.p, out.segment_id.p, out.num_cpgs.p, out.category.p, out.start.p, out.end.p,
+                out.width.p, out.fused_std.p, out.beta.p, out.std_.p};
+  ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<RowsFromEstimates><<<n_out, PC_THREADS, 0, st>>>(P, live.p, n_live, cat.p, heads.p, n_out, rows, o));
+  DevBuf<int32_t> gflag(st, (size_t)n_out), gpos(st, (size_t)n_out), gheads(st, (size_t)n_out);
+  ML_LAUNCH(eng, "k_pc_group_heads", k_pc_group_heads<<<cdiv(n_out, 256), 256, 0, st>>>(n_out, o, gflag.p));
+  scan.run(eng, gflag.p, n_out, gpos.p, gheads.p);
+  ML_LAUNCH(eng, "k_ps_seq_ids", k_ps_seq_ids<<<cdiv(n_out, 256), 256, 0, st>>>(n_out, gflag.p, gpos.p, gheads.p, out.segment_id.p));
+  stream_sync(st);
+}

@@ -115,6 +115,23 @@ void call_pmd_split_device(Engine& eng, const CallTable& t, const int8_t* d_cate
                            const int8_t* d_row_in_valley, const SegDeviceOut& pmd, double pmd_valley_min_width,
                            int split_pmds, MergedDev& M, PiecesDev& P);
 
+// R/call.R:169-199: the PMD calls.  One row per merged region of pmd_call after :198: category 1 "PMD" / 0 "other".
+struct PmdCallParams {    // arguments of segment_methylation_singlechr (R/call.R:31-35), its defaults
+  double pmd_std_threshold = 0.15, pmd_max_beta = 0.75, pmd_valley_min_width = 5000, max_distance = 500;
+  int32_t merge_pmds = 1, pad = 0;
+};
+struct PmdCallDev {
+  int64_t n = 0;
+  DevBuf<int32_t> job, est, segment_id, num_cpgs;
+  DevBuf<int8_t> category;
+  DevBuf<uint32_t> start, end;
+  DevBuf<double> width, fused_std, beta, std_;
+  void alloc(cudaStream_t st, int64_t count);
+};
+void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const void* d_pos, int pos_f64,
+                      const double* d_betahat, const double* d_pw, const PiecesDev& pieces, const PmdCallParams& p,
+                      PmdCallDev& out);
+
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,
                                   double max_distance, CallTable& out);

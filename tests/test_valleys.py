@@ -356,3 +356,77 @@ def test_gpu_pmd_split_matches_oracle(engine, oracle, reps):
         assert min(counts) > 50, counts
     finally:
         res.free()
+
+
+# ---- R/call.R:169-199: per-position gather along split_call, PMD calls, merge, statistics --------------------------------
+def test_pmd_calls_oracle_hand_example(oracle):
+    from oracle import pmd_calls as PC
+    # 60 positions 200 apart with noisy methylation (a PMD-like stretch), then 30 positions of high methylation
+    pos = np.concatenate([1000 + 200 * np.arange(60), 13000 + 200 * np.arange(30)]).astype(np.int32)
+    nm = np.concatenate([np.tile([2, 9, 5, 8], 15), np.full(30, 9)]).astype(np.int32)
+    pooled = dict(estimate_id=np.ones(90, np.int32), pos=pos, Nmeth=nm, coverage=np.full(90, 10, np.int32))
+    split = dict(estimate_id=np.array([1, 1, 1]), start=np.array([1000.0, 4001.0, 13001.0]), end=np.array([4000.0, 13000.0, 18800.0]),
+                 fused_std=np.array([0.3, 0.2, 0.01]))
+    r = PC.pmd_calls(pooled, split)
+    # piece 1: positions 1000..4000 (16), 3003 wide: not admissible.  Piece 2: 4000 (start - 1 <= pos: position 4000 counts
+    # twice) .. 13000 (46), 9003 wide, noisy: a PMD.  Piece 3: 13000 (again) .. 18800 (30), wide enough but not noisy
+    assert r["category"].tolist() == [0, 1, 0]
+    assert r["start"].tolist() == [1000.0, 4000.0, 13000.0] and r["end"].tolist() == [4002.0, 13002.0, 18802.0]
+    assert r["num_cpgs"].tolist() == [16, 46, 30] and r["width"].tolist() == [3003.0, 9003.0, 5803.0]
+    v2 = nm[15:61] / 10.0
+    assert r["beta"][1] == pytest.approx(v2.mean(), abs=1e-15) and r["std"][1] == pytest.approx(v2.std(ddof=1), abs=1e-15)
+    assert r["std"][2] == 0.0 and r["beta"][2] == 0.9
+    # a lower width threshold makes piece 1 admissible too: pieces 1 and 2 are both PMD and merge
+    r = PC.pmd_calls(pooled, split, pmd_valley_min_width=2500.0)
+    assert r["category"].tolist() == [1, 0] and r["start"].tolist() == [1000.0, 13000.0] and r["end"].tolist() == [13002.0, 18802.0]
+    assert r["num_cpgs"].tolist() == [62, 30] and r["fused_std"][0] == 0.25
+    v = np.concatenate([nm[:16], nm[15:61]]) / 10.0
+    assert r["beta"][0] == pytest.approx(v.mean(), abs=1e-15) and r["std"][0] == pytest.approx(v.std(ddof=1), abs=1e-15)
+    # merge.pmds = F keeps them apart
+    assert PC.pmd_calls(pooled, split, pmd_valley_min_width=2500.0, merge_pmds=False)["category"].tolist() == [1, 1, 0]
+    # a piece without positions has no row; the two "other" rows around it lie more than 5000 apart: not merged
+    split["start"][1], split["end"][1] = 4002.0, 4100.0
+    r = PC.pmd_calls(pooled, split)
+    assert r["start"].tolist() == [1000.0, 13000.0] and r["category"].tolist() == [0, 0]
+
+
+def close(a, b, tol):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return a.shape == b.shape and np.all(np.abs(a - b) <= tol * np.maximum(1.0, np.abs(b)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps", [(2,), (2, 2)])
+def test_gpu_pmd_calls_match_oracle(engine, oracle, reps):
+    from methylasso_b200._native import MlParams
+    from oracle import pmd_calls as PC
+    from test_calltable import pooled_from_table
+    tables = [synth.chromosome_table(n, 900 + i, reps) for i, n in enumerate((60_000, 9_000, 25_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        n_pmd = []
+        for kw in (dict(), dict(pmd_lambda2=100.0, pmd_valley_min_width=1500.0, pmd_std_threshold=0.1),
+                   dict(pmd_lambda2=100.0, pmd_valley_min_width=1500.0, pmd_std_threshold=0.1, merge_pmds=False, split_pmds=False)):
+            split_kw = {k: v for k, v in kw.items() if k in ("pmd_valley_min_width",)}
+            _, pieces = res.call_pmd_split(0.01, 500.0, kw.get("pmd_lambda2", 1000.0), kw.get("split_pmds", True), **split_kw)
+            got = res.call_pmds(0.01, 500.0, **kw)
+            okw = {k: v for k, v in kw.items() if k in ("pmd_valley_min_width", "pmd_std_threshold", "merge_pmds")}
+            total = 0
+            for j, t in enumerate(tables):
+                pj = pieces["job"] == j
+                want = PC.pmd_calls(pooled_from_table(t), {k: pieces[k][pj].astype(np.float64) for k in ("estimate_id", "start", "end", "fused_std")}, **okw)
+                g = got["job"] == j
+                assert g.sum() == want["start"].size, (j, int(g.sum()), want["start"].size)
+                for k in ("condition", "category", "start", "end", "width", "num_cpgs"):
+                    assert np.array_equal(got[k][g].astype(np.float64), want[k].astype(np.float64)), (j, k)
+                for k in ("fused_std", "beta", "std"):
+                    assert close(got[k][g], want[k], 1e-12), (j, k)
+                for c in np.unique(got["condition"][g]):       # regions numbered per condition
+                    m = g & (got["condition"] == c)
+                    assert np.array_equal(got["segment_id"][m], np.arange(1, m.sum() + 1))
+                total += int((want["category"] == 1).sum())
+            n_pmd.append(total)
+        assert n_pmd[1] > 3 and n_pmd[2] > 3, n_pmd
+    finally:
+        res.free()
