@@ -364,7 +364,7 @@ ML_API int ml_result_call_pmd_split(ml_engine *eng, ml_result *r, double tol_val
  * (:190-198; sd of a single value -> 0).  Rows = pmd_call after :198, ordered by (job, condition, start);
  * category 1 = "PMD", 0 = "other" (drop = T keeps the PMD rows, :217); segment_id numbers the regions per condition.
  * The means / sd use double-double sums where R accumulates in long double (equal to the last bit or so, as in the
- * call table).  The final annotation of seg_call with PMD.status (:201-215) still runs in R.
+ * call table).  The final annotation of seg_call with PMD.status (:201-215) is ml_result_call_pmd_status.
  * pmd == NULL: the reference's defaults.  Query with NULL outputs for *n_rows first; any output may be NULL. */
 typedef struct {
   double pmd_lambda2, pmd_std_threshold, pmd_max_beta;          /* 1000, 0.15, 0.75 */
@@ -375,6 +375,21 @@ ML_API int ml_result_call_pmds(ml_engine *eng, ml_result *r, double tol_val, dou
                                int64_t *n_rows, int32_t *job, int32_t *condition, int8_t *category,
                                int32_t *segment_id, uint32_t *start, uint32_t *end, double *width, int32_t *num_cpgs,
                                double *fused_std, double *beta, double *std);
+
+/* ---- PMD status of the segments (R/call.R:201-215) -----------------------------------------------------------------------
+ * Continues ml_result_call_pmds: seg_call (the merged table of ml_result_call_pmd_split) is joined with the PMD table
+ * (foverlaps, :203), exact duplicates are removed (:209: a segment that overlaps several regions keeps one row per
+ * distinct status, in order of first appearance), LMRs inside a PMD lose their category (:210) and every admissible
+ * UMR takes the status its two admissible neighbours of the condition share - "other" when they differ, NA when one
+ * is missing or NA (:211-212).  Rows = seg_call after :212, ordered by (job, condition, start): pmd_status 1 "PMD",
+ * 0 "other", -1 NA; category 0 NA, 1 "LMR", 2 "UMR", 3 "UMR-DMV"; merged_row = the row of ml_result_call_pmd_split's
+ * merged table, src_row / src_valley as there.  drop = T of the reference (:214-218) keeps the rows with category != 0
+ * and the PMD rows of ml_result_call_pmds.  Query with NULL outputs for *n_rows first; any output may be NULL. */
+ML_API int ml_result_call_pmd_status(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                     const ml_lmr_params *lmr, const ml_valley_params *valley, const ml_pmd_params *pmd,
+                                     int64_t *n_rows, int32_t *job, int32_t *condition, uint32_t *start, uint32_t *end,
+                                     int8_t *category, int8_t *pmd_status, int32_t *merged_row, int32_t *src_row,
+                                     int32_t *src_valley);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

@@ -115,6 +115,8 @@ SIGNATURES = {
                                            C.POINTER(MlValleyParams), C.c_int, _I64P] + [_P] * 9 + [_I64P] + [_P] * 7),
     "ml_result_call_pmds": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
                                       C.POINTER(MlPmdParams), _I64P] + [_P] * 11),
+    "ml_result_call_pmd_status": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
+                                            C.POINTER(MlPmdParams), _I64P] + [_P] * 9),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),

@@ -520,6 +520,28 @@ class Result:
         self.eng._check(self.eng.lib.ml_result_call_pmds(*args, C.byref(n), *[_p(out[k]) for k, _ in self.PMD_COLUMNS]))
         return {k: v[:n.value] for k, v in out.items()}
 
+    STATUS_COLUMNS = (("job", np.int32), ("condition", np.int32), ("start", np.uint32), ("end", np.uint32),
+                      ("category", np.int8), ("pmd_status", np.int8), ("merged_row", np.int32), ("src_row", np.int32),
+                      ("src_valley", np.int32))
+
+    def call_pmd_status(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, pmd_std_threshold=0.15,
+                        pmd_max_beta=0.75, split_pmds=True, merge_pmds=True, valley_max_beta=0.1,
+                        pmd_valley_min_width=5000.0, min_num_cpgs=4, **lmr_thresholds):
+        """R/call.R:201-215 on the resident tables: seg_call after :212 (see ml_result_call_pmd_status); the rows with
+        category != 0 are the reference's `lmr_umr_valley` table (drop = T)."""
+        from ._native import MlLmrParams, MlPmdParams, MlValleyParams
+        lp = MlLmrParams(max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs), **lmr_thresholds)
+        vp = MlValleyParams(valley_max_beta=float(valley_max_beta), pmd_valley_min_width=float(pmd_valley_min_width),
+                            max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs))
+        pp = MlPmdParams(pmd_lambda2=float(pmd_lambda2), pmd_std_threshold=float(pmd_std_threshold),
+                         pmd_max_beta=float(pmd_max_beta), split_pmds=1 if split_pmds else 0, merge_pmds=1 if merge_pmds else 0)
+        n = C.c_int64(0)
+        args = (self.eng.h, self.h, float(tol_val), float(max_distance), C.byref(lp), C.byref(vp), C.byref(pp))
+        self.eng._check(self.eng.lib.ml_result_call_pmd_status(*args, C.byref(n), *([None] * 9)))
+        out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.STATUS_COLUMNS}
+        self.eng._check(self.eng.lib.ml_result_call_pmd_status(*args, C.byref(n), *[_p(out[k]) for k, _ in self.STATUS_COLUMNS]))
+        return {k: v[:n.value] for k, v in out.items()}
+
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
         ns = C.c_int64(0)

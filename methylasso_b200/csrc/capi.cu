@@ -1129,6 +1129,46 @@ int ml_result_call_pmds(ml_engine* eng, ml_result* r, double tol_val, double max
   return ML_OK;
   ML_CATCH
 }
+
+int ml_result_call_pmd_status(ml_engine* eng, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* lmr,
+                              const ml_valley_params* valley, const ml_pmd_params* pmd, int64_t* n_rows, int32_t* job,
+                              int32_t* condition, uint32_t* start, uint32_t* end, int8_t* category, int8_t* pmd_status,
+                              int32_t* merged_row, int32_t* src_row, int32_t* src_valley) {
+  if (!eng || !r || !n_rows) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
+  if (pmd) pp = *pmd;
+  PmdSplitState S;
+  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, S);
+  if (rc) return rc;
+  Result& R = *r->r;
+  PmdCallParams cp;
+  cp.pmd_std_threshold = pp.pmd_std_threshold;
+  cp.pmd_max_beta = pp.pmd_max_beta;
+  cp.pmd_valley_min_width = S.vp.pmd_valley_min_width;
+  cp.max_distance = S.vp.max_distance;
+  cp.merge_pmds = pp.merge_pmds;
+  PmdCallDev calls;
+  call_pmds_device(eng->e, result_groups(R), R.start.p, 1, R.betahat.p, R.pw.p, S.P, cp, calls);
+  FinalDev F;
+  call_pmd_status_device(eng->e, S.M, calls, S.lu.is_admissible.p, F);
+  *n_rows = F.n;
+  const size_t n = (size_t)F.n;
+  if (n) {
+    if (job) F.job.download(job, n);
+    if (condition) F.est.download(condition, n);
+    if (start) F.start.download(start, n);
+    if (end) F.end.download(end, n);
+    if (category) F.category.download(category, n);
+    if (pmd_status) F.status.download(pmd_status, n);
+    if (merged_row) F.merged.download(merged_row, n);
+    if (src_row) F.src_row.download(src_row, n);
+    if (src_valley) F.src_valley.download(src_valley, n);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
 }  // extern "C"
 
 namespace ml {

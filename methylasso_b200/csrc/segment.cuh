@@ -4,6 +4,7 @@
 #include "common.h"
 #include "valley_core.cuh"
 #include "pmdsplit_core.cuh"
+#include "pmdstatus_core.cuh"
 
 namespace ml {
 
@@ -131,6 +132,17 @@ struct PmdCallDev {
 void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const void* d_pos, int pos_f64,
                       const double* d_betahat, const double* d_pw, const PiecesDev& pieces, const PmdCallParams& p,
                       PmdCallDev& out);
+
+// R/call.R:201-215: seg_call annotated with PMD.status.  One row per (merged row, distinct status): `merged` indexes
+// the MergedDev table; status 1 "PMD", 0 "other", -1 NA; category after :210; adm = is.admissible (-1 on a valley).
+struct FinalDev {
+  int64_t n = 0;
+  DevBuf<int32_t> merged, job, est, src_row, src_valley;
+  DevBuf<uint32_t> start, end;
+  DevBuf<int8_t> status, category, adm;
+  void alloc(cudaStream_t st, int64_t count);
+};
+void call_pmd_status_device(Engine& eng, MergedDev& M, const PmdCallDev& pmd, const int8_t* d_row_adm, FinalDev& out);
 
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,

@@ -5,6 +5,7 @@
 #include <vector>
 #include "../../methylasso_b200/csrc/valley_core.cuh"
 #include "../../methylasso_b200/csrc/pmdsplit_core.cuh"
+#include "../../methylasso_b200/csrc/pmdstatus_core.cuh"
 
 using namespace ml;
 
@@ -119,6 +120,29 @@ int64_t emu_pmd_split(int64_t n, const int32_t* job, const int32_t* est, const u
   }
   *n_pieces = off[n_x];
   return nm;
+}
+
+// R/call.R:201-215 with the functions of pmdstatus_core.cuh, in the order call_pmd_status_device launches them.
+// Outputs hold up to 2 * nm rows.  Returns the number of final rows.
+int64_t emu_pmd_status(int32_t nm, int32_t* m_job, int32_t* m_est, uint32_t* m_start, uint32_t* m_end, int8_t* m_cat,
+                       int32_t* m_src_row, const int8_t* row_adm, int32_t n_g, const int32_t* g_job, const int32_t* g_est,
+                       const uint32_t* g_start, const uint32_t* g_end, const int8_t* g_cat, int32_t* f_merged,
+                       int8_t* f_status, int8_t* f_category, int8_t* f_adm) {
+  if (nm == 0) return 0;
+  const MergedTable M{nm, m_job, m_est, m_src_row, nullptr, nullptr, m_start, m_end, m_cat, nullptr};
+  const PmdRegions G{n_g, g_job, g_est, g_start, g_end, g_cat};
+  std::vector<int32_t> extra((size_t)nm + 1, 0);
+  for (int32_t m = 0; m < nm; ++m) { int8_t a, b; extra[m + 1] = extra[m] + st_statuses(M, G, m, a, b) - 1; }
+  const int32_t nf = nm + extra[nm];
+  const FinalRows F{f_merged, f_status, f_category, f_adm};
+  for (int32_t m = 0; m < nm; ++m) st_emit(M, G, row_adm, m, m + extra[m], F);
+  std::vector<int32_t> flag(nf);
+  for (int32_t i = 0; i < nf; ++i) flag[i] = f_adm[i] == 1 ? 1 : 0;
+  const std::vector<int32_t> list = compact(flag);
+  std::vector<int8_t> ns(f_status, f_status + nf);
+  for (int32_t r = 0; r < (int32_t)list.size(); ++r) ns[list[r]] = st_umr_status(M, F, list.data(), (int32_t)list.size(), r);
+  for (int32_t i = 0; i < nf; ++i) f_status[i] = ns[i];
+  return nf;
 }
 
 // sum of doubles with x87.cuh's 64-bit-significand accumulator vs the host's long double (summary.c rsum)

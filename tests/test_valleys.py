@@ -430,3 +430,127 @@ def test_gpu_pmd_calls_match_oracle(engine, oracle, reps):
         assert n_pmd[1] > 3 and n_pmd[2] > 3, n_pmd
     finally:
         res.free()
+
+
+# ---- R/call.R:201-215: seg_call joined with the PMD table, PMD.status ------------------------------------------------------
+def test_pmd_status_oracle_hand_example(oracle):
+    from oracle import pmd_status as ST
+    # seven admissible segments of one condition + a valley (adm NA); PMD table: other | PMD | other
+    M = dict(condition=np.ones(8, np.int64), start=np.arange(8) * 1000.0 + 1000, end=np.arange(8) * 1000.0 + 1900,
+             category=np.array([0, 2, 0, 1, 2, 0, 3, 2]), src_row=np.array([0, 1, 2, 3, 4, 5, -1, 6]))
+    pmd = dict(condition=np.ones(3, np.int64), start=np.array([1000.0, 3500.0, 7000.0]), end=np.array([3400.0, 6950.0, 8900.0]),
+               category=np.array([0, 1, 0]))
+    r = ST.annotate(M, np.ones(7, np.int64), pmd)
+    # row 2 ([3000, 3900]) overlaps "other" and "PMD": two rows; the others one each
+    assert r["merged"].tolist() == [0, 1, 2, 2, 3, 4, 5, 6, 7]
+    # the LMR (row 3) lies in the PMD: category dropped; UMR row 1 sits between other / other: other; UMR row 4 between the
+    # ex-LMR (PMD) and row 5 (PMD): PMD; the valley is not admissible (NA): it is neither updated nor seen as a neighbour,
+    # so the last UMR (row 7) has no successor: NA
+    assert r["category"].tolist() == [0, 2, 0, 0, 0, 2, 0, 3, 2]
+    assert r["status"].tolist() == [0, 0, 0, 1, 1, 1, 1, 0, -1]
+    assert r["adm"].tolist() == [1, 1, 1, 1, 1, 1, 1, -1, 1]
+    # neighbours that differ: "other"
+    pmd2 = dict(condition=np.ones(2, np.int64), start=np.array([1000.0, 2950.0]), end=np.array([1900.0, 8900.0]), category=np.array([0, 1]))
+    r = ST.annotate(M, np.ones(7, np.int64), pmd2)
+    assert r["status"][1] == 0 and r["merged"].tolist() == list(range(8))       # row 1: no region -> NA, then other (0 vs 1)
+    # an inadmissible neighbour is skipped: row 1's neighbours become row 0 and row 3
+    adm = np.ones(7, np.int64); adm[2] = 0
+    r = ST.annotate(M, adm, pmd)
+    assert r["status"][1] == 0 and r["status"][5] == 1
+
+
+def test_emulated_pmd_status_matches_oracle(emu, oracle):
+    from oracle import pmd_status as ST
+    rng = np.random.default_rng(5)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    two = na = changed = 0
+    for trial in range(150):
+        # merged table: segments of 1-3 conditions of 2 jobs, widths / gaps small enough to touch now and then
+        rows = []
+        for j in range(2):
+            for c in range(1, int(rng.integers(2, 4))):
+                pos = 1000
+                for _ in range(int(rng.integers(1, 60))):
+                    w = int(rng.integers(1, 800))
+                    rows.append((j, c, pos, pos + w))
+                    pos += w + int(rng.integers(0, 3) if rng.random() < 0.5 else rng.integers(3, 3000))
+        nm = len(rows)
+        job, cond, start, end = (np.asarray([r[k] for r in rows]) for k in range(4))
+        cat = rng.choice([0, 1, 2, 3], nm, p=[0.45, 0.2, 0.25, 0.1]).astype(np.int8)
+        src_row = np.where(cat == 3, -1, np.cumsum(cat != 3) - 1).astype(np.int32)
+        row_adm = (rng.random(int((cat != 3).sum()) + 1) < 0.8).astype(np.int8)
+        # PMD table: consecutive regions per (job, condition) covering most of the range, some holes
+        g = []
+        for j in np.unique(job):
+            for c in np.unique(cond[job == j]):
+                m = (job == j) & (cond == c)
+                lo, hi = int(start[m].min()), int(end[m].max())
+                cuts = np.unique(np.concatenate([[lo], rng.integers(lo, hi + 1, int(rng.integers(0, 8))), [hi + 1]]))
+                for a, b in zip(cuts[:-1], cuts[1:]):
+                    if rng.random() < 0.85:
+                        g.append((j, c, a + int(rng.integers(0, 2)), b - 1 + int(rng.integers(0, 3)), int(rng.random() < 0.5)))
+        gj, gc, gs, ge, gcat = (np.asarray([r[k] for r in g] or [0]) [:len(g)] for k in range(5))
+        f = dict(merged=np.empty(2 * nm, np.int32), status=np.empty(2 * nm, np.int8), category=np.empty(2 * nm, np.int8),
+                 adm=np.empty(2 * nm, np.int8))
+        cols = [np.ascontiguousarray(a, dt) for a, dt in ((job, np.int32), (cond, np.int32), (start, np.uint32), (end, np.uint32),
+                                                          (cat, np.int8), (src_row, np.int32), (row_adm, np.int8))]
+        gcols = [np.ascontiguousarray(a, dt) for a, dt in ((gj, np.int32), (gc, np.int32), (gs, np.uint32), (ge, np.uint32), (gcat, np.int8))]
+        nf = emu.lib.emu_pmd_status(C.c_int32(nm), *[p(a) for a in cols], C.c_int32(len(g)), *[p(a) for a in gcols],
+                                    *[p(f[k]) for k in ("merged", "status", "category", "adm")])
+        at = 0
+        for j in np.unique(job):
+            m = job == j
+            base = int(np.nonzero(m)[0][0])
+            gm = gj == j if len(g) else np.zeros(0, bool)
+            want = ST.annotate(dict(condition=cond[m], start=start[m].astype(float), end=end[m].astype(float), category=cat[m],
+                                    src_row=src_row[m]), row_adm,
+                               dict(condition=gc[gm], start=gs[gm].astype(float), end=ge[gm].astype(float), category=gcat[gm]))
+            k = want["merged"].size
+            assert np.array_equal(f["merged"][at:at + k], want["merged"] + base), (trial, j)
+            for key in ("status", "category", "adm"):
+                assert np.array_equal(f[key][at:at + k], want[key]), (trial, j, key)
+            two += int(k - m.sum())
+            na += int((want["status"] < 0).sum())
+            at += k
+        assert at == nf
+    assert two > 50 and na > 50
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps", [(2,), (2, 2)])
+def test_gpu_pmd_status_matches_oracle(engine, oracle, reps):
+    from methylasso_b200._native import MlParams
+    from oracle import pmd_status as ST
+    tables = [synth.chromosome_table(n, 950 + i, reps) for i, n in enumerate((60_000, 9_000, 25_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    res = engine.detect_batch(ptr, cols, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        adm = res.call_lmr_umr(0.01, 500.0)["is_admissible"]
+        n_pmd_rows = []
+        for kw in (dict(), dict(pmd_lambda2=100.0, pmd_valley_min_width=1500.0, pmd_std_threshold=0.1)):
+            split_kw = {k: v for k, v in kw.items() if k == "pmd_valley_min_width"}
+            merged, _ = res.call_pmd_split(0.01, 500.0, kw.get("pmd_lambda2", 1000.0), True, **split_kw)
+            pmd = res.call_pmds(0.01, 500.0, **kw)
+            got = res.call_pmd_status(0.01, 500.0, **kw)
+            at = total = 0
+            for j in range(len(tables)):
+                m = merged["job"] == j
+                base = int(np.nonzero(m)[0][0])
+                g = pmd["job"] == j
+                M = {k: merged[k][m].astype(np.int64) for k in ("condition", "category", "src_row")}
+                M["start"], M["end"] = merged["start"][m].astype(float), merged["end"][m].astype(float)
+                want = ST.annotate(M, adm, dict(condition=pmd["condition"][g], start=pmd["start"][g].astype(float),
+                                                end=pmd["end"][g].astype(float), category=pmd["category"][g]))
+                k = want["merged"].size
+                assert np.array_equal(got["merged_row"][at:at + k], want["merged"] + base), j
+                assert np.array_equal(got["pmd_status"][at:at + k], want["status"]), j
+                assert np.array_equal(got["category"][at:at + k], want["category"]), j
+                for key in ("job", "condition", "start", "end", "src_row", "src_valley"):
+                    assert np.array_equal(got[key][at:at + k], merged[key][got["merged_row"][at:at + k]]), (j, key)
+                total += int((want["status"] == 1).sum())
+                at += k
+            assert at == got["job"].size
+            n_pmd_rows.append(total)
+        assert n_pmd_rows[1] > 20, n_pmd_rows
+    finally:
+        res.free()
