@@ -830,10 +830,72 @@ def _genome_wide(data, params, detection_type, model, engine=None, combine_diff=
     return ret
 
 
-def signal_detection_fast(data, lambda2=25, tol_val=0.01, max_iter=1, ncores=1, verbose=True, engine=None):
-    """R/genome_wide.R:64-78.  `ncores` is accepted and ignored: chromosomes are batched on the GPU."""
+def signal_detection_fast(data, lambda2=25, tol_val=0.01, max_iter=1, ncores=1, verbose=True, engine=None,
+                          keep_resident=False):
+    """R/genome_wide.R:64-78.  `ncores` is accepted and ignored: chromosomes are batched on the GPU.
+    keep_resident=True leaves the input and the fit in HBM (ret["_resident"]) for segment_methylation."""
     p = MlParams(lambda2, lambda2 + 1, 0.0, tol_val, 50.0, 1.0, max_iter, 1, 1, MODEL_FAST, 0, 0)
-    return _genome_wide(data, p, "signal", "normal", engine, verbose=verbose)
+    return _genome_wide(data, p, "signal", "normal", engine, verbose=verbose, keep_resident=keep_resident)
+
+
+def segment_methylation(data, ret, ncores=1, min_num_cpgs=4, pmd_lambda2=1000, pmd_std_threshold=0.15,
+                        umr_std_threshold=0.1, umr_max_beta=0.1, lmr_max_beta=0.5, pmd_max_beta=0.75, valley_max_beta=0.1,
+                        pmd_valley_min_width=5000, max_distance=500, min_width=30, flank_width=300, flank_dist_max=5000,
+                        flank_num_cpgs=10, flank_beta_min=0.5, umr_large_width=500, umr_large_density=0.03,
+                        split_pmds=True, merge_pmds=True, drop=True, tol_val=0.01):
+    """R/call.R:229-244 (segment_methylation) around :31-221 (segment_methylation_singlechr), for the result of
+    signal_detection_fast(..., keep_resident=True): the whole rule engine runs on the GPU on the resident fit, all
+    chromosomes at once.  Returns dict(lmr_umr_valley, pmd) of column dicts with the reference's column order
+    (:241-243; `num.cpgs` is `num_cpgs`, `PMD.status` is `PMD_status`: "PMD" / "other" / None); `ov`, the per-position
+    join, is not returned.  `data` is only consulted through the resident batch; `ncores` is ignored."""
+    if ret.get("detection.type") != "signal":
+        raise MethyLassoError(19, "segment_methylation on the GPU needs a signal fit (a difference fit is segmented on its "
+                                  "reference condition by the reference, R/call.R:40-44: not available natively)")
+    fit = ret.get("_resident")
+    if fit is None or fit.res is None:
+        raise MethyLassoError(19, "segment_methylation needs signal_detection_fast(..., keep_resident=True): the rule "
+                                  "engine works on the fit resident in HBM")
+    res = fit.res
+    lmr = dict(min_width=float(min_width), flank_width=float(flank_width), flank_dist_max=float(flank_dist_max),
+               lmr_max_beta=float(lmr_max_beta), flank_beta_min=float(flank_beta_min), umr_max_beta=float(umr_max_beta),
+               umr_std_threshold=float(umr_std_threshold), umr_large_width=float(umr_large_width),
+               umr_large_density=float(umr_large_density), flank_num_cpgs=int(flank_num_cpgs))
+    common = dict(valley_max_beta=valley_max_beta, pmd_valley_min_width=pmd_valley_min_width, min_num_cpgs=min_num_cpgs, **lmr)
+    pkw = dict(pmd_lambda2=pmd_lambda2, pmd_std_threshold=pmd_std_threshold, pmd_max_beta=pmd_max_beta,
+               split_pmds=split_pmds, merge_pmds=merge_pmds)
+    call = res.call_table(tol_val, max_distance)
+    val = res.call_valleys(tol_val, max_distance, **common)
+    merged, _ = res.call_pmd_split(tol_val, max_distance, pmd_lambda2, split_pmds, **common)
+    pmd = res.call_pmds(tol_val, max_distance, **pkw, **common)
+    fin = res.call_pmd_status(tol_val, max_distance, **pkw, **common)
+    names = np.asarray(fit.names)
+    src, sv = fin["src_row"], fin["src_valley"]
+    is_row = src >= 0
+
+    def col(ck, vk, dtype=np.float64):
+        out = np.full(src.size, np.nan) if dtype == np.float64 else np.zeros(src.size, dtype)
+        out[is_row] = call[ck][src[is_row]]
+        if vk is not None:
+            out[~is_row] = val[vk][sv[~is_row]]
+        return out
+    status_names = np.array([None, "other", "PMD"], dtype=object)
+    cat_names = np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)
+    seg = dict(condition=fin["condition"], chr=names[fin["job"]] if src.size else np.empty(0, dtype=object),
+               start=fin["start"], end=fin["end"], width=col("width", "width"),
+               segment_id=merged["segment_id"][fin["merged_row"]] if src.size else np.empty(0, np.int32),
+               beta=col("beta", "beta"), coverage=col("coverage", "coverage"), pseudoweight=col("pseudoweight", "pseudoweight"),
+               num_cpgs=col("num_cpgs", "num_cpgs", np.int64), std=col("std", None), category=cat_names[fin["category"]],
+               PMD_status=status_names[fin["pmd_status"] + 1])
+    pmd_t = dict(condition=pmd["condition"], chr=names[pmd["job"]] if pmd["job"].size else np.empty(0, dtype=object),
+                 start=pmd["start"], end=pmd["end"], width=pmd["width"], segment_id=pmd["segment_id"], beta=pmd["beta"],
+                 std=pmd["std"], category=np.where(pmd["category"] == 1, "PMD", "other").astype(object),
+                 num_cpgs=pmd["num_cpgs"], fused_std=pmd["fused_std"])
+    if drop:                                                   # R/call.R:214-218
+        keep = fin["category"] != 0
+        seg = {k: v[keep] for k, v in seg.items()}
+        pk = pmd["category"] == 1
+        pmd_t = {k: v[pk] for k, v in pmd_t.items()}
+    return dict(lmr_umr_valley=seg, pmd=pmd_t)
 
 
 def signal_detection(data, optimize_lambda2=False, lambda2=25, max_lambda2=1000, optimize_hyper=False,

@@ -554,3 +554,47 @@ def test_gpu_pmd_status_matches_oracle(engine, oracle, reps):
         assert n_pmd_rows[1] > 20, n_pmd_rows
     finally:
         res.free()
+
+
+# ---- the whole rule engine, from raw rows: api.segment_methylation against the chain of restatements ----------------------
+@pytest.mark.gpu
+def test_gpu_segment_methylation_end_to_end(engine, oracle):
+    from methylasso_b200 import api
+    from oracle import rule_engine as RE
+    from test_calltable import pooled_from_table
+    tables = [synth.chromosome_table(n, 970 + i, (2,)) for i, n in enumerate((50_000, 20_000))]
+    data = {k: np.concatenate([t[k] for t in tables]) for k in tables[0]}
+    data["chr"] = np.concatenate([np.full(t["pos"].size, f"chr{i + 1}", dtype=object) for i, t in enumerate(tables)])
+    for kw in (dict(), dict(pmd_lambda2=100, pmd_valley_min_width=1500, pmd_std_threshold=0.1)):
+        ret = api.signal_detection_fast(data, lambda2=25, engine=engine, keep_resident=True, verbose=False)
+        try:
+            got = api.segment_methylation(data, ret, **kw)
+        finally:
+            ret["_resident"].free()
+        n_rows = n_pmd = 0
+        for i, t in enumerate(tables):
+            o = oracle.detect(t, 0, lambda2=25.0)
+            want = RE.segment_methylation_singlechr(pooled_from_table(t), o["estimates"], **kw)
+            g = got["lmr_umr_valley"]
+            m = g["chr"] == f"chr{i + 1}"
+            w = want["lmr_umr_valley"]
+            assert m.sum() == w["start"].size, (i, int(m.sum()), w["start"].size)
+            for k in ("condition", "start", "end", "segment_id", "width", "coverage", "num_cpgs"):
+                assert np.array_equal(np.asarray(g[k][m], np.float64), np.asarray(w[k], np.float64)), (i, k)
+            assert np.array_equal(g["category"][m], np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)[w["category"]]), i
+            assert np.array_equal(g["PMD_status"][m], np.array([None, "other", "PMD"], dtype=object)[w["pmd_status"] + 1]), i
+            for k in ("beta", "pseudoweight", "std"):
+                a, b = np.asarray(g[k][m], float), np.asarray(w[k], float)
+                assert np.array_equal(np.isnan(a), np.isnan(b)) and close(a[~np.isnan(a)], b[~np.isnan(b)], 1e-12), (i, k)
+            p = got["pmd"]
+            pm = p["chr"] == f"chr{i + 1}"
+            wp = want["pmd"]
+            assert pm.sum() == wp["start"].size, (i, int(pm.sum()), wp["start"].size)
+            for k in ("condition", "start", "end", "width", "num_cpgs"):
+                assert np.array_equal(np.asarray(p[k][pm], np.float64), np.asarray(wp[k], np.float64)), (i, k)
+            for k in ("beta", "std", "fused_std"):
+                assert close(p[k][pm], wp[k], 1e-12), (i, k)
+            n_rows += int(m.sum())
+            n_pmd += int(pm.sum())
+        assert n_rows > 50
+    assert n_pmd > 0
