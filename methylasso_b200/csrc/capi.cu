@@ -1025,8 +1025,16 @@ struct PmdSplitState {
   PiecesDev P;
   ValleyParams vp;
 };
-int run_pmd_split(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
-                  const ml_lmr_params* lmr, const ml_valley_params* params, int split_pmds, PmdSplitState& S) {
+struct RuleState {
+  PmdSplitState S;
+  bool has_calls = false, has_final = false;
+  PmdCallParams cp;
+  PmdCallDev calls;
+  FinalDev F;
+};
+// the state for these arguments: the cached one when nothing it was built from has changed, else computed now
+int rule_state(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
+               const ml_lmr_params* lmr, const ml_valley_params* params, int split_pmds, RuleState** out) {
   int64_t ns = 0;   // call table + PMD candidate segments (std_call, R/call.R:93-95) resident
   const int rc = ml_result_call_pmd_segments(eng, r, tol_val, max_distance, pmd_lambda2, &ns, nullptr, nullptr, nullptr,
                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -1036,15 +1044,49 @@ int run_pmd_split(ml_engine* eng, ml_result* r, double tol_val, double max_dista
   tls_mailbox() = &eng->e.mailbox;
   LmrParams lp;
   if (lmr) memcpy(&lp, lmr, sizeof lp);
-  if (params) memcpy(&S.vp, params, sizeof S.vp);
-  else S.vp.max_distance = max_distance;
+  ValleyParams vp;
+  if (params) memcpy(&vp, params, sizeof vp);
+  else vp.max_distance = max_distance;
   Result& R = *r->r;
-  const CallTable& ct = *R.call_cache;
-  call_lmr_umr_device(eng->e, ct, lp, S.lu);
-  call_valleys_device(eng->e, ct, S.lu.category.p, S.vp, S.v, S.row_in, S.low_w, S.low_b);
-  call_pmd_split_device(eng->e, ct, S.lu.category.p, S.v, S.row_in.p, *R.call_pmd_cache, S.vp.pmd_valley_min_width, split_pmds,
-                        S.M, S.P);
+  const CallTable* ct = R.call_cache.get();
+  const SegDeviceOut* pc = R.call_pmd_cache.get();
+  struct Key { double tol, maxd, lam; LmrParams lp; ValleyParams vp; int split; const void *ct, *pc; } key;
+  memset(&key, 0, sizeof key);
+  key.tol = tol_val; key.maxd = max_distance; key.lam = pmd_lambda2; key.lp = lp; key.vp = vp; key.split = split_pmds;
+  key.ct = ct; key.pc = pc;
+  if (!R.rule_cache || R.rule_key.size() != sizeof key || memcmp(R.rule_key.data(), &key, sizeof key) != 0) {
+    R.rule_cache.reset();
+    auto st = std::make_shared<RuleState>();
+    PmdSplitState& S = st->S;
+    S.vp = vp;
+    call_lmr_umr_device(eng->e, *ct, lp, S.lu);
+    call_valleys_device(eng->e, *ct, S.lu.category.p, S.vp, S.v, S.row_in, S.low_w, S.low_b);
+    call_pmd_split_device(eng->e, *ct, S.lu.category.p, S.v, S.row_in.p, *pc, S.vp.pmd_valley_min_width, split_pmds, S.M, S.P);
+    R.rule_cache = st;
+    R.rule_key.assign((const char*)&key, (const char*)&key + sizeof key);
+  }
+  *out = static_cast<RuleState*>(R.rule_cache.get());
   return ML_OK;
+}
+// R/call.R:169-199 (and :201-215 when want_final) on the state, computed once per set of PMD parameters
+void rule_calls(ml_engine* eng, ml_result* r, RuleState& st, const ml_pmd_params& pp, bool want_final) {
+  Result& R = *r->r;
+  PmdCallParams cp;
+  cp.pmd_std_threshold = pp.pmd_std_threshold;
+  cp.pmd_max_beta = pp.pmd_max_beta;
+  cp.pmd_valley_min_width = st.S.vp.pmd_valley_min_width;
+  cp.max_distance = st.S.vp.max_distance;
+  cp.merge_pmds = pp.merge_pmds;
+  if (!st.has_calls || memcmp(&cp, &st.cp, sizeof cp) != 0) {
+    call_pmds_device(eng->e, result_groups(R), R.start.p, 1, R.betahat.p, R.pw.p, st.S.P, cp, st.calls);
+    st.cp = cp;
+    st.has_calls = true;
+    st.has_final = false;
+  }
+  if (want_final && !st.has_final) {
+    call_pmd_status_device(eng->e, st.S.M, st.calls, st.S.lu.is_admissible.p, st.F);
+    st.has_final = true;
+  }
 }
 }  // namespace
 
@@ -1057,11 +1099,11 @@ int ml_result_call_pmd_split(ml_engine* eng, ml_result* r, double tol_val, doubl
                              double* p_fused_std, double* p_pseudoweight) {
   if (!eng || !r || !n_merged || !n_pieces) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
-  PmdSplitState S;
-  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pmd_lambda2, lmr, params, split_pmds, S);
+  RuleState* st = nullptr;
+  const int rc = rule_state(eng, r, tol_val, max_distance, pmd_lambda2, lmr, params, split_pmds, &st);
   if (rc) return rc;
-  MergedDev& M = S.M;
-  PiecesDev& P = S.P;
+  MergedDev& M = st->S.M;
+  PiecesDev& P = st->S.P;
   *n_merged = M.n;
   *n_pieces = P.n;
   const size_t nm = (size_t)M.n, np = (size_t)P.n;
@@ -1098,18 +1140,11 @@ int ml_result_call_pmds(ml_engine* eng, ml_result* r, double tol_val, double max
   ML_TRY
   ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
   if (pmd) pp = *pmd;
-  PmdSplitState S;
-  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, S);
+  RuleState* st = nullptr;
+  const int rc = rule_state(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, &st);
   if (rc) return rc;
-  Result& R = *r->r;
-  PmdCallParams cp;
-  cp.pmd_std_threshold = pp.pmd_std_threshold;
-  cp.pmd_max_beta = pp.pmd_max_beta;
-  cp.pmd_valley_min_width = S.vp.pmd_valley_min_width;
-  cp.max_distance = S.vp.max_distance;
-  cp.merge_pmds = pp.merge_pmds;
-  PmdCallDev out;
-  call_pmds_device(eng->e, result_groups(R), R.start.p, 1, R.betahat.p, R.pw.p, S.P, cp, out);
+  rule_calls(eng, r, *st, pp, false);
+  PmdCallDev& out = st->calls;
   *n_rows = out.n;
   const size_t n = (size_t)out.n;
   if (n) {
@@ -1138,20 +1173,11 @@ int ml_result_call_pmd_status(ml_engine* eng, ml_result* r, double tol_val, doub
   ML_TRY
   ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
   if (pmd) pp = *pmd;
-  PmdSplitState S;
-  const int rc = run_pmd_split(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, S);
+  RuleState* st = nullptr;
+  const int rc = rule_state(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, &st);
   if (rc) return rc;
-  Result& R = *r->r;
-  PmdCallParams cp;
-  cp.pmd_std_threshold = pp.pmd_std_threshold;
-  cp.pmd_max_beta = pp.pmd_max_beta;
-  cp.pmd_valley_min_width = S.vp.pmd_valley_min_width;
-  cp.max_distance = S.vp.max_distance;
-  cp.merge_pmds = pp.merge_pmds;
-  PmdCallDev calls;
-  call_pmds_device(eng->e, result_groups(R), R.start.p, 1, R.betahat.p, R.pw.p, S.P, cp, calls);
-  FinalDev F;
-  call_pmd_status_device(eng->e, S.M, calls, S.lu.is_admissible.p, F);
+  rule_calls(eng, r, *st, pp, true);
+  FinalDev& F = st->F;
   *n_rows = F.n;
   const size_t n = (size_t)F.n;
   if (n) {

@@ -106,6 +106,11 @@ struct Result {
   // group_call of the last ml_result_call_differences call and the arguments it was computed with
   std::shared_ptr<struct DiffCallTable> diff_cache;
   double diff_key[5] = {0, 0, 0, 0, 0};
+  // tables of the rule engine (R/call.R:75-215) of the last ml_result_call_pmd_split / _pmds / _pmd_status call and the
+  // arguments they were computed with (query-then-fetch and the chain of the three entries without recomputing);
+  // the type lives in capi.cu
+  std::shared_ptr<void> rule_cache;
+  std::vector<char> rule_key;
 };
 
 // group_call of R/call.R:305-332 (call_differences_singlechr), device arrays; rows ordered by (job, estimate, segment)

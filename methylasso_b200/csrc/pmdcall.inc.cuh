@@ -48,6 +48,7 @@ struct PcPieces {         // per piece of split_call: inputs, then what :169-175
   int64_t *row_lo, *row_hi;
   uint32_t *pstart, *pend;         // min(pos), max(pos) + 2 (:171)
   double *beta, *cov;
+  DD* sum;                         // double-double sum of the piece's methylation values (first sweep)
 };
 
 // :169-175  one block per piece: positions with start - 1 <= pos <= end (foverlaps of [pos, pos + 1]), mean of
@@ -107,6 +108,7 @@ k_pc_piece_stats(const SegGroup* __restrict__ groups, int ng, const void* __rest
     P.pend[k] = m > 0 ? (uint32_t)last + 2u : 0u;
     P.beta[k] = mean;
     P.cov[k] = csum;
+    P.sum[k] = sum;
   }
 }
 __global__ void k_pc_live(PcPieces P, int32_t* __restrict__ flag) {
@@ -142,53 +144,64 @@ struct PcOut {
   uint32_t *start, *end;
   double *width, *fused_std, *beta, *std_;
 };
-// :193-198  one block per merged region: min start, max end, num.cpgs, mean(fused_std) over its rows (R's mean),
-// mean / sd of the methylation values of all its positions (rows matched by two touching pieces count twice, as the
-// concatenated betavals lists do)
+// :193-198  statistics of a merged region from per-piece partial sums, so that the work is spread over the pieces (a
+// genome's "other" regions span millions of positions; one block per region took 13 ms on a 28 M-CpG genome).
+// Region v = live pieces [heads[v], heads[v + 1]).  (a) one thread per region: mean0 = sum of the pieces' sums / count.
+struct PcRegion {
+  int32_t n;
+  const int32_t* heads;
+  double *mean0, *count;
+  DD *t, *q;                       // per live piece: sum(x - mean0), sum((x - mean0)^2) with its region's mean0
+};
+__global__ void k_pc_region_mean0(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, PcRegion R) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= R.n) return;
+  const int32_t r0 = R.heads[v], r1 = v + 1 < R.n ? R.heads[v + 1] : n_live;
+  DD s{0.0, 0.0};
+  double m = 0.0;
+  for (int32_t r = r0; r < r1; ++r) { s = dd_merge(s, P.sum[live[r]]); m += (double)P.ncpg[live[r]]; }
+  R.mean0[v] = (s.hi + s.lo) / m;
+  R.count[v] = m;
+}
+// (b) one block per live piece: the two central sums about its region's mean0; a position that two touching pieces
+// share enters both, as in the reference's concatenated betavals
 template <class Rows>
 __global__ void __launch_bounds__(PC_THREADS)
-k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const int8_t* __restrict__ cat,
-           const int32_t* __restrict__ heads, int32_t n_heads, Rows rows, PcOut o) {
+k_pc_piece_moments(PcPieces P, const int32_t* __restrict__ live, const int32_t* __restrict__ region_of, PcRegion R, Rows rows) {
   __shared__ DD smd[PC_THREADS / 32];
-  __shared__ double sms[PC_THREADS / 32];
-  const int v = blockIdx.x;
-  const int32_t r0 = heads[v], r1 = v + 1 < n_heads ? heads[v + 1] : n_live;
-  DD sum{0.0, 0.0};
-  double m = 0.0;
-  for (int32_t r = r0; r < r1; ++r) {
-    const int32_t k = live[r];
+  const int r = blockIdx.x;
+  const int32_t k = live[r];
+  const double mean0 = R.mean0[region_of[r]];
+  DD t{0.0, 0.0}, q{0.0, 0.0};
+  if (is_finite(mean0))
     for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
-      if (rows.valid(i)) { dd_add(sum, rows.x(i)); m += 1.0; }
-  }
-  sum = pc_block_sum(sum, smd);
-  m = pc_block_sum(m, sms);
-  double mean = (sum.hi + sum.lo) / m;
-  DD t{0.0, 0.0};
-  if (is_finite(mean))
-    for (int32_t r = r0; r < r1; ++r) {
-      const int32_t k = live[r];
-      for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
-        if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
-    }
+      if (rows.valid(i)) { const double d = rows.x(i) - mean0; dd_add(t, d); dd_add(q, d * d); }
   t = pc_block_sum(t, smd);
-  if (is_finite(mean)) mean += (t.hi + t.lo) / m;
-  DD ss{0.0, 0.0};
-  if (m >= 2)
-    for (int32_t r = r0; r < r1; ++r) {
-      const int32_t k = live[r];
-      for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
-        if (rows.valid(i)) { const double d = rows.x(i) - mean; dd_add(ss, d * d); }
-    }
-  ss = pc_block_sum(ss, smd);
-  if (threadIdx.x != 0) return;
+  q = pc_block_sum(q, smd);
+  if (threadIdx.x == 0) { R.t[r] = t; R.q[r] = q; }
+}
+// (c) one thread per region: mean = mean0 + T / M (R's second pass), sum of squares about it = Q - (T / M) T
+__global__ void k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const int8_t* __restrict__ cat,
+                           PcRegion R, PcOut o) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= R.n) return;
+  const int32_t r0 = R.heads[v], r1 = v + 1 < R.n ? R.heads[v + 1] : n_live;
+  DD T{0.0, 0.0}, Q{0.0, 0.0};
   uint32_t lo = P.pstart[live[r0]], hi = P.pend[live[r0]];
   int64_t ncpg = 0;
   for (int32_t r = r0; r < r1; ++r) {
     const int32_t k = live[r];
+    T = dd_merge(T, R.t[r]);
+    Q = dd_merge(Q, R.q[r]);
     lo = P.pstart[k] < lo ? P.pstart[k] : lo;
     hi = P.pend[k] > hi ? P.pend[k] : hi;
     ncpg += P.ncpg[k];
   }
+  const double m = R.count[v], mean0 = R.mean0[v];
+  const double delta = (T.hi + T.lo) / m;
+  const double mean = is_finite(mean0) ? mean0 + delta : mean0;
+  DD ss = Q;
+  dd_add(ss, -delta * (T.hi + T.lo));
   const int32_t k0 = live[r0];
   o.job[v] = P.job[k0];
   o.est[v] = P.est[k0];
@@ -199,7 +212,11 @@ k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const i
   o.fused_std[v] = x87_mean(r1 - r0, [&](int q) { return P.fused_std[live[r0 + q]]; });
   o.width[v] = (double)hi - (double)lo + 1;
   o.beta[v] = mean;
-  o.std_[v] = m >= 2 ? sqrt((ss.hi + ss.lo) / (m - 1)) : 0.0;      // sd of one value is NA -> 0 (:197)
+  o.std_[v] = m >= 2 ? sqrt(fmax(ss.hi + ss.lo, 0.0) / (m - 1)) : 0.0;      // sd of one value is NA -> 0 (:197)
+}
+__global__ void k_pc_region_of(int32_t n, const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, int32_t* __restrict__ region_of) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) region_of[r] = pos[r] + flag[r] - 1;
 }
 // segment_id of :186 / :189 is only a grouping key in the reference; the regions are numbered 1.. per condition here
 __global__ void k_pc_group_heads(int32_t n, PcOut o, int32_t* __restrict__ flag) {
@@ -231,8 +248,9 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
   DevBuf<int64_t> p_lo(st, (size_t)np), p_hi(st, (size_t)np);
   DevBuf<uint32_t> p_start(st, (size_t)np), p_end(st, (size_t)np);
   DevBuf<double> p_beta(st, (size_t)np), p_cov(st, (size_t)np);
+  DevBuf<DD> p_sum(st, (size_t)np);
   const PcPieces P{np, pieces.job.p, pieces.est.p, pieces.start.p, pieces.end.p, pieces.fused_std.p, p_group.p, p_ncpg.p,
-                   p_lo.p, p_hi.p, p_start.p, p_end.p, p_beta.p, p_cov.p};
+                   p_lo.p, p_hi.p, p_start.p, p_end.p, p_beta.p, p_cov.p, p_sum.p};
   ML_LAUNCH(eng, "k_pc_piece_stats", k_pc_piece_stats<RowsFromEstimates><<<np, PC_THREADS, 0, st>>>(d_groups.p, ng, d_pos, pos_f64, rows, P));
   DevBuf<int32_t> flag(st, (size_t)np), live(st, (size_t)np), heads(st, (size_t)np);
   ML_LAUNCH(eng, "k_pc_live", k_pc_live<<<cdiv(np, 256), 256, 0, st>>>(P, flag.p));
@@ -241,11 +259,19 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
   if (n_live == 0) { stream_sync(st); return; }
   DevBuf<int8_t> cat(st, (size_t)n_live);
   ML_LAUNCH(eng, "k_pc_heads", k_pc_heads<<<cdiv(n_live, 256), 256, 0, st>>>(P, p, n_live, live.p, cat.p, flag.p));
-  const int32_t n_out = scan.run(eng, flag.p, n_live, nullptr, heads.p);
+  DevBuf<int32_t> hpos(st, (size_t)n_live);
+  const int32_t n_out = scan.run(eng, flag.p, n_live, hpos.p, heads.p);
   out.alloc(st, n_out);
   const PcOut o{out.job.p, out.est.p, out.segment_id.p, out.num_cpgs.p, out.category.p, out.start.p, out.end.p,
                 out.width.p, out.fused_std.p, out.beta.p, out.std_.p};
-  ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<RowsFromEstimates><<<n_out, PC_THREADS, 0, st>>>(P, live.p, n_live, cat.p, heads.p, n_out, rows, o));
+  DevBuf<double> r_mean0(st, (size_t)n_out), r_count(st, (size_t)n_out);
+  DevBuf<DD> r_t(st, (size_t)n_live), r_q(st, (size_t)n_live);
+  DevBuf<int32_t> region_of(st, (size_t)n_live);
+  const PcRegion Rg{n_out, heads.p, r_mean0.p, r_count.p, r_t.p, r_q.p};
+  ML_LAUNCH(eng, "k_pc_region_mean0", k_pc_region_mean0<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, Rg));
+  ML_LAUNCH(eng, "k_pc_region_of", k_pc_region_of<<<cdiv(n_live, 256), 256, 0, st>>>(n_live, flag.p, hpos.p, region_of.p));
+  ML_LAUNCH(eng, "k_pc_piece_moments", k_pc_piece_moments<RowsFromEstimates><<<n_live, PC_THREADS, 0, st>>>(P, live.p, region_of.p, Rg, rows));
+  ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, cat.p, Rg, o));
   DevBuf<int32_t> gflag(st, (size_t)n_out), gpos(st, (size_t)n_out), gheads(st, (size_t)n_out);
   ML_LAUNCH(eng, "k_pc_group_heads", k_pc_group_heads<<<cdiv(n_out, 256), 256, 0, st>>>(n_out, o, gflag.p));
   scan.run(eng, gflag.p, n_out, gpos.p, gheads.p);
