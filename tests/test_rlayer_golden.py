@@ -125,3 +125,42 @@ def test_gpu_reproduces_valley_fixtures(engine):
             assert close(got["low_id_beta"], v[f"{name}_low_id_beta"], 1e-13), name
     finally:
         res.free()
+
+
+RE_CASES = (("default", {}), ("narrow", dict(pmd_lambda2=100.0, pmd_valley_min_width=1200.0, pmd_std_threshold=0.1)))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_rule_engine_fixtures(engine):
+    """The tables of the whole rule engine (R/call.R:31-221, drop = F) in valley_fixtures.npz against the resident path."""
+    from methylasso_b200._native import MlParams
+    g, v = np.load(GOLD), np.load(VGOLD)
+    t = {k: g["lu_in_" + k] for k in COLS}
+    res = engine.detect_batch(np.array([0, t["pos"].size], np.int64), t, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        call = res.call_table(0.01, 500.0)
+        for name, kw in RE_CASES:
+            vkw = {k: x for k, x in kw.items() if k == "pmd_valley_min_width"}
+            val = res.call_valleys(0.01, 500.0, **vkw)
+            merged, _ = res.call_pmd_split(0.01, 500.0, kw.get("pmd_lambda2", 1000.0), True, **vkw)
+            pmd = res.call_pmds(0.01, 500.0, **kw)
+            fin = res.call_pmd_status(0.01, 500.0, **kw)
+            w = {k[len(f"re_{name}_lmr_umr_valley_"):]: v[k] for k in v.files if k.startswith(f"re_{name}_lmr_umr_valley_")}
+            assert fin["start"].size == w["start"].size
+            for k, gk in (("condition", "condition"), ("start", "start"), ("end", "end"), ("category", "category"), ("pmd_status", "pmd_status")):
+                assert np.array_equal(np.asarray(fin[gk], np.float64), np.asarray(w[k], np.float64)), (name, k)
+            assert np.array_equal(merged["segment_id"][fin["merged_row"]], w["segment_id"]), name
+            is_row = fin["src_row"] >= 0
+            for k in ("width", "beta", "coverage", "pseudoweight", "num_cpgs"):
+                got = np.where(is_row, call[k][np.maximum(fin["src_row"], 0)],
+                               val[k][np.maximum(fin["src_valley"], 0)] if val[k].size else np.nan)
+                assert close(got, w[k], 1e-12), (name, k)
+            wp = {k[len(f"re_{name}_pmd_"):]: v[k] for k in v.files if k.startswith(f"re_{name}_pmd_")}
+            assert pmd["start"].size == wp["start"].size
+            for k in ("condition", "category", "start", "end", "width", "num_cpgs"):
+                assert np.array_equal(np.asarray(pmd[k], np.float64), np.asarray(wp[k], np.float64)), (name, k)
+            for k in ("fused_std", "beta", "std"):
+                assert close(pmd[k], wp[k], 1e-12), (name, k)
+            assert (wp["category"] == 1).sum() >= 5 and (w["category"] > 0).sum() >= 50
+    finally:
+        res.free()
