@@ -31,3 +31,33 @@ dmr_calling_gpu = function(data, ref, lambda2 = 25, min.diff = 0.1, pval.cutoff 
   diff_call[(!is.na(diff)) & abs(diff) >= min.diff & coverage.score >= cov.score & pval <= pval.cutoff &
             fdr <= fdr.cutoff & pmin(num.cpgs, num.cpgs.ref) >= min.num.cpgs]
 }
+
+# Replacement for Part 1 of the CLI (signal_detection_fast followed by segment_methylation, R/call.R:229-244 around
+# :31-221): the fit and the whole rule engine run on the GPU for all chromosomes at once; only the two result tables come
+# back (`ov`, the per-position join, is not produced).  Arguments and defaults are those of segment_methylation_singlechr.
+segment_methylation_gpu = function(data, lambda2 = 25, pmd_lambda2 = 1000, pmd_std_threshold = 0.15, umr_std_threshold = 0.1,
+                                   umr_max_beta = 0.1, lmr_max_beta = 0.5, pmd_max_beta = 0.75, valley_max_beta = 0.1,
+                                   pmd_valley_min_width = 5000, max_distance = 500, min_num_cpgs = 4, min_width = 30,
+                                   flank.width = 300, flank.dist.max = 5000, flank.num.cpgs = 10, flank.beta.min = 0.5,
+                                   umr_large_width = 500, umr_large_density = 0.03, split.pmds = T, merge.pmds = T, drop = T,
+                                   tol_val = 0.01) {
+  setkey(data, chr, dataset, pos)
+  chrs = data[, unique(chr)]
+  job_ptr = c(0, data[, .N, keyby = chr][, cumsum(N)])
+  lmr = c(min_width, max_distance, flank.width, flank.dist.max, lmr_max_beta, flank.beta.min, umr_max_beta, umr_std_threshold,
+          umr_large_width, umr_large_density, min_num_cpgs, flank.num.cpgs)
+  valley = c(valley_max_beta, pmd_valley_min_width, max_distance, min_num_cpgs)
+  pmd = c(pmd_lambda2, pmd_std_threshold, pmd_max_beta, as.integer(split.pmds), as.integer(merge.pmds))
+  segments = MethyLasso:::segment_methylation_batch(data, job_ptr, lambda2, tol_val, max_distance, lmr, valley, pmd)
+  segments = lapply(segments, function(x) { x = as.data.table(x); x[, chr := chrs[job]]; x[, job := NULL]
+                                            x[, condition := levels(data$condition)[condition]]; x })
+  if (drop == T) {                                                          # R/call.R:214-218
+    segments$lmr_umr_valley = segments$lmr_umr_valley[!is.na(category)]
+    segments$pmd = segments$pmd[category == "PMD"]
+    segments$pmd[, fused_std := NULL]
+  }
+  setcolorder(segments$lmr_umr_valley, c("condition", "chr", "start", "end", "width", "segment_id", "beta", "coverage",
+                                         "pseudoweight", "num.cpgs", "std", "category", "PMD.status"))
+  setcolorder(segments$pmd, c("condition", "chr", "start", "end", "width", "segment_id", "beta", "std", "category"))
+  segments
+}

@@ -196,6 +196,101 @@ DataFrame call_differences_batch(const DataFrame& data, const NumericVector& job
                            _["coverage.score"] = score);
 }
 
+// NEW: Part 1 of the CLI in one native call: signal_detection_fast of every chromosome (R/genome_wide.R:64-78) and the
+// rule engine of segment_methylation_singlechr (R/call.R:31-221) on the resident fit - call table, LMR / UMR annotation,
+// std fusion, valleys, PMD split / calls and the segments' PMD status.  Returns list(lmr_umr_valley, pmd) with drop = F
+// semantics (all rows; category / PMD.status are NA where the reference has NA); segment_methylation_gpu in
+// r/R/genome_wide_gpu.R applies the drop of :214-218 and names the columns.  `lmr` / `valley` / `pmd` are numeric vectors
+// in the field order of ml_lmr_params / ml_valley_params / ml_pmd_params (include/methylasso_b200.h).
+List segment_methylation_batch(const DataFrame& data, const NumericVector& job_ptr, double lambda2, double tol_val,
+                               double max_distance, const NumericVector& lmr, const NumericVector& valley,
+                               const NumericVector& pmd) {
+  need_columns(data);
+  if (lmr.size() != 12 || valley.size() != 4 || pmd.size() != 5) stop("lmr / valley / pmd must hold 12 / 4 / 5 values");
+  IntegerVector dset = data["dataset"], cond = data["condition"], rep = data["replicate"], pos = data["pos"],
+                nmeth = data["Nmeth"], cov = data["coverage"];
+  std::vector<int64_t> ptr(job_ptr.begin(), job_ptr.end());
+  const int nj = (int)ptr.size() - 1;
+  const ml_lmr_params lp{lmr[0], lmr[1], lmr[2], lmr[3], lmr[4], lmr[5], lmr[6], lmr[7], lmr[8], lmr[9], (int32_t)lmr[10],
+                         (int32_t)lmr[11]};
+  const ml_valley_params vp{valley[0], valley[1], valley[2], (int32_t)valley[3], 0};
+  const ml_pmd_params pp{pmd[0], pmd[1], pmd[2], (int32_t)pmd[3], (int32_t)pmd[4]};
+  ml_batch* batch = nullptr;
+  ml_result* res = nullptr;
+  std::vector<int> status(nj);
+  check(ml_batch_upload(engine(), nj, ptr.data(), dset.begin(), cond.begin(), rep.begin(), pos.begin(), nmeth.begin(),
+                        cov.begin(), &batch, nullptr));
+  const ml_params p = fast_params(lambda2, tol_val, 1);
+  int rc = ml_batch_detect(engine(), batch, &p, &res, status.data());
+  auto bail = [&](int code) { if (code != ML_OK) { ml_result_free(res); ml_batch_free(batch); stop(ml_last_error()); } };
+  bail(rc);
+  int64_t nc = 0, nv = 0, nr = 0, nm = 0, npc = 0, np = 0, nf = 0;
+  // call table (:43-72), valleys (:100-133), merged table (:131-140), PMD table (:169-199), final rows (:201-215)
+  bail(ml_result_call_table(engine(), res, tol_val, max_distance, &nc, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+  NumericVector c_width(nc), c_beta(nc), c_cov(nc), c_pw(nc), c_std(nc);
+  IntegerVector c_ncpg(nc);
+  bail(ml_result_call_table(engine(), res, tol_val, max_distance, &nc, 0, 0, 0, 0, 0, c_width.begin(), c_beta.begin(),
+                            c_cov.begin(), c_pw.begin(), c_ncpg.begin(), c_std.begin()));
+  bail(ml_result_call_valleys(engine(), res, tol_val, max_distance, &lp, &vp, &nv, 0, 0, 0, 0, 0, 0, 0, 0, 0, &nr, 0, 0, 0));
+  NumericVector v_width(nv), v_beta(nv), v_cov(nv), v_pw(nv);
+  IntegerVector v_ncpg(nv);
+  bail(ml_result_call_valleys(engine(), res, tol_val, max_distance, &lp, &vp, &nv, 0, 0, 0, 0, v_width.begin(), v_beta.begin(),
+                              v_cov.begin(), v_pw.begin(), v_ncpg.begin(), &nr, 0, 0, 0));
+  bail(ml_result_call_pmd_split(engine(), res, tol_val, max_distance, pp.pmd_lambda2, &lp, &vp, pp.split_pmds, &nm, 0, 0, 0, 0, 0,
+                                0, 0, 0, 0, &npc, 0, 0, 0, 0, 0, 0, 0));
+  IntegerVector m_seg(nm);
+  bail(ml_result_call_pmd_split(engine(), res, tol_val, max_distance, pp.pmd_lambda2, &lp, &vp, pp.split_pmds, &nm, 0, 0,
+                                m_seg.begin(), 0, 0, 0, 0, 0, 0, &npc, 0, 0, 0, 0, 0, 0, 0));
+  bail(ml_result_call_pmds(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &np, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+  IntegerVector p_job(np), p_cond(np), p_seg(np), p_ncpg(np);
+  std::vector<int8_t> p_cat(np);
+  std::vector<uint32_t> p_start(np), p_end(np);
+  NumericVector p_width(np), p_fused(np), p_beta(np), p_std(np);
+  bail(ml_result_call_pmds(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &np, p_job.begin(), p_cond.begin(), p_cat.data(),
+                           p_seg.begin(), p_start.data(), p_end.data(), p_width.begin(), p_ncpg.begin(), p_fused.begin(),
+                           p_beta.begin(), p_std.begin()));
+  bail(ml_result_call_pmd_status(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &nf, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+  IntegerVector f_job(nf), f_cond(nf), f_merged(nf), f_row(nf), f_val(nf);
+  std::vector<int8_t> f_cat(nf), f_status(nf);
+  std::vector<uint32_t> f_start(nf), f_end(nf);
+  rc = ml_result_call_pmd_status(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &nf, f_job.begin(), f_cond.begin(),
+                                 f_start.data(), f_end.data(), f_cat.data(), f_status.data(), f_merged.begin(), f_row.begin(),
+                                 f_val.begin());
+  ml_result_free(res);
+  ml_batch_free(batch);
+  check(rc);
+  // the value columns of a final row come from its call-table row or from its valley (std is NA on a valley)
+  NumericVector start(nf), end(nf), width(nf), beta(nf), coverage(nf), pw(nf), sd(nf);
+  IntegerVector segment_id(nf), ncpg(nf);
+  CharacterVector category(nf), pmd_status(nf);
+  static const char* cat_names[] = {nullptr, "LMR", "UMR", "UMR-DMV"};
+  for (int64_t i = 0; i < nf; ++i) {
+    const int r = f_row[i], v = f_val[i];
+    start[i] = f_start[i]; end[i] = f_end[i]; segment_id[i] = m_seg[f_merged[i]];
+    width[i] = r >= 0 ? c_width[r] : v_width[v];
+    beta[i] = r >= 0 ? c_beta[r] : v_beta[v];
+    coverage[i] = r >= 0 ? c_cov[r] : v_cov[v];
+    pw[i] = r >= 0 ? c_pw[r] : v_pw[v];
+    ncpg[i] = r >= 0 ? c_ncpg[r] : v_ncpg[v];
+    sd[i] = r >= 0 ? c_std[r] : NA_REAL;
+    if (f_cat[i] == 0) category[i] = NA_STRING; else category[i] = cat_names[f_cat[i]];
+    if (f_status[i] < 0) pmd_status[i] = NA_STRING; else pmd_status[i] = f_status[i] == 1 ? "PMD" : "other";
+  }
+  NumericVector ps(p_start.begin(), p_start.end()), pe(p_end.begin(), p_end.end());
+  CharacterVector pc(np);
+  for (int64_t i = 0; i < np; ++i) pc[i] = p_cat[i] == 1 ? "PMD" : "other";
+  return List::create(
+      _["lmr_umr_valley"] = DataFrame::create(_["job"] = f_job + 1, _["condition"] = f_cond, _["start"] = start, _["end"] = end,
+                                              _["width"] = width, _["segment_id"] = segment_id, _["beta"] = beta,
+                                              _["coverage"] = coverage, _["pseudoweight"] = pw, _["num.cpgs"] = ncpg,
+                                              _["std"] = sd, _["category"] = category, _["PMD.status"] = pmd_status,
+                                              _["stringsAsFactors"] = false),
+      _["pmd"] = DataFrame::create(_["job"] = p_job + 1, _["condition"] = p_cond, _["start"] = ps, _["end"] = pe,
+                                   _["width"] = p_width, _["segment_id"] = p_seg, _["beta"] = p_beta, _["std"] = p_std,
+                                   _["category"] = pc, _["num.cpgs"] = p_ncpg, _["fused_std"] = p_fused,
+                                   _["stringsAsFactors"] = false));
+}
+
 // NEW: wilcox.test(x_g, y_g, conf.int = F)$p.value for many groups (CSR offsets) and p.adjust(p, 'fdr')
 NumericVector wilcoxon_groups(const NumericVector& x_ptr, const NumericVector& x, const NumericVector& y_ptr,
                               const NumericVector& y) {
@@ -225,6 +320,7 @@ RCPP_MODULE(MethyLasso_cpp) {
   function("weighted_1d_flsa", &weighted_1d_flsa, List::create(_["y"], _["wt"], _["lambda2"], _["lambda1"] = 0));
   function("signal_detection_fast_batch", &signal_detection_fast_batch);
   function("call_differences_batch", &call_differences_batch);
+  function("segment_methylation_batch", &segment_methylation_batch);
   function("wilcoxon_groups", &wilcoxon_groups);
   function("p_adjust_fdr", &p_adjust_fdr);
 }
