@@ -37,3 +37,13 @@ def test_split_jobs_partitions_and_balances():
     for jobs, gptr, gcols in groups:
         for i, j in enumerate(jobs):
             assert np.array_equal(gcols["pos"][gptr[i]:gptr[i + 1]], tables[j]["pos"])
+
+
+def test_segment_methylation_refuses_what_it_cannot_do():
+    """R/call.R:229-244 mirror: needs a signal fit kept resident (no GPU needed to be told so)."""
+    import pytest
+    from methylasso_b200 import api
+    with pytest.raises(api.MethyLassoError, match="signal fit"):
+        api.segment_methylation({}, {"detection.type": "difference"})
+    with pytest.raises(api.MethyLassoError, match="keep_resident"):
+        api.segment_methylation({}, {"detection.type": "signal"})
