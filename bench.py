@@ -938,6 +938,32 @@ def main():
                        "peak_source": pk_kind, "alg_bytes_per_launch": top_bw["alg_bytes_per_launch"],
                        "avg_launch_ms": top_bw["avg_launch_ms"]}
 
+    # ---- auxiliary, untimed part of no metric: the rule engine of segment_methylation_singlechr (R/call.R:75-215) on the
+    # resident fit of this workload - LMR / UMR annotation, valleys, PMD split / calls, PMD status.  Every repetition uses
+    # a new key (flank_dist_max 5000 / 5000.5: distances are integers, same results) so that nothing is reused.
+    rule_engine = None
+    if rank == 0:
+        try:
+            res_r, _, _ = step_resident()
+            eng.synchronize()
+            walls, fin, pmd = [], None, None
+            for rep in range(4):
+                t0 = time.perf_counter()
+                kw = dict(flank_dist_max=5000.0 + 0.5 * (rep & 1))
+                pmd = res_r.call_pmds(TOL, MAX_DISTANCE, PMD_LAMBDA2, **kw)
+                fin = res_r.call_pmd_status(TOL, MAX_DISTANCE, PMD_LAMBDA2, **kw)
+                eng.synchronize()
+                walls.append((time.perf_counter() - t0) * 1e3)
+            res_r.free()
+            rule_engine = {"host_wall_ms": float(np.median(walls[1:])), "host_wall_ms_each": [round(w, 2) for w in walls],
+                           "rows": int(fin["category"].size), "lmr": int((fin["category"] == 1).sum()),
+                           "umr": int((fin["category"] == 2).sum()), "valleys": int((fin["category"] == 3).sum()),
+                           "pmds": int((pmd["category"] == 1).sum()),
+                           "what": "R/call.R:75-215 on the resident call table, result tables downloaded; not part of the "
+                                   "timed step (the reference arm does not run it)"}
+        except Exception as exc:                                   # never let the auxiliary line break the bench
+            rule_engine = {"error": repr(exc)}
+
     # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -962,6 +988,7 @@ def main():
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
             "host_wall_ms_each_step": step_wall_res, "disturbed_attempts": disturbed, "cpu_binding": numa,
             "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
+            "rule_engine": rule_engine,
         }
         print(json.dumps(line), flush=True)
         if args.out:
