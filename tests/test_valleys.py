@@ -598,3 +598,37 @@ def test_gpu_segment_methylation_end_to_end(engine, oracle):
             n_pmd += int(pm.sum())
         assert n_rows > 50
     assert n_pmd > 0
+
+
+@pytest.mark.gpu
+def test_gpu_config1_rule_engine(engine, oracle):
+    """configs[0] of BASELINE.json end to end: one chr22-sized sample (0.4 M CpGs, one condition), lambda2 = 25, the fit and
+    the whole rule engine against the chain of restatements (all rows, drop = F)."""
+    from methylasso_b200 import api
+    from oracle import rule_engine as RE
+    from test_calltable import pooled_from_table
+    t = synth.chromosome_table(400_000, 20241, (1,))
+    data = dict(t, chr=np.full(t["pos"].size, "chr22", dtype=object))
+    ret = api.signal_detection_fast(data, lambda2=25, engine=engine, keep_resident=True, verbose=False)
+    try:
+        got = api.segment_methylation(data, ret, drop=False)
+    finally:
+        ret["_resident"].free()
+    o = oracle.detect(t, 0, lambda2=25.0)
+    want = RE.segment_methylation_singlechr(pooled_from_table(t), o["estimates"])["all"]
+    g, w = got["lmr_umr_valley"], want["lmr_umr_valley"]
+    assert g["start"].size == w["start"].size
+    for k in ("condition", "start", "end", "segment_id", "width", "coverage", "num_cpgs"):
+        assert np.array_equal(np.asarray(g[k], np.float64), np.asarray(w[k], np.float64)), k
+    assert np.array_equal(g["category"], np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)[w["category"]])
+    assert np.array_equal(g["PMD_status"], np.array([None, "other", "PMD"], dtype=object)[w["pmd_status"] + 1])
+    for k in ("beta", "pseudoweight", "std"):
+        assert close(np.nan_to_num(np.asarray(g[k], float), nan=-1.0), np.nan_to_num(np.asarray(w[k], float), nan=-1.0), 1e-12), k
+    p, wp = got["pmd"], want["pmd"]
+    assert p["start"].size == wp["start"].size
+    for k in ("condition", "start", "end", "width", "num_cpgs"):
+        assert np.array_equal(np.asarray(p[k], np.float64), np.asarray(wp[k], np.float64)), k
+    assert np.array_equal(p["category"] == "PMD", wp["category"] == 1)
+    for k in ("beta", "std", "fused_std"):
+        assert close(p[k], wp[k], 1e-12), k
+    assert (w["category"] == 1).sum() > 50 and (w["category"] == 2).sum() > 200 and (wp["category"] == 1).sum() > 5
