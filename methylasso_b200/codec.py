@@ -15,6 +15,22 @@ import numpy as np
 from . import api
 
 
+def load_text(path: str) -> bytes:
+    """The bytes of a replicate file; a gzip file (magic 1f 8b, whatever its name) is inflated on the host, as fread does
+    through R.utils (MethyLasso.R:246-262 reads `.gz` files the same way) - the parser itself takes plain text."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    if raw[:2] == b"\x1f\x8b":
+        import gzip
+        return gzip.decompress(raw)
+    return raw
+
+
+def read_replicate_file(engine, path: str, **kw):
+    """read_replicate on a file path (plain or gzip)."""
+    return read_replicate(engine, load_text(path), **kw)
+
+
 def _is_number(tok: bytes) -> bool:
     try:
         float(tok)

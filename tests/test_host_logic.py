@@ -47,3 +47,13 @@ def test_segment_methylation_refuses_what_it_cannot_do():
         api.segment_methylation({}, {"detection.type": "difference"})
     with pytest.raises(api.MethyLassoError, match="keep_resident"):
         api.segment_methylation({}, {"detection.type": "signal"})
+
+
+def test_codec_load_text_inflates_gzip(tmp_path):
+    import gzip
+    from methylasso_b200 import codec
+    text = b"chr1\t100\t100\t50\t5\t5\nchr1\t102\t102\t25\t2\t6\n"
+    plain, packed = tmp_path / "a.cov", tmp_path / "a.cov.gz"
+    plain.write_bytes(text)
+    packed.write_bytes(gzip.compress(text))
+    assert codec.load_text(str(plain)) == text and codec.load_text(str(packed)) == text
