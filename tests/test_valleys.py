@@ -294,43 +294,48 @@ def check_split_against_oracle(merged, pieces, t, category, val, std_call, split
     return n_pieces
 
 
+def split_trial(emu, rng, t, trial):
+    """One emulated run of R/call.R:131-168 on table t against the restatement; returns (pieces, valley rows)."""
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    n = t["start"].size
+    category = np.zeros(n, np.int8)
+    category[(t["beta"] < 0.1) & (rng.random(n) < 0.4)] = 2
+    category[(t["beta"] >= 0.1) & (rng.random(n) < 0.1)] = 1
+    kw = [{}, dict(pmd_valley_min_width=2500.0), dict(valley_max_beta=0.05, pmd_valley_min_width=1500.0)][trial % 3]
+    pvw = kw.get("pmd_valley_min_width", 5000.0)
+    val = emu(t, category, **kw)
+    x = random_std_call(rng, t)
+    cols = [np.ascontiguousarray(t[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32), ("end", np.uint32))]
+    cols += [np.ascontiguousarray(category, np.int8), np.ascontiguousarray(val["row_in_valley"], np.int8)]
+    nv = val["start"].size
+    vcols = [np.ascontiguousarray(val[k], dt) for k, dt in (("job", np.int32), ("condition", np.int32), ("start", np.uint32),
+                                                             ("end", np.uint32), ("row0", np.int32))]
+    nx = x["start"].size
+    xcols = [np.ascontiguousarray(x[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32),
+                                                           ("end", np.uint32), ("fused_std", np.float64), ("pseudoweight", np.float64))]
+    split_pmds = trial % 4 != 1
+    merged = {k: np.empty(n + nv + 1, dt) for k, dt in MCOLS}
+    cap = nx + 2 * (n + nv) + 8
+    pieces = {k: np.empty(cap, dt) for k, dt in PCOLS}
+    npc = C.c_int64(0)
+    nm = emu.lib.emu_pmd_split(C.c_int64(n), *[p(a) for a in cols], C.c_int32(nv), *[p(a) for a in vcols], C.c_int32(nx),
+                               *[p(a) for a in xcols], C.c_double(pvw), C.c_int(1 if split_pmds else 0),
+                               *[p(merged[k]) for k in ("job", "condition", "segment_id", "start", "end", "category", "src_row",
+                                                        "src_valley", "follows_large_gap")],
+                               C.c_int64(cap), C.byref(npc), *[p(pieces[k]) for k, _ in PCOLS])
+    assert npc.value >= 0
+    merged = {k: v[:nm] for k, v in merged.items()}
+    pieces = {k: v[:npc.value] for k, v in pieces.items()}
+    return (check_split_against_oracle(merged, pieces, t, category, val, x, split_pmds, pvw), int((merged["src_valley"] >= 0).sum()))
+
+
 def test_emulated_pmd_split_matches_oracle(emu, oracle):
     rng = np.random.default_rng(11)
-    p = lambda a: a.ctypes.data_as(C.c_void_p)
     total = n_valley_rows = 0
     for trial in range(90):
-        t = random_table(rng, adjacent=trial % 5 == 4)
-        n = t["start"].size
-        category = np.zeros(n, np.int8)
-        category[(t["beta"] < 0.1) & (rng.random(n) < 0.4)] = 2
-        category[(t["beta"] >= 0.1) & (rng.random(n) < 0.1)] = 1
-        kw = [{}, dict(pmd_valley_min_width=2500.0), dict(valley_max_beta=0.05, pmd_valley_min_width=1500.0)][trial % 3]
-        pvw = kw.get("pmd_valley_min_width", 5000.0)
-        val = emu(t, category, **kw)
-        x = random_std_call(rng, t)
-        cols = [np.ascontiguousarray(t[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32), ("end", np.uint32))]
-        cols += [np.ascontiguousarray(category, np.int8), np.ascontiguousarray(val["row_in_valley"], np.int8)]
-        nv = val["start"].size
-        vcols = [np.ascontiguousarray(val[k], dt) for k, dt in (("job", np.int32), ("condition", np.int32), ("start", np.uint32),
-                                                                 ("end", np.uint32), ("row0", np.int32))]
-        nx = x["start"].size
-        xcols = [np.ascontiguousarray(x[k], dt) for k, dt in (("job", np.int32), ("estimate_id", np.int32), ("start", np.uint32),
-                                                               ("end", np.uint32), ("fused_std", np.float64), ("pseudoweight", np.float64))]
-        split_pmds = trial % 4 != 1
-        merged = {k: np.empty(n + nv + 1, dt) for k, dt in MCOLS}
-        cap = nx + 2 * (n + nv) + 8
-        pieces = {k: np.empty(cap, dt) for k, dt in PCOLS}
-        npc = C.c_int64(0)
-        nm = emu.lib.emu_pmd_split(C.c_int64(n), *[p(a) for a in cols], C.c_int32(nv), *[p(a) for a in vcols], C.c_int32(nx),
-                                   *[p(a) for a in xcols], C.c_double(pvw), C.c_int(1 if split_pmds else 0),
-                                   *[p(merged[k]) for k in ("job", "condition", "segment_id", "start", "end", "category", "src_row",
-                                                            "src_valley", "follows_large_gap")],
-                                   C.c_int64(cap), C.byref(npc), *[p(pieces[k]) for k, _ in PCOLS])
-        assert npc.value >= 0
-        merged = {k: v[:nm] for k, v in merged.items()}
-        pieces = {k: v[:npc.value] for k, v in pieces.items()}
-        total += check_split_against_oracle(merged, pieces, t, category, val, x, split_pmds, pvw)
-        n_valley_rows += int((merged["src_valley"] >= 0).sum())
+        a, b = split_trial(emu, rng, random_table(rng, adjacent=trial % 5 == 4), trial)
+        total += a
+        n_valley_rows += b
     assert total > 2000 and n_valley_rows > 100
 
 
