@@ -2,6 +2,7 @@
 per-shard segment tables, and that the sharded result equals the single-process result."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -80,3 +81,71 @@ def test_two_ranks_gloo_equals_single_process(oracle):
             assert np.array_equal(gathered[k][at:at + n], s[k]), (j, k)
         at += n
     assert at == gathered["job"].size
+
+
+# ---- the same exchange for the tables of the rule engine (R/call.R:31-221): lmr_umr_valley and pmd per shard ------------------
+RULE_SIZES = (30_000, 6_000, 14_000)
+RULE_KEYS = {"lmr_umr_valley": ("condition", "start", "end", "segment_id", "width", "beta", "coverage", "pseudoweight",
+                                "num_cpgs", "std", "category", "pmd_status"),
+             "pmd": ("condition", "category", "start", "end", "width", "num_cpgs", "fused_std", "beta", "std")}
+
+
+def _rule_tables(O, t, j):
+    from oracle import rule_engine as RE
+    from test_calltable import pooled_from_table
+    r = O.detect(t, O.MODEL_FAST, lambda2=25.0)
+    out = RE.segment_methylation_singlechr(pooled_from_table(t), r["estimates"], pmd_lambda2=100.0, pmd_valley_min_width=1500.0,
+                                           pmd_std_threshold=0.1)["all"]
+    res = {}
+    for name, keys in RULE_KEYS.items():
+        tab = {k: (np.asarray(out[name][k], np.int32) if np.asarray(out[name][k]).dtype.kind in "iu" else np.asarray(out[name][k], np.float64))
+               for k in keys}
+        tab["job"] = np.full(tab["start"].size, j, np.int32)
+        res[name] = tab
+    return res
+
+
+def _rule_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle import oracle as O
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tables = [synth.chromosome_table(n, 400 + i, (2,)) for i, n in enumerate(RULE_SIZES)]
+    rank_of = shard.lpt_assign([shard.job_cost(t["pos"].size) for t in tables], world)
+    mine = [_rule_tables(O, tables[j], j) for j in shard.my_jobs(rank_of, rank)]    # stands in for the GPU engine
+    gathered = {}
+    for name, keys in RULE_KEYS.items():
+        cols = keys + ("job",)
+        local = {k: (np.concatenate([m[name][k] for m in mine]) if mine else
+                     np.empty(0, np.int32 if k in ("job", "condition", "category", "pmd_status", "segment_id", "num_cpgs") else np.float64))
+                 for k in cols}
+        tab, _ = shard.all_gather_tables_packed(local, dist)           # NaN (NA std / beta of a valley) travels as it is
+        gathered[name] = shard.reorder_by_job(tab)
+    if rank == 0:
+        q.put((gathered, rank_of.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_gloo_rule_engine_tables(oracle):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rule_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    gathered, rank_of = q.get(timeout=90)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert set(rank_of) == {0, 1}
+    tables = [synth.chromosome_table(n, 400 + i, (2,)) for i, n in enumerate(RULE_SIZES)]
+    want = [_rule_tables(oracle, t, j) for j, t in enumerate(tables)]
+    for name, keys in RULE_KEYS.items():
+        for k in keys + ("job",):
+            w = np.concatenate([x[name][k] for x in want])
+            assert np.array_equal(gathered[name][k], w, equal_nan=True) and gathered[name][k].dtype == w.dtype, (name, k)
+    assert gathered["pmd"]["start"].size > 10 and (gathered["lmr_umr_valley"]["category"] > 0).sum() > 30
