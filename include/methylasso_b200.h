@@ -334,7 +334,7 @@ ML_API int ml_result_call_valleys(ml_engine *eng, ml_result *r, double tol_val, 
                                   double *beta, double *coverage, double *pseudoweight, int32_t *num_cpgs,
                                   int64_t *n_rows, int8_t *row_in_valley, double *low_id_width, double *low_id_beta);
 
-/* ---- valleys into the call table, PMD candidate regions (R/call.R:131-164) --------------------------------------------
+/* ---- valleys into the call table, PMD candidate regions (R/call.R:131-168) --------------------------------------------
  * Continues ml_result_call_valleys on the same resident tables.  Merged table = seg_call after :140: the call-table
  * rows that overlap no valley plus the valleys, ordered by (job, condition, start); m_category 0 NA, 1 "LMR", 2 "UMR",
  * 3 "UMR-DMV"; m_src_row = the row of ml_result_call_table / ml_result_call_lmr_umr it came from (-1 for a valley),
@@ -343,7 +343,8 @@ ML_API int ml_result_call_valleys(ml_engine *eng, ml_result *r, double tol_val, 
  * :139-140.  Pieces = split_call after :168: the PMD candidate segments of ml_result_call_pmd_segments(pmd_lambda2)
  * (std_call, :93-95) intersected with the "isolate" / "complement" regions of :143-156 (split_pmds != 0: UMRs and
  * valleys isolate, :145; else valleys only, :148), fused_std set to 0 outside "complement" (:161), ordered by (job,
- * estimate_id, start) with p_segment_id = seq_len(.N) per estimate_id (:164).  The per-position gather and the PMD
+ * estimate_id, start) with p_segment_id = seq_len(.N) per estimate_id (:164), counted behind the segments that match no
+ * region (rows of NAs that sort first and are dropped at :168).  The per-position gather and the PMD
  * calls (:169-199) are ml_result_call_pmds.  Query with NULL outputs for the counts first; any output may be NULL. */
 ML_API int ml_result_call_pmd_split(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
                                     double pmd_lambda2, const ml_lmr_params *lmr, const ml_valley_params *params,
