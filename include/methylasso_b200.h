@@ -97,7 +97,10 @@ ML_API void ml_engine_destroy(ml_engine *eng);
 /* engine knobs: "flsa_chunk", "flsa_warm", "flsa_sequential" (1 = start-to-end DP, one thread
  * per series: the bit-faithful verification mode), "profile" (1 = time every kernel),
  * "profile_reserve_events" (pre-create that many timing events), "pool_headroom_percent" (grow the engine's
- * memory pool now by that share of what it holds, so that steady-state calls never map memory) */
+ * memory pool now by that share of what it holds, so that steady-state calls never map memory),
+ * "host_threads" (threads of ml_batch_upload's scan of the dataset column, default 4), "want_mu" (default 1; 0: a
+ * one-step FAST fit does not store the per-row mu, which nothing in the reference's R layer reads - asking for it
+ * from such a result is an error) */
 ML_API int ml_engine_set(ml_engine *eng, const char *key, long long value);
 /* number of kernel launches issued by this engine so far */
 ML_API long long ml_engine_launch_count(const ml_engine *eng);
@@ -137,23 +140,24 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
                                      const double *d_y, const double *d_wt, const double *lambda2,
                                      double lambda1, double *d_beta);
 
-/* debugging aid, not part of the drop-in surface: raw DP solution (no clamp) of one series and its
- * back-pointers tm[k], tp[k] (k = 0..n-2) */
-ML_API int ml_debug_flsa_backpointers(ml_engine *eng, int64_t n, const double *y, const double *wt,
-                                      double lambda2, double *beta, double *tm, double *tp);
-
-/* debugging aid: num[i] / den[i] computed by the chain walker's split division (reciprocal prepared in advance, then the
- * quotient part of the compiler's own division sequence) and by the plain division; the two must agree bit for bit */
-ML_API int ml_debug_divide(ml_engine *eng, int64_t n, const double *num, const double *den, double *out_split,
-                           double *out_plain);
-
 /* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
  *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
-/* Copy the six columns to the GPU and keep them resident (validation and indexing run on the
- * device inside ml_batch_detect).  status may be NULL; it is zero-filled. */
+/* Make the rows of the jobs resident: pos / nmeth / coverage are copied to the GPU (12 bytes per row); dataset,
+ * condition and replicate are factor codes that the reference reads where the dataset changes only
+ * (core/Observations.hpp:36-56; core/data_design_helpers.cpp:17-23), so they are reduced on the host to one entry
+ * per run of equal dataset codes (a streaming compare over the dataset column while the DMA runs) and never
+ * uploaded.  Validation of the rows and indexing run on the device inside ml_batch_detect.  status may be NULL; it
+ * is zero-filled. */
 ML_API int ml_batch_upload(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
                     const int32_t *condition, const int32_t *replicate, const int32_t *pos,
                     const int32_t *nmeth, const int32_t *coverage, ml_batch **out, int *status);
+/* The same for a caller that already has the runs (R: rows are keyed by (chr, dataset, pos), so
+ * data[, .(.N, condition[1], replicate[1]), by = .(chr, dataset)] is the run table): datasets of job j are entries
+ * dset_ptr[j] .. dset_ptr[j+1]-1 of dset_row (job-relative first row; 0 for the first), dset_condition and
+ * dset_replicate; the dataset codes are taken to be 1, 2, ... in that order. */
+ML_API int ml_batch_upload_runs(ml_engine *eng, int njobs, const int64_t *job_ptr, const int64_t *dset_ptr,
+                         const int64_t *dset_row, const int32_t *dset_condition, const int32_t *dset_replicate,
+                         const int32_t *pos, const int32_t *nmeth, const int32_t *coverage, ml_batch **out);
 ML_API void ml_batch_free(ml_batch *b);
 /* Run methylation_detection on every valid job of a resident batch.  `params` is one struct
  * shared by all jobs.  status[njobs] (may be NULL) receives per-job codes. */
@@ -391,6 +395,23 @@ ML_API int ml_result_call_pmd_status(ml_engine *eng, ml_result *r, double tol_va
                                      int64_t *n_rows, int32_t *job, int32_t *condition, uint32_t *start, uint32_t *end,
                                      int8_t *category, int8_t *pmd_status, int32_t *merged_row, int32_t *src_row,
                                      int32_t *src_valley);
+
+/* ---- segment_methylation in one call (R/call.R:229-244 around :31-221) -----------------------------------------------------
+ * Everything above on the resident fit, and the two tables the reference returns, assembled on the device so that only
+ * their rows cross PCIe: `lmr_umr_valley` = seg_call after :212 with the columns of :241 (job = chromosome index,
+ * condition, start, end, width, segment_id, beta, coverage, pseudoweight, num_cpgs, std (NaN = NA on valleys), category
+ * 0 NA / 1 LMR / 2 UMR / 3 UMR-DMV, pmd_status -1 NA / 0 other / 1 PMD) and `pmd` = pmd_call after :198 with the
+ * columns of :242.  drop != 0 (the reference's default, :214-218) keeps the rows with a category and the "PMD" rows.
+ * Query with NULL outputs for the two counts first; any output may be NULL. */
+ML_API int ml_result_segment_methylation(ml_engine *eng, ml_result *r, double tol_val, double max_distance,
+                                         const ml_lmr_params *lmr, const ml_valley_params *valley,
+                                         const ml_pmd_params *pmd, int drop, int64_t *n_seg, int32_t *job,
+                                         int32_t *condition, uint32_t *start, uint32_t *end, double *width,
+                                         int32_t *segment_id, double *beta, double *coverage, double *pseudoweight,
+                                         int32_t *num_cpgs, double *std, int8_t *category, int8_t *pmd_status,
+                                         int64_t *n_pmd, int32_t *p_job, int32_t *p_condition, uint32_t *p_start,
+                                         uint32_t *p_end, double *p_width, int32_t *p_segment_id, double *p_beta,
+                                         double *p_std, int8_t *p_category, int32_t *p_num_cpgs, double *p_fused_std);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

@@ -82,9 +82,8 @@ SIGNATURES = {
     "ml_weighted_1d_flsa": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch_device": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
-    "ml_debug_flsa_backpointers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, _P, _P, _P]),
-    "ml_debug_divide": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P]),
     "ml_batch_upload": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P), _P]),
+    "ml_batch_upload_runs": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "ml_batch_free": (None, [_P]),
     "ml_batch_detect": (C.c_int, [_P, _P, C.POINTER(MlParams), C.POINTER(_P), _P]),
     "ml_detect_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(MlParams),
@@ -117,10 +116,20 @@ SIGNATURES = {
                                       C.POINTER(MlPmdParams), _I64P] + [_P] * 11),
     "ml_result_call_pmd_status": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
                                             C.POINTER(MlPmdParams), _I64P] + [_P] * 9),
+    "ml_result_segment_methylation": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams),
+                                                C.POINTER(MlValleyParams), C.POINTER(MlPmdParams), C.c_int, _I64P] + [_P] * 13
+                                      + [_I64P] + [_P] * 11),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),
     "ml_segment_call_table": (C.c_int, [_P, C.c_int64] + [_P] * 4 + [C.c_int64] + [_P] * 5 + [C.c_double, _I64P] + [_P] * 10),
+}
+
+# test hooks of csrc/debug_api.h: exported, but not part of the drop-in surface
+DEBUG_SIGNATURES = {
+    "ml_debug_flsa_backpointers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, _P, _P, _P]),
+    "ml_debug_scan_runs": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int, C.c_int64, _I64P, _P, _P, _P,
+                                     C.POINTER(C.c_int32), _I64P]),
 }
 
 _lib = None
@@ -136,7 +145,7 @@ def load():
             f"{LIB_PATH} not found: build it with `python -m methylasso_b200.build` "
             "(nvcc, sm_100a). methylasso_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for name, (res, args) in SIGNATURES.items():
+    for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args

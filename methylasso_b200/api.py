@@ -80,6 +80,7 @@ class Engine:
         if rc:
             raise MethyLassoError(rc, self.lib.ml_last_error().decode())
         self.h = h
+        self.want_mu = True
 
     def pinned_buffer(self, name, n, dtype):
         """View of n elements of an engine-owned page-locked buffer called `name` (allocated on first use, grown
@@ -111,6 +112,8 @@ class Engine:
 
     def set(self, key: str, value: int):
         self._check(self.lib.ml_engine_set(self.h, key.encode(), int(value)))
+        if key == "want_mu":
+            self.want_mu = bool(value)
 
     @property
     def launch_count(self) -> int:
@@ -222,6 +225,19 @@ class Engine:
                                              C.byref(h), None))
         return Batch(self, h, job_ptr.size - 1)
 
+    def upload_runs(self, job_ptr, dset_ptr, dset_row, dset_condition, dset_replicate, cols) -> "Batch":
+        """ml_batch_upload_runs: the caller hands the dataset runs (first row, condition, replicate of every dataset
+        of every job) instead of the three factor columns; cols needs pos, Nmeth, coverage only."""
+        job_ptr = np.ascontiguousarray(job_ptr, dtype=np.int64)
+        dset_ptr = np.ascontiguousarray(dset_ptr, dtype=np.int64)
+        dset_row = np.ascontiguousarray(dset_row, dtype=np.int64)
+        dc, dr = _i32(dset_condition), _i32(dset_replicate)
+        arrs = [_i32(cols[k]) for k in ("pos", "Nmeth", "coverage")]
+        h = C.c_void_p()
+        self._check(self.lib.ml_batch_upload_runs(self.h, job_ptr.size - 1, _p(job_ptr), _p(dset_ptr), _p(dset_row), _p(dc),
+                                                  _p(dr), *[_p(a) for a in arrs], C.byref(h)))
+        return Batch(self, h, job_ptr.size - 1)
+
     def detect(self, batch: "Batch", params: MlParams) -> "Result":
         h = C.c_void_p()
         status = np.zeros(max(batch.njobs, 1), np.int32)
@@ -286,6 +302,7 @@ class Result:
     def __init__(self, eng, h, status):
         self.eng, self.h, self.status = eng, h, status
         self.njobs = status.size
+        self.has_mu = bool(getattr(eng, "want_mu", True))    # one-step fits of an engine with want_mu = 0 store no mu
 
     def free(self):
         if self.h:
@@ -318,7 +335,7 @@ class Result:
         n, P, E, D, status = self.sizes(job)
         if status:
             raise MethyLassoError(status, self.eng.lib.ml_strerror(status).decode())
-        mu = np.empty(n) if want_mu else None
+        mu = np.empty(n) if (want_mu and self.has_mu) else None
         lam, off = np.empty(E), np.empty(D)
         est = dict(estimate_id=np.empty(E * P, np.int32), start=np.empty(E * P), beta=np.empty(E * P),
                    betahat=np.empty(E * P), pseudoweight=np.empty(E * P))
@@ -541,6 +558,42 @@ class Result:
         out = {k: np.empty(max(n.value, 1), dt) for k, dt in self.STATUS_COLUMNS}
         self.eng._check(self.eng.lib.ml_result_call_pmd_status(*args, C.byref(n), *[_p(out[k]) for k, _ in self.STATUS_COLUMNS]))
         return {k: v[:n.value] for k, v in out.items()}
+
+    REGION_SEG_COLUMNS = (("job", np.int32), ("condition", np.int32), ("start", np.uint32), ("end", np.uint32),
+                          ("width", np.float64), ("segment_id", np.int32), ("beta", np.float64), ("coverage", np.float64),
+                          ("pseudoweight", np.float64), ("num_cpgs", np.int32), ("std", np.float64), ("category", np.int8),
+                          ("pmd_status", np.int8))
+    REGION_PMD_COLUMNS = (("job", np.int32), ("condition", np.int32), ("start", np.uint32), ("end", np.uint32),
+                          ("width", np.float64), ("segment_id", np.int32), ("beta", np.float64), ("std", np.float64),
+                          ("category", np.int8), ("num_cpgs", np.int32), ("fused_std", np.float64))
+
+    def segment_methylation_tables(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, pmd_std_threshold=0.15,
+                                   pmd_max_beta=0.75, split_pmds=True, merge_pmds=True, valley_max_beta=0.1,
+                                   pmd_valley_min_width=5000.0, min_num_cpgs=4, drop=True, reuse_pinned=False,
+                                   **lmr_thresholds):
+        """ml_result_segment_methylation: the whole rule engine of R/call.R:31-221 on the resident fit and the two
+        tables the reference returns (`lmr_umr_valley`, `pmd`), assembled on the device.  Returns (seg, pmd): dicts of
+        columns with integer codes (category 0 NA / 1 LMR / 2 UMR / 3 UMR-DMV, pmd_status -1 NA / 0 other / 1 PMD; pmd
+        category 1 PMD / 0 other); `job` indexes the jobs of the batch."""
+        from ._native import MlLmrParams, MlPmdParams, MlValleyParams
+        lp = MlLmrParams(max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs), **lmr_thresholds)
+        vp = MlValleyParams(valley_max_beta=float(valley_max_beta), pmd_valley_min_width=float(pmd_valley_min_width),
+                            max_distance=float(max_distance), min_num_cpgs=int(min_num_cpgs))
+        pp = MlPmdParams(pmd_lambda2=float(pmd_lambda2), pmd_std_threshold=float(pmd_std_threshold),
+                         pmd_max_beta=float(pmd_max_beta), split_pmds=1 if split_pmds else 0, merge_pmds=1 if merge_pmds else 0)
+        ns, npm = C.c_int64(0), C.c_int64(0)
+        args = (self.eng.h, self.h, float(tol_val), float(max_distance), C.byref(lp), C.byref(vp), C.byref(pp), 1 if drop else 0)
+        self.eng._check(self.eng.lib.ml_result_segment_methylation(*args, C.byref(ns), *([None] * 13), C.byref(npm), *([None] * 11)))
+        if reuse_pinned:
+            seg = {k: self.eng.pinned_buffer("rseg_" + k, max(ns.value, 1), dt) for k, dt in self.REGION_SEG_COLUMNS}
+            pmd = {k: self.eng.pinned_buffer("rpmd_" + k, max(npm.value, 1), dt) for k, dt in self.REGION_PMD_COLUMNS}
+        else:
+            seg = {k: np.empty(max(ns.value, 1), dt) for k, dt in self.REGION_SEG_COLUMNS}
+            pmd = {k: np.empty(max(npm.value, 1), dt) for k, dt in self.REGION_PMD_COLUMNS}
+        self.eng._check(self.eng.lib.ml_result_segment_methylation(
+            *args, C.byref(ns), *[_p(seg[k]) for k, _ in self.REGION_SEG_COLUMNS], C.byref(npm),
+            *[_p(pmd[k]) for k, _ in self.REGION_PMD_COLUMNS]))
+        return ({k: v[:ns.value] for k, v in seg.items()}, {k: v[:npm.value] for k, v in pmd.items()})
 
     def call_pmd_segments(self, tol_val=0.01, max_distance=500.0, pmd_lambda2=1000.0, fetch=True, want_fused=False):
         """R/call.R:93-95 on the call table (std and width as the reference computes them)."""
@@ -863,40 +916,25 @@ def segment_methylation(data, ret, ncores=1, min_num_cpgs=4, pmd_lambda2=1000, p
     common = dict(valley_max_beta=valley_max_beta, pmd_valley_min_width=pmd_valley_min_width, min_num_cpgs=min_num_cpgs, **lmr)
     pkw = dict(pmd_lambda2=pmd_lambda2, pmd_std_threshold=pmd_std_threshold, pmd_max_beta=pmd_max_beta,
                split_pmds=split_pmds, merge_pmds=merge_pmds)
-    call = res.call_table(tol_val, max_distance)
-    val = res.call_valleys(tol_val, max_distance, **common)
-    merged, _ = res.call_pmd_split(tol_val, max_distance, pmd_lambda2, split_pmds, **common)
-    pmd = res.call_pmds(tol_val, max_distance, **pkw, **common)
-    fin = res.call_pmd_status(tol_val, max_distance, **pkw, **common)
-    names = np.asarray(fit.names)
-    src, sv = fin["src_row"], fin["src_valley"]
-    is_row = src >= 0
+    seg_t, pmd_c = res.segment_methylation_tables(tol_val, max_distance, drop=drop, **pkw, **common)
+    return region_tables(seg_t, pmd_c, np.asarray(fit.names))
 
-    def col(ck, vk, dtype=np.float64):
-        out = np.full(src.size, np.nan) if dtype == np.float64 else np.zeros(src.size, dtype)
-        out[is_row] = call[ck][src[is_row]]
-        if vk is not None:
-            out[~is_row] = val[vk][sv[~is_row]]
-        return out
-    status_names = np.array([None, "other", "PMD"], dtype=object)
-    cat_names = np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)
-    seg = dict(condition=fin["condition"], chr=names[fin["job"]] if src.size else np.empty(0, dtype=object),
-               start=fin["start"], end=fin["end"], width=col("width", "width"),
-               segment_id=merged["segment_id"][fin["merged_row"]] if src.size else np.empty(0, np.int32),
-               beta=col("beta", "beta"), coverage=col("coverage", "coverage"), pseudoweight=col("pseudoweight", "pseudoweight"),
-               num_cpgs=col("num_cpgs", "num_cpgs", np.int64), std=col("std", None), category=cat_names[fin["category"]],
-               PMD_status=status_names[fin["pmd_status"] + 1])
-    pmd_t = dict(condition=pmd["condition"], chr=names[pmd["job"]] if pmd["job"].size else np.empty(0, dtype=object),
-                 start=pmd["start"], end=pmd["end"], width=pmd["width"], segment_id=pmd["segment_id"], beta=pmd["beta"],
-                 std=pmd["std"], category=np.where(pmd["category"] == 1, "PMD", "other").astype(object),
-                 num_cpgs=pmd["num_cpgs"], fused_std=pmd["fused_std"])
-    if drop:                                                   # R/call.R:214-218
-        keep = fin["category"] != 0
-        seg = {k: v[keep] for k, v in seg.items()}
-        pk = pmd["category"] == 1
-        pmd_t = {k: v[pk] for k, v in pmd_t.items()}
+
+STATUS_NAMES = np.array([None, "other", "PMD"], dtype=object)          # pmd_status + 1
+CATEGORY_NAMES = np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)
+
+
+def region_tables(seg_t, pmd_c, names):
+    """The two tables of ml_result_segment_methylation with the reference's columns and labels (R/call.R:241-243)."""
+    seg = dict(condition=seg_t["condition"], chr=names[seg_t["job"]] if seg_t["job"].size else np.empty(0, dtype=object),
+               start=seg_t["start"], end=seg_t["end"], width=seg_t["width"], segment_id=seg_t["segment_id"], beta=seg_t["beta"],
+               coverage=seg_t["coverage"], pseudoweight=seg_t["pseudoweight"], num_cpgs=seg_t["num_cpgs"].astype(np.int64),
+               std=seg_t["std"], category=CATEGORY_NAMES[seg_t["category"]], PMD_status=STATUS_NAMES[seg_t["pmd_status"] + 1])
+    pmd_t = dict(condition=pmd_c["condition"], chr=names[pmd_c["job"]] if pmd_c["job"].size else np.empty(0, dtype=object),
+                 start=pmd_c["start"], end=pmd_c["end"], width=pmd_c["width"], segment_id=pmd_c["segment_id"], beta=pmd_c["beta"],
+                 std=pmd_c["std"], category=np.where(pmd_c["category"] == 1, "PMD", "other").astype(object),
+                 num_cpgs=pmd_c["num_cpgs"], fused_std=pmd_c["fused_std"])
     return dict(lmr_umr_valley=seg, pmd=pmd_t)
-
 
 def signal_detection(data, optimize_lambda2=False, lambda2=25, max_lambda2=1000, optimize_hyper=False,
                      hyper=100, nouter=20, bf_per_kb=50, tol_val=0.01, max_iter=30, ncores=1, engine=None):

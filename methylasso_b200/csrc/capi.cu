@@ -8,6 +8,7 @@
 #include <string>
 
 #include "../../include/methylasso_b200.h"
+#include "debug_api.h"
 #include "detect.cuh"
 #include "segment.cuh"
 #include "stats.cuh"
@@ -84,12 +85,17 @@ static int fail(int code, const std::string& msg) {
   return code;
 }
 
+// An exception may unwind frames that small readbacks were registered into (mailbox_fetch keeps the destination
+// address until the next stream_sync): drop those records, or a later synchronisation would write through them.
+static void mailbox_abort() {
+  if (Mailbox* m = tls_mailbox()) { m->pending.clear(); m->used = 0; m->in_used = 0; }
+}
 #define ML_TRY try {
 #define ML_CATCH                                                        \
   }                                                                     \
-  catch (const MlError& e) { return fail(e.code, e.what()); }           \
-  catch (const std::bad_alloc&) { return fail(ML_ERR_CUDA, "host allocation failed"); } \
-  catch (const std::exception& e) { return fail(ML_ERR_BAD_ARGUMENT, e.what()); }
+  catch (const MlError& e) { mailbox_abort(); return fail(e.code, e.what()); }           \
+  catch (const std::bad_alloc&) { mailbox_abort(); return fail(ML_ERR_CUDA, "host allocation failed"); } \
+  catch (const std::exception& e) { mailbox_abort(); return fail(ML_ERR_BAD_ARGUMENT, e.what()); }
 
 static_assert(sizeof(ml_params) == sizeof(Params), "ml_params / Params layout mismatch");
 
@@ -165,9 +171,17 @@ int ml_engine_create(int device, ml_engine** out) {
   h->e.mailbox.in_cap = 32 << 20;
   ML_CUDA(cudaHostAlloc((void**)&h->e.mailbox.in_host, h->e.mailbox.in_cap, cudaHostAllocMapped | cudaHostAllocWriteCombined));
   ML_CUDA(cudaHostGetDevicePointer((void**)&h->e.mailbox.in_dev, h->e.mailbox.in_host, 0));
-  if (const char* s = getenv("ML_FLSA_CHUNK")) h->e.flsa_chunk = atoi(s);
-  if (const char* s = getenv("ML_FLSA_WARM")) h->e.flsa_warm = atoi(s);
-  if (const char* s = getenv("ML_FLSA_SEQUENTIAL")) h->e.flsa_sequential = atoi(s);
+  // tunables are read from the environment HERE, once per engine: nothing on a launch path calls getenv
+  auto env_int = [](const char* name, int& v) { if (const char* s = getenv(name)) v = atoi(s); };
+  env_int("ML_FLSA_CHUNK", h->e.flsa_chunk);
+  env_int("ML_FLSA_WARM", h->e.flsa_warm);
+  env_int("ML_FLSA_SEQUENTIAL", h->e.flsa_sequential);
+  env_int("ML_FLSA_SMALL_N", h->e.flsa_small_n);
+  env_int("ML_FLSA_CHUNK_BIG", h->e.flsa_chunk_big);
+  env_int("ML_FLSA_WARM_BIG", h->e.flsa_warm_big);
+  env_int("ML_FLSA_CHUNK_SMALL", h->e.flsa_chunk_small);
+  env_int("ML_FLSA_WARM_SMALL", h->e.flsa_warm_small);
+  env_int("ML_HOST_THREADS", h->e.host_threads);
   *out = guard.release();
   return ML_OK;
   ML_CATCH
@@ -192,6 +206,8 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   if (k == "flsa_chunk") eng->e.flsa_chunk = (int)value;
   else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
   else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
+  else if (k == "host_threads") eng->e.host_threads = (int)std::max<long long>(1, value);
+  else if (k == "want_mu") eng->e.want_mu = value != 0;
   else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }
   else if (k == "profile_reserve_events") {
     // pre-create timing events so that a profiled region does not call cudaEventCreate
@@ -319,12 +335,27 @@ int ml_debug_flsa_backpointers(ml_engine* eng, int64_t n, const double* y, const
   plan.solve(d_y.p, d_w.p, d_b.p, 0, 0.0, nullptr);
   d_b.download(beta, (size_t)n);
   plan.debug_backpointers(tm, tp);
-  if (getenv("ML_DEBUG_CHUNKS")) {
-    std::vector<ChunkState> cs;
-    plan.debug_chunk_states(cs);
-    for (size_t c = 0; c < cs.size(); ++c)
-      fprintf(stderr, "chunk %zu status %d count %d pad %d\n", c, cs[c].status, cs[c].count, cs[c].pad);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_debug_scan_runs(int64_t n, const int32_t* dataset, const int32_t* condition, const int32_t* replicate,
+                       const int32_t* pos, int threads, int64_t cap, int64_t* n_runs, int64_t* first_row,
+                       int32_t* run_condition, int32_t* run_replicate, int32_t* code, int64_t* code_row) {
+  if (n < 0 || !n_runs || (n > 0 && (!dataset || !condition || !replicate || !pos))) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  Batch b;
+  debug_scan_runs(n, dataset, condition, replicate, pos, threads, b);
+  const int64_t k = b.n_runs(0);
+  *n_runs = k;
+  for (int64_t t = 0; t < k && t < cap; ++t) {
+    if (first_row) first_row[t] = b.dptr[t];
+    if (run_condition) run_condition[t] = b.dcond[t];
+    if (run_replicate) run_replicate[t] = b.drep[t];
   }
+  const unsigned long long key = b.host_key[0];
+  if (code) *code = key == ~0ull ? 0 : (int32_t)(key & 0xff);
+  if (code_row) *code_row = key == ~0ull ? -1 : (int64_t)((key >> 8) & 0xfffffffffffffull);
   return ML_OK;
   ML_CATCH
 }
@@ -389,6 +420,24 @@ int ml_batch_upload(ml_engine* eng, int njobs, const int64_t* job_ptr, const int
   h->b = batch_upload(eng->e, njobs, job_ptr, dataset, condition, replicate, pos, nmeth, coverage);
   if (status)
     for (int j = 0; j < njobs; ++j) status[j] = 0;  // validation runs on the device inside detect
+  *out = h.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_batch_upload_runs(ml_engine* eng, int njobs, const int64_t* job_ptr, const int64_t* dset_ptr,
+                         const int64_t* dset_row, const int32_t* dset_condition, const int32_t* dset_replicate,
+                         const int32_t* pos, const int32_t* nmeth, const int32_t* coverage, ml_batch** out) {
+  if (!eng || !out || !job_ptr || !dset_ptr) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  if (njobs > 0 && job_ptr[njobs] > 0 && (!dset_row || !dset_condition || !dset_replicate || !pos || !nmeth || !coverage))
+    throw MlError(ML_ERR_BAD_ARGUMENT, "NULL column");
+  auto h = std::make_unique<ml_batch>();
+  h->b = batch_upload_runs(eng->e, njobs, job_ptr, dset_ptr, dset_row, dset_condition, dset_replicate, pos, nmeth, coverage);
   *out = h.release();
   return ML_OK;
   ML_CATCH
@@ -470,6 +519,7 @@ int ml_result_copy_job(ml_engine* eng, const ml_result* r, int job, double* mu, 
   if (j.status) return fail(j.status, ml_strerror(j.status));
   cudaStream_t st = eng->e.stream;
   const size_t EP = (size_t)j.E * (size_t)j.P;
+  if (mu && !R.has_mu) return fail(ML_ERR_BAD_ARGUMENT, "mu was not stored (engine key want_mu = 0)");
   if (mu) ML_CUDA(cudaMemcpyAsync(mu, R.mu.p + j.row0, sizeof(double) * (size_t)j.nrows, cudaMemcpyDeviceToHost, st));
   if (offset) ML_CUDA(cudaMemcpyAsync(offset, R.offset.p + j.off0, sizeof(double) * (size_t)j.D, cudaMemcpyDeviceToHost, st));
   if (beta) ML_CUDA(cudaMemcpyAsync(beta, R.beta.p + j.par0, sizeof(double) * EP, cudaMemcpyDeviceToHost, st));
@@ -488,14 +538,15 @@ int ml_result_copy_job(ml_engine* eng, const ml_result* r, int job, double* mu, 
   ML_CATCH
 }
 
-static int result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
+static int result_copy_all(ml_engine* eng, ml_result* r, double* mu, double* offset, int32_t* estimate_id,
                            double* start, double* beta, double* betahat, double* pseudoweight, bool async) {
   if (!eng || !r) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   ML_TRY
   ML_CUDA(cudaSetDevice(eng->e.device));
   tls_pool() = eng->e.pool;
   tls_mailbox() = &eng->e.mailbox;
-  const Result& R = *r->r;
+  Result& R = *r->r;
+  if (mu && !R.has_mu) return fail(ML_ERR_BAD_ARGUMENT, "mu was not stored (engine key want_mu = 0)");
   // The asynchronous variant copies on the engine's copy stream, so that later compute calls on the main
   // stream overlap with the transfer; the copy stream first waits for whatever the main stream still has
   // in flight for this result (ml_batch_detect does not synchronise at its end).
@@ -532,19 +583,25 @@ static int result_copy_all(ml_engine* eng, const ml_result* r, double* mu, doubl
   }
   if (estimate_id && R.npar)
     ML_CUDA(cudaMemcpyAsync(estimate_id, R.est_id.p, sizeof(int32_t) * (size_t)R.npar, cudaMemcpyDeviceToHost, st));
-  if (!async) stream_sync(st);
+  if (async) {
+    // the result's buffers are freed in main-stream order: its destructor makes the main stream wait for these copies
+    if (!R.copy_done) ML_CUDA(cudaEventCreateWithFlags(&R.copy_done, cudaEventDisableTiming));
+    ML_CUDA(cudaEventRecord(R.copy_done, st));
+  } else {
+    stream_sync(st);
+  }
   return ML_OK;
   ML_CATCH
 }
 
 int ml_result_copy_all(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
                        double* start, double* beta, double* betahat, double* pseudoweight) {
-  return result_copy_all(eng, r, mu, offset, estimate_id, start, beta, betahat, pseudoweight, false);
+  return result_copy_all(eng, const_cast<ml_result*>(r), mu, offset, estimate_id, start, beta, betahat, pseudoweight, false);
 }
 
 int ml_result_copy_all_async(ml_engine* eng, const ml_result* r, double* mu, double* offset, int32_t* estimate_id,
                              double* start, double* beta, double* betahat, double* pseudoweight) {
-  return result_copy_all(eng, r, mu, offset, estimate_id, start, beta, betahat, pseudoweight, true);
+  return result_copy_all(eng, const_cast<ml_result*>(r), mu, offset, estimate_id, start, beta, betahat, pseudoweight, true);
 }
 
 void ml_result_free(ml_result* r) {
@@ -694,6 +751,10 @@ std::vector<SegGroup> result_groups(const Result& R) {
 }
 int ensure_call_table(ml_engine* eng, ml_result* r, double tol_val, double max_distance) {
   Result& R = *r->r;
+  if (R.diff_combined)
+    return fail(ML_ERR_BAD_ARGUMENT, "the call table of a difference fit is not available natively: after the combine the "
+                                     "estimates hold differences, not pooled counts (the reference segments the reference "
+                                     "condition of such a fit, R/call.R:40-44)");
   if (!R.counts_exact)
     return fail(ML_ERR_BAD_ARGUMENT, "the resident call table needs a FAST result with max_iter = 1 (pooled counts are "
                                      "recovered from betahat * pseudoweight); use ml_segment_call_table otherwise");
@@ -909,17 +970,6 @@ int ml_result_call_differences(ml_engine* eng, const ml_batch* b, ml_result* r, 
   ML_CATCH
 }
 
-int ml_debug_divide(ml_engine* eng, int64_t n, const double* num, const double* den, double* out_split, double* out_plain) {
-  if (!eng || n <= 0 || !num || !den || !out_split || !out_plain) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
-  ML_TRY
-  ML_CUDA(cudaSetDevice(eng->e.device));
-  tls_pool() = eng->e.pool;
-  tls_mailbox() = &eng->e.mailbox;
-  debug_divide(eng->e, n, num, den, out_split, out_plain);
-  return ML_OK;
-  ML_CATCH
-}
-
 int ml_host_alloc(uint64_t bytes, void** out) {
   if (!out) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
   *out = nullptr;
@@ -1031,6 +1081,8 @@ struct RuleState {
   PmdCallParams cp;
   PmdCallDev calls;
   FinalDev F;
+  int regions_drop = -1;     // -1: the region tables have not been gathered for the current calls
+  RegionTables regions;
 };
 // the state for these arguments: the cached one when nothing it was built from has changed, else computed now
 int rule_state(ml_engine* eng, ml_result* r, double tol_val, double max_distance, double pmd_lambda2,
@@ -1082,10 +1134,12 @@ void rule_calls(ml_engine* eng, ml_result* r, RuleState& st, const ml_pmd_params
     st.cp = cp;
     st.has_calls = true;
     st.has_final = false;
+    st.regions_drop = -1;
   }
   if (want_final && !st.has_final) {
     call_pmd_status_device(eng->e, st.S.M, st.calls, st.S.lu.is_admissible.p, st.F);
     st.has_final = true;
+    st.regions_drop = -1;
   }
 }
 }  // namespace
@@ -1190,6 +1244,63 @@ int ml_result_call_pmd_status(ml_engine* eng, ml_result* r, double tol_val, doub
     if (merged_row) F.merged.download(merged_row, n);
     if (src_row) F.src_row.download(src_row, n);
     if (src_valley) F.src_valley.download(src_valley, n);
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+int ml_result_segment_methylation(ml_engine* eng, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* lmr,
+                                  const ml_valley_params* valley, const ml_pmd_params* pmd, int drop, int64_t* n_seg,
+                                  int32_t* job, int32_t* condition, uint32_t* start, uint32_t* end, double* width,
+                                  int32_t* segment_id, double* beta, double* coverage, double* pseudoweight, int32_t* num_cpgs,
+                                  double* std_, int8_t* category, int8_t* pmd_status, int64_t* n_pmd, int32_t* p_job,
+                                  int32_t* p_condition, uint32_t* p_start, uint32_t* p_end, double* p_width,
+                                  int32_t* p_segment_id, double* p_beta, double* p_std, int8_t* p_category,
+                                  int32_t* p_num_cpgs, double* p_fused_std) {
+  if (!eng || !r || !n_seg || !n_pmd) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
+  if (pmd) pp = *pmd;
+  RuleState* st = nullptr;
+  const int rc = rule_state(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, &st);
+  if (rc) return rc;
+  rule_calls(eng, r, *st, pp, true);
+  drop = drop ? 1 : 0;
+  if (st->regions_drop != drop) {
+    region_tables_device(eng->e, *r->r->call_cache, st->S.v, st->S.M, st->calls, st->F, drop, st->regions);
+    st->regions_drop = drop;
+  }
+  const RegionTables& T = st->regions;
+  *n_seg = T.n_seg;
+  *n_pmd = T.n_pmd;
+  const size_t ns = (size_t)T.n_seg, np = (size_t)T.n_pmd;
+  if (ns) {
+    if (job) T.s_job.download(job, ns);
+    if (condition) T.s_condition.download(condition, ns);
+    if (start) T.s_start.download(start, ns);
+    if (end) T.s_end.download(end, ns);
+    if (width) T.s_width.download(width, ns);
+    if (segment_id) T.s_segment_id.download(segment_id, ns);
+    if (beta) T.s_beta.download(beta, ns);
+    if (coverage) T.s_coverage.download(coverage, ns);
+    if (pseudoweight) T.s_pseudoweight.download(pseudoweight, ns);
+    if (num_cpgs) T.s_num_cpgs.download(num_cpgs, ns);
+    if (std_) T.s_std.download(std_, ns);
+    if (category) T.s_category.download(category, ns);
+    if (pmd_status) T.s_pmd_status.download(pmd_status, ns);
+  }
+  if (np) {
+    if (p_job) T.p_job.download(p_job, np);
+    if (p_condition) T.p_condition.download(p_condition, np);
+    if (p_start) T.p_start.download(p_start, np);
+    if (p_end) T.p_end.download(p_end, np);
+    if (p_width) T.p_width.download(p_width, np);
+    if (p_segment_id) T.p_segment_id.download(p_segment_id, np);
+    if (p_beta) T.p_beta.download(p_beta, np);
+    if (p_std) T.p_std.download(p_std, np);
+    if (p_category) T.p_category.download(p_category, np);
+    if (p_num_cpgs) T.p_num_cpgs.download(p_num_cpgs, np);
+    if (p_fused_std) T.p_fused_std.download(p_fused_std, np);
   }
   stream_sync(eng->e.stream);
   return ML_OK;

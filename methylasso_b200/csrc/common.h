@@ -112,6 +112,10 @@ struct Engine {
   int flsa_chunk = 0;       // 0 = choose from total work
   int flsa_warm = 0;        // 0 = choose from lambda
   int flsa_sequential = 0;  // 1 = one thread per series start-to-end (bit-faithful verification mode)
+  // chunk / warm-up lengths by series length (read from the environment once, when the engine is created)
+  int flsa_small_n = 262144, flsa_chunk_big = 448, flsa_warm_big = 512, flsa_chunk_small = 64, flsa_warm_small = 768;
+  int host_threads = 4;     // host threads of batch_upload's run scan over the dataset column
+  int want_mu = 1;          // 0: a one-step fit does not store the per-row mu (nothing in the reference's R layer reads it)
   // launch accounting for bench.py's gpu_launches
   long long launches = 0;
 };

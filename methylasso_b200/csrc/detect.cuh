@@ -57,15 +57,28 @@ enum : int32_t {  // per-job control bits, re-uploaded every global step of the 
   CTL_NO_MU = 64, CTL_DRES = 128, CTL_ZERO_PARAMS = 256
 };
 
+// Input rows of a batch, resident in HBM.  Only pos / Nmeth / coverage live on the device: dataset, condition
+// and replicate are factor codes that are constant along each dataset's run of rows (the reference validates them
+// at run boundaries only, core/Observations.hpp:36-56), so the host keeps them as a RUN TABLE (one entry per job
+// and dataset: first row, condition, replicate, first / last position) and nothing of those three columns crosses
+// PCIe.  Every job's rows start at a multiple of ROW_ALIGN in the device columns (16-byte vector loads).
 struct Batch {
   Engine* eng = nullptr;
   int njobs = 0;
-  int64_t nrows = 0;
-  std::vector<int64_t> job_ptr;
-  std::vector<int32_t> hint_D, hint_C;  // dataset / condition of each job's last row (host copy)
-  DevBuf<int32_t> dataset, condition, replicate, pos, nmeth, cov;
-  DevBuf<int64_t> d_job_ptr;
+  int64_t nrows = 0;         // rows handed in by the caller
+  int64_t nrows_dev = 0;     // rows of the device columns (job starts padded to ROW_ALIGN)
+  std::vector<int64_t> job_ptr;      // caller offsets (njobs + 1)
+  std::vector<int64_t> dev_row0;     // first device row of each job
+  // run table: entries [run0[j], run0[j+1]) belong to job j, one per dataset run found before the first
+  // structural offence; dptr holds run0[j+1] - run0[j] + 1 job-relative row offsets starting at dptr0[j]
+  std::vector<int32_t> run0, dptr0;
+  std::vector<int32_t> dptr, dcond, drep, dfirst, dlast;
+  std::vector<unsigned long long> host_key;   // first structural offence per job (validation key), ~0: none
+  std::vector<int32_t> last_condition;        // condition of each job's last row (data_design_helpers.cpp:23)
+  DevBuf<int32_t> pos, nmeth, cov;
+  int n_runs(int j) const { return run0[j + 1] - run0[j]; }
 };
+constexpr int ROW_ALIGN = 32;
 
 struct JobHost {
   int32_t status = 0;
@@ -81,6 +94,16 @@ struct Result {
   Engine* eng = nullptr;
   std::vector<JobHost> jobs;
   int64_t nrows = 0, npar = 0;  // totals over the batch (npar = sum E*P over valid jobs)
+  int64_t nrows_dev = 0;        // rows of the device columns (job starts padded, Batch::dev_row0); JobHost::row0 indexes them
+  bool has_mu = true;           // mu was stored (engine key want_mu, see batch_detect)
+  cudaEvent_t copy_done = nullptr;   // last asynchronous download on the copy stream (ml_result_copy_all_async)
+  ~Result() {
+    // the buffers below are freed in main-stream order: not before an asynchronous download of them has finished
+    if (copy_done) {
+      if (eng) cudaStreamWaitEvent(eng->stream, copy_done, 0);
+      cudaEventDestroy(copy_done);
+    }
+  }
   int32_t noff = 0;
   DevBuf<double> mu;                      // per row (rows of failed jobs are untouched)
   DevBuf<double> beta, betahat, pw;       // per parameter
@@ -88,6 +111,8 @@ struct Result {
   DevBuf<double> offset;
   DevBuf<int32_t> est_id;                 // per parameter: estimator index + 1
   std::vector<int64_t> start0;            // per job: offset into start (P entries)
+  DevBuf<int32_t> rowstart;               // FAST: [job][dataset][P] first row of dataset d on parameter k (-1: none), kept for
+  std::vector<int64_t> tab0;              // the DMR caller's join of the raw rows (R/call.R:258-263); per job: offset into it
   int64_t nstart = 0;
   // segments of the last ml_result_segments call (query-then-fetch without recomputing)
   std::unique_ptr<SegDeviceOut> seg_cache;
@@ -130,7 +155,15 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
 std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
                                     const int32_t* condition, const int32_t* replicate,
                                     const int32_t* pos, const int32_t* nmeth, const int32_t* cov);
+// the same from a caller-made run table: dset_ptr[j] .. dset_ptr[j+1] index the datasets of job j in
+// dset_row (first row of each dataset, job-relative) / dset_condition / dset_replicate
+std::unique_ptr<Batch> batch_upload_runs(Engine& eng, int njobs, const int64_t* job_ptr, const int64_t* dset_ptr,
+                                         const int64_t* dset_row, const int32_t* dset_condition,
+                                         const int32_t* dset_replicate, const int32_t* pos, const int32_t* nmeth,
+                                         const int32_t* cov);
 std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p);
+void debug_scan_runs(int64_t n, const int32_t* dataset, const int32_t* condition, const int32_t* replicate,
+                     const int32_t* pos, int threads, Batch& b);
 void result_fast_diff_combine(Engine& eng, Result& r);
 // per-device constant tables of the IRLS kernels (idempotent; called when an engine is created)
 void detect_init_device_tables(cudaStream_t st);

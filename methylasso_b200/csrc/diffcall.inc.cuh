@@ -31,37 +31,6 @@ struct DcGroup {        // one comparison = (job, estimator e >= 1)
   int32_t cond_x, cond_ref, pad;
 };
 
-// condition of every dataset of every job, read at the dataset's first row (rows are sorted by dataset)
-__global__ void k_dc_dataset_cond(const DcJob* __restrict__ jobs, const int32_t* __restrict__ ent_job,
-                                  const int32_t* __restrict__ ent_d, int n_ent, const int32_t* __restrict__ dataset,
-                                  const int32_t* __restrict__ condition, int32_t* __restrict__ dcond) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_ent) return;
-  const DcJob J = jobs[ent_job[i]];
-  const int d = ent_d[i];                       // 0 .. D - 1
-  int lo = 0, hi = J.nrows;                     // first row with dataset id >= d + 1
-  while (lo < hi) { const int mid = (lo + hi) >> 1; if (dataset[J.jrow0 + mid] < d + 1) lo = mid + 1; else hi = mid; }
-  dcond[J.dc0 + d] = lo < J.nrows ? condition[J.jrow0 + lo] : 0;
-}
-
-// (dataset, parameter) -> row of the job, -1 where the dataset has no data at the position
-__global__ void __launch_bounds__(256)
-k_dc_rowidx(const DcJob* __restrict__ jobs, int n_jobs, int64_t n_rows_total, const int32_t* __restrict__ dataset,
-            const int32_t* __restrict__ pos, const double* __restrict__ start, int32_t* __restrict__ rowidx) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rows_total) return;
-  int lo = 0, hi = n_jobs - 1;                  // last valid job with jrow0 <= r
-  if (n_jobs == 0 || r < jobs[0].jrow0) return;
-  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (jobs[mid].jrow0 <= r) lo = mid; else hi = mid - 1; }
-  const DcJob J = jobs[lo];
-  if (r >= J.jrow0 + J.nrows) return;           // a row of a job that failed validation
-  const double p = (double)pos[r];
-  const double* s = start + J.start0;
-  int a = 0, b = J.P;
-  while (a < b) { const int mid = (a + b) >> 1; if (s[mid] < p) a = mid + 1; else b = mid; }
-  rowidx[J.tab0 + (int64_t)(dataset[r] - 1) * J.P + a] = (int32_t)(r - J.jrow0);
-}
-
 // number of datasets that cover each position of each job (R/call.R:326 table(data$pos))
 __global__ void __launch_bounds__(256)
 k_dc_dscount(const DcJob* __restrict__ jobs, const int32_t* __restrict__ tile_job, const int32_t* __restrict__ tile_k0,
@@ -425,6 +394,9 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
   std::vector<int32_t> ent_job, ent_d, ptile_job, ptile_k0, gtile_group, gtile_k0, cond_of_group, slot_of_group;
   int64_t tab = 0;
   int32_t dmeta = 0;
+  std::vector<int32_t> h_dcond;      // condition of every dataset of every valid job (run table of the batch)
+  if (!R.rowstart.p || R.tab0.size() != R.jobs.size())
+    throw MlError(19, "call_differences needs a FAST fit (the row table of the unique-position leg)");
   for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
     const JobHost& j = R.jobs[jn];
     if (j.status) continue;
@@ -432,7 +404,10 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
     if (j.C < 2) throw MlError(14, "Needs at least two conditions!");
     if (ref_condition < 1 || ref_condition > j.C) throw MlError(15, "Invalid reference condition!");
     const int slot = (int)jobs.size();
-    jobs.push_back(DcJob{B.job_ptr[jn], R.start0[jn], tab, (int32_t)j.nrows, (int32_t)j.P, j.D, dmeta});
+    // tab0: the (dataset, parameter) -> row table the fit itself built (Result::rowstart); on the FAST leg a bin of a
+    // dataset holds exactly one row, so it is mdata's join of the raw rows onto the union of positions
+    jobs.push_back(DcJob{B.dev_row0[jn], R.start0[jn], R.tab0[jn], (int32_t)j.nrows, (int32_t)j.P, j.D, dmeta});
+    for (int d = 0; d < j.D; ++d) h_dcond.push_back(B.dcond[B.run0[jn] + d]);
     tab += (int64_t)j.D * j.P;
     dmeta += j.D;
     for (int d = 0; d < j.D; ++d) { ent_job.push_back(slot); ent_d.push_back(d); }
@@ -462,13 +437,10 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
   d_ent_job.upload(ent_job); d_ent_d.upload(ent_d); d_ptj.upload(ptile_job); d_ptk.upload(ptile_k0);
   d_gtg.upload(gtile_group); d_gtk.upload(gtile_k0); d_cond.upload(cond_of_group); d_slot.upload(slot_of_group);
   // ---- mdata ----------------------------------------------------------------------------------------------
-  DevBuf<int32_t> dcond(st, (size_t)std::max(1, dmeta)), rowidx(st, (size_t)tab),
-      dscount(st, (size_t)std::max<int64_t>(1, R.nstart));
-  ML_CUDA(cudaMemsetAsync(rowidx.p, 0xff, (size_t)tab * sizeof(int32_t), st));
-  ML_LAUNCH(eng, "k_dc_dataset_cond", k_dc_dataset_cond<<<cdiv((long long)ent_job.size(), 128), 128, 0, st>>>(
-      d_jobs.p, d_ent_job.p, d_ent_d.p, (int)ent_job.size(), B.dataset.p, B.condition.p, dcond.p));
-  ML_LAUNCH(eng, "k_dc_rowidx", k_dc_rowidx<<<cdiv(B.nrows, 256), 256, 0, st>>>(d_jobs.p, n_jobs, B.nrows, B.dataset.p,
-                                                                             B.pos.p, R.start.p, rowidx.p));
+  DevBuf<int32_t> dcond(st, (size_t)std::max(1, dmeta)), dscount(st, (size_t)std::max<int64_t>(1, R.nstart));
+  dcond.upload(h_dcond);
+  (void)tab;
+  const DevBuf<int32_t>& rowidx = R.rowstart;
   ML_LAUNCH(eng, "k_dc_dscount", k_dc_dscount<<<(int)ptile_job.size(), 256, 0, st>>>(d_jobs.p, d_ptj.p, d_ptk.p, rowidx.p, dscount.p));
   DevBuf<double> xcov(st, (size_t)R.npar), xbeta(st, (size_t)R.npar), rcov(st, (size_t)R.npar), rbeta(st, (size_t)R.npar);
   ML_LAUNCH(eng, "k_dc_pool", k_dc_pool<<<(int)gtile_group.size(), 256, 0, st>>>(

@@ -38,6 +38,13 @@ class FlsaPlan {
   void solve(const double* d_y, const double* d_w, double* d_beta, int post, double lambda1,
              double* d_sums, const std::vector<int32_t>* skip_series = nullptr);
 
+  // The same in two halves, so that the caller can read its own results back in the same synchronisation:
+  // solve_async enqueues everything and stages the solver's flags for the next stream_sync; solve_finish (after that
+  // synchronisation) returns true when a fallback path had to rewrite beta / the sums.
+  void solve_async(const double* d_y, const double* d_w, double* d_beta, int post, double lambda1,
+                   double* d_sums, const std::vector<int32_t>* skip_series = nullptr);
+  bool solve_finish();
+
   // debugging aid: copy the back-pointers of the last solve to the host (total_len doubles each)
   void debug_backpointers(double* h_tm, double* h_tp) const {
     d_tm_.download(h_tm, (size_t)total_len_);
@@ -80,10 +87,13 @@ class FlsaPlan {
   std::vector<SeriesDesc> h_series_;
   std::vector<int32_t> h_series_tile0_;
   Stats stats_;
+  struct Job { const double *y = nullptr, *w = nullptr; double* beta = nullptr; int post = 0; double lambda1 = 0;
+               double* sums = nullptr; bool skip = false, pending = false; } job_;   // arguments of the solve in flight
+  std::vector<int32_t> h_flags_, h_skip_;
+  int32_t h_counters_[4] = {0, 0, 0, 0};
+  bool chain_launched_ = false;
+  void backward();
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);
 };
-
-// debugging aid: num / den through the chain walker's split division (reciprocal prepared first) and plainly
-void debug_divide(Engine& eng, int64_t n, const double* num, const double* den, double* out_split, double* out_plain);
 
 }  // namespace ml

@@ -336,35 +336,45 @@ ML_HD bool flsa_main(const SeriesDesc& S, const ChunkDesc& c, const double* __re
   return true;
 }
 
-// ---- start-to-end DP with the knot window in caller-provided scratch of 2n doubles x 3 -------
-// (the reference's own memory layout, gfl_tf.c:233-240); used when a window outgrows KNOT_CAP.
-ML_HD void flsa_sequential_forward(int n, const double* __restrict__ y, const double* __restrict__ w,
-                                   double lam, double* __restrict__ x, double* __restrict__ a,
-                                   double* __restrict__ b, double* __restrict__ tm,
-                                   double* __restrict__ tp, double* beta_last) {
-  int l = n - 1, r = n;
-  tm[0] = -lam / w[0] + y[0];
-  tp[0] = lam / w[0] + y[0];
-  x[l] = tm[0]; x[r] = tp[0];
-  a[l] = w[0];  b[l] = -w[0] * y[0] + lam;
-  a[r] = -w[0]; b[r] = w[0] * y[0] + lam;
-  for (int k = 1; k < n - 1; ++k) {
-    const double wk = w[k], yk = y[k];
-    double alo = wk, blo = -wk * yk - lam, ahi = -wk, bhi = wk * yk - lam;
-    int lo = l, hi = r;
-    while (lo <= r) { if (alo * x[lo] + blo > -lam) break; alo += a[lo]; blo += b[lo]; ++lo; }
-    while (hi >= lo) { if (-ahi * x[hi] - bhi < lam) break; ahi += a[hi]; bhi += b[hi]; --hi; }
-    tm[k] = (-lam - blo) / alo;
-    l = lo - 1; x[l] = tm[k];
-    tp[k] = (lam + bhi) / (-ahi);
-    r = hi + 1; x[r] = tp[k];
-    a[l] = alo; b[l] = blo + lam;
-    a[r] = ahi; b[r] = bhi + lam;
+// ---- start-to-end DP with the knot window in a global-memory ring -----------------------------
+// For series whose window outgrows KNOT_CAP (monotone stretches: up to n + 1 knots).  The ring lives in
+// caller-provided scratch of 3 * cap doubles, cap a power of two >= n + 2, so it can never overflow; the steps are
+// the very dp_step / dp_last of the chunked path.
+struct GlobalRing {
+  static constexpr int CAP = 0x7fffffff;   // never the limit: the scratch is sized for the series
+  double* base;
+  int mask;                                // capacity - 1
+  ML_HD double x(int i) const { return base[i & mask]; }
+  ML_HD double a(int i) const { return base[(int64_t)(mask + 1) + (i & mask)]; }
+  ML_HD double b(int i) const { return base[2 * (int64_t)(mask + 1) + (i & mask)]; }
+  ML_HD void set(int i, double x_, double a_, double b_) {
+    const int k = i & mask;
+    base[k] = x_;
+    base[(int64_t)(mask + 1) + k] = a_;
+    base[2 * (int64_t)(mask + 1) + k] = b_;
   }
-  const double wk = w[n - 1], yk = y[n - 1];
-  double alo = wk, blo = -wk * yk - lam;
-  for (int lo = l; lo <= r; ++lo) { if (alo * x[lo] + blo > 0) break; alo += a[lo]; blo += b[lo]; }
-  *beta_last = -blo / alo;
+};
+ML_HD int64_t flsa_sequential_cap(int n) {
+  int64_t cap = 4;
+  while (cap < (int64_t)n + 2) cap <<= 1;
+  return cap;
+}
+ML_HD void flsa_sequential_forward(int n, const double* __restrict__ y, const double* __restrict__ w, double lam,
+                                   double* __restrict__ scratch /* 3 * flsa_sequential_cap(n) */,
+                                   double* __restrict__ tm, double* __restrict__ tp, double* beta_last) {
+  Knots<GlobalRing> q;
+  q.ring.base = scratch;
+  q.ring.mask = (int)(flsa_sequential_cap(n) - 1);
+  double t1, t2;
+  knots_init_first(q, y[0], w[0], lam, t1, t2);
+  tm[0] = t1;
+  tp[0] = t2;
+  for (int k = 1; k < n - 1; ++k) {
+    dp_step(q, y[k], w[k], lam, t1, t2);
+    tm[k] = t1;
+    tp[k] = t2;
+  }
+  *beta_last = dp_last(q, y[n - 1], w[n - 1], lam);
 }
 
 // ---- back-substitution as a clamp monoid ----------------------------------------------------

@@ -812,5 +812,6 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
 #include "pmdsplit.inc.cuh"
 #include "pmdcall.inc.cuh"
 #include "pmdstatus.inc.cuh"
+#include "regions.inc.cuh"
 
 }  // namespace ml

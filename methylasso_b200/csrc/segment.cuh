@@ -144,6 +144,23 @@ struct FinalDev {
 };
 void call_pmd_status_device(Engine& eng, MergedDev& M, const PmdCallDev& pmd, const int8_t* d_row_adm, FinalDev& out);
 
+// The tables segment_methylation returns (R/call.R:214-220, columns of :241-243), gathered on the device:
+// lmr_umr_valley = seg_call with PMD.status (drop: rows with a category only), pmd = pmd_call (drop: "PMD" rows only).
+// category: 0 NA, 1 LMR, 2 UMR, 3 UMR-DMV; pmd_status: -1 NA, 0 other, 1 PMD; pmd category: 1 PMD, 0 other.
+struct RegionTables {
+  int64_t n_seg = 0, n_pmd = 0;
+  DevBuf<int32_t> s_job, s_condition, s_segment_id, s_num_cpgs;
+  DevBuf<uint32_t> s_start, s_end;
+  DevBuf<double> s_width, s_beta, s_coverage, s_pseudoweight, s_std;
+  DevBuf<int8_t> s_category, s_pmd_status;
+  DevBuf<int32_t> p_job, p_condition, p_segment_id, p_num_cpgs;
+  DevBuf<int8_t> p_category;
+  DevBuf<uint32_t> p_start, p_end;
+  DevBuf<double> p_width, p_fused_std, p_beta, p_std;
+};
+void region_tables_device(Engine& eng, const CallTable& ct, const ValleyTable& val, const MergedDev& M, const PmdCallDev& pmd,
+                          const FinalDev& F, int drop, RegionTables& out);
+
 int64_t call_table_from_estimates(Engine& eng, const std::vector<SegGroup>& groups, const SegDeviceOut& seg,
                                   const void* d_pos, int pos_f64, const double* d_betahat, const double* d_pw,
                                   double max_distance, CallTable& out);

@@ -1,0 +1,201 @@
+"""Genome-wide calls from HOST buffers through several engines of one GPU.
+
+What `MethyLasso.R` does for one condition (Part 1, MethyLasso.R:559-592) is
+    ret <- signal_detection_fast(data, lambda2 = 25)       # R/genome_wide.R:64-78: one native call per chromosome
+    seg <- segment_methylation(data, ret, ...)             # R/call.R:229-244: the rule engine, per chromosome
+and for two conditions (Part 2, :453-469)
+    ret <- difference_detection_fast(data, ref, ...)       # R/genome_wide.R:121-135, R/fast_diff.R:12-30
+    dmr <- call_differences(data, ret, ...)                # R/call.R:348-365
+Here the chromosomes of such a call are split into groups; every group has an engine (a CUDA stream and a memory
+pool) and a host thread, so that the upload of one group, the kernels of another and the download of a third overlap
+(`api.EnginePool`).  Jobs never interact, so the result does not depend on the grouping.
+
+The class below is the one code path behind `bench.py`'s end-to-end numbers AND `tests/test_gpu_pipeline.py`, which
+checks its outputs against single-engine calls and against the CPU restatement of the reference.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import api
+from ._native import MlParams
+
+_INPUT = ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")
+
+
+def _pin(arr, lib):
+    out = api.pinned_empty(arr.size, arr.dtype, lib)
+    out[:] = arr
+    return out
+
+
+class GenomePipeline:
+    """The jobs (chromosomes) of one data set, split into groups for `n_engines` engines of one GPU.
+
+    job_ptr / cols: the batch as `synth.concat_jobs` or `api.split_by_chr` give it.  pin=True copies every group's
+    input columns into page-locked memory once (the host buffers the calls below read from)."""
+
+    def __init__(self, job_ptr, cols, n_engines=6, device=-1, lambda2=25.0, tol_val=0.01, edge_share=None, pin=True,
+                 host_threads=None):
+        self.pool = api.EnginePool(max(1, int(n_engines)), device)
+        self.lib = self.pool.engines[0].lib
+        self.params = MlParams(float(lambda2), float(lambda2) + 1, 0.0, float(tol_val), 50.0, 1.0, 1, 1, 1, api.MODEL_FAST, 0, 0)
+        self.tol_val = float(tol_val)
+        self.njobs = int(np.asarray(job_ptr).size - 1)
+        self.groups = []
+        for jobs, gptr, gcols in api.split_jobs(job_ptr, cols, len(self.pool.engines), edge_share=edge_share):
+            gcols = {k: np.ascontiguousarray(gcols[k], np.int32) for k in _INPUT}
+            if pin:
+                gcols = {k: _pin(v, self.lib) for k, v in gcols.items()}
+            self.groups.append((np.asarray(jobs, np.int32), np.ascontiguousarray(gptr, np.int64), gcols))
+        if host_threads:
+            for e in self.pool.engines:
+                e.set("host_threads", int(host_threads))
+        self.timeline = []
+        self._t0 = 0.0
+
+    # ---- bytes that cross PCIe per call (from the arrays themselves) ----------------------------------------------
+    def h2d_bytes(self):
+        """pos / Nmeth / coverage of every row: the three factor columns are reduced to a run table on the host."""
+        return int(sum(3 * 4 * int(g[1][-1]) for g in self.groups))
+
+    def close(self):
+        self.pool.close()
+
+    def warm_pools(self, percent=25):
+        for e in self.pool.engines:
+            e.set("pool_headroom_percent", int(percent))
+
+    def _stamp(self, marks):
+        self.timeline.append([round((t - self._t0) * 1e3, 2) for t in marks])
+
+    def _run(self, fn):
+        self.timeline = []
+        self._t0 = time.perf_counter()
+        return self.pool.map(fn, self.groups)
+
+    # ---- Part 1 of the CLI: region tables only --------------------------------------------------------------------
+    def segment_methylation(self, max_distance=500.0, drop=True, **rule_kw):
+        """signal_detection_fast + segment_methylation for all chromosomes: host columns in, the two region tables
+        out (`lmr_umr_valley`, `pmd` as `api.Result.segment_methylation_tables` returns them, `job` = index of the
+        chromosome in the batch, rows ordered by chromosome).  Per group: ml_batch_upload, ml_batch_detect (mu not
+        stored: nothing in the reference's R layer reads it), ml_result_segment_methylation."""
+        pool = self.pool
+
+        def run_group(eng, grp):
+            jobs, gptr, gcols = grp
+            t = [time.perf_counter()]
+            eng.set("want_mu", 0)
+            with pool.h2d_turn:
+                t.append(time.perf_counter())
+                bt = eng.upload(gptr, gcols)
+            t.append(time.perf_counter())
+            res = eng.detect(bt, self.params)
+            t.append(time.perf_counter())
+            seg, pmd = res.segment_methylation_tables(self.tol_val, max_distance, drop=drop, reuse_pinned=True, **rule_kw)
+            status = res.status.copy()
+            res.free()
+            bt.free()
+            t.append(time.perf_counter())
+            self._stamp(t)
+            return jobs, seg, pmd, status
+
+        outs = self._run(run_group)
+        return self._merge_regions(outs)
+
+    def _merge_regions(self, outs):
+        segs, pmds = [], []
+        status = np.zeros(self.njobs, np.int32)
+        for jobs, seg, pmd, st in outs:
+            status[jobs] = st
+            segs.append({k: (jobs[v] if k == "job" else v) for k, v in seg.items()})
+            pmds.append({k: (jobs[v] if k == "job" else v) for k, v in pmd.items()})
+        out = []
+        for parts in (segs, pmds):
+            cat = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+            order = np.argsort(cat["job"], kind="stable")
+            out.append({k: v[order] for k, v in cat.items()})
+        return out[0], out[1], status
+
+    # ---- the reference's own return values: per-CpG tables too ------------------------------------------------------
+    def signal_detection_fast(self, max_distance=500.0, pmd_lambda2=1000.0, want_mu=True, buffers=None):
+        """signal_detection_fast with everything the reference's list holds (mu, offset, the estimates table) downloaded
+        into page-locked buffers, plus the segment table, the call table and the PMD candidate segments of every
+        chromosome (R/call.R:53-95).  Returns one dict per group: jobs, mu, offset, estimates, segments, call_table,
+        pmd_segments.  `buffers` (from `output_buffers`) are reused from call to call."""
+        pool = self.pool
+        bufs = buffers or self.output_buffers(want_mu)
+
+        def run_group(eng, item):
+            grp, o = item
+            jobs, gptr, gcols = grp
+            t = [time.perf_counter()]
+            eng.set("want_mu", 1 if want_mu else 0)
+            with pool.h2d_turn:
+                t.append(time.perf_counter())
+                bt = eng.upload(gptr, gcols)
+            t.append(time.perf_counter())
+            res = eng.detect(bt, self.params)
+            bt.free()
+            t.append(time.perf_counter())
+            # D2H of mu / estimates is enqueued on the copy stream and overlaps the segmentation kernels
+            res.copy_all_async(o["mu"] if want_mu else None, o["offset"], o["estimate_id"], o["start"], o["beta"], o["betahat"],
+                               o["pseudoweight"])
+            res.segments_count(self.tol_val)                      # resident; the tables are fetched after the big copies
+            res.call_table(self.tol_val, max_distance, fetch=False)
+            res.call_pmd_segments(self.tol_val, max_distance, pmd_lambda2, fetch=False)
+            t.append(time.perf_counter())
+            eng.synchronize()
+            seg = res.segments(self.tol_val, reuse_pinned=True)    # the engine's own page-locked buffers
+            call = res.call_table(self.tol_val, max_distance, reuse_pinned=True)
+            pmd = res.call_pmd_segments(self.tol_val, max_distance, pmd_lambda2)
+            status = res.status.copy()
+            res.free()
+            t.append(time.perf_counter())
+            self._stamp(t)
+            est = {k: o[k] for k in ("estimate_id", "start", "beta", "betahat", "pseudoweight")}
+            return dict(jobs=jobs, mu=o["mu"] if want_mu else None, offset=o["offset"], estimates=est, segments=seg,
+                        call_table=call, pmd_segments=pmd, status=status)
+
+        self.timeline = []
+        self._t0 = time.perf_counter()
+        return pool.map(run_group, list(zip(self.groups, bufs)))
+
+    def output_buffers(self, want_mu=True):
+        """Page-locked output buffers of signal_detection_fast, sized by one untimed fit per group."""
+        if getattr(self, "_bufs", None) is not None and self._bufs_mu == want_mu:
+            return self._bufs
+
+        def size_group(eng, grp):
+            jobs, gptr, gcols = grp
+            res = eng.detect_batch(gptr, gcols, self.params)
+            sizes = [res.sizes(j) for j in range(res.njobs)]
+            res.free()
+            ep = int(sum(s[1] * s[2] for s in sizes if s[4] == 0))
+            nd = int(sum(s[3] for s in sizes if s[4] == 0))
+            nr = int(sum(s[0] for s in sizes if s[4] == 0))
+            o = dict(offset=api.pinned_empty(max(nd, 1), np.float64, self.lib),
+                     estimate_id=api.pinned_empty(max(ep, 1), np.int32, self.lib),
+                     **{k: api.pinned_empty(max(ep, 1), np.float64, self.lib) for k in ("start", "beta", "betahat", "pseudoweight")})
+            o["mu"] = api.pinned_empty(max(nr, 1), np.float64, self.lib) if want_mu else None
+            o["n"] = (nr, ep, nd)
+            return o
+        self._bufs = self.pool.map(size_group, self.groups)
+        self._bufs_mu = want_mu
+        return self._bufs
+
+    @staticmethod
+    def d2h_bytes_regions(seg, pmd):
+        return int(sum(v.nbytes for v in seg.values()) + sum(v.nbytes for v in pmd.values()))
+
+    @staticmethod
+    def d2h_bytes_full(outs):
+        total = 0
+        for o in outs:
+            nr, ep, nd = 0, 0, 0
+            total += (o["mu"].nbytes if o["mu"] is not None else 0) + o["offset"].nbytes
+            total += sum(v.nbytes for v in o["estimates"].values())
+            total += sum(v.nbytes for k in ("segments", "call_table", "pmd_segments") for v in o[k].values())
+        return int(total)

@@ -79,8 +79,8 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   double blast;
   if (ovf) {
     stats[4] = std::max<long long>(stats[4], 1);
-    std::vector<double> x(2 * (size_t)n), a(2 * (size_t)n), b(2 * (size_t)n);
-    flsa_sequential_forward(n, y, w, lam, x.data(), a.data(), b.data(), tm, tp, &blast);
+    std::vector<double> scratch(3 * (size_t)flsa_sequential_cap(n));
+    flsa_sequential_forward(n, y, w, lam, scratch.data(), tm, tp, &blast);
   } else {
     Knots<BigRing> q; knots_load(q, st.back());
     blast = dp_last(q, y[n - 1], w[n - 1], lam);
