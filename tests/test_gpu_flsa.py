@@ -172,32 +172,3 @@ def test_hypothesis_kkt_and_oracle(engine, oracle):
         if not zeros_allowed and ok.all() and np.all(np.abs(ref) < 35):
             assert kkt_residual(y, w, got, lam) < 1e-6 * max(1.0, float(np.max(w)) * float(np.max(np.abs(y))) / lam)
     check()
-
-
-def test_split_division_is_the_ieee_division(engine):
-    """The chain walker divides with a reciprocal prepared in advance (flsa.cu: rcp_refine / div_with_rcp, the
-    compiler's own division sequence cut in two).  It must return the bits of the plain IEEE division for every
-    operand pair, including zeros, infinities, NaN, subnormals and the extremes of the exponent range."""
-    import ctypes as C
-    rng = np.random.default_rng(123)
-    n = 2_000_000
-    num = rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, n)
-    den = rng.normal(size=n) * 10.0 ** rng.integers(-12, 12, n)
-    # methylation-like operands: integer counts, lambda offsets
-    k = n // 4
-    num[:k] = -25.0 - rng.integers(-3000, 3000, k).astype(float)
-    den[:k] = rng.integers(1, 200, k).astype(float) * rng.choice([-1.0, 1.0], k)
-    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308,
-                        -1.7976931348623157e308, 1.0, -1.0, 3.0, 1e-300, 1e300, 6.6e-37, 1.4e-39, 2.0 ** -1022, 2.0 ** 1023])
-    gn, gd = np.meshgrid(special, special)
-    num = np.concatenate([num, gn.ravel()])
-    den = np.concatenate([den, gd.ravel()])
-    a, b = np.empty_like(num), np.empty_like(num)
-    p = lambda v: v.ctypes.data_as(C.c_void_p)
-    engine._check(engine.lib.ml_debug_divide(engine.h, num.size, p(num), p(den), p(a), p(b)))
-    with np.errstate(all="ignore"):
-        host = num / den
-    assert np.array_equal(a.view(np.uint64)[~np.isnan(b)], b.view(np.uint64)[~np.isnan(b)])
-    assert np.array_equal(np.isnan(a), np.isnan(b))
-    ok = ~np.isnan(host)
-    assert np.array_equal(b.view(np.uint64)[ok], host.view(np.uint64)[ok])      # and the device's division is IEEE
