@@ -51,35 +51,34 @@ class FlsaPlan {
     d_tp_.download(h_tp, (size_t)total_len_);
     stream_sync(eng_.stream);
   }
-  void debug_chunk_states(std::vector<ChunkState>& out) const {
-    out.resize((size_t)n_chunks_);
-    d_states_.download(out.data(), (size_t)n_chunks_);
-    stream_sync(eng_.stream);
-  }
   int n_series() const { return (int)series_.size(); }
   int n_chunks() const { return n_chunks_; }
   int n_tiles() const { return n_tiles_; }
   int chunk_len() const { return chunk_; }
   int warm_len() const { return warm_; }
   // counters of the last solve (read back with the overflow flags)
-  struct Stats { int chunks_unresolved_after_a = 0, series_fallback = 0; };
+  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0; };
   Stats last_stats() const { return stats_; }
 
  private:
   Engine& eng_;
   std::vector<FlsaSeries> series_;
   int64_t total_len_;
-  int stats_open_after_main_ = 0;
+  int64_t total_steps_ = 0;         // DP steps of all chunks
   int chunk_ = 0, warm_ = 0, n_chunks_ = 0, n_tiles_ = 0, max_tiles_per_series_ = 0;
   DevBuf<SeriesDesc> d_series_;
   DevBuf<ChunkDesc> d_chunks_;
-  DevBuf<ChunkState> d_states_;
+  DevBuf<int32_t> d_win_i32_;       // saved windows of the speculative runs (SpecWindows, flsa_core.cuh)
+  DevBuf<double> d_win_f64_;
+  DevBuf<int8_t> d_verdict_;        // per chunk: 1 = verified
+  DevBuf<int32_t> d_heads_;         // chain heads (chunks the walkers start from)
+  SpecWindows win_{};
   DevBuf<TileDesc> d_tiles_;
   DevBuf<int32_t> d_series_tile0_;  // first tile of each series (+1 sentinel)
   DevBuf<double> d_tm_, d_tp_;
   DevBuf<double> d_beta_last_;
   DevBuf<int32_t> d_flags_;         // per series: bit0 overflow, bit1 clamp-order violation
-  DevBuf<int32_t> d_counters_;      // [0] chunks not done after pass A
+  DevBuf<int32_t> d_counters_;      // [0] chunks verified, [1] chunks redone by the walkers, [2] longest chain, [3] chains
   DevBuf<Clamp> d_tile_agg_;
   DevBuf<double> d_tile_in_;
   DevBuf<double> d_tile_sums_;      // 2 per tile
@@ -91,7 +90,6 @@ class FlsaPlan {
                double* sums = nullptr; bool skip = false, pending = false; } job_;   // arguments of the solve in flight
   std::vector<int32_t> h_flags_, h_skip_;
   int32_t h_counters_[4] = {0, 0, 0, 0};
-  bool chain_launched_ = false;
   void backward();
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);
 };

@@ -12,15 +12,19 @@
 //    the knot window (the piecewise-linear message) in a small ring.
 //  * A chunk that does not start at the head of its series does not know the incoming message.
 //    The message is a non-decreasing function confined to [-lam, +lam] and the DP update is
-//    monotone in it, so the thread runs TWO copies of the DP through a warm-up stretch, one from
-//    the message "-lam everywhere" and one from "+lam everywhere".  The true state is sandwiched
-//    between them; when their knot windows become bit-identical the state is pinned and the
-//    thread continues with one copy, now exact.  (Measured on WGBS-like series: the windows
-//    coalesce after a few hundred steps at lam=25 and the coalesced window was bit-identical to
-//    the sequential run's window in every case — scripts/experiments/coalesce.py.)
-//  * A chunk whose warm-up did not coalesce takes its start state from the (exact) end state its
-//    left neighbour saved, or retries with a warm-up eight times longer in the next round; what
-//    is still open after the last round is finished in order by one lane per series.
+//    monotone in it, so a copy of the DP started from the message "-lam everywhere" stays below
+//    the true state and one started from "+lam everywhere" stays above it.  Every chunk is run
+//    SPECULATIVELY by one thread: through a warm-up stretch in front of the chunk and then through
+//    the chunk itself, from the lower bound if the chunk's index in its series is even and from the
+//    upper bound if it is odd.  The thread saves its knot window S just before the chunk's first
+//    step and its window E after the chunk's last step.
+//  * Chunk c is VERIFIED when S_c is bit-identical to E_{c-1}: the two are copies from opposite
+//    bounds, the true state lies between them, so both ARE the true state - everything chunk c
+//    computed from S_c on is exact, and so is the end state of chunk c-1.  (Measured on WGBS-like
+//    series: windows started 512 steps back coincide for ~94 % of the chunks at lam=25.)  This is
+//    the sandwich argument with ONE warm-up copy per chunk: the second copy is the neighbour's run.
+//  * Chunks that are not verified form chains; a chain is redone in order from the exact end state
+//    of the verified chunk on its left (flsa_chain_kernel), one lane pair per chain.
 //  * The back-substitution beta_k = clamp(beta_{k+1}; tm_k, tp_k) is a composition of clamps,
 //    which is again a clamp: a reverse parallel scan with min/max only (exact).
 #pragma once
@@ -39,13 +43,10 @@ enum : int32_t {
   SERIES_SEQUENTIAL = 2,  // lam < 0 / NaN: the sandwich does not apply; one chunk, run start-to-end
 };
 enum : int32_t {
-  CHUNK_END_VALID = 1,   // end-of-chunk knot window saved and exact
-  CHUNK_DONE = 2,        // every tm/tp of the chunk written
-  CHUNK_OVERFLOW = 4,    // knot window outgrew KNOT_CAP: series goes to the global-scratch kernel
-  CHUNK_START_VALID = 16, // the saved window is the exact state just BEFORE the chunk's first step
-  CHUNK_CLAIMED = 32,    // a chain walker (flsa_chain_kernel) has taken the chunk in this launch
-  CHUNK_IRREGULAR = 8,   // some tm_k > tp_k (rounding on absurd inputs): clamps do not compose, the
-                         // series' back-substitution is redone element by element
+  SPEC_EXACT = 1,      // the run started at the head of its series: exact by construction, nothing to verify
+  SPEC_OVERFLOW = 2,   // the window outgrew the speculative ring: S / E are not usable, the chunk is redone by a walker
+  SPEC_IRREGULAR = 4,  // some tm_k > tp_k (rounding on absurd inputs): clamps do not compose, the
+                       // series' back-substitution is redone element by element
 };
 
 struct SeriesDesc {
@@ -62,15 +63,20 @@ struct SeriesDesc {
 struct ChunkDesc {
   int32_t series;
   int32_t kb, ke;  // DP steps [kb, ke) of the series; step k folds element k, 1 <= k <= n-2
-  int32_t pad;
+  int32_t idx;     // index of the chunk within its series (its parity chooses the bound the speculation starts from)
 };
 
-struct ChunkState {
-  int32_t status;
-  int32_t count;          // knots saved
-  int32_t reserved;
-  int32_t pad;            // snapshot of status taken at the start of a launch (neighbour reads)
-  double x[KNOT_CAP], a[KNOT_CAP], b[KNOT_CAP];
+// The saved windows of all chunks, struct-of-arrays [field][slot][chunk] (consecutive threads = consecutive chunks write
+// consecutive addresses).  S = window just before step kb, E = window after step ke - 1.
+#ifndef ML_SPEC_CAP
+#define ML_SPEC_CAP 16
+#endif
+constexpr int SPEC_CAP = ML_SPEC_CAP;   // knots a speculative run may hold (ring in shared memory) and save
+struct SpecWindows {
+  int32_t* status;             // SPEC_* per chunk
+  int32_t *s_count, *e_count;  // knots saved (0: none)
+  double *sx, *sa, *sb, *ex, *ea, *eb;
+  int64_t stride;              // number of chunks
 };
 
 // ---- knot window -------------------------------------------------------------------------
@@ -209,130 +215,239 @@ ML_HD double dp_last(const Knots<Ring>& q, double y, double w, double lam) {
   return -blo / alo;
 }
 
+// ---- the same step, arranged for a short dependent chain -------------------------------------------------------------
+// One thread carries BOTH scans of a step.  Measured on B200 (scripts/flsa_latency.py): the plain dp_step above costs a
+// lone thread ~1400 cycles per step - two scan loops one after the other, every comparison behind a shared-memory load
+// and its address arithmetic, two divisions behind their own branches.  Here
+//   * the knot at each end of the window is also kept in registers (it is the knot the previous step created: the first
+//     comparison of each scan needs no load), and the second knot of each side is loaded before it is known to be needed;
+//   * the two scans advance in the same basic block, one knot per side per round (independent chains: they overlap);
+//   * the two quotients are formed together, the zero-numerator shortcut (knot_div) as selects instead of branches.
+// The arithmetic of each side - which products, sums and quotients, in which order - is dp_step's, so the results are
+// the same bits (tests/test_emu.py runs this very function on the CPU against the reference DP).
 template <class Ring>
-ML_HD bool knots_same(const Knots<Ring>& p, const Knots<Ring>& q) {
-  if (p.r - p.l != q.r - q.l) return false;
-  const int cnt = p.r - p.l + 1;
+struct KnotsC {
+  Ring ring;
+  int l, r;                    // logical indices of the leftmost / rightmost live knot
+  double xl, al, bl;           // == ring[l] whenever l <= r
+  double xr, ar, br;           // == ring[r]
+};
+template <class Ring>
+ML_HD void knots_cache(KnotsC<Ring>& q) {
+  q.xl = q.ring.x(q.l); q.al = q.ring.a(q.l); q.bl = q.ring.b(q.l);
+  q.xr = q.ring.x(q.r); q.ar = q.ring.a(q.r); q.br = q.ring.b(q.r);
+}
+template <class Ring>
+ML_HD void knots_init_first(KnotsC<Ring>& q, double y0, double w0, double lam, double& tm0, double& tp0) {
+  q.l = 0;
+  q.r = 1;
+  tm0 = -lam / w0 + y0;
+  tp0 = lam / w0 + y0;
+  const double bl = -w0 * y0 + lam, br = w0 * y0 + lam;
+  q.ring.set(0, tm0, w0, bl);
+  q.ring.set(1, tp0, -w0, br);
+  knots_cache(q);
+}
+template <class Ring>
+ML_HD void knots_init_bound(KnotsC<Ring>& q, int sign, double lam) {
+  q.l = 0;
+  q.r = 0;
+  q.ring.set(0, sign < 0 ? HUGE_VAL : -HUGE_VAL, 0.0, 2 * lam);
+  knots_cache(q);
+}
+
+// num / a with the zero-numerator shortcut of knot_div as selects: the division never sees a zero numerator (so it
+// stays on its fast path) and two quotients can be formed side by side
+ML_HD double knot_div_sel(double num, double a) {
+#ifdef __CUDA_ARCH__
+  const bool z = num == 0.0 && a != 0.0 && a == a;
+  const double qn = (z ? 1.0 : num) / a;
+  const double zero = __longlong_as_double((__double_as_longlong(num) ^ __double_as_longlong(a)) & (long long)0x8000000000000000ull);
+  return z ? zero : qn;
+#else
+  return num / a;
+#endif
+}
+
+template <class Ring>
+ML_HD bool dp_step_c(KnotsC<Ring>& q, double y, double w, double lam, double& tm, double& tp) {
+  const double wy = w * y;
+  double al = w, bl = -wy - lam;           // gfl_tf.c:286-287 (seeds of the incoming element)
+  double ar = -w, br = wy - lam;           // :288-289
+  const int l = q.l, r = q.r;
+  const double nlam = -lam;
+  // second knot of each side, on its way before the first comparisons are known
+  double x2l = 0.0, a2l = 0.0, b2l = 0.0, x2r = 0.0, a2r = 0.0, b2r = 0.0;
+  if (l < r) {
+    x2l = q.ring.x(l + 1); a2l = q.ring.a(l + 1); b2l = q.ring.b(l + 1);
+    x2r = q.ring.x(r - 1); a2r = q.ring.a(r - 1); b2r = q.ring.b(r - 1);
+  }
+  int i = l, j = r;
+  // first knots: registers
+  bool goL = l <= r && !(al * q.xl + bl > nlam);
+  bool goR = l <= r && !(ar * q.xr + br > nlam);
+  if (goL) { al += q.al; bl += q.bl; i = l + 1; }
+  if (goR) { ar += q.ar; br += q.br; j = r - 1; }
+  // second knots: already loaded
+  goL = goL && i <= r && !(al * x2l + bl > nlam);
+  goR = goR && j >= l && !(ar * x2r + br > nlam);
+  if (goL) { al += a2l; bl += b2l; ++i; }
+  if (goR) { ar += a2r; br += b2r; --j; }
+  // the rest from the ring, one knot per side per round
+  while (goL || goR) {
+    const bool inL = goL && i <= r, inR = goR && j >= l;
+    double xa = 0.0, aa = 0.0, ba = 0.0, xb = 0.0, ab = 0.0, bb = 0.0;
+    if (inL) { xa = q.ring.x(i); aa = q.ring.a(i); ba = q.ring.b(i); }
+    if (inR) { xb = q.ring.x(j); ab = q.ring.a(j); bb = q.ring.b(j); }
+    goL = inL && !(al * xa + bl > nlam);
+    goR = inR && !(ar * xb + br > nlam);
+    if (goL) { al += aa; bl += ba; ++i; }
+    if (goR) { ar += ab; br += bb; --j; }
+  }
+  const int lo = i;
+  int hi = j;
+  if (hi < lo - 1) {                       // both scans crossed: redo the right one with gfl_tf.c:264's bound
+    ar = -w;
+    br = wy - lam;
+    hi = side_scan(q.ring, r, -1, lo, ar, br, lam);
+  }
+  tm = knot_div_sel(nlam - bl, al);        // :272
+  tp = knot_div_sel(nlam - br, ar);        // :277, (lam + bhi) / (-ahi) bit for bit
+  const int nl = lo - 1, nr = hi + 1;
+  if (nr - nl + 1 > Ring::CAP) return false;
+  const double bls = bl + lam, brs = br + lam;
+  q.ring.set(nl, tm, al, bls);             // :282-285
+  q.ring.set(nr, tp, ar, brs);
+  q.l = nl;
+  q.r = nr;
+  q.xl = tm; q.al = al; q.bl = bls;
+  q.xr = tp; q.ar = ar; q.br = brs;
+  return true;
+}
+template <class Ring>
+ML_HD double dp_last(const KnotsC<Ring>& q, double y, double w, double lam) {
+  double alo = w, blo = -w * y - lam;
+  for (int lo = q.l; lo <= q.r; ++lo) {
+    if (alo * q.ring.x(lo) + blo > 0) break;
+    alo += q.ring.a(lo);
+    blo += q.ring.b(lo);
+  }
+  return -blo / alo;
+}
+
+// ---- saved windows ------------------------------------------------------------------------------
+template <class K>
+ML_HD void window_save(const K& q, int32_t* count, double* x, double* a, double* b, int64_t stride, int64_t c) {
+  const int cnt = q.r - q.l + 1;
   for (int k = 0; k < cnt; ++k) {
-    if (f64_bits(p.ring.x(p.l + k)) != f64_bits(q.ring.x(q.l + k)) ||
-        f64_bits(p.ring.a(p.l + k)) != f64_bits(q.ring.a(q.l + k)) ||
-        f64_bits(p.ring.b(p.l + k)) != f64_bits(q.ring.b(q.l + k)))
+    x[k * stride + c] = q.ring.x(q.l + k);
+    a[k * stride + c] = q.ring.a(q.l + k);
+    b[k * stride + c] = q.ring.b(q.l + k);
+  }
+  count[c] = cnt;
+}
+// the end window of chunk c into a ring (always fits: SPEC_CAP <= every ring's capacity)
+template <class Ring>
+ML_HD void window_load_end(KnotsC<Ring>& q, const SpecWindows& W, int64_t c) {
+  const int cnt = W.e_count[c];
+  for (int k = 0; k < cnt; ++k) q.ring.set(k, W.ex[k * W.stride + c], W.ea[k * W.stride + c], W.eb[k * W.stride + c]);
+  q.l = 0;
+  q.r = cnt - 1;
+  knots_cache(q);
+}
+// S of chunk c bit-identical to E of chunk c - 1 (both saved by speculative runs that did not overflow)
+ML_HD bool windows_meet(const SpecWindows& W, int64_t c) {
+  if ((W.status[c] | W.status[c - 1]) & SPEC_OVERFLOW) return false;
+  const int cnt = W.s_count[c];
+  if (cnt <= 0 || cnt != W.e_count[c - 1]) return false;
+  for (int k = 0; k < cnt; ++k) {
+    const int64_t is = k * W.stride + c, ie = is - 1;
+    if (f64_bits(W.sx[is]) != f64_bits(W.ex[ie]) || f64_bits(W.sa[is]) != f64_bits(W.ea[ie]) ||
+        f64_bits(W.sb[is]) != f64_bits(W.eb[ie]))
       return false;
   }
   return true;
 }
-
-template <class Ring>
-ML_HD void knots_save(const Knots<Ring>& q, ChunkState& st) {
-  const int cnt = q.r - q.l + 1;   // <= KNOT_CAP: callers only instantiate rings up to KNOT_CAP
-  for (int k = 0; k < cnt; ++k) {
-    st.x[k] = q.ring.x(q.l + k);
-    st.a[k] = q.ring.a(q.l + k);
-    st.b[k] = q.ring.b(q.l + k);
-  }
-  st.count = cnt;
+// Verdict on chunk c of a series whose first chunk is c0 (chunks of a series are consecutive): its own outputs are
+// exact when its run was exact by construction or its start window met the left neighbour's end window.
+ML_HD bool chunk_verified(const SpecWindows& W, int64_t c, int64_t c0) {
+  if (W.status[c] & SPEC_OVERFLOW) return false;
+  if (W.status[c] & SPEC_EXACT) return true;
+  return c > c0 && windows_meet(W, c);
 }
 
-// false if the saved window does not fit this ring
+// ---- the speculative run of one chunk (scalar statement; flsa_spec_kernel in flsa.cu is the same procedure with the
+// loads of y / w issued ahead and a trip count that is uniform across the warp) ---------------------------------------
+// Steps [max(kb - warm, 1), ke): from the exact first-element window when the stretch reaches the head of the series
+// (SPEC_EXACT), else from the message "-lam everywhere" (even chunk index) or "+lam everywhere" (odd).  Back-pointers
+// are written for [kb, ke) only.  y, w, tm, tp point at element 0 of the series.
 template <class Ring>
-ML_HD bool knots_load(Knots<Ring>& q, const ChunkState& st) {
-  const int cnt = st.count;
-  if (cnt > Ring::CAP) return false;
-  for (int k = 0; k < cnt; ++k) q.ring.set(k, st.x[k], st.a[k], st.b[k]);
-  q.l = 0;
-  q.r = cnt - 1;
-  return true;
-}
-
-// ---- warm-up: pin the state at the start of a chunk ------------------------------------------
-// Runs the two sandwich copies over [kb - warm, kb) (or the exact DP from element 0 when the chunk
-// is that close to the head of its series).  If the two windows become bit-identical the window
-// is carried to kb and saved in `st` with CHUNK_START_VALID.  The loop has the same trip count
-// for every thread of a warp (divergence-free apart from the data-dependent knot pops).
-// y, w, tm, tp point at element 0 of the series.  Returns false on ring overflow (st untouched).
-template <class Ring>
-ML_HD bool flsa_warm(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
-                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
-                     ChunkState& st, int warm, Knots<Ring>& q, Knots<Ring>& p) {
+ML_HD void flsa_spec_run(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, const double* __restrict__ y,
+                         const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
+                         const SpecWindows& W, int warm, KnotsC<Ring>& q) {
   const double lam = S.lam;
-  const int kb = c.kb;
+  const int kb = cd.kb;
   double t1, t2;
-  bool ok = true, dual, pristine;
-  int k;
+  int status = 0, k;
+  bool pristine;
   if (kb - warm <= 1) {
-    // exact by construction: first element (gfl_tf.c:231-240), then steps 1 .. kb-1
-    knots_init_first(q, y[0], w[0], lam, t1, t2);
+    knots_init_first(q, y[0], w[0], lam, t1, t2);   // gfl_tf.c:231-240
     if (kb == 1) {
       tm[0] = t1;
       tp[0] = t2;
-      if (t1 > t2) st.status |= CHUNK_IRREGULAR;
+      if (t1 > t2) status |= SPEC_IRREGULAR;
     }
-    dual = false;
+    status |= SPEC_EXACT;
     pristine = false;
     k = 1;
   } else {
-    knots_init_bound(q, -1, lam);
-    knots_init_bound(p, +1, lam);
-    dual = true;
-    pristine = true;   // both windows still hold only their +-inf sentinel
+    knots_init_bound(q, (cd.idx & 1) ? +1 : -1, lam);
+    pristine = true;   // the window still holds only its +-inf sentinel
     k = kb - warm;
   }
-  double yn = 0.0, wn = 0.0;   // element k, loaded one step ahead of its use (k + 1 <= n - 1 always)
-  if (k < kb) { yn = y[k]; wn = w[k]; }
-  for (; k < kb && ok; ++k) {
-    const double yk = yn, wk = wn;
-    yn = y[k + 1];
-    wn = w[k + 1];
+  bool ok = true;
+  for (; k < cd.ke && ok; ++k) {
+    if (k == kb) window_save(q, W.s_count, W.sx, W.sa, W.sb, W.stride, c);
     if (pristine) {
       // A zero-weight element leaves a constant message unchanged (clip(+-lam + 0)); the generic
       // step cannot express that on a sentinel-only window (0 * inf), so skip it exactly.
-      if (!(wk > 0)) continue;
+      if (!(w[k] > 0)) {
+        if (k >= kb) ok = false;   // no back-pointers without a real window: left to the walker (absurd input)
+        continue;
+      }
       pristine = false;
     }
-    if (dual) {
-      ok = dp_step(q, yk, wk, lam, t1, t2);
-      ok = dp_step(p, yk, wk, lam, t1, t2) && ok;
-      // the windows are compared knot by knot every 8th step (and at the last one): pinning is
-      // noticed at most 7 steps late, which costs nothing but those 7 duplicated steps
-      if (ok && ((k & 7) == 7 || k == kb - 1) && knots_same(p, q)) dual = false;
-    } else {
-      ok = dp_step(q, yk, wk, lam, t1, t2);
+    ok = dp_step_c(q, y[k], w[k], lam, t1, t2);
+    if (ok && k >= kb) {
+      tm[k] = t1;
+      tp[k] = t2;
+      if (t1 > t2) status |= SPEC_IRREGULAR;
     }
   }
-  if (!ok) return false;
-  if (dual) return true;   // not pinned within this warm-up: a later round looks further back
-  knots_save(q, st);
-  st.status |= CHUNK_START_VALID;
-  return true;
+  if (ok && kb >= cd.ke) window_save(q, W.s_count, W.sx, W.sa, W.sb, W.stride, c);   // empty chunk (n == 2)
+  if (!ok || pristine) {
+    W.status[c] = (status & ~SPEC_EXACT) | SPEC_OVERFLOW;
+    W.s_count[c] = 0;
+    W.e_count[c] = 0;
+    return;
+  }
+  window_save(q, W.e_count, W.ex, W.ea, W.eb, W.stride, c);
+  W.status[c] = status;
 }
 
-// ---- main: the chunk's own steps from a pinned start state ------------------------------------
-// `start` is the chunk's own CHUNK_START_VALID window or its left neighbour's CHUNK_END_VALID
-// window (the same state by definition).  Writes tm/tp of [kb, ke), saves the end state.
-// Returns false on ring overflow (st untouched).
+// ---- the walker's redo of one chunk from an exact window already in its ring --------------------------------
+// Returns false on ring overflow.  *irregular is set when some tm_k > tp_k.
 template <class Ring>
-ML_HD bool flsa_main(const SeriesDesc& S, const ChunkDesc& c, const double* __restrict__ y,
-                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
-                     const ChunkState& start, ChunkState& st, Knots<Ring>& q) {
-  if (!knots_load(q, start)) return false;
-  const double lam = S.lam;
+ML_HD bool flsa_redo_chunk(const SeriesDesc& S, const ChunkDesc& cd, const double* __restrict__ y,
+                           const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
+                           KnotsC<Ring>& q, bool* irregular) {
   double t1, t2;
-  bool ok = true, irregular = false;
-  double yn = 0.0, wn = 0.0;
-  if (c.kb < c.ke) { yn = y[c.kb]; wn = w[c.kb]; }
-  for (int k = c.kb; k < c.ke && ok; ++k) {
-    const double yk = yn, wk = wn;
-    yn = y[k + 1];
-    wn = w[k + 1];
-    ok = dp_step(q, yk, wk, lam, t1, t2);
+  for (int k = cd.kb; k < cd.ke; ++k) {
+    if (!dp_step_c(q, y[k], w[k], S.lam, t1, t2)) return false;
     tm[k] = t1;
     tp[k] = t2;
-    irregular |= (t1 > t2);
+    if (t1 > t2) *irregular = true;
   }
-  if (!ok) return false;
-  if (irregular) st.status |= CHUNK_IRREGULAR;
-  knots_save(q, st);
-  st.status = (st.status & ~CHUNK_START_VALID) | CHUNK_END_VALID | CHUNK_DONE;
   return true;
 }
 

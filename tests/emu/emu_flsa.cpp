@@ -9,8 +9,9 @@ using namespace ml;
 
 extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int chunk, int warm,
                         double* beta, double* tm, double* tp, int tile, long long* stats) {
-  // stats: [0] chunks, [1] pinned by the first warm-up, [2] started from the left neighbour, [3] finished in C, [4] overflow,
-  //        [5] max steps of B prefix, [6] chunks that outgrew the fast ring, [7] clamp order violations
+  // stats: [0] chunks, [1] verified (exact by construction or start window met the neighbour's end window),
+  //        [2] exact by construction, [3] redone by the walker, [4] series fallback (window > KNOT_CAP),
+  //        [5] longest chain, [6] speculative runs that outgrew SPEC_CAP, [7] clamp order violations
   for (int i = 0; i < 8; ++i) stats[i] = 0;
   if (n == 0) return 0;
   if (n == 1 || lam == 0) { for (int i = 0; i < n; ++i) beta[i] = y[i]; return 0; }
@@ -20,70 +21,62 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   if (S.mode == SERIES_SEQUENTIAL) cd.push_back(ChunkDesc{0, steps_lo, steps_hi, 0});
   else {
     for (int k = steps_lo; k < steps_hi || cd.empty(); k += chunk) {
-      cd.push_back(ChunkDesc{0, k, std::min(k + chunk, std::max(steps_hi, steps_lo)), 0});
+      cd.push_back(ChunkDesc{0, k, std::min(k + chunk, std::max(steps_hi, steps_lo)), (int)cd.size()});
       if (steps_hi <= steps_lo) break;
     }
   }
-  S.n_chunks = (int)cd.size();
-  std::vector<ChunkState> st(cd.size());
-  stats[0] = (long long)cd.size();
-  typedef LocalRing<KNOT_CAP_FAST> FastRing;   // same two-tier policy as the kernels
+  const int64_t nc = (int64_t)cd.size();
+  S.n_chunks = (int)nc;
+  stats[0] = nc;
+  std::vector<int32_t> status(nc, 0), s_count(nc, 0), e_count(nc, 0);
+  std::vector<double> win(6 * (size_t)SPEC_CAP * nc);
+  SpecWindows W{status.data(), s_count.data(), e_count.data(), win.data(), win.data() + SPEC_CAP * nc,
+                win.data() + 2 * SPEC_CAP * nc, win.data() + 3 * SPEC_CAP * nc, win.data() + 4 * SPEC_CAP * nc,
+                win.data() + 5 * SPEC_CAP * nc, nc};
+  typedef LocalRing<SPEC_CAP> SpecRing;
   typedef LocalRing<KNOT_CAP> BigRing;
-  for (size_t c = 0; c < cd.size(); ++c) { st[c].status = 0; st[c].count = 0; st[c].pad = 0; }
-  auto run_main = [&](bool count_b) {
-    std::vector<int> snap(cd.size());
-    for (size_t c = 0; c < cd.size(); ++c) snap[c] = st[c].status;   // pad: statuses before this launch
-    for (size_t c = 0; c < cd.size(); ++c) {
-      if (snap[c] & (CHUNK_DONE | CHUNK_OVERFLOW)) continue;
-      const ChunkState* start = nullptr;
-      if (snap[c] & CHUNK_START_VALID) start = &st[c];
-      else if (cd[c].kb > 1 && (snap[c - 1] & CHUNK_END_VALID) && !(snap[c - 1] & CHUNK_OVERFLOW)) start = &st[c - 1];
-      if (!start) continue;
-      if (!(snap[c] & CHUNK_START_VALID)) stats[2]++;
-      Knots<FastRing> q;
-      if (!flsa_main(S, cd[c], y, w, tm, tp, *start, st[c], q)) {
-        stats[6]++;
-        Knots<BigRing> Q;
-        if (!flsa_main(S, cd[c], y, w, tm, tp, *start, st[c], Q)) st[c].status |= CHUNK_OVERFLOW;
-      }
-    }
-  };
-  int wlen = warm;
-  for (int round = 0; round < 3; ++round) {
-    for (size_t c = 0; c < cd.size(); ++c) {
-      if (st[c].status & (CHUNK_DONE | CHUNK_OVERFLOW | CHUNK_START_VALID)) continue;
-      Knots<FastRing> q, p;
-      if (!flsa_warm(S, cd[c], y, w, tm, tp, st[c], wlen, q, p)) {
-        stats[6]++;
-        Knots<BigRing> Q, P;
-        if (!flsa_warm(S, cd[c], y, w, tm, tp, st[c], wlen, Q, P)) st[c].status |= CHUNK_OVERFLOW;
-      }
-      if (round == 0 && (st[c].status & CHUNK_START_VALID)) stats[1]++;
-    }
-    run_main(false);
-    if (S.mode == SERIES_SEQUENTIAL) break;
-    run_main(true);
-    wlen = wlen > (1 << 27) ? wlen : wlen * 8;
+  // sequential series: one chunk from the head, exact by construction (warm covers everything)
+  for (int64_t c = 0; c < nc; ++c) {
+    KnotsC<SpecRing> q;
+    flsa_spec_run(S, cd[c], c, y, w, tm, tp, W, S.mode == SERIES_SEQUENTIAL ? n : warm, q);
+    if (status[c] & SPEC_OVERFLOW) stats[6]++;
+    if (status[c] & SPEC_EXACT) stats[2]++;
+    if (status[c] & SPEC_IRREGULAR) stats[7]++;
   }
-  // pass C: chains, in order
+  // verdicts from the immutable windows, then the chains in order
+  std::vector<char> verified(nc);
+  for (int64_t c = 0; c < nc; ++c) { verified[c] = chunk_verified(W, c, 0); stats[1] += verified[c]; }
   bool ovf = false;
-  for (size_t c = 0; c < cd.size(); ++c) {
-    if (st[c].status & CHUNK_OVERFLOW) { ovf = true; break; }
-    if (st[c].status & CHUNK_DONE) continue;
-    if (c == 0 || !(st[c - 1].status & CHUNK_END_VALID)) return -1;
-    { Knots<BigRing> Q;
-      if (!flsa_main(S, cd[c], y, w, tm, tp, st[c - 1], st[c], Q)) st[c].status |= CHUNK_OVERFLOW; }
-    if (st[c].status & CHUNK_OVERFLOW) { ovf = true; break; }
+  KnotsC<BigRing> Q;
+  bool have = false;     // Q holds the exact window after chunk c - 1
+  long long run = 0;
+  for (int64_t c = 0; c < nc && !ovf; ++c) {
+    if (verified[c]) { have = false; run = 0; continue; }
+    if (!have) {
+      if (c == 0) {        // the head chunk itself overflowed: exact start from element 0
+        double t1, t2;
+        knots_init_first(Q, y[0], w[0], lam, t1, t2);
+        tm[0] = t1; tp[0] = t2;
+      } else {
+        if (!verified[c - 1]) return -1;   // cannot happen: a walker always comes from a verified chunk
+        window_load_end(Q, W, c - 1);
+      }
+    }
+    bool irr = false;
+    if (!flsa_redo_chunk(S, cd[c], y, w, tm, tp, Q, &irr)) { ovf = true; break; }
+    if (irr) stats[7]++;
+    have = true;
     stats[3]++;
+    stats[5] = std::max(stats[5], ++run);
   }
   double blast;
   if (ovf) {
-    stats[4] = std::max<long long>(stats[4], 1);
+    stats[4] = 1;
     std::vector<double> scratch(3 * (size_t)flsa_sequential_cap(n));
     flsa_sequential_forward(n, y, w, lam, scratch.data(), tm, tp, &blast);
   } else {
-    Knots<BigRing> q; knots_load(q, st.back());
-    blast = dp_last(q, y[n - 1], w[n - 1], lam);
+    if (!have) window_load_end(Q, W, nc - 1);     // the last chunk was verified: its saved end window is exact
+    blast = dp_last(Q, y[n - 1], w[n - 1], lam);
   }
   // backward: 3-phase reverse clamp scan over tiles of `tile` back-pointers (k = 0..n-2)
   const int m = n - 1;
@@ -92,7 +85,6 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   for (int t = 0; t < ntiles; ++t) {
     Clamp f = clamp_identity();
     for (int k = std::min(m, (t + 1) * tile) - 1; k >= t * tile; --k) {
-      if (tm[k] > tp[k]) stats[7]++;
       f = clamp_then(f, Clamp{tm[k], tp[k]});
     }
     agg[t] = f;

@@ -10,7 +10,7 @@ from test_oracle import FIXTURES, VALIDATION_CASES, fixture_table, _tbl
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-REL = 1e-6  # north_star: fitted betas within 1e-6 relative (measured deviations are ~1e-15)
+REL = 1e-10  # north_star: fitted betas within 1e-6 relative; asserted per element at 1e-10 (measured: ~1e-12 and below)
 
 
 def params(model=0, lambda2=25.0, tol_val=0.01, max_iter=1, nouter=1, max_lambda2=None, lambda1=0.0,
@@ -28,9 +28,9 @@ def run_one(engine, t, **kw):
 
 
 def close(a, b, rel=REL):
+    """per element: |a - b| <= rel * max(|b|, 1e-3)"""
     a, b = np.asarray(a, float), np.asarray(b, float)
-    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
-    return a.shape == b.shape and (a.size == 0 or float(np.max(np.abs(a - b))) <= rel * scale)
+    return a.shape == b.shape and (a.size == 0 or bool(np.all(np.abs(a - b) <= rel * np.maximum(np.abs(b), 1e-3))))
 
 
 def seg_row_counts(est_id, est_start, seg):
@@ -59,6 +59,9 @@ def assert_job_matches(r, o, exact_fast=True):
     # map, `mlogp > old_mlogp` compares two sums that are equal up to the rounding of their
     # association order (Eigen's, the oracle's and the GPU's all differ): not asserted.
     assert (r["irls_steps"], r["outer_iters"]) == (o["irls_steps"], o["outer_iters"])
+    # a15: the -log posterior of the last evaluation (Posterior.ipp:63-69) itself, not only its side effects
+    if "last_mlogp" in o:
+        assert abs(r["mlogp"] - o["last_mlogp"]) <= 1e-9 * max(1.0, abs(o["last_mlogp"])), (r["mlogp"], o["last_mlogp"])
 
 
 @pytest.mark.parametrize("prefix", list(FIXTURES))
@@ -310,6 +313,22 @@ def test_placement_independence(engine):
     for c in ("beta", "betahat", "pseudoweight"):
         assert np.array_equal(r1["estimates"][c], r2["estimates"][c])
     assert np.array_equal(r1["mu"], r2["mu"]) and np.array_equal(r1["offset"], r2["offset"])
+
+
+def test_chr1_three_replicates_against_the_port(engine, oracle):
+    """The largest job of the bench workload (chr1: 2.26 M CpGs x 3 replicates) against the CPU port with the
+    reference's verbatim DP: support, pseudodata and segment boundaries identical, estimates to 1e-10."""
+    t = synth.chromosome_table(2_260_000, 20242 * 50, (3,))
+    r = run_one(engine, t)
+    o = oracle.detect(t, oracle.MODEL_FAST, lambda2=25.0)
+    assert_job_matches(r, o)
+    assert np.array_equal(r["estimates"]["pseudoweight"], o["estimates"]["pseudoweight"])
+    assert np.array_equal(r["estimates"]["betahat"], o["estimates"]["betahat"])
+    seg = engine.segment_methylation_helper(r["estimates"], 0.01)
+    oseg = oracle.segment_methylation_helper(o["estimates"], 0.01)
+    for c in ("estimate_id", "segment_id", "start", "end"):
+        assert np.array_equal(seg[c], oseg[c]), c
+    assert close(seg["beta"], oseg["beta"]) and close(seg["pseudoweight"], oseg["pseudoweight"])
 
 
 def test_full_genome_shape_properties(engine):

@@ -109,13 +109,17 @@ def test_sequential_mode_is_bit_faithful_on_real_valued_data(engine, oracle):
     assert np.array_equal(got, oracle.weighted_1d_flsa(y, w, 3.0))
 
 
-def test_full_size_chromosome_properties(engine):
-    """chr1-sized series (2.26 M): too long for the oracle in a unit test; check optimality (KKT)
-    and that chunked == sequential mode bit for bit (count data)."""
+def test_full_size_chromosome_against_the_verbatim_dp(engine, oracle):
+    """chr1-sized series (2.26 M CpGs, count data): bit-equal to the reference's own tf_dp_weight
+    (src/core/gfl/gfl_tf.c:184-321, compiled verbatim under oracle/_ref when present, else its restatement) at the
+    UMR/LMR penalty and at the PMD penalty; optimal (KKT); chunked == sequential mode."""
     t = synth.chromosome_table(2_260_000, 99, (1,))
     y, w = pooled_series(t)
+    for lam in (25.0, 1000.0):
+        beta = engine.weighted_1d_flsa(y, w, lam)
+        assert np.array_equal(beta, oracle.weighted_1d_flsa(y, w, lam)), lam
+        assert kkt_residual(y, w, beta, lam) < 1e-8
     beta = engine.weighted_1d_flsa(y, w, 25.0)
-    assert kkt_residual(y, w, beta, 25.0) < 1e-8
     engine.set("flsa_sequential", 1)
     try:
         seq = engine.weighted_1d_flsa(y, w, 25.0)
