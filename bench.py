@@ -6,25 +6,28 @@
 Workload (config.workload): BASELINE.json configs[1] — a full human-genome-shaped synthetic WGBS
 sample set (~28 M CpGs over 24 chromosomes, one condition, 3 replicates, coverage ~ Poisson(20)
 filtered at >= 5), UMR/LMR segmentation at lambda2 = 25 followed by the PMD std fusion at
-lambda2 = 1000.  One STEP = the native calls the reference's R layer makes for that config:
+lambda2 = 1000.  The native calls the reference's R layer makes for that config:
     signal_detection_fast (24 x signal_detection_fast_singlechr, MethyLasso.R:559)
     segment_methylation_helper on the estimates            (R/call.R:53)
     the per-segment call table: gap split, shrink, mean/sd (R/call.R:55-72; data.table code in the reference,
                                                             native here so that the chain stays on the device)
     weighted_1d_flsa(std, width, 1000) per chromosome      (R/call.R:93)
     segment_methylation_helper on the fused table          (R/call.R:95)
-`value` times the step with inputs already resident in HBM (validation, indexing, IRLS, FLSA,
-segmentation all inside); `e2e` times the same step through the host-buffer C ABI from pinned host
-memory, including the H2D of the six input columns and the D2H of mu, the estimates table and both
-segment tables.  With N > 1 every rank processes its own genome (independent units, no data-path
-collective; weak scaling) and the ranks all-gather their segment-table sizes over NCCL at the end.
+One STEP = Part 1 of MethyLasso.R for that config (:559-592): the calls above plus the rule engine of
+segment_methylation_singlechr (R/call.R:75-215: LMR / UMR / DMV annotation, PMD split, calls, status) and the assembly of the
+two tables it returns.  `value` times the step with inputs already resident in HBM; `e2e` times
+`pipeline.GenomePipeline.segment_methylation`: pinned host columns in, the two region tables of the whole genome out on
+the host.  With N > 1 the SAME genome is sharded: its 24 chromosomes are assigned to the ranks longest-first, every
+rank processes its own (no data-path collective) and the per-shard region tables are pushed into every rank's HBM over
+NVLink at the end (`ml_gather_*`); `scaling` is "strong".  `verified` compares what the timed step computed with the CPU
+leg's tables of the same run.
 
 Timing hygiene: `value` is one contiguous loop of K steps between two CUDA events, no per-kernel instrumentation
 (the `kernels` table comes from a second pass over the same K steps).  Clocks / throttle reasons are read through NVML
 right before and right after that loop and, polled every 5 ms, during one more untimed repetition of the step: any
-driver query issued while the steps run can stall them (measured).  The boxes are shared and an outside stall of
-0.1-1.5 s hits about one step in a hundred; a loop in which one step took more than 1.3 x the loop's median step
-(undisturbed loops stay within 1.15 x) is listed under `disturbed_attempts` and the loop is timed again (at most twice).
+driver query issued while the steps run can stall them (measured).  The loop is timed ONCE (no retry); the host wall
+time of every step is listed in `host_wall_ms_each_step`, so that a step disturbed from outside (the boxes are shared)
+shows.
 
 --impl reference times the reference's CPU path for the same workload on the host cores: the oracle's
 plain-C restatement of methylation_detection with the reference's own tf_dp_weight (oracle/_ref,
@@ -140,10 +143,11 @@ class ClockSampler:
                        "during one more, untimed repetition of the same step"}
 
 
-def bind_to_gpu_cpus(gpu_index):
+def bind_to_gpu_cpus(gpu_index, world=1):
     """One process per GPU: run this rank's threads on the CPUs NVML reports as local to its GPU, so that the pinned
-    host buffers of the e2e step (allocated afterwards: first touch) sit in the memory of the GPU's own NUMA node and
-    the ranks do not all cross the socket interconnect for their 3 GB per step.  Best effort; returns what was done."""
+    host buffers of the e2e step (allocated afterwards: first touch) sit in the memory of the GPU's own NUMA node.  On
+    the boxes of this pool NVML reports the same CPU set for every GPU, so the set is also cut into `world` disjoint
+    slices, one per rank: the ranks' engine threads do not migrate over each other.  Best effort; returns what was done."""
     try:
         import pynvml as nv
         nv.nvmlInit()
@@ -155,8 +159,12 @@ def bind_to_gpu_cpus(gpu_index):
         cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
         cpus &= set(os.sched_getaffinity(0))
         if cpus:
-            os.sched_setaffinity(0, cpus)
-            return {"cpus": len(cpus), "first": min(cpus), "last": max(cpus)}
+            ordered = sorted(cpus)
+            share = len(ordered) // max(1, world)
+            if world > 1 and share >= 2:
+                ordered = ordered[gpu_index * share:(gpu_index + 1) * share]
+            os.sched_setaffinity(0, set(ordered))
+            return {"cpus": len(ordered), "first": ordered[0], "last": ordered[-1], "gpu_local_set": len(cpus)}
     except Exception as e:           # no NVML, no permission: run unbound
         return {"error": str(e)[:80]}
     return None
@@ -172,8 +180,9 @@ def make_workload(total_cpgs, seed_offset=0):
 # ------------------------------------------------------------------------------------------------
 # reference arm: oracle port + the reference's verbatim DP, all host threads
 # ------------------------------------------------------------------------------------------------
-def reference_step(tables, O, threads):
-    """One pass of the same native-call sequence on the CPU; returns unique CpGs processed."""
+def reference_step(tables, O, threads, keep=False):
+    """One pass of the same native-call sequence on the CPU; returns unique CpGs processed (and, keep=True, the segment
+    table and the PMD candidate segment table of every chromosome)."""
     out = [None] * len(tables)
 
     def work(ids):
@@ -192,7 +201,7 @@ def reference_step(tables, O, threads):
             pmd = O.segment_methylation_helper(dict(estimate_id=call["estimate_id"], start=call["start"].astype(np.int32),
                                                     beta=fused, betahat=call["std"],
                                                     pseudoweight=call["pseudoweight"]), TOL)  # R/call.R:95
-            out[j] = (r["n_params"], seg["start"].size, pmd["start"].size)
+            out[j] = (r["n_params"], seg["start"].size, pmd["start"].size, (seg, pmd) if keep else None)
     order = sorted(range(len(tables)), key=lambda j: -tables[j]["pos"].size)  # longest first
     buckets = [[] for _ in range(threads)]
     load = [0] * threads
@@ -205,6 +214,8 @@ def reference_step(tables, O, threads):
         th.start()
     for th in ths:
         th.join()
+    if keep:
+        return sum(o[0] for o in out), [o[3] for o in out]
     return sum(o[0] for o in out)
 
 
@@ -269,34 +280,29 @@ def workload_config(args, tables, ptr, U=None):
 
 
 # ------------------------------------------------------------------------------------------------
-# algorithmic bytes per launch: N rows, EP = E*P parameters, D datasets
+# DRAM traffic per launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json, written by
+# scripts/ncu_traffic.py together with a hash of the kernel sources it was taken on): refused when the sources changed
 # ------------------------------------------------------------------------------------------------
-def kernel_bytes(N, EP, D, words):
-    return {
-        "k_validate": 24 * N,
-        "k_dset_bounds": 0,
-        "k_bitmap_mark": 4 * N + 8 * words,
-        "k_bitmap_tile_count": 4 * words,
-        "k_bitmap_word_prefix": 8 * words,
-        "k_rank_unique": 16 * N + 4 * D * EP + 8 * EP,
-        "k_pseudodata": 4 * D * EP + 8 * N + 32 * EP,
-        "k_offset_partial": 8 * N,
-        "flsa_warm_kernel": 16 * EP,   # y, w of the warm-up stretch (warm == chunk: one extra read of each)
-        "flsa_main_kernel": 32 * EP,   # y, w read; tm, tp written
-        "flsa_bwd_reduce_kernel": 16 * EP,
-        "flsa_bwd_apply_kernel": 32 * EP,
-        "k_center": 16 * EP,
-        "k_eval_rows": 22 * N,          # two launches per step: the initial evaluation reads nmeth, cov (8 N: every parameter is
-                                        # still zero, no index, no gather, no mu), the one after the update 36 N; average
-        "k_tv_partial": 4 * EP,         # likewise: the initial launch writes zeros, the second reads beta (8 EP)
-        "k_seg_run_heads": 12 * EP,
-        "k_seg_emit": 28 * EP,          # beta, betahat, pw, start once (two launches: the second one is on the call table)
-        "k_call_count": 16 * EP,        # pos, pw
-        "k_call_parts": 16 * EP,        # pos, pw
-        "k_call_emit_part": 24 * EP,    # pos, betahat, pw once (the second and third sweeps hit L1 / L2)
-        "k_scan_tile_sums": 4 * EP,
-        "k_scan_apply": 12 * EP,
-    }
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "methylasso_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode())
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def load_ncu_traffic():
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(tpath):
+        return {}, {}, "no capture committed"
+    with open(tpath) as f:
+        tj = json.load(f)
+    if tj.get("kernel_source_hash") != kernel_source_hash():
+        return {}, {}, "stale: profiles/ncu_traffic.json was captured on other kernel sources (%s)" % tj.get("kernel_source_hash")
+    return tj.get("dram_bytes_per_launch", {}), tj.get("detail", {}), "profiles/ncu_traffic.json (%s)" % tj.get("captured", "")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,123 +454,30 @@ def run_dmr(args, local):
     eng.close()
 
 
+def run_aux(args, local):
+    raise SystemExit("--aux %s: not implemented yet" % args.aux)
+
+
 # ------------------------------------------------------------------------------------------------
-# auxiliary line: ONE genome sharded over the ranks, longest chromosome first (north star, point 3)
+# verification of what was timed against the CPU leg's tables
 # ------------------------------------------------------------------------------------------------
-def run_strong(args, rank, world, local):
-    """Strong scaling of configs[1]: the 24 chromosomes of one genome are assigned to the ranks longest-first
-    (methylasso_b200.shard.lpt_assign), every rank runs its shard resident (detect, segments, call table, PMD fusion)
-    with no data-path collective, and the per-shard segment and PMD tables are all-gathered over NCCL at the end
-    (shard.all_gather_tables) - inside the timed region.  Rank 0 checks the gathered tables against its own
-    single-GPU run of the whole genome (bit-equal: a job gives the same bits wherever it is placed)."""
-    import torch
-    import torch.distributed as dist
-    from methylasso_b200 import api, shard
-    from methylasso_b200._native import MlParams
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    eng = api.Engine(local)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
-    params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
-    tables, ptr, cols = make_workload(args.cpgs, seed_offset=0)          # the SAME genome on every rank
-    sizes = np.diff(ptr)
-    rank_of = shard.lpt_assign([shard.job_cost(n) for n in sizes], world)
-    mine = shard.my_jobs(rank_of, rank)
-    mptr = np.zeros(len(mine) + 1, np.int64)
-    mptr[1:] = np.cumsum(sizes[mine])
-    mcols = {k: np.ascontiguousarray(np.concatenate([cols[k][ptr[j]:ptr[j + 1]] for j in mine])) for k in cols}
-    batch = eng.upload(mptr, mcols)
-    job_ids = np.asarray(mine, np.int32)
-
-    t_parts = [0.0, 0.0]           # host wall of the shard's own work / of the exchange, accumulated over the timed steps
-
-    def step():
-        t0 = time.perf_counter()
-        res = eng.detect(batch, params)
-        seg = res.segments(TOL)
-        pmd = res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
-        res.free()
-        for t in (seg, pmd):
-            t["job"] = job_ids[t["job"]]                                  # shard-local job index -> chromosome
-        t1 = time.perf_counter()
-        # the exchange: every rank ends up with every shard's tables in its HBM; rank 0 also copies them to its host
-        gs = shard.all_gather_packed(seg, dist, device=f"cuda:{local}") if world > 1 else None
-        gp = shard.all_gather_packed(pmd, dist, device=f"cuda:{local}") if world > 1 else None
-        if world > 1 and rank == 0:
-            gs = ([p.cpu() for p in gs[0]],) + gs[1:]
-            gp = ([p.cpu() for p in gp[0]],) + gp[1:]
-        t_parts[0] += t1 - t0
-        t_parts[1] += time.perf_counter() - t1
-        return seg, pmd, gs, gp
-
-    def tables_of(seg, pmd, gs, gp):      # untimed: the gathered matrices as tables in chromosome order
-        if world > 1:
-            seg, pmd = shard.unpack_gathered(*gs), shard.unpack_gathered(*gp)
-        return shard.reorder_by_job(seg), shard.reorder_by_job(pmd)
-
-    for _ in range(max(3, args.warmup)):
-        out = step()
-    t_parts[0] = t_parts[1] = 0.0
-    eng.set("pool_headroom_percent", 25)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    wall = []
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        out = step()
-        wall.append(round((time.perf_counter() - t0) * 1e3, 2))
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        seg, pmd = tables_of(*out)
-        same = None
-        if world > 1:                      # the whole genome on this GPU alone must give the same tables
-            full = eng.upload(ptr, cols)
-            res = eng.detect(full, params)
-            s1, p1 = res.segments(TOL), res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
-            res.free()
-            full.free()
-            same = all(np.array_equal(seg[k], s1[k], equal_nan=True) for k in s1) and \
-                all(np.array_equal(pmd[k], p1[k], equal_nan=True) for k in p1)
-        U = int(sum(np.unique(t["pos"]).size for t in tables))
-        line = {"metric": "CpGs/sec through IRLS+weighted 1D FLSA, ONE genome sharded over the ranks (aux)",
-                "value": U / (float(ms.item()) * 1e-3), "unit": "CpG/s", "n_gpus": world, "steps": args.steps,
-                "ms_per_step": float(ms.item()), "scaling": "strong", "host_wall_ms_each_step_rank0": wall,
-                "jobs_per_rank": np.bincount(rank_of, minlength=world).tolist(),
-                "rows_per_rank": np.bincount(rank_of, weights=sizes, minlength=world).astype(np.int64).tolist(),
-                "segments": int(seg["start"].size), "pmd_segments": int(pmd["start"].size),
-                "gathered_tables_equal_single_gpu": same,
-                "rank0_ms_per_step_shard_work": t_parts[0] * 1e3 / args.steps,
-                "rank0_ms_per_step_exchange_and_merge": t_parts[1] * 1e3 / args.steps,
-                "timed": "detect + segments + call table + PMD fusion of the rank's chromosomes, fetch of its segment and "
-                         "PMD tables, NCCL all-gather of both (one packed matrix per table: every rank holds all shards "
-                         "in HBM afterwards), copy of the gathered matrices to rank 0's host; max over ranks"}
-        print(json.dumps(line), flush=True)
-        if args.out:
-            with open(args.out, "a") as f:
-                f.write(json.dumps(line) + "\n")
-    batch.free()
-    eng.close()
-    if world > 1:
-        dist.destroy_process_group()
+def tables_match(got, want_per_job, job_ids, keys=("start", "end")):
+    """got: a table with a `job` column (shard-local job index); want_per_job[j]: the CPU leg's table of chromosome j."""
+    for local, j in enumerate(job_ids):
+        m = got["job"] == local
+        w = want_per_job[int(j)]
+        for k in keys:
+            if not np.array_equal(np.asarray(got[k][m], np.int64), np.asarray(w[k], np.int64)):
+                return False
+    return True
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--strong", action="store_true",
-                    help="auxiliary measurement: one genome sharded over the ranks (strong scaling) instead of the contract line")
     ap.add_argument("--dmr", action="store_true",
                     help="auxiliary measurement: configs[2] (3 vs 3 DMR calling) instead of the contract line")
+    ap.add_argument("--aux", default=None, choices=[None, "config0", "sweep", "full", "cohort"],
+                    help="auxiliary measurements of the other BASELINE.json configs (one JSON line each, not the contract line)")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -572,15 +485,11 @@ def main():
     ap.add_argument("--cpgs", type=int, default=synth.GENOME_CPGS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-groups", type=int, default=6,
-                    help="engines (streams + host threads) the e2e step spreads the chromosomes over; 1 = single call")
-    ap.add_argument("--resident-groups", type=int, default=0,
-                    help="> 1: also time the resident step with the chromosomes spread over this many engines")
-    ap.add_argument("--e2e-edge", type=float, default=0.0,
-                    help="share of the rows given to the first and to the last group of the e2e pipeline (0 = balanced)")
-    ap.add_argument("--e2e-no-mu", action="store_true",
-                    help="auxiliary: the e2e step does not download mu (the reference returns it, but neither MethyLasso.R "
-                         "nor R/call.R ever reads ret$mu); 39 %% fewer bytes come back")
+    ap.add_argument("--no-per-cpg", action="store_true", help="skip the secondary e2e figure (per-CpG outputs downloaded)")
+    ap.add_argument("--e2e-groups", type=int, default=0,
+                    help="engines (streams + host threads) the e2e step spreads the rank's chromosomes over (0: 6 on one "
+                         "GPU, 3 per rank otherwise)")
+    ap.add_argument("--gather", default="ipc", choices=["ipc", "nccl"], help="transport of the final exchange (N > 1)")
     ap.add_argument("--out", default=None, help="also append the JSON line to this file")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed resident steps (ncu --profile-from-start off)")
@@ -598,54 +507,68 @@ def main():
         if rank == 0:
             run_dmr(args, local)
         return
-    if args.strong:
-        run_strong(args, rank, world, local)
+    if args.aux:
+        if rank == 0:
+            run_aux(args, local)
         return
 
     import torch
     import torch.distributed as dist
-    from methylasso_b200 import api
+    from methylasso_b200 import api, shard
     from methylasso_b200._native import MlParams
+    from methylasso_b200.pipeline import GenomePipeline
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: methylasso_b200 has no CPU path")
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_cpus(local) if world > 1 else None      # before any pinned buffer is allocated (first touch)
+    numa = bind_to_gpu_cpus(local, world) if world > 1 else None      # before any pinned buffer is allocated (first touch)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
 
     eng = api.Engine(local)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
+    eng.set("want_mu", 0)        # nothing in the reference's R layer reads ret$mu (the per-CpG e2e variant below stores it)
     params = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
 
-    # started seconds before anything is timed (NVML initialisation, or nvidia-smi's start-up in the fall-back, can
-    # stall CUDA calls for 50-350 ms)
+    # started seconds before anything is timed (NVML initialisation can stall CUDA calls for 50-350 ms)
     sampler = ClockSampler(local)
     sampler.start()
-    tables, ptr, cols = make_workload(args.cpgs, seed_offset=rank)
-    N = int(ptr[-1])
-    # pinned host copies of the inputs (e2e) and of the outputs
-    pin = {k: torch.from_numpy(v).pin_memory() for k, v in cols.items()}
-    pcols = {k: v.numpy() for k, v in pin.items()}
-    batch = eng.upload(ptr, pcols)
+    # ONE genome, the same on every rank; its chromosomes are assigned to the ranks longest-first (R/genome_wide.R:42-43
+    # hands them to forked workers one by one)
+    tables, ptr, cols = make_workload(args.cpgs)
+    sizes = np.diff(ptr)
+    rank_of = shard.lpt_assign([shard.job_cost(n) for n in sizes], world)
+    mine = shard.my_jobs(rank_of, rank)
+    job_ids = np.asarray(mine, np.int32)
+    mptr = np.zeros(len(mine) + 1, np.int64)
+    mptr[1:] = np.cumsum(sizes[mine])
+    mcols = {k: np.ascontiguousarray(np.concatenate([cols[k][ptr[j]:ptr[j + 1]] for j in mine])) for k in cols} if world > 1 else cols
+    N_mine, N_all = int(mptr[-1]), int(ptr[-1])
+    batch = eng.upload(mptr, mcols)
+    gather = shard.RegionGather(eng, rank, world, 8 << 20, dist if world > 1 else None, dev, args.gather)
 
     def step_resident():
+        """Part 1 of MethyLasso.R on the rank's chromosomes, resident: fit, segments, call table, PMD std fusion, rule
+        engine, the two region tables assembled on the device; with N > 1 the tables of all ranks end up in every
+        rank's HBM (ml_gather_push + the counts' collective)."""
         res = eng.detect(batch, params)
-        nseg = res.segments_count(TOL)
-        res.call_table(TOL, MAX_DISTANCE, fetch=False)
-        npmd = res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
-        return res, nseg, npmd
+        counts = gather.all_gather(res, job_ids, TOL, MAX_DISTANCE, fetch=False)
+        return res, counts
 
     # sizes (one untimed call)
-    res, nseg, npmd = step_resident()
-    sizes = [res.sizes(j) for j in range(res.njobs)]
-    assert all(s[4] == 0 for s in sizes), "a synthetic chromosome failed validation"
-    U = int(sum(s[1] for s in sizes))
-    EP = int(sum(s[1] * s[2] for s in sizes))
-    D = 3
-    words = int(sum((int(t["pos"].max()) - int(t["pos"].min())) // 32 + 1 for t in tables))
+    res, counts0 = step_resident()
+    szs = [res.sizes(j) for j in range(res.njobs)]
+    assert all(s[4] == 0 for s in szs), "a synthetic chromosome failed validation"
+    U_mine = int(sum(s[1] for s in szs))
+    nseg_tab = res.segments_count(TOL)
+    npmd_tab = res.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
     res.free()
+    u_all = torch.tensor([U_mine], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(u_all, op=dist.ReduceOp.SUM)
+    U = int(u_all.item())
 
     def barrier():
         if world > 1:
@@ -655,57 +578,44 @@ def main():
     # ---- value: resident inputs ------------------------------------------------------------------
     lw0 = eng.launch_count
     for _ in range(args.warmup):
-        r, _, _ = step_resident()
+        r, _ = step_resident()
         r.free()
     per_step = (eng.launch_count - lw0) // max(1, args.warmup)
     eng.set("pool_headroom_percent", 25)     # no cuMemMap inside a timed step
     gc.collect()
     gc.disable()
     barrier()
-    # The GPU boxes are shared: now and then something outside this process (another tenant's driver queries take a
-    # node-wide lock) stalls one step for 0.1-1.5 s (seen with no sampler of our own running: steps of 969 and 1535 ms
-    # among 15 ms ones).  A K-step loop in which a step took more than DISTURBED x the loop's median step is recorded under
-    # `disturbed_attempts` and the whole loop is timed again, at most twice; the reported numbers are those of ONE
-    # contiguous K-step loop.
-    disturbed = []
-    for attempt in range(3):
-        sampler.mark()
-        sampler.sample()
-        l0 = eng.launch_count
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if args.profiler_range and attempt == 0:
-            torch.cuda.cudart().cudaProfilerStart()
-        ev0.record(stream)
-        step_wall_res = []
-        for _ in range(args.steps):
-            tw0 = time.perf_counter()
-            r, nseg, npmd = step_resident()
-            r.free()
-            step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
-        ev1.record(stream)
-        sampler.sample()
-        if args.profiler_range and attempt == 0:
-            torch.cuda.synchronize()
-            torch.cuda.cudart().cudaProfilerStop()
-        barrier()
-        launches = eng.launch_count - l0
-        ms = ev0.elapsed_time(ev1) / args.steps
-        bad = torch.tensor([1.0 if max(step_wall_res) > DISTURBED * float(np.median(step_wall_res)) else 0.0], device="cuda")
-        if world > 1:
-            dist.all_reduce(bad, op=dist.ReduceOp.MAX)       # every rank repeats or none does
-        if bad.item() == 0.0 or attempt == 2 or args.profiler_range:
-            break
-        disturbed.append({"ms_per_step": ms, "host_wall_ms_each_step": step_wall_res})
+    sampler.mark()
+    sampler.sample()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
+    ev0.record(stream)
+    step_wall_res = []
+    for _ in range(args.steps):             # ONE loop of K steps, timed once: no retry, every step's host wall is listed
+        tw0 = time.perf_counter()
+        r, counts = step_resident()
+        r.free()
+        step_wall_res.append(round((time.perf_counter() - tw0) * 1e3, 2))
+    ev1.record(stream)
+    sampler.sample()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+    barrier()
+    launches = eng.launch_count - l0
+    ms = ev0.elapsed_time(ev1) / args.steps
 
     def one_more():
-        r_, _, _ = step_resident()
+        r_, _ = step_resident()
         r_.free()
     sampler.sample_during(one_more)
     clocks = sampler.stop()
     # the same K steps once more with a pair of CUDA events around every kernel (the per-kernel durations of the
-    # roofline and of `kernels`); kept out of `value`: ~800 event records cost a step about 0.4 ms
+    # roofline and of `kernels`); kept out of `value`
     eng.set("profile", 1)
-    r, _, _ = step_resident()                # fills the engine's pool of timing events
+    r, _ = step_resident()                # fills the engine's pool of timing events
     r.free()
     eng.set("profile_reserve_events", int(2.2 * per_step * (args.steps + 1)))   # no cudaEventCreate while timing
     eng.profile_reset()
@@ -713,7 +623,7 @@ def main():
     pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pv0.record(stream)
     for _ in range(args.steps):
-        r, _, _ = step_resident()
+        r, _ = step_resident()
         r.free()
     pv1.record(stream)
     barrier()
@@ -726,210 +636,140 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    u_all = torch.tensor([U], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(u_all, op=dist.ReduceOp.SUM)
-    value = float(u_all.item()) / (ms_max * 1e-3)
+    value = U / (ms_max * 1e-3)
 
-    # ---- resident inputs, chromosomes spread over several engines (streams + host threads) ---------
-    # The latency-bound phases of one group (FLSA left-neighbour rounds, PMD chains, host round trips) overlap
-    # with the bandwidth-bound kernels of the others.
-    resident_pool = None
-    if args.resident_groups > 1:
-        Gr = args.resident_groups
-        rpool = api.EnginePool(Gr, local)
-        rgroups = []
-        for k, (jobs, gptr, gcols) in enumerate(api.split_jobs(ptr, cols, Gr)):
-            rgroups.append((rpool.engines[k % Gr].upload(gptr, gcols), jobs))
-
-        def run_group_resident(eng_g, grp):
-            bt, jobs = grp
-            rr = eng_g.detect(bt, params)
-            ns = rr.segments_count(TOL)
-            rr.call_table(TOL, MAX_DISTANCE, fetch=False)
-            npm = rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
-            rr.free()
-            eng_g.synchronize()
-            return ns, npm
-        for _ in range(max(3, args.warmup)):
-            outs_r = rpool.map(run_group_resident, rgroups)
-        for e_g in rpool.engines:
-            e_g.set("pool_headroom_percent", 10)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        lr0 = sum(e_g.launch_count for e_g in rpool.engines)
-        r0.record(stream)
-        for _ in range(args.steps):
-            outs_r = rpool.map(run_group_resident, rgroups)
-        torch.cuda.synchronize()
-        r1.record(stream)
-        barrier()
-        rms = r0.elapsed_time(r1) / args.steps
-        t3 = torch.tensor([rms], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        resident_pool = {"engines": Gr, "ms_per_step": float(t3.item()), "value": float(u_all.item()) / (float(t3.item()) * 1e-3),
-                         "unit": "CpG/s", "gpu_launches": int(sum(e_g.launch_count for e_g in rpool.engines) - lr0),
-                         "segments": [int(sum(o[0] for o in outs_r)), int(sum(o[1] for o in outs_r))]}
-        for bt, _ in rgroups:
-            bt.free()
-        rpool.close()
+    # ---- what the timed step computed, kept for the checks below: the gathered region tables (all ranks' shards) and
+    # this rank's segment / PMD-candidate tables
+    res_v = eng.detect(batch, params)
+    seg_v = res_v.segments(TOL)
+    pmd_v = res_v.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
+    reg_seg, reg_pmd = gather.all_gather(res_v, job_ids, TOL, MAX_DISTANCE)
+    reg_seg, reg_pmd = shard.reorder_by_job(reg_seg), shard.reorder_by_job(reg_pmd)
+    res_v.free()
 
     # ---- e2e: host buffers through the C ABI -------------------------------------------------------
-    e2e = None
+    e2e = e2e_percpg = None
+    e2e_equal = None
     if not args.no_e2e:
-        # The user-level call: chromosomes split into groups, one engine (stream) + host thread per group,
-        # so H2D of one group, kernels of another and D2H of a third overlap.  Inputs and outputs are
-        # pinned host buffers; sizes are known from the untimed call above.
-        G = max(1, args.e2e_groups)
-        pool = api.EnginePool(G, local)
-        groups = []
-        for jobs, gptr, gcols in api.split_jobs(ptr, cols, G, edge_share=(args.e2e_edge or None)):
-            pin_in = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in gcols.items()}
-            n_g = int(gptr[-1])
-            ep_g = int(sum(sizes[j][1] * sizes[j][2] for j in jobs))
-            outb = dict(mu=torch.empty(n_g, dtype=torch.float64).pin_memory().numpy(),
-                        off=torch.empty(3 * len(jobs), dtype=torch.float64).pin_memory().numpy(),   # pageable would make the
-                        # asynchronous copy call block until the detect kernels are done
-                        est_id=torch.empty(ep_g, dtype=torch.int32).pin_memory().numpy(),
-                        **{k: torch.empty(ep_g, dtype=torch.float64).pin_memory().numpy()
-                           for k in ("start", "beta", "betahat", "pseudoweight")})
-            groups.append((jobs, gptr, pin_in, outb))
-
-        def run_group(eng_g, grp):
-            jobs, gptr, pin_in, o = grp
-            ts = [time.perf_counter()]
-            with pool.h2d_turn:
-                ts.append(time.perf_counter())
-                bt = eng_g.upload(gptr, pin_in)
-            ts.append(time.perf_counter())
-            rr = eng_g.detect(bt, params)
-            bt.free()
-            ts.append(time.perf_counter())
-            # D2H of mu / estimates is enqueued on the copy stream and overlaps the segmentation kernels
-            rr.copy_all_async(None if args.e2e_no_mu else o["mu"], o["off"], o["est_id"], o["start"], o["beta"],
-                              o["betahat"], o["pseudoweight"])
-            ts.append(time.perf_counter())
-            rr.segments_count(TOL)                      # resident; the tables are fetched after the big copies
-            rr.call_table(TOL, MAX_DISTANCE, fetch=False)
-            rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2, fetch=False)
-            ts.append(time.perf_counter())
-            eng_g.synchronize()
-            seg = rr.segments(TOL, reuse_pinned=True)               # the engine's own page-locked buffers
-            call = rr.call_table(TOL, MAX_DISTANCE, reuse_pinned=True)
-            pmd = rr.call_pmd_segments(TOL, MAX_DISTANCE, PMD_LAMBDA2)
-            pmd["call_table"] = call
-            rr.free()
-            ts.append(time.perf_counter())
-            timeline.append((len(jobs), [round((x - t_step0[0]) * 1e3, 1) for x in ts]))
-            return seg, pmd
-
-        timeline, t_step0 = [], [0.0]
+        G = args.e2e_groups or (6 if world == 1 else 3)
+        pipe = GenomePipeline(mptr, mcols, n_engines=G, device=local, lambda2=LAMBDA2, tol_val=TOL)
 
         def step_e2e():
-            timeline.clear()
-            t_step0[0] = time.perf_counter()
-            return pool.map(run_group, groups)
+            """host columns in (pinned), region tables of the whole genome out on rank 0's host"""
+            seg, pmd, status = pipe.segment_methylation(MAX_DISTANCE)
+            if world == 1:
+                return seg, pmd
+            return gather_host(seg, pmd)
+
+        def gather_host(seg, pmd):
+            # N > 1, end to end: every rank's tables come back to its host with the fit's last call; the shards are
+            # then all-gathered as packed matrices (32-bit integers and doubles are exact in a float64 matrix)
+            seg = dict(seg, job=job_ids[seg["job"]])
+            pmd = dict(pmd, job=job_ids[pmd["job"]])
+            gs = shard.all_gather_tables_packed({k: np.asarray(v, np.float64) if v.dtype.kind != "f" else v for k, v in seg.items()}, dist, dev)[0]
+            gp = shard.all_gather_tables_packed({k: np.asarray(v, np.float64) if v.dtype.kind != "f" else v for k, v in pmd.items()}, dist, dev)[0]
+            return gs, gp
         for _ in range(max(3, args.warmup)):
             outs = step_e2e()
-        for e_g in pool.engines:          # pre-grow each engine's pool a little: no cuMemMap inside a timed step
-            e_g.set("pool_headroom_percent", 25)
+        pipe.warm_pools(25)               # pre-grow each engine's pool a little: no cuMemMap inside a timed step
         gc.collect()
-        gc.disable()                      # no collector pause inside a 50 ms step
+        gc.disable()                      # no collector pause inside a 25 ms step
         barrier()
-        e2e_sampler = sampler
-        e2e_disturbed = []
-        for attempt in range(3):             # same policy as for the resident loop
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e2e_sampler.mark()
-            e2e_sampler.sample()
-            t0 = time.perf_counter()
-            e0.record(stream)
-            step_wall = []
-            for _ in range(args.steps):
-                ts0 = time.perf_counter()
-                outs = step_e2e()
-                step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
-            torch.cuda.synchronize()
-            e1.record(stream)
-            wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-            barrier()
-            bad = torch.tensor([1.0 if max(step_wall) > DISTURBED * float(np.median(step_wall)) else 0.0], device="cuda")
-            if world > 1:
-                dist.all_reduce(bad, op=dist.ReduceOp.MAX)
-            if bad.item() == 0.0 or attempt == 2:
-                break
-            e2e_disturbed.append({"ms_per_step": e0.elapsed_time(e1) / args.steps, "host_wall_ms_each_step": step_wall})
-        timeline_timed = sorted(timeline, key=lambda t: t[1][0])
-        e2e_sampler.sample()
-        e2e_sampler.sample_during(step_e2e)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler2 = sampler
+        sampler2.mark()
+        sampler2.sample()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        step_wall = []
+        for _ in range(args.steps):
+            ts0 = time.perf_counter()
+            outs = step_e2e()
+            step_wall.append(round((time.perf_counter() - ts0) * 1e3, 1))
+        torch.cuda.synchronize()
+        e1.record(stream)
+        wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         barrier()
+        timeline = sorted(pipe.timeline)
+        sampler2.sample()
+        sampler2.sample_during(step_e2e)
         gc.enable()
-        ems = e0.elapsed_time(e1) / args.steps
-        t2 = torch.tensor([ems], device="cuda", dtype=torch.float64)
+        t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
+        h2d = torch.tensor([float(pipe.h2d_bytes())], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        seg_bytes = sum(v.nbytes for sg, pm in outs for v in list(sg.values()) + [x for x in pm.values() if not isinstance(x, dict)]
-                        + list(pm["call_table"].values()))
-        e2e = {"value": float(u_all.item()) / (float(t2.item()) * 1e-3), "unit": "CpG/s",
-               "ms_per_step": float(t2.item()), "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": 24 * N,
-               "d2h_bytes_per_step": int((0 if args.e2e_no_mu else 8 * N) + 36 * EP + seg_bytes), "engines": G,
-               "mu_downloaded": not args.e2e_no_mu,
-               "host_wall_ms_each_step": step_wall, "disturbed_attempts": e2e_disturbed, "clocks": e2e_sampler.stop(),
-               "timeline_ms_last_step": timeline_timed,  # per group: start, h2d start/end, detect end, d2h enqueued, segments+pmd end, all done
-               "api": "EnginePool.map over chromosome groups: ml_batch_upload + ml_batch_detect + ml_result_copy_all + "
-                      "ml_result_segments + ml_result_pmd_segments per group, transfers taking turns per direction"}
-        pool.close()
+            dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+        seg_e, pmd_e = outs
+        if world == 1:
+            d2h_bytes = GenomePipeline.d2h_bytes_regions(seg_e, pmd_e)
+        else:
+            d2h_bytes = int(sum(np.asarray(v).nbytes for v in seg_e.values()) + sum(np.asarray(v).nbytes for v in pmd_e.values()))
+        # the e2e call's tables against the resident step's gathered tables (bit for bit)
+        se, pe = shard.reorder_by_job(seg_e), shard.reorder_by_job(pmd_e)
+        e2e_equal = bool(all(np.array_equal(np.asarray(se[k], np.float64), np.asarray(reg_seg[k], np.float64), equal_nan=True) for k in reg_seg)
+                         and all(np.array_equal(np.asarray(pe[k], np.float64), np.asarray(reg_pmd[k], np.float64), equal_nan=True) for k in reg_pmd))
+        e2e = {"value": U / (float(t2.item()) * 1e-3), "unit": "CpG/s", "ms_per_step": float(t2.item()),
+               "host_wall_ms_per_step": wall_ms, "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h_bytes),
+               "engines_per_gpu": G, "host_wall_ms_each_step": step_wall, "clocks": sampler2.stop(),
+               "timeline_ms_last_step_rank0": timeline,   # per group: start, h2d start, h2d end, fit enqueued, tables on the host
+               "outputs": "the two tables segment_methylation returns (lmr_umr_valley, pmd) for the whole genome, on the host",
+               "api": "GenomePipeline.segment_methylation: per chromosome group ml_batch_upload (pos / Nmeth / coverage from pinned "
+                      "host memory; dataset / condition / replicate reduced to a run table on the host) + ml_batch_detect "
+                      "(mu not stored) + ml_result_segment_methylation (rule engine on the device, region tables downloaded)"
+                      + ("; then the shards' tables all-gathered from the hosts (torch.distributed, packed)" if world > 1 else ""),
+               "superset_of_reference_arm": "the reference arm stops at the PMD candidate segments (R/call.R:95); this call also "
+                                            "runs R/call.R:75-215 (LMR / UMR / DMV annotation, PMD split, calls, status)"}
+        # ---- secondary e2e figure: everything the reference's own return values hold, per CpG, downloaded -----------
+        if world == 1 and not args.no_per_cpg:
+            bufs = pipe.output_buffers(True)
+            for _ in range(3):
+                o2 = pipe.signal_detection_fast(MAX_DISTANCE, PMD_LAMBDA2, want_mu=True, buffers=bufs)
+            gc.collect()
+            gc.disable()
+            torch.cuda.synchronize()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record(stream)
+            pw = []
+            for _ in range(args.steps):
+                ts0 = time.perf_counter()
+                o2 = pipe.signal_detection_fast(MAX_DISTANCE, PMD_LAMBDA2, want_mu=True, buffers=bufs)
+                pw.append(round((time.perf_counter() - ts0) * 1e3, 1))
+            torch.cuda.synchronize()
+            p1.record(stream)
+            torch.cuda.synchronize()
+            gc.enable()
+            pms = p0.elapsed_time(p1) / args.steps
+            e2e_percpg = {"value": U / (pms * 1e-3), "unit": "CpG/s", "ms_per_step": pms, "host_wall_ms_each_step": pw,
+                          "h2d_bytes_per_step": pipe.h2d_bytes(), "d2h_bytes_per_step": GenomePipeline.d2h_bytes_full(o2),
+                          "outputs": "mu, offset, the estimates table (5 columns per CpG), the segment table, the call table and "
+                                     "the PMD candidate segments of every chromosome: the reference's per-CpG return values too"}
+        pipe.close()
 
-    # ---- K16: all-gather of per-shard segment summaries over NCCL ---------------------------------
-    gathered = None
-    if world > 1:
-        mine = torch.tensor([U, nseg, npmd], device="cuda", dtype=torch.int64)
-        allv = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allv, mine)
-        gathered = [v.tolist() for v in allv]
-
-    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    # ---- roofline: per-launch algorithmic bytes recorded by the engine at launch time, from the launch's own sizes ----
     pk, pk_kind = peaks()
-    kb = kernel_bytes(N, EP, D, words)
-    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
-    # capture of this same command (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py)
-    traffic, ncu_detail = {}, {}
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f)
-        traffic, ncu_detail = tj.get("dram_bytes_per_launch", {}), tj.get("detail", {})
+    traffic, ncu_detail, traffic_note = load_ncu_traffic()
     table = []
     for name, (tot_ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
         per = tot_ms / max(1, n)
-        # data-dependent kernels (FLSA chunk kernels) report the bytes of the DP steps they completed
-        b = (prof_work[name] / max(1, n)) if name in prof_work else kb.get(name)
+        b = (prof_work[name] / max(1, n)) if name in prof_work else None
         gbs = (b / (per * 1e-3) / 1e9) if b and per > 0 else None
         table.append({"kernel": name, "ms_per_step": tot_ms / args.steps, "launches_per_step": n / args.steps,
                       "avg_launch_ms": per, "alg_bytes_per_launch": b, "GBps": gbs,
                       "frac_of_hbm": (gbs / pk["hbm_gbs"]) if gbs else None,
                       "ncu_dram_bytes_per_launch": traffic.get(name)})
+    latency_bound = ("flsa_spec_kernel", "flsa_chain_kernel", "flsa_verify_kernel")
     top = table[0] if table else None
     roofline = None
     if top:
         roofline = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": top["frac_of_hbm"], "traffic": top["ncu_dram_bytes_per_launch"], "peak_source": pk_kind,
-                    "alg_bytes_per_launch": top["alg_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
-                    # what bounds a latency-bound kernel: DP steps per second from this run, issue
-                    # and occupancy figures from the committed ncu capture
-                    "latency_bound": ({"dp_steps_per_s": (top["alg_bytes_per_launch"] / (16.0 if top["kernel"] == "flsa_warm_kernel" else 32.0))
-                                                         / (top["avg_launch_ms"] * 1e-3),
-                                       "ncu_issue_active_pct": ncu_detail.get(top["kernel"], {}).get("mean_issue_active_pct"),
-                                       "ncu_warps_active_pct": ncu_detail.get(top["kernel"], {}).get("mean_warps_active_pct"),
-                                       "ncu_fp64_pipe_pct": ncu_detail.get(top["kernel"], {}).get("mean_fp64_pipe_pct")}
-                                      if top["kernel"].startswith("flsa_") and top["alg_bytes_per_launch"] else None),
-                    "note": "FLSA chunk kernels run a dependent fp64 compare/add/divide chain per element (latency-bound, "
-                            "not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped kernels "
-                            "of the step are listed in `kernels` with their own fractions"}
-
-    # the largest kernel of the step that IS bandwidth-shaped (elementwise / gather / reduction sweeps of the IRLS loop)
-    latency_bound = ("flsa_warm_kernel", "flsa_main_kernel", "flsa_chain_kernel", "flsa_pass_c_kernel")
+                    "frac": top["frac_of_hbm"], "traffic": top["ncu_dram_bytes_per_launch"], "traffic_source": traffic_note,
+                    "peak_source": pk_kind, "alg_bytes_per_launch": top["alg_bytes_per_launch"], "avg_launch_ms": top["avg_launch_ms"],
+                    "latency_bound": ({"dp_steps_per_s": (top["alg_bytes_per_launch"] / 32.0) / (top["avg_launch_ms"] * 1e-3),
+                                       "ncu": ncu_detail.get(top["kernel"])}
+                                      if top["kernel"] in latency_bound and top["alg_bytes_per_launch"] else None),
+                    "note": "the FLSA forward kernels run a dependent fp64 compare / add / divide chain per element "
+                            "(latency-bound, not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped "
+                            "kernels of the step are listed in `kernels` with their own fractions"}
     top_bw = next((t for t in table if t["kernel"] not in latency_bound and t["GBps"]), None)
     roofline_bw = None
     if top_bw:
@@ -937,63 +777,90 @@ def main():
                        "unit": "GB/s", "frac": top_bw["frac_of_hbm"], "traffic": top_bw["ncu_dram_bytes_per_launch"],
                        "peak_source": pk_kind, "alg_bytes_per_launch": top_bw["alg_bytes_per_launch"],
                        "avg_launch_ms": top_bw["avg_launch_ms"]}
+    alg_total = sum(v for v in prof_work.values()) / max(1, args.steps)
+    step_roofline = {"alg_bytes_per_step_all_kernels": alg_total, "fused_floor_bytes": 32 * N_mine + 68 * U_mine,
+                     "fused_floor_ms": (32 * N_mine + 68 * U_mine) / (pk["hbm_gbs"] * 1e9) * 1e3,
+                     "frac_of_fused_floor": ((32 * N_mine + 68 * U_mine) / (pk["hbm_gbs"] * 1e9) * 1e3) / ms_max}
 
-    # ---- auxiliary, untimed part of no metric: the rule engine of segment_methylation_singlechr (R/call.R:75-215) on the
-    # resident fit of this workload - LMR / UMR annotation, valleys, PMD split / calls, PMD status.  Every repetition uses
-    # a new key (flank_dist_max 5000 / 5000.5: distances are integers, same results) so that nothing is reused.
-    rule_engine = None
-    if rank == 0:
-        try:
-            res_r, _, _ = step_resident()
-            eng.synchronize()
-            walls, fin, pmd = [], None, None
-            for rep in range(4):
-                t0 = time.perf_counter()
-                kw = dict(flank_dist_max=5000.0 + 0.5 * (rep & 1))
-                pmd = res_r.call_pmds(TOL, MAX_DISTANCE, PMD_LAMBDA2, **kw)
-                fin = res_r.call_pmd_status(TOL, MAX_DISTANCE, PMD_LAMBDA2, **kw)
-                eng.synchronize()
-                walls.append((time.perf_counter() - t0) * 1e3)
-            res_r.free()
-            rule_engine = {"host_wall_ms": float(np.median(walls[1:])), "host_wall_ms_each": [round(w, 2) for w in walls],
-                           "rows": int(fin["category"].size), "lmr": int((fin["category"] == 1).sum()),
-                           "umr": int((fin["category"] == 2).sum()), "valleys": int((fin["category"] == 3).sum()),
-                           "pmds": int((pmd["category"] == 1).sum()),
-                           "what": "R/call.R:75-215 on the resident call table, result tables downloaded; not part of the "
-                                   "timed step (the reference arm does not run it)"}
-        except Exception as exc:                                   # never let the auxiliary line break the bench
-            rule_engine = {"error": repr(exc)}
-
-    # ---- CPU baseline on rank 0 (bounded sample) ----------------------------------------------------
+    # ---- CPU baseline on rank 0 (bounded sample) and the comparison of what was timed with its tables --------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    verified = None
+    if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as O
         O.build()
         dp = "reference tf_dp_weight (oracle/_ref)" if O.use_reference_dp(True) else "oracle DP restatement"
         t0 = time.perf_counter()
-        Us = reference_step(tables, O, 1)        # the whole workload once, on one host thread (~12 s)
+        Us, kept = reference_step(tables, O, 1, keep=True)        # the whole workload once, on one host thread (~13 s)
         dt = time.perf_counter() - t0
         cpu = {"value": Us / dt, "unit": "CpG/s", "cores": 1, "kind": "port",
                "sample": f"one pass over the whole workload ({Us} CpGs, {dt:.1f} s), single thread; oracle C restatement "
                          f"of methylation_detection, DP = {dp}"}
+        verified = {
+            "segments_equal_cpu": tables_match(seg_v, [k[0] for k in kept], job_ids),
+            "pmd_candidate_segments_equal_cpu": tables_match(pmd_v, [k[1] for k in kept], job_ids),
+            "what": "segment boundaries (start, end) of the UMR/LMR segmentation and of the PMD std fusion computed by the "
+                    "timed resident step on this rank's chromosomes against the CPU leg's, chromosome by chromosome; "
+                    "e2e tables against the resident step's gathered tables bit for bit",
+            "e2e_region_tables_equal_resident": e2e_equal,
+        }
+        # the rule engine's output of one chromosome (the smallest of this rank) against the chain of CPU restatements
+        try:
+            from oracle import rule_engine as RE
+            jsmall = int(min(mine, key=lambda j: sizes[j]))
+            t = tables[jsmall]
+            u, inv = np.unique(t["pos"], return_inverse=True)
+            pooled = dict(estimate_id=np.ones(u.size, np.int32), pos=u.astype(np.int32),
+                          Nmeth=np.bincount(inv, t["Nmeth"], u.size).astype(np.int32),
+                          coverage=np.bincount(inv, t["coverage"], u.size).astype(np.int32))
+            o = O.detect(t, O.MODEL_FAST, lambda2=LAMBDA2, tol_val=TOL, max_iter=1)
+            want = RE.segment_methylation_singlechr(pooled, o["estimates"])
+            m = reg_seg["job"] == jsmall
+            pm = reg_pmd["job"] == jsmall
+            ok = (int(m.sum()) == want["lmr_umr_valley"]["start"].size and int(pm.sum()) == want["pmd"]["start"].size)
+            if ok:
+                for k in ("start", "end", "category", "pmd_status", "num_cpgs"):
+                    ok = ok and np.array_equal(np.asarray(reg_seg[k][m], np.int64), np.asarray(want["lmr_umr_valley"][k], np.int64))
+                for k in ("start", "end", "num_cpgs"):
+                    ok = ok and np.array_equal(np.asarray(reg_pmd[k][pm], np.int64), np.asarray(want["pmd"][k], np.int64))
+            verified["rule_engine_sample_equal_cpu"] = bool(ok)
+            verified["rule_engine_sample"] = f"chromosome {jsmall} ({int(u.size)} CpGs): {int(m.sum())} region rows, {int(pm.sum())} PMDs"
+        except Exception as exc:
+            verified["rule_engine_sample_equal_cpu"] = None
+            verified["rule_engine_sample"] = repr(exc)
+        verified["all"] = bool(verified["segments_equal_cpu"] and verified["pmd_candidate_segments_equal_cpu"]
+                               and verified["rule_engine_sample_equal_cpu"] is not False and e2e_equal is not False)
 
     if rank == 0:
+        cat = reg_seg["category"]
         line = {
             "metric": "CpGs/sec through IRLS+weighted 1D FLSA", "value": value, "unit": "CpG/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, tables, ptr, U), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "roofline_largest_bandwidth_kernel": roofline_bw, "cpu_baseline": cpu,
-            "kernels": table[:16], "resident_pipelined": resident_pool, "ms_per_step_with_kernel_events": ms_profiled,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args, tables, ptr, U),
+                           partition="one genome; its 24 chromosomes assigned to the ranks longest-first (LPT), no data-path "
+                                     "collective; the per-shard region tables pushed into every rank's HBM at the end",
+                           jobs_per_rank=np.bincount(rank_of, minlength=world).tolist(),
+                           rows_per_rank=np.bincount(rank_of, weights=sizes, minlength=world).astype(np.int64).tolist(),
+                           gather_transport=gather.transport),
+            "clocks": clocks, "e2e": e2e, "e2e_per_cpg_outputs": e2e_percpg, "gpu_launches": int(launches),
+            "verified": verified,
+            "roofline": roofline, "roofline_largest_bandwidth_kernel": roofline_bw, "roofline_step": step_roofline,
+            "cpu_baseline": cpu,
+            "kernels": table[:20], "ms_per_step_with_kernel_events": ms_profiled,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
-            "host_wall_ms_each_step": step_wall_res, "disturbed_attempts": disturbed, "cpu_binding": numa,
-            "segments": {"umr_lmr_segments": int(nseg), "pmd_segments": int(npmd)}, "gathered": gathered,
-            "rule_engine": rule_engine,
+            "host_wall_ms_each_step": step_wall_res, "cpu_binding": numa,
+            "step": "per rank: ml_batch_detect + ml_gather_push (segments, call table, PMD std fusion, rule engine, region tables, "
+                    "push into every rank's window) + the counts' all-gather; inputs resident",
+            "regions": {"umr_lmr_segments_this_rank": int(nseg_tab), "pmd_candidate_segments_this_rank": int(npmd_tab),
+                        "region_rows": int(cat.size), "lmr": int((cat == 1).sum()), "umr": int((cat == 2).sum()),
+                        "dmv": int((cat == 3).sum()), "pmds": int(reg_pmd["start"].size),
+                        "rows_per_rank": [int(c[0]) for c in counts], "pmds_per_rank": [int(c[1]) for c in counts]},
         }
         print(json.dumps(line), flush=True)
         if args.out:
             with open(args.out, "a") as f:
                 f.write(json.dumps(line) + "\n")
+    gather.close()
     batch.free()
     eng.close()
     if world > 1:

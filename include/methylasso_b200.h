@@ -142,7 +142,7 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
 
 /* ---- detection: signal_detection_fast_singlechr / signal_detection_singlechr /
  *      difference_detection_singlechr (src/MethyLasso_cpp.cpp:13-26), batched over jobs --------- */
-/* Make the rows of the jobs resident: pos / nmeth / coverage are copied to the GPU (12 bytes per row); dataset,
+/* Make the rows of the jobs resident: pos / nmeth / coverage are copied to the GPU (6 to 12 bytes per row); dataset,
  * condition and replicate are factor codes that the reference reads where the dataset changes only
  * (core/Observations.hpp:36-56; core/data_design_helpers.cpp:17-23), so they are reduced on the host to one entry
  * per run of equal dataset codes (a streaming compare over the dataset column while the DMA runs) and never
@@ -151,6 +151,16 @@ ML_API int ml_weighted_1d_flsa_batch_device(ml_engine *eng, int nseries, const i
 ML_API int ml_batch_upload(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
                     const int32_t *condition, const int32_t *replicate, const int32_t *pos,
                     const int32_t *nmeth, const int32_t *coverage, ml_batch **out, int *status);
+/* ml_batch_upload in two halves, for callers that overlap the host work of one batch with the transfers of another
+ * (several engines of one GPU): ml_batch_stage is host work only - the run table, and Nmeth / coverage packed into the
+ * engine's page-locked staging area with one or two bytes per count when every count of the batch fits (else the
+ * columns travel as they are) - and ml_batch_commit copies pos and the packed counts (6 or 8 bytes per row instead
+ * of 12) and unpacks them on the device.  The caller's columns must stay valid until the commit; one staged batch per
+ * engine at a time.  ml_batch_upload is the two calls in a row. */
+ML_API int ml_batch_stage(ml_engine *eng, int njobs, const int64_t *job_ptr, const int32_t *dataset,
+                   const int32_t *condition, const int32_t *replicate, const int32_t *pos,
+                   const int32_t *nmeth, const int32_t *coverage, ml_batch **out);
+ML_API int ml_batch_commit(ml_engine *eng, ml_batch *b);
 /* The same for a caller that already has the runs (R: rows are keyed by (chr, dataset, pos), so
  * data[, .(.N, condition[1], replicate[1]), by = .(chr, dataset)] is the run table): datasets of job j are entries
  * dset_ptr[j] .. dset_ptr[j+1]-1 of dset_row (job-relative first row; 0 for the first), dset_condition and
@@ -412,6 +422,30 @@ ML_API int ml_result_segment_methylation(ml_engine *eng, ml_result *r, double to
                                          int64_t *n_pmd, int32_t *p_job, int32_t *p_condition, uint32_t *p_start,
                                          uint32_t *p_end, double *p_width, int32_t *p_segment_id, double *p_beta,
                                          double *p_std, int8_t *p_category, int32_t *p_num_cpgs, double *p_fused_std);
+
+/* ---- K16: exchange of the per-shard region tables between the GPUs of one box --------------------------------------------
+ * The reference parallelises over chromosomes with forked workers and concatenates what they return
+ * (R/genome_wide.R:6-15, 42-43; R/call.R:230-244 rbindlist).  Here a worker is one process per GPU and the concatenation
+ * is a push over NVLink: every rank owns a window in its HBM (one slot per rank and parity), exported as a CUDA IPC handle;
+ * ml_gather_push runs the rule engine on the resident fit if that has not been done, packs the two region tables of
+ * ml_result_segment_methylation (same columns, `job` mapped through job_ids[] to the caller's global job index) and writes
+ * them into this rank's slot of every opened window with one kernel (peer stores), returning when they have landed.
+ * The caller then all-gathers the two counts per rank (that collective is also the barrier before anybody reads) and
+ * ml_gather_fetch copies the used part of every slot of the LOCAL window to host memory (slot w at w * slot_bytes, laid
+ * out as ml_gather_layout says: offsets[24] of the 13 + 11 columns, each 16-byte aligned, behind a 64-byte header).
+ * peers = 0 writes the local slot only (for a caller that moves slots with a collective of its own: ml_gather_window
+ * gives the device address of the window of a parity).  Alternate parity from call to call. */
+typedef struct ml_gather ml_gather;
+ML_API int ml_gather_layout(int64_t n_seg, int64_t n_pmd, int64_t *offsets, int64_t *total_bytes);
+ML_API int ml_gather_create(ml_engine *eng, int rank, int world, int64_t slot_bytes, ml_gather **out);
+ML_API int ml_gather_ipc_handle(ml_gather *g, void *handle64);
+ML_API int ml_gather_open(ml_gather *g, const void *handles);
+ML_API int ml_gather_window(ml_gather *g, int parity, void **dev_ptr, int64_t *slot_bytes);
+ML_API int ml_gather_push(ml_engine *eng, ml_gather *g, ml_result *r, double tol_val, double max_distance,
+                          const ml_lmr_params *lmr, const ml_valley_params *valley, const ml_pmd_params *pmd, int drop,
+                          const int32_t *job_ids, int parity, int peers, int64_t *n_seg, int64_t *n_pmd);
+ML_API int ml_gather_fetch(ml_engine *eng, ml_gather *g, int parity, const int64_t *used_bytes, void *host_dst);
+ML_API void ml_gather_destroy(ml_gather *g);
 
 /* ---- input codec: methylation count files (MethyLasso.R:246-262: fread(file, select = c(1, 2, a, b))) -----------------
  * Parses the text of one file on the GPU: column 1 = chromosome, column 2 = position, col_a / col_b (0-based, >= 2) =

@@ -83,6 +83,8 @@ SIGNATURES = {
     "ml_weighted_1d_flsa_batch": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_weighted_1d_flsa_batch_device": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, C.c_double, _P]),
     "ml_batch_upload": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P), _P]),
+    "ml_batch_stage": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
+    "ml_batch_commit": (C.c_int, [_P, _P]),
     "ml_batch_upload_runs": (C.c_int, [_P, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "ml_batch_free": (None, [_P]),
     "ml_batch_detect": (C.c_int, [_P, _P, C.POINTER(MlParams), C.POINTER(_P), _P]),
@@ -119,6 +121,15 @@ SIGNATURES = {
     "ml_result_segment_methylation": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams),
                                                 C.POINTER(MlValleyParams), C.POINTER(MlPmdParams), C.c_int, _I64P] + [_P] * 13
                                       + [_I64P] + [_P] * 11),
+    "ml_gather_layout": (C.c_int, [C.c_int64, C.c_int64, _P, _I64P]),
+    "ml_gather_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
+    "ml_gather_ipc_handle": (C.c_int, [_P, _P]),
+    "ml_gather_open": (C.c_int, [_P, _P]),
+    "ml_gather_window": (C.c_int, [_P, C.c_int, C.POINTER(_P), _I64P]),
+    "ml_gather_push": (C.c_int, [_P, _P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams), C.POINTER(MlValleyParams),
+                                 C.POINTER(MlPmdParams), C.c_int, _P, C.c_int, C.c_int, _I64P, _I64P]),
+    "ml_gather_fetch": (C.c_int, [_P, _P, C.c_int, _P, _P]),
+    "ml_gather_destroy": (None, [_P]),
     "ml_text_parse": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_char, C.POINTER(_P), _I64P, _I64P]),
     "ml_text_fetch": (C.c_int, [_P, _P] + [_P] * 8),
     "ml_text_free": (None, [_P]),

@@ -225,6 +225,22 @@ class Engine:
                                              C.byref(h), None))
         return Batch(self, h, job_ptr.size - 1)
 
+    def stage(self, job_ptr, cols) -> "Batch":
+        """First half of `upload` (host work only: run table, counts packed for the bus); finish with `commit`.  The
+        columns must stay alive and unchanged until then."""
+        job_ptr = np.ascontiguousarray(job_ptr, dtype=np.int64)
+        c = {k: _i32(cols[k]) for k in _COLUMNS}
+        h = C.c_void_p()
+        self._check(self.lib.ml_batch_stage(self.h, job_ptr.size - 1, _p(job_ptr), *[_p(c[k]) for k in _COLUMNS], C.byref(h)))
+        b = Batch(self, h, job_ptr.size - 1)
+        b._keep = (job_ptr, c)
+        return b
+
+    def commit(self, batch: "Batch") -> "Batch":
+        self._check(self.lib.ml_batch_commit(self.h, batch.h))
+        batch._keep = None
+        return batch
+
     def upload_runs(self, job_ptr, dset_ptr, dset_row, dset_condition, dset_replicate, cols) -> "Batch":
         """ml_batch_upload_runs: the caller hands the dataset runs (first row, condition, replicate of every dataset
         of every job) instead of the three factor columns; cols needs pos, Nmeth, coverage only."""
@@ -636,6 +652,9 @@ class EnginePool:
         # with compute); taking turns lets group 1 compute while group 2 uploads.
         self.h2d_turn = threading.Lock()
         self.d2h_turn = threading.Lock()
+        # the host passes over a group's input columns (run scan, packing of the counts) use several threads each:
+        # one group at a time, so that the first group is ready for the bus as early as possible
+        self.pack_turn = threading.Lock()
         # one long-lived worker thread per engine (a fresh thread per call makes the CUDA runtime set up
         # per-thread state again and again; measured as a 100 ms hiccup every ~64 threads)
         self._tasks = [queue.Queue() for _ in range(n_engines)]

@@ -40,6 +40,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    # host-only passes over the input columns: the host compiler alone (function clones for AVX2, chosen at load time)
+    hobj = os.path.join(objdir, "hostpack.o")
+    hcmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-pthread", "-c",
+            os.path.join(CSRC, "hostpack.cpp"), "-o", hobj]
+    if verbose:
+        print(" ".join(hcmd))
+    subprocess.check_call(hcmd)
     objs = []
     for src, obj, p in procs:
         out, _ = p.communicate()
@@ -48,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
-    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", OUT, *objs, hobj, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-pthread"]
     subprocess.check_call(cmd)
     return OUT
 

@@ -197,6 +197,7 @@ void ml_engine_destroy(ml_engine* eng) {
   if (eng->e.pool) cudaMemPoolDestroy(eng->e.pool);
   if (eng->e.mailbox.host) cudaFreeHost(eng->e.mailbox.host);
   if (eng->e.mailbox.in_host) cudaFreeHost(eng->e.mailbox.in_host);
+  if (eng->e.stage_host) cudaFreeHost(eng->e.stage_host);
   delete eng;
 }
 
@@ -421,6 +422,34 @@ int ml_batch_upload(ml_engine* eng, int njobs, const int64_t* job_ptr, const int
   if (status)
     for (int j = 0; j < njobs; ++j) status[j] = 0;  // validation runs on the device inside detect
   *out = h.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_batch_stage(ml_engine* eng, int njobs, const int64_t* job_ptr, const int32_t* dataset, const int32_t* condition,
+                   const int32_t* replicate, const int32_t* pos, const int32_t* nmeth, const int32_t* coverage,
+                   ml_batch** out) {
+  if (!eng || !out || !job_ptr) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *out = nullptr;
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  if (njobs > 0 && job_ptr[njobs] > 0 && (!dataset || !condition || !replicate || !pos || !nmeth || !coverage))
+    throw MlError(ML_ERR_BAD_ARGUMENT, "NULL column (data should contain columns dataset, condition, "
+                                       "replicate, pos, Nmeth and coverage!)");
+  auto h = std::make_unique<ml_batch>();
+  h->b = batch_stage(eng->e, njobs, job_ptr, dataset, condition, replicate, pos, nmeth, coverage);
+  *out = h.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_batch_commit(ml_engine* eng, ml_batch* b) {
+  if (!eng || !b || !b->b) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  batch_commit(eng->e, *b->b);
   return ML_OK;
   ML_CATCH
 }
@@ -1306,6 +1335,224 @@ int ml_result_segment_methylation(ml_engine* eng, ml_result* r, double tol_val, 
   return ML_OK;
   ML_CATCH
 }
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// K16: the exchange of the per-shard region tables (what R/call.R:233-244 does with rbindlist over the chromosomes a
+// worker handled, R/genome_wide.R:6-15 with the fits).  One process per GPU; every rank owns a WINDOW in its HBM with
+// one slot per rank and parity, exported with cudaIpcGetMemHandle and mapped by the peers.  A rank's push is ONE kernel
+// that packs its two region tables and writes them into its slot of EVERY rank's window over NVLink (peer stores): the
+// tables never touch the host on their way.  Ordering between ranks (all pushes done before anybody reads) is the
+// caller's collective on the counts (torch.distributed); slots of the two parities alternate from call to call, so a
+// fast rank's next push cannot overwrite what a slow rank is still reading.
+// Slot layout: 64-byte header {n_seg, n_pmd}, then the 13 + 11 columns back to back, each padded to 16 bytes
+// (ml_gather_layout is the one statement of it).
+// ------------------------------------------------------------------------------------------------
+struct ml_gather {
+  int device = 0, rank = 0, world = 1;
+  int64_t slot_bytes = 0;
+  char* local = nullptr;                  // 2 * world * slot_bytes
+  std::vector<char*> window;              // per rank: base of that rank's window as mapped here
+  std::vector<bool> mapped;
+};
+
+namespace {
+constexpr int GATHER_COLS = 24;
+constexpr int GATHER_MAX_WORLD = 16;
+const int kGatherElem[GATHER_COLS] = {4, 4, 4, 4, 8, 4, 8, 8, 8, 4, 8, 1, 1,      // job condition start end width segment_id beta coverage pseudoweight num_cpgs std category pmd_status
+                                      4, 4, 4, 4, 8, 4, 8, 8, 1, 4, 8};           // job condition start end width segment_id beta std category num_cpgs fused_std
+int64_t gather_layout(int64_t n_seg, int64_t n_pmd, int64_t* off) {
+  int64_t at = 64;
+  for (int c = 0; c < GATHER_COLS; ++c) {
+    off[c] = at;
+    at += ((c < 13 ? n_seg : n_pmd) * kGatherElem[c] + 15) / 16 * 16;
+  }
+  return at;
+}
+struct PushArgs {
+  const char* src[GATHER_COLS];
+  int64_t bytes[GATHER_COLS];
+  int64_t off[GATHER_COLS];
+  char* dst[GATHER_MAX_WORLD];
+  int world;
+  int64_t n_seg, n_pmd;
+  const int32_t* job_ids;                // shard-local job index -> global job (columns 0 and 13)
+};
+__global__ void __launch_bounds__(256) k_gather_push(PushArgs A) {
+  const int c = blockIdx.y;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if (c == GATHER_COLS) {                // header
+    if (tid == 0)
+      for (int r = 0; r < A.world; ++r) {
+        int64_t* h = reinterpret_cast<int64_t*>(A.dst[r]);
+        h[0] = A.n_seg;
+        h[1] = A.n_pmd;
+      }
+    return;
+  }
+  const bool remap = (c == 0 || c == 13) && A.job_ids != nullptr;
+  const int64_t nb = A.bytes[c];
+  const int64_t nw = nb / 4;
+  const uint32_t* s4 = reinterpret_cast<const uint32_t*>(A.src[c]);
+  for (int64_t i = tid; i < nw; i += nth) {
+    uint32_t v = s4[i];
+    if (remap) v = (uint32_t)A.job_ids[v];
+    for (int r = 0; r < A.world; ++r) reinterpret_cast<uint32_t*>(A.dst[r] + A.off[c])[i] = v;
+  }
+  for (int64_t i = nw * 4 + tid; i < nb; i += nth)
+    for (int r = 0; r < A.world; ++r) (A.dst[r] + A.off[c])[i] = A.src[c][i];
+}
+}  // namespace
+
+extern "C" {
+
+int ml_gather_layout(int64_t n_seg, int64_t n_pmd, int64_t* offsets, int64_t* total_bytes) {
+  if (n_seg < 0 || n_pmd < 0 || !total_bytes) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  int64_t off[GATHER_COLS];
+  *total_bytes = gather_layout(n_seg, n_pmd, off);
+  if (offsets) memcpy(offsets, off, sizeof off);
+  return ML_OK;
+}
+
+int ml_gather_create(ml_engine* eng, int rank, int world, int64_t slot_bytes, ml_gather** out) {
+  if (!eng || !out || world < 1 || world > GATHER_MAX_WORLD || rank < 0 || rank >= world || slot_bytes < 64)
+    return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  auto g = std::make_unique<ml_gather>();
+  g->device = eng->e.device;
+  g->rank = rank;
+  g->world = world;
+  g->slot_bytes = (slot_bytes + 255) / 256 * 256;
+  // plain cudaMalloc: memory of a stream-ordered pool cannot be exported as an IPC handle
+  ML_CUDA(cudaMalloc((void**)&g->local, (size_t)(2 * world * g->slot_bytes)));
+  ML_CUDA(cudaMemset(g->local, 0, (size_t)(2 * world * g->slot_bytes)));
+  g->window.assign(world, nullptr);
+  g->mapped.assign(world, false);
+  g->window[rank] = g->local;
+  *out = g.release();
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_gather_ipc_handle(ml_gather* g, void* handle64) {
+  if (!g || !handle64) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ML_CUDA(cudaSetDevice(g->device));
+  cudaIpcMemHandle_t h;
+  ML_CUDA(cudaIpcGetMemHandle(&h, g->local));
+  memcpy(handle64, &h, 64);
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_gather_open(ml_gather* g, const void* handles) {
+  if (!g || !handles) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; ++r) {
+    if (r == g->rank || g->mapped[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    ML_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->window[r] = (char*)p;
+    g->mapped[r] = true;
+  }
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_gather_window(ml_gather* g, int parity, void** dev_ptr, int64_t* slot_bytes) {
+  if (!g || !dev_ptr) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  *dev_ptr = g->local + (size_t)(parity & 1) * g->world * g->slot_bytes;
+  if (slot_bytes) *slot_bytes = g->slot_bytes;
+  return ML_OK;
+}
+
+int ml_gather_push(ml_engine* eng, ml_gather* g, ml_result* r, double tol_val, double max_distance, const ml_lmr_params* lmr,
+                   const ml_valley_params* valley, const ml_pmd_params* pmd, int drop, const int32_t* job_ids, int parity,
+                   int peers, int64_t* n_seg, int64_t* n_pmd) {
+  if (!eng || !g || !r || !n_seg || !n_pmd) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ml_pmd_params pp{1000.0, 0.15, 0.75, 1, 1};
+  if (pmd) pp = *pmd;
+  RuleState* st = nullptr;
+  const int rc = rule_state(eng, r, tol_val, max_distance, pp.pmd_lambda2, lmr, valley, pp.split_pmds, &st);
+  if (rc) return rc;
+  rule_calls(eng, r, *st, pp, true);
+  drop = drop ? 1 : 0;
+  if (st->regions_drop != drop) {
+    region_tables_device(eng->e, *r->r->call_cache, st->S.v, st->S.M, st->calls, st->F, drop, st->regions);
+    st->regions_drop = drop;
+  }
+  const RegionTables& T = st->regions;
+  *n_seg = T.n_seg;
+  *n_pmd = T.n_pmd;
+  PushArgs A;
+  memset(&A, 0, sizeof A);
+  const int64_t total = gather_layout(T.n_seg, T.n_pmd, A.off);
+  if (total > g->slot_bytes) return fail(ML_ERR_BAD_ARGUMENT, "ml_gather_push: the tables do not fit the slot");
+  const void* src[GATHER_COLS] = {T.s_job.p, T.s_condition.p, T.s_start.p, T.s_end.p, T.s_width.p, T.s_segment_id.p, T.s_beta.p,
+                                  T.s_coverage.p, T.s_pseudoweight.p, T.s_num_cpgs.p, T.s_std.p, T.s_category.p,
+                                  T.s_pmd_status.p, T.p_job.p, T.p_condition.p, T.p_start.p, T.p_end.p, T.p_width.p,
+                                  T.p_segment_id.p, T.p_beta.p, T.p_std.p, T.p_category.p, T.p_num_cpgs.p, T.p_fused_std.p};
+  int64_t most = 0;
+  for (int c = 0; c < GATHER_COLS; ++c) {
+    A.src[c] = (const char*)src[c];
+    A.bytes[c] = (c < 13 ? T.n_seg : T.n_pmd) * kGatherElem[c];
+    most = std::max(most, A.bytes[c]);
+  }
+  A.n_seg = T.n_seg;
+  A.n_pmd = T.n_pmd;
+  // destinations: this rank's slot in every mapped window (peers != 0) or in its own window only (the caller moves
+  // the slot with a collective of its own)
+  const size_t slot = ((size_t)(parity & 1) * g->world + g->rank) * g->slot_bytes;
+  A.world = 0;
+  for (int w = 0; w < g->world; ++w) {
+    if (w != g->rank && !(peers && g->mapped[w])) continue;
+    A.dst[A.world++] = g->window[w] + slot;
+  }
+  DevBuf<int32_t> d_ids;
+  if (job_ids) {
+    d_ids.alloc(eng->e.stream, r->r->jobs.size());
+    d_ids.upload(job_ids, r->r->jobs.size());
+    A.job_ids = d_ids.p;
+  }
+  const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (most / 4 + 255) / 256)), GATHER_COLS + 1);
+  ML_LAUNCH(eng->e, "k_gather_push", k_gather_push<<<grid, 256, 0, eng->e.stream>>>(A));
+  eng->e.prof.add_work("k_gather_push", (double)total * (1 + A.world));
+  stream_sync(eng->e.stream);      // peer stores have landed when this returns
+  return ML_OK;
+  ML_CATCH
+}
+
+int ml_gather_fetch(ml_engine* eng, ml_gather* g, int parity, const int64_t* used_bytes, void* host_dst) {
+  if (!eng || !g || !used_bytes || !host_dst) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(g->device));
+  for (int w = 0; w < g->world; ++w) {
+    if (used_bytes[w] < 0 || used_bytes[w] > g->slot_bytes) return fail(ML_ERR_BAD_ARGUMENT, "ml_gather_fetch: bad size");
+    if (!used_bytes[w]) continue;
+    const size_t slot = ((size_t)(parity & 1) * g->world + w) * g->slot_bytes;
+    ML_CUDA(cudaMemcpyAsync((char*)host_dst + (size_t)w * g->slot_bytes, g->local + slot, (size_t)used_bytes[w],
+                            cudaMemcpyDeviceToHost, eng->e.stream));
+  }
+  stream_sync(eng->e.stream);
+  return ML_OK;
+  ML_CATCH
+}
+
+void ml_gather_destroy(ml_gather* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  for (int w = 0; w < g->world; ++w)
+    if (w != g->rank && g->mapped[w]) cudaIpcCloseMemHandle(g->window[w]);
+  cudaFree(g->local);
+  delete g;
+}
+
 }  // extern "C"
 
 namespace ml {

@@ -114,7 +114,9 @@ struct Engine {
   int flsa_sequential = 0;  // 1 = one thread per series start-to-end (bit-faithful verification mode)
   // chunk / warm-up lengths by series length (read from the environment once, when the engine is created)
   int flsa_small_n = 262144, flsa_chunk_big = 448, flsa_warm_big = 512, flsa_chunk_small = 64, flsa_warm_small = 768;
-  int host_threads = 4;     // host threads of batch_upload's run scan over the dataset column
+  int host_threads = 4;     // host threads of batch_upload's passes over the input columns (run scan, packing of the counts)
+  char* stage_host = nullptr;   // page-locked staging area of batch_stage (grown on demand, freed with the engine)
+  size_t stage_cap = 0;
   int want_mu = 1;          // 0: a one-step fit does not store the per-row mu (nothing in the reference's R layer reads it)
   // launch accounting for bench.py's gpu_launches
   long long launches = 0;

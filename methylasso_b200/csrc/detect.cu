@@ -23,9 +23,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <thread>
+#include <atomic>
 
 #include "detect.cuh"
+#include "hostpack.h"
 #include "tiles.cuh"
 
 namespace ml {
@@ -917,32 +918,14 @@ k_fill_estimate_id(const ParTile* __restrict__ tiles, const JobDev* __restrict__
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// indices i in [lo, hi), i >= 1, with v[i] != v[i - 1]
-void transitions_in(const int32_t* v, int64_t lo, int64_t hi, std::vector<int64_t>& out) {
-  constexpr int64_t B = 4096;
-  int64_t i = std::max<int64_t>(lo, 1);
-  while (i < hi) {
-    const int64_t e = std::min(hi, i + B);
-    const int32_t first = v[i - 1];
-    int32_t acc = 0;
-    for (int64_t k = i; k < e; ++k) acc |= v[k] ^ first;      // vectorised by the host compiler
-    if (acc)
-      for (int64_t k = i; k < e; ++k)
-        if (v[k] != v[k - 1]) out.push_back(k);
-    i = e;
-  }
-}
-
 std::vector<int64_t> find_transitions(const int32_t* v, int64_t n, int threads) {
   std::vector<int64_t> all;
   if (n < 2) return all;
-  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n / (1 << 20)));
+  const int T = (int)std::max<int64_t>(1, std::min<int64_t>(threads, n / (1 << 18)));
   if (T <= 1) { transitions_in(v, 0, n, all); return all; }
-  std::vector<std::vector<int64_t>> part(T);
-  std::vector<std::thread> th;
-  for (int t = 0; t < T; ++t)
-    th.emplace_back([&, t] { transitions_in(v, n * t / T, n * (t + 1) / T, part[t]); });
-  for (auto& x : th) x.join();
+  const int pieces = 4 * T;
+  std::vector<std::vector<int64_t>> part(pieces);
+  parallel_for(pieces, T, [&](int t) { transitions_in(v, n * t / pieces, n * (t + 1) / pieces, part[t]); });
   for (auto& pv : part) all.insert(all.end(), pv.begin(), pv.end());
   return all;
 }
@@ -1035,12 +1018,29 @@ void batch_copy_columns(Batch& b, const int32_t* pos, const int32_t* nmeth, cons
 
 }  // namespace
 
-std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
-                                    const int32_t* condition, const int32_t* replicate,
-                                    const int32_t* pos, const int32_t* nmeth, const int32_t* cov) {
+// device side of the packing: one thread per four rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_unpack_counts(const T* __restrict__ packed, int64_t nrows4, int32_t* __restrict__ nmeth, int32_t* __restrict__ cov) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nrows4) return;
+  T v[8];
+  if (sizeof(T) == 1) *reinterpret_cast<uint2*>(v) = __ldg(reinterpret_cast<const uint2*>(packed) + q);
+  else *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(packed) + q);
+  reinterpret_cast<int4*>(nmeth)[q] = make_int4((int)v[0], (int)v[2], (int)v[4], (int)v[6]);
+  reinterpret_cast<int4*>(cov)[q] = make_int4((int)v[1], (int)v[3], (int)v[5], (int)v[7]);
+}
+
+std::unique_ptr<Batch> batch_stage(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                                   const int32_t* condition, const int32_t* replicate,
+                                   const int32_t* pos, const int32_t* nmeth, const int32_t* cov) {
   auto b = batch_begin(eng, njobs, job_ptr);
-  batch_copy_columns(*b, pos, nmeth, cov);                     // DMA runs while the host looks for the runs
-  const std::vector<int64_t> tr = find_transitions(dataset, b->nrows, eng.host_threads);
+  b->h_pos = pos;
+  b->h_nmeth = nmeth;
+  b->h_cov = cov;
+  const int T = std::max(1, eng.host_threads);
+  // ---- the run table (dataset / condition / replicate never leave the host) ----
+  const std::vector<int64_t> tr = find_transitions(dataset, b->nrows, T);
   size_t ti = 0;
   std::vector<int64_t> starts;
   std::vector<int32_t> dsv, cond, rep;
@@ -1054,7 +1054,92 @@ std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_p
     add_job_runs(*b, j1 - j0, starts, dsv, cond, rep, pos + j0);
     b->last_condition.push_back(j1 > j0 ? condition[j1 - 1] : 0);
   }
-  stream_sync(eng.stream);  // the caller may reuse its buffers after return
+  // ---- Nmeth / coverage packed for the bus, laid out as the device columns are (jobs at multiples of ROW_ALIGN) ----
+  const size_t need = 4 * ((size_t)b->nrows_dev + ROW_ALIGN);      // two 16-bit counts per row at most
+  if (eng.stage_cap < need) {
+    if (eng.stage_host) cudaFreeHost(eng.stage_host);
+    eng.stage_host = nullptr;
+    eng.stage_cap = 0;
+    ML_CUDA(cudaHostAlloc((void**)&eng.stage_host, need + need / 8, cudaHostAllocPortable));
+    eng.stage_cap = need + need / 8;
+  }
+  if (b->nrows == 0) { b->pack_bytes = 1; return b; }
+  // pieces of at most 2^18 rows, handed out one at a time to the pool's threads (a piece never spans two jobs)
+  struct Piece { int job; int64_t lo, hi; };
+  std::vector<Piece> pieces;
+  for (int j = 0; j < njobs; ++j)
+    for (int64_t lo = b->job_ptr[j]; lo < b->job_ptr[j + 1]; lo += (1 << 18))
+      pieces.push_back(Piece{j, lo, std::min<int64_t>(lo + (1 << 18), b->job_ptr[j + 1])});
+  auto run = [&](auto tag) -> bool {
+    typedef decltype(tag) U;
+    U* out = reinterpret_cast<U*>(eng.stage_host);
+    std::atomic<int> bad{0};
+    parallel_for((int)pieces.size(), T, [&](int k) {
+      if (bad.load(std::memory_order_relaxed)) return;
+      const Piece& pc = pieces[k];
+      const int64_t shift = b->dev_row0[pc.job] - b->job_ptr[pc.job];      // caller row -> device row
+      bool ok;
+      if (sizeof(U) == 1) ok = pack_counts_u8(nmeth, cov, shift, pc.lo + shift, pc.hi + shift, reinterpret_cast<uint8_t*>(out));
+      else ok = pack_counts_u16(nmeth, cov, shift, pc.lo + shift, pc.hi + shift, reinterpret_cast<uint16_t*>(out));
+      if (!ok) bad.store(1, std::memory_order_relaxed);
+    });
+    if (bad.load()) return false;
+    // the padding rows behind every job: zeros
+    for (int j = 0; j < njobs; ++j) {
+      const int64_t e = b->dev_row0[j] + (b->job_ptr[j + 1] - b->job_ptr[j]);
+      const int64_t pad_end = j + 1 < njobs ? b->dev_row0[j + 1] : b->nrows_dev + ROW_ALIGN;
+      memset(out + 2 * e, 0, sizeof(U) * 2 * (size_t)(pad_end - e));
+    }
+    return true;
+  };
+  if (run(uint8_t())) b->pack_bytes = 1;
+  else if (run(uint16_t())) b->pack_bytes = 2;
+  else b->pack_bytes = 0;
+  return b;
+}
+
+void batch_commit(Engine& eng, Batch& b) {
+  if (b.committed) return;
+  cudaStream_t st = eng.stream;
+  if (b.pack_bytes == 0 || b.nrows == 0) {
+    batch_copy_columns(b, b.h_pos, b.h_nmeth, b.h_cov);
+  } else {
+    const size_t n = (size_t)b.nrows_dev + ROW_ALIGN;
+    b.pos.alloc(st, n);
+    b.nmeth.alloc(st, n);
+    b.cov.alloc(st, n);
+    const size_t bytes = 2 * (size_t)b.pack_bytes * n;
+    DevBuf<char> packed(st, bytes);
+    ML_CUDA(cudaMemcpyAsync(packed.p, eng.stage_host, bytes, cudaMemcpyHostToDevice, st));
+    int j = 0;
+    while (j < b.njobs) {                                      // consecutive jobs without padding between them: one copy
+      int k = j;
+      while (k + 1 < b.njobs && b.dev_row0[k + 1] - b.dev_row0[j] == b.job_ptr[k + 1] - b.job_ptr[j]) ++k;
+      const int64_t rows = b.job_ptr[k + 1] - b.job_ptr[j];
+      if (rows > 0)
+        ML_CUDA(cudaMemcpyAsync(b.pos.p + b.dev_row0[j], b.h_pos + b.job_ptr[j], sizeof(int32_t) * (size_t)rows,
+                                cudaMemcpyHostToDevice, st));
+      j = k + 1;
+    }
+    const int64_t n4 = (int64_t)(n / 4);
+    if (b.pack_bytes == 1)
+      ML_LAUNCH(eng, "k_unpack_counts", k_unpack_counts<uint8_t><<<cdiv(n4, 256), 256, 0, st>>>(
+          reinterpret_cast<const uint8_t*>(packed.p), n4, b.nmeth.p, b.cov.p));
+    else
+      ML_LAUNCH(eng, "k_unpack_counts", k_unpack_counts<uint16_t><<<cdiv(n4, 256), 256, 0, st>>>(
+          reinterpret_cast<const uint16_t*>(packed.p), n4, b.nmeth.p, b.cov.p));
+    eng.prof.add_work("k_unpack_counts", (double)(bytes + 8 * n));
+  }
+  stream_sync(st);  // the caller may reuse its buffers after return
+  b.committed = true;
+  b.h_pos = b.h_nmeth = b.h_cov = nullptr;
+}
+
+std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                                    const int32_t* condition, const int32_t* replicate,
+                                    const int32_t* pos, const int32_t* nmeth, const int32_t* cov) {
+  auto b = batch_stage(eng, njobs, job_ptr, dataset, condition, replicate, pos, nmeth, cov);
+  batch_commit(eng, *b);
   return b;
 }
 
@@ -1097,6 +1182,7 @@ std::unique_ptr<Batch> batch_upload_runs(Engine& eng, int njobs, const int64_t* 
     b->last_condition.push_back(d1 > d0 ? dset_condition[d1 - 1] : 0);
   }
   stream_sync(eng.stream);
+  b->committed = true;
   return b;
 }
 
@@ -1120,6 +1206,7 @@ int decode_status(unsigned long long key) { return key == ~0ull ? 0 : (int)(key 
 }  // namespace
 
 std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
+  if (!b.committed) throw MlError(19, "the batch was staged but never uploaded (ml_batch_upload_staged)");
   if (p.optimize_lambda2 || p.optimize_hyper)
     throw MlError(19, "optimize_lambda2 / optimize_hyper are not supported (FALSE at every reference call site)");
   if (p.model < 0 || p.model > 2) throw MlError(19, "unknown model");

@@ -76,6 +76,10 @@ struct Batch {
   std::vector<unsigned long long> host_key;   // first structural offence per job (validation key), ~0: none
   std::vector<int32_t> last_condition;        // condition of each job's last row (data_design_helpers.cpp:23)
   DevBuf<int32_t> pos, nmeth, cov;
+  // between batch_stage and batch_commit: the caller's columns and how Nmeth / coverage were packed for the bus
+  const int32_t *h_pos = nullptr, *h_nmeth = nullptr, *h_cov = nullptr;
+  int pack_bytes = 0;        // bytes per packed count: 1 (all counts < 256), 2 (< 65536), 0: not packed (int32 columns copied as they are)
+  bool committed = false;
   int n_runs(int j) const { return run0[j + 1] - run0[j]; }
 };
 constexpr int ROW_ALIGN = 32;
@@ -155,6 +159,14 @@ int64_t call_differences_device(Engine& eng, const Batch& B, const Result& R, in
 std::unique_ptr<Batch> batch_upload(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
                                     const int32_t* condition, const int32_t* replicate,
                                     const int32_t* pos, const int32_t* nmeth, const int32_t* cov);
+// batch_upload in two halves.  batch_stage is host work only (run table of the factor columns; Nmeth / coverage packed
+// into the engine's page-locked staging area, one or two bytes per count when they all fit - a third to a half of the
+// bytes that cross PCIe); batch_commit copies pos and the packed counts and unpacks them on the device.  The caller's
+// columns must stay valid in between; one staged batch per engine at a time.
+std::unique_ptr<Batch> batch_stage(Engine& eng, int njobs, const int64_t* job_ptr, const int32_t* dataset,
+                                   const int32_t* condition, const int32_t* replicate,
+                                   const int32_t* pos, const int32_t* nmeth, const int32_t* cov);
+void batch_commit(Engine& eng, Batch& b);
 // the same from a caller-made run table: dset_ptr[j] .. dset_ptr[j+1] index the datasets of job j in
 // dset_row (first row of each dataset, job-relative) / dset_condition / dset_replicate
 std::unique_ptr<Batch> batch_upload_runs(Engine& eng, int njobs, const int64_t* job_ptr, const int64_t* dset_ptr,

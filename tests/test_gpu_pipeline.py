@@ -36,7 +36,7 @@ def test_pipeline_region_tables(engine, oracle):
         seg, pmd, status = pipe.segment_methylation()
         seg = {k: v.copy() for k, v in seg.items()}
         pmd = {k: v.copy() for k, v in pmd.items()}
-        assert pipe.h2d_bytes() == 12 * int(ptr[-1])
+        assert pipe.h2d_bytes() == 6 * int(ptr[-1])     # pos + two one-byte counts per row
     finally:
         pipe.close()
     assert not status.any()
@@ -144,3 +144,46 @@ def test_want_mu_off_refuses_mu(engine):
             b.free()
     finally:
         engine.set("want_mu", 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scale", [1, 30, 4000])
+def test_packed_upload_modes(engine, oracle, scale):
+    """ml_batch_stage packs Nmeth / coverage with one byte per count (all < 256), two (all < 65536) or not at all: the
+    fit is the same as the CPU restatement's in every mode, through upload and through stage + commit."""
+    t = synth.chromosome_table(30_000, 606, (2,))
+    t = dict(t, Nmeth=(t["Nmeth"] * scale).astype(np.int32), coverage=(t["coverage"] * scale).astype(np.int32))
+    assert (scale == 1) == (int(t["coverage"].max()) < 256) and (scale <= 30) == (int(t["coverage"].max()) < 65536)
+    ptr = np.array([0, t["pos"].size], np.int64)
+    p = MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+    want = oracle.detect(t, oracle.MODEL_FAST, lambda2=25.0)
+    engine.set("want_mu", 1)
+    for two_calls in (False, True):
+        bt = engine.commit(engine.stage(ptr, t)) if two_calls else engine.upload(ptr, t)
+        res = engine.detect(bt, p)
+        try:
+            got = res.job(0)
+        finally:
+            res.free()
+            bt.free()
+        assert np.array_equal(got["estimates"]["pseudoweight"], want["estimates"]["pseudoweight"])
+        assert np.array_equal(got["estimates"]["betahat"], want["estimates"]["betahat"])
+        assert _close(got["estimates"]["beta"], want["estimates"]["beta"]) and _close(got["mu"], want["mu"])
+
+
+@pytest.mark.gpu
+def test_packed_upload_keeps_the_validation_codes(engine):
+    """A negative count or Nmeth > coverage must still be refused with the reference's own message code
+    (core/Observations.hpp:48-54): the packing falls back to the plain columns / keeps the offending values."""
+    from methylasso_b200 import api
+    t = synth.chromosome_table(5_000, 11, (2,))
+    ptr = np.array([0, t["pos"].size], np.int64)
+    p = MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+    for col, val, code in (("Nmeth", -1, 11), ("coverage", -3, 11), ("Nmeth", 250, 12)):
+        bad = {k: v.copy() for k, v in t.items()}
+        bad[col][1234] = val
+        res = engine.detect_batch(ptr, bad, p)
+        try:
+            assert res.status.tolist() == [code], (col, val, res.status.tolist())
+        finally:
+            res.free()
