@@ -51,25 +51,87 @@ struct PcPieces {         // per piece of split_call: inputs, then what :169-175
   DD* sum;                         // double-double sum of the piece's methylation values (first sweep)
 };
 
-// :169-175  one block per piece: positions with start - 1 <= pos <= end (foverlaps of [pos, pos + 1]), mean of
-// Nmeth / coverage (two-pass, as R's mean), coverage sum, position count, first and last position
+// :169-175  the positions of a piece are those with start - 1 <= pos <= end (foverlaps of [pos, pos + 1]); per piece: mean
+// of Nmeth / coverage (two-pass, as R's mean), coverage sum, position count, first and last position.  Pieces differ in
+// size by five orders of magnitude (a PMD of a few hundred positions, the background between two PMDs with a million),
+// so a piece of more than PC_MIN_SHARE rows is swept by up to PC_SUB blocks, each over a contiguous share of its rows:
+// block k < n takes share 0 of piece k, the blocks behind them take the (piece, share) pairs k_pc_piece_rows listed.  The
+// partial sums are combined per piece in share order (fixed order: the result does not depend on the launch).
+constexpr int PC_SUB = 256;
+constexpr int64_t PC_MIN_SHARE = 1024;            // rows below which a piece is not cut further
+struct PcPart { DD sum; double csum, m, first, last; };
+struct PcShares {
+  int32_t *nshares, *base;   // per piece: number of shares, list position of its share 1
+  int32_t* count;            // listed extra shares
+  int32_t *item, *share;
+  int32_t cap;
+};
+// where the partial result of share y of item i (a piece, or a live piece) lives: the first shares in item order, the
+// listed ones behind them in list order (n = number of items)
+__device__ __forceinline__ size_t pc_slot(int n, int i, int y, int base) { return y == 0 ? (size_t)i : (size_t)n + base + y - 1; }
+__device__ __forceinline__ int pc_nshares(int64_t n) {
+  const int64_t s = (n + PC_MIN_SHARE - 1) / PC_MIN_SHARE;
+  return s < 1 ? 1 : (s > PC_SUB ? PC_SUB : (int)s);
+}
+__device__ __forceinline__ void pc_share(int64_t lo, int64_t hi, int y, int64_t& a, int64_t& b) {
+  const int64_t n = hi - lo;
+  const int64_t len = (n + pc_nshares(n) - 1) / pc_nshares(n);
+  a = lo + y * len;
+  a = a < hi ? a : hi;
+  b = a + len < hi ? a + len : hi;
+}
+// one thread per piece: its group and rows, the number of shares; shares beyond the first go on the list
+__global__ void k_pc_piece_rows(const SegGroup* __restrict__ groups, int ng, const void* __restrict__ pos, int pos_f64, PcPieces P,
+                                PcShares L) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n) return;
+  const int g = pc_find_group(groups, ng, P.job[k], P.est[k]);
+  int64_t lo = 0, hi = 0;
+  if (g >= 0) segment_rows(groups[g], pos, pos_f64, P.start[k], P.end[k], lo, hi);
+  P.group[k] = g;
+  P.row_lo[k] = lo;
+  P.row_hi[k] = hi;
+  const int ns = pc_nshares(hi - lo);
+  L.nshares[k] = ns;
+  int base = 0;
+  if (ns > 1) {
+    base = atomicAdd(L.count, ns - 1);
+    for (int y = 1; y < ns; ++y)
+      if (base + y - 1 < L.cap) { L.item[base + y - 1] = k; L.share[base + y - 1] = y; }
+  }
+  L.base[k] = base;
+}
+// which (piece, share) a WARP works on (most pieces hold a handful of positions: a block each would be mostly launch
+// overhead); false: nothing
+constexpr int PC_WARPS = PC_THREADS / 32;
+__device__ __forceinline__ bool pc_warp_item(int n, const PcShares& L, int& k, int& y) {
+  const int w = blockIdx.x * PC_WARPS + (threadIdx.x >> 5);
+  if (w < n) { k = w; y = 0; return true; }
+  const int idx = w - n;
+  const int cnt = *L.count < L.cap ? *L.count : L.cap;
+  if (idx >= cnt) return false;
+  k = L.item[idx];
+  y = L.share[idx];
+  return true;
+}
 template <class Rows>
 __global__ void __launch_bounds__(PC_THREADS)
-k_pc_piece_stats(const SegGroup* __restrict__ groups, int ng, const void* __restrict__ pos, int pos_f64, Rows rows, PcPieces P) {
-  __shared__ DD smd[PC_THREADS / 32];
-  __shared__ double sms[PC_THREADS / 32];
-  const int k = blockIdx.x;
-  const int g = pc_find_group(groups, ng, P.job[k], P.est[k]);
+k_pc_piece_stats(const SegGroup* __restrict__ groups, const void* __restrict__ pos, int pos_f64, Rows rows, PcPieces P, PcShares L,
+                 PcPart* __restrict__ part) {
+  int k, y;
+  if (!pc_warp_item(P.n, L, k, y)) return;
+  const int lane = threadIdx.x & 31;
+  const int g = P.group[k];
   if (g < 0) {
-    if (threadIdx.x == 0) { P.group[k] = -1; P.ncpg[k] = 0; P.row_lo[k] = P.row_hi[k] = 0; }
+    if (lane == 0) part[pc_slot(P.n, k, y, L.base[k])] = PcPart{DD{0.0, 0.0}, 0.0, 0.0, 4294967296.0, -1.0};
     return;
   }
   const SegGroup G = groups[g];
-  int64_t lo, hi;
-  segment_rows(G, pos, pos_f64, P.start[k], P.end[k], lo, hi);
+  int64_t a, b;
+  pc_share(P.row_lo[k], P.row_hi[k], y, a, b);
   DD sum{0.0, 0.0};
   double csum = 0.0, m = 0.0, first = 4294967296.0, last = -1.0;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += PC_THREADS) {
+  for (int64_t i = a + lane; i < b; i += 32) {
     if (!rows.valid(i)) continue;
     dd_add(sum, rows.x(i));
     csum += rows.cov(i);
@@ -78,39 +140,71 @@ k_pc_piece_stats(const SegGroup* __restrict__ groups, int ng, const void* __rest
     first = fmin(first, p);
     last = fmax(last, p);
   }
-  sum = pc_block_sum(sum, smd);
-  csum = pc_block_sum(csum, sms);
-  m = pc_block_sum(m, sms);
-  // the positions are sorted: first / last valid one by a min / max over the block
+  sum = dd_warp_sum(sum);
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) {
-    first = fmin(first, __shfl_xor_sync(0xffffffffu, first, d));
+    csum += __shfl_xor_sync(0xffffffffu, csum, d);
+    m += __shfl_xor_sync(0xffffffffu, m, d);
+    first = fmin(first, __shfl_xor_sync(0xffffffffu, first, d));     // the positions are sorted: first / last valid one
     last = fmax(last, __shfl_xor_sync(0xffffffffu, last, d));
   }
-  __shared__ double smf[PC_THREADS / 32], sml[PC_THREADS / 32];
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) { smf[threadIdx.x >> 5] = first; sml[threadIdx.x >> 5] = last; }
-  __syncthreads();
-  for (int w = 0; w < PC_THREADS / 32; ++w) { first = fmin(first, smf[w]); last = fmax(last, sml[w]); }
-  double mean = (sum.hi + sum.lo) / m;
-  DD t{0.0, 0.0};
-  if (m > 0 && is_finite(mean))
-    for (int64_t i = lo + threadIdx.x; i < hi; i += PC_THREADS)
-      if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
-  t = pc_block_sum(t, smd);
-  if (m > 0 && is_finite(mean)) mean += (t.hi + t.lo) / m;
-  if (threadIdx.x == 0) {
-    P.group[k] = g;
-    P.ncpg[k] = (int32_t)m;
-    P.row_lo[k] = lo;
-    P.row_hi[k] = hi;
-    P.pstart[k] = m > 0 ? (uint32_t)first : 0u;
-    P.pend[k] = m > 0 ? (uint32_t)last + 2u : 0u;
-    P.beta[k] = mean;
-    P.cov[k] = csum;
-    P.sum[k] = sum;
-  }
+  if (lane == 0) part[pc_slot(P.n, k, y, L.base[k])] = PcPart{sum, csum, m, first, last};
 }
+// one thread per piece: the shares in order -> first-pass mean (left in P.beta for the second pass)
+__global__ void k_pc_piece_mean0(PcPieces P, PcShares L, const PcPart* __restrict__ part) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n) return;
+  DD sum{0.0, 0.0};
+  double csum = 0.0, m = 0.0, first = 4294967296.0, last = -1.0;
+  const int ns = L.nshares[k];
+  for (int y = 0; y < ns; ++y) {
+    const PcPart q = part[pc_slot(P.n, k, y, L.base[k])];
+    sum = dd_merge(sum, q.sum);
+    csum += q.csum;
+    m += q.m;
+    first = fmin(first, q.first);
+    last = fmax(last, q.last);
+  }
+  if (P.group[k] < 0) m = 0.0;
+  P.ncpg[k] = (int32_t)m;
+  P.pstart[k] = m > 0 ? (uint32_t)first : 0u;
+  P.pend[k] = m > 0 ? (uint32_t)last + 2u : 0u;
+  P.beta[k] = (sum.hi + sum.lo) / m;
+  P.cov[k] = csum;
+  P.sum[k] = sum;
+}
+// second pass of R's mean: sum of the deviations from the first-pass mean, per share
+template <class Rows>
+__global__ void __launch_bounds__(PC_THREADS)
+k_pc_piece_dev(Rows rows, PcPieces P, PcShares L, DD* __restrict__ part_t) {
+  int k, y;
+  if (!pc_warp_item(P.n, L, k, y)) return;
+  const int lane = threadIdx.x & 31;
+  const double mean = P.beta[k];
+  int64_t a, b;
+  pc_share(P.row_lo[k], P.row_hi[k], y, a, b);
+  DD t{0.0, 0.0};
+  if (P.group[k] >= 0 && P.ncpg[k] > 0 && is_finite(mean) && a < b) {     // (uniform over the warp)
+    for (int64_t i = a + lane; i < b; i += 32)
+      if (rows.valid(i)) dd_add(t, rows.x(i) - mean);
+    t = dd_warp_sum(t);
+  }
+  if (lane == 0) part_t[pc_slot(P.n, k, y, L.base[k])] = t;
+}
+__global__ void k_pc_piece_mean(PcPieces P, PcShares L, const DD* __restrict__ part_t) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P.n) return;
+  const double m = (double)P.ncpg[k];
+  double mean = P.beta[k];
+  if (m > 0 && is_finite(mean)) {
+    DD t{0.0, 0.0};
+    const int ns = L.nshares[k];
+    for (int y = 0; y < ns; ++y) t = dd_merge(t, part_t[pc_slot(P.n, k, y, L.base[k])]);
+    mean += (t.hi + t.lo) / m;
+  }
+  P.beta[k] = mean;
+}
+
 __global__ void k_pc_live(PcPieces P, int32_t* __restrict__ flag) {
   const int32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < P.n) flag[k] = P.ncpg[k] > 0 ? 1 : 0;
@@ -163,22 +257,50 @@ __global__ void k_pc_region_mean0(PcPieces P, const int32_t* __restrict__ live, 
   R.mean0[v] = (s.hi + s.lo) / m;
   R.count[v] = m;
 }
-// (b) one block per live piece: the two central sums about its region's mean0; a position that two touching pieces
-// share enters both, as in the reference's concatenated betavals
+// (b) per live piece, in shares like the first sweep (block r < n_live: share 0 of live piece r; the listed shares behind
+// them, by way of the piece -> live index map): the two central sums about its region's mean0; a position that two
+// touching pieces share enters both, as in the reference's concatenated betavals
+__global__ void k_pc_live_index(int32_t n_live, const int32_t* __restrict__ live, int32_t* __restrict__ index_of) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_live) index_of[live[r]] = r;
+}
 template <class Rows>
 __global__ void __launch_bounds__(PC_THREADS)
-k_pc_piece_moments(PcPieces P, const int32_t* __restrict__ live, const int32_t* __restrict__ region_of, PcRegion R, Rows rows) {
-  __shared__ DD smd[PC_THREADS / 32];
-  const int r = blockIdx.x;
-  const int32_t k = live[r];
+k_pc_piece_moments(PcPieces P, PcShares L, int32_t n_live, const int32_t* __restrict__ live, const int32_t* __restrict__ index_of,
+                   const int32_t* __restrict__ region_of, PcRegion R, Rows rows, DD* __restrict__ part_t, DD* __restrict__ part_q) {
+  const int w = blockIdx.x * PC_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  int r, k, y;
+  if (w < n_live) { r = w; k = live[r]; y = 0; }
+  else {
+    const int idx = w - n_live;
+    const int cnt = *L.count < L.cap ? *L.count : L.cap;
+    if (idx >= cnt) return;
+    k = L.item[idx];
+    y = L.share[idx];
+    r = index_of[k];
+    if (r < 0) return;                     // the piece holds no position: it is not live
+  }
   const double mean0 = R.mean0[region_of[r]];
+  int64_t a, b;
+  pc_share(P.row_lo[k], P.row_hi[k], y, a, b);
   DD t{0.0, 0.0}, q{0.0, 0.0};
-  if (is_finite(mean0))
-    for (int64_t i = P.row_lo[k] + threadIdx.x; i < P.row_hi[k]; i += PC_THREADS)
+  if (is_finite(mean0) && a < b) {
+    for (int64_t i = a + lane; i < b; i += 32)
       if (rows.valid(i)) { const double d = rows.x(i) - mean0; dd_add(t, d); dd_add(q, d * d); }
-  t = pc_block_sum(t, smd);
-  q = pc_block_sum(q, smd);
-  if (threadIdx.x == 0) { R.t[r] = t; R.q[r] = q; }
+    t = dd_warp_sum(t);
+    q = dd_warp_sum(q);
+  }
+  if (lane == 0) { const size_t at = pc_slot(n_live, r, y, L.base[k]); part_t[at] = t; part_q[at] = q; }
+}
+__global__ void k_pc_piece_moments_sum(PcPieces P, PcShares L, int32_t n_live, const int32_t* __restrict__ live,
+                                       const DD* __restrict__ part_t, const DD* __restrict__ part_q, PcRegion R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_live) return;
+  DD t{0.0, 0.0}, q{0.0, 0.0};
+  const int k = live[r], ns = L.nshares[k];
+  for (int y = 0; y < ns; ++y) { const size_t at = pc_slot(n_live, r, y, L.base[k]); t = dd_merge(t, part_t[at]); q = dd_merge(q, part_q[at]); }
+  R.t[r] = t;
+  R.q[r] = q;
 }
 // (c) one thread per region: mean = mean0 + T / M (R's second pass), sum of squares about it = Q - (T / M) T
 __global__ void k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const int8_t* __restrict__ cat,
@@ -251,7 +373,23 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
   DevBuf<DD> p_sum(st, (size_t)np);
   const PcPieces P{np, pieces.job.p, pieces.est.p, pieces.start.p, pieces.end.p, pieces.fused_std.p, p_group.p, p_ncpg.p,
                    p_lo.p, p_hi.p, p_start.p, p_end.p, p_beta.p, p_cov.p, p_sum.p};
-  ML_LAUNCH(eng, "k_pc_piece_stats", k_pc_piece_stats<RowsFromEstimates><<<np, PC_THREADS, 0, st>>>(d_groups.p, ng, d_pos, pos_f64, rows, P));
+  // shares of the long pieces: at most (rows of the estimates table) / PC_MIN_SHARE of them beyond every piece's first
+  int64_t total_rows = 0;
+  for (const SegGroup& g : groups) total_rows += g.nrows;
+  const int32_t share_cap = (int32_t)(total_rows / PC_MIN_SHARE + 64);
+  DevBuf<int32_t> sh_n(st, (size_t)np), sh_base(st, (size_t)np), sh_count(st, 1), sh_item(st, (size_t)share_cap), sh_share(st, (size_t)share_cap);
+  sh_count.zero();
+  const PcShares L{sh_n.p, sh_base.p, sh_count.p, sh_item.p, sh_share.p, share_cap};
+  ML_LAUNCH(eng, "k_pc_piece_rows", k_pc_piece_rows<<<cdiv(np, 128), 128, 0, st>>>(d_groups.p, ng, d_pos, pos_f64, P, L));
+  {
+    DevBuf<PcPart> part(st, (size_t)np + share_cap);
+    DevBuf<DD> part_t(st, (size_t)np + share_cap);
+    ML_LAUNCH(eng, "k_pc_piece_stats", k_pc_piece_stats<RowsFromEstimates><<<cdiv(np + share_cap, PC_WARPS), PC_THREADS, 0, st>>>(
+        d_groups.p, d_pos, pos_f64, rows, P, L, part.p));
+    ML_LAUNCH(eng, "k_pc_piece_mean0", k_pc_piece_mean0<<<cdiv(np, 128), 128, 0, st>>>(P, L, part.p));
+    ML_LAUNCH(eng, "k_pc_piece_dev", k_pc_piece_dev<RowsFromEstimates><<<cdiv(np + share_cap, PC_WARPS), PC_THREADS, 0, st>>>(rows, P, L, part_t.p));
+    ML_LAUNCH(eng, "k_pc_piece_mean", k_pc_piece_mean<<<cdiv(np, 128), 128, 0, st>>>(P, L, part_t.p));
+  }
   DevBuf<int32_t> flag(st, (size_t)np), live(st, (size_t)np), heads(st, (size_t)np);
   ML_LAUNCH(eng, "k_pc_live", k_pc_live<<<cdiv(np, 256), 256, 0, st>>>(P, flag.p));
   Scan scan;
@@ -270,7 +408,16 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
   const PcRegion Rg{n_out, heads.p, r_mean0.p, r_count.p, r_t.p, r_q.p};
   ML_LAUNCH(eng, "k_pc_region_mean0", k_pc_region_mean0<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, Rg));
   ML_LAUNCH(eng, "k_pc_region_of", k_pc_region_of<<<cdiv(n_live, 256), 256, 0, st>>>(n_live, flag.p, hpos.p, region_of.p));
-  ML_LAUNCH(eng, "k_pc_piece_moments", k_pc_piece_moments<RowsFromEstimates><<<n_live, PC_THREADS, 0, st>>>(P, live.p, region_of.p, Rg, rows));
+  {
+    DevBuf<DD> part_t(st, (size_t)n_live + share_cap), part_q(st, (size_t)n_live + share_cap);
+    DevBuf<int32_t> index_of(st, (size_t)np);
+    ML_CUDA(cudaMemsetAsync(index_of.p, 0xff, sizeof(int32_t) * (size_t)np, st));
+    ML_LAUNCH(eng, "k_pc_live_index", k_pc_live_index<<<cdiv(n_live, 256), 256, 0, st>>>(n_live, live.p, index_of.p));
+    ML_LAUNCH(eng, "k_pc_piece_moments", k_pc_piece_moments<RowsFromEstimates><<<cdiv(n_live + share_cap, PC_WARPS), PC_THREADS, 0, st>>>(
+        P, L, n_live, live.p, index_of.p, region_of.p, Rg, rows, part_t.p, part_q.p));
+    ML_LAUNCH(eng, "k_pc_piece_moments_sum", k_pc_piece_moments_sum<<<cdiv(n_live, 128), 128, 0, st>>>(P, L, n_live, live.p, part_t.p,
+                                                                                                        part_q.p, Rg));
+  }
   ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, cat.p, Rg, o));
   DevBuf<int32_t> gflag(st, (size_t)n_out), gpos(st, (size_t)n_out), gheads(st, (size_t)n_out);
   ML_LAUNCH(eng, "k_pc_group_heads", k_pc_group_heads<<<cdiv(n_out, 256), 256, 0, st>>>(n_out, o, gflag.p));
