@@ -172,7 +172,7 @@ def bind_to_gpu_cpus(gpu_index, world=1):
 
 def make_workload(total_cpgs, seed_offset=0):
     tables = synth.genome_tables(2, total_cpgs=total_cpgs, reps_per_condition=(3,),
-                                 seed=synth.BASE_SEED + 2 + 1000 * seed_offset)
+                                 seed=synth.BASE_SEED + 2 + 1000 * seed_offset, dmv=True)
     ptr, cols = synth.concat_jobs(tables)
     return tables, ptr, cols
 
@@ -454,8 +454,208 @@ def run_dmr(args, local):
     eng.close()
 
 
+def _timed(fn, steps, warmup, sync):
+    """host wall per call, in ms, after warm-up; sync() drains the device"""
+    for _ in range(warmup):
+        fn()
+    sync()
+    out = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fn()
+        sync()
+        out.append((time.perf_counter() - t0) * 1e3)
+    return out
+
+
 def run_aux(args, local):
-    raise SystemExit("--aux %s: not implemented yet" % args.aux)
+    """Auxiliary lines for the other BASELINE.json configs (never the contract line; each prints one JSON line with its
+    own CPU figure from the port on a bounded sample):
+      config0  configs[0]: one chr22-sized sample (0.4 M CpGs, one condition, one replicate), UMR / LMR segmentation + PMDs
+      full     the FULL model (beta-binomial / logit, even bins, max_iter 30 x nouter 20; src/signal_detection.cpp:49-80,
+               src/difference_detection.cpp:13-45) on one chr22-sized chromosome, 3 replicates (and 2 x 2 for the difference)
+      cohort   configs[3]: 64 samples segmented independently, sharded over the ranks by sample (torchrun for N > 1)"""
+    import torch
+    from methylasso_b200 import api
+    from methylasso_b200._native import MlParams
+    from methylasso_b200.pipeline import GenomePipeline
+    from oracle import oracle as O
+    torch.cuda.set_device(local)
+    steps, warm = args.steps, max(3, args.warmup)
+    line = {"aux": args.aux, "n_gpus": 1, "steps": steps, "dtype": "f64", "data": "synthetic"}
+    if args.aux == "config0":
+        eng = api.Engine(local)
+        eng.set("want_mu", 0)
+        t = synth.chromosome_table(400_000, synth.BASE_SEED + 1, (1,))
+        ptr = np.array([0, t["pos"].size], np.int64)
+        p = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+        batch = eng.upload(ptr, t)
+        keep = {}
+
+        def resident():
+            res = eng.detect(batch, p)
+            keep["tables"] = res.segment_methylation_tables(TOL, MAX_DISTANCE, reuse_pinned=True)
+            keep["U"] = res.sizes(0)[1]
+            res.free()
+        pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory().numpy() for k, v in t.items()}
+
+        def e2e():
+            bt = eng.upload(ptr, pin)
+            res = eng.detect(bt, p)
+            keep["tables_e2e"] = res.segment_methylation_tables(TOL, MAX_DISTANCE, reuse_pinned=True)
+            res.free()
+            bt.free()
+        wr = _timed(resident, steps, warm, eng.synchronize)
+        we = _timed(e2e, steps, warm, eng.synchronize)
+        O.build()
+        O.use_reference_dp(True)
+        t0 = time.perf_counter()
+        Us, kept = reference_step([t], O, 1, keep=True)
+        dt = time.perf_counter() - t0
+        U = int(keep["U"])
+        seg, pmd = keep["tables"]
+        line.update({"metric": "CpGs/sec through IRLS+weighted 1D FLSA (aux, configs[0])", "value": U / (np.median(wr) * 1e-3),
+                     "unit": "CpG/s", "ms_per_step": float(np.median(wr)), "host_wall_ms_each_step": [round(x, 3) for x in wr],
+                     "config": {"workload": "configs[0]: one chr22-sized sample, one condition, one replicate, lambda2 = 25, PMD lambda2 = 1000",
+                                "cpgs": U, "rows": int(ptr[-1])},
+                     "e2e": {"value": U / (np.median(we) * 1e-3), "unit": "CpG/s", "ms_per_step": float(np.median(we)),
+                             "h2d_bytes_per_step": 6 * int(ptr[-1]), "d2h_bytes_per_step": GenomePipeline.d2h_bytes_regions(seg, pmd)},
+                     "regions": {"rows": int(seg["start"].size), "pmds": int(pmd["start"].size)},
+                     "cpu_baseline": {"value": Us / dt, "unit": "CpG/s", "cores": 1, "kind": "port",
+                                      "sample": "the whole workload once (%.2f s): fit, segments, call table, PMD std fusion "
+                                                "(no rule engine)" % dt}})
+        batch.free()
+        eng.close()
+    elif args.aux == "full":
+        eng = api.Engine(local)
+        out = {}
+        for name, reps, model, ncpg in (("signal", (3,), 1, 400_000), ("difference", (2, 2), 2, 400_000)):
+            t = synth.chromosome_table(ncpg, synth.BASE_SEED + 7, reps)
+            ptr = np.array([0, t["pos"].size], np.int64)
+            p = MlParams(LAMBDA2, 1000.0, 0.0, TOL, 50.0, 100.0, 30, 20, 1, model, 0, 0)
+            batch = eng.upload(ptr, t)
+            info = {}
+
+            def run():
+                res = eng.detect(batch, p)
+                info.update(res.info(0), P=res.sizes(0)[1], E=res.sizes(0)[2], status=int(res.status[0]))
+                res.free()
+            l0 = eng.launch_count
+            w = _timed(run, max(2, steps // 2), 1, eng.synchronize)
+            launches = (eng.launch_count - l0) // (max(2, steps // 2) + 1)
+            # the port on a bounded sample of the same shape (1/8 of the positions: the fit of the whole chromosome
+            # takes the port minutes)
+            small = synth.chromosome_table(ncpg // 8, synth.BASE_SEED + 7, reps)
+            O.build()
+            t0 = time.perf_counter()
+            o = O.detect(small, model, lambda2=LAMBDA2, max_lambda2=1000.0, tol_val=TOL, max_iter=30, nouter=20, hyper=100.0,
+                         bf_per_kb=50.0, ref=1)
+            dt = time.perf_counter() - t0
+            rows = int(ptr[-1])
+            out[name] = {"rows": rows, "bins_per_estimator": int(info["P"]), "estimators": int(info["E"]), "status": info["status"],
+                         "irls_steps": info["irls_steps"], "dampings": info["dampings"], "outer_iters": info["outer_iters"],
+                         "converged": info["converged"], "ms": float(np.median(w)), "ms_each": [round(x, 2) for x in w],
+                         "rows_per_s": rows / (np.median(w) * 1e-3), "kernel_launches_per_fit": int(launches),
+                         "ms_per_irls_step": float(np.median(w)) / max(1, info["irls_steps"]),
+                         # SURVEY.md 8(d): 36 N + 64 E P bytes per IRLS step
+                         "alg_bytes_per_irls_step": 36 * rows + 64 * int(info["E"]) * int(info["P"]),
+                         "cpu_port": {"rows": int(small["pos"].size), "seconds": dt, "rows_per_s": small["pos"].size / dt,
+                                      "irls_steps": o["irls_steps"], "cores": 1}}
+            pk, _ = peaks()
+            out[name]["frac_of_hbm_per_irls_step"] = (out[name]["alg_bytes_per_irls_step"] / (out[name]["ms_per_irls_step"] * 1e-3)
+                                                      / 1e9 / pk["hbm_gbs"])
+            batch.free()
+        line.update({"metric": "rows/sec through the FULL (beta-binomial / logit) IRLS + FLSA (aux)", "unit": "rows/s",
+                     "value": out["signal"]["rows_per_s"], "ms_per_step": out["signal"]["ms"],
+                     "config": {"workload": "signal_detection / difference_detection (FULL model) on one chr22-sized chromosome: "
+                                            "max_iter 30, nouter 20, 50 bins per kb, hyper 100, lambda2 25"},
+                     "signal": out["signal"], "difference": out["difference"],
+                     "note": "the IRLS / damping decisions are taken on the host: one stream synchronisation and a 40-byte "
+                             "readback per evaluation (a fit of a few hundred evaluations is bound by those round trips and by "
+                             "the latency-bound FLSA passes, not by bandwidth)"})
+        eng.close()
+    elif args.aux == "cohort":
+        import torch.distributed as dist
+        from methylasso_b200 import shard
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:
+            numa = bind_to_gpu_cpus(local, world)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        n_samples, scale = 64, 8
+        mine = [s for s in range(n_samples) if s % world == rank]          # samples are the same size: round-robin
+        t0 = time.perf_counter()
+        samples = []
+        for s_ in mine:
+            tabs = synth.genome_tables(4, total_cpgs=synth.GENOME_CPGS // scale, reps_per_condition=(1,),
+                                       seed=(synth.BASE_SEED + 4) * 1000 + s_)
+            samples.append(synth.concat_jobs(tabs))
+        gen_s = time.perf_counter() - t0
+        G = 4 if world == 1 else 3
+        # one pipeline per sample shape would re-pin per sample; the cohort is processed sample by sample through ONE
+        # pool of engines, the chromosomes of a sample split over the engines
+        pool_pipe = GenomePipeline(samples[0][0], samples[0][1], n_engines=G, device=local, lambda2=LAMBDA2, tol_val=TOL, pin=True)
+        prepared = []                       # every sample's chromosome groups in page-locked memory of their own (the host
+        for ptr, cols in samples:           # buffers the timed calls read from)
+            pool_pipe.rebind(ptr, cols, reuse_pinned=False)
+            prepared.append(pool_pipe.bound())
+        rows_mine = int(sum(int(ptr[-1]) for ptr, _ in samples))
+
+        def run_all():
+            nreg = 0
+            for prep in prepared:
+                pool_pipe.bind(prep)
+                seg, pmd, status = pool_pipe.segment_methylation(MAX_DISTANCE)
+                nreg += int(seg["start"].size)
+            return nreg
+        for _ in range(1):
+            nreg = run_all()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(max(1, steps // 2)):
+            nreg = run_all()
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / max(1, steps // 2)], device="cuda", dtype=torch.float64)
+        tot = torch.tensor([float(sum(int(np.unique(c["pos"][p[j]:p[j + 1]]).size) for p, c in samples[:1] for j in range(p.size - 1)))
+                            * len(samples), float(rows_mine), float(nreg)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        line = None
+        if rank == 0:
+            U = float(tot[0].item())
+            line = {"aux": "cohort", "metric": "CpGs/sec, cohort of 64 samples end to end (aux, configs[3])", "unit": "CpG/s",
+                    "value": U / (float(ms.item()) * 1e-3), "ms_per_step": float(ms.item()), "n_gpus": world, "scaling": "strong",
+                    "config": {"workload": "configs[3]: 64 synthetic single-replicate samples of 24 chromosomes at 1/%d of the genome "
+                                           "size (%d CpGs each: 64 full genomes do not fit the host's memory budget of a bench "
+                                           "run), segmented independently, samples dealt to the ranks round-robin" % (scale, synth.GENOME_CPGS // scale),
+                               "samples": n_samples, "samples_per_rank": len(mine), "engines_per_gpu": G},
+                    "what": "per sample: host columns (pinned) -> ml_batch_stage / commit -> detect -> region tables on the host "
+                            "(GenomePipeline.segment_methylation); max over ranks of the time for the rank's samples",
+                    "rows": float(tot[1].item()), "region_rows": float(tot[2].item()), "generation_s_rank0": gen_s}
+        pool_pipe.close()
+        if world > 1:
+            dist.destroy_process_group()
+        if line is None:
+            return
+        # CPU figure: one sample on one thread
+        O.build()
+        O.use_reference_dp(True)
+        tabs = synth.genome_tables(4, total_cpgs=synth.GENOME_CPGS // scale, reps_per_condition=(1,), seed=(synth.BASE_SEED + 4) * 1000)
+        t0 = time.perf_counter()
+        Us = reference_step(tabs, O, 1)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": Us / dt, "unit": "CpG/s", "cores": 1, "kind": "port", "sample": "one sample of the cohort, %.1f s" % dt}
+    print(json.dumps(line), flush=True)
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(json.dumps(line) + "\n")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -508,7 +708,7 @@ def main():
             run_dmr(args, local)
         return
     if args.aux:
-        if rank == 0:
+        if rank == 0 or args.aux == "cohort":
             run_aux(args, local)
         return
 

@@ -178,6 +178,10 @@ struct DevBuf {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// algorithmic bytes of the launch just made (compulsory reads + writes from the launch's own sizes): bench.py divides
+// them by the kernel's measured time; recorded only while the profiler is on
+#define ML_WORK(ENG, NAME, BYTES) (ENG).prof.add_work(NAME, (double)(BYTES))
+
 // every kernel launch of the engine goes through this: error check, launch count, optional timing
 #define ML_LAUNCH(ENG, NAME, ...)            \
   do {                                       \

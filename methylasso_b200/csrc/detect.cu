@@ -179,7 +179,7 @@ __device__ __forceinline__ void row_residual(int model, int first, int nmeth, in
 //   * the -log pdf of the initial evaluation (Posterior.ipp:25): every parameter and offset is still +0.
 // ------------------------------------------------------------------------------------------------
 template <bool BITMAP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs, const int32_t* __restrict__ alive,
               const int32_t* __restrict__ dptr, const int32_t* __restrict__ pos, const int32_t* __restrict__ nmeth,
               const int32_t* __restrict__ cov, const int64_t* __restrict__ bm0, const int32_t* __restrict__ minpos,
@@ -188,6 +188,9 @@ k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs
   __shared__ double sm[3][8];
   const RowTile t = tiles[blockIdx.x];
   const JobDev J = jobs[t.job];
+  // the unique-position leg is the FAST model's: a compile-time model folds the beta-binomial code (lgamma, log, exp)
+  // out of this instantiation, which halves its registers
+  const int model = BITMAP ? (int)MODEL_FAST : J.model;
   const Rows4 r = rows4(t);
   const bool live = alive[t.job] != 0;
   unsigned long long best = ~0ull;
@@ -203,7 +206,7 @@ k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs
     const int32_t mp = BITMAP ? minpos[t.job] : 0;
     const int64_t b0 = BITMAP ? bm0[t.job] : 0;
     const uint32_t nbits = BITMAP ? (uint32_t)((bm0[t.job + 1] - b0) * 32) : 0u;
-    const double m0 = irls_mu(J.model, 0. + (0. + 1. * 0.));       // mu of the initial evaluation
+    const double m0 = irls_mu(model, 0. + (0. + 1. * 0.));         // mu of the initial evaluation
     uint32_t cw = 0xffffffffu, cb = 0u;                             // bits of one bitmap word, flushed together
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -229,11 +232,11 @@ k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs
         }
       }
       double z, W;
-      row_residual(J.model, 1, nm[q], cv[q], 0.0, J.nu, z, W);
+      row_residual(model, 1, nm[q], cv[q], 0.0, J.nu, z, W);
       sw += W;
       sz += z * W;
       const double nobs = (double)cv[q];
-      lik += irls_minus_log_pdf(J.model, div_nz((double)nm[q], nobs), nobs, m0, J.nu, log2pi);
+      lik += irls_minus_log_pdf(model, div_nz((double)nm[q], nobs), nobs, m0, J.nu, log2pi);
     }
     if (BITMAP && cb) atomicOr(&bitmap[b0 + cw], cb);
   }
@@ -537,74 +540,111 @@ k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
 // issued together (the kernel is bound by the latency of these dependent loads), and W comes from the table.
 // Operations and their order are those of k_pseudodata (What = 0 + W, Zs = 0 + z W, ...): same bits.
 constexpr int PD_FAST_D = 8;
+constexpr int PD_ILP = 2;                // parameter tiles per block: a thread carries one parameter of each, their loads in flight together
 template <int PD_D>                      // datasets held in registers: 4 (more resident warps) or PD_FAST_D
-__global__ void __launch_bounds__(PAR_TILE, PD_D <= 4 ? 6 : 4)
-k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
+__global__ void __launch_bounds__(PAR_TILE, PD_D <= 4 ? 3 : 2)
+k_pseudodata_fast(const ParTile* __restrict__ tiles, int n_tiles, const JobDev* __restrict__ jobs,
                   const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
                   const int32_t* __restrict__ rowstart, double* __restrict__ beta, double* __restrict__ old_beta,
                   double* __restrict__ betahat, double* __restrict__ pw, const int32_t* __restrict__ pos,
                   const int64_t* __restrict__ start0, double* __restrict__ start /*null: already written*/) {
   // the table is read from global memory (L1): measured 0.93 ms against 1.08 ms with a per-block copy in shared memory
   const double* wtab = g_fast_w;
-  const ParTile t = tiles[blockIdx.x];
-  const int c = ctl[t.job];
-  if (!(c & CTL_UPDATE)) return;
-  if ((int)threadIdx.x >= t.cnt) return;
-  const JobDev J = jobs[t.job];
-  const int first = (c & CTL_FIRST) ? 1 : 0;
-  const int k = t.k0 + threadIdx.x;
-  const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
-  double Cd[PD_D];
-  int r0s[PD_D], cv[PD_D], nm[PD_D];
-  double mp[PD_D];
+  // The kernel waits for two levels of dependent loads (first-row look-up, then the row): every thread works on PD_ILP
+  // parameters, one from each of PD_ILP tiles, and issues each level for all of them before using any.
+  struct JobBits { int64_t par0, tab0, row0; int32_t P, E, D, des0; };     // the fields of JobDev used here
+  bool on[PD_ILP];
+  ParTile t[PD_ILP];
+  JobBits J[PD_ILP];
+  int first[PD_ILP], k[PD_ILP];
+  int64_t pi[PD_ILP];
 #pragma unroll
-  for (int d = 0; d < PD_D; ++d) {
-    Cd[d] = d < J.D ? design[J.des0 + d * J.E + t.e] : 0.0;
-    r0s[d] = (d < J.D && Cd[d] != 0) ? rowstart[J.tab0 + (int64_t)d * J.P + k] : -1;
-  }
-#pragma unroll
-  for (int d = 0; d < PD_D; ++d) {
-    const int64_t g = J.row0 + (r0s[d] >= 0 ? r0s[d] : 0);
-    cv[d] = r0s[d] >= 0 ? rc.cov[g] : 1;
-    nm[d] = r0s[d] >= 0 ? rc.nmeth[g] : 0;
-    mp[d] = (r0s[d] >= 0 && !first) ? rc.mu_res[g] : 0.0;
-  }
-  const double b = beta[pi];
-  if (start && t.e == 0) {
-    // the support (BinDesign::starts): the position of the parameter, read from the first dataset that has it.
-    // With several estimators a position may belong to datasets of another condition only: look at all datasets.
-    int rs = -1;
-    for (int d = 0; d < J.D && rs < 0; ++d) rs = d < PD_D && r0s[d] >= 0 ? r0s[d] : rowstart[J.tab0 + (int64_t)d * J.P + k];
-    if (rs >= 0) start[start0[t.job] + k] = (double)(int32_t)(double)(uint32_t)pos[J.row0 + rs];
-  }
-  double Wd[PD_D], Zd[PD_D];
-  double wt = 0.0;
-#pragma unroll
-  for (int d = 0; d < PD_D; ++d) {
-    Wd[d] = 0.0;
-    Zd[d] = 0.0;
-    if (r0s[d] >= 0) {
-      double z, W;
-      fast_residual(wtab, first, nm[d], cv[d], mp[d], z, W);
-      Wd[d] = 0.0 + W;                   // Binner::bin starts its sums at zero (Binner.cpp:29-36)
-      Zd[d] = 0.0 + z * W;
-      wt += (Cd[d] * Wd[d]) * Cd[d];
+  for (int h = 0; h < PD_ILP; ++h) {
+    const int ti = blockIdx.x * PD_ILP + h;
+    on[h] = ti < n_tiles;
+    first[h] = 0;
+    k[h] = 0;
+    pi[h] = 0;
+    J[h] = JobBits{0, 0, 0, 0, 1, 0, 0};
+    t[h] = ParTile{0, 0, 0, 0};
+    if (on[h]) {
+      t[h] = tiles[ti];
+      const int c = ctl[t[h].job];
+      on[h] = (c & CTL_UPDATE) && (int)threadIdx.x < t[h].cnt;
+      first[h] = (c & CTL_FIRST) ? 1 : 0;
+    }
+    if (on[h]) {
+      const JobDev* Jp = jobs + t[h].job;
+      J[h] = JobBits{Jp->par0, Jp->tab0, Jp->row0, Jp->P, Jp->E, Jp->D, Jp->des0};
+      k[h] = t[h].k0 + threadIdx.x;
+      pi[h] = J[h].par0 + (int64_t)t[h].e * J[h].P + k[h];
     }
   }
-  double inv = 1 / wt;
-  if (!is_finite(inv)) inv = 0.0;        // pseudo-inverse (pseudodata_helpers.hpp:33-34)
-  double bh = 0.0;
+  double Cd[PD_ILP][PD_D];
+  int r0s[PD_ILP][PD_D];
 #pragma unroll
-  for (int d = 0; d < PD_D; ++d) {
-    if (r0s[d] >= 0) {
-      const double q = Zd[d] / Wd[d];
-      const double zhat = (Wd[d] == 0) ? Wd[d] : q;
-      bh += (inv * Cd[d]) * (Wd[d] * zhat);
+  for (int h = 0; h < PD_ILP; ++h)
+#pragma unroll
+    for (int d = 0; d < PD_D; ++d) {
+      Cd[h][d] = (on[h] && d < J[h].D) ? design[J[h].des0 + d * J[h].E + t[h].e] : 0.0;
+      r0s[h][d] = (on[h] && d < J[h].D && Cd[h][d] != 0) ? rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]] : -1;
     }
+  int cv[PD_ILP][PD_D], nm[PD_ILP][PD_D];
+  double mp[PD_ILP][PD_D], b[PD_ILP];
+#pragma unroll
+  for (int h = 0; h < PD_ILP; ++h) {
+#pragma unroll
+    for (int d = 0; d < PD_D; ++d) {
+      const bool has = r0s[h][d] >= 0;
+      const int64_t g = has ? J[h].row0 + r0s[h][d] : 0;
+      cv[h][d] = has ? rc.cov[g] : 1;
+      nm[h][d] = has ? rc.nmeth[g] : 0;
+      mp[h][d] = (has && !first[h]) ? rc.mu_res[g] : 0.0;
+    }
+    b[h] = on[h] ? beta[pi[h]] : 0.0;
   }
-  old_beta[pi] = b;
-  betahat[pi] = bh + b;
-  pw[pi] = wt;
+#pragma unroll
+  for (int h = 0; h < PD_ILP; ++h) {
+    if (!on[h]) continue;
+    if (start && t[h].e == 0) {
+      // the support (BinDesign::starts): the position of the parameter, read from the first dataset that has it.
+      // With several estimators a position may belong to datasets of another condition only: look at all datasets.
+      int rs = -1;
+#pragma unroll
+      for (int d = 0; d < PD_D; ++d)
+        if (rs < 0 && d < J[h].D) rs = r0s[h][d] >= 0 ? r0s[h][d] : rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]];
+      for (int d = PD_D; d < J[h].D && rs < 0; ++d) rs = rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]];
+      if (rs >= 0) start[start0[t[h].job] + k[h]] = (double)(int32_t)(double)(uint32_t)pos[J[h].row0 + rs];
+    }
+    double Wd[PD_D], Zd[PD_D];
+    double wt = 0.0;
+#pragma unroll
+    for (int d = 0; d < PD_D; ++d) {
+      Wd[d] = 0.0;
+      Zd[d] = 0.0;
+      if (r0s[h][d] >= 0) {
+        double z, W;
+        fast_residual(wtab, first[h], nm[h][d], cv[h][d], mp[h][d], z, W);
+        Wd[d] = 0.0 + W;                   // Binner::bin starts its sums at zero (Binner.cpp:29-36)
+        Zd[d] = 0.0 + z * W;
+        wt += (Cd[h][d] * Wd[d]) * Cd[h][d];
+      }
+    }
+    double inv = 1 / wt;
+    if (!is_finite(inv)) inv = 0.0;        // pseudo-inverse (pseudodata_helpers.hpp:33-34)
+    double bh = 0.0;
+#pragma unroll
+    for (int d = 0; d < PD_D; ++d) {
+      if (r0s[h][d] >= 0) {
+        const double q = Zd[d] / Wd[d];
+        const double zhat = (Wd[d] == 0) ? Wd[d] : q;
+        bh += (inv * Cd[h][d]) * (Wd[d] * zhat);
+      }
+    }
+    old_beta[pi[h]] = b[h];
+    betahat[pi[h]] = bh + b[h];
+    pw[pi[h]] = wt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -612,6 +652,7 @@ k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ 
 // The reference adds the rows of a dataset left to right (Binner.cpp:34); here the association is
 // a fixed tree per tile followed by a left-to-right sum over tiles (documented deviation, ~1e-16).
 // ------------------------------------------------------------------------------------------------
+template <int MODEL>                    // MODEL_FAST: compile-time model (no beta-binomial code); -1: the job's own
 __global__ void __launch_bounds__(256)
 k_offset_partial(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
                  const int32_t* __restrict__ ctl, RowCols rc, double* __restrict__ part /*2 per tile*/) {
@@ -634,7 +675,7 @@ k_offset_partial(const RowTile* __restrict__ tiles, const JobDev* __restrict__ j
     for (int q = 0; q < 4; ++q) {
       if (!(r.mask >> q & 1)) continue;
       double z, W;
-      row_residual(J.model, first, nm[q], cv[q], mr[q], J.nu, z, W);
+      row_residual(MODEL >= 0 ? MODEL : J.model, first, nm[q], cv[q], mr[q], J.nu, z, W);
       sw += W;
       sz += z * W;
     }
@@ -734,7 +775,8 @@ k_damp(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
 // ------------------------------------------------------------------------------------------------
 // K10/K11/K13: mu, -log pdf and max |delta mu| per row tile
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int MODEL>                    // MODEL_FAST: compile-time model (no beta-binomial code); -1: the job's own
+__global__ void __launch_bounds__(256, 4)
 k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
             const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
             const double* __restrict__ beta, const double* __restrict__ off, double log2pi,
@@ -777,11 +819,11 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
     double m[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      m[q] = irls_mu(J.model, eta[q] + (0. + 1. * o));
+      m[q] = irls_mu(MODEL >= 0 ? MODEL : J.model, eta[q] + (0. + 1. * o));
       if (!(r.mask >> q & 1)) continue;
       const double nobs = (double)cv[q];
       const double y = div_nz((double)nm[q], nobs);
-      lik += irls_minus_log_pdf(J.model, y, nobs, m[q], J.nu, log2pi);
+      lik += irls_minus_log_pdf(MODEL >= 0 ? MODEL : J.model, y, nobs, m[q], J.nu, log2pi);
       if (need_dres) dres = fmax(dres, fabs(m[q] - mr[q]));
       if (want_outer) dout = fmax(dout, fabs(m[q] - mo[q]));
     }
@@ -1344,9 +1386,11 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   DevBuf<WTileDesc> d_wt;
   DevBuf<int32_t> d_job_wtile0, d_job_unique;
   std::vector<int32_t> uniq(nj, 0);
+  int64_t bitmap_words = 0;
   if (fast) {
     for (int j = 0; j < nj; ++j) h_bm0[j + 1] += h_bm0[j];
     const int64_t nwords = h_bm0[nj];
+    bitmap_words = nwords;
     std::vector<int32_t> job_wtile0(nj + 1, 0);
     int n_wt = 0;
     {
@@ -1374,17 +1418,21 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       ML_LAUNCH(eng, "k_first_sweep", k_first_sweep<true><<<n_rt, 256, 0, st>>>(
           cx.rtiles.p, cx.jobs.p, cx.ctl.p, cx.dptr.p, b.pos.p, b.nmeth.p, b.cov.p, d_bm0.p, d_minpos.p, d_bitmap.p,
           d_keys.p, log2pi, cx.off_part.p, cx.row_part.p));
+      ML_WORK(eng, "k_first_sweep", 12.0 * (double)b.nrows + 4.0 * (double)nwords);
     if (n_wt) {
       ML_LAUNCH(eng, "k_bitmap_tile_count", k_bitmap_tile_count<<<n_wt, 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p));
+      ML_WORK(eng, "k_bitmap_tile_count", 4.0 * (double)nwords);
       ML_LAUNCH(eng, "k_bitmap_job_scan", k_bitmap_job_scan<<<cdiv((long long)nj * 32, 128), 128, 0, st>>>(d_job_wtile0.p, nj, d_wtile_count.p,
                                                                        d_job_unique.p));
       ML_LAUNCH(eng, "k_bitmap_block_prefix", k_bitmap_block_prefix<<<n_wt, 256, 0, st>>>(d_wt.p, d_bitmap.p, d_wtile_count.p, d_bprefix.p));
+      ML_WORK(eng, "k_bitmap_block_prefix", 4.5 * (double)nwords);
       d_job_unique.download(uniq.data(), nj);
     }
   } else if (n_rt) {
     ML_LAUNCH(eng, "k_first_sweep", k_first_sweep<false><<<n_rt, 256, 0, st>>>(
         cx.rtiles.p, cx.jobs.p, cx.ctl.p, cx.dptr.p, b.pos.p, b.nmeth.p, b.cov.p, nullptr, nullptr, nullptr,
         d_keys.p, log2pi, cx.off_part.p, cx.row_part.p));
+    ML_WORK(eng, "k_first_sweep", 12.0 * (double)b.nrows);
   }
   std::vector<unsigned long long> keys(nj);
   d_keys.download(keys.data(), nj);
@@ -1485,6 +1533,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       ML_LAUNCH(eng, "k_rank_unique", k_rank_unique<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, d_bm0.p, d_minpos.p, d_bitmap.p,
                                           d_bprefix.p, cx.start0.p, cx.ctl.p, cx.pidx.p, cx.rowstart.p,
                                           start_by_pseudodata ? nullptr : res->start.p));
+      ML_WORK(eng, "k_rank_unique", 8.0 * (double)b.nrows + 4.0 * (double)ntab + 4.5 * (double)bitmap_words);
     } else {
       ML_LAUNCH(eng, "k_even_bins", k_even_bins<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, b.pos.p, cx.ctl.p, cx.pidx.p));
       ML_LAUNCH(eng, "k_rowstart_runs", k_rowstart_runs<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.dptr.p, cx.pidx.p, cx.ctl.p,
@@ -1550,7 +1599,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   bool sweep_sums = true;        // off_part / row_part still hold the first sweep's sums (first IRLS step, initial evaluation)
   bool init_pending = false;     // the initial evaluation's scalars are on the device, not yet read
   while (alive > 0) {
-    bool any_update = false, any_damp = false, any_eval = false, all_init = true;
+    bool any_update = false, any_damp = false, any_eval = false, all_init = true, S_any_not_first = false;
     for (int j = 0; j < nj; ++j) {
       int c = 0;
       const St& s = S[j];
@@ -1560,6 +1609,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       if (s.state != S_INIT_EVAL && s.state != S_DONE) all_init = false;
       if (s.state != S_INIT_EVAL && s.it > 0) c |= CTL_DRES;
       if (s.first) c |= CTL_FIRST;
+      else if (s.state != S_DONE) S_any_not_first = true;
       if (!store_mu) c |= CTL_NO_MU;
       if (c & CTL_EVAL) any_eval = true;
       ctl[j] = (s.state == S_DONE) ? 0 : c;
@@ -1569,12 +1619,17 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     auto center = [&]() {
       ML_LAUNCH(eng, "k_center", k_center<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, cx.sums.p, cx.beta_raw.p,
                                             res->beta.p, cx.tv_part.p));
+      ML_WORK(eng, "k_center", 16.0 * (double)npar);
     };
     auto evaluate = [&](double* d_scalars) {
       if (!init_pass)
-        ML_LAUNCH(eng, "k_eval_rows", k_eval_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p, res->beta.p,
+        ML_LAUNCH(eng, "k_eval_rows", (fast ? k_eval_rows<MODEL_FAST> : k_eval_rows<-1>)<<<n_rt, 256, 0, st>>>(
+                                          cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p, res->beta.p,
                                           res->offset.p, log2pi, res->mu.p, cx.mu_outer.p, want_outer ? 1 : 0,
                                           cx.row_part.p));
+      if (!init_pass)
+        ML_WORK(eng, "k_eval_rows", 12.0 * (double)b.nrows + 8.0 * (double)npar + (store_mu ? 8.0 * (double)b.nrows : 0.0)
+                                        + (want_outer ? 8.0 * (double)b.nrows : 0.0) + (S_any_not_first ? 8.0 * (double)b.nrows : 0.0));
       if (any_damp)
         ML_LAUNCH(eng, "k_tv_partial", k_tv_partial<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, res->beta.p, cx.tv_part.p));
       ML_LAUNCH(eng, "k_job_finalize", k_job_finalize<<<nj, 256, 0, st>>>(cx.jobs.p, nj, cx.ctl.p, cx.row_part.p, cx.tv_part.p,
@@ -1582,19 +1637,23 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     };
     if (any_update) {
       if (p.model == MODEL_FAST && max_D <= 4)
-        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<4><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<4><<<cdiv(n_pt, PD_ILP), PAR_TILE, 0, st>>>(cx.ptiles.p, n_pt, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
                                                         cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                                         res->pw.p, b.pos.p, cx.start0.p, start_by_pseudodata ? res->start.p : nullptr));
       else if (p.model == MODEL_FAST && max_D <= PD_FAST_D)
-        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<PD_FAST_D><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<PD_FAST_D><<<cdiv(n_pt, PD_ILP), PAR_TILE, 0, st>>>(cx.ptiles.p, n_pt, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
                                                                 cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                                                 res->pw.p, b.pos.p, cx.start0.p, start_by_pseudodata ? res->start.p : nullptr));
       else
         ML_LAUNCH(eng, "k_pseudodata", k_pseudodata<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.dptr.p, cx.design.p,
                                                 cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                                 res->pw.p));
+      ML_WORK(eng, "k_pseudodata", 4.0 * (double)ntab + 8.0 * (double)b.nrows + 32.0 * (double)npar + (start_by_pseudodata && sweep_sums ? 12.0 * (double)nstart : 0.0)
+                                       + (S_any_not_first ? 8.0 * (double)b.nrows : 0.0));
       if (!sweep_sums)     // the first step's sums of W and z W were formed by the first sweep
-        ML_LAUNCH(eng, "k_offset_partial", k_offset_partial<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p));
+        ML_LAUNCH(eng, "k_offset_partial", (fast ? k_offset_partial<MODEL_FAST> : k_offset_partial<-1>)<<<n_rt, 256, 0, st>>>(
+            cx.rtiles.p, cx.jobs.p, cx.ctl.p, rc, cx.off_part.p));
+        ML_WORK(eng, "k_offset_partial", 16.0 * (double)b.nrows);
       ML_LAUNCH(eng, "k_offset_finalize", k_offset_finalize<<<n_ent, 128, 0, st>>>(cx.ent_job.p, cx.ent_d.p, n_ent, cx.jobs.p, cx.ctl.p,
                                                           cx.dtile0.p, cx.off_part.p, res->offset.p,
                                                           cx.old_off.p));
@@ -1609,6 +1668,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     if (any_damp) {
       ML_LAUNCH(eng, "k_damp", k_damp<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, wnew, res->beta.p, cx.old_beta.p,
                                         res->offset.p, cx.old_off.p));
+      ML_WORK(eng, "k_damp", 24.0 * (double)npar);
       for (int j = 0; j < nj; ++j)
         if (ctl[j] & CTL_DAMP) res->jobs[j].dampings++;
     }
@@ -1702,6 +1762,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
       cx.ctl.upload(ctl);
       ML_LAUNCH(eng, "k_copy_rows", k_copy_rows<<<n_rt, 256, 0, st>>>(cx.rtiles.p, cx.jobs.p, cx.ctl.p, res->mu.p, cx.mu_res.p,
                                         want_outer ? cx.mu_outer.p : nullptr));
+      ML_WORK(eng, "k_copy_rows", 16.0 * (double)b.nrows);
     }
   }
   for (int j = 0; j < nj; ++j) {
@@ -1715,6 +1776,7 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
   }
   res->est_id.alloc(st, (size_t)std::max<int64_t>(1, npar));
   if (n_pt) ML_LAUNCH(eng, "k_fill_estimate_id", k_fill_estimate_id<<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, res->est_id.p));
+  ML_WORK(eng, "k_fill_estimate_id", 4.0 * (double)npar);
   res->counts_exact = fast && p.max_iter == 1;
   // no synchronisation here: every host decision has been taken, the scratch buffers are freed in stream
   // order, and whatever reads the result next (copy, segmentation) is enqueued on the same stream

@@ -118,6 +118,8 @@ struct Scan {
     ML_LAUNCH(eng, "k_scan_tile_sums", k_scan_tile_sums<<<nt, 256, 0, st>>>(flags, n, tile_sum.p));
     ML_LAUNCH(eng, "k_scan_block", k_scan_block<<<1, 256, 0, st>>>(tile_sum.p, nt, total.p));
     ML_LAUNCH(eng, "k_scan_apply", k_scan_apply<<<nt, 256, 0, st>>>(flags, n, tile_sum.p, pos, compact));
+    ML_WORK(eng, "k_scan_tile_sums", 4.0 * (double)n);
+    ML_WORK(eng, "k_scan_apply", (4.0 + (pos ? 4.0 : 0.0) + (compact ? 4.0 : 0.0)) * (double)n);
     int32_t h = 0;
     total.download(&h, 1);
     stream_sync(st);
@@ -658,6 +660,9 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
       seg_group.p, row_lo.p, row_hi.p));
   ML_LAUNCH(eng, "k_call_count", k_call_count<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
       d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, gaps.p));
+  double call_rows = 0.0;                  // rows of the estimates table the segments lie on
+  for (const SegGroup& g : groups) call_rows += (double)g.nrows;
+  ML_WORK(eng, "k_call_count", 16.0 * call_rows);          // position and pooled coverage of every row
   Scan scan;
   scan.run(eng, gaps.p, n_segs, gap_off.p, nullptr);
   const int32_t total = scan.run(eng, parts.p, n_segs, part_off.p, nullptr);
@@ -671,6 +676,8 @@ static int64_t call_table_impl(Engine& eng, const std::vector<SegGroup>& groups_
   ML_LAUNCH(eng, "k_call_parts", k_call_parts<Rows><<<cdiv((long long)n_segs * 32, 256), 256, 0, st>>>(
       d_groups.p, seg_group.p, n_segs, row_lo.p, row_hi.p, d_pos, pos_f64, rows, max_distance, parts.p, part_off.p,
       part_first.p, part_seg.p, part_end.p));
+  ML_WORK(eng, "k_call_parts", 16.0 * call_rows);
+  if (total > 0) ML_WORK(eng, "k_call_emit_part", 24.0 * call_rows + 80.0 * (double)total);   // pos, betahat, pw once; the row of the table
   if (total > 0)
     ML_LAUNCH(eng, "k_call_emit_part", k_call_emit_part<Rows><<<cdiv((long long)total * PART_LANES, 256), 256, 0, st>>>(
         d_groups.p, d_g0.p, seg_group.p, total, row_hi.p, seg.seg_id.p, seg.pseudoweight.p, d_pos, pos_f64, rows,
@@ -730,6 +737,7 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   flags.zero();   // rows outside every group (none in practice) are not heads
   ML_LAUNCH(eng, "k_seg_run_heads", k_seg_run_heads<<<(int)tile_group.size(), 256, 0, st>>>(d_groups.p, d_tile_group.p, d_tile_r0.p, d_beta,
                                                           flags.p));
+  ML_WORK(eng, "k_seg_run_heads", 12.0 * (double)nrows);      // beta read, one flag written
   Scan scan;
   DevBuf<int32_t> run_row(st, (size_t)nrows);
   const int32_t n_runs = scan.run(eng, flags.p, nrows, run_pos.p, run_row.p);
@@ -765,6 +773,8 @@ int64_t segment_device(Engine& eng, const std::vector<SegGroup>& groups_in, int6
   ML_LAUNCH(eng, "k_seg_emit", k_seg_emit<<<cdiv(n_segs, 128), 128, 0, st>>>(d_groups.p, run_group.p, seg_run.p, n_segs, run_row.p,
                                                 seg_of_run.p, run_pos.p, d_start, start_f64, d_beta,
                                                 d_betahat, d_pw, out, long_list.p, n_long.p));
+  ML_WORK(eng, "k_seg_emit", 28.0 * (double)nrows + 64.0 * (double)n_segs);   // start, beta, betahat, pw of every row once (long
+                                                                              // segments: by k_seg_emit_long); the segment rows
   ML_LAUNCH(eng, "k_seg_emit_long",
             k_seg_emit_long<<<(int)std::min<int64_t>(max_long, (int64_t)eng.sm_count * 8), 256, 0, st>>>(
                 long_list.p, n_long.p, d_beta, d_betahat, d_pw, out));

@@ -43,13 +43,10 @@ class GenomePipeline:
         self.lib = self.pool.engines[0].lib
         self.params = MlParams(float(lambda2), float(lambda2) + 1, 0.0, float(tol_val), 50.0, 1.0, 1, 1, 1, api.MODEL_FAST, 0, 0)
         self.tol_val = float(tol_val)
-        self.njobs = int(np.asarray(job_ptr).size - 1)
-        self.groups = []
-        for jobs, gptr, gcols in api.split_jobs(job_ptr, cols, len(self.pool.engines), edge_share=edge_share):
-            gcols = {k: np.ascontiguousarray(gcols[k], np.int32) for k in _INPUT}
-            if pin:
-                gcols = {k: _pin(v, self.lib) for k, v in gcols.items()}
-            self.groups.append((np.asarray(jobs, np.int32), np.ascontiguousarray(gptr, np.int64), gcols))
+        self.pin = bool(pin)
+        self._pinned = []               # per group: column name -> page-locked buffer (kept across rebind)
+        self._edge_share = edge_share
+        self.rebind(job_ptr, cols)
         import os
         # packing threads: all CPUs of this process but four (the engines' own host threads and the driver's need some; measured
         # on a 16-CPU box: 12 threads 25.4 ms per genome, 16 threads 28 ms with outliers, 8 threads 28 ms)
@@ -59,6 +56,36 @@ class GenomePipeline:
         self.host_threads = ht
         self.timeline = []
         self._t0 = 0.0
+
+    def rebind(self, job_ptr, cols, reuse_pinned=True):
+        """Another data set of the same kind through the same engines (a cohort, sample after sample): the groups are cut
+        anew and copied into the page-locked buffers of the previous ones where they fit (reuse_pinned=False: into
+        buffers of their own, so that `bound()` / `bind()` can switch between prepared data sets without copying)."""
+        if not reuse_pinned:
+            self._pinned = []
+        self.njobs = int(np.asarray(job_ptr).size - 1)
+        self.groups = []
+        self._bufs = None
+        parts = api.split_jobs(job_ptr, cols, len(self.pool.engines), edge_share=self._edge_share)
+        for g, (jobs, gptr, gcols) in enumerate(parts):
+            gcols = {k: np.ascontiguousarray(gcols[k], np.int32) for k in _INPUT}
+            if self.pin:
+                if g >= len(self._pinned):
+                    self._pinned.append({})
+                held = self._pinned[g]
+                for k, v in gcols.items():
+                    if k not in held or held[k].size < v.size:
+                        held[k] = api.pinned_empty(int(v.size * 1.1) + 64, v.dtype, self.lib)
+                    held[k][:v.size] = v
+                    gcols[k] = held[k][:v.size]
+            self.groups.append((np.asarray(jobs, np.int32), np.ascontiguousarray(gptr, np.int64), gcols))
+
+    def bound(self):
+        return self.njobs, self.groups
+
+    def bind(self, prepared):
+        self.njobs, self.groups = prepared
+        self._bufs = None
 
     # ---- bytes that cross PCIe per call ---------------------------------------------------------------------------
     def h2d_bytes(self):

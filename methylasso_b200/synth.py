@@ -46,8 +46,11 @@ def _runs(rng, n, mean_a, mean_b):
     return lens, state
 
 
-def truth(n_cpgs: int, seed: int):
-    """Positions (strictly increasing int32) and true methylation per CpG."""
+def truth(n_cpgs: int, seed: int, dmv: bool = False):
+    """Positions (strictly increasing int32) and true methylation per CpG.  dmv=True adds, from a random stream of its
+    own (everything else is unchanged): unmethylated stretches of 6-15 kb, about one per 150 000 CpGs - wide enough for
+    the reference's valley rule (R/call.R:100-133, pmd_valley_min_width = 5000) - and low-methylated regions inside
+    the PMD blocks (R/call.R:201-212 drops LMRs that lie in PMDs)."""
     rng = np.random.default_rng(seed)
     # background runs (mean 340 CpGs) alternate with CpG-island clusters (mean 60): ~15 % in islands
     lens, state = _runs(rng, n_cpgs, 340.0, 60.0)
@@ -95,6 +98,17 @@ def truth(n_cpgs: int, seed: int):
         p[sl] = np.where(is_umr[sl], p[sl], vals)
         is_pmd[sl] = True
         covered += w
+        if dmv and i1 - i0 > 200 and rng.random() < 0.7:          # an LMR inside the block
+            a = int(i0) + int(rng.integers(20, i1 - i0 - 60))
+            p[a:a + int(rng.integers(8, 41))] = rng.uniform(0.12, 0.3)
+    if dmv:
+        rng2 = np.random.default_rng(seed * 31 + 7)
+        for _ in range(max(1, n_cpgs // 150_000)):
+            i = int(rng2.integers(0, max(1, n_cpgs - 2)))
+            j = int(np.searchsorted(pos, pos[i] + int(rng2.integers(6_000, 15_001))))
+            if j - i >= 8 and j < n_cpgs:
+                p[i:j] = rng2.uniform(0.01, 0.05)
+                is_umr[i:j] = True
     return pos.astype(np.int32), np.clip(p, 0.0, 1.0), is_umr, is_pmd
 
 
@@ -123,9 +137,9 @@ def shift_condition(p, seed, n_regions=None):
     return q, truth_regions
 
 
-def chromosome_table(n_cpgs, seed, reps_per_condition=(1,), mean_cov=20.0, min_cov=5):
+def chromosome_table(n_cpgs, seed, reps_per_condition=(1,), mean_cov=20.0, min_cov=5, dmv=False):
     """One chromosome's input table: dict of int32 columns sorted by (dataset, pos)."""
-    pos, p, _, _ = truth(n_cpgs, seed)
+    pos, p, _, _ = truth(n_cpgs, seed, dmv)
     cols = {k: [] for k in ("dataset", "condition", "replicate", "pos", "Nmeth", "coverage")}
     dset = 0
     for c, nrep in enumerate(reps_per_condition, start=1):
@@ -143,11 +157,11 @@ def chromosome_table(n_cpgs, seed, reps_per_condition=(1,), mean_cov=20.0, min_c
 
 
 def genome_tables(config_index=2, total_cpgs=GENOME_CPGS, reps_per_condition=(3,), n_chr=24,
-                  mean_cov=20.0, seed=None):
+                  mean_cov=20.0, seed=None, dmv=False):
     """List of per-chromosome tables for a whole synthetic genome (config 2/3 shapes)."""
     seed = BASE_SEED + config_index if seed is None else seed
     sizes = chromosome_cpgs(total_cpgs)[:n_chr]
-    return [chromosome_table(n, seed * 50 + i, reps_per_condition, mean_cov)
+    return [chromosome_table(n, seed * 50 + i, reps_per_condition, mean_cov, dmv=dmv)
             for i, n in enumerate(sizes)]
 
 

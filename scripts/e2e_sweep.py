@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from methylasso_b200 import synth
 from methylasso_b200.pipeline import GenomePipeline
 
-tables = synth.genome_tables(2, total_cpgs=synth.GENOME_CPGS, reps_per_condition=(3,), seed=synth.BASE_SEED + 2)
+tables = synth.genome_tables(2, total_cpgs=synth.GENOME_CPGS, reps_per_condition=(3,), seed=synth.BASE_SEED + 2, dmv=True)
 ptr, cols = synth.concat_jobs(tables)
 shapes = [tuple(float(x) for x in a.split(":")) for a in sys.argv[1:]] or [(6, 0.0)]
 for G, edge in shapes:

@@ -2,8 +2,7 @@
 
     python scripts/ncu_traffic.py gpurun_out/ncu_full_raw.csv profiles/ncu_traffic.json
 
-Per kernel (function name; the FLSA main kernel is split into its first launch and the left-neighbour rounds
-by launch order, as bench.py names them): launches captured, mean DRAM bytes per launch
+Per kernel (function name): launches captured, mean DRAM bytes per launch
 (dram__bytes_read.sum + dram__bytes_write.sum), mean duration, achieved occupancy and issue-slot utilisation.
 """
 import csv
@@ -45,15 +44,10 @@ def main(src, dst):
         if len(r) < len(names):
             continue
         full = r[col["Kernel Name"]]
-        m = re.search(r"flsa_(main|warm)_kernel<\(int\)(\d+)>", full)
-        if m:      # bench.py's names: the 32-knot main kernel is the first pass, the 64-knot one the left-neighbour rounds
-            k = {("main", "32"): "flsa_main_kernel", ("main", "64"): "flsa_main_kernel[left]",
-                 ("warm", "16"): "flsa_warm_kernel", ("warm", "64"): "flsa_warm_kernel[retry]"}.get(m.groups(), m.group(0))
-        else:
-            k = re.sub(r"^void ", "", full.strip())
-            k = re.sub(r"^ml::", "", k)
-            k = re.sub(r"^(<?unnamed>|\(anonymous namespace\))::", "", k)
-            k = re.sub(r"[<(].*", "", k)
+        k = re.sub(r"^void ", "", full.strip())
+        k = re.sub(r"^ml::", "", k)
+        k = re.sub(r"^(<?unnamed>|\(anonymous namespace\))::", "", k)
+        k = re.sub(r"[<(].*", "", k)
         acc[k]["dram"].append((scaled(r, "dram__bytes_read.sum") or 0) + (scaled(r, "dram__bytes_write.sum") or 0))
         acc[k]["ms"].append(scaled(r, "gpu__time_duration.sum"))
         for key, short in (("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active_pct"),
@@ -63,7 +57,14 @@ def main(src, dst):
                            ("launch__registers_per_thread", "registers")):
             if key in col:
                 acc[k][short].append(num(r[col[key]]))
-    out = {"source": src, "dram_bytes_per_launch": {}, "detail": {}}
+    import datetime
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    # bench.py refuses the numbers below when the kernel sources have changed since this capture
+    out = {"source": src, "kernel_source_hash": bench.kernel_source_hash(),
+           "captured": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ"),
+           "dram_bytes_per_launch": {}, "detail": {}}
     for k, d in acc.items():
         n = len(d["dram"])
         out["dram_bytes_per_launch"][k] = sum(d["dram"]) / n
@@ -74,7 +75,7 @@ def main(src, dst):
                 det["mean_" + key] = sum(v) / len(v)
         out["detail"][k] = det
     # bench.py names a launch by what it does, not by the specialisation that ran
-    for fn, name in (("k_pseudodata_fast", "k_pseudodata"), ("flsa_chain2_kernel", "flsa_chain_kernel")):
+    for fn, name in (("k_pseudodata_fast", "k_pseudodata"),):
         if fn in out["dram_bytes_per_launch"] and name not in out["dram_bytes_per_launch"]:
             out["dram_bytes_per_launch"][name] = out["dram_bytes_per_launch"][fn]
     json.dump(out, open(dst, "w"), indent=1, sort_keys=True)

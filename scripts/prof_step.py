@@ -15,7 +15,7 @@ ap.add_argument("--cpgs", type=int, default=synth.GENOME_CPGS)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--regions", action="store_true", help="the whole rule engine (segment_methylation tables) per step")
 args = ap.parse_args()
-tables = synth.genome_tables(2, total_cpgs=args.cpgs, reps_per_condition=(3,), seed=synth.BASE_SEED + 2)
+tables = synth.genome_tables(2, total_cpgs=args.cpgs, reps_per_condition=(3,), seed=synth.BASE_SEED + 2, dmv=True)
 ptr, cols = synth.concat_jobs(tables)
 eng = api.Engine(0)
 batch = eng.upload(ptr, cols)

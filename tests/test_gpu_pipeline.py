@@ -12,7 +12,9 @@ SIZES = (60_000, 35_000, 35_000, 20_000, 12_000, 9_000, 5_000)
 
 
 def _genome(reps=(3,)):
-    tables = [synth.chromosome_table(n, 4100 + i, reps) for i, n in enumerate(SIZES)]
+    # dmv=True: 6-15 kb unmethylated stretches and LMRs inside PMD blocks, so that the valley (UMR-DMV) and the
+    # LMR-in-PMD rules of R/call.R:100-133, 201-212 are exercised
+    tables = [synth.chromosome_table(n, 4100 + i, reps, dmv=True) for i, n in enumerate(SIZES)]
     ptr, cols = synth.concat_jobs(tables)
     return tables, ptr, cols
 
@@ -70,6 +72,7 @@ def test_pipeline_region_tables(engine, oracle):
             assert _close(pmd[k][pm], wp[k]), (j, k)
         n_rows += int(m.sum())
     assert n_rows > 100 and pmd["start"].size > 3
+    assert int((seg["category"] == 3).sum()) >= 2          # valleys were called (and equal the restatement's)
 
 
 @pytest.mark.gpu
