@@ -526,6 +526,53 @@ def run_aux(args, local):
                                                 "(no rule engine)" % dt}})
         batch.free()
         eng.close()
+    elif args.aux == "sweep":
+        eng = api.Engine(local)
+        eng.set("want_mu", 0)
+        tables, ptr, cols = make_workload(args.cpgs)
+        lams = np.geomspace(10, 2000, 16)
+        p = MlParams(LAMBDA2, LAMBDA2 + 1, 0.0, TOL, 50.0, 1.0, 1, 1, 1, 0, 0, 0)
+        batch = eng.upload(ptr, cols)
+        res = eng.detect(batch, p)
+        U = int(sum(res.sizes(j)[1] for j in range(res.njobs)))
+        keep = {}
+
+        def sweep():
+            keep["nseg"] = res.lambda_sweep(lams, TOL)
+        w = _timed(sweep, steps, 2, eng.synchronize)
+        eng.set("profile", 1)
+        eng.profile_reset()
+        sweep()
+        eng.synchronize()
+        prof = eng.profile()
+        eng.set("profile", 0)
+        res.free()
+        batch.free()
+        # CPU: the reference's verbatim DP on the pooled series of the smallest chromosome, all 16 values, one thread
+        O.build()
+        O.use_reference_dp(True)
+        t = min(tables, key=lambda x: x["pos"].size)
+        u, inv = np.unique(t["pos"], return_inverse=True)
+        cv = np.bincount(inv, t["coverage"], u.size).astype(float)
+        y = np.bincount(inv, t["Nmeth"], u.size) / cv
+        t0 = time.perf_counter()
+        for lam in lams:
+            O.weighted_1d_flsa(y, cv, float(lam))
+        dt = time.perf_counter() - t0
+        ms = float(np.median(w))
+        line.update({"metric": "series elements/sec through the batched FLSA, 16-value lambda2 sweep (aux, configs[4])",
+                     "unit": "elements/s", "value": 16.0 * U / (ms * 1e-3), "ms_per_step": ms,
+                     "host_wall_ms_each_step": [round(x, 2) for x in w],
+                     "config": {"workload": "configs[4]: lambda2 = geomspace(10, 2000, 16) on the full synthetic genome; the 16 x 24 "
+                                            "series read the 24 resident pseudodata streams (ml_result_lambda_sweep), then centring "
+                                            "and segment_methylation_helper per value", "cpgs": U, "lambdas": [float(x) for x in lams]},
+                     "segments_per_lambda": [int(x) for x in keep["nseg"]],
+                     "kernels": [{"kernel": k, "ms": round(v[0], 3), "launches": v[1]} for k, v in
+                                 sorted(prof.items(), key=lambda kv: -kv[1][0])[:10]],
+                     "cpu_baseline": {"value": 16.0 * u.size / dt, "unit": "elements/s", "cores": 1, "kind": "reference",
+                                      "sample": "tf_dp_weight (verbatim, oracle/_ref) on the pooled series of the smallest "
+                                                "chromosome (%d CpGs), 16 values, %.2f s" % (u.size, dt)}})
+        eng.close()
     elif args.aux == "full":
         eng = api.Engine(local)
         out = {}
@@ -543,6 +590,12 @@ def run_aux(args, local):
             l0 = eng.launch_count
             w = _timed(run, max(2, steps // 2), 1, eng.synchronize)
             launches = (eng.launch_count - l0) // (max(2, steps // 2) + 1)
+            eng.set("profile", 1)
+            eng.profile_reset()
+            run()
+            eng.synchronize()
+            prof = eng.profile()
+            eng.set("profile", 0)
             # the port on a bounded sample of the same shape (1/8 of the positions: the fit of the whole chromosome
             # takes the port minutes)
             small = synth.chromosome_table(ncpg // 8, synth.BASE_SEED + 7, reps)
@@ -559,6 +612,8 @@ def run_aux(args, local):
                          "ms_per_irls_step": float(np.median(w)) / max(1, info["irls_steps"]),
                          # 36 N + 64 E P bytes per IRLS step
                          "alg_bytes_per_irls_step": 36 * rows + 64 * int(info["E"]) * int(info["P"]),
+                         "kernels": [{"kernel": k_, "ms": round(v_[0], 2), "launches": v_[1]} for k_, v_ in
+                                     sorted(prof.items(), key=lambda kv: -kv[1][0])[:8]],
                          "cpu_port": {"rows": int(small["pos"].size), "seconds": dt, "rows_per_s": small["pos"].size / dt,
                                       "irls_steps": o["irls_steps"], "cores": 1}}
             pk, _ = peaks()

@@ -423,6 +423,16 @@ ML_API int ml_result_segment_methylation(ml_engine *eng, ml_result *r, double to
                                          uint32_t *p_end, double *p_width, int32_t *p_segment_id, double *p_beta,
                                          double *p_std, int8_t *p_category, int32_t *p_num_cpgs, double *p_fused_std);
 
+/* ---- lambda2 sweep on a resident one-step FAST fit (BASELINE.json configs[4]) ---------------------------------------------
+ * signal_detection_fast for nlam values of lambda2 at once: the pseudodata of a one-step FAST fit do not depend on lambda2
+ * (src/signal_detection.cpp:11-47 with max_iter = 1), so the sweep is ONE batched weighted_1d_flsa call in which the series
+ * of all lambda2 values read the same resident (betahat, pseudoweight) stream, followed by the centring
+ * (core/params_helpers.hpp:23-30) and segment_methylation_helper per value.  n_segments[nlam] (may be NULL) receives the
+ * number of segments per value; beta (may be NULL) the fitted coefficients, nlam blocks laid out like the result's own
+ * beta column (ml_result_copy_all order). */
+ML_API int ml_result_lambda_sweep(ml_engine *eng, ml_result *r, int nlam, const double *lambda2, double lambda1,
+                                  double tol_val, int64_t *n_segments, double *beta);
+
 /* ---- K16: exchange of the per-shard region tables between the GPUs of one box --------------------------------------------
  * The reference parallelises over chromosomes with forked workers and concatenates what they return
  * (R/genome_wide.R:6-15, 42-43; R/call.R:230-244 rbindlist).  Here a worker is one process per GPU and the concatenation

@@ -121,6 +121,7 @@ SIGNATURES = {
     "ml_result_segment_methylation": (C.c_int, [_P, _P, C.c_double, C.c_double, C.POINTER(MlLmrParams),
                                                 C.POINTER(MlValleyParams), C.POINTER(MlPmdParams), C.c_int, _I64P] + [_P] * 13
                                       + [_I64P] + [_P] * 11),
+    "ml_result_lambda_sweep": (C.c_int, [_P, _P, C.c_int, _P, C.c_double, C.c_double, _P, _P]),
     "ml_gather_layout": (C.c_int, [C.c_int64, C.c_int64, _P, _I64P]),
     "ml_gather_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
     "ml_gather_ipc_handle": (C.c_int, [_P, _P]),

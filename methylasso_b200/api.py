@@ -368,6 +368,20 @@ class Result:
     def fast_diff_combine(self):
         self.eng._check(self.eng.lib.ml_result_fast_diff_combine(self.eng.h, self.h))
 
+    def lambda_sweep(self, lambdas, tol_val=0.01, lambda1=0.0, want_beta=False):
+        """ml_result_lambda_sweep: the one-step FAST fit of this result redone for every lambda2 of `lambdas` in one batched
+        FLSA call on the resident pseudodata.  Returns the number of segments per value (and, want_beta, the coefficients
+        as an array [len(lambdas), total parameters] in copy_all order)."""
+        lam = np.ascontiguousarray(lambdas, np.float64)
+        nseg = np.zeros(lam.size, np.int64)
+        beta = None
+        if want_beta:
+            npar = int(sum(self.sizes(j)[1] * self.sizes(j)[2] for j in range(self.njobs) if self.sizes(j)[4] == 0))
+            beta = np.empty((lam.size, npar))
+        self.eng._check(self.eng.lib.ml_result_lambda_sweep(self.eng.h, self.h, lam.size, _p(lam), float(lambda1), float(tol_val),
+                                                            _p(nseg), _p(beta)))
+        return (nseg, beta) if want_beta else nseg
+
     def segments(self, tol_val=0.01, reuse_pinned=False):
         """segment_methylation_helper on the resident estimates of every valid job.  reuse_pinned=True downloads
         into engine-owned page-locked buffers and returns views of them (valid until the next such call)."""

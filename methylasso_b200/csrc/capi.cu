@@ -1338,6 +1338,81 @@ int ml_result_segment_methylation(ml_engine* eng, ml_result* r, double tol_val, 
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------
+// lambda2 sweep (BASELINE.json configs[4]): the one-step FAST fit's pseudodata (betahat, pseudoweight) do not depend on
+// lambda2, so a sweep is one batched FLSA call whose series - one per (chromosome, estimator, lambda2) - all read the ONE
+// resident pseudodata stream of their chromosome (FlsaSeries::off_in) and write their own lane of the output; then the
+// centring (core/params_helpers.hpp:23-30) and segment_methylation_helper per lane.
+// ------------------------------------------------------------------------------------------------
+namespace ml {
+__global__ void __launch_bounds__(256)
+k_sweep_center(int ns, const int64_t* __restrict__ off, const int32_t* __restrict__ len, const double* __restrict__ sums,
+               double* __restrict__ beta) {
+  const int s = blockIdx.y;
+  if (s >= ns) return;
+  const double mean = sums[2 * s] / sums[2 * s + 1];
+  double* b = beta + off[s];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < len[s]; k += gridDim.x * blockDim.x) b[k] = b[k] - mean;
+}
+}  // namespace ml
+
+extern "C" int ml_result_lambda_sweep(ml_engine* eng, ml_result* r, int nlam, const double* lambda2, double lambda1, double tol_val,
+                                      int64_t* n_segments, double* beta_out) {
+  if (!eng || !r || nlam <= 0 || !lambda2) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  Result& R = *r->r;
+  if (!R.counts_exact || R.diff_combined)
+    return fail(ML_ERR_BAD_ARGUMENT, "lambda2 sweep: needs the result of a one-step FAST fit (its pseudodata do not depend on lambda2)");
+  for (int l = 0; l < nlam; ++l)
+    if (!(lambda2[l] > 0)) return fail(13, "lambda2 must be positive");      // fitter_lasso.ipp:4
+  cudaStream_t st = eng->e.stream;
+  const int64_t npar = R.npar;
+  std::vector<FlsaSeries> series;
+  std::vector<int64_t> off;
+  std::vector<int32_t> len;
+  int max_len = 1;
+  for (int l = 0; l < nlam; ++l)
+    for (const JobHost& j : R.jobs) {
+      if (j.status) continue;
+      for (int e = 0; e < j.E; ++e) {
+        FlsaSeries fs{(int64_t)l * npar + j.par0 + (int64_t)e * j.P, (int32_t)j.P, lambda2[l]};
+        fs.off_in = j.par0 + (int64_t)e * j.P;
+        series.push_back(fs);
+        off.push_back(fs.off);
+        len.push_back(fs.n);
+        max_len = std::max(max_len, (int)fs.n);
+      }
+    }
+  const int ns = (int)series.size();
+  if (ns == 0) { if (n_segments) for (int l = 0; l < nlam; ++l) n_segments[l] = 0; return ML_OK; }
+  DevBuf<double> beta(st, (size_t)nlam * (size_t)npar), sums(st, 2 * (size_t)ns);
+  {
+    FlsaPlan plan(eng->e, series, (int64_t)nlam * npar);
+    plan.solve(R.betahat.p, R.pw.p, beta.p, 1, lambda1, sums.p);
+  }
+  DevBuf<int64_t> d_off(st, (size_t)ns);
+  DevBuf<int32_t> d_len(st, (size_t)ns);
+  d_off.upload(off);
+  d_len.upload(len);
+  ML_LAUNCH(eng->e, "k_sweep_center", k_sweep_center<<<dim3((unsigned)std::min(64, cdiv(max_len, 1024)), (unsigned)ns), 256, 0, st>>>(
+      ns, d_off.p, d_len.p, sums.p, beta.p));
+  ML_WORK(eng->e, "k_sweep_center", 16.0 * (double)nlam * (double)npar);
+  if (n_segments) {
+    const std::vector<SegGroup> groups = result_groups(R);
+    for (int l = 0; l < nlam; ++l) {
+      SegDeviceOut ds;
+      n_segments[l] = segment_device(eng->e, groups, npar, R.start.p, 1, beta.p + (size_t)l * npar, R.betahat.p, R.pw.p, tol_val, ds);
+    }
+  }
+  if (beta_out) ML_CUDA(cudaMemcpyAsync(beta_out, beta.p, sizeof(double) * (size_t)nlam * (size_t)npar, cudaMemcpyDeviceToHost, st));
+  stream_sync(st);
+  return ML_OK;
+  ML_CATCH
+}
+
+// ------------------------------------------------------------------------------------------------
 // K16: the exchange of the per-shard region tables (what R/call.R:233-244 does with rbindlist over the chromosomes a
 // worker handled, R/genome_wide.R:6-15 with the fits).  One process per GPU; every rank owns a WINDOW in its HBM with
 // one slot per rank and parity, exported with cudaIpcGetMemHandle and mapped by the peers.  A rank's push is ONE kernel

@@ -540,111 +540,74 @@ k_pseudodata(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
 // issued together (the kernel is bound by the latency of these dependent loads), and W comes from the table.
 // Operations and their order are those of k_pseudodata (What = 0 + W, Zs = 0 + z W, ...): same bits.
 constexpr int PD_FAST_D = 8;
-constexpr int PD_ILP = 2;                // parameter tiles per block: a thread carries one parameter of each, their loads in flight together
 template <int PD_D>                      // datasets held in registers: 4 (more resident warps) or PD_FAST_D
-__global__ void __launch_bounds__(PAR_TILE, PD_D <= 4 ? 3 : 2)
-k_pseudodata_fast(const ParTile* __restrict__ tiles, int n_tiles, const JobDev* __restrict__ jobs,
+__global__ void __launch_bounds__(PAR_TILE, PD_D <= 4 ? 6 : 4)
+k_pseudodata_fast(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
                   const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
                   const int32_t* __restrict__ rowstart, double* __restrict__ beta, double* __restrict__ old_beta,
                   double* __restrict__ betahat, double* __restrict__ pw, const int32_t* __restrict__ pos,
                   const int64_t* __restrict__ start0, double* __restrict__ start /*null: already written*/) {
   // the table is read from global memory (L1): measured 0.93 ms against 1.08 ms with a per-block copy in shared memory
   const double* wtab = g_fast_w;
-  // The kernel waits for two levels of dependent loads (first-row look-up, then the row): every thread works on PD_ILP
-  // parameters, one from each of PD_ILP tiles, and issues each level for all of them before using any.
-  struct JobBits { int64_t par0, tab0, row0; int32_t P, E, D, des0; };     // the fields of JobDev used here
-  bool on[PD_ILP];
-  ParTile t[PD_ILP];
-  JobBits J[PD_ILP];
-  int first[PD_ILP], k[PD_ILP];
-  int64_t pi[PD_ILP];
+  const ParTile t = tiles[blockIdx.x];
+  const int c = ctl[t.job];
+  if (!(c & CTL_UPDATE)) return;
+  if ((int)threadIdx.x >= t.cnt) return;
+  const JobDev J = jobs[t.job];
+  const int first = (c & CTL_FIRST) ? 1 : 0;
+  const int k = t.k0 + threadIdx.x;
+  const int64_t pi = J.par0 + (int64_t)t.e * J.P + k;
+  double Cd[PD_D];
+  int r0s[PD_D], cv[PD_D], nm[PD_D];
+  double mp[PD_D];
 #pragma unroll
-  for (int h = 0; h < PD_ILP; ++h) {
-    const int ti = blockIdx.x * PD_ILP + h;
-    on[h] = ti < n_tiles;
-    first[h] = 0;
-    k[h] = 0;
-    pi[h] = 0;
-    J[h] = JobBits{0, 0, 0, 0, 1, 0, 0};
-    t[h] = ParTile{0, 0, 0, 0};
-    if (on[h]) {
-      t[h] = tiles[ti];
-      const int c = ctl[t[h].job];
-      on[h] = (c & CTL_UPDATE) && (int)threadIdx.x < t[h].cnt;
-      first[h] = (c & CTL_FIRST) ? 1 : 0;
-    }
-    if (on[h]) {
-      const JobDev* Jp = jobs + t[h].job;
-      J[h] = JobBits{Jp->par0, Jp->tab0, Jp->row0, Jp->P, Jp->E, Jp->D, Jp->des0};
-      k[h] = t[h].k0 + threadIdx.x;
-      pi[h] = J[h].par0 + (int64_t)t[h].e * J[h].P + k[h];
-    }
-  }
-  double Cd[PD_ILP][PD_D];
-  int r0s[PD_ILP][PD_D];
-#pragma unroll
-  for (int h = 0; h < PD_ILP; ++h)
-#pragma unroll
-    for (int d = 0; d < PD_D; ++d) {
-      Cd[h][d] = (on[h] && d < J[h].D) ? design[J[h].des0 + d * J[h].E + t[h].e] : 0.0;
-      r0s[h][d] = (on[h] && d < J[h].D && Cd[h][d] != 0) ? rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]] : -1;
-    }
-  int cv[PD_ILP][PD_D], nm[PD_ILP][PD_D];
-  double mp[PD_ILP][PD_D], b[PD_ILP];
-#pragma unroll
-  for (int h = 0; h < PD_ILP; ++h) {
-#pragma unroll
-    for (int d = 0; d < PD_D; ++d) {
-      const bool has = r0s[h][d] >= 0;
-      const int64_t g = has ? J[h].row0 + r0s[h][d] : 0;
-      cv[h][d] = has ? rc.cov[g] : 1;
-      nm[h][d] = has ? rc.nmeth[g] : 0;
-      mp[h][d] = (has && !first[h]) ? rc.mu_res[g] : 0.0;
-    }
-    b[h] = on[h] ? beta[pi[h]] : 0.0;
+  for (int d = 0; d < PD_D; ++d) {
+    Cd[d] = d < J.D ? design[J.des0 + d * J.E + t.e] : 0.0;
+    r0s[d] = (d < J.D && Cd[d] != 0) ? rowstart[J.tab0 + (int64_t)d * J.P + k] : -1;
   }
 #pragma unroll
-  for (int h = 0; h < PD_ILP; ++h) {
-    if (!on[h]) continue;
-    if (start && t[h].e == 0) {
-      // the support (BinDesign::starts): the position of the parameter, read from the first dataset that has it.
-      // With several estimators a position may belong to datasets of another condition only: look at all datasets.
-      int rs = -1;
-#pragma unroll
-      for (int d = 0; d < PD_D; ++d)
-        if (rs < 0 && d < J[h].D) rs = r0s[h][d] >= 0 ? r0s[h][d] : rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]];
-      for (int d = PD_D; d < J[h].D && rs < 0; ++d) rs = rowstart[J[h].tab0 + (int64_t)d * J[h].P + k[h]];
-      if (rs >= 0) start[start0[t[h].job] + k[h]] = (double)(int32_t)(double)(uint32_t)pos[J[h].row0 + rs];
-    }
-    double Wd[PD_D], Zd[PD_D];
-    double wt = 0.0;
-#pragma unroll
-    for (int d = 0; d < PD_D; ++d) {
-      Wd[d] = 0.0;
-      Zd[d] = 0.0;
-      if (r0s[h][d] >= 0) {
-        double z, W;
-        fast_residual(wtab, first[h], nm[h][d], cv[h][d], mp[h][d], z, W);
-        Wd[d] = 0.0 + W;                   // Binner::bin starts its sums at zero (Binner.cpp:29-36)
-        Zd[d] = 0.0 + z * W;
-        wt += (Cd[h][d] * Wd[d]) * Cd[h][d];
-      }
-    }
-    double inv = 1 / wt;
-    if (!is_finite(inv)) inv = 0.0;        // pseudo-inverse (pseudodata_helpers.hpp:33-34)
-    double bh = 0.0;
-#pragma unroll
-    for (int d = 0; d < PD_D; ++d) {
-      if (r0s[h][d] >= 0) {
-        const double q = Zd[d] / Wd[d];
-        const double zhat = (Wd[d] == 0) ? Wd[d] : q;
-        bh += (inv * Cd[h][d]) * (Wd[d] * zhat);
-      }
-    }
-    old_beta[pi[h]] = b[h];
-    betahat[pi[h]] = bh + b[h];
-    pw[pi[h]] = wt;
+  for (int d = 0; d < PD_D; ++d) {
+    const int64_t g = J.row0 + (r0s[d] >= 0 ? r0s[d] : 0);
+    cv[d] = r0s[d] >= 0 ? rc.cov[g] : 1;
+    nm[d] = r0s[d] >= 0 ? rc.nmeth[g] : 0;
+    mp[d] = (r0s[d] >= 0 && !first) ? rc.mu_res[g] : 0.0;
   }
+  const double b = beta[pi];
+  if (start && t.e == 0) {
+    // the support (BinDesign::starts): the position of the parameter, read from the first dataset that has it.
+    // With several estimators a position may belong to datasets of another condition only: look at all datasets.
+    int rs = -1;
+    for (int d = 0; d < J.D && rs < 0; ++d) rs = d < PD_D && r0s[d] >= 0 ? r0s[d] : rowstart[J.tab0 + (int64_t)d * J.P + k];
+    if (rs >= 0) start[start0[t.job] + k] = (double)(int32_t)(double)(uint32_t)pos[J.row0 + rs];
+  }
+  double Wd[PD_D], Zd[PD_D];
+  double wt = 0.0;
+#pragma unroll
+  for (int d = 0; d < PD_D; ++d) {
+    Wd[d] = 0.0;
+    Zd[d] = 0.0;
+    if (r0s[d] >= 0) {
+      double z, W;
+      fast_residual(wtab, first, nm[d], cv[d], mp[d], z, W);
+      Wd[d] = 0.0 + W;                   // Binner::bin starts its sums at zero (Binner.cpp:29-36)
+      Zd[d] = 0.0 + z * W;
+      wt += (Cd[d] * Wd[d]) * Cd[d];
+    }
+  }
+  double inv = 1 / wt;
+  if (!is_finite(inv)) inv = 0.0;        // pseudo-inverse (pseudodata_helpers.hpp:33-34)
+  double bh = 0.0;
+#pragma unroll
+  for (int d = 0; d < PD_D; ++d) {
+    if (r0s[d] >= 0) {
+      const double q = Zd[d] / Wd[d];
+      const double zhat = (Wd[d] == 0) ? Wd[d] : q;
+      bh += (inv * Cd[d]) * (Wd[d] * zhat);
+    }
+  }
+  old_beta[pi] = b;
+  betahat[pi] = bh + b;
+  pw[pi] = wt;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1474,7 +1437,10 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     J.ptile0 = pt_at;
     h_start0[j] = nstart;
     for (int e = 0; e < J.E; ++e) {
-      series.push_back(FlsaSeries{npar + (int64_t)e * J.P, J.P, p.lambda2});
+      FlsaSeries fs{npar + (int64_t)e * J.P, J.P, p.lambda2};
+      // FULL: at most rows / datasets bins of an estimator hold a position (the even bins are mostly empty)
+      if (!fast && J.P > 0) fs.density = std::min(1.0, (double)J.nrows / std::max(1, (int)J.D) / (double)J.P);
+      series.push_back(fs);
       pt_spans.push_back(TileSpan{0, (int64_t)J.P, j, e, PAR_TILE, 0});
       pt_nt.push_back(span_tiles(J.P, PAR_TILE));
       pt_at += pt_nt.back();
@@ -1637,11 +1603,11 @@ std::unique_ptr<Result> batch_detect(Engine& eng, Batch& b, const Params& p) {
     };
     if (any_update) {
       if (p.model == MODEL_FAST && max_D <= 4)
-        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<4><<<cdiv(n_pt, PD_ILP), PAR_TILE, 0, st>>>(cx.ptiles.p, n_pt, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<4><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
                                                         cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                                         res->pw.p, b.pos.p, cx.start0.p, start_by_pseudodata ? res->start.p : nullptr));
       else if (p.model == MODEL_FAST && max_D <= PD_FAST_D)
-        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<PD_FAST_D><<<cdiv(n_pt, PD_ILP), PAR_TILE, 0, st>>>(cx.ptiles.p, n_pt, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
+        ML_LAUNCH(eng, "k_pseudodata", k_pseudodata_fast<PD_FAST_D><<<n_pt, PAR_TILE, 0, st>>>(cx.ptiles.p, cx.jobs.p, cx.ctl.p, rc, cx.design.p,
                                                                 cx.rowstart.p, res->beta.p, cx.old_beta.p, res->betahat.p,
                                                                 res->pw.p, b.pos.p, cx.start0.p, start_by_pseudodata ? res->start.p : nullptr));
       else

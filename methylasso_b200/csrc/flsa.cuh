@@ -9,6 +9,8 @@ struct FlsaSeries {
   int64_t off;  // element offset of the series in the concatenated y / w / beta arrays
   int32_t n;
   double lam;
+  int64_t off_in = -1;   // >= 0: y / w are read at this offset instead (several series on one input stream)
+  double density = 1.0;  // hint: share of the elements with a positive weight (FULL model: non-empty bins)
 };
 
 struct TileDesc {

@@ -58,6 +58,8 @@ struct SeriesDesc {
   double lam;
   int32_t warm;         // warm-up steps in front of each chunk of this series (0: the launch's default)
   int32_t pad;
+  int64_t off_in;       // offset of element 0 in the INPUT arrays y / w (== off unless several series share one input: the
+                        // lanes of a lambda2 sweep read the same pseudodata)
 };
 
 struct ChunkDesc {
@@ -324,6 +326,26 @@ ML_HD bool dp_step_c(KnotsC<Ring>& q, double y, double w, double lam, double& tm
   q.xr = tp; q.ar = ar; q.br = brs;
   return true;
 }
+// A zero-weight element (an empty bin of the FULL model's even binning: four bins in five) leaves the message unchanged in
+// exact arithmetic; the reference still runs its step, which re-derives the two end knots from themselves.  That step
+// depends on the state alone (w y = 0 whatever y), so once it has left the window bit for bit as it found it, it is a
+// fixed point: every further zero-weight element in a row returns the same back-pointers (the end knots' positions)
+// and changes nothing.  `fixed` carries that knowledge from one element to the next; any other element resets it.
+template <class Ring>
+ML_HD bool dp_step_z(KnotsC<Ring>& q, double y, double w, double lam, double& tm, double& tp, bool& fixed) {
+  if (w == 0.0 && y == y && !(y - y != 0.0)) {          // w y is a zero (y finite)
+    if (fixed) { tm = q.xl; tp = q.xr; return true; }
+    const int l0 = q.l, r0 = q.r;
+    const double xl = q.xl, al = q.al, bl = q.bl, xr = q.xr, ar = q.ar, br = q.br;
+    const bool ok = dp_step_c(q, y, w, lam, tm, tp);
+    fixed = ok && q.l == l0 && q.r == r0 && f64_bits(q.xl) == f64_bits(xl) && f64_bits(q.al) == f64_bits(al) &&
+            f64_bits(q.bl) == f64_bits(bl) && f64_bits(q.xr) == f64_bits(xr) && f64_bits(q.ar) == f64_bits(ar) &&
+            f64_bits(q.br) == f64_bits(br);
+    return ok;
+  }
+  fixed = false;
+  return dp_step_c(q, y, w, lam, tm, tp);
+}
 template <class Ring>
 ML_HD double dp_last(const KnotsC<Ring>& q, double y, double w, double lam) {
   double alo = w, blo = -w * y - lam;
@@ -405,7 +427,7 @@ ML_HD void flsa_spec_run(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, co
     pristine = true;   // the window still holds only its +-inf sentinel
     k = kb - warm;
   }
-  bool ok = true;
+  bool ok = true, zfix = false;
   for (; k < cd.ke && ok; ++k) {
     if (k == kb) window_save(q, W.s_count, W.sx, W.sa, W.sb, W.stride, c);
     if (pristine) {
@@ -417,7 +439,7 @@ ML_HD void flsa_spec_run(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, co
       }
       pristine = false;
     }
-    ok = dp_step_c(q, y[k], w[k], lam, t1, t2);
+    ok = dp_step_z(q, y[k], w[k], lam, t1, t2, zfix);
     if (ok && k >= kb) {
       tm[k] = t1;
       tp[k] = t2;
@@ -442,8 +464,9 @@ ML_HD bool flsa_redo_chunk(const SeriesDesc& S, const ChunkDesc& cd, const doubl
                            const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
                            KnotsC<Ring>& q, bool* irregular) {
   double t1, t2;
+  bool zfix = false;
   for (int k = cd.kb; k < cd.ke; ++k) {
-    if (!dp_step_c(q, y[k], w[k], S.lam, t1, t2)) return false;
+    if (!dp_step_z(q, y[k], w[k], S.lam, t1, t2, zfix)) return false;
     tm[k] = t1;
     tp[k] = t2;
     if (t1 > t2) *irregular = true;

@@ -149,6 +149,37 @@ def test_lambda_sweep_config5(engine, oracle):
         assert kkt_residual(y, w, g, float(lam)) < 1e-8
 
 
+def test_lambda_sweep_on_the_resident_fit(engine, oracle):
+    """BASELINE config 5 as the engine runs it: ml_result_lambda_sweep - the 16 lambda2 lanes of every chromosome read ONE
+    resident pseudodata stream (no tiling of y / w).  Every lane equals the single-lambda2 fit bit for bit (same FLSA, same
+    centring), its segment count the single fit's, and the port's coefficients to 1e-10."""
+    from methylasso_b200._native import MlParams
+    tables = [synth.chromosome_table(n, 770 + i, (3,)) for i, n in enumerate((40_000, 25_000))]
+    ptr, cols = synth.concat_jobs(tables)
+    lams = np.geomspace(10, 2000, 16)
+    lams[::4] = np.round(lams[::4])
+    res = engine.detect_batch(ptr, cols, MlParams(25.0, 26.0, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+    try:
+        nseg, beta = res.lambda_sweep(lams, 0.01, want_beta=True)
+        sizes = [res.sizes(j)[1] for j in range(res.njobs)]
+    finally:
+        res.free()
+    for i in (0, 5, 12, 15):
+        lam = float(lams[i])
+        one = engine.detect_batch(ptr, cols, MlParams(lam, lam + 1, 0.0, 0.01, 50.0, 1.0, 1, 1, 1, 0, 0, 0))
+        try:
+            at = 0
+            for j, P in enumerate(sizes):
+                assert np.array_equal(beta[i, at:at + P], one.job(j)["estimates"]["beta"]), (lam, j)
+                want = oracle.detect(tables[j], oracle.MODEL_FAST, lambda2=lam)["estimates"]["beta"]
+                assert np.all(np.abs(beta[i, at:at + P] - want) <= 1e-10 * np.maximum(np.abs(want), 1e-3)), (lam, j)
+                at += P
+            assert int(nseg[i]) == one.segments_count(0.01), lam
+        finally:
+            one.free()
+    assert np.all(np.diff(nseg) <= 0) or nseg[0] > nseg[-1]       # a larger penalty fuses more
+
+
 def test_hypothesis_kkt_and_oracle(engine, oracle):
     """Property test on arbitrary inputs: optimality conditions + agreement with the oracle."""
     from hypothesis import given, settings, strategies as st
