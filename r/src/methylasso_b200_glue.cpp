@@ -44,7 +44,11 @@ List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml
   std::vector<int> status(nj);
   check(ml_detect_batch(engine(), nj, job_ptr.data(), dset.begin(), cond.begin(), rep.begin(), pos.begin(),
                         nmeth.begin(), cov.begin(), &p, &res, status.data()));
-  if (diff_fast) check(ml_result_fast_diff_combine(engine(), res));
+  if (diff_fast) {
+    const int rc_diff = ml_result_fast_diff_combine(engine(), res);
+    if (rc_diff != ML_OK) { const std::string msg = ml_last_error(); ml_result_free(res); stop(msg); }
+  }
+  Rcpp::checkUserInterrupt();        // the fit is done and resident; nothing is lost by stopping here but the result
   List out(nj);
   for (int j = 0; j < nj; ++j) {
     int64_t n, P; int32_t E, D, st;
@@ -58,8 +62,9 @@ List detect(const DataFrame& data, const std::vector<int64_t>& job_ptr, const ml
     // ever reads ret$mu (R/genome_wide.R:9 only concatenates it): want_mu = FALSE leaves it on the device
     NumericVector mu(want_mu ? n : 0), lambda2(E), offset(D), start(E * P), beta(E * P), betahat(E * P), pw(E * P);
     IntegerVector id(E * P);
-    check(ml_result_copy_job(engine(), res, j, want_mu ? mu.begin() : nullptr, lambda2.begin(), offset.begin(), id.begin(),
-                             start.begin(), beta.begin(), betahat.begin(), pw.begin()));
+    const int rc_copy = ml_result_copy_job(engine(), res, j, want_mu ? mu.begin() : nullptr, lambda2.begin(), offset.begin(),
+                                           id.begin(), start.begin(), beta.begin(), betahat.begin(), pw.begin());
+    if (rc_copy != ML_OK) { const std::string msg = ml_last_error(); ml_result_free(res); stop(msg); }
     int32_t conv; double hyper;
     ml_result_job_info(res, j, &conv, nullptr, nullptr, nullptr, &hyper, nullptr);
     DataFrame est = DataFrame::create(_["estimate_id"] = id, _["start"] = start, _["beta"] = beta,
@@ -198,13 +203,14 @@ DataFrame call_differences_batch(const DataFrame& data, const NumericVector& job
 
 // NEW: Part 1 of the CLI in one native call: signal_detection_fast of every chromosome (R/genome_wide.R:64-78) and the
 // rule engine of segment_methylation_singlechr (R/call.R:31-221) on the resident fit - call table, LMR / UMR annotation,
-// std fusion, valleys, PMD split / calls and the segments' PMD status.  Returns list(lmr_umr_valley, pmd) with drop = F
-// semantics (all rows; category / PMD.status are NA where the reference has NA); segment_methylation_gpu in
-// r/R/genome_wide_gpu.R applies the drop of :214-218 and names the columns.  `lmr` / `valley` / `pmd` are numeric vectors
-// in the field order of ml_lmr_params / ml_valley_params / ml_pmd_params (include/methylasso_b200.h).
+// std fusion, valleys, PMD split / calls and the segments' PMD status - with the two result tables assembled on the
+// device (ml_result_segment_methylation): only their rows cross PCIe.  `drop` is the reference's (:214-218).  Chromosomes
+// are processed `chunk_jobs` at a time so that R can interrupt between chunks (Rcpp::checkUserInterrupt, as
+// core/Estimator.hpp:50 and core/Posterior.ipp:17,53 do inside their loops).  `lmr` / `valley` / `pmd` are numeric
+// vectors in the field order of ml_lmr_params / ml_valley_params / ml_pmd_params (include/methylasso_b200.h).
 List segment_methylation_batch(const DataFrame& data, const NumericVector& job_ptr, double lambda2, double tol_val,
                                double max_distance, const NumericVector& lmr, const NumericVector& valley,
-                               const NumericVector& pmd) {
+                               const NumericVector& pmd, bool drop = true, int chunk_jobs = 8) {
   need_columns(data);
   if (lmr.size() != 12 || valley.size() != 4 || pmd.size() != 5) stop("lmr / valley / pmd must hold 12 / 4 / 5 values");
   IntegerVector dset = data["dataset"], cond = data["condition"], rep = data["replicate"], pos = data["pos"],
@@ -215,77 +221,90 @@ List segment_methylation_batch(const DataFrame& data, const NumericVector& job_p
                          (int32_t)lmr[11]};
   const ml_valley_params vp{valley[0], valley[1], valley[2], (int32_t)valley[3], 0};
   const ml_pmd_params pp{pmd[0], pmd[1], pmd[2], (int32_t)pmd[3], (int32_t)pmd[4]};
-  ml_batch* batch = nullptr;
-  ml_result* res = nullptr;
-  std::vector<int> status(nj);
-  check(ml_batch_upload(engine(), nj, ptr.data(), dset.begin(), cond.begin(), rep.begin(), pos.begin(), nmeth.begin(),
-                        cov.begin(), &batch, nullptr));
   const ml_params p = fast_params(lambda2, tol_val, 1);
-  int rc = ml_batch_detect(engine(), batch, &p, &res, status.data());
-  auto bail = [&](int code) { if (code != ML_OK) { ml_result_free(res); ml_batch_free(batch); stop(ml_last_error()); } };
-  bail(rc);
-  int64_t nc = 0, nv = 0, nr = 0, nm = 0, npc = 0, np = 0, nf = 0;
-  // call table (:43-72), valleys (:100-133), merged table (:131-140), PMD table (:169-199), final rows (:201-215)
-  bail(ml_result_call_table(engine(), res, tol_val, max_distance, &nc, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
-  NumericVector c_width(nc), c_beta(nc), c_cov(nc), c_pw(nc), c_std(nc);
-  IntegerVector c_ncpg(nc);
-  bail(ml_result_call_table(engine(), res, tol_val, max_distance, &nc, 0, 0, 0, 0, 0, c_width.begin(), c_beta.begin(),
-                            c_cov.begin(), c_pw.begin(), c_ncpg.begin(), c_std.begin()));
-  bail(ml_result_call_valleys(engine(), res, tol_val, max_distance, &lp, &vp, &nv, 0, 0, 0, 0, 0, 0, 0, 0, 0, &nr, 0, 0, 0));
-  NumericVector v_width(nv), v_beta(nv), v_cov(nv), v_pw(nv);
-  IntegerVector v_ncpg(nv);
-  bail(ml_result_call_valleys(engine(), res, tol_val, max_distance, &lp, &vp, &nv, 0, 0, 0, 0, v_width.begin(), v_beta.begin(),
-                              v_cov.begin(), v_pw.begin(), v_ncpg.begin(), &nr, 0, 0, 0));
-  bail(ml_result_call_pmd_split(engine(), res, tol_val, max_distance, pp.pmd_lambda2, &lp, &vp, pp.split_pmds, &nm, 0, 0, 0, 0, 0,
-                                0, 0, 0, 0, &npc, 0, 0, 0, 0, 0, 0, 0));
-  IntegerVector m_seg(nm);
-  bail(ml_result_call_pmd_split(engine(), res, tol_val, max_distance, pp.pmd_lambda2, &lp, &vp, pp.split_pmds, &nm, 0, 0,
-                                m_seg.begin(), 0, 0, 0, 0, 0, 0, &npc, 0, 0, 0, 0, 0, 0, 0));
-  bail(ml_result_call_pmds(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &np, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
-  IntegerVector p_job(np), p_cond(np), p_seg(np), p_ncpg(np);
-  std::vector<int8_t> p_cat(np);
-  std::vector<uint32_t> p_start(np), p_end(np);
-  NumericVector p_width(np), p_fused(np), p_beta(np), p_std(np);
-  bail(ml_result_call_pmds(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &np, p_job.begin(), p_cond.begin(), p_cat.data(),
-                           p_seg.begin(), p_start.data(), p_end.data(), p_width.begin(), p_ncpg.begin(), p_fused.begin(),
-                           p_beta.begin(), p_std.begin()));
-  bail(ml_result_call_pmd_status(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &nf, 0, 0, 0, 0, 0, 0, 0, 0, 0));
-  IntegerVector f_job(nf), f_cond(nf), f_merged(nf), f_row(nf), f_val(nf);
-  std::vector<int8_t> f_cat(nf), f_status(nf);
-  std::vector<uint32_t> f_start(nf), f_end(nf);
-  rc = ml_result_call_pmd_status(engine(), res, tol_val, max_distance, &lp, &vp, &pp, &nf, f_job.begin(), f_cond.begin(),
-                                 f_start.data(), f_end.data(), f_cat.data(), f_status.data(), f_merged.begin(), f_row.begin(),
-                                 f_val.begin());
-  ml_result_free(res);
-  ml_batch_free(batch);
-  check(rc);
-  // the value columns of a final row come from its call-table row or from its valley (std is NA on a valley)
-  NumericVector start(nf), end(nf), width(nf), beta(nf), coverage(nf), pw(nf), sd(nf);
-  IntegerVector segment_id(nf), ncpg(nf);
-  CharacterVector category(nf), pmd_status(nf);
-  static const char* cat_names[] = {nullptr, "LMR", "UMR", "UMR-DMV"};
-  for (int64_t i = 0; i < nf; ++i) {
-    const int r = f_row[i], v = f_val[i];
-    start[i] = f_start[i]; end[i] = f_end[i]; segment_id[i] = m_seg[f_merged[i]];
-    width[i] = r >= 0 ? c_width[r] : v_width[v];
-    beta[i] = r >= 0 ? c_beta[r] : v_beta[v];
-    coverage[i] = r >= 0 ? c_cov[r] : v_cov[v];
-    pw[i] = r >= 0 ? c_pw[r] : v_pw[v];
-    ncpg[i] = r >= 0 ? c_ncpg[r] : v_ncpg[v];
-    sd[i] = r >= 0 ? c_std[r] : NA_REAL;
-    if (f_cat[i] == 0) category[i] = NA_STRING; else category[i] = cat_names[f_cat[i]];
-    if (f_status[i] < 0) pmd_status[i] = NA_STRING; else pmd_status[i] = f_status[i] == 1 ? "PMD" : "other";
+  ml_engine_set(engine(), "want_mu", 0);          // nothing below reads mu
+  struct Part {
+    std::vector<int32_t> job, condition, segment_id, num_cpgs, p_job, p_condition, p_segment_id, p_num_cpgs;
+    std::vector<uint32_t> start, end, p_start, p_end;
+    std::vector<double> width, beta, coverage, pw, sd, p_width, p_beta, p_std, p_fused;
+    std::vector<int8_t> category, status, p_category;
+  };
+  std::vector<Part> parts;
+  if (chunk_jobs < 1) chunk_jobs = 1;
+  for (int j0 = 0; j0 < nj; j0 += chunk_jobs) {
+    Rcpp::checkUserInterrupt();                   // between chunks: nothing native is alive here
+    const int j1 = std::min(nj, j0 + chunk_jobs), n = j1 - j0;
+    std::vector<int64_t> sub(n + 1);
+    for (int j = 0; j <= n; ++j) sub[j] = ptr[j0 + j] - ptr[j0];
+    const int64_t r0 = ptr[j0];
+    ml_batch* batch = nullptr;
+    ml_result* res = nullptr;
+    std::vector<int> status(n);
+    auto bail = [&](int code) {
+      if (code != ML_OK) {
+        const std::string msg = ml_last_error();
+        ml_result_free(res);
+        ml_batch_free(batch);
+        ml_engine_set(engine(), "want_mu", 1);
+        stop(msg);
+      }
+    };
+    bail(ml_batch_upload(engine(), n, sub.data(), dset.begin() + r0, cond.begin() + r0, rep.begin() + r0, pos.begin() + r0,
+                         nmeth.begin() + r0, cov.begin() + r0, &batch, nullptr));
+    bail(ml_batch_detect(engine(), batch, &p, &res, status.data()));
+    int64_t ns = 0, np = 0;
+    bail(ml_result_segment_methylation(engine(), res, tol_val, max_distance, &lp, &vp, &pp, drop ? 1 : 0, &ns, 0, 0, 0, 0, 0, 0, 0,
+                                       0, 0, 0, 0, 0, 0, &np, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    Part q;
+    q.job.resize(ns); q.condition.resize(ns); q.start.resize(ns); q.end.resize(ns); q.width.resize(ns); q.segment_id.resize(ns);
+    q.beta.resize(ns); q.coverage.resize(ns); q.pw.resize(ns); q.num_cpgs.resize(ns); q.sd.resize(ns); q.category.resize(ns);
+    q.status.resize(ns);
+    q.p_job.resize(np); q.p_condition.resize(np); q.p_start.resize(np); q.p_end.resize(np); q.p_width.resize(np);
+    q.p_segment_id.resize(np); q.p_beta.resize(np); q.p_std.resize(np); q.p_category.resize(np); q.p_num_cpgs.resize(np);
+    q.p_fused.resize(np);
+    bail(ml_result_segment_methylation(engine(), res, tol_val, max_distance, &lp, &vp, &pp, drop ? 1 : 0, &ns, q.job.data(),
+                                       q.condition.data(), q.start.data(), q.end.data(), q.width.data(), q.segment_id.data(),
+                                       q.beta.data(), q.coverage.data(), q.pw.data(), q.num_cpgs.data(), q.sd.data(),
+                                       q.category.data(), q.status.data(), &np, q.p_job.data(), q.p_condition.data(),
+                                       q.p_start.data(), q.p_end.data(), q.p_width.data(), q.p_segment_id.data(), q.p_beta.data(),
+                                       q.p_std.data(), q.p_category.data(), q.p_num_cpgs.data(), q.p_fused.data()));
+    ml_result_free(res);
+    ml_batch_free(batch);
+    for (auto& v : q.job) v += j0;
+    for (auto& v : q.p_job) v += j0;
+    parts.push_back(std::move(q));
   }
-  NumericVector ps(p_start.begin(), p_start.end()), pe(p_end.begin(), p_end.end());
-  CharacterVector pc(np);
-  for (int64_t i = 0; i < np; ++i) pc[i] = p_cat[i] == 1 ? "PMD" : "other";
+  ml_engine_set(engine(), "want_mu", 1);
+  int64_t nf = 0, np = 0;
+  for (const Part& q : parts) { nf += (int64_t)q.job.size(); np += (int64_t)q.p_job.size(); }
+  IntegerVector f_job(nf), f_cond(nf), segment_id(nf), ncpg(nf), p_job(np), p_cond(np), p_seg(np), p_ncpg(np);
+  NumericVector start(nf), end(nf), width(nf), beta(nf), coverage(nf), pw(nf), sd(nf), ps(np), pe(np), p_width(np), p_beta(np),
+      p_std(np), p_fused(np);
+  CharacterVector category(nf), pmd_status(nf), pc(np);
+  static const char* cat_names[] = {nullptr, "LMR", "UMR", "UMR-DMV"};
+  int64_t a = 0, b = 0;
+  for (const Part& q : parts) {
+    for (size_t i = 0; i < q.job.size(); ++i, ++a) {
+      f_job[a] = q.job[i] + 1; f_cond[a] = q.condition[i]; start[a] = q.start[i]; end[a] = q.end[i]; width[a] = q.width[i];
+      segment_id[a] = q.segment_id[i]; beta[a] = q.beta[i]; coverage[a] = q.coverage[i]; pw[a] = q.pw[i]; ncpg[a] = q.num_cpgs[i];
+      sd[a] = q.sd[i] == q.sd[i] ? q.sd[i] : NA_REAL;                       // NaN marks a valley: it has no std column
+      if (q.category[i] == 0) category[a] = NA_STRING; else category[a] = cat_names[q.category[i]];
+      if (q.status[i] < 0) pmd_status[a] = NA_STRING; else pmd_status[a] = q.status[i] == 1 ? "PMD" : "other";
+    }
+    for (size_t i = 0; i < q.p_job.size(); ++i, ++b) {
+      p_job[b] = q.p_job[i] + 1; p_cond[b] = q.p_condition[i]; ps[b] = q.p_start[i]; pe[b] = q.p_end[i]; p_width[b] = q.p_width[i];
+      p_seg[b] = q.p_segment_id[i]; p_beta[b] = q.p_beta[i]; p_std[b] = q.p_std[i]; p_ncpg[b] = q.p_num_cpgs[i];
+      p_fused[b] = q.p_fused[i];
+      pc[b] = q.p_category[i] == 1 ? "PMD" : "other";
+    }
+  }
   return List::create(
-      _["lmr_umr_valley"] = DataFrame::create(_["job"] = f_job + 1, _["condition"] = f_cond, _["start"] = start, _["end"] = end,
+      _["lmr_umr_valley"] = DataFrame::create(_["job"] = f_job, _["condition"] = f_cond, _["start"] = start, _["end"] = end,
                                               _["width"] = width, _["segment_id"] = segment_id, _["beta"] = beta,
                                               _["coverage"] = coverage, _["pseudoweight"] = pw, _["num.cpgs"] = ncpg,
                                               _["std"] = sd, _["category"] = category, _["PMD.status"] = pmd_status,
                                               _["stringsAsFactors"] = false),
-      _["pmd"] = DataFrame::create(_["job"] = p_job + 1, _["condition"] = p_cond, _["start"] = ps, _["end"] = pe,
+      _["pmd"] = DataFrame::create(_["job"] = p_job, _["condition"] = p_cond, _["start"] = ps, _["end"] = pe,
                                    _["width"] = p_width, _["segment_id"] = p_seg, _["beta"] = p_beta, _["std"] = p_std,
                                    _["category"] = pc, _["num.cpgs"] = p_ncpg, _["fused_std"] = p_fused,
                                    _["stringsAsFactors"] = false));
@@ -320,7 +339,9 @@ RCPP_MODULE(MethyLasso_cpp) {
   function("weighted_1d_flsa", &weighted_1d_flsa, List::create(_["y"], _["wt"], _["lambda2"], _["lambda1"] = 0));
   function("signal_detection_fast_batch", &signal_detection_fast_batch);
   function("call_differences_batch", &call_differences_batch);
-  function("segment_methylation_batch", &segment_methylation_batch);
+  function("segment_methylation_batch", &segment_methylation_batch,
+           List::create(_["data"], _["job_ptr"], _["lambda2"], _["tol_val"], _["max_distance"], _["lmr"], _["valley"], _["pmd"],
+                        _["drop"] = true, _["chunk_jobs"] = 8));
   function("wilcoxon_groups", &wilcoxon_groups);
   function("p_adjust_fdr", &p_adjust_fdr);
 }
