@@ -641,15 +641,18 @@ def run_aux(args, local):
         n_samples, scale = 64, 8
         mine = [s for s in range(n_samples) if s % world == rank]          # samples are the same size: round-robin
         t0 = time.perf_counter()
+        per_call = 8                      # samples handed to the engine per call: their 8 x 24 chromosomes are jobs of one batch
         samples = []
-        for s_ in mine:
-            tabs = synth.genome_tables(4, total_cpgs=synth.GENOME_CPGS // scale, reps_per_condition=(1,),
-                                       seed=(synth.BASE_SEED + 4) * 1000 + s_)
+        for c0 in range(0, len(mine), per_call):
+            tabs = []
+            for s_ in mine[c0:c0 + per_call]:
+                tabs += synth.genome_tables(4, total_cpgs=synth.GENOME_CPGS // scale, reps_per_condition=(1,),
+                                            seed=(synth.BASE_SEED + 4) * 1000 + s_)
             samples.append(synth.concat_jobs(tabs))
         gen_s = time.perf_counter() - t0
-        G = 4 if world == 1 else 3
-        # one pipeline per sample shape would re-pin per sample; the cohort is processed sample by sample through ONE
-        # pool of engines, the chromosomes of a sample split over the engines
+        G = 6 if world == 1 else 3
+        # the cohort goes through ONE pool of engines, `per_call` samples at a time: the engine takes any number of jobs per
+        # call, and 8 samples of this size are as much work as one full genome (a sample alone is latency-bound)
         pool_pipe = GenomePipeline(samples[0][0], samples[0][1], n_engines=G, device=local, lambda2=LAMBDA2, tol_val=TOL, pin=True)
         prepared = []                       # every sample's chromosome groups in page-locked memory of their own (the host
         for ptr, cols in samples:           # buffers the timed calls read from)
@@ -678,8 +681,8 @@ def run_aux(args, local):
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1) / max(1, steps // 2)], device="cuda", dtype=torch.float64)
-        tot = torch.tensor([float(sum(int(np.unique(c["pos"][p[j]:p[j + 1]]).size) for p, c in samples[:1] for j in range(p.size - 1)))
-                            * len(samples), float(rows_mine), float(nreg)], device="cuda", dtype=torch.float64)
+        # one replicate per sample: every row is a position of its own
+        tot = torch.tensor([float(rows_mine), float(rows_mine), float(nreg)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -691,9 +694,9 @@ def run_aux(args, local):
                     "config": {"workload": "configs[3]: 64 synthetic single-replicate samples of 24 chromosomes at 1/%d of the genome "
                                            "size (%d CpGs each: 64 full genomes do not fit the host's memory budget of a bench "
                                            "run), segmented independently, samples dealt to the ranks round-robin" % (scale, synth.GENOME_CPGS // scale),
-                               "samples": n_samples, "samples_per_rank": len(mine), "engines_per_gpu": G},
-                    "what": "per sample: host columns (pinned) -> ml_batch_stage / commit -> detect -> region tables on the host "
-                            "(GenomePipeline.segment_methylation); max over ranks of the time for the rank's samples",
+                               "samples": n_samples, "samples_per_rank": len(mine), "samples_per_call": per_call, "engines_per_gpu": G},
+                    "what": "per call (8 samples = 192 chromosomes): host columns (pinned) -> ml_batch_stage / commit -> detect -> region "
+                            "tables on the host (GenomePipeline.segment_methylation); max over ranks of the time for the rank's samples",
                     "rows": float(tot[1].item()), "region_rows": float(tot[2].item()), "generation_s_rank0": gen_s}
         pool_pipe.close()
         if world > 1:

@@ -149,3 +149,26 @@ def test_two_ranks_gloo_rule_engine_tables(oracle):
             w = np.concatenate([x[name][k] for x in want])
             assert np.array_equal(gathered[name][k], w, equal_nan=True) and gathered[name][k].dtype == w.dtype, (name, k)
     assert gathered["pmd"]["start"].size > 10 and (gathered["lmr_umr_valley"]["category"] > 0).sum() > 30
+
+
+def test_gather_layout_matches_the_python_unpack():
+    """ml_gather_layout (the slot layout of the native K16 exchange, no GPU needed): 64-byte header, the 13 + 11 columns of
+    the two region tables back to back, each 16-byte aligned and sized by its dtype; RegionGather.fetch slices the
+    fetched bytes with exactly these offsets."""
+    import ctypes as C
+    from methylasso_b200 import _native
+    from methylasso_b200.api import Result
+    lib = _native.load()
+    cols = list(Result.REGION_SEG_COLUMNS) + list(Result.REGION_PMD_COLUMNS)
+    assert len(cols) == 24
+    for ns, npm in ((0, 0), (1, 1), (31147, 1458), (5, 100003)):
+        off = (C.c_int64 * 24)()
+        tot = C.c_int64()
+        assert lib.ml_gather_layout(ns, npm, off, C.byref(tot)) == 0
+        at = 64
+        for c, (name, dt) in enumerate(cols):
+            assert off[c] == at and at % 16 == 0, (name, off[c], at)
+            n = ns if c < 13 else npm
+            at += (n * np.dtype(dt).itemsize + 15) // 16 * 16
+        assert tot.value == at
+    assert lib.ml_gather_layout(-1, 0, None, C.byref(tot)) != 0
