@@ -181,6 +181,9 @@ int ml_engine_create(int device, ml_engine** out) {
   env_int("ML_FLSA_WARM_BIG", h->e.flsa_warm_big);
   env_int("ML_FLSA_CHUNK_SMALL", h->e.flsa_chunk_small);
   env_int("ML_FLSA_WARM_SMALL", h->e.flsa_warm_small);
+  env_int("ML_FLSA_ROUTE", h->e.flsa_route);
+  env_int("ML_FLSA_SCAN_CHUNK_SMALL", h->e.flsa_scan_chunk_small);
+  env_int("ML_FLSA_SCAN_CHUNK_BIG", h->e.flsa_scan_chunk_big);
   env_int("ML_HOST_THREADS", h->e.host_threads);
   *out = guard.release();
   return ML_OK;
@@ -207,6 +210,9 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   if (k == "flsa_chunk") eng->e.flsa_chunk = (int)value;
   else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
   else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
+  else if (k == "flsa_route") eng->e.flsa_route = (int)value;
+  else if (k == "flsa_scan_chunk_small") eng->e.flsa_scan_chunk_small = (int)std::max<long long>(1, value);
+  else if (k == "flsa_scan_chunk_big") eng->e.flsa_scan_chunk_big = (int)std::max<long long>(1, value);
   else if (k == "host_threads") eng->e.host_threads = (int)std::max<long long>(1, value);
   else if (k == "want_mu") eng->e.want_mu = value != 0;
   else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }

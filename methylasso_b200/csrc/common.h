@@ -114,6 +114,10 @@ struct Engine {
   int flsa_sequential = 0;  // 1 = one thread per series start-to-end (bit-faithful verification mode)
   // chunk / warm-up lengths by series length (read from the environment once, when the engine is created)
   int flsa_small_n = 262144, flsa_chunk_big = 448, flsa_warm_big = 512, flsa_chunk_small = 64, flsa_warm_small = 768;
+  // route of a series through the forward pass: 0 = by the series itself (short series and series with empty bins take
+  // the scan route, flsa_core.cuh; long dense ones the speculative route), 1 = speculative route only, 2 = scan route only
+  int flsa_route = 0;
+  int flsa_scan_chunk_small = 64, flsa_scan_chunk_big = 448;
   int host_threads = 4;     // host threads of batch_upload's passes over the input columns (run scan, packing of the counts)
   char* stage_host = nullptr;   // page-locked staging area of batch_stage (grown on demand, freed with the engine)
   size_t stage_cap = 0;

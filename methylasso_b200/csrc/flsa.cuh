@@ -55,11 +55,13 @@ class FlsaPlan {
   }
   int n_series() const { return (int)series_.size(); }
   int n_chunks() const { return n_chunks_; }
+  int n_scan_chunks() const { return n_scan_chunks_; }
+  int n_scan_groups() const { return n_scan_groups_; }
   int n_tiles() const { return n_tiles_; }
   int chunk_len() const { return chunk_; }
   int warm_len() const { return warm_; }
   // counters of the last solve (read back with the overflow flags)
-  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0; };
+  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0, scan_chunks = 0; };
   Stats last_stats() const { return stats_; }
 
  private:
@@ -75,6 +77,16 @@ class FlsaPlan {
   DevBuf<int8_t> d_verdict_;        // per chunk: 1 = verified
   DevBuf<int32_t> d_heads_;         // chain heads (chunks the walkers start from)
   SpecWindows win_{};
+  // scan route (flsa_core.cuh): chunk table of its own, groups of chunks, the maps of chunks and groups
+  int n_scan_chunks_ = 0, n_scan_groups_ = 0, n_scan_series_ = 0;
+  int64_t scan_steps_ = 0;
+  DevBuf<ChunkDesc> d_scan_chunks_;
+  DevBuf<ScanGroup> d_scan_groups_;
+  DevBuf<int32_t> d_scan_series_;   // per scan-route series: series index, first group, number of groups
+  DevBuf<int32_t> d_scan_i32_;
+  DevBuf<double> d_scan_f64_;
+  ScanFns scan_chunk_fns_{}, scan_group_fns_{};
+  MsgArray scan_group_start_{};
   DevBuf<TileDesc> d_tiles_;
   DevBuf<int32_t> d_series_tile0_;  // first tile of each series (+1 sentinel)
   DevBuf<double> d_tm_, d_tp_;
@@ -93,6 +105,7 @@ class FlsaPlan {
   std::vector<int32_t> h_flags_, h_skip_;
   int32_t h_counters_[4] = {0, 0, 0, 0};
   void backward();
+  void forward_scan(const double* d_y, const double* d_w, const int32_t* skip);
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);
 };
 

@@ -42,6 +42,7 @@ enum : int32_t {
   SERIES_TRIVIAL = 1,     // n <= 1 or lam == 0: beta = y            (gfl_tf.c:210-215)
   SERIES_SEQUENTIAL = 2,  // lam < 0 / NaN: the sandwich does not apply; one chunk, run start-to-end
 };
+enum : int32_t { ROUTE_SPEC = 0, ROUTE_SCAN = 1 };
 enum : int32_t {
   SPEC_EXACT = 1,      // the run started at the head of its series: exact by construction, nothing to verify
   SPEC_OVERFLOW = 2,   // the window outgrew the speculative ring: S / E are not usable, the chunk is redone by a walker
@@ -57,7 +58,7 @@ struct SeriesDesc {
   int32_t mode;
   double lam;
   int32_t warm;         // warm-up steps in front of each chunk of this series (0: the launch's default)
-  int32_t pad;
+  int32_t route;        // ROUTE_SPEC / ROUTE_SCAN: which forward pass the series takes (first_chunk indexes that route's table)
   int64_t off_in;       // offset of element 0 in the INPUT arrays y / w (== off unless several series share one input: the
                         // lanes of a lambda2 sweep read the same pseudodata)
 };
@@ -66,6 +67,12 @@ struct ChunkDesc {
   int32_t series;
   int32_t kb, ke;  // DP steps [kb, ke) of the series; step k folds element k, 1 <= k <= n-2
   int32_t idx;     // index of the chunk within its series (its parity chooses the bound the speculation starts from)
+};
+// scan route: chunks [c0, c0 + nc) of one series (indices into the scan route's chunk table)
+struct ScanGroup {
+  int32_t series;
+  int32_t c0, nc;
+  int32_t kind;    // bit 0: the first group of its series, bit 1: the last one (its map is never applied to anything)
 };
 
 // The saved windows of all chunks, struct-of-arrays [field][slot][chunk] (consecutive threads = consecutive chunks write
@@ -465,12 +472,394 @@ ML_HD bool flsa_redo_chunk(const SeriesDesc& S, const ChunkDesc& cd, const doubl
                            KnotsC<Ring>& q, bool* irregular) {
   double t1, t2;
   bool zfix = false;
+  double yn = 0.0, wn = 1.0;                       // one element ahead: the load does not wait for the step before it
+  if (cd.kb < cd.ke) { yn = y[cd.kb]; wn = w[cd.kb]; }
   for (int k = cd.kb; k < cd.ke; ++k) {
-    if (!dp_step_z(q, y[k], w[k], S.lam, t1, t2, zfix)) return false;
+    const double yk = yn, wk = wn;
+    if (k + 1 < cd.ke) { yn = y[k + 1]; wn = w[k + 1]; }
+    if (!dp_step_z(q, yk, wk, S.lam, t1, t2, zfix)) return false;
     tm[k] = t1;
     tp[k] = t2;
     if (t1 > t2) *irregular = true;
   }
+  return true;
+}
+
+// ---- a chunk as a map on messages: the SCAN route ------------------------------------------------------------------------
+// At every point b the DP step acts on the message value v = delta(b) as v -> clip(v + w (b - y), -lam, +lam), and a
+// composition of such clamp-shift maps is one again.  For a whole chunk and an incoming value in [-lam, +lam] that gives
+//     delta_out(b) = min( B(b), max( A(b), delta_in(b) + Sw b - Swy ) ),
+// where A and B are the chunk's end messages from the incoming messages "-lam everywhere" and "+lam everywhere" (two runs
+// of the chunk's own steps from the two bounds, no warm-up) and Sw = sum of w, Swy = sum of w y over the chunk.
+// G = delta_in + Sw b - Swy has G - A and G - B non-decreasing in b (A and B have slopes <= Sw), so delta_out is A up to
+// the point b1 where G crosses A, G between b1 and the point b2 where G crosses B, and B beyond: in the knot
+// representation of the windows (delta(b) = -lam + sum over knots left of b of (a b + b_knot)) that is A's knots below b1,
+// one knot at b1 that switches from A's line to G's, delta_in's knots between b1 and b2 (the increments of G are those of
+// delta_in), one knot at b2 that switches to B's line, and B's knots above b2 (pw_compose).  The exact end state of a
+// chunk therefore follows from the exact state in front of it by a MERGE of three short knot lists instead of a re-run of
+// its steps, and the chunk maps themselves compose the same way: (A, B, Sw, Swy) of "chunk 1 then chunk 2" is
+// (chunk 2 applied to A1, chunk 2 applied to B1, Sw1 + Sw2, Swy1 + Swy2).  That makes the forward pass a SCAN:
+//   1. every chunk, from both bounds, on its own steps                                  (flsa_scan_bounds_kernel)
+//   2. the maps of the chunks of a group composed in order, one group per thread pair    (flsa_scan_reduce_kernel)
+//   3. the exact message in front of every group, one thread per series                  (flsa_scan_carry_kernel)
+//   4. the exact message in front of every chunk of a group, one thread per group        (flsa_scan_starts_kernel)
+//   5. every chunk redone from its exact start window: back-pointers, last coefficient   (flsa_scan_redo_kernel)
+// The dependent path is 2 chunk lengths of DP steps plus about 2 sqrt(2 chunks) merges whatever the data - where the
+// speculative route (warm-up, verification, walkers) degenerates into walking a whole series at one thread's pace when
+// the memory of the series is longer than any affordable warm-up (lambda2 = 1000 on the PMD step, the FULL model's bins).
+// On count data with an integer penalty every sum above is exact and the crossings are correctly rounded quotients of
+// the same exact numbers the sequential run divides: the scan reproduces tf_dp_weight bit for bit there
+// (tests/test_emu.py); elsewhere it differs from it in the last bits like any reassociation.
+constexpr int PW_CAP = 32;                // knots a message of the scan route may hold
+struct PwMsg {
+  int n;
+  double x[PW_CAP], a[PW_CAP], b[PW_CAP];
+};
+// false when the window holds more knots than a message may, or a knot that is not at a finite place (the sentinels of a
+// window no element with a weight has touched; the NaN / infinite knots a zero-weight FIRST element leaves behind,
+// gfl_tf.c:231-240 with w = 0): such a series is left to the start-to-end kernel
+template <class K>
+ML_HD bool pw_from_window(const K& q, PwMsg& m) {
+  m.n = 0;
+  if (q.r - q.l + 1 > PW_CAP) return false;
+  for (int i = q.l; i <= q.r; ++i) {
+    const double x = q.ring.x(i);
+    if (!is_finite(x)) return false;
+    m.x[m.n] = x; m.a[m.n] = q.ring.a(i); m.b[m.n] = q.ring.b(i);
+    ++m.n;
+  }
+  return m.n >= 1;
+}
+template <class Ring>
+ML_HD bool pw_to_window(const PwMsg& m, KnotsC<Ring>& q) {
+  if (m.n > Ring::CAP || m.n < 1) return false;
+  for (int i = 0; i < m.n; ++i) q.ring.set(i, m.x[i], m.a[i], m.b[i]);
+  q.l = 0;
+  q.r = m.n - 1;
+  knots_cache(q);
+  return true;
+}
+// messages in global memory, [slot][index] (consecutive indices = consecutive addresses); n < 0 marks a failure
+struct MsgArray {
+  int32_t* n;
+  double *x, *a, *b;
+  int64_t stride;
+};
+ML_HD void pw_save(const PwMsg& m, const MsgArray& M, int64_t i) {
+  for (int k = 0; k < m.n; ++k) {
+    M.x[k * M.stride + i] = m.x[k];
+    M.a[k * M.stride + i] = m.a[k];
+    M.b[k * M.stride + i] = m.b[k];
+  }
+  M.n[i] = m.n;
+}
+ML_HD bool pw_load(const MsgArray& M, int64_t i, PwMsg& m) {
+  const int n = M.n[i];
+  if (n < 1 || n > PW_CAP) { m.n = 0; return false; }
+  for (int k = 0; k < n; ++k) {
+    m.x[k] = M.x[k * M.stride + i];
+    m.a[k] = M.a[k * M.stride + i];
+    m.b[k] = M.b[k * M.stride + i];
+  }
+  m.n = n;
+  return true;
+}
+// the maps of chunks (or of groups of chunks): end messages from the two bounds and the two sums; sw == 0 (no element
+// with a weight) is the identity, its messages are not stored (n == 0)
+struct ScanFns {
+  MsgArray A, B;
+  double *sw, *swy;
+};
+
+// a cursor over a message: the line s b + t that holds just right of the knots consumed so far
+struct PwCursor { int i; double s, t; };
+ML_HD void pw_advance(const PwMsg& m, PwCursor& c) { c.s += m.a[c.i]; c.t += m.b[c.i]; ++c.i; }
+ML_HD double pw_next_x(const PwMsg& m, const PwCursor& c) { return c.i < m.n ? m.x[c.i] : HUGE_VAL; }
+ML_HD bool pw_emit(PwMsg& out, double x, double a, double b) {
+  if (out.n >= PW_CAP) return false;
+  out.x[out.n] = x; out.a[out.n] = a; out.b[out.n] = b;
+  ++out.n;
+  return true;
+}
+// A knot that switches between two lines which are the same line up to the rounding of their sums (G and A coincide
+// wherever neither the incoming message nor A has been clipped yet) carries noise, not a change of line: it is dropped.
+// Never on count data with an integer penalty, where the increments are exact (integers, or exactly zero).
+ML_HD bool pw_emit_switch(PwMsg& out, double x, double a, double b, double scale_a, double scale_b) {
+  const double tiny = 8.0 * 2.220446049250313e-16;
+  if ((a < 0 ? -a : a) <= tiny * scale_a && (b < 0 ? -b : b) <= tiny * scale_b) return true;
+  return pw_emit(out, x, a, b);
+}
+
+// out = the map (A, B, Sw, Swy), Sw > 0, applied to the message `in`.  All three messages regular (pw_from_window).
+// Returns false when out would hold more than PW_CAP knots.
+ML_HD bool pw_compose(const PwMsg& in, const PwMsg& A, const PwMsg& B, double Sw, double Swy, double lam, PwMsg& out) {
+  PwCursor cA{0, 0.0, -lam}, cT{0, 0.0, -lam}, cB{0, 0.0, -lam};
+  out.n = 0;
+  const double sc_a = Sw, sc_b = (Swy < 0 ? -Swy : Swy) + lam;     // magnitudes the sums behind a switch knot were formed at
+  // ---- b1: G - A = (sT + Sw - sA) b + (tT - Swy - tA) first reaches zero --------------------------------------------
+  double b1 = -HUGE_VAL;
+  for (;;) {
+    const double xa = pw_next_x(A, cA), xt = pw_next_x(in, cT);
+    const double hi = xa < xt ? xa : xt;               // the current lines hold up to the next knot of either list
+    const double sl = (cT.s + Sw) - cA.s, ic = (cT.t - Swy) - cA.t;
+    // G overtakes A at the latest on the last piece (G -> +inf there, A <= lam)
+    const bool cross = hi == HUGE_VAL ? true : (sl * hi + ic >= 0);
+    if (cross) {
+      // A has no knot left: it has reached +lam, so has B above it, and G has not caught up with A before: out is A
+      if (cA.i == A.n) return out.n >= 1;
+      double c = sl != 0.0 ? -ic / sl : b1;
+      if (!(c >= b1)) c = b1;                          // numerically before the piece: at its start
+      if (c > hi) c = hi;
+      b1 = c;
+      break;
+    }
+    if (xa <= xt) {                                    // A's knot passes unchanged (out is A below b1)
+      if (!pw_emit(out, A.x[cA.i], A.a[cA.i], A.b[cA.i])) return false;
+      pw_advance(A, cA);
+    } else {
+      pw_advance(in, cT);                              // the incoming message's knots below b1 vanish under A
+    }
+    b1 = hi;
+  }
+  // (the knot at b1, from A's line to G's, is written once b2 is known: when the stretch on which G holds is empty the
+  // two switches collapse into one knot from A's line to B's - or none, where A and B coincide)
+  const double sA = cA.s, tA = cA.t;                   // A's line at b1
+  const double gs1 = (cT.s + Sw) - sA, gt1 = (cT.t - Swy) - tA;
+  // ---- b2: G - B first reaches zero (B's knots up to b1 first) -------------------------------------------------------
+  while (pw_next_x(B, cB) <= b1) pw_advance(B, cB);
+  double b2 = b1;
+  bool between = false;                                // some knot of the incoming message lies on the stretch of G
+  for (;;) {
+    const double xb = pw_next_x(B, cB), xt = pw_next_x(in, cT);
+    const double hi = xb < xt ? xb : xt;
+    const double sl = (cT.s + Sw) - cB.s, ic = (cT.t - Swy) - cB.t;
+    const bool cross = hi == HUGE_VAL ? true : (sl * hi + ic >= 0);
+    if (cross) {
+      if (cB.i == 0) {
+        // B has not left -lam yet where G overtakes it: neither has A below it, and G stays above B from here on: out is B
+        out.n = 0;
+        for (int i = 0; i < B.n; ++i) pw_emit(out, B.x[i], B.a[i], B.b[i]);
+        return out.n >= 1;
+      }
+      double c = sl != 0.0 ? -ic / sl : b2;
+      if (!(c >= b2)) c = b2;
+      if (c > hi) c = hi;
+      b2 = c;
+      break;
+    }
+    if (xt <= xb) {                                    // the incoming message's knot passes unchanged (G's increments are its own)
+      if (!between) {
+        if (!pw_emit_switch(out, b1, gs1, gt1, sc_a, sc_b)) return false;
+        between = true;
+      }
+      if (!pw_emit(out, in.x[cT.i], in.a[cT.i], in.b[cT.i])) return false;
+      pw_advance(in, cT);
+    } else {
+      pw_advance(B, cB);                               // B's knots below b2 lie above G
+    }
+    b2 = hi;
+  }
+  if (!between && b2 == b1) {
+    // empty stretch: straight from A's line to B's
+    if (!pw_emit_switch(out, b1, cB.s - sA, cB.t - tA, sc_a, sc_b)) return false;
+  } else {
+    if (!between && !pw_emit_switch(out, b1, gs1, gt1, sc_a, sc_b)) return false;
+    // the knot at b2: from G's line to B's
+    if (!pw_emit_switch(out, b2, cB.s - (cT.s + Sw), cB.t - (cT.t - Swy), sc_a, sc_b)) return false;
+  }
+  // then the rest of B
+  for (; cB.i < B.n; ++cB.i)
+    if (!pw_emit(out, B.x[cB.i], B.a[cB.i], B.b[cB.i])) return false;
+  return out.n >= 1 && is_finite(b1) && is_finite(b2);
+}
+
+// A series whose first element has no weight does not start from a message of the regular kind: gfl_tf.c:231-240 with
+// w = 0 leaves knots at -inf / +inf, and from the second weightless element on the window is "+lam everywhere" with a NaN
+// knot of zero increments riding along - a fixed point of the weightless step, whose back-pointers are (-inf, NaN).  The
+// scan keeps such a window LITERALLY (so that the steps run on it do what the reference does, bit for bit); as the input
+// of a map it is the upper bound: the map's B, exactly.
+ML_HD bool pw_is_plus_literal(const PwMsg& m) { return m.n >= 1 && m.n <= 2 && m.x[0] == -HUGE_VAL && m.a[0] == 0.0; }
+ML_HD bool pw_is_regular(const PwMsg& m) {
+  if (m.n < 1) return false;
+  for (int i = 0; i < m.n; ++i)
+    if (!is_finite(m.x[i])) return false;
+  return true;
+}
+// res = the map (A, B, sw, swy) of chunk / group i of F applied to *cur (res is cur, tmp, or a message loaded into tmp)
+ML_HD bool pw_apply(const ScanFns& F, int64_t i, double lam, PwMsg*& cur, PwMsg*& tmp, PwMsg& A, PwMsg& B) {
+  const int na = F.A.n[i], nb = F.B.n[i];
+  if (na < 0 || nb < 0) return false;
+  if (na == 0 || nb == 0) return true;                 // identity
+  if (pw_is_plus_literal(*cur)) return pw_load(F.B, i, *cur);
+  if (!pw_load(F.A, i, A) || !pw_load(F.B, i, B)) return false;
+  if (!pw_compose(*cur, A, B, F.sw[i], F.swy[i], lam, *tmp)) return false;
+  PwMsg* t = cur; cur = tmp; tmp = t;
+  return true;
+}
+
+// Step 1, one chunk and one side (sign < 0: from "-lam everywhere", the map's A; sign > 0: its B): the chunk's own steps
+// from the bound, nothing written but the end message; the side sign < 0 also stores the chunk's sums.
+// The FIRST chunk of a series is run from the first element instead (its side sign < 0 only): exact by construction,
+// back-pointers written, and its map is the constant one (A = B = its end window, kept literally).
+template <class Ring>
+ML_HD void scan_bounds(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, int sign, const double* __restrict__ y,
+                       const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp,
+                       double* beta_last, const ScanFns& F, KnotsC<Ring>& q) {
+  double t1, t2;
+  if (cd.idx == 0) {
+    if (sign > 0) return;
+    knots_init_first(q, y[0], w[0], S.lam, t1, t2);    // gfl_tf.c:231-240
+    tm[0] = t1;
+    tp[0] = t2;
+    bool irregular = false;
+    const bool ok = flsa_redo_chunk(S, cd, y, w, tm, tp, q, &irregular);
+    const int cnt = q.r - q.l + 1;
+    PwMsg E;
+    E.n = 0;
+    if (ok && cnt <= PW_CAP) {
+      for (int k = 0; k < cnt; ++k) { E.x[k] = q.ring.x(q.l + k); E.a[k] = q.ring.a(q.l + k); E.b[k] = q.ring.b(q.l + k); }
+      E.n = cnt;
+    }
+    if (E.n > 0 && (pw_is_regular(E) || pw_is_plus_literal(E) || S.n_chunks == 1)) {
+      pw_save(E, F.A, c);
+      pw_save(E, F.B, c);
+      if (S.n_chunks == 1) *beta_last = dp_last(q, y[S.n - 1], w[S.n - 1], S.lam);   // gfl_tf.c:294-302
+    } else {
+      F.A.n[c] = -1;
+      F.B.n[c] = -1;
+    }
+    F.sw[c] = 1.0;                                     // (a constant map is never applied through its sums)
+    F.swy[c] = 0.0;
+    return;
+  }
+  knots_init_bound(q, sign, S.lam);
+  bool pristine = true, zfix = false, ok = true;
+  double sw = 0.0, swy = 0.0;
+  double yn = 0.0, wn = 1.0;                       // one element ahead
+  if (cd.kb < cd.ke) { yn = y[cd.kb]; wn = w[cd.kb]; }
+  for (int k = cd.kb; k < cd.ke && ok; ++k) {
+    const double yk = yn, wk = wn;
+    if (k + 1 < cd.ke) { yn = y[k + 1]; wn = w[k + 1]; }
+    sw += wk;
+    swy += wk * yk;
+    if (pristine) {
+      if (!(wk > 0)) continue;     // a constant message stays what it is under a zero-weight element (flsa_spec_run)
+      pristine = false;
+    }
+    ok = dp_step_z(q, yk, wk, S.lam, t1, t2, zfix);
+  }
+  const MsgArray& M = sign < 0 ? F.A : F.B;
+  if (!ok || !is_finite(sw) || !is_finite(swy)) {
+    M.n[c] = -1;
+  } else if (pristine || !(sw > 0)) {
+    M.n[c] = (pristine && sw == 0.0) ? 0 : -1;       // identity; anything else without a window is not a map we can state
+  } else {
+    const int cnt = q.r - q.l + 1;
+    bool good = cnt <= PW_CAP;
+    for (int k = 0; k < cnt && good; ++k) {
+      const double x = q.ring.x(q.l + k);
+      good = is_finite(x);
+      M.x[k * M.stride + c] = x;
+      M.a[k * M.stride + c] = q.ring.a(q.l + k);
+      M.b[k * M.stride + c] = q.ring.b(q.l + k);
+    }
+    M.n[c] = good ? cnt : -1;
+  }
+  if (sign < 0) { F.sw[c] = sw; F.swy[c] = swy; }
+}
+
+// Step 2, one group and one side: the maps of chunks [c0, c0 + nc) composed in order.  m0 / m1 / A / B are the caller's
+// scratch messages; on return *res points at the side's message of the group's map (n == 0 and *Sw == 0: the identity).
+// In a series' first group the map is the constant one (its first chunk's is): both sides are the group's exact end
+// message, only the side sign < 0 is computed.  Returns false when a chunk failed or a message outgrew PW_CAP.
+ML_HD bool scan_reduce_side(int64_t c0, int nc, int sign, const ScanFns& F, double lam, PwMsg* m0, PwMsg* m1, PwMsg& A,
+                            PwMsg& B, PwMsg** res, double* Sw, double* Swy) {
+  bool pristine = true;
+  double sw_all = 0.0, swy_all = 0.0;
+  PwMsg *cur = m0, *tmp = m1;
+  cur->n = 0;
+  for (int64_t c = c0; c < c0 + nc; ++c) {
+    const int na = F.A.n[c], nb = F.B.n[c];
+    if (na < 0 || nb < 0) return false;
+    if (na == 0 || nb == 0) continue;                  // identity
+    if (pristine) {
+      if (!pw_load(sign < 0 ? F.A : F.B, c, *cur)) return false;
+      pristine = false;
+    } else if (!pw_apply(F, c, lam, cur, tmp, A, B)) {
+      return false;
+    }
+    sw_all += F.sw[c];
+    swy_all += F.swy[c];
+  }
+  *res = cur;
+  *Sw = sw_all;
+  *Swy = swy_all;
+  return true;
+}
+
+// Step 3, one series: the exact message in front of each of its groups [g0 + 1, g0 + ng), written to GT (the first group
+// starts at the head of the series; its map is constant: its A message is the exact state behind it).
+ML_HD bool scan_carry(double lam, int64_t g0, int ng, const ScanFns& G, const MsgArray& GT, PwMsg* m0, PwMsg* m1, PwMsg& A,
+                      PwMsg& B) {
+  if (ng <= 1) return true;
+  PwMsg *cur = m0, *tmp = m1;
+  if (!pw_load(G.A, g0, *cur)) return false;
+  for (int64_t g = g0 + 1; g < g0 + ng; ++g) {
+    pw_save(*cur, GT, g);
+    if (g + 1 == g0 + ng) break;                       // the last group's map is not needed
+    if (!pw_apply(G, g, lam, cur, tmp, A, B)) return false;
+  }
+  return true;
+}
+
+// Step 4, one group: the exact message in front of each of its chunks.  The start message of chunk c takes the place of
+// the chunk's A message (which has been read by then).  `first`: the series' first group - its first chunk needs no
+// start (it was run from the first element), the second one starts from the first one's end window.
+ML_HD bool scan_starts(int64_t g, int64_t c0, int nc, bool first, const ScanFns& F, const MsgArray& GT, double lam, PwMsg* m0,
+                       PwMsg* m1, PwMsg& A, PwMsg& B) {
+  PwMsg *cur = m0, *tmp = m1;
+  int64_t c = c0;
+  if (first) {
+    if (nc <= 1) return F.A.n[c0] >= 1;
+    if (!pw_load(F.A, c0, *cur)) return false;
+    c = c0 + 1;
+  } else if (!pw_load(GT, g, *cur)) {
+    return false;
+  }
+  for (; c < c0 + nc; ++c) {
+    const int na = F.A.n[c], nb = F.B.n[c];
+    if (na < 0 || nb < 0) return false;
+    const bool last = c + 1 == c0 + nc;
+    if (last || na == 0 || nb == 0) { pw_save(*cur, F.A, c); continue; }
+    if (pw_is_plus_literal(*cur)) {
+      pw_save(*cur, F.A, c);
+      if (!pw_load(F.B, c, *cur)) return false;
+      continue;
+    }
+    if (!pw_load(F.A, c, A) || !pw_load(F.B, c, B)) return false;
+    pw_save(*cur, F.A, c);
+    if (!pw_compose(*cur, A, B, F.sw[c], F.swy[c], lam, *tmp)) return false;
+    PwMsg* t = cur; cur = tmp; tmp = t;
+  }
+  return true;
+}
+
+// Step 5, one chunk but a series' first: redone from its exact start window (stored by step 4 in the place of the chunk's
+// A message); the series' last chunk also yields the last coefficient.  Returns false on a missing start or ring overflow.
+template <class Ring>
+ML_HD bool scan_redo(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, const double* __restrict__ y,
+                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp, const MsgArray& T,
+                     KnotsC<Ring>& q, double* beta_last) {
+  const int n = T.n[c];
+  if (n < 1 || n > Ring::CAP) return false;
+  if (cd.idx == 0) return true;
+  for (int k = 0; k < n; ++k) q.ring.set(k, T.x[k * T.stride + c], T.a[k * T.stride + c], T.b[k * T.stride + c]);
+  q.l = 0;
+  q.r = n - 1;
+  knots_cache(q);
+  bool irregular = false;
+  if (!flsa_redo_chunk(S, cd, y, w, tm, tp, q, &irregular)) return false;
+  if (cd.idx == S.n_chunks - 1) *beta_last = dp_last(q, y[S.n - 1], w[S.n - 1], S.lam);   // gfl_tf.c:294-302
   return true;
 }
 

@@ -104,6 +104,85 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   return 0;
 }
 
+// The scan route (flsa_core.cuh, "a chunk as a map on messages"): the five steps exactly as the kernels of flsa.cu run
+// them, one loop iteration per device thread.  stats: [0] chunks, [1] groups, [4] failed (left to the start-to-end run),
+// [5] largest message saved.
+extern "C" int emu_flsa_scan(int n, const double* y, const double* w, double lam, int chunk, int group,
+                             double* beta, double* tm, double* tp, int tile, long long* stats) {
+  for (int i = 0; i < 8; ++i) stats[i] = 0;
+  if (n == 0) return 0;
+  if (n == 1 || lam == 0) { for (int i = 0; i < n; ++i) beta[i] = y[i]; return 0; }
+  if (!(lam > 0)) return -2;
+  SeriesDesc S{0, n, 0, 0, SERIES_NORMAL, lam};
+  std::vector<ChunkDesc> cd;
+  const int steps_lo = 1, steps_hi = n - 1;
+  for (int k = steps_lo; k < steps_hi || cd.empty(); k += chunk) {
+    cd.push_back(ChunkDesc{0, k, std::min(k + chunk, std::max(steps_hi, steps_lo)), (int)cd.size()});
+    if (steps_hi <= steps_lo) break;
+  }
+  const int64_t nc = (int64_t)cd.size();
+  S.n_chunks = (int)nc;
+  const int64_t ng = (nc + group - 1) / group;
+  stats[0] = nc;
+  stats[1] = ng;
+  auto make = [](std::vector<int32_t>& cnt, std::vector<double>& v, int64_t m) {
+    cnt.assign(m, -7);
+    v.assign(3 * (size_t)PW_CAP * m, 0.0);
+    return MsgArray{cnt.data(), v.data(), v.data() + PW_CAP * m, v.data() + 2 * PW_CAP * m, m};
+  };
+  std::vector<int32_t> nA, nB, nGA, nGB, nGT;
+  std::vector<double> vA, vB, vGA, vGB, vGT, sw(nc), swy(nc), gsw(ng), gswy(ng);
+  ScanFns F{make(nA, vA, nc), make(nB, vB, nc), sw.data(), swy.data()};
+  ScanFns G{make(nGA, vGA, ng), make(nGB, vGB, ng), gsw.data(), gswy.data()};
+  MsgArray GT = make(nGT, vGT, ng);
+  typedef LocalRing<PW_CAP> RunRing;
+  bool fail = false;
+  double blast = 0.0;
+  // 1: bounds (the first chunk: exact from the first element)
+  for (int64_t c = 0; c < nc; ++c)
+    for (int sign = -1; sign <= 1; sign += 2) {
+      KnotsC<RunRing> q;
+      scan_bounds(S, cd[c], c, sign, y, w, tm, tp, &blast, F, q);
+    }
+  // 2: group maps
+  PwMsg m0, m1, A, B;
+  for (int64_t g = 0; g < ng; ++g)
+    for (int sign = -1; sign <= 1; sign += 2) {
+      const MsgArray& M = sign < 0 ? G.A : G.B;
+      if (g == ng - 1 || (g == 0 && sign > 0)) { M.n[g] = 0; if (sign < 0) { G.sw[g] = 0; G.swy[g] = 0; } continue; }
+      PwMsg* res = nullptr;
+      double Sw = 0, Swy = 0;
+      const int64_t c0 = g * group;
+      const int cnt = (int)std::min<int64_t>(group, nc - c0);
+      if (!scan_reduce_side(c0, cnt, sign, F, lam, &m0, &m1, A, B, &res, &Sw, &Swy)) { M.n[g] = -1; continue; }
+      if (res->n > 0) pw_save(*res, M, g); else M.n[g] = 0;
+      if (sign < 0) { G.sw[g] = Sw; G.swy[g] = Swy; }
+    }
+  // 3: carry
+  fail = !scan_carry(lam, 0, (int)ng, G, GT, &m0, &m1, A, B);
+  // 4: starts
+  for (int64_t g = 0; g < ng && !fail; ++g) {
+    const int64_t c0 = g * group;
+    fail = !scan_starts(g, c0, (int)std::min<int64_t>(group, nc - c0), g == 0, F, GT, lam, &m0, &m1, A, B);
+  }
+  // 5: redo
+  for (int64_t c = 0; c < nc && !fail; ++c) {
+    KnotsC<RunRing> q;
+    stats[5] = std::max<long long>(stats[5], F.A.n[c]);
+    double bl = 0.0;
+    fail = !scan_redo(S, cd[c], c, y, w, tm, tp, F.A, q, &bl);
+    if (c == nc - 1 && c > 0) blast = bl;
+  }
+  if (fail) {
+    stats[4] = 1;
+    std::vector<double> scratch(3 * (size_t)flsa_sequential_cap(n));
+    flsa_sequential_forward(n, y, w, lam, scratch.data(), tm, tp, &blast);
+  }
+  flsa_sequential_backward(n, tm, tp, blast, beta);
+  (void)tile;
+  return 0;
+}
+
 #include "../../methylasso_b200/csrc/irls_core.cuh"
 extern "C" void emu_even_bin(int n, const double* v, double lower, double size, unsigned nbins, unsigned* out) {
   for (int i = 0; i < n; ++i) out[i] = ml::even_bin(v[i], lower, size, nbins);

@@ -35,7 +35,18 @@ def emu():
         rc = L.emu_flsa(n, p(y), p(w), C.c_double(lam), chunk, warm, p(beta), p(tm), p(tp), tile, p(st))
         assert rc == 0
         return beta, st
+    def scan(y, w, lam, chunk=64, group=8):
+        """the scan route (flsa_core.cuh): the five steps of flsa.cu's scan kernels, thread by thread"""
+        y, w = np.ascontiguousarray(y, float), np.ascontiguousarray(w, float)
+        n = y.size
+        beta, tm, tp = np.zeros(n), np.zeros(n + 1), np.zeros(n + 1)
+        st = np.zeros(8, np.int64)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = L.emu_flsa_scan(n, p(y), p(w), C.c_double(lam), chunk, group, p(beta), p(tm), p(tp), 2048, p(st))
+        assert rc == 0
+        return beta, st
     run.lib = L
+    run.scan = scan
     return run
 
 
@@ -81,6 +92,59 @@ def test_chunked_dp_generic_inputs_within_rounding(emu, oracle):
         if ok.any():
             worst = max(worst, np.max(np.abs(beta[ok] - ref[ok])) / scale)
     assert worst < 1e-11, worst
+
+
+@pytest.mark.parametrize("reps", [(1,), (3,)])
+def test_scan_route_bit_exact_on_count_data(emu, oracle, reps):
+    """Chunks as maps on messages, composed by merges of knot lists: on count data with an integer penalty every sum is
+    exact and every crossing the correctly rounded quotient of the numbers the sequential run divides - the same bits,
+    whatever the chunk and group lengths.  A fractional penalty re-associates sums like the speculative route does."""
+    t = synth.chromosome_table(120_000, 31, reps)
+    y, w = pooled_series(t)
+    for lam in (10.0, 25.0, 1000.0):
+        ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+        for chunk, group in ((64, 16), (448, 12), (7, 3)):
+            beta, st = emu.scan(y, w, lam, chunk, group)
+            assert st[4] == 0, (lam, chunk, group)          # no fallback on WGBS-like data
+            assert np.array_equal(beta, ref), (lam, chunk, group)
+    ref, _, _ = oracle.tf_dp_weight(y, w, 17.3, "port")
+    beta, st = emu.scan(y, w, 17.3, 64, 16)
+    assert st[4] == 0 and np.max(np.abs(beta - ref)) < 1e-11
+
+
+def test_scan_route_generic_inputs_within_rounding(emu, oracle):
+    """Real-valued data, zero weights inside the series and AT ITS HEAD (the reference's first-element formulas with
+    w = 0 leave knots at infinity and then a NaN knot: the scan keeps that window literally), every chunk / group length;
+    monotone series outgrow a message's capacity and are finished start to end."""
+    rng = np.random.default_rng(0)
+    worst, fallbacks, zero_heads = 0.0, 0, 0
+    for trial in range(500):
+        n = int(rng.integers(2, 500))
+        kind = trial % 5
+        if kind == 0:
+            y, w = rng.random(n), rng.integers(0, 3, n).astype(float)
+        elif kind == 1:
+            y, w = np.sort(rng.random(n)), rng.random(n)
+        elif kind == 2:
+            y, w = np.repeat(rng.random(n // 7 + 1), 7)[:n], rng.integers(0, 50, n).astype(float)
+        elif kind == 3:
+            y = rng.integers(0, 2, n).astype(float)
+            w = np.where(rng.random(n) < 0.8, 0.0, rng.integers(1, 30, n)).astype(float)
+        else:
+            y, w = rng.normal(size=n), rng.exponential(size=n)
+        lam = float(rng.choice([1e-3, 0.1, 0.5, 5.0, 25.0, 1000.0]))
+        ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+        beta, st = emu.scan(y, w, lam, int(rng.choice([1, 2, 4, 16, 64])), int(rng.choice([1, 2, 3, 8])))
+        if kind != 1:
+            assert st[4] == 0, (trial, kind)
+            zero_heads += int(w[0] == 0)
+        fallbacks += int(st[4])
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(beta), ok), (trial, kind)
+        if ok.any():
+            worst = max(worst, np.max(np.abs(beta[ok] - ref[ok])) / max(1.0, np.max(np.abs(ref[ok]))))
+    assert worst < 1e-11, worst
+    assert zero_heads > 50 and 0 < fallbacks < 100
 
 
 def test_side_symmetric_step_is_bit_exact_on_any_input(emu, oracle):

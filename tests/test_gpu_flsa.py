@@ -57,6 +57,49 @@ def test_count_data_bit_exact(engine, oracle, reps):
         assert np.array_equal(got, ref), lam
 
 
+def test_routes_on_count_data_bit_exact(engine, oracle):
+    """Both forward passes on the same series: the speculative route forced onto a short series and the scan route
+    (chunks as maps on messages, flsa_core.cuh) forced onto a long one.  Count data, integer penalties: bit-equal to the
+    reference's verbatim DP either way; a fractional penalty within rounding."""
+    t = synth.chromosome_table(400_000, 20241, (3,))
+    y, w = pooled_series(t)
+    ys, ws = y[:150_000], w[:150_000]
+    try:
+        for route, (yy, ww) in ((2, (y, w)), (1, (ys, ws)), (0, (ys, ws))):
+            engine.set("flsa_route", route)
+            for lam in (25.0, 1000.0):
+                assert np.array_equal(engine.weighted_1d_flsa(yy, ww, lam), oracle.weighted_1d_flsa(yy, ww, lam)), (route, lam)
+            got, ref = engine.weighted_1d_flsa(yy, ww, 17.3), oracle.weighted_1d_flsa(yy, ww, 17.3)
+            assert float(np.max(np.abs(got - ref))) < 1e-10, route
+    finally:
+        engine.set("flsa_route", 0)
+
+
+def test_scan_route_on_pmd_like_series(engine, oracle):
+    """The PMD step's shape (R/call.R:93): a few 10^4 real-valued standard deviations weighted by segment widths, lambda2 =
+    1000 - the series whose memory no warm-up covers.  Scan route (the default for short series) against the verbatim DP:
+    per element to 1e-12 of the scale, whatever the chunk length; with zero weights at the head and inside."""
+    rng = np.random.default_rng(77)
+    n = 60_000
+    y = np.abs(rng.normal(0.15, 0.08, n)) * (1 + (np.arange(n) // 7000) % 2)
+    w = np.round(rng.lognormal(5.5, 1.0, n))
+    ref = oracle.weighted_1d_flsa(y, w, 1000.0)
+    try:
+        for chunk in (0, 32, 448):
+            engine.set("flsa_chunk", chunk)
+            got = engine.weighted_1d_flsa(y, w, 1000.0)
+            assert np.all(np.abs(got - ref) <= 1e-12 * max(1.0, float(np.max(np.abs(ref))))), chunk
+    finally:
+        engine.set("flsa_chunk", 0)
+    w2 = w.copy()
+    w2[:3] = 0.0
+    w2[rng.random(n) < 0.7] = 0.0
+    got, ref = engine.weighted_1d_flsa(y, w2, 1000.0), oracle.weighted_1d_flsa(y, w2, 1000.0)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), ok)
+    assert np.all(np.abs(got[ok] - ref[ok]) <= 1e-12 * max(1.0, float(np.max(np.abs(ref[ok])))))
+
+
 def test_generic_inputs_and_ragged_batch(engine, oracle):
     rng = np.random.default_rng(0)
     ys, ws, lams, ptr = [], [], [], [0]
