@@ -685,14 +685,31 @@ ML_HD bool pw_is_regular(const PwMsg& m) {
     if (!is_finite(m.x[i])) return false;
   return true;
 }
-// res = the map (A, B, sw, swy) of chunk / group i of F applied to *cur (res is cur, tmp, or a message loaded into tmp)
-ML_HD bool pw_apply(const ScanFns& F, int64_t i, double lam, PwMsg*& cur, PwMsg*& tmp, PwMsg& A, PwMsg& B) {
+// The drivers of steps 2-4 below are written for a TEAM: on the device a warp whose lanes move the messages between global
+// and shared memory together (one knot per lane, one round trip per message instead of one per knot) while its leader
+// does the merging; on the CPU (tests/emu) a team of one.  Control flow is uniform across the team: every decision is
+// taken on values all members see (counts in global memory, messages in memory shared by the team).
+struct SerialTeam {
+  ML_HD bool leader() const { return true; }
+  ML_HD bool all(bool leaders_verdict) const { return leaders_verdict; }
+  ML_HD void sync() const {}
+  ML_HD bool load(const MsgArray& M, int64_t i, PwMsg& m) const { return pw_load(M, i, m); }
+  ML_HD void save(const PwMsg& m, const MsgArray& M, int64_t i) const { pw_save(m, M, i); }
+};
+// *cur = the map (A, B, sw, swy) of chunk / group i of F applied to *cur (tmp, A, B: scratch messages of the team)
+template <class Team>
+ML_HD bool pw_apply(const Team& team, const ScanFns& F, int64_t i, double lam, PwMsg*& cur, PwMsg*& tmp, PwMsg& A, PwMsg& B) {
   const int na = F.A.n[i], nb = F.B.n[i];
   if (na < 0 || nb < 0) return false;
   if (na == 0 || nb == 0) return true;                 // identity
-  if (pw_is_plus_literal(*cur)) return pw_load(F.B, i, *cur);
-  if (!pw_load(F.A, i, A) || !pw_load(F.B, i, B)) return false;
-  if (!pw_compose(*cur, A, B, F.sw[i], F.swy[i], lam, *tmp)) return false;
+  if (pw_is_plus_literal(*cur)) return team.load(F.B, i, *cur);
+  if (!team.load(F.A, i, A) || !team.load(F.B, i, B)) return false;
+  const double sw = F.sw[i], swy = F.swy[i];
+  bool ok = false;
+  if (team.leader()) ok = pw_compose(*cur, A, B, sw, swy, lam, *tmp);
+  ok = team.all(ok);
+  team.sync();
+  if (!ok) return false;
   PwMsg* t = cur; cur = tmp; tmp = t;
   return true;
 }
@@ -772,20 +789,22 @@ ML_HD void scan_bounds(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, int 
 // scratch messages; on return *res points at the side's message of the group's map (n == 0 and *Sw == 0: the identity).
 // In a series' first group the map is the constant one (its first chunk's is): both sides are the group's exact end
 // message, only the side sign < 0 is computed.  Returns false when a chunk failed or a message outgrew PW_CAP.
-ML_HD bool scan_reduce_side(int64_t c0, int nc, int sign, const ScanFns& F, double lam, PwMsg* m0, PwMsg* m1, PwMsg& A,
-                            PwMsg& B, PwMsg** res, double* Sw, double* Swy) {
+template <class Team>
+ML_HD bool scan_reduce_side(const Team& team, int64_t c0, int nc, int sign, const ScanFns& F, double lam, PwMsg* m0, PwMsg* m1,
+                            PwMsg& A, PwMsg& B, PwMsg** res, double* Sw, double* Swy) {
   bool pristine = true;
   double sw_all = 0.0, swy_all = 0.0;
   PwMsg *cur = m0, *tmp = m1;
-  cur->n = 0;
+  if (team.leader()) cur->n = 0;
+  team.sync();
   for (int64_t c = c0; c < c0 + nc; ++c) {
     const int na = F.A.n[c], nb = F.B.n[c];
     if (na < 0 || nb < 0) return false;
     if (na == 0 || nb == 0) continue;                  // identity
     if (pristine) {
-      if (!pw_load(sign < 0 ? F.A : F.B, c, *cur)) return false;
+      if (!team.load(sign < 0 ? F.A : F.B, c, *cur)) return false;
       pristine = false;
-    } else if (!pw_apply(F, c, lam, cur, tmp, A, B)) {
+    } else if (!pw_apply(team, F, c, lam, cur, tmp, A, B)) {
       return false;
     }
     sw_all += F.sw[c];
@@ -799,15 +818,16 @@ ML_HD bool scan_reduce_side(int64_t c0, int nc, int sign, const ScanFns& F, doub
 
 // Step 3, one series: the exact message in front of each of its groups [g0 + 1, g0 + ng), written to GT (the first group
 // starts at the head of the series; its map is constant: its A message is the exact state behind it).
-ML_HD bool scan_carry(double lam, int64_t g0, int ng, const ScanFns& G, const MsgArray& GT, PwMsg* m0, PwMsg* m1, PwMsg& A,
-                      PwMsg& B) {
+template <class Team>
+ML_HD bool scan_carry(const Team& team, double lam, int64_t g0, int ng, const ScanFns& G, const MsgArray& GT, PwMsg* m0,
+                      PwMsg* m1, PwMsg& A, PwMsg& B) {
   if (ng <= 1) return true;
   PwMsg *cur = m0, *tmp = m1;
-  if (!pw_load(G.A, g0, *cur)) return false;
+  if (!team.load(G.A, g0, *cur)) return false;
   for (int64_t g = g0 + 1; g < g0 + ng; ++g) {
-    pw_save(*cur, GT, g);
+    team.save(*cur, GT, g);
     if (g + 1 == g0 + ng) break;                       // the last group's map is not needed
-    if (!pw_apply(G, g, lam, cur, tmp, A, B)) return false;
+    if (!pw_apply(team, G, g, lam, cur, tmp, A, B)) return false;
   }
   return true;
 }
@@ -815,30 +835,36 @@ ML_HD bool scan_carry(double lam, int64_t g0, int ng, const ScanFns& G, const Ms
 // Step 4, one group: the exact message in front of each of its chunks.  The start message of chunk c takes the place of
 // the chunk's A message (which has been read by then).  `first`: the series' first group - its first chunk needs no
 // start (it was run from the first element), the second one starts from the first one's end window.
-ML_HD bool scan_starts(int64_t g, int64_t c0, int nc, bool first, const ScanFns& F, const MsgArray& GT, double lam, PwMsg* m0,
-                       PwMsg* m1, PwMsg& A, PwMsg& B) {
+template <class Team>
+ML_HD bool scan_starts(const Team& team, int64_t g, int64_t c0, int nc, bool first, const ScanFns& F, const MsgArray& GT,
+                       double lam, PwMsg* m0, PwMsg* m1, PwMsg& A, PwMsg& B) {
   PwMsg *cur = m0, *tmp = m1;
   int64_t c = c0;
   if (first) {
     if (nc <= 1) return F.A.n[c0] >= 1;
-    if (!pw_load(F.A, c0, *cur)) return false;
+    if (!team.load(F.A, c0, *cur)) return false;
     c = c0 + 1;
-  } else if (!pw_load(GT, g, *cur)) {
+  } else if (!team.load(GT, g, *cur)) {
     return false;
   }
   for (; c < c0 + nc; ++c) {
     const int na = F.A.n[c], nb = F.B.n[c];
     if (na < 0 || nb < 0) return false;
     const bool last = c + 1 == c0 + nc;
-    if (last || na == 0 || nb == 0) { pw_save(*cur, F.A, c); continue; }
+    if (last || na == 0 || nb == 0) { team.save(*cur, F.A, c); continue; }
     if (pw_is_plus_literal(*cur)) {
-      pw_save(*cur, F.A, c);
-      if (!pw_load(F.B, c, *cur)) return false;
+      team.save(*cur, F.A, c);
+      if (!team.load(F.B, c, *cur)) return false;
       continue;
     }
-    if (!pw_load(F.A, c, A) || !pw_load(F.B, c, B)) return false;
-    pw_save(*cur, F.A, c);
-    if (!pw_compose(*cur, A, B, F.sw[c], F.swy[c], lam, *tmp)) return false;
+    if (!team.load(F.A, c, A) || !team.load(F.B, c, B)) return false;
+    team.save(*cur, F.A, c);
+    const double sw = F.sw[c], swy = F.swy[c];
+    bool ok = false;
+    if (team.leader()) ok = pw_compose(*cur, A, B, sw, swy, lam, *tmp);
+    ok = team.all(ok);
+    team.sync();
+    if (!ok) return false;
     PwMsg* t = cur; cur = tmp; tmp = t;
   }
   return true;
@@ -853,7 +879,19 @@ ML_HD bool scan_redo(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, const 
   const int n = T.n[c];
   if (n < 1 || n > Ring::CAP) return false;
   if (cd.idx == 0) return true;
-  for (int k = 0; k < n; ++k) q.ring.set(k, T.x[k * T.stride + c], T.a[k * T.stride + c], T.b[k * T.stride + c]);
+  for (int k0 = 0; k0 < n; k0 += 4) {                  // four knots' loads in flight before the first of them is stored
+    double xs[4], as[4], bs[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u < n) { xs[u] = T.x[(k0 + u) * T.stride + c]; as[u] = T.a[(k0 + u) * T.stride + c]; bs[u] = T.b[(k0 + u) * T.stride + c]; }
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int u = 0; u < 4; ++u)
+      if (k0 + u < n) q.ring.set(k0 + u, xs[u], as[u], bs[u]);
+  }
   q.l = 0;
   q.r = n - 1;
   knots_cache(q);

@@ -154,16 +154,16 @@ extern "C" int emu_flsa_scan(int n, const double* y, const double* w, double lam
       double Sw = 0, Swy = 0;
       const int64_t c0 = g * group;
       const int cnt = (int)std::min<int64_t>(group, nc - c0);
-      if (!scan_reduce_side(c0, cnt, sign, F, lam, &m0, &m1, A, B, &res, &Sw, &Swy)) { M.n[g] = -1; continue; }
+      if (!scan_reduce_side(SerialTeam(), c0, cnt, sign, F, lam, &m0, &m1, A, B, &res, &Sw, &Swy)) { M.n[g] = -1; continue; }
       if (res->n > 0) pw_save(*res, M, g); else M.n[g] = 0;
       if (sign < 0) { G.sw[g] = Sw; G.swy[g] = Swy; }
     }
   // 3: carry
-  fail = !scan_carry(lam, 0, (int)ng, G, GT, &m0, &m1, A, B);
+  fail = !scan_carry(SerialTeam(), lam, 0, (int)ng, G, GT, &m0, &m1, A, B);
   // 4: starts
   for (int64_t g = 0; g < ng && !fail; ++g) {
     const int64_t c0 = g * group;
-    fail = !scan_starts(g, c0, (int)std::min<int64_t>(group, nc - c0), g == 0, F, GT, lam, &m0, &m1, A, B);
+    fail = !scan_starts(SerialTeam(), g, c0, (int)std::min<int64_t>(group, nc - c0), g == 0, F, GT, lam, &m0, &m1, A, B);
   }
   // 5: redo
   for (int64_t c = 0; c < nc && !fail; ++c) {
