@@ -119,6 +119,12 @@ ML_API int ml_engine_profile_get(ml_engine *eng, int i, char *name, int name_cap
  * completed x 32 B, warm-up steps x 16 B); -1 when the kernel's traffic follows from the batch shape alone. */
 ML_API int ml_engine_profile_work(ml_engine *eng, int i, double *bytes);
 ML_API int ml_engine_profile_reset(ml_engine *eng);
+/* Timeline of the profiled launches since the last reset (enable with ml_engine_set(eng, "profile_timeline", 1) next to
+ * "profile"): start / end of each launch in ms on the clock of one event of the process, so that the engines of a pool
+ * can be laid side by side.  With names == NULL returns the number of spans; else fills up to `count` spans from
+ * `first` (names: count x name_cap bytes) and returns how many. */
+ML_API int ml_engine_profile_spans(ml_engine *eng, int first, int count, char *names, int name_cap, float *t0_ms,
+                                   float *t1_ms);
 
 /* Page-locked host memory for large outputs that a caller fills again and again: a download into pageable memory goes
  * through the driver's bounce buffers at a fraction of the PCIe rate.  Allocate ONCE and reuse - page-locking costs

@@ -77,6 +77,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_longlong)]),
     "ml_engine_profile_work": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double)]),
     "ml_engine_profile_reset": (C.c_int, [_P]),
+    "ml_engine_profile_spans": (C.c_int, [_P, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "ml_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(_P)]),
     "ml_host_free": (None, [_P]),
     "ml_weighted_1d_flsa": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, C.c_double, _P]),

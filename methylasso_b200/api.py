@@ -155,6 +155,18 @@ class Engine:
     def profile_reset(self):
         self._check(self.lib.ml_engine_profile_reset(self.h))
 
+    def profile_spans(self):
+        """[(kernel name, start ms, end ms)] of the profiled launches since the last reset, on the process-wide clock
+        (set("profile_timeline", 1) next to set("profile", 1))."""
+        n = self.lib.ml_engine_profile_spans(self.h, 0, 0, None, 0, None, None)
+        if n <= 0:
+            return []
+        names = C.create_string_buffer(n * 48)
+        t0, t1 = (C.c_float * n)(), (C.c_float * n)()
+        k = self.lib.ml_engine_profile_spans(self.h, 0, n, names, 48, t0, t1)
+        raw = names.raw
+        return [(raw[i * 48:(i + 1) * 48].split(b"\0", 1)[0].decode(), float(t0[i]), float(t1[i])) for i in range(k)]
+
     def segment_call_table(self, pooled, seg, max_distance=500.0):
         """R/call.R:43-68 from host tables: pooled = dict(estimate_id, pos, Nmeth, coverage) per position and
         condition sorted by (estimate_id, pos); seg = the table of segment_methylation_helper."""

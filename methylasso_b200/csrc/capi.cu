@@ -5,6 +5,7 @@
 #include <cstring>
 #include <iterator>
 #include <memory>
+#include <mutex>
 #include <string>
 
 #include "../../include/methylasso_b200.h"
@@ -216,6 +217,21 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   else if (k == "host_threads") eng->e.host_threads = (int)std::max<long long>(1, value);
   else if (k == "want_mu") eng->e.want_mu = value != 0;
   else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }
+  else if (k == "profile_timeline") {
+    // keep the start / end of every profiled launch on the clock of one event of the process (all engines share it)
+    ML_TRY
+    static cudaEvent_t origin = nullptr;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    if (value && !origin) {
+      ML_CUDA(cudaEventCreate(&origin));
+      ML_CUDA(cudaEventRecord(origin, eng->e.stream));
+      ML_CUDA(cudaEventSynchronize(origin));
+    }
+    eng->e.prof.collect();
+    eng->e.prof.origin = value ? origin : nullptr;
+    ML_CATCH
+  }
   else if (k == "profile_reserve_events") {
     // pre-create timing events so that a profiled region does not call cudaEventCreate
     ML_TRY
@@ -302,6 +318,21 @@ int ml_engine_profile_work(ml_engine* eng, int i, double* bytes) {
   auto w = eng->e.prof.work.find(it->first);
   *bytes = w == eng->e.prof.work.end() ? -1.0 : w->second;
   return ML_OK;
+}
+int ml_engine_profile_spans(ml_engine* eng, int first, int count, char* names, int name_cap, float* t0_ms, float* t1_ms) {
+  if (!eng) return 0;
+  try { eng->e.prof.collect(); } catch (...) { return 0; }
+  const int n = (int)eng->e.prof.spans.size();
+  if (!names || !t0_ms || !t1_ms) return n;
+  int k = 0;
+  for (int i = first; i < n && k < count; ++i, ++k) {
+    const Profiler::Span& sp = eng->e.prof.spans[i];
+    strncpy(names + (size_t)k * name_cap, sp.name, name_cap - 1);
+    names[(size_t)k * name_cap + name_cap - 1] = 0;
+    t0_ms[k] = sp.t0;
+    t1_ms[k] = sp.t1;
+  }
+  return k;
 }
 int ml_engine_profile_reset(ml_engine* eng) {
   if (!eng) return fail(ML_ERR_BAD_ARGUMENT, "NULL engine");

@@ -36,6 +36,11 @@ struct Profiler {
   std::vector<cudaEvent_t> pool;
   std::map<std::string, std::pair<double, long long>> acc;  // name -> (total ms, launches)
   std::map<std::string, double> work;   // name -> algorithmic bytes moved, for kernels whose work is data-dependent
+  // optional timeline: start / end of every launch relative to `origin` (an event of the process, so that the engines
+  // of a pool share one clock)
+  struct Span { const char* name; float t0, t1; };
+  cudaEvent_t origin = nullptr;
+  std::vector<Span> spans;
   void add_work(const char* name, double bytes) { if (on) work[name] += bytes; }
   cudaEvent_t get() {
     if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
@@ -61,12 +66,17 @@ struct Profiler {
       auto& a = acc[r.name];
       a.first += ms;
       a.second += 1;
+      if (origin) {
+        float t0 = 0;
+        ML_CUDA(cudaEventElapsedTime(&t0, origin, r.a));
+        spans.push_back(Span{r.name, t0, t0 + ms});
+      }
       pool.push_back(r.a);
       pool.push_back(r.b);
     }
     pending.clear();
   }
-  void reset() { collect(); acc.clear(); work.clear(); }
+  void reset() { collect(); acc.clear(); work.clear(); spans.clear(); }
   ~Profiler() { for (cudaEvent_t e : pool) cudaEventDestroy(e); }
 };
 
