@@ -183,6 +183,7 @@ int ml_engine_create(int device, ml_engine** out) {
   env_int("ML_FLSA_CHUNK_SMALL", h->e.flsa_chunk_small);
   env_int("ML_FLSA_WARM_SMALL", h->e.flsa_warm_small);
   env_int("ML_FLSA_ROUTE", h->e.flsa_route);
+  env_int("ML_FLSA_SCAN_LAMBDA", h->e.flsa_scan_lambda);
   env_int("ML_FLSA_SCAN_CHUNK_SMALL", h->e.flsa_scan_chunk_small);
   env_int("ML_FLSA_SCAN_CHUNK_BIG", h->e.flsa_scan_chunk_big);
   env_int("ML_HOST_THREADS", h->e.host_threads);
@@ -212,11 +213,30 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   else if (k == "flsa_warm") eng->e.flsa_warm = (int)value;
   else if (k == "flsa_sequential") eng->e.flsa_sequential = (int)value;
   else if (k == "flsa_route") eng->e.flsa_route = (int)value;
+  else if (k == "flsa_scan_lambda") eng->e.flsa_scan_lambda = (int)value;
   else if (k == "flsa_scan_chunk_small") eng->e.flsa_scan_chunk_small = (int)std::max<long long>(1, value);
   else if (k == "flsa_scan_chunk_big") eng->e.flsa_scan_chunk_big = (int)std::max<long long>(1, value);
   else if (k == "host_threads") eng->e.host_threads = (int)std::max<long long>(1, value);
   else if (k == "want_mu") eng->e.want_mu = value != 0;
   else if (k == "profile") { if (!value) eng->e.prof.collect(); eng->e.prof.on = value != 0; }
+  else if (k == "stream_priority") {
+    // Re-create the engine's own stream at priority level `value` (0 = the lowest, as created; larger = served first
+    // when kernels of several streams wait for SMs; clamped to what the device offers).  For the engines of a pool whose
+    // groups enter one after the other: the group that enters last is the one everybody waits for.  Only right after
+    // the engine was created (nothing allocated or in flight on the stream yet).
+    ML_TRY
+    if (!eng->e.own_stream) throw MlError(ML_ERR_BAD_ARGUMENT, "stream_priority: the engine runs on a caller's stream");
+    ML_CUDA(cudaSetDevice(eng->e.device));
+    int least = 0, greatest = 0;
+    ML_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));    // numerically lower = higher priority
+    const int pr = (int)std::max<long long>(greatest, least - std::max<long long>(0, value));
+    ML_CUDA(cudaStreamSynchronize(eng->e.stream));
+    cudaStream_t fresh = nullptr;
+    ML_CUDA(cudaStreamCreateWithPriority(&fresh, cudaStreamNonBlocking, pr));
+    ML_CUDA(cudaStreamDestroy(eng->e.stream));
+    eng->e.stream = fresh;
+    ML_CATCH
+  }
   else if (k == "profile_timeline") {
     // keep the start / end of every profiled launch on the clock of one event of the process (all engines share it)
     ML_TRY

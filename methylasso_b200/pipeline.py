@@ -15,6 +15,9 @@ checks its outputs against single-engine calls and against the CPU restatement o
 """
 from __future__ import annotations
 
+import contextlib
+import os
+import threading
 import time
 
 import numpy as np
@@ -31,6 +34,41 @@ def _pin(arr, lib):
     return out
 
 
+class _Turns:
+    """The groups of a call take a resource (the packing threads, the bus) in the order of their index: the engine of group k
+    is served before those of the groups in front of it (its stream has the higher priority), because after the last upload
+    everybody waits for the last group's chain of kernels."""
+
+    def __init__(self):
+        self.cv = threading.Condition()
+        self.next = 0
+
+    def reset(self):
+        with self.cv:
+            self.next = 0
+            self.cv.notify_all()
+
+    def abort(self):
+        with self.cv:
+            self.next = -1
+            self.cv.notify_all()
+
+    @contextlib.contextmanager
+    def turn(self, i):
+        with self.cv:
+            while self.next != i and self.next >= 0:
+                self.cv.wait()
+            if self.next < 0:
+                raise RuntimeError("another group of this call failed")
+        try:
+            yield
+        finally:
+            with self.cv:
+                if self.next >= 0:
+                    self.next = i + 1
+                self.cv.notify_all()
+
+
 class GenomePipeline:
     """The jobs (chromosomes) of one data set, split into groups for `n_engines` engines of one GPU.
 
@@ -41,6 +79,10 @@ class GenomePipeline:
                  host_threads=None):
         self.pool = api.EnginePool(max(1, int(n_engines)), device)
         self.lib = self.pool.engines[0].lib
+        self._pack, self._bus = _Turns(), _Turns()
+        if len(self.pool.engines) > 1 and os.environ.get("ML_PIPE_PRIORITY", "1") != "0":
+            for k, e in enumerate(self.pool.engines):      # group k enters after group k - 1: served first
+                e.set("stream_priority", k)
         self.params = MlParams(float(lambda2), float(lambda2) + 1, 0.0, float(tol_val), 50.0, 1.0, 1, 1, 1, api.MODEL_FAST, 0, 0)
         self.tol_val = float(tol_val)
         self.pin = bool(pin)
@@ -102,13 +144,20 @@ class GenomePipeline:
 
     def _upload(self, eng, gptr, gcols, t):
         """ml_batch_stage (host passes, one group at a time on all the packing threads) then ml_batch_commit (the
-        transfers, one group at a time on the bus); the packing of a group overlaps the transfer of the one before."""
-        with self.pool.pack_turn:
-            t.append(time.perf_counter())
-            bt = eng.stage(gptr, gcols)
-        with self.pool.h2d_turn:
-            t.append(time.perf_counter())
-            eng.commit(bt)
+        transfers, one group at a time on the bus); the packing of a group overlaps the transfer of the one before.  The
+        groups take their turns in index order."""
+        i = self._group_index[id(gptr)]
+        try:
+            with self._pack.turn(i):
+                t.append(time.perf_counter())
+                bt = eng.stage(gptr, gcols)
+            with self._bus.turn(i):
+                t.append(time.perf_counter())
+                eng.commit(bt)
+        except BaseException:
+            self._pack.abort()
+            self._bus.abort()
+            raise
         t.append(time.perf_counter())
         return bt
 
@@ -122,10 +171,13 @@ class GenomePipeline:
     def _stamp(self, marks):
         self.timeline.append([round((t - self._t0) * 1e3, 2) for t in marks])
 
-    def _run(self, fn):
+    def _run(self, fn, items=None):
         self.timeline = []
+        self._group_index = {id(g[1]): i for i, g in enumerate(self.groups)}
+        self._pack.reset()
+        self._bus.reset()
         self._t0 = time.perf_counter()
-        return self.pool.map(fn, self.groups)
+        return self.pool.map(fn, self.groups if items is None else items)
 
     # ---- Part 1 of the CLI: region tables only --------------------------------------------------------------------
     def segment_methylation(self, max_distance=500.0, drop=True, **rule_kw):
@@ -204,9 +256,7 @@ class GenomePipeline:
             return dict(jobs=jobs, mu=o["mu"] if want_mu else None, offset=o["offset"], estimates=est, segments=seg,
                         call_table=call, pmd_segments=pmd, status=status)
 
-        self.timeline = []
-        self._t0 = time.perf_counter()
-        return pool.map(run_group, list(zip(self.groups, bufs)))
+        return self._run(run_group, list(zip(self.groups, bufs)))
 
     def output_buffers(self, want_mu=True):
         """Page-locked output buffers of signal_detection_fast, sized by one untimed fit per group."""
