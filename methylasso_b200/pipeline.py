@@ -89,7 +89,6 @@ class GenomePipeline:
         self._pinned = []               # per group: column name -> page-locked buffer (kept across rebind)
         self._edge_share = edge_share
         self.rebind(job_ptr, cols)
-        import os
         # packing threads: all CPUs of this process but four (the engines' own host threads and the driver's need some; measured
         # on a 16-CPU box: 12 threads 25.4 ms per genome, 16 threads 28 ms with outliers, 8 threads 28 ms)
         ht = int(host_threads or os.environ.get("ML_HOST_THREADS") or max(4, min(32, len(os.sched_getaffinity(0)) - 4)))
