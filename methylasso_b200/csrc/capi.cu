@@ -157,6 +157,7 @@ int ml_engine_create(int device, ml_engine** out) {
   ML_CUDA(cudaStreamCreateWithFlags(&h->e.stream, cudaStreamNonBlocking));
   ML_CUDA(cudaStreamCreateWithFlags(&h->e.copy_stream, cudaStreamNonBlocking));
   detect_init_device_tables(h->e.stream);
+  segment_init_device_tables(h->e.stream);
   // the engine's own pool; freed blocks stay in it, so steady-state calls never reach the driver
   cudaMemPoolProps props = {};
   props.allocType = cudaMemAllocationTypePinned;
@@ -397,6 +398,16 @@ int ml_debug_flsa_backpointers(ml_engine* eng, int64_t n, const double* y, const
   ML_CATCH
 }
 
+int ml_debug_div_counts(ml_engine* eng, int max_num, int max_den, long long* pairs, long long* mismatches) {
+  if (!eng || !pairs || !mismatches || max_num < 0 || max_den < 2) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
+  ML_TRY
+  ML_CUDA(cudaSetDevice(eng->e.device));
+  tls_pool() = eng->e.pool;
+  tls_mailbox() = &eng->e.mailbox;
+  debug_div_counts(eng->e, max_num, max_den, pairs, mismatches);
+  return ML_OK;
+  ML_CATCH
+}
 int ml_debug_scan_runs(int64_t n, const int32_t* dataset, const int32_t* condition, const int32_t* replicate,
                        const int32_t* pos, int threads, int64_t cap, int64_t* n_runs, int64_t* first_row,
                        int32_t* run_condition, int32_t* run_replicate, int32_t* code, int64_t* code_row) {

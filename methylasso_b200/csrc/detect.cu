@@ -28,6 +28,7 @@
 #include "detect.cuh"
 #include "hostpack.h"
 #include "tiles.cuh"
+#include "counts_div.cuh"
 
 namespace ml {
 
@@ -147,7 +148,7 @@ __global__ void k_init_fast_w() {
 __device__ __forceinline__ void fast_residual(const double* __restrict__ tab, int first, int nmeth, int cov, double mu_prev,
                                               double& z, double& W) {
   const double nobs = (double)cov;
-  const double y = div_nz((double)nmeth, nobs);
+  const double y = div_counts(nmeth, cov);
   if ((unsigned)cov < (unsigned)FAST_W_TABLE) {
     W = tab[cov];
     z = first ? y : (y - mu_prev);           // identity_link.cpp:20-23 | :32-36
@@ -162,7 +163,7 @@ __device__ __forceinline__ void row_residual(int model, int first, int nmeth, in
     fast_residual(g_fast_w, first, nmeth, cov, mu_prev, z, W);
   } else {
     const double nobs = (double)cov;
-    irls_residual(model, first, div_nz((double)nmeth, nobs), nobs, mu_prev, nu, z, W);
+    irls_residual(model, first, div_counts(nmeth, cov), nobs, mu_prev, nu, z, W);
   }
 }
 
@@ -236,7 +237,7 @@ k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs
       sw += W;
       sz += z * W;
       const double nobs = (double)cv[q];
-      lik += irls_minus_log_pdf(model, div_nz((double)nm[q], nobs), nobs, m0, J.nu, log2pi);
+      lik += irls_minus_log_pdf(model, div_counts(nm[q], cv[q]), nobs, m0, J.nu, log2pi);
     }
     if (BITMAP && cb) atomicOr(&bitmap[b0 + cw], cb);
   }
@@ -457,7 +458,7 @@ __device__ __forceinline__ void bin_residuals(const JobDev& J, const RowCols& rc
     const int64_t g = J.row0 + r;
     if (r != r0 && rc.pidx[g] != k) break;
     const double nobs = (double)rc.cov[g];
-    const double y = div_nz((double)rc.nmeth[g], nobs);
+    const double y = div_counts(rc.nmeth[g], rc.cov[g]);
     double z, W;
     irls_residual(J.model, first, y, nobs, first ? 0.0 : rc.mu_res[g], J.nu, z, W);
     What += W;
@@ -785,7 +786,7 @@ k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
       m[q] = irls_mu(MODEL >= 0 ? MODEL : J.model, eta[q] + (0. + 1. * o));
       if (!(r.mask >> q & 1)) continue;
       const double nobs = (double)cv[q];
-      const double y = div_nz((double)nm[q], nobs);
+      const double y = div_counts(nm[q], cv[q]);
       lik += irls_minus_log_pdf(MODEL >= 0 ? MODEL : J.model, y, nobs, m[q], J.nu, log2pi);
       if (need_dres) dres = fmax(dres, fabs(m[q] - mr[q]));
       if (want_outer) dout = fmax(dout, fabs(m[q] - mo[q]));
@@ -1783,6 +1784,7 @@ void result_fast_diff_combine(Engine& eng, Result& r) {
 void detect_init_device_tables(cudaStream_t st) {
   k_init_fast_w<<<cdiv(FAST_W_TABLE, 256), 256, 0, st>>>();
   ML_CHECK_LAUNCH();
+  init_rcp_table(st);
   ML_CUDA(cudaStreamSynchronize(st));
 }
 

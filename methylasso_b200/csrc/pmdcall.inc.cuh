@@ -247,15 +247,23 @@ struct PcRegion {
   double *mean0, *count;
   DD *t, *q;                       // per live piece: sum(x - mean0), sum((x - mean0)^2) with its region's mean0
 };
+// One WARP per region (an "other" region between two PMDs holds hundreds of pieces): lanes take the live pieces in a stride,
+// their partial sums are merged in a fixed order (double-double: the order shows in the last bits of the low word only).
 __global__ void k_pc_region_mean0(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, PcRegion R) {
-  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (v >= R.n) return;
   const int32_t r0 = R.heads[v], r1 = v + 1 < R.n ? R.heads[v + 1] : n_live;
   DD s{0.0, 0.0};
   double m = 0.0;
-  for (int32_t r = r0; r < r1; ++r) { s = dd_merge(s, P.sum[live[r]]); m += (double)P.ncpg[live[r]]; }
-  R.mean0[v] = (s.hi + s.lo) / m;
-  R.count[v] = m;
+  for (int32_t r = r0 + lane; r < r1; r += 32) { s = dd_merge(s, P.sum[live[r]]); m += (double)P.ncpg[live[r]]; }
+  s = dd_warp_sum(s);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m += __shfl_xor_sync(0xffffffffu, m, d);       // counts: exact in any order
+  if (lane == 0) {
+    R.mean0[v] = (s.hi + s.lo) / m;
+    R.count[v] = m;
+  }
 }
 // (b) per live piece, in shares like the first sweep (block r < n_live: share 0 of live piece r; the listed shares behind
 // them, by way of the piece -> live index map): the two central sums about its region's mean0; a position that two
@@ -302,23 +310,45 @@ __global__ void k_pc_piece_moments_sum(PcPieces P, PcShares L, int32_t n_live, c
   R.t[r] = t;
   R.q[r] = q;
 }
-// (c) one thread per region: mean = mean0 + T / M (R's second pass), sum of squares about it = Q - (T / M) T
+// (c) one warp per region: mean = mean0 + T / M (R's second pass), sum of squares about it = Q - (T / M) T; fused_std = the
+// mean of the pieces' values, two passes like R's mean() with double-double sums in the place of its long double
 __global__ void k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t n_live, const int8_t* __restrict__ cat,
                            PcRegion R, PcOut o) {
-  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (v >= R.n) return;
   const int32_t r0 = R.heads[v], r1 = v + 1 < R.n ? R.heads[v + 1] : n_live;
-  DD T{0.0, 0.0}, Q{0.0, 0.0};
-  uint32_t lo = P.pstart[live[r0]], hi = P.pend[live[r0]];
-  int64_t ncpg = 0;
-  for (int32_t r = r0; r < r1; ++r) {
+  DD T{0.0, 0.0}, Q{0.0, 0.0}, F{0.0, 0.0};
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  long long ncpg = 0;
+  for (int32_t r = r0 + lane; r < r1; r += 32) {
     const int32_t k = live[r];
     T = dd_merge(T, R.t[r]);
     Q = dd_merge(Q, R.q[r]);
+    dd_add(F, P.fused_std[k]);
     lo = P.pstart[k] < lo ? P.pstart[k] : lo;
     hi = P.pend[k] > hi ? P.pend[k] : hi;
     ncpg += P.ncpg[k];
   }
+  T = dd_warp_sum(T);
+  Q = dd_warp_sum(Q);
+  F = dd_warp_sum(F);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const uint32_t ol = __shfl_xor_sync(0xffffffffu, lo, d), oh = __shfl_xor_sync(0xffffffffu, hi, d);
+    lo = ol < lo ? ol : lo;
+    hi = oh > hi ? oh : hi;
+    ncpg += __shfl_xor_sync(0xffffffffu, ncpg, d);
+  }
+  const double np_ = (double)(r1 - r0);
+  double fmean = (F.hi + F.lo) / np_;
+  if (is_finite(fmean)) {
+    DD D{0.0, 0.0};
+    for (int32_t r = r0 + lane; r < r1; r += 32) dd_add(D, P.fused_std[live[r]] - fmean);
+    D = dd_warp_sum(D);
+    fmean += (D.hi + D.lo) / np_;
+  }
+  if (lane) return;
   const double m = R.count[v], mean0 = R.mean0[v];
   const double delta = (T.hi + T.lo) / m;
   const double mean = is_finite(mean0) ? mean0 + delta : mean0;
@@ -331,7 +361,7 @@ __global__ void k_pc_merge(PcPieces P, const int32_t* __restrict__ live, int32_t
   o.start[v] = lo;
   o.end[v] = hi;
   o.ncpg[v] = (int32_t)ncpg;
-  o.fused_std[v] = x87_mean(r1 - r0, [&](int q) { return P.fused_std[live[r0 + q]]; });
+  o.fused_std[v] = fmean;
   o.width[v] = (double)hi - (double)lo + 1;
   o.beta[v] = mean;
   o.std_[v] = m >= 2 ? sqrt(fmax(ss.hi + ss.lo, 0.0) / (m - 1)) : 0.0;      // sd of one value is NA -> 0 (:197)
@@ -406,7 +436,7 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
   DevBuf<DD> r_t(st, (size_t)n_live), r_q(st, (size_t)n_live);
   DevBuf<int32_t> region_of(st, (size_t)n_live);
   const PcRegion Rg{n_out, heads.p, r_mean0.p, r_count.p, r_t.p, r_q.p};
-  ML_LAUNCH(eng, "k_pc_region_mean0", k_pc_region_mean0<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, Rg));
+  ML_LAUNCH(eng, "k_pc_region_mean0", k_pc_region_mean0<<<cdiv(32LL * n_out, 128), 128, 0, st>>>(P, live.p, n_live, Rg));
   ML_LAUNCH(eng, "k_pc_region_of", k_pc_region_of<<<cdiv(n_live, 256), 256, 0, st>>>(n_live, flag.p, hpos.p, region_of.p));
   {
     DevBuf<DD> part_t(st, (size_t)n_live + share_cap), part_q(st, (size_t)n_live + share_cap);
@@ -418,7 +448,7 @@ void call_pmds_device(Engine& eng, const std::vector<SegGroup>& groups, const vo
     ML_LAUNCH(eng, "k_pc_piece_moments_sum", k_pc_piece_moments_sum<<<cdiv(n_live, 128), 128, 0, st>>>(P, L, n_live, live.p, part_t.p,
                                                                                                         part_q.p, Rg));
   }
-  ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<<<cdiv(n_out, 128), 128, 0, st>>>(P, live.p, n_live, cat.p, Rg, o));
+  ML_LAUNCH(eng, "k_pc_merge", k_pc_merge<<<cdiv(32LL * n_out, 128), 128, 0, st>>>(P, live.p, n_live, cat.p, Rg, o));
   DevBuf<int32_t> gflag(st, (size_t)n_out), gpos(st, (size_t)n_out), gheads(st, (size_t)n_out);
   ML_LAUNCH(eng, "k_pc_group_heads", k_pc_group_heads<<<cdiv(n_out, 256), 256, 0, st>>>(n_out, o, gflag.p));
   scan.run(eng, gflag.p, n_out, gpos.p, gheads.p);

@@ -68,9 +68,11 @@ __global__ void k_ps_unmatched(PmdSegs X, const int32_t* __restrict__ cnt, int32
   const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x < X.n) ms_group_unmatched(X, cnt, x, na_group);
 }
-__global__ void k_ps_emit(Regions G, PmdSegs X, const int32_t* __restrict__ off, const int32_t* __restrict__ na_group, Pieces P) {
-  const int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x < X.n) ms_emit_pieces(G, X, x, off[x], na_group[x], P);
+// one warp per segment: a PMD-sized segment is cut into thousands of pieces
+__global__ void k_ps_emit(Regions G, PmdSegs X, const int32_t* __restrict__ cnt, const int32_t* __restrict__ off,
+                          const int32_t* __restrict__ na_group, Pieces P) {
+  const int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (x < X.n) ms_emit_pieces(G, X, x, off[x], na_group[x], P, cnt[x], (int32_t)(threadIdx.x & 31), 32);
 }
 // :164  seq_len(.N) per estimate_id, counted behind the region-less segments that sort first
 __global__ void k_ps_piece_ids(int32_t n, const int32_t* __restrict__ flag, const int32_t* __restrict__ pos,
@@ -153,7 +155,7 @@ void call_pmd_split_device(Engine& eng, const CallTable& t, const int8_t* d_cate
   if (np == 0) return;
   DevBuf<int32_t> p_na(st, (size_t)np);
   const Pieces Pv{P.job.p, P.est.p, p_na.p, P.start.p, P.end.p, P.fused_std.p, P.pw.p};
-  ML_LAUNCH(eng, "k_ps_emit", k_ps_emit<<<cdiv(nx, 128), 128, 0, st>>>(G, X, off.p, na_group.p, Pv));
+  ML_LAUNCH(eng, "k_ps_emit", k_ps_emit<<<cdiv(32LL * nx, 128), 128, 0, st>>>(G, X, cnt.p, off.p, na_group.p, Pv));
   DevBuf<int32_t> pflag(st, (size_t)np), ppos(st, (size_t)np), pheads(st, (size_t)np);
   ML_LAUNCH(eng, "k_ps_piece_heads", k_ps_piece_heads<<<cdiv(np, 256), 256, 0, st>>>(np, Pv, pflag.p));
   scan.run(eng, pflag.p, np, ppos.p, pheads.p);

@@ -86,10 +86,19 @@ ML_HD int32_t ms_first_region(const Regions& G, const PmdSegs& X, int32_t x) {
   }
   return lo;
 }
+// the regions of a group are ordered by start: those that overlap segment x are [first, the first one that starts behind
+// its end) - a second binary search instead of a walk (a PMD-sized segment overlaps thousands of regions)
 ML_HD int32_t ms_count_pieces(const Regions& G, const PmdSegs& X, int32_t x) {
-  int32_t y = ms_first_region(G, X, x), k = 0;
-  while (y < G.n && G.job[y] == X.job[x] && G.est[y] == X.est[x] && G.start[y] <= X.end[x]) { ++k; ++y; }
-  return k;
+  const int32_t first = ms_first_region(G, X, x);
+  const int32_t j = X.job[x], e = X.est[x];
+  const uint32_t xe = X.end[x];
+  int32_t lo = first, hi = G.n;
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    const bool in = G.job[mid] == j && G.est[mid] == e && G.start[mid] <= xe;
+    if (in) lo = mid + 1; else hi = mid;
+  }
+  return lo - first;
 }
 // A segment can be left without any region: it starts on a call-table row, and a row that merely TOUCHES a valley (its
 // last CpG two bases before the valley's first: end = max(pos) + 2 = the valley's start) is removed at :133 although
@@ -107,16 +116,20 @@ struct Pieces {           // split_call after :168
   double *fused_std, *pw;
 };
 // :159-161  one piece per (segment, region) match: the intersection; fused_std = 0 outside "complement"
-ML_HD void ms_emit_pieces(const Regions& G, const PmdSegs& X, int32_t x, int32_t at, int32_t na, const Pieces& P) {
-  int32_t y = ms_first_region(G, X, x);
-  while (y < G.n && G.job[y] == X.job[x] && G.est[y] == X.est[x] && G.start[y] <= X.end[x]) {
-    P.job[at] = X.job[x]; P.est[at] = X.est[x]; P.na[at] = na;
-    P.start[at] = G.start[y] > X.start[x] ? G.start[y] : X.start[x];
-    P.end[at] = G.end[y] < X.end[x] ? G.end[y] : X.end[x];
-    P.fused_std[at] = G.isolate[y] ? 0.0 : X.fused_std[x];
-    P.pw[at] = X.pw[x];
-    ++at; ++y;
-  }
+// piece i of segment x (its overlap with region first + i), written at `at`
+ML_HD void ms_emit_piece(const Regions& G, const PmdSegs& X, int32_t x, int32_t y, int32_t at, int32_t na, const Pieces& P) {
+  P.job[at] = X.job[x]; P.est[at] = X.est[x]; P.na[at] = na;
+  P.start[at] = G.start[y] > X.start[x] ? G.start[y] : X.start[x];
+  P.end[at] = G.end[y] < X.end[x] ? G.end[y] : X.end[x];
+  P.fused_std[at] = G.isolate[y] ? 0.0 : X.fused_std[x];
+  P.pw[at] = X.pw[x];
+}
+// the `count` pieces of segment x from position `at` on, every `stride`-th one starting with piece `i0` (the lanes of a
+// warp share a segment; 0, 1: all of them in order)
+ML_HD void ms_emit_pieces(const Regions& G, const PmdSegs& X, int32_t x, int32_t at, int32_t na, const Pieces& P,
+                          int32_t count, int32_t i0 = 0, int32_t stride = 1) {
+  const int32_t first = ms_first_region(G, X, x);
+  for (int32_t i = i0; i < count; i += stride) ms_emit_piece(G, X, x, first + i, at + i, na, P);
 }
 
 }  // namespace ml

@@ -14,6 +14,7 @@
 #include <cstring>
 
 #include "segment.cuh"
+#include "counts_div.cuh"
 #include "detect.cuh"
 #include "flsa.cuh"
 #include "hd.h"
@@ -326,18 +327,18 @@ struct RowsFromEstimates {   // FAST result: betahat = pooled Nmeth / pooled cov
   const double* pw;          // and Nmeth / pw is then R's own `Nmeth/coverage`.  Parameters without data in this
   __device__ bool valid(int64_t i) const { return pw[i] > 0; }         // condition (pw == 0) are not rows of mdata.
   __device__ double cov(int64_t i) const { return pw[i]; }
-  __device__ double x(int64_t i) const { return div_nz(rint(betahat[i] * pw[i]), pw[i]); }
+  __device__ double x(int64_t i) const { return div_counts(rint(betahat[i] * pw[i]), pw[i]); }
   // the same in two steps: plain loads first (raw, cov), arithmetic later
   __device__ double raw(int64_t i) const { return betahat[i]; }
   __device__ bool valid_cov(double c) const { return c > 0; }
-  __device__ double x_from(double r, double c) const { return div_nz(rint(r * c), c); }
+  __device__ double x_from(double r, double c) const { return div_counts(rint(r * c), c); }
 };
 struct RowsFromCounts {      // host table: pooled Nmeth, coverage per position as given
   const int32_t* nmeth;
   const int32_t* coverage;
   __device__ bool valid(int64_t) const { return true; }
   __device__ double cov(int64_t i) const { return (double)coverage[i]; }
-  __device__ double x(int64_t i) const { return div_nz((double)nmeth[i], (double)coverage[i]); }
+  __device__ double x(int64_t i) const { return div_counts(nmeth[i], coverage[i]); }
   __device__ double raw(int64_t i) const { return (double)nmeth[i]; }
   __device__ bool valid_cov(double) const { return true; }
   __device__ double x_from(double r, double c) const { return div_nz(r, c); }
@@ -823,5 +824,35 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
 #include "pmdcall.inc.cuh"
 #include "pmdstatus.inc.cuh"
 #include "regions.inc.cuh"
+
+void segment_init_device_tables(cudaStream_t st) {
+  init_rcp_table(st);          // this translation unit's copy of the reciprocal table (counts_div.cuh)
+  ML_CUDA(cudaStreamSynchronize(st));
+}
+
+namespace {
+__global__ void k_debug_div_counts(int max_num, int max_den, unsigned long long* __restrict__ bad) {
+  const long long total = (long long)(max_num + 1) * (max_den - 1);
+  unsigned long long mine = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int num = (int)(i % (max_num + 1)), den = 1 + (int)(i / (max_num + 1));
+    const double want = (double)num / (double)den;
+    const double a = div_counts(num, den), b = div_counts((double)num, (double)den);
+    mine += (f64_bits(a) != f64_bits(want)) + (f64_bits(b) != f64_bits(want));
+  }
+  if (mine) atomicAdd(bad, mine);
+}
+}  // namespace
+void debug_div_counts(Engine& eng, int max_num, int max_den, long long* pairs, long long* mismatches) {
+  cudaStream_t st = eng.stream;
+  DevBuf<unsigned long long> bad(st, 1);
+  bad.zero();
+  ML_LAUNCH(eng, "k_debug_div_counts", k_debug_div_counts<<<1184, 256, 0, st>>>(max_num, max_den, bad.p));
+  unsigned long long h = 0;
+  bad.download(&h, 1);
+  stream_sync(st);
+  *pairs = (long long)(max_num + 1) * (max_den - 1);
+  *mismatches = (long long)h;
+}
 
 }  // namespace ml

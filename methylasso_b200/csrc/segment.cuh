@@ -177,4 +177,10 @@ int64_t segment_host_table(Engine& eng, int64_t n, const int32_t* estimate_id, c
                            const double* beta, const double* betahat, const double* pw, double tol_val,
                            SegHostOut& out);
 
+// once per device, at engine creation: tables the kernels of segment.cu read (counts_div.cuh)
+void segment_init_device_tables(cudaStream_t st);
+
+// test hook (debug_api.h): pairs checked / pairs whose quotient differs from the division's
+void debug_div_counts(Engine& eng, int max_num, int max_den, long long* pairs, long long* mismatches);
+
 }  // namespace ml

@@ -113,7 +113,7 @@ int64_t emu_pmd_split(int64_t n, const int32_t* job, const int32_t* est, const u
   if (off[n_x] > cap) { *n_pieces = -1; return nm; }
   std::vector<int32_t> p_na((size_t)off[n_x] + 1);
   const Pieces P{p_job, p_est, p_na.data(), p_start, p_end, p_fused, p_pw};
-  for (int32_t x = 0; x < n_x; ++x) ms_emit_pieces(G, X, x, off[x], na_group[x], P);
+  for (int32_t x = 0; x < n_x; ++x) ms_emit_pieces(G, X, x, off[x], na_group[x], P, cnt[x]);
   for (int32_t k = 0; k < off[n_x]; ++k) {
     if (k == 0 || p_job[k] != p_job[k - 1] || p_est[k] != p_est[k - 1]) head = k;
     p_seg[k] = k - head + 1 + p_na[k];

@@ -395,3 +395,12 @@ def test_engine_pool_grouping_is_result_neutral(engine):
         for c in ("beta", "betahat", "pseudoweight"):
             assert np.array_equal(got[j]["estimates"][c], whole[j]["estimates"][c])
         assert np.array_equal(got[j]["mu"], whole[j]["mu"])
+
+
+def test_count_quotient_without_the_division_has_its_bits(engine):
+    """counts_div.cuh on the device: all 67 M pairs (0 <= Nmeth <= 65536, 1 <= coverage < 1024), both signatures of
+    div_counts against the device's IEEE division."""
+    import ctypes as C
+    pairs, bad = C.c_longlong(), C.c_longlong()
+    engine._check(engine.lib.ml_debug_div_counts(engine.h, 65536, 1024, C.byref(pairs), C.byref(bad)))
+    assert pairs.value == 65537 * 1023 and bad.value == 0

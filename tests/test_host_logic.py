@@ -1,4 +1,6 @@
 """CPU tests of the Python host layer that need no GPU: chromosome splitting, job grouping."""
+import os
+
 import numpy as np
 
 from methylasso_b200 import api, synth
@@ -57,3 +59,17 @@ def test_codec_load_text_inflates_gzip(tmp_path):
     plain.write_bytes(text)
     packed.write_bytes(gzip.compress(text))
     assert codec.load_text(str(plain)) == text and codec.load_text(str(packed)) == text
+
+
+def test_two_fma_quotient_of_counts_is_the_ieee_quotient():
+    """counts_div.cuh: for an integer numerator up to 65536 and a coverage below 1024 the quotient formed from the
+    correctly rounded reciprocal by two FMAs has the bits of the division - every pair, on the CPU with the C library's fma."""
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    src, lib = os.path.join(here, "emu", "emu_counts_div.cpp"), os.path.join(here, "emu", "libemu_counts_div.so")
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", lib, src])
+    L = C.CDLL(lib)
+    L.emu_counts_div_mismatches.restype = C.c_longlong
+    assert L.emu_counts_div_mismatches(65536, 1024) == 0
