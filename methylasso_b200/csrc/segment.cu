@@ -109,10 +109,64 @@ k_scan_apply(const int32_t* __restrict__ flags, int64_t n, const int32_t* __rest
   }
 }
 
+// The same scan in ONE launch for short inputs (the tables of the rule engine: 10^3 .. 10^5 rows, where three launches
+// cost more than the work): a single block walks the flags 4096 at a time.
+constexpr int SCAN_SMALL_THREADS = 1024, SCAN_SMALL_V = 4;
+constexpr int64_t SCAN_SMALL_MAX = 1 << 15;
+__global__ void __launch_bounds__(SCAN_SMALL_THREADS)
+k_scan_small(const int32_t* __restrict__ flags, int n, int32_t* __restrict__ pos, int32_t* __restrict__ compact,
+             int32_t* __restrict__ total) {
+  __shared__ int32_t sm[SCAN_SMALL_THREADS / 32];
+  __shared__ int32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int base0 = 0; base0 < n; base0 += SCAN_SMALL_THREADS * SCAN_SMALL_V) {
+    const int base = base0 + threadIdx.x * SCAN_SMALL_V;
+    int32_t f[SCAN_SMALL_V];
+    int32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_SMALL_V; ++k) {
+      f[k] = (base + k < n) ? flags[base + k] : 0;
+      mine += f[k];
+    }
+    int32_t inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) sm[wid] = inc;
+    __syncthreads();
+    int32_t run = carry_s + inc - mine;
+    for (int k = 0; k < wid; ++k) run += sm[k];
+#pragma unroll
+    for (int k = 0; k < SCAN_SMALL_V; ++k) {
+      if (base + k < n) {
+        if (pos) pos[base + k] = run;
+        if (compact && f[k]) compact[run] = base + k;
+      }
+      run += f[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_SMALL_THREADS - 1) carry_s = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
 struct Scan {
   DevBuf<int32_t> tile_sum, total;
   int32_t run(Engine& eng, const int32_t* flags, int64_t n, int32_t* pos, int32_t* compact) {
     cudaStream_t st = eng.stream;
+    if (n <= SCAN_SMALL_MAX) {
+      total.alloc(st, 1);
+      ML_LAUNCH(eng, "k_scan_small", k_scan_small<<<1, SCAN_SMALL_THREADS, 0, st>>>(flags, (int)n, pos, compact, total.p));
+      int32_t h = 0;
+      total.download(&h, 1);
+      stream_sync(st);
+      return h;
+    }
     const int nt = cdiv(n, STILE);
     tile_sum.alloc(st, std::max(1, nt));
     total.alloc(st, 1);
