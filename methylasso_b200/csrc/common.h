@@ -127,8 +127,10 @@ struct Engine {
   // route of a series through the forward pass: 0 = by the series itself (short series and series with empty bins take
   // the scan route, flsa_core.cuh; long dense ones the speculative route), 1 = speculative route only, 2 = scan route only
   int flsa_route = 0;
-  int flsa_scan_lambda = 50;    // route 0: series with a penalty of at least this take the scan route too (the memory of a
-                                // series grows with lambda2 / weight: at the PMD step's 1000 no warm-up covers it)
+  int flsa_scan_lambda = 26;    // route 0: series with a penalty of at least this take the scan route too.  The memory of a
+                                // series grows with lambda2 / weight: on WGBS coverage the speculative route verifies 97 %
+                                // of its chunks at the reference's default 25, walks chains of a hundred chunks at 41
+                                // (configs[4] sweep: 37 ms in the walkers) and no warm-up covers the PMD step's 1000
   int flsa_scan_chunk_small = 64, flsa_scan_chunk_big = 448;
   int host_threads = 4;     // host threads of batch_upload's passes over the input columns (run scan, packing of the counts)
   char* stage_host = nullptr;   // page-locked staging area of batch_stage (grown on demand, freed with the engine)
