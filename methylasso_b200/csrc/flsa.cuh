@@ -61,7 +61,7 @@ class FlsaPlan {
   int chunk_len() const { return chunk_; }
   int warm_len() const { return warm_; }
   // counters of the last solve (read back with the overflow flags)
-  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0, scan_chunks = 0; };
+  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0, scan_chunks = 0, series_rerouted = 0; };
   Stats last_stats() const { return stats_; }
 
  private:
@@ -82,7 +82,12 @@ class FlsaPlan {
   int64_t scan_steps_ = 0;
   DevBuf<ChunkDesc> d_scan_chunks_;
   DevBuf<ScanGroup> d_scan_groups_;
-  DevBuf<int32_t> d_scan_series_;   // per scan-route series: series index, first group, number of groups
+  DevBuf<int32_t> d_scan_series_;   // per series with scan tables: series index, first group, number of groups
+  DevBuf<SeriesDesc> d_scan_desc_;   // the series as the scan route sees them (first_chunk / n_chunks of ITS chunk table)
+  DevBuf<int32_t> d_route_;         // per series, per solve: 1 = the scan route's kernels process it (set by the plan for
+                                    // scan-route series, by a walker that gave up for ROUTE_SPEC_DUAL ones)
+  std::vector<int32_t> h_route_init_;
+  std::vector<SeriesDesc> h_scan_desc_;
   DevBuf<int32_t> d_scan_i32_;
   DevBuf<double> d_scan_f64_;
   ScanFns scan_chunk_fns_{}, scan_group_fns_{};
@@ -92,7 +97,8 @@ class FlsaPlan {
   DevBuf<double> d_tm_, d_tp_;
   DevBuf<double> d_beta_last_;
   DevBuf<int32_t> d_flags_;         // per series: bit0 overflow, bit1 clamp-order violation
-  DevBuf<int32_t> d_counters_;      // [0] chunks verified, [1] chunks redone by the walkers, [2] longest chain, [3] chains
+  DevBuf<int32_t> d_counters_;      // [0] chunks verified, [1] chunks redone by the walkers, [2] longest chain, [3] chains,
+                                    // [4] series the walkers handed over to the scan route
   DevBuf<Clamp> d_tile_agg_;
   DevBuf<double> d_tile_in_;
   DevBuf<double> d_tile_sums_;      // 2 per tile
@@ -103,7 +109,7 @@ class FlsaPlan {
   struct Job { const double *y = nullptr, *w = nullptr; double* beta = nullptr; int post = 0; double lambda1 = 0;
                double* sums = nullptr; bool skip = false, pending = false; } job_;   // arguments of the solve in flight
   std::vector<int32_t> h_flags_, h_skip_;
-  int32_t h_counters_[4] = {0, 0, 0, 0};
+  int32_t h_counters_[5] = {0, 0, 0, 0, 0};
   void backward();
   void forward_scan(const double* d_y, const double* d_w, const int32_t* skip);
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);

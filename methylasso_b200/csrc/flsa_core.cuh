@@ -42,7 +42,9 @@ enum : int32_t {
   SERIES_TRIVIAL = 1,     // n <= 1 or lam == 0: beta = y            (gfl_tf.c:210-215)
   SERIES_SEQUENTIAL = 2,  // lam < 0 / NaN: the sandwich does not apply; one chunk, run start-to-end
 };
-enum : int32_t { ROUTE_SPEC = 0, ROUTE_SCAN = 1 };
+// ROUTE_SPEC_DUAL: speculative route, with the scan route's tables built too: a series whose walkers meet a chain longer
+// than the engine's limit is handed over to the scan route on the device (flsa_chain_kernel sets its entry of `route`)
+enum : int32_t { ROUTE_SPEC = 0, ROUTE_SCAN = 1, ROUTE_SPEC_DUAL = 2 };
 enum : int32_t {
   SPEC_EXACT = 1,      // the run started at the head of its series: exact by construction, nothing to verify
   SPEC_OVERFLOW = 2,   // the window outgrew the speculative ring: S / E are not usable, the chunk is redone by a walker

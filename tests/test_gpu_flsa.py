@@ -75,6 +75,28 @@ def test_routes_on_count_data_bit_exact(engine, oracle):
         engine.set("flsa_route", 0)
 
 
+def test_walkers_hand_a_series_over_to_the_scan_route(engine, oracle):
+    """A long dense series takes the speculative route; when its walkers meet a chain of more than flsa_chain_limit
+    chunks the series is handed over to the scan route ON THE DEVICE (its tables are built next to the speculative ones).
+    Count data with the limit at 1 (every chain of two chunks triggers it): still bit-equal to the verbatim DP.  Real-valued
+    data (windows from opposite bounds agree numerically long before they agree bit for bit): per element to 1e-10."""
+    t = synth.chromosome_table(400_000, 20241, (3,))
+    y, w = pooled_series(t)
+    ref = oracle.weighted_1d_flsa(y, w, 25.0)
+    try:
+        for limit in (1, 6, 0):
+            engine.set("flsa_chain_limit", limit)
+            assert np.array_equal(engine.weighted_1d_flsa(y, w, 25.0), ref), limit
+    finally:
+        engine.set("flsa_chain_limit", 6)
+    rng = np.random.default_rng(5)
+    n = 300_000
+    yr = np.cumsum(rng.normal(0, 0.01, n)) + rng.normal(0, 0.3, n)
+    wr = rng.exponential(20.0, n)
+    got, want = engine.weighted_1d_flsa(yr, wr, 20.0), oracle.weighted_1d_flsa(yr, wr, 20.0)
+    assert np.all(np.abs(got - want) <= 1e-10 * max(1.0, float(np.max(np.abs(want)))))
+
+
 def test_scan_route_on_pmd_like_series(engine, oracle):
     """The PMD step's shape (R/call.R:93): a few 10^4 real-valued standard deviations weighted by segment widths, lambda2 =
     1000 - the series whose memory no warm-up covers.  Scan route (the default for short series) against the verbatim DP:
