@@ -100,7 +100,13 @@ ML_API void ml_engine_destroy(ml_engine *eng);
  * memory pool now by that share of what it holds, so that steady-state calls never map memory),
  * "host_threads" (threads of ml_batch_upload's scan of the dataset column, default 4), "want_mu" (default 1; 0: a
  * one-step FAST fit does not store the per-row mu, which nothing in the reference's R layer reads - asking for it
- * from such a result is an error) */
+ * from such a result is an error); the forward pass of the FLSA solver: "flsa_route" (0 = by the series itself, 1 =
+ * speculative route only, 2 = scan route only), "flsa_scan_lambda" (route 0: penalties from this value on take the scan
+ * route, default 26), "flsa_chain_limit" (route 0: chunks a walker redoes before it hands its series over to the scan
+ * route, default 6; 0 = never), "flsa_scan_chunk_small" / "flsa_scan_chunk_big" (chunk lengths of the scan route);
+ * "stream_priority" (re-create the engine's stream at that priority level, right after creation only),
+ * "profile_timeline" (1 = keep the start / end of every profiled launch: ml_engine_profile_spans).  Every route gives the
+ * reference's result: bit for bit on count data with an integer penalty, within rounding elsewhere. */
 ML_API int ml_engine_set(ml_engine *eng, const char *key, long long value);
 /* number of kernel launches issued by this engine so far */
 ML_API long long ml_engine_launch_count(const ml_engine *eng);
