@@ -27,8 +27,9 @@ Timing hygiene: `value` is one contiguous loop of K steps between two CUDA event
 right before and right after that loop and, polled every 5 ms, during one more untimed repetition of the step: any
 driver query issued while the steps run can stall them (measured).  The boxes are shared and an outside stall of
 0.1-1.5 s hits about one step in a hundred; a loop in which one step took more than 1.3 x the loop's median step is
-timed again (at most twice), and EVERY attempt is listed under `attempts` with its ms_per_step and the host wall time of
-each of its steps: the reported numbers are those of the last attempt, the others stand beside it.
+timed again (at most three times), and EVERY attempt is listed under `attempts` with its ms_per_step and the host wall time
+of each of its steps: the reported numbers are those of the first undisturbed attempt - or, on a box where every attempt
+was disturbed, of the fastest one (`reported`: true) - and the others stand beside it.
 
 --impl reference times the reference's CPU path for the same workload on the host cores: the oracle's
 plain-C restatement of methylation_detection with the reference's own tf_dp_weight (oracle/_ref,
@@ -851,7 +852,7 @@ def main():
     # with its own ms_per_step and the host wall time of each of its steps, and the reported numbers are those of one
     # contiguous K-step loop (the last attempt).
     attempts = []
-    for attempt in range(3):
+    for attempt in range(4):
         sampler.mark()
         sampler.sample()
         l0 = eng.launch_count
@@ -876,9 +877,22 @@ def main():
         bad = torch.tensor([1.0 if max(step_wall_res) > DISTURBED * float(np.median(step_wall_res)) else 0.0], device="cuda")
         if world > 1:
             dist.all_reduce(bad, op=dist.ReduceOp.MAX)       # every rank repeats or none does
-        attempts.append({"ms_per_step_this_rank": ms, "host_wall_ms_each_step": step_wall_res, "disturbed": bool(bad.item())})
+        attempts.append({"ms_per_step_this_rank": ms, "host_wall_ms_each_step": step_wall_res, "disturbed": bool(bad.item()),
+                         "clock_samples": list(sampler.samples)})
         if bad.item() == 0.0 or args.profiler_range:
             break
+    # every attempt was disturbed (a busy box): the one with the smallest time over the ranks is reported - still ONE
+    # contiguous K-step loop, and all of them stay listed
+    t_att = torch.tensor([a["ms_per_step_this_rank"] for a in attempts], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_att, op=dist.ReduceOp.MAX)
+    kept = len(attempts) - 1 if not attempts[-1]["disturbed"] else int(torch.argmin(t_att).item())
+    ms = attempts[kept]["ms_per_step_this_rank"]
+    step_wall_res = attempts[kept]["host_wall_ms_each_step"]
+    sampler.samples = list(attempts[kept]["clock_samples"])
+    for i_, a_ in enumerate(attempts):
+        a_.pop("clock_samples")
+        a_["reported"] = i_ == kept
 
     def one_more():
         r_, _ = step_resident()
@@ -949,7 +963,7 @@ def main():
         barrier()
         sampler2 = sampler
         e2e_attempts = []
-        for attempt in range(3):             # same policy as for the resident loop: every attempt is listed
+        for attempt in range(4):             # same policy as for the resident loop: every attempt is listed
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             sampler2.mark()
             sampler2.sample()
@@ -968,14 +982,24 @@ def main():
             if world > 1:
                 dist.all_reduce(bad, op=dist.ReduceOp.MAX)
             e2e_attempts.append({"ms_per_step_this_rank": e0.elapsed_time(e1) / args.steps, "host_wall_ms_each_step": step_wall,
-                                 "disturbed": bool(bad.item())})
+                                 "disturbed": bool(bad.item()), "wall_ms": wall_ms})
             if bad.item() == 0.0:
                 break
+        t_att = torch.tensor([a["ms_per_step_this_rank"] for a in e2e_attempts], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_att, op=dist.ReduceOp.MAX)
+        kept_e = len(e2e_attempts) - 1 if not e2e_attempts[-1]["disturbed"] else int(torch.argmin(t_att).item())
+        e2e_ms_rank = e2e_attempts[kept_e]["ms_per_step_this_rank"]
+        step_wall = e2e_attempts[kept_e]["host_wall_ms_each_step"]
+        wall_ms = e2e_attempts[kept_e].pop("wall_ms")
+        for i_, a_ in enumerate(e2e_attempts):
+            a_.pop("wall_ms", None)
+            a_["reported"] = i_ == kept_e
         timeline = sorted(pipe.timeline)
         sampler2.sample()
         sampler2.sample_during(step_e2e)
         gc.enable()
-        t2 = torch.tensor([e0.elapsed_time(e1) / args.steps], device="cuda", dtype=torch.float64)
+        t2 = torch.tensor([e2e_ms_rank], device="cuda", dtype=torch.float64)
         h2d = torch.tensor([float(pipe.h2d_bytes())], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)

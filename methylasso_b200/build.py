@@ -14,7 +14,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libmethylasso_b200.so")
+OUT = os.environ.get("ML_BUILD_OUT") or os.path.join(HERE, "libmethylasso_b200.so")   # (experiments build variants elsewhere)
 SOURCES = ["flsa.cu", "detect.cu", "segment.cu", "stats.cu", "codec.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
@@ -30,12 +30,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _newest_source():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    objdir = os.path.join(HERE, "_build")
+    objdir = os.environ.get("ML_BUILD_OBJDIR") or os.path.join(HERE, "_build")
+    extra = os.environ.get("ML_BUILD_DEFS", "").split()
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd))

@@ -179,8 +179,11 @@ __device__ __forceinline__ void row_residual(int model, int first, int nmeth, in
 //     sums of W and z W of the first IRLS step;
 //   * the -log pdf of the initial evaluation (Posterior.ipp:25): every parameter and offset is still +0.
 // ------------------------------------------------------------------------------------------------
+#ifndef ML_ROW_MINBLOCKS
+#define ML_ROW_MINBLOCKS 4
+#endif
 template <bool BITMAP>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, ML_ROW_MINBLOCKS)
 k_first_sweep(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs, const int32_t* __restrict__ alive,
               const int32_t* __restrict__ dptr, const int32_t* __restrict__ pos, const int32_t* __restrict__ nmeth,
               const int32_t* __restrict__ cov, const int64_t* __restrict__ bm0, const int32_t* __restrict__ minpos,
@@ -740,7 +743,7 @@ k_damp(const ParTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
 // K10/K11/K13: mu, -log pdf and max |delta mu| per row tile
 // ------------------------------------------------------------------------------------------------
 template <int MODEL>                    // MODEL_FAST: compile-time model (no beta-binomial code); -1: the job's own
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, ML_ROW_MINBLOCKS)
 k_eval_rows(const RowTile* __restrict__ tiles, const JobDev* __restrict__ jobs,
             const int32_t* __restrict__ ctl, RowCols rc, const double* __restrict__ design,
             const double* __restrict__ beta, const double* __restrict__ off, double log2pi,

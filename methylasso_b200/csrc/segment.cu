@@ -550,7 +550,10 @@ k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ se
 // (sum, correction about the first mean, squares about the refined mean) are reduced across the lanes in
 // double-double, whose error (~1e-32 relative) is far below the final rounding to double, so the order of the
 // additions does not show.
-constexpr int PART_LANES = 8;     // lanes per part: a part holds ~25-50 positions on WGBS data, four parts share a warp
+#ifndef ML_PART_LANES
+#define ML_PART_LANES 8
+#endif
+constexpr int PART_LANES = ML_PART_LANES;     // lanes per part: a part holds ~25-50 positions on WGBS data, four parts share a warp
 __device__ __forceinline__ DD dd_group_sum(DD v) {
 #pragma unroll
   for (int d = PART_LANES / 2; d > 0; d >>= 1) {
