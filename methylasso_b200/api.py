@@ -942,17 +942,20 @@ def segment_methylation(data, ret, ncores=1, min_num_cpgs=4, pmd_lambda2=1000, p
                         flank_num_cpgs=10, flank_beta_min=0.5, umr_large_width=500, umr_large_density=0.03,
                         split_pmds=True, merge_pmds=True, drop=True, tol_val=0.01):
     """R/call.R:229-244 (segment_methylation) around :31-221 (segment_methylation_singlechr), for the result of
-    signal_detection_fast(..., keep_resident=True): the whole rule engine runs on the GPU on the resident fit, all
+    signal_detection_fast(..., keep_resident=True) - or of difference_detection_fast(..., keep_resident=True), whose
+    reference condition is then segmented (:40-44): the whole rule engine runs on the GPU on the resident fit, all
     chromosomes at once.  Returns dict(lmr_umr_valley, pmd) of column dicts with the reference's column order
     (:241-243; `num.cpgs` is `num_cpgs`, `PMD.status` is `PMD_status`: "PMD" / "other" / None); `ov`, the per-position
     join, is not returned.  `data` is only consulted through the resident batch; `ncores` is ignored."""
-    if ret.get("detection.type") != "signal":
-        raise MethyLassoError(19, "segment_methylation on the GPU needs a signal fit (a difference fit is segmented on its "
-                                  "reference condition by the reference, R/call.R:40-44: not available natively)")
+    if ret.get("detection.type") not in ("signal", "difference"):
+        raise MethyLassoError(19, "segment_methylation needs the result of signal_detection_fast or difference_detection_fast")
     fit = ret.get("_resident")
     if fit is None or fit.res is None:
-        raise MethyLassoError(19, "segment_methylation needs signal_detection_fast(..., keep_resident=True): the rule "
-                                  "engine works on the fit resident in HBM")
+        raise MethyLassoError(19, "segment_methylation needs signal_detection_fast / difference_detection_fast(..., "
+                                  "keep_resident=True): the rule engine works on the fit resident in HBM")
+    # A difference fit: "will return the segmentation of the reference dataset" (R/call.R:40-44: estimate_id 1 of the
+    # estimates, the rows of ret$ref.cond of the data).  The engine does the same on the resident fit: after the combine
+    # the call table and the rule engine see the first estimator only, whose pooled counts the combine leaves untouched.
     res = fit.res
     lmr = dict(min_width=float(min_width), flank_width=float(flank_width), flank_dist_max=float(flank_dist_max),
                lmr_max_beta=float(lmr_max_beta), flank_beta_min=float(flank_beta_min), umr_max_beta=float(umr_max_beta),

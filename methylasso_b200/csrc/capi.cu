@@ -838,35 +838,47 @@ void call_download(const CallTable& c, const CallHostOut& h) {
   if (h.num_cpgs) c.num_cpgs.download(h.num_cpgs, n);
   if (h.std_) c.t.stdev.download(h.std_, n);
 }
+// The (job, estimator) groups the call table and the rule engine work on.  Of a DIFFERENCE fit (ml_result_fast_diff_combine
+// applied) only the reference condition is segmented: R/call.R:40-44 keeps estimate_id 1 of the estimates and the rows of
+// ret$ref.cond of the data - the first estimator, whose pooled counts the combine leaves untouched (R/fast_diff.R:16, :24).
 std::vector<SegGroup> result_groups(const Result& R) {
   std::vector<SegGroup> groups;
   for (size_t jn = 0; jn < R.jobs.size(); ++jn) {
     const JobHost& j = R.jobs[jn];
     if (j.status) continue;
-    for (int e = 0; e < j.E; ++e)
+    for (int e = 0; e < (R.diff_combined ? std::min(1, j.E) : j.E); ++e)
       groups.push_back(SegGroup{j.par0 + (int64_t)e * j.P, j.P, R.start0[jn], e + 1, (int32_t)jn});
   }
   return groups;
 }
 int ensure_call_table(ml_engine* eng, ml_result* r, double tol_val, double max_distance) {
   Result& R = *r->r;
-  if (R.diff_combined)
-    return fail(ML_ERR_BAD_ARGUMENT, "the call table of a difference fit is not available natively: after the combine the "
-                                     "estimates hold differences, not pooled counts (the reference segments the reference "
-                                     "condition of such a fit, R/call.R:40-44)");
   if (!R.counts_exact)
     return fail(ML_ERR_BAD_ARGUMENT, "the resident call table needs a FAST result with max_iter = 1 (pooled counts are "
                                      "recovered from betahat * pseudoweight); use ml_segment_call_table otherwise");
-  if (!R.seg_cache || R.seg_tol != tol_val) {
-    int64_t ns = 0;
-    const int rc = ml_result_segments(eng, r, tol_val, &ns, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                      nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    R.call_cache.reset();
+  const SegDeviceOut* segs = nullptr;
+  if (R.diff_combined) {
+    if (!R.seg_ref_cache || R.seg_ref_tol != tol_val) {
+      auto ds_new = std::make_unique<SegDeviceOut>();
+      ds_new->n = segment_device(eng->e, result_groups(R), R.npar, R.start.p, 1, R.beta.p, R.betahat.p, R.pw.p, tol_val, *ds_new);
+      R.seg_ref_cache = std::move(ds_new);
+      R.seg_ref_tol = tol_val;
+      R.call_cache.reset();
+    }
+    segs = R.seg_ref_cache.get();
+  } else {
+    if (!R.seg_cache || R.seg_tol != tol_val) {
+      int64_t ns = 0;
+      const int rc = ml_result_segments(eng, r, tol_val, &ns, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                        nullptr, nullptr, nullptr);
+      if (rc) return rc;
+      R.call_cache.reset();
+    }
+    segs = R.seg_cache.get();
   }
   if (!R.call_cache || R.call_tol != tol_val || R.call_max_distance != max_distance) {
     auto c = std::make_unique<CallTable>();
-    call_table_from_estimates(eng->e, result_groups(R), *R.seg_cache, R.start.p, 1, R.betahat.p, R.pw.p, max_distance, *c);
+    call_table_from_estimates(eng->e, result_groups(R), *segs, R.start.p, 1, R.betahat.p, R.pw.p, max_distance, *c);
     R.call_cache = std::move(c);
     R.call_tol = tol_val;
     R.call_max_distance = max_distance;

@@ -1779,6 +1779,7 @@ void result_fast_diff_combine(Engine& eng, Result& r) {
   stream_sync(st);
   r.diff_combined = true;
   r.seg_cache.reset();        // tables computed from the estimates before the combine are stale
+  r.seg_ref_cache.reset();
   r.pmd_cache.reset();
   r.call_cache.reset();
   r.call_pmd_cache.reset();

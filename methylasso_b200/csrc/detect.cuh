@@ -121,6 +121,10 @@ struct Result {
   // segments of the last ml_result_segments call (query-then-fetch without recomputing)
   std::unique_ptr<SegDeviceOut> seg_cache;
   double seg_tol = 0;
+  // a difference fit: the segments of its REFERENCE condition alone (estimate_id 1), which is what segment_methylation
+  // works on when it is given such a fit (R/call.R:40-44)
+  std::unique_ptr<SegDeviceOut> seg_ref_cache;
+  double seg_ref_tol = 0;
   std::unique_ptr<SegDeviceOut> pmd_cache;
   DevBuf<double> pmd_fused;
   double pmd_tol = 0, pmd_lambda2 = 0;

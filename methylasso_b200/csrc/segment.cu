@@ -551,7 +551,7 @@ k_call_parts(const SegGroup* __restrict__ groups, const int32_t* __restrict__ se
 // double-double, whose error (~1e-32 relative) is far below the final rounding to double, so the order of the
 // additions does not show.
 #ifndef ML_PART_LANES
-#define ML_PART_LANES 8
+#define ML_PART_LANES 16
 #endif
 constexpr int PART_LANES = ML_PART_LANES;     // lanes per part: a part holds ~25-50 positions on WGBS data, four parts share a warp
 __device__ __forceinline__ DD dd_group_sum(DD v) {

@@ -42,13 +42,14 @@ def test_split_jobs_partitions_and_balances():
 
 
 def test_segment_methylation_refuses_what_it_cannot_do():
-    """R/call.R:229-244 mirror: needs a signal fit kept resident (no GPU needed to be told so)."""
+    """R/call.R:229-244 mirror: needs a fit kept resident (no GPU needed to be told so)."""
     import pytest
     from methylasso_b200 import api
-    with pytest.raises(api.MethyLassoError, match="signal fit"):
-        api.segment_methylation({}, {"detection.type": "difference"})
-    with pytest.raises(api.MethyLassoError, match="keep_resident"):
-        api.segment_methylation({}, {"detection.type": "signal"})
+    with pytest.raises(api.MethyLassoError, match="signal_detection_fast or difference_detection_fast"):
+        api.segment_methylation({}, {"detection.type": "something else"})
+    for kind in ("signal", "difference"):
+        with pytest.raises(api.MethyLassoError, match="keep_resident"):
+            api.segment_methylation({}, {"detection.type": kind})
 
 
 def test_codec_load_text_inflates_gzip(tmp_path):

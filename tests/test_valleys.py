@@ -606,6 +606,60 @@ def test_gpu_segment_methylation_end_to_end(engine, oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_segment_methylation_on_a_difference_fit(engine, oracle):
+    """R/call.R:40-44: given the result of difference_detection_fast, segment_methylation "will return the segmentation of
+    the reference dataset" - estimate_id 1 of the estimates (which the combine of R/fast_diff.R leaves untouched) and the
+    rows of the reference condition.  Two conditions with two replicates each; condition 2 covers positions condition 1
+    does not (zero pseudoweights in the reference condition's series)."""
+    from methylasso_b200 import api
+    from oracle import rule_engine as RE
+    from test_calltable import pooled_from_table
+    tables = []
+    for i, n in enumerate((40_000, 15_000)):
+        t = synth.chromosome_table(n, 1170 + i, (2, 2))
+        upos = np.unique(t["pos"])
+        gone = upos[np.random.default_rng(i).random(upos.size) < 0.04]          # positions only condition 2 covers
+        keep = ~((t["condition"] == 1) & np.isin(t["pos"], gone))
+        tables.append({k: v[keep] for k, v in t.items()})
+    data = {k: np.concatenate([t[k] for t in tables]) for k in tables[0]}
+    data["chr"] = np.concatenate([np.full(t["pos"].size, f"chr{i + 1}", dtype=object) for i, t in enumerate(tables)])
+    ret = api.difference_detection_fast(data, 1, lambda2=25, engine=engine, keep_resident=True, verbose=False)
+    try:
+        assert ret["detection.type"] == "difference"
+        got = api.segment_methylation(data, ret)
+        dmr = api.call_differences(data, ret)            # the DMR caller still works on the same resident fit
+        assert dmr is not None
+    finally:
+        ret["_resident"].free()
+    n_rows = 0
+    for i, t in enumerate(tables):
+        o = oracle.detect(t, 0, lambda2=25.0)
+        est = o["estimates"]
+        ref = est["estimate_id"] == 1
+        pooled = pooled_from_table(t)
+        pm1 = pooled["estimate_id"] == 1
+        want = RE.segment_methylation_singlechr({k: v[pm1] for k, v in pooled.items()}, {k: v[ref] for k, v in est.items()})
+        g, w = got["lmr_umr_valley"], want["lmr_umr_valley"]
+        m = g["chr"] == f"chr{i + 1}"
+        assert m.sum() == w["start"].size, (i, int(m.sum()), w["start"].size)
+        assert np.all(g["condition"][m] == 1)
+        for k in ("start", "end", "segment_id", "width", "coverage", "num_cpgs"):
+            assert np.array_equal(np.asarray(g[k][m], np.float64), np.asarray(w[k], np.float64)), (i, k)
+        assert np.array_equal(g["category"][m], np.array([None, "LMR", "UMR", "UMR-DMV"], dtype=object)[w["category"]]), i
+        assert np.array_equal(g["PMD_status"][m], np.array([None, "other", "PMD"], dtype=object)[w["pmd_status"] + 1]), i
+        for k in ("beta", "std"):
+            a, b = np.asarray(g[k][m], float), np.asarray(w[k], float)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and close(a[~np.isnan(a)], b[~np.isnan(b)], 1e-12), (i, k)
+        p, wp = got["pmd"], want["pmd"]
+        pm = p["chr"] == f"chr{i + 1}"
+        assert pm.sum() == wp["start"].size
+        for k in ("start", "end", "width", "num_cpgs"):
+            assert np.array_equal(np.asarray(p[k][pm], np.float64), np.asarray(wp[k], np.float64)), (i, k)
+        n_rows += int(m.sum())
+    assert n_rows > 30
+
+
+@pytest.mark.gpu
 def test_gpu_config1_rule_engine(engine, oracle):
     """configs[0] of BASELINE.json end to end: one chr22-sized sample (0.4 M CpGs, one condition), lambda2 = 25, the fit and
     the whole rule engine against the chain of restatements (all rows, drop = F)."""
