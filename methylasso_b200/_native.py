@@ -141,6 +141,7 @@ SIGNATURES = {
 # test hooks of csrc/debug_api.h: exported, but not part of the drop-in surface
 DEBUG_SIGNATURES = {
     "ml_debug_flsa_backpointers": (C.c_int, [_P, C.c_int64, _P, _P, C.c_double, _P, _P, _P]),
+    "ml_debug_flsa_last_stats": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "ml_debug_div_counts": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "ml_debug_scan_runs": (C.c_int, [C.c_int64, _P, _P, _P, _P, C.c_int, C.c_int64, _I64P, _P, _P, _P,
                                      C.POINTER(C.c_int32), _I64P]),

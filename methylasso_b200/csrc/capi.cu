@@ -400,6 +400,11 @@ int ml_debug_flsa_backpointers(ml_engine* eng, int64_t n, const double* y, const
   ML_CATCH
 }
 
+int ml_debug_flsa_last_stats(ml_engine* eng, int* out7) {
+  if (!eng || !out7) return fail(ML_ERR_BAD_ARGUMENT, "NULL argument");
+  for (int i = 0; i < 7; ++i) out7[i] = eng->e.flsa_last[i];
+  return ML_OK;
+}
 int ml_debug_div_counts(ml_engine* eng, int max_num, int max_den, long long* pairs, long long* mismatches) {
   if (!eng || !pairs || !mismatches || max_num < 0 || max_den < 2) return fail(ML_ERR_BAD_ARGUMENT, "bad argument");
   ML_TRY

@@ -138,6 +138,9 @@ struct Engine {
   char* stage_host = nullptr;   // page-locked staging area of batch_stage (grown on demand, freed with the engine)
   size_t stage_cap = 0;
   int want_mu = 1;          // 0: a one-step fit does not store the per-row mu (nothing in the reference's R layer reads it)
+  // counters of the last FLSA solve (tests): chunks verified, redone by walkers, longest chain, chains, series handed over
+  // to the scan route, chunks of the scan route's tables, series finished by the start-to-end kernel
+  int flsa_last[7] = {0, 0, 0, 0, 0, 0, 0};
   // launch accounting for bench.py's gpu_launches
   long long launches = 0;
 };

@@ -14,6 +14,9 @@ ML_API int ml_debug_flsa_backpointers(ml_engine *eng, int64_t n, const double *y
 ML_API int ml_debug_scan_runs(int64_t n, const int32_t *dataset, const int32_t *condition, const int32_t *replicate,
                               const int32_t *pos, int threads, int64_t cap, int64_t *n_runs, int64_t *first_row,
                               int32_t *run_condition, int32_t *run_replicate, int32_t *code, int64_t *code_row);
+/* counters of the engine's last FLSA solve: chunks verified, chunks redone by the walkers, longest chain, chains, series the
+ * walkers handed over to the scan route, chunks in the scan route's tables, series finished by the start-to-end kernel */
+ML_API int ml_debug_flsa_last_stats(ml_engine *eng, int *out7);
 /* counts_div.cuh on the device: every pair 0 <= num <= max_num, 1 <= den < max_den through div_counts (both signatures) and
  * through the device's IEEE division; *mismatches = pairs whose bits differ (must be 0). */
 ML_API int ml_debug_div_counts(ml_engine *eng, int max_num, int max_den, long long *pairs, long long *mismatches);

@@ -80,20 +80,42 @@ def test_walkers_hand_a_series_over_to_the_scan_route(engine, oracle):
     chunks the series is handed over to the scan route ON THE DEVICE (its tables are built next to the speculative ones).
     Count data with the limit at 1 (every chain of two chunks triggers it): still bit-equal to the verbatim DP.  Real-valued
     data (windows from opposite bounds agree numerically long before they agree bit for bit): per element to 1e-10."""
+    import ctypes as C
+
+    def stats():
+        out = (C.c_int * 7)()
+        engine._check(engine.lib.ml_debug_flsa_last_stats(engine.h, out))
+        return dict(zip(("verified", "redone", "longest", "chains", "handed_over", "scan_chunks", "fallback"), out))
     t = synth.chromosome_table(400_000, 20241, (3,))
     y, w = pooled_series(t)
     ref = oracle.weighted_1d_flsa(y, w, 25.0)
     try:
-        for limit in (1, 6, 0):
+        longest = None
+        for limit in (0, 1, 6):
             engine.set("flsa_chain_limit", limit)
             assert np.array_equal(engine.weighted_1d_flsa(y, w, 25.0), ref), limit
+            st = stats()
+            assert st["fallback"] == 0 and st["verified"] > 0, st
+            if limit == 0:                                  # no hand-over, no scan tables: the walkers finish every chain
+                assert st["handed_over"] == 0 and st["scan_chunks"] == 0, st
+                longest = st["longest"]
+            else:                                           # handed over exactly when some chain is longer than the limit
+                assert st["handed_over"] == int(longest > limit), (limit, longest, st)
+        rng = np.random.default_rng(5)
+        n = 300_000
+        yr = np.cumsum(rng.normal(0, 0.01, n)) + rng.normal(0, 0.3, n)
+        wr = rng.exponential(20.0, n)
+        want = oracle.weighted_1d_flsa(yr, wr, 20.0)
+        engine.set("flsa_chain_limit", 0)
+        got0 = engine.weighted_1d_flsa(yr, wr, 20.0)
+        longest = stats()["longest"]
+        engine.set("flsa_chain_limit", 6)
+        got = engine.weighted_1d_flsa(yr, wr, 20.0)
+        assert stats()["handed_over"] == int(longest > 6), (longest, stats())
+        assert longest > 6                                  # real-valued data: windows rarely turn bit-identical in time
     finally:
         engine.set("flsa_chain_limit", 6)
-    rng = np.random.default_rng(5)
-    n = 300_000
-    yr = np.cumsum(rng.normal(0, 0.01, n)) + rng.normal(0, 0.3, n)
-    wr = rng.exponential(20.0, n)
-    got, want = engine.weighted_1d_flsa(yr, wr, 20.0), oracle.weighted_1d_flsa(yr, wr, 20.0)
+    assert np.all(np.abs(got0 - want) <= 1e-10 * max(1.0, float(np.max(np.abs(want)))))
     assert np.all(np.abs(got - want) <= 1e-10 * max(1.0, float(np.max(np.abs(want)))))
 
 
