@@ -186,6 +186,7 @@ int ml_engine_create(int device, ml_engine** out) {
   env_int("ML_FLSA_ROUTE", h->e.flsa_route);
   env_int("ML_FLSA_SCAN_LAMBDA", h->e.flsa_scan_lambda);
   env_int("ML_FLSA_CHAIN_LIMIT", h->e.flsa_chain_limit);
+  env_int("ML_FLSA_FINE", h->e.flsa_fine);
   env_int("ML_FLSA_SCAN_CHUNK_SMALL", h->e.flsa_scan_chunk_small);
   env_int("ML_FLSA_SCAN_CHUNK_BIG", h->e.flsa_scan_chunk_big);
   env_int("ML_HOST_THREADS", h->e.host_threads);
@@ -217,6 +218,7 @@ int ml_engine_set(ml_engine* eng, const char* key, long long value) {
   else if (k == "flsa_route") eng->e.flsa_route = (int)value;
   else if (k == "flsa_scan_lambda") eng->e.flsa_scan_lambda = (int)value;
   else if (k == "flsa_chain_limit") eng->e.flsa_chain_limit = (int)value;
+  else if (k == "flsa_fine") eng->e.flsa_fine = value != 0;
   else if (k == "flsa_scan_chunk_small") eng->e.flsa_scan_chunk_small = (int)std::max<long long>(1, value);
   else if (k == "flsa_scan_chunk_big") eng->e.flsa_scan_chunk_big = (int)std::max<long long>(1, value);
   else if (k == "host_threads") eng->e.host_threads = (int)std::max<long long>(1, value);

@@ -132,6 +132,7 @@ struct Engine {
                                 // of its chunks at the reference's default 25, walks chains of a hundred chunks at 41
                                 // (configs[4] sweep: 37 ms in the walkers) and no warm-up covers the PMD step's 1000
   int flsa_scan_chunk_small = 64, flsa_scan_chunk_big = 448;
+  int flsa_fine = 1;            // 1: chains of the speculative route by composition (fine chains, flsa_core.cuh); 0: walkers only
   int flsa_chain_limit = 6;     // route 0: a walker that has redone this many chunks and still faces an unverified one hands
                                 // its series over to the scan route (0: never)
   int host_threads = 4;     // host threads of batch_upload's passes over the input columns (run scan, packing of the counts)

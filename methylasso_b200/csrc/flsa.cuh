@@ -61,7 +61,8 @@ class FlsaPlan {
   int chunk_len() const { return chunk_; }
   int warm_len() const { return warm_; }
   // counters of the last solve (read back with the overflow flags)
-  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0, scan_chunks = 0, series_rerouted = 0; };
+  struct Stats { int chunks_verified = 0, chunks_redone = 0, longest_chain = 0, chains = 0, series_fallback = 0, scan_chunks = 0, series_rerouted = 0,
+                 fine_chains = 0, walker_chains = 0; };
   Stats last_stats() const { return stats_; }
 
  private:
@@ -84,6 +85,13 @@ class FlsaPlan {
   DevBuf<ScanGroup> d_scan_groups_;
   DevBuf<int32_t> d_scan_series_;   // per series with scan tables: series index, first group, number of groups
   DevBuf<SeriesDesc> d_scan_desc_;   // the series as the scan route sees them (first_chunk / n_chunks of ITS chunk table)
+  // fine chains (flsa_core.cuh): chain / item tables, the maps of the sub-chunks, the chains left to the walkers
+  int fine_cap_items_ = 0, fine_cap_chains_ = 0;
+  DevBuf<FineChain> d_fine_chains_;
+  DevBuf<FineItem> d_fine_items_;
+  DevBuf<int32_t> d_fine_i32_, d_wheads_;
+  DevBuf<double> d_fine_f64_;
+  ScanFns fine_fns_{};
   DevBuf<int32_t> d_route_;         // per series, per solve: 1 = the scan route's kernels process it (set by the plan for
                                     // scan-route series, by a walker that gave up for ROUTE_SPEC_DUAL ones)
   std::vector<int32_t> h_route_init_;
@@ -109,7 +117,7 @@ class FlsaPlan {
   struct Job { const double *y = nullptr, *w = nullptr; double* beta = nullptr; int post = 0; double lambda1 = 0;
                double* sums = nullptr; bool skip = false, pending = false; } job_;   // arguments of the solve in flight
   std::vector<int32_t> h_flags_, h_skip_;
-  int32_t h_counters_[5] = {0, 0, 0, 0, 0};
+  int32_t h_counters_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   void backward();
   void forward_scan(const double* d_y, const double* d_w, const int32_t* skip);
   void fallback_sequential(const std::vector<int>& which, const double* d_y, const double* d_w);

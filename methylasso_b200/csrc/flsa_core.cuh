@@ -903,6 +903,64 @@ ML_HD bool scan_redo(const SeriesDesc& S, const ChunkDesc& cd, int64_t c, const 
   return true;
 }
 
+// ---- the chains of the speculative route by composition ("fine chains") ---------------------------------------------
+// A chain of unverified chunks is walked at one thread's pace: 448 dependent DP steps per chunk, 0.63 ms for a chain of two
+// on the bench genome - a floor that every solve pays, whatever its size.  The same algebra as the scan route's cuts it:
+// every chunk of the chain is split into FINE_SUB sub-chunks, each of them is run from the two bounds on its own steps (two
+// threads per sub-chunk), ONE warp per chain turns the exact end window of the verified chunk in front of the chain into
+// the exact start message of every sub-chunk (scan_starts on the E windows), and every sub-chunk is redone from its start
+// by a thread of its own: 2 x 56 dependent steps and at most FINE_SUB x (chain length) merges.  A chain whose messages
+// outgrow PW_CAP, or whose start window is not of the regular kind, is left to a walker as before.
+constexpr int FINE_SUB = 8;
+struct FineChain {
+  int32_t head;     // first chunk of the chain (index into the speculative route's chunk table)
+  int32_t len;      // chunks
+  int32_t base;     // its first item in the item tables
+  int32_t ok;       // set by the warp that built the start messages
+};
+struct FineItem {
+  int32_t chunk;    // chunk of the speculative route's table
+  int32_t sub;      // 0 .. FINE_SUB - 1
+  int32_t chain;    // index into the chain table
+  int32_t pad;
+};
+// DP steps [kb, ke) of sub-chunk `sub` of a chunk (the last ones may be empty)
+ML_HD void fine_span(const ChunkDesc& cd, int sub, int& kb, int& ke) {
+  const int len = cd.ke - cd.kb;
+  const int sl = (len + FINE_SUB - 1) / FINE_SUB;
+  kb = cd.kb + sub * sl;
+  if (kb > cd.ke) kb = cd.ke;
+  ke = kb + sl < cd.ke ? kb + sl : cd.ke;
+}
+// the E windows of the speculative runs seen as an array of messages (same [slot][chunk] layout)
+ML_HD MsgArray fine_end_windows(const SpecWindows& W) { return MsgArray{W.e_count, W.ex, W.ea, W.eb, W.stride}; }
+// one chain: exact start messages of its n_items sub-chunks into F.A[base ..] (team: a warp, or the emulation's team of one)
+template <class Team>
+ML_HD bool fine_chain_starts(const Team& team, const SpecWindows& W, int64_t head, int n_items, int64_t base, const ScanFns& F,
+                             double lam, PwMsg* m0, PwMsg* m1, PwMsg& A, PwMsg& B) {
+  // the message in front of the chain must be one the merges understand
+  if (!team.load(fine_end_windows(W), head - 1, *m0)) return false;
+  if (!pw_is_regular(*m0) && !pw_is_plus_literal(*m0)) return false;
+  return scan_starts(team, head - 1, base, n_items, false, F, fine_end_windows(W), lam, m0, m1, A, B);
+}
+// one sub-chunk redone from its exact start (F.A[item]); `last`: it ends its series (the last coefficient is due)
+template <class Ring>
+ML_HD bool fine_redo(const SeriesDesc& S, int kb, int ke, int64_t item, bool last, const double* __restrict__ y,
+                     const double* __restrict__ w, double* __restrict__ tm, double* __restrict__ tp, const MsgArray& T,
+                     KnotsC<Ring>& q, double* beta_last) {
+  const int n = T.n[item];
+  if (n < 1 || n > Ring::CAP) return false;
+  for (int k = 0; k < n; ++k) q.ring.set(k, T.x[k * T.stride + item], T.a[k * T.stride + item], T.b[k * T.stride + item]);
+  q.l = 0;
+  q.r = n - 1;
+  knots_cache(q);
+  bool irregular = false;
+  const ChunkDesc span{0, kb, ke, 1};
+  if (!flsa_redo_chunk(S, span, y, w, tm, tp, q, &irregular)) return false;
+  if (last) *beta_last = dp_last(q, y[S.n - 1], w[S.n - 1], S.lam);   // gfl_tf.c:294-302
+  return true;
+}
+
 // ---- start-to-end DP with the knot window in a global-memory ring -----------------------------
 // For series whose window outgrows KNOT_CAP (monotone stretches: up to n + 1 knots).  The ring lives in
 // caller-provided scratch of 3 * cap doubles, cap a power of two >= n + 2, so it can never overflow; the steps are

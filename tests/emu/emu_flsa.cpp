@@ -7,6 +7,9 @@
 
 using namespace ml;
 
+static int g_fine = 0;          // 1: chains of the speculative route by composition (fine chains) where they apply
+extern "C" void emu_set_fine(int on) { g_fine = on; }
+
 extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int chunk, int warm,
                         double* beta, double* tm, double* tp, int tile, long long* stats) {
   // stats: [0] chunks, [1] verified (exact by construction or start window met the neighbour's end window),
@@ -49,9 +52,52 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
   bool ovf = false;
   KnotsC<BigRing> Q;
   bool have = false;     // Q holds the exact window after chunk c - 1
+  double fine_last = 0.0;
+  bool have_fine_last = false;
   long long run = 0;
   for (int64_t c = 0; c < nc && !ovf; ++c) {
     if (verified[c]) { have = false; run = 0; continue; }
+    if (g_fine && !have && c > 0) {
+      // ---- the chain that starts here, by composition: bounds of its sub-chunks, start messages, redo (flsa.cu's
+      // flsa_fine_* kernels, one loop iteration per device thread); on failure the walker below takes it
+      int64_t len = 0;
+      while (c + len < nc && !verified[c + len]) ++len;
+      const int n_items = (int)len * FINE_SUB;
+      std::vector<int32_t> nA(n_items, -7), nB(n_items, -7);
+      std::vector<double> vA(3 * (size_t)PW_CAP * n_items), vB(3 * (size_t)PW_CAP * n_items), sw(n_items), swy(n_items);
+      ScanFns F{MsgArray{nA.data(), vA.data(), vA.data() + (size_t)PW_CAP * n_items, vA.data() + 2 * (size_t)PW_CAP * n_items, n_items},
+                MsgArray{nB.data(), vB.data(), vB.data() + (size_t)PW_CAP * n_items, vB.data() + 2 * (size_t)PW_CAP * n_items, n_items},
+                sw.data(), swy.data()};
+      typedef LocalRing<PW_CAP> RunRing;
+      for (int i = 0; i < n_items; ++i)
+        for (int sign = -1; sign <= 1; sign += 2) {
+          int kb, ke;
+          fine_span(cd[c + i / FINE_SUB], i % FINE_SUB, kb, ke);
+          KnotsC<RunRing> q;
+          double unused = 0;
+          scan_bounds(S, ChunkDesc{0, kb, ke, 1}, i, sign, y, w, tm, tp, &unused, F, q);
+        }
+      PwMsg m0, m1, A, B;
+      bool ok = fine_chain_starts(SerialTeam(), W, c, n_items, 0, F, lam, &m0, &m1, A, B);
+      double bl = 0;
+      bool got_last = false;
+      for (int i = 0; i < n_items && ok; ++i) {
+        int kb, ke;
+        fine_span(cd[c + i / FINE_SUB], i % FINE_SUB, kb, ke);
+        const bool last = (c + i / FINE_SUB == nc - 1) && (i % FINE_SUB == FINE_SUB - 1);
+        KnotsC<RunRing> q;
+        ok = fine_redo(S, kb, ke, i, last, y, w, tm, tp, F.A, q, &bl);
+        if (ok && last) got_last = true;
+      }
+      if (ok) {
+        stats[3] += len;
+        stats[5] = std::max(stats[5], (long long)len);
+        c += len - 1;
+        if (got_last) { fine_last = bl; have_fine_last = true; }
+        have = false;
+        continue;
+      }
+    }
     if (!have) {
       if (c == 0) {        // the head chunk itself overflowed: exact start from element 0
         double t1, t2;
@@ -74,6 +120,8 @@ extern "C" int emu_flsa(int n, const double* y, const double* w, double lam, int
     stats[4] = 1;
     std::vector<double> scratch(3 * (size_t)flsa_sequential_cap(n));
     flsa_sequential_forward(n, y, w, lam, scratch.data(), tm, tp, &blast);
+  } else if (have_fine_last) {
+    blast = fine_last;
   } else {
     if (!have) window_load_end(Q, W, nc - 1);     // the last chunk was verified: its saved end window is exact
     blast = dp_last(Q, y[n - 1], w[n - 1], lam);

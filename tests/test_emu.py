@@ -23,6 +23,7 @@ def emu():
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", LIB, SRC])
     L = C.CDLL(LIB)
+    L.emu_set_fine(0)
     L.emu_clamp35_soft.restype = C.c_double
     L.emu_clamp35_soft.argtypes = [C.c_double, C.c_double]
 
@@ -110,6 +111,48 @@ def test_scan_route_bit_exact_on_count_data(emu, oracle, reps):
     ref, _, _ = oracle.tf_dp_weight(y, w, 17.3, "port")
     beta, st = emu.scan(y, w, 17.3, 64, 16)
     assert st[4] == 0 and np.max(np.abs(beta - ref)) < 1e-11
+
+
+def test_fine_chains_of_the_speculative_route(emu, oracle):
+    """The chains of unverified chunks by composition (eight sub-chunks per chunk, bounds / start messages / redo) instead of
+    a walk: bit-equal on count data with integer penalties whatever the chunking, within rounding on arbitrary inputs; a
+    chain the merges cannot take (irregular start window, a message of more than 32 knots) is left to the walker."""
+    emu.lib.emu_set_fine(1)
+    try:
+        t = synth.chromosome_table(120_000, 31, (3,))
+        y, w = pooled_series(t)
+        for lam in (25.0, 1000.0):
+            ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+            for chunk, warm in ((448, 512), (256, 64), (64, 16)):
+                beta, st = emu(y, w, lam, chunk, warm)
+                assert np.array_equal(beta, ref), (lam, chunk, warm)
+                assert st[4] == 0
+        rng = np.random.default_rng(0)
+        worst = 0.0
+        for trial in range(300):
+            n = int(rng.integers(2, 500))
+            kind = trial % 5
+            if kind == 0:
+                y, w = rng.random(n), rng.integers(0, 3, n).astype(float)
+            elif kind == 1:
+                y, w = np.sort(rng.random(n)), rng.random(n)
+            elif kind == 2:
+                y, w = np.repeat(rng.random(n // 7 + 1), 7)[:n], rng.integers(0, 50, n).astype(float)
+            elif kind == 3:
+                y = rng.integers(0, 2, n).astype(float)
+                w = np.where(rng.random(n) < 0.8, 0.0, rng.integers(1, 30, n)).astype(float)
+            else:
+                y, w = rng.normal(size=n), rng.exponential(size=n)
+            lam = float(rng.choice([1e-3, 0.1, 0.5, 5.0, 25.0, 1000.0]))
+            ref, _, _ = oracle.tf_dp_weight(y, w, lam, "port")
+            beta, st = emu(y, w, lam, int(rng.choice([1, 2, 4, 16, 64])), int(rng.choice([1, 2, 8, 32])), int(rng.choice([1, 3, 8, 64])))
+            ok = np.isfinite(ref)
+            assert np.array_equal(np.isfinite(beta), ok), (trial, kind)
+            if ok.any():
+                worst = max(worst, np.max(np.abs(beta[ok] - ref[ok])) / max(1.0, np.max(np.abs(ref[ok]))))
+        assert worst < 1e-11, worst
+    finally:
+        emu.lib.emu_set_fine(0)
 
 
 def test_scan_route_generic_inputs_within_rounding(emu, oracle):
