@@ -1173,7 +1173,7 @@ def main():
             "verified": verified,
             "roofline": roofline, "roofline_largest_bandwidth_kernel": roofline_bw, "roofline_step": step_roofline,
             "cpu_baseline": cpu,
-            "kernels": table[:20], "ms_per_step_with_kernel_events": ms_profiled,
+            "kernels": table[:40], "ms_per_step_with_kernel_events": ms_profiled,
             "kernel_ms_per_step_total": sum(t["ms_per_step"] for t in table),
             "host_wall_ms_each_step": step_wall_res, "attempts": attempts, "cpu_binding": numa,
             "step": "per rank: ml_batch_detect + ml_gather_push (segments, call table, PMD std fusion, rule engine, region tables, "
