@@ -257,7 +257,7 @@ def run_reference(args, rank, world):
     line = {
         "impl": "reference", "metric": "CpGs/sec through IRLS+weighted 1D FLSA", "value": value, "unit": "CpG/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, tables, ptr, U),
         "cpu_baseline": {"value": value, "unit": "CpG/s", "cores": threads, "kind": "port",
                          "sample": f"whole workload per step; oracle C restatement of methylation_detection, DP = {kind_dp}, "
