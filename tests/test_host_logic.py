@@ -74,3 +74,46 @@ def test_two_fma_quotient_of_counts_is_the_ieee_quotient():
     L = C.CDLL(lib)
     L.emu_counts_div_mismatches.restype = C.c_longlong
     assert L.emu_counts_div_mismatches(65536, 1024) == 0
+
+
+def test_pipeline_turns_are_taken_in_index_order_and_an_abort_frees_the_waiters():
+    """pipeline._Turns: the groups of an end-to-end call take the packing threads and the bus in the order of their index,
+    whatever order their threads arrive in; a failing group does not leave the others waiting for ever."""
+    import random
+    import threading
+    import time
+    import pytest
+    from methylasso_b200.pipeline import _Turns
+    turns, order = _Turns(), []
+
+    def worker(i):
+        time.sleep(random.random() * 0.02)
+        with turns.turn(i):
+            order.append(i)
+    ths = [threading.Thread(target=worker, args=(i,)) for i in random.sample(range(8), 8)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(5)
+    assert order == list(range(8))
+    turns.reset()
+    seen = []
+
+    def waiter():
+        try:
+            with turns.turn(3):
+                seen.append("ran")
+        except RuntimeError:
+            seen.append("released")
+    th = threading.Thread(target=waiter)
+    th.start()
+    time.sleep(0.02)
+    turns.abort()
+    th.join(5)
+    assert seen == ["released"]
+    with pytest.raises(RuntimeError):
+        with turns.turn(0):
+            pass
+    turns.reset()
+    with turns.turn(0):
+        pass
