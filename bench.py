@@ -1075,7 +1075,10 @@ def main():
                     "note": "the FLSA forward kernels run a dependent fp64 compare / add / divide chain per element "
                             "(latency-bound, not HBM-bound): their HBM fraction is reported as measured; the bandwidth-shaped "
                             "kernels of the step are listed in `kernels` with their own fractions"}
-    top_bw = next((t for t in table if t["kernel"] not in latency_bound and t["GBps"]), None)
+    # the bandwidth-shaped kernel that moves the most algorithmic bytes per step (not the slowest one: that may be bound by
+    # instruction issue, like the call table's emit kernel, and is listed in `kernels` with its own fraction)
+    bw = [t for t in table if t["kernel"] not in latency_bound and not t["kernel"].startswith("flsa_") and t["GBps"]]
+    top_bw = max(bw, key=lambda t: t["alg_bytes_per_launch"] * t["launches_per_step"]) if bw else None
     roofline_bw = None
     if top_bw:
         roofline_bw = {"kernel": top_bw["kernel"], "bound": "hbm", "achieved": top_bw["GBps"], "peak": pk["hbm_gbs"],
