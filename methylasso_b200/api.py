@@ -12,6 +12,7 @@ forking one R worker per chromosome (fork + CUDA do not mix)
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -81,6 +82,12 @@ class Engine:
             raise MethyLassoError(rc, self.lib.ml_last_error().decode())
         self.h = h
         self.want_mu = True
+        # what lives on this engine (batches, results, gather windows): released before the engine itself, whatever order
+        # the caller - or the interpreter at exit - lets go of them in
+        self._children = weakref.WeakSet()
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def pinned_buffer(self, name, n, dtype):
         """View of n elements of an engine-owned page-locked buffer called `name` (allocated on first use, grown
@@ -96,6 +103,11 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
+            for child in list(getattr(self, "_children", ())):
+                try:
+                    (getattr(child, "free", None) or child.close)()
+                except Exception:
+                    pass
             self.__dict__.pop("_pinned", None)
             self.lib.ml_engine_destroy(self.h)
             self.h = None
@@ -311,6 +323,7 @@ def _seg_buffers(n, with_job):
 class Batch:
     def __init__(self, eng, h, njobs):
         self.eng, self.h, self.njobs = eng, h, njobs
+        eng._adopt(self)
 
     def free(self):
         if self.h:
@@ -329,6 +342,7 @@ class Result:
 
     def __init__(self, eng, h, status):
         self.eng, self.h, self.status = eng, h, status
+        eng._adopt(self)
         self.njobs = status.size
         self.has_mu = bool(getattr(eng, "want_mu", True))    # one-step fits of an engine with want_mu = 0 store no mu
 

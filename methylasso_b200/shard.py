@@ -132,6 +132,7 @@ class RegionGather:
         self.eng, self.rank, self.world, self.dist, self.device = eng, int(rank), int(world), dist, device
         self.h = C.c_void_p()
         eng._check(eng.lib.ml_gather_create(eng.h, self.rank, self.world, int(slot_bytes), C.byref(self.h)))
+        eng._adopt(self)           # the window is released before the engine, whatever order they are let go of in
         sb = C.c_int64()
         p = C.c_void_p()
         eng._check(eng.lib.ml_gather_window(self.h, 0, C.byref(p), C.byref(sb)))
@@ -167,6 +168,12 @@ class RegionGather:
         if self.h:
             self.eng.lib.ml_gather_destroy(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def layout(self, n_seg, n_pmd):
         import ctypes as C
